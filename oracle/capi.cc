@@ -1,0 +1,257 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY. Never linked into / imported by the product path.
+ *
+ * Flat C surface over the oracle classes so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs can drive it through ctypes.  See the class headers for reference file:line.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "cache_aware.h"
+
+using namespace orc;
+
+namespace {
+struct IndexerBox {
+    PositionalIndexer ix;
+    std::map<uint32_t, WorkerBlockMap> wbs;  // "caller-owned" reverse maps (event_tree.rs:246), one per worker
+    explicit IndexerBox(size_t j) : ix(j) {}
+};
+struct PolicyBox {
+    CacheAwarePolicy pol;
+    std::vector<Worker> workers;
+    explicit PolicyBox(const CacheAwareConfig& c) : pol(c) {}
+};
+size_t copy_str(const std::string& s, char* out, size_t cap) {
+    if (out && cap) { size_t n = std::min(cap - 1, s.size()); memcpy(out, s.data(), n); out[n] = 0; }
+    return s.size();
+}
+std::string join(const std::vector<std::string>& v) {
+    std::string s;
+    for (size_t i = 0; i < v.size(); ++i) { if (i) s.push_back('\n'); s += v[i]; }
+    return s;
+}
+}  // namespace
+
+extern "C" {
+
+void orc_reset_globals() { tree_globals() = TreeGlobals(); }
+uint64_t orc_token_ts() { return tree_globals().token_ts; }
+uint64_t orc_string_epoch() { return tree_globals().string_epoch; }
+
+// ---- hashing ----
+uint64_t orc_xxh3_64(const void* d, size_t n, uint64_t seed) { return xxh3_64(d, n, seed); }
+uint64_t orc_content_hash(const uint32_t* t, size_t n) { return compute_content_hash(t, n); }
+uint64_t orc_next_seq_hash(uint64_t prev, uint64_t cur) { return compute_next_seq_hash(prev, cur); }
+size_t orc_request_content_hashes(const uint32_t* t, size_t n, size_t bs, uint64_t* out, size_t cap) {
+    auto v = compute_request_content_hashes(t, n, bs);
+    for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return v.size();
+}
+
+// ---- PositionalIndexer ----
+void* orc_indexer_new(size_t jump) { return new IndexerBox(jump); }
+void orc_indexer_free(void* h) { delete (IndexerBox*)h; }
+uint32_t orc_indexer_intern_worker(void* h, const char* url) { return ((IndexerBox*)h)->ix.intern_worker(url); }
+int64_t orc_indexer_worker_id(void* h, const char* url) {
+    auto r = ((IndexerBox*)h)->ix.worker_id(url);
+    return r ? (int64_t)*r : -1;
+}
+int orc_indexer_apply_stored(void* h, uint32_t wid, const uint64_t* seq, const uint64_t* content, size_t n, int has_parent,
+                             uint64_t parent) {
+    auto* b = (IndexerBox*)h;
+    return b->ix.apply_stored(wid, seq, content, n, has_parent != 0, parent, b->wbs[wid]);
+}
+void orc_indexer_apply_removed(void* h, uint32_t wid, const uint64_t* seq, size_t n) {
+    auto* b = (IndexerBox*)h;
+    b->ix.apply_removed(wid, seq, n, b->wbs[wid]);
+}
+void orc_indexer_apply_cleared(void* h, uint32_t wid) {
+    auto* b = (IndexerBox*)h;
+    b->ix.apply_cleared(wid, b->wbs[wid]);
+}
+void orc_indexer_remove_worker(void* h, uint32_t wid) {
+    auto* b = (IndexerBox*)h;
+    b->ix.remove_worker(wid, b->wbs[wid]);
+    b->wbs.erase(wid);
+}
+size_t orc_indexer_current_size(void* h) { return ((IndexerBox*)h)->ix.current_size(); }
+size_t orc_indexer_entry_count(void* h) { return ((IndexerBox*)h)->ix.entry_count(); }
+size_t orc_indexer_tree_size(void* h, uint32_t wid) { return ((IndexerBox*)h)->ix.tree_size(wid); }
+size_t orc_indexer_worker_blocks(void* h, uint32_t wid) { return ((IndexerBox*)h)->wbs[wid].size(); }
+size_t orc_indexer_find_matches(void* h, const uint64_t* hashes, size_t n, int early_exit, uint32_t* ids, uint32_t* scores,
+                                uint64_t* tree_sizes, size_t cap) {
+    std::vector<uint64_t> v(hashes, hashes + n);
+    OverlapScores ov = ((IndexerBox*)h)->ix.find_matches(v, early_exit != 0);
+    size_t i = 0;
+    for (auto& kv : ov.scores) {
+        if (i < cap) { ids[i] = kv.first; scores[i] = kv.second; tree_sizes[i] = ov.tree_sizes[kv.first]; }
+        ++i;
+    }
+    return i;
+}
+
+// ---- TokenTree ----
+void* orc_ttree_new(int policy) { return new TokenTree((EvictionPolicy)policy); }
+void orc_ttree_free(void* h) { delete (TokenTree*)h; }
+void orc_ttree_insert(void* h, const uint32_t* t, size_t n, const char* tenant) { ((TokenTree*)h)->insert_tokens(t, n, tenant); }
+// out_counts: [matched, input, nodes_visited, edge_tokens_compared]; valid set '\n'-joined into valid_out
+size_t orc_ttree_match(void* h, const uint32_t* t, size_t n, char* tenant_out, size_t cap, uint64_t* out_counts,
+                       char* valid_out, size_t valid_cap) {
+    TokenMatch m = ((TokenTree*)h)->match_prefix_with_counts(t, n);
+    out_counts[0] = m.matched; out_counts[1] = m.input; out_counts[2] = m.nodes_visited; out_counts[3] = m.edge_tokens_compared;
+    copy_str(join(m.valid), valid_out, valid_cap);
+    return copy_str(m.tenant, tenant_out, cap);
+}
+void orc_ttree_evict_tenant(void* h, const char* tenant, size_t max_tokens) { ((TokenTree*)h)->evict_tenant(tenant, max_tokens); }
+void orc_ttree_evict_by_size(void* h, size_t max_size) { ((TokenTree*)h)->evict_tenant_by_size(max_size); }
+size_t orc_ttree_tenant_size(void* h, const char* tenant) { return ((TokenTree*)h)->tenant_token_size(tenant); }
+size_t orc_ttree_node_count(void* h) { return ((TokenTree*)h)->node_count(); }
+void orc_ttree_clear(void* h) { ((TokenTree*)h)->clear(); }
+void orc_ttree_set_priority(void* h, const uint32_t* t, size_t n, int32_t p) { ((TokenTree*)h)->set_priority_on_path(t, n, p); }
+// serialises iter_entries as text: one line per entry "tok,tok,...|tenant=ts;tenant=ts"
+size_t orc_ttree_entries(void* h, char* out, size_t cap) {
+    std::vector<std::pair<std::vector<uint32_t>, std::vector<std::pair<std::string, uint64_t>>>> es;
+    ((TokenTree*)h)->entries(es);
+    std::string s;
+    for (auto& e : es) {
+        for (size_t i = 0; i < e.first.size(); ++i) { if (i) s.push_back(','); s += std::to_string(e.first[i]); }
+        s.push_back('|');
+        for (size_t i = 0; i < e.second.size(); ++i) { if (i) s.push_back(';'); s += e.second[i].first + "=" + std::to_string(e.second[i].second); }
+        s.push_back('\n');
+    }
+    return copy_str(s, out, cap);
+}
+
+// ---- StringTree ----
+void* orc_stree_new() { return new StringTree(); }
+void orc_stree_free(void* h) { delete (StringTree*)h; }
+void orc_stree_insert(void* h, const char* text, size_t n, const char* tenant) { ((StringTree*)h)->insert_text(std::string(text, n), tenant); }
+size_t orc_stree_match(void* h, const char* text, size_t n, char* tenant_out, size_t cap, uint64_t* out_counts, char* valid_out,
+                       size_t valid_cap) {
+    StringMatch m = ((StringTree*)h)->match_prefix_with_counts(std::string(text, n));
+    out_counts[0] = m.matched; out_counts[1] = m.input; out_counts[2] = m.nodes_visited;
+    copy_str(join(m.valid), valid_out, valid_cap);
+    return copy_str(m.tenant, tenant_out, cap);
+}
+size_t orc_stree_prefix_match_tenant(void* h, const char* text, size_t n, const char* tenant, char* out, size_t cap) {
+    return copy_str(((StringTree*)h)->prefix_match_tenant(std::string(text, n), tenant), out, cap);
+}
+int orc_stree_force_cached_tenant(void* h, const char* text, size_t n, const char* tenant) {
+    return ((StringTree*)h)->force_cached_tenant(std::string(text, n), tenant) ? 1 : 0;
+}
+void orc_stree_evict_by_size(void* h, size_t max_size) { ((StringTree*)h)->evict_tenant_by_size(max_size); }
+void orc_stree_evict_by_tenant(void* h, const char* tenant, size_t max_chars) { ((StringTree*)h)->evict_by_tenant(tenant, max_chars); }
+void orc_stree_remove_tenant_all(void* h, const char* tenant) { ((StringTree*)h)->remove_tenant_all(tenant); }
+size_t orc_stree_tenant_size(void* h, const char* tenant) { return ((StringTree*)h)->tenant_char_size(tenant); }
+size_t orc_stree_node_count(void* h) { return ((StringTree*)h)->node_count(); }
+size_t orc_stree_used_sizes(void* h, char* out, size_t cap) {
+    std::string s;
+    for (auto& kv : ((StringTree*)h)->used_size_per_tenant()) s += kv.first + "=" + std::to_string(kv.second) + "\n";
+    return copy_str(s, out, cap);
+}
+size_t orc_stree_char_counts(void* h, char* out, size_t cap) {
+    std::string s;
+    for (auto& kv : ((StringTree*)h)->tenant_char_counts()) s += kv.first + "=" + std::to_string(kv.second) + "\n";
+    return copy_str(s, out, cap);
+}
+size_t orc_stree_entries(void* h, char* out, size_t cap) {
+    std::vector<std::pair<std::string, std::vector<std::pair<std::string, uint64_t>>>> es;
+    ((StringTree*)h)->entries(es);
+    std::string s;
+    for (auto& e : es) {
+        s += e.first; s.push_back('\x1f');
+        for (size_t i = 0; i < e.second.size(); ++i) { if (i) s.push_back(';'); s += e.second[i].first + "=" + std::to_string(e.second[i].second); }
+        s.push_back('\x1e');
+    }
+    return copy_str(s, out, cap);
+}
+
+// ---- CacheAwarePolicy ----
+void* orc_policy_new(float cache_threshold, uint64_t abs_thr, float rel_thr, uint64_t evict_secs, uint64_t max_tree, uint64_t block_size) {
+    CacheAwareConfig c;
+    c.cache_threshold = cache_threshold; c.balance_abs_threshold = abs_thr; c.balance_rel_threshold = rel_thr;
+    c.eviction_interval_secs = evict_secs; c.max_tree_size = max_tree; c.block_size = block_size;
+    return new PolicyBox(c);
+}
+void orc_policy_free(void* h) { delete (PolicyBox*)h; }
+// Defines the worker slice later passed to select (urls[i], models[i]); calls init_workers when `init` != 0.
+void orc_policy_set_workers(void* h, const char* const* urls, const char* const* models, size_t n, int init) {
+    auto* b = (PolicyBox*)h;
+    b->workers.clear();
+    for (size_t i = 0; i < n; ++i) { Worker w; w.url = urls[i]; w.model_id = models ? models[i] : ""; b->workers.push_back(w); }
+    if (init) b->pol.init_workers(b->workers);
+}
+void orc_policy_set_state(void* h, const uint64_t* loads, const uint8_t* healthy, const uint8_t* circuit_ok, size_t n) {
+    auto* b = (PolicyBox*)h;
+    for (size_t i = 0; i < n && i < b->workers.size(); ++i) {
+        if (loads) b->workers[i].load = loads[i];
+        if (healthy) b->workers[i].healthy = healthy[i] != 0;
+        if (circuit_ok) b->workers[i].circuit_ok = circuit_ok[i] != 0;
+    }
+}
+uint64_t orc_policy_processed(void* h, size_t i) { return ((PolicyBox*)h)->workers[i].processed; }
+void orc_policy_set_monitor(void* h, int present) { ((PolicyBox*)h)->pol.set_monitor(present != 0); }
+void orc_policy_attach_indexer(void* h, const char* model, void* indexer) {
+    ((PolicyBox*)h)->pol.attach_indexer(model, &((IndexerBox*)indexer)->ix);
+}
+void orc_policy_set_block_size(void* h, const char* model, size_t bs) { ((PolicyBox*)h)->pol.set_block_size(model, bs); }
+int orc_policy_has_event_indexer(void* h, const char* model) { return ((PolicyBox*)h)->pol.has_event_indexer(model) ? 1 : 0; }
+void orc_policy_evict_cache(void* h, size_t max_size) { ((PolicyBox*)h)->pol.evict_cache(max_size); }
+void* orc_policy_token_tree(void* h, const char* model) { return ((PolicyBox*)h)->pol.token_tree(model); }
+void* orc_policy_string_tree(void* h, const char* model) { return ((PolicyBox*)h)->pol.string_tree(model); }
+
+// out: [idx, branch, matched, input, score, n_valid]; valid idx list into valid_out (cap entries)
+void orc_policy_select(void* h, const char* text, size_t text_len, int has_text, const uint32_t* tokens, size_t n_tokens,
+                       int has_tokens, int64_t* out, int64_t* valid_out, size_t valid_cap) {
+    auto* b = (PolicyBox*)h;
+    std::string t;
+    if (has_text) t.assign(text, text_len);
+    Decision d = b->pol.select_worker(b->workers, has_text ? &t : nullptr, tokens, n_tokens, has_tokens != 0);
+    out[0] = d.idx; out[1] = d.branch; out[2] = (int64_t)d.matched; out[3] = (int64_t)d.input; out[4] = d.score;
+    out[5] = (int64_t)d.valid.size();
+    for (size_t i = 0; i < d.valid.size() && i < valid_cap; ++i) valid_out[i] = d.valid[i];
+}
+
+// Batch of token requests against ONE fleet snapshot (the product's batch contract): ragged tokens, offsets[n+1].
+// Event-driven / imbalanced / tree branches all go through select_worker in request order.
+// out_idx[i], out_branch[i], out_matched[i] per request.  Returns elapsed seconds (for the cpu_baseline leg).
+double orc_policy_select_batch_tokens(void* h, const uint32_t* tokens, const uint64_t* offsets, size_t n, int32_t* out_idx,
+                                      uint8_t* out_branch, uint32_t* out_matched) {
+    auto* b = (PolicyBox*)h;
+    auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < n; ++i) {
+        Decision d = b->pol.select_worker(b->workers, nullptr, tokens + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), true);
+        out_idx[i] = (int32_t)d.idx;
+        if (out_branch) out_branch[i] = (uint8_t)d.branch;
+        if (out_matched) out_matched[i] = (uint32_t)d.matched;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// Read-only event-mode scoring of a batch with `threads` host threads (the reference's concurrent-read design:
+// select_worker takes &self and the index is only read).  Each thread gets a private copy of the fleet vector
+// (the processed counter is the only thing select_worker writes in event mode).  Returns elapsed seconds.
+double orc_policy_select_batch_tokens_mt(void* h, const uint32_t* tokens, const uint64_t* offsets, size_t n, int32_t* out_idx,
+                                         int threads) {
+    auto* b = (PolicyBox*)h;
+    if (threads < 1) threads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; ++t) {
+        ts.emplace_back([=]() {
+            std::vector<Worker> ws = b->workers;
+            size_t lo = n * (size_t)t / (size_t)threads, hi = n * (size_t)(t + 1) / (size_t)threads;
+            for (size_t i = lo; i < hi; ++i) {
+                Decision d = b->pol.select_worker(ws, nullptr, tokens + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), true);
+                out_idx[i] = (int32_t)d.idx;
+            }
+        });
+    }
+    for (auto& th : ts) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+"""ctypes binding of the CPU oracle (oracle/liborc.so).  TEST INFRASTRUCTURE ONLY.
+
+Mirrors the reference's Rust API names so the ported unit tests read like the originals
+(crates/kv_index/src/{event_tree,token_tree,string_tree}.rs, model_gateway/src/policies/cache_aware.rs).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(os.path.join(ROOT, "oracle", "liborc.so"))
+        vp, sz, u64, u32, i64, cp = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int64, C.c_char_p
+        P = C.POINTER
+
+        def sig(name, res, *args):
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = list(args)
+
+        sig("orc_reset_globals", None)
+        sig("orc_token_ts", u64)
+        sig("orc_string_epoch", u64)
+        sig("orc_xxh3_64", u64, vp, sz, u64)
+        sig("orc_content_hash", u64, vp, sz)
+        sig("orc_next_seq_hash", u64, u64, u64)
+        sig("orc_request_content_hashes", sz, vp, sz, sz, vp, sz)
+        sig("orc_indexer_new", vp, sz)
+        sig("orc_indexer_free", None, vp)
+        sig("orc_indexer_intern_worker", u32, vp, cp)
+        sig("orc_indexer_worker_id", i64, vp, cp)
+        sig("orc_indexer_apply_stored", C.c_int, vp, u32, vp, vp, sz, C.c_int, u64)
+        sig("orc_indexer_apply_removed", None, vp, u32, vp, sz)
+        sig("orc_indexer_apply_cleared", None, vp, u32)
+        sig("orc_indexer_remove_worker", None, vp, u32)
+        sig("orc_indexer_current_size", sz, vp)
+        sig("orc_indexer_entry_count", sz, vp)
+        sig("orc_indexer_tree_size", sz, vp, u32)
+        sig("orc_indexer_find_matches", sz, vp, vp, sz, C.c_int, vp, vp, vp, sz)
+        sig("orc_ttree_new", vp, C.c_int)
+        sig("orc_ttree_free", None, vp)
+        sig("orc_ttree_insert", None, vp, vp, sz, cp)
+        sig("orc_ttree_match", sz, vp, vp, sz, vp, sz, vp, vp, sz)
+        sig("orc_ttree_evict_tenant", None, vp, cp, sz)
+        sig("orc_ttree_evict_by_size", None, vp, sz)
+        sig("orc_ttree_tenant_size", sz, vp, cp)
+        sig("orc_ttree_node_count", sz, vp)
+        sig("orc_ttree_clear", None, vp)
+        sig("orc_ttree_set_priority", None, vp, vp, sz, C.c_int32)
+        sig("orc_ttree_entries", sz, vp, vp, sz)
+        sig("orc_stree_new", vp)
+        sig("orc_stree_free", None, vp)
+        sig("orc_stree_insert", None, vp, cp, sz, cp)
+        sig("orc_stree_match", sz, vp, cp, sz, vp, sz, vp, vp, sz)
+        sig("orc_stree_prefix_match_tenant", sz, vp, cp, sz, cp, vp, sz)
+        sig("orc_stree_force_cached_tenant", C.c_int, vp, cp, sz, cp)
+        sig("orc_stree_evict_by_size", None, vp, sz)
+        sig("orc_stree_evict_by_tenant", None, vp, cp, sz)
+        sig("orc_stree_remove_tenant_all", None, vp, cp)
+        sig("orc_stree_tenant_size", sz, vp, cp)
+        sig("orc_stree_node_count", sz, vp)
+        sig("orc_stree_used_sizes", sz, vp, vp, sz)
+        sig("orc_stree_char_counts", sz, vp, vp, sz)
+        sig("orc_stree_entries", sz, vp, vp, sz)
+        sig("orc_policy_new", vp, C.c_float, u64, C.c_float, u64, u64, u64)
+        sig("orc_policy_free", None, vp)
+        sig("orc_policy_set_workers", None, vp, P(cp), P(cp), sz, C.c_int)
+        sig("orc_policy_set_state", None, vp, vp, vp, vp, sz)
+        sig("orc_policy_processed", u64, vp, sz)
+        sig("orc_policy_set_monitor", None, vp, C.c_int)
+        sig("orc_policy_attach_indexer", None, vp, cp, vp)
+        sig("orc_policy_set_block_size", None, vp, cp, sz)
+        sig("orc_policy_has_event_indexer", C.c_int, vp, cp)
+        sig("orc_policy_evict_cache", None, vp, sz)
+        sig("orc_policy_token_tree", vp, vp, cp)
+        sig("orc_policy_string_tree", vp, vp, cp)
+        sig("orc_policy_select", None, vp, cp, sz, C.c_int, vp, sz, C.c_int, vp, vp, sz)
+        sig("orc_policy_select_batch_tokens", C.c_double, vp, vp, vp, sz, vp, vp, vp)
+        sig("orc_policy_select_batch_tokens_mt", C.c_double, vp, vp, vp, sz, vp, C.c_int)
+        _lib = L
+    return _lib
+
+
+def _u32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint32))
+
+
+def _u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a.size else None
+
+
+def reset_globals():
+    lib().orc_reset_globals()
+
+
+def xxh3_64(data: bytes, seed: int = 0) -> int:
+    buf = C.create_string_buffer(data, len(data))
+    return lib().orc_xxh3_64(C.cast(buf, C.c_void_p), len(data), seed)
+
+
+def compute_content_hash(tokens) -> int:
+    t = _u32(tokens)
+    return lib().orc_content_hash(_ptr(t), t.size)
+
+
+def compute_next_seq_hash(prev: int, cur: int) -> int:
+    return lib().orc_next_seq_hash(prev, cur)
+
+
+def compute_request_content_hashes(tokens, block_size):
+    t = _u32(tokens)
+    cap = (t.size // block_size) if block_size else 0
+    out = np.zeros(max(cap, 1), dtype=np.uint64)
+    n = lib().orc_request_content_hashes(_ptr(t), t.size, block_size, _ptr(out), cap)
+    return [int(x) for x in out[:n]]
+
+
+WORKER_NOT_TRACKED = "WorkerNotTracked"
+PARENT_BLOCK_NOT_FOUND = "ParentBlockNotFound"
+
+
+class ApplyError(Exception):
+    pass
+
+
+class PositionalIndexer:
+    """kv_index::PositionalIndexer.  Blocks are (seq_hash, content_hash) pairs; the per-worker
+    WorkerBlockMap the reference makes caller-owned lives inside the handle, keyed by worker id."""
+
+    def __init__(self, jump_size=32):
+        if jump_size <= 0:
+            raise ValueError("jump_size must be greater than 0")
+        self.h = lib().orc_indexer_new(jump_size)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_indexer_free(self.h)
+            self.h = None
+
+    def intern_worker(self, url):
+        return lib().orc_indexer_intern_worker(self.h, url.encode())
+
+    def worker_id(self, url):
+        r = lib().orc_indexer_worker_id(self.h, url.encode())
+        return None if r < 0 else r
+
+    def apply_stored(self, wid, blocks, parent=None):
+        seq = _u64([b[0] for b in blocks])
+        con = _u64([b[1] for b in blocks])
+        rc = lib().orc_indexer_apply_stored(self.h, wid, _ptr(seq), _ptr(con), len(blocks), 0 if parent is None else 1,
+                                            0 if parent is None else parent)
+        if rc == 1:
+            raise ApplyError(WORKER_NOT_TRACKED)
+        if rc == 2:
+            raise ApplyError(PARENT_BLOCK_NOT_FOUND)
+
+    def apply_removed(self, wid, seq_hashes):
+        s = _u64(seq_hashes)
+        lib().orc_indexer_apply_removed(self.h, wid, _ptr(s), s.size)
+
+    def apply_cleared(self, wid):
+        lib().orc_indexer_apply_cleared(self.h, wid)
+
+    def remove_worker(self, wid):
+        lib().orc_indexer_remove_worker(self.h, wid)
+
+    def current_size(self):
+        return lib().orc_indexer_current_size(self.h)
+
+    def entry_count(self):
+        return lib().orc_indexer_entry_count(self.h)
+
+    def find_matches(self, content_hashes, early_exit=False):
+        hs = _u64(content_hashes)
+        cap = 4096
+        ids = np.zeros(cap, np.uint32)
+        sc = np.zeros(cap, np.uint32)
+        ts = np.zeros(cap, np.uint64)
+        n = lib().orc_indexer_find_matches(self.h, _ptr(hs), hs.size, 1 if early_exit else 0, _ptr(ids), _ptr(sc), _ptr(ts), cap)
+        assert n <= cap
+        return ({int(ids[i]): int(sc[i]) for i in range(n)}, {int(ids[i]): int(ts[i]) for i in range(n)})
+
+
+class TokenMatch:
+    def __init__(self, tenant, matched, inp, nodes, edge, valid):
+        self.tenant, self.matched_token_count, self.input_token_count = tenant, matched, inp
+        self.nodes_visited, self.edge_tokens_compared, self.valid = nodes, edge, valid
+
+
+LRU, LFU, FIFO, MRU, FILO, PRIORITY = range(6)
+
+
+class TokenTree:
+    def __init__(self, policy=LRU, handle=None):
+        self.owned = handle is None
+        self.h = lib().orc_ttree_new(policy) if handle is None else handle
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.owned:
+            lib().orc_ttree_free(self.h)
+            self.h = None
+
+    def insert_tokens(self, tokens, tenant):
+        t = _u32(tokens)
+        lib().orc_ttree_insert(self.h, _ptr(t), t.size, tenant.encode())
+
+    def match_prefix_with_counts(self, tokens):
+        t = _u32(tokens)
+        ten = C.create_string_buffer(1024)
+        val = C.create_string_buffer(1 << 16)
+        cnt = np.zeros(4, np.uint64)
+        lib().orc_ttree_match(self.h, _ptr(t), t.size, C.cast(ten, C.c_void_p), 1024, _ptr(cnt), C.cast(val, C.c_void_p), 1 << 16)
+        valid = [v for v in val.value.decode().split("\n") if v]
+        return TokenMatch(ten.value.decode(), int(cnt[0]), int(cnt[1]), int(cnt[2]), int(cnt[3]), valid)
+
+    def prefix_match_legacy(self, tokens):
+        r = self.match_prefix_with_counts(tokens)
+        return list(tokens[: r.matched_token_count]), r.tenant
+
+    def evict_tenant(self, tenant, max_tokens):
+        lib().orc_ttree_evict_tenant(self.h, tenant.encode(), max_tokens)
+
+    def evict_tenant_by_size(self, max_size):
+        lib().orc_ttree_evict_by_size(self.h, max_size)
+
+    def tenant_token_size(self, tenant):
+        return lib().orc_ttree_tenant_size(self.h, tenant.encode())
+
+    def node_count(self):
+        return lib().orc_ttree_node_count(self.h)
+
+    def clear(self):
+        lib().orc_ttree_clear(self.h)
+
+    def set_priority(self, tokens, p):
+        t = _u32(tokens)
+        lib().orc_ttree_set_priority(self.h, _ptr(t), t.size, p)
+
+    def entries(self):
+        n = lib().orc_ttree_entries(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().orc_ttree_entries(self.h, C.cast(buf, C.c_void_p), n + 1)
+        out = []
+        for line in buf.value.decode().split("\n"):
+            if not line:
+                continue
+            toks, tens = line.split("|")
+            out.append(([int(x) for x in toks.split(",")] if toks else [],
+                        [(kv.rsplit("=", 1)[0], int(kv.rsplit("=", 1)[1])) for kv in tens.split(";") if kv]))
+        return out
+
+
+class StringMatch:
+    def __init__(self, tenant, matched, inp, nodes, valid):
+        self.tenant, self.matched_char_count, self.input_char_count, self.nodes_visited, self.valid = tenant, matched, inp, nodes, valid
+
+
+class Tree:
+    """kv_index::Tree (string tree)."""
+
+    def __init__(self, handle=None):
+        self.owned = handle is None
+        self.h = lib().orc_stree_new() if handle is None else handle
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.owned:
+            lib().orc_stree_free(self.h)
+            self.h = None
+
+    def insert_text(self, text, tenant):
+        b = text.encode()
+        lib().orc_stree_insert(self.h, b, len(b), tenant.encode())
+
+    def match_prefix_with_counts(self, text):
+        b = text.encode()
+        ten = C.create_string_buffer(1024)
+        val = C.create_string_buffer(1 << 16)
+        cnt = np.zeros(4, np.uint64)
+        lib().orc_stree_match(self.h, b, len(b), C.cast(ten, C.c_void_p), 1024, _ptr(cnt), C.cast(val, C.c_void_p), 1 << 16)
+        valid = [v for v in val.value.decode().split("\n") if v]
+        return StringMatch(ten.value.decode(), int(cnt[0]), int(cnt[1]), int(cnt[2]), valid)
+
+    def prefix_match_legacy(self, text):
+        r = self.match_prefix_with_counts(text)
+        return text[: r.matched_char_count], r.tenant
+
+    def prefix_match_tenant(self, text, tenant):
+        b = text.encode()
+        n = lib().orc_stree_prefix_match_tenant(self.h, b, len(b), tenant.encode(), None, 0)
+        # the call above already touched the timestamp; size known → fetch via a second read-only-equivalent call
+        buf = C.create_string_buffer(len(b) + 1)
+        lib().orc_stree_prefix_match_tenant(self.h, b, len(b), tenant.encode(), C.cast(buf, C.c_void_p), len(b) + 1)
+        return buf.raw[:n].decode()
+
+    def force_cached_tenant(self, text, tenant):
+        b = text.encode()
+        return bool(lib().orc_stree_force_cached_tenant(self.h, b, len(b), tenant.encode()))
+
+    def evict_tenant_by_size(self, max_size):
+        lib().orc_stree_evict_by_size(self.h, max_size)
+
+    def evict_by_tenant(self, tenant, max_chars):
+        lib().orc_stree_evict_by_tenant(self.h, tenant.encode(), max_chars)
+
+    def remove_tenant_all(self, tenant):
+        lib().orc_stree_remove_tenant_all(self.h, tenant.encode())
+
+    def tenant_char_size(self, tenant):
+        return lib().orc_stree_tenant_size(self.h, tenant.encode())
+
+    def node_count(self):
+        return lib().orc_stree_node_count(self.h)
+
+    def _kv(self, fn):
+        n = fn(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        fn(self.h, C.cast(buf, C.c_void_p), n + 1)
+        out = {}
+        for line in buf.value.decode().split("\n"):
+            if line:
+                k, v = line.rsplit("=", 1)
+                out[k] = int(v)
+        return out
+
+    def get_used_size_per_tenant(self):
+        return self._kv(lib().orc_stree_used_sizes)
+
+    def get_tenant_char_count(self):
+        return self._kv(lib().orc_stree_char_counts)
+
+    def entries(self):
+        n = lib().orc_stree_entries(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().orc_stree_entries(self.h, C.cast(buf, C.c_void_p), n + 1)
+        out = []
+        for rec in buf.raw[:n].decode().split("\x1e"):
+            if not rec:
+                continue
+            path, tens = rec.split("\x1f")
+            out.append((path, [(kv.rsplit("=", 1)[0], int(kv.rsplit("=", 1)[1])) for kv in tens.split(";") if kv]))
+        return out
+
+
+BRANCHES = ["no_healthy", "imbalanced_min_load", "event_overlap", "event_min_load", "tree_match", "tree_min_load",
+            "tree_fallback_first_healthy", "no_tree_random"]
+
+
+class Decision:
+    def __init__(self, out, valid):
+        self.idx = None if out[0] < 0 else int(out[0])
+        self.branch = BRANCHES[int(out[1])]
+        self.matched, self.input, self.score = int(out[2]), int(out[3]), int(out[4])
+        self.valid = valid
+
+
+class CacheAwarePolicy:
+    """policies::CacheAwarePolicy + the Worker scalars it reads.  Worker state is set by index into the slice."""
+
+    def __init__(self, cache_threshold=0.5, balance_abs_threshold=32, balance_rel_threshold=1.1, eviction_interval_secs=0,
+                 max_tree_size=10000, block_size=16):
+        self.h = lib().orc_policy_new(cache_threshold, balance_abs_threshold, balance_rel_threshold, eviction_interval_secs,
+                                      max_tree_size, block_size)
+        self.n = 0
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_policy_free(self.h)
+            self.h = None
+
+    def set_workers(self, urls, models=None, init=True):
+        self.n = len(urls)
+        U = (C.c_char_p * len(urls))(*[u.encode() for u in urls])
+        M = (C.c_char_p * len(urls))(*[(m or "").encode() for m in (models or [""] * len(urls))])
+        lib().orc_policy_set_workers(self.h, U, M, len(urls), 1 if init else 0)
+
+    def set_state(self, loads=None, healthy=None, circuit_ok=None):
+        lo = _u64(loads) if loads is not None else None
+        he = np.ascontiguousarray(np.asarray(healthy, dtype=np.uint8)) if healthy is not None else None
+        ci = np.ascontiguousarray(np.asarray(circuit_ok, dtype=np.uint8)) if circuit_ok is not None else None
+        lib().orc_policy_set_state(self.h, _ptr(lo) if lo is not None else None, _ptr(he) if he is not None else None,
+                                   _ptr(ci) if ci is not None else None, self.n)
+
+    def processed(self, i):
+        return lib().orc_policy_processed(self.h, i)
+
+    def set_kv_event_monitor(self, present=True):
+        lib().orc_policy_set_monitor(self.h, 1 if present else 0)
+
+    def attach_indexer(self, model, indexer):
+        self._keep.append(indexer)
+        lib().orc_policy_attach_indexer(self.h, model.encode(), indexer.h)
+
+    def set_block_size(self, model, bs):
+        lib().orc_policy_set_block_size(self.h, model.encode(), bs)
+
+    def has_event_indexer(self, model):
+        return bool(lib().orc_policy_has_event_indexer(self.h, model.encode()))
+
+    def evict_cache(self, max_size):
+        lib().orc_policy_evict_cache(self.h, max_size)
+
+    def token_tree(self, model="unknown"):
+        h = lib().orc_policy_token_tree(self.h, model.encode())
+        return TokenTree(handle=h) if h else None
+
+    def string_tree(self, model="unknown"):
+        h = lib().orc_policy_string_tree(self.h, model.encode())
+        return Tree(handle=h) if h else None
+
+    def select_worker(self, request_text=None, tokens=None):
+        out = np.zeros(6, np.int64)
+        valid = np.zeros(max(self.n, 1) + 8, np.int64)
+        tb = request_text.encode() if request_text is not None else b""
+        tk = _u32(tokens) if tokens is not None else _u32([])
+        lib().orc_policy_select(self.h, tb, len(tb), 1 if request_text is not None else 0, _ptr(tk), tk.size,
+                                1 if tokens is not None else 0, _ptr(out), _ptr(valid), valid.size)
+        return Decision(out, [int(v) for v in valid[: int(out[5])]])
+
+    def select_batch_tokens(self, tokens, offsets, threads=0):
+        tk = _u32(tokens)
+        off = _u64(offsets)
+        n = off.size - 1
+        idx = np.zeros(n, np.int32)
+        if threads and threads > 1:
+            secs = lib().orc_policy_select_batch_tokens_mt(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), threads)
+            return idx, None, None, secs
+        br = np.zeros(n, np.uint8)
+        ma = np.zeros(n, np.uint32)
+        secs = lib().orc_policy_select_batch_tokens(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), _ptr(br), _ptr(ma))
+        return idx, br, ma, secs
