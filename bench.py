@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py — cache_aware routing decisions/sec on B200 (BASELINE.json metric, configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # smgx (CUDA) arm
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores (oracle port)
+
+A "step" is one batch of B=4096 synthetic 512-token requests routed against a 64-worker fleet and a 1.0M-entry
+GPU-resident positional KV index (event-driven cache_aware mode).
+  value : whole-job decisions/s, request tokens already resident in HBM, CUDA events on the launching stream.
+  e2e   : the same metric through the public C-ABI call with HOST (pinned) buffers — H2D of the tokens and D2H of
+          the picks are inside the timed region (pipelined over the library's stream lanes).
+Under torchrun every rank owns a full replica (fleet ≤ 512 workers ⇒ "replicas only", no data-path collective;
+SURVEY §8e) and routes its own batches: weak scaling, value = all ranks' decisions ÷ max-over-ranks time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cache_aware routing decisions/sec"
+CFG = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=1.5, block_size=16)  # CLI defaults main.rs:156-165
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("event_select_kernel_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_population(n_seq, T, seed):
+    from smg_b200 import synth
+    return synth.gen_sequences(n_seq, T, seed)
+
+
+def algorithmic_bytes_per_decision(kinds, keeps, T, W, B, bs):
+    """SURVEY §8d byte model for K2b + K3: 4·T tokens hashed + Pr·(32 + ceil(W/8)) index bytes + 16·W/B + 4,
+    with Pr the probes the reference algorithm issues for that request (jump 64 ≥ P): full hit 2 (pos 0, pos P-1);
+    novel 1; stored prefix of k blocks 2 + k (linear drain scans positions 1..k)."""
+    entry = 32 + (W + 7) // 8
+    pr = np.where(kinds == 0, 2, np.where(kinds == 1, 2 + keeps // bs, 1)).astype(np.float64)
+    return float(4 * T + pr.mean() * entry + 16.0 * W / B + 4), float(pr.mean())
+
+
+def gen_batch(seqs, B, seed, bs):
+    """config-2 mix; returns tokens [B,T], kinds (0 full hit, 1 partial, 2 novel), keep (tokens kept for partials)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 2000))
+    n_seq, T = seqs.shape
+    P = T // bs
+    kind_r = rng.random(B)
+    pick = rng.integers(0, n_seq, size=B)
+    out = rng.integers(0, 50000, size=(B, T), dtype=np.uint32)
+    kinds = np.where(kind_r < 0.8, 0, np.where(kind_r < 0.9, 1, 2))
+    keeps = rng.integers(1, P, size=B) * bs
+    out[kinds == 0] = seqs[pick[kinds == 0]]
+    for i in np.nonzero(kinds == 1)[0]:
+        out[i, :keeps[i]] = seqs[pick[i], :keeps[i]]
+    return out, kinds, keeps
+
+
+def populate(pol, ix, seqs, W, bs):
+    """31 250 sequences × 32 blocks → 1.0 M (position, content) entries, worker = i mod W."""
+    from smg_b200 import synth
+    urls = synth.worker_urls(W)
+    for u in urls:
+        ix.intern_worker(u)
+    n_seq, T = seqs.shape
+    P = T // bs
+    flat = np.ascontiguousarray(seqs.reshape(-1))
+    hashes = np.zeros(n_seq * P, np.uint64)
+    got = C.c_uint32()
+    # content hashes of the whole population in a few kernel launches (convert_kv_block hashes token_ids, kv_event_monitor.rs:592)
+    chunk = 4096 * T
+    for off in range(0, flat.size, chunk):
+        part = flat[off:off + chunk]
+        nb = part.size // bs
+        pol._h.call("smgx_content_hashes", part.ctypes.data_as(C.c_void_p), part.size, bs,
+                    hashes[off // bs:].ctypes.data_as(C.c_void_p), nb, C.byref(got))
+    seq_ids = np.arange(1, n_seq * P + 1, dtype=np.uint64)
+    for s in range(n_seq):
+        pol._h.call("smgx_indexer_apply_stored", ix.model, s % W, seq_ids[s * P:(s + 1) * P].ctypes.data_as(C.c_void_p),
+                    hashes[s * P:(s + 1) * P].ctypes.data_as(C.c_void_p), P, None)
+    return hashes
+
+
+def populate_oracle(seqs, hashes, W, bs, jump):
+    from oracle import orc
+    from smg_b200 import synth
+    urls = synth.worker_urls(W)
+    op = orc.CacheAwarePolicy(eviction_interval_secs=0, **CFG)
+    op.set_workers(urls)
+    oix = orc.PositionalIndexer(jump)
+    for u in urls:
+        oix.intern_worker(u)
+    n_seq, T = seqs.shape
+    P = T // bs
+    L = orc.lib()
+    seq_ids = np.arange(1, n_seq * P + 1, dtype=np.uint64)
+    for s in range(n_seq):
+        L.orc_indexer_apply_stored(oix.h, s % W, seq_ids[s * P:(s + 1) * P].ctypes.data_as(C.c_void_p),
+                                   hashes[s * P:(s + 1) * P].ctypes.data_as(C.c_void_p), P, 0, 0)
+    op.attach_indexer("unknown", oix)
+    op.set_kv_event_monitor(True)
+    return op, oix
+
+
+def oracle_hashes(seqs, bs):
+    from oracle import orc
+    n_seq, T = seqs.shape
+    out = np.zeros(n_seq * (T // bs), np.uint64)
+    L = orc.lib()
+    for s in range(n_seq):
+        row = np.ascontiguousarray(seqs[s])
+        L.orc_request_content_hashes(row.ctypes.data_as(C.c_void_p), T, bs, out[s * (T // bs):].ctypes.data_as(C.c_void_p), T // bs)
+    return out
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU algorithm (oracle port — the Rust crate cannot be built here, no cargo)
+    on all host threads, same workload/metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    from smg_b200 import synth
+    B, T, W, bs = args.batch, args.tokens, args.workers, 16
+    seqs = build_population(args.sequences, T, 42)
+    hashes = oracle_hashes(seqs, bs)
+    op, _ = populate_oracle(seqs, hashes, W, bs, 64)
+    loads = synth.poisson_loads(W, 8, 42)
+    op.set_state(loads, [1] * W, [1] * W)
+    cores = os.cpu_count() or 1
+    batches = [synth.ragged(gen_batch(seqs, B, 42 + i, bs)[0]) for i in range(4)]
+    for i in range(args.warmup):
+        tk, off = batches[i % len(batches)]
+        op.select_batch_tokens(tk, off.astype(np.uint64), threads=cores)
+    t = 0.0
+    for i in range(args.steps):
+        tk, off = batches[i % len(batches)]
+        t += op.select_batch_tokens(tk, off.astype(np.uint64), threads=cores)[3]
+    val = args.steps * B / t
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "batch": B, "tokens": T, "workers": W, "mode": "event_driven"},
+            "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} batches of {B} requests, read-only event-mode matching sharded over {cores} host threads"},
+            "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"config2: 1xB200 per rank, {args.workers} workers, {args.tokens}-token requests, {args.sequences * (args.tokens // 16)}-entry "
+            f"positional KV index (event-driven cache_aware), batch={args.batch}, mix 80% full-hit / 10% partial / 10% novel")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="smgx", choices=["smgx", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--tokens", type=int, default=512)
+    ap.add_argument("--workers", type=int, default=64)
+    ap.add_argument("--sequences", type=int, default=31250)
+    ap.add_argument("--ring", type=int, default=32, help="distinct device-resident batches cycled through (ring × batch × tokens × 4 B > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, synth
+    from smg_b200 import _lib
+    B, T, W, bs, R = args.batch, args.tokens, args.workers, 16, args.ring
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), device_id=local_rank, max_batch=B, max_tokens_per_request=T)
+    h, L = pol._h, _lib.load()
+    urls = synth.worker_urls(W)
+    ws = [BasicWorker(u) for u in urls]
+    loads = synth.poisson_loads(W, 8, 42)
+    for w, l in zip(ws, loads):
+        w.set_load(int(l))
+    pol.init_workers(ws)
+    mon = pol.kv_event_monitor(bs)
+    ix = mon.create_indexer("unknown", 64)
+    pol.set_kv_event_monitor(mon)
+    seqs = build_population(args.sequences, T, 42)
+    t0 = time.time()
+    hashes = populate(pol, ix, seqs, W, bs)
+    t_pop = time.time() - t0
+    model = pol._push_fleet(ws)
+
+    # ---- device-resident ring of distinct batches (ring × 8 MB > 126 MB L2) ----
+    err = _lib.new_err()
+    offsets = (np.arange(B + 1, dtype=np.uint64) * T).astype(np.uint32)
+    d_off = L.smgx_device_alloc(h.p, offsets.nbytes, C.byref(err))
+    h.call("smgx_memcpy_h2d", d_off, offsets.ctypes.data_as(C.c_void_p), offsets.nbytes)
+    d_tok, d_out, host_batches, kinds_all, keeps_all = [], [], [], [], []
+    for r in range(R):
+        q, kinds, keeps = gen_batch(seqs, B, 42 + 1000 * rank + r, bs)
+        kinds_all.append(kinds); keeps_all.append(keeps)
+        flat = np.ascontiguousarray(q.reshape(-1))
+        if r < 8:
+            host_batches.append(flat)
+        dt = L.smgx_device_alloc(h.p, flat.nbytes, C.byref(err))
+        h.call("smgx_memcpy_h2d", dt, flat.ctypes.data_as(C.c_void_p), flat.nbytes)
+        d_tok.append(dt)
+        d_out.append(L.smgx_device_alloc(h.p, B * 4, C.byref(err)))
+    alg_bytes, mean_pr = algorithmic_bytes_per_decision(np.concatenate(kinds_all), np.concatenate(keeps_all), T, W, B, bs)
+
+    def barrier():
+        h.call("smgx_synchronize")
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_dev(i):
+        h.call("smgx_select_batch_tokens_device", model, 0, d_tok[i % R], d_off, B, T, d_out[i % R], None)
+
+    # ---- kernel-only (inputs resident in HBM) ----
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = pol.kernel_launches()
+    ms = C.c_float()
+    h.call("smgx_timer_start", 0)
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    h.call("smgx_timer_stop_ms", 0, C.byref(ms))
+    barrier()
+    gpu_launches = pol.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = max_over_ranks(ms.value / 1e3)
+    value = world * args.steps * B / t_dev
+
+    # parity spot check of the last timed batch against the oracle happens in tests/; here only sanity: picks in range
+    out = np.zeros(B, np.int32)
+    h.call("smgx_memcpy_d2h", out.ctypes.data_as(C.c_void_p), d_out[(args.warmup + args.steps - 1) % R], B * 4)
+    assert out.min() >= 0 and out.max() < W
+
+    # ---- end to end: public C-ABI call with pinned HOST buffers, H2D + D2H inside the timed region ----
+    depth = L.smgx_pipeline_depth(h.p)
+    nh = len(host_batches)
+    pin_tok, pin_out = [], []
+    for r in range(nh):
+        p = L.smgx_alloc_pinned(host_batches[r].nbytes)
+        C.memmove(p, host_batches[r].ctypes.data, host_batches[r].nbytes)
+        pin_tok.append(p)
+    for r in range(depth):
+        pin_out.append(L.smgx_alloc_pinned(B * 4))
+    pin_off = L.smgx_alloc_pinned(offsets.nbytes)
+    C.memmove(pin_off, offsets.ctypes.data, offsets.nbytes)
+    tickets = [None] * depth
+
+    def e2e_run(n_steps):
+        for i in range(n_steps):
+            slot = i % depth
+            if tickets[slot] is not None:
+                h.call("smgx_wait", tickets[slot])
+            t = C.c_uint64()
+            h.call("smgx_submit_tokens", model, pin_tok[i % nh], pin_off, B, pin_out[slot], None, C.byref(t))
+            tickets[slot] = t.value
+        for s in range(depth):
+            if tickets[s] is not None:
+                h.call("smgx_wait", tickets[s])
+                tickets[s] = None
+
+    e2e_run(max(args.warmup, depth))
+    barrier()
+    t1 = time.perf_counter()
+    e2e_run(args.steps)
+    h.call("smgx_synchronize")
+    t_e2e = max_over_ranks(time.perf_counter() - t1)
+    e2e_value = world * args.steps * B / t_e2e
+    # per-decision latency = completion time of the batch the request rode in (depth-1 submission, no queueing)
+    lat = []
+    for i in range(min(args.steps, 200)):
+        a = time.perf_counter()
+        t = C.c_uint64()
+        h.call("smgx_submit_tokens", model, pin_tok[i % nh], pin_off, B, pin_out[0], None, C.byref(t))
+        h.call("smgx_wait", t.value)
+        lat.append(time.perf_counter() - a)
+    p99_us = float(np.percentile(lat, 99) * 1e6)
+    p50_us = float(np.percentile(lat, 50) * 1e6)
+
+    peak, peak_src = measured_peak()
+    avg_launch_s = ms.value / 1e3 / args.steps
+    achieved = alg_bytes * B / avg_launch_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "batch": B, "tokens": T, "workers": W, "block_size": bs, "jump_size": 64,
+                   "index_entries": int(ix.entry_count()), "mode": "event_driven", "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2_hygiene": f"ring of {R} distinct device-resident batches = {R * B * T * 4 / 2**20:.0f} MiB of tokens > L2; index "
+                                 f"({ix.entry_count() * 32 / 2**20:.0f} MiB live slots) is the L2-resident working set",
+                   "index_build_s": round(t_pop, 2)},
+        "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(B * T * 4 + (B + 1) * 4), "d2h_bytes_per_step": int(B * 4),
+                "pipeline_depth": int(depth), "timing": "host wall clock around K pipelined submit/wait calls, device synchronised on both sides"},
+        "p50_decision_latency_us": p50_us, "p99_decision_latency_us": p99_us,
+        "gpu_launches": int(gpu_launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                     "kernel": "event_select_kernel", "algorithmic_bytes_per_decision": alg_bytes, "mean_reference_probes": mean_pr,
+                     "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(seqs, hashes, args, bs)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(seqs, hashes, args, bs):
+    """The oracle (C++ restatement of the reference algorithm) on ONE host core, sequential reference semantics,
+    bounded sample of the same workload."""
+    from smg_b200 import synth
+    B, T, W = args.batch, args.tokens, args.workers
+    op, _ = populate_oracle(seqs, hashes, W, bs, 64)
+    op.set_state(synth.poisson_loads(W, 8, 42), [1] * W, [1] * W)
+    tk, off = synth.ragged(gen_batch(seqs, B, 42, bs)[0])
+    off = off.astype(np.uint64)
+    op.select_batch_tokens(tk, off)            # warm
+    t, n = 0.0, 0
+    while t < 8.0 and n < 400:
+        t += op.select_batch_tokens(tk, off)[3]
+        n += 1
+    return {"value": n * B / t, "unit": "decisions/s", "cores": 1, "kind": "port",
+            "sample": f"{n} passes over one batch of {B} requests (same index, same mix), single thread, {t:.1f} s of CPU work"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+/*
+ * smgx — B200-native cache-aware worker pick behind a C ABI.
+ *
+ * Drop-in boundary for SMG's `--policy cache_aware` hot path.  The Rust side that a maintainer adds is a
+ * `struct GpuCacheAwarePolicy { h: *mut smgx_policy }` implementing
+ *     trait LoadBalancingPolicy            (model_gateway/src/policies/mod.rs:43-86)
+ * registered at PolicyFactory::create_from_config / create_by_name
+ *                                          (model_gateway/src/policies/factory.rs:22-39, :84)
+ * See INTEGRATION.md for the binding.  Conventions mirror the reference's only existing C ABI
+ * (bindings/golang/src/error.rs:6-15, memory.rs:10-27, tokenizer.rs:113-161):
+ *   - every call returns an smgx_status (0 = success) or a nullable handle;
+ *   - `char** err` is optional; on failure it receives a callee-allocated NUL-terminated message that the
+ *     caller releases with smgx_free_string();
+ *   - opaque handle from *_create, released by *_free; null pointer arguments → SMGX_INVALID_ARGUMENT;
+ *   - hot-path buffers are CALLER-allocated (ideally pinned, see smgx_alloc_pinned); nothing is malloc'ed per call.
+ *
+ * There is NO CPU fallback: every select/find call runs hand-written sm_100a kernels and fails with
+ * SMGX_DEVICE_ERROR when no CUDA device is usable.  No torch types, plain pointers and sizes only.
+ */
+#ifndef SMGX_H
+#define SMGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMGX_ABI_VERSION 1
+
+typedef enum smgx_status {
+    SMGX_SUCCESS = 0,
+    SMGX_INVALID_ARGUMENT = 1,   /* SglErrorCode::InvalidArgument  (bindings/golang/src/error.rs:9)  */
+    SMGX_TOKENIZATION_ERROR = 2, /* SglErrorCode::TokenizationError                                   */
+    SMGX_MEMORY_ERROR = 4,       /* SglErrorCode::MemoryError                                         */
+    SMGX_DEVICE_ERROR = 5,       /* CUDA runtime / no device — there is no CPU fallback               */
+    SMGX_WORKER_NOT_TRACKED = 10,    /* kv_index ApplyError::WorkerNotTracked    (event_tree.rs:90-95) */
+    SMGX_PARENT_BLOCK_NOT_FOUND = 11,/* kv_index ApplyError::ParentBlockNotFound (event_tree.rs:90-95) */
+    SMGX_NOT_FOUND = 12,         /* unknown model key / no indexer for the model                      */
+    SMGX_UNKNOWN_ERROR = 99
+} smgx_status;
+
+/* Which branch of CacheAwarePolicy::select_worker produced a pick (cache_aware.rs:648-690). */
+typedef enum smgx_branch {
+    SMGX_BR_NO_HEALTHY = 0,              /* healthy_indices empty → None               (:653-655) */
+    SMGX_BR_IMBALANCED_MIN_LOAD = 1,     /* select_worker_min_load                     (:356-440) */
+    SMGX_BR_EVENT_OVERLAP = 2,           /* score_overlap hit                          (:776-831) */
+    SMGX_BR_EVENT_MIN_LOAD = 3,          /* event-driven, no overlap → min load        (:759-768) */
+    SMGX_BR_TREE_MATCH = 4,              /* match_rate > cache_threshold → tenant      (:854-859) */
+    SMGX_BR_TREE_MIN_LOAD = 5,           /* match_rate ≤ threshold → min load          (:860-865) */
+    SMGX_BR_TREE_FALLBACK_FIRST_HEALTHY = 6, /* tenant gone/unhealthy → healthy[0]     (:892-894) */
+    SMGX_BR_NO_TREE_RANDOM = 7           /* no tree for model (:896-903); smgx returns healthy[0] */
+} smgx_branch;
+
+/* CacheAwareConfig (model_gateway/src/policies/mod.rs:94-117) + device placement. */
+typedef struct smgx_cache_aware_config {
+    float cache_threshold;            /* default 0.5  */
+    uint64_t balance_abs_threshold;   /* default 32   */
+    float balance_rel_threshold;      /* default 1.1  */
+    uint64_t eviction_interval_secs;  /* default 30; 0 = no background eviction (the caller drives smgx_evict_cache) */
+    uint64_t max_tree_size;           /* default 10000 */
+    uint64_t block_size;              /* default 16   */
+    int32_t device_id;                /* CUDA ordinal; -1 = host-mirror only (index writers work, every select fails) */
+    uint32_t max_batch;               /* largest n accepted by one select call (sizes device staging); 0 → 65536 */
+    uint32_t max_tokens_per_request;  /* sizes per-warp scratch; 0 → 32768 */
+} smgx_cache_aware_config;
+
+/* Per-request detail, optional output of the select calls. */
+typedef struct smgx_decision_info {
+    uint32_t matched;   /* event mode: overlap score in blocks; tree modes: matched tokens / chars */
+    uint32_t input;     /* request length in tokens / chars                                        */
+    uint8_t branch;     /* smgx_branch                                                             */
+    uint8_t reserved[3];
+} smgx_decision_info;
+
+typedef struct smgx_policy smgx_policy;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+void smgx_default_config(smgx_cache_aware_config* cfg);                 /* CacheAwareConfig::default() (mod.rs:106-117) */
+smgx_policy* smgx_policy_create(const smgx_cache_aware_config* cfg, char** err);   /* CacheAwarePolicy::with_config (cache_aware.rs:120) */
+void smgx_policy_free(smgx_policy* p);
+const char* smgx_policy_name(void);                                     /* "cache_aware" (cache_aware.rs:704-706) */
+uint32_t smgx_abi_version(void);
+void smgx_free_string(char* s);                                         /* sgl_free_string (memory.rs:10-15) */
+void* smgx_alloc_pinned(size_t bytes);                                  /* page-locked host memory for hot-path buffers */
+void smgx_free_pinned(void* ptr);
+
+/* ---- fleet: the `&[Arc<dyn Worker>]` slice select_worker receives ----------------------------------------- */
+/* Defines the worker slice for `model_key` (normalize_model_key: "" → "unknown", mod.rs:151-157) in slice order and
+ * performs init_workers (cache_aware.rs:219-249).  Calling it again replaces the slice (trees are kept). */
+smgx_status smgx_set_workers(smgx_policy* p, const char* model_key, const char* const* urls, uint32_t n, char** err);
+/* Worker scalars read by the path (worker/worker.rs:151-153,187,208): load(), is_healthy(), circuit_breaker_can_execute().
+ * `circuit_ok` may be NULL (= all 1).  The snapshot applies to every later select call until replaced. */
+smgx_status smgx_set_fleet_state(smgx_policy* p, const char* model_key, const uint64_t* loads, const uint8_t* healthy,
+                                 const uint8_t* circuit_ok, uint32_t n, char** err);
+/* add_worker_by_url / remove_worker_by_url (cache_aware.rs:269-308; removal is a no-op in the reference too). */
+smgx_status smgx_add_worker(smgx_policy* p, const char* model_key, const char* url, char** err);
+smgx_status smgx_remove_worker(smgx_policy* p, const char* model_key, const char* url, char** err);
+/* increment_processed() counters accumulated per slice index since the last call; out may be NULL to reset. */
+smgx_status smgx_take_processed(smgx_policy* p, const char* model_key, uint64_t* out_counts, uint32_t n, char** err);
+
+/* ---- event-driven index: kv_index::PositionalIndexer (crates/kv_index/src/event_tree.rs) ------------------- */
+/* set_kv_event_monitor(Some/None) (cache_aware.rs:213-215). */
+smgx_status smgx_set_kv_event_monitor(smgx_policy* p, int present, char** err);
+/* KvEventMonitor creates one indexer per model (kv_event_monitor.rs); jump_size default there is 64 (:31). */
+smgx_status smgx_indexer_create(smgx_policy* p, const char* model_key, uint32_t jump_size, char** err);
+smgx_status smgx_indexer_set_block_size(smgx_policy* p, const char* model_key, uint32_t block_size, char** err); /* learned block size */
+smgx_status smgx_indexer_intern_worker(smgx_policy* p, const char* model_key, const char* url, uint32_t* out_id, char** err);      /* :509-525 */
+smgx_status smgx_indexer_worker_id(smgx_policy* p, const char* model_key, const char* url, int64_t* out_id /* -1 = None */, char** err); /* :294 */
+/* apply_stored (:305-366).  StoredBlock = {seq_hash, content_hash}; parent_seq_hash NULL = None.
+ * Returns SMGX_WORKER_NOT_TRACKED / SMGX_PARENT_BLOCK_NOT_FOUND so the caller can replicate the fresh-chain
+ * fallback of kv_event_monitor.rs:559-571.  The per-worker WorkerBlockMap (:246) lives inside the policy. */
+smgx_status smgx_indexer_apply_stored(smgx_policy* p, const char* model_key, uint32_t worker_id, const uint64_t* seq_hashes,
+                                      const uint64_t* content_hashes, uint32_t n_blocks, const uint64_t* parent_seq_hash, char** err);
+/* Same, hashing `token_ids` (n_blocks × block_size u32) like convert_kv_block (kv_event_monitor.rs:592-597). */
+smgx_status smgx_indexer_apply_stored_tokens(smgx_policy* p, const char* model_key, uint32_t worker_id, const uint64_t* seq_hashes,
+                                             const uint32_t* token_ids, uint32_t block_size, uint32_t n_blocks,
+                                             const uint64_t* parent_seq_hash, char** err);
+smgx_status smgx_indexer_apply_removed(smgx_policy* p, const char* model_key, uint32_t worker_id, const uint64_t* seq_hashes, uint32_t n, char** err); /* :380-404 */
+smgx_status smgx_indexer_apply_cleared(smgx_policy* p, const char* model_key, uint32_t worker_id, char** err);  /* :410-420 */
+smgx_status smgx_indexer_remove_worker(smgx_policy* p, const char* model_key, uint32_t worker_id, char** err);  /* :426-435 */
+smgx_status smgx_indexer_current_size(smgx_policy* p, const char* model_key, uint64_t* out, char** err);        /* :438-444 */
+smgx_status smgx_indexer_entry_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err);         /* index.len() */
+/* find_matches (:461) on the GPU: `content_hashes` (host) → per-worker overlap.  out_scores[w] = 0 means "absent from
+ * OverlapScores.scores"; out_tree_sizes[w] is valid where out_scores[w] > 0.  Arrays hold `cap` entries (≥ worker count). */
+smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, const uint64_t* content_hashes, uint32_t n,
+                                      int early_exit, uint32_t* out_scores, uint64_t* out_tree_sizes, uint32_t cap,
+                                      uint32_t* out_n_workers, char** err);
+/* compute_request_content_hashes (:141-151) on the GPU, for callers/tests that want the hashes themselves. */
+smgx_status smgx_content_hashes(smgx_policy* p, const uint32_t* tokens, uint32_t n_tokens, uint32_t block_size,
+                                uint64_t* out_hashes, uint32_t cap, uint32_t* out_n, char** err);
+
+/* ---- the hot call: LoadBalancingPolicy::select_worker, batched (cache_aware.rs:648-690) -------------------- */
+/* n requests, request i = tokens[offsets[i] .. offsets[i+1]) (SelectWorkerInfo.tokens = Some).  All requests see the
+ * fleet snapshot and index state current at submission.  out_worker_idx[i] = index into the slice given to
+ * smgx_set_workers, or -1 for None.  `out_info` may be NULL.  Host buffers; the call copies H2D, runs the kernels and
+ * copies the result back before returning. */
+smgx_status smgx_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets,
+                                     uint32_t n, int32_t* out_worker_idx, smgx_decision_info* out_info, char** err);
+/* Pipelined form for the host batcher: up to smgx_pipeline_depth() submissions may be in flight; each owns a stream
+ * and device staging.  Buffers must stay valid (and should be pinned) until smgx_wait(ticket) returns. */
+uint32_t smgx_pipeline_depth(const smgx_policy* p);
+smgx_status smgx_submit_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                               int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err);
+smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err);
+
+/* Device-resident form (inputs already in HBM; used by bench.py's kernel-only leg and by callers that tokenize on
+ * the GPU).  Pointers are device pointers on the policy's device; asynchronous on the policy's stream `lane`
+ * (0 ≤ lane < smgx_pipeline_depth()).  `max_request_tokens` bounds the longest request of the batch (sizes the per-warp
+ * shared-memory scratch; 0 = config max_tokens_per_request; a longer request is reported by smgx_synchronize).
+ * d_out_info may be NULL. */
+smgx_status smgx_select_batch_tokens_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens,
+                                            const uint32_t* d_offsets, uint32_t n, uint32_t max_request_tokens,
+                                            int32_t* d_out_worker_idx, smgx_decision_info* d_out_info, char** err);
+void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err);
+void smgx_device_free(smgx_policy* p, void* dptr);
+smgx_status smgx_memcpy_h2d(smgx_policy* p, void* dptr, const void* host, size_t bytes, char** err);
+smgx_status smgx_memcpy_d2h(smgx_policy* p, void* host, const void* dptr, size_t bytes, char** err);
+smgx_status smgx_synchronize(smgx_policy* p, char** err);
+/* CUDA-event timing on the launching stream (lane): start/stop bracket whatever is enqueued between them. */
+smgx_status smgx_timer_start(smgx_policy* p, uint32_t lane, char** err);
+smgx_status smgx_timer_stop_ms(smgx_policy* p, uint32_t lane, float* out_ms, char** err);
+/* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
+uint64_t smgx_kernel_launches(const smgx_policy* p);
+/* Writes a buffer larger than L2 (bench hygiene between timed iterations). */
+smgx_status smgx_flush_l2(smgx_policy* p, char** err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMGX_H */

@@ -1,0 +1,64 @@
+// Kernel-facing structures and launch wrappers (implemented in event_kernels.cu).
+#pragma once
+#include <cstdint>
+
+#include "common.h"
+#include "event_index.h"
+
+namespace smgx {
+
+// Per-model fleet snapshot as the kernels see it.  Built on the device by fleet_prepare_kernel from the raw slice
+// arrays the caller hands to smgx_set_fleet_state.  "id space" = PositionalIndexer worker ids; "slice space" =
+// indices into the `&[Arc<dyn Worker>]` slice select_worker returns (cache_aware.rs:648).
+struct FleetDerived {
+    int32_t min_load_idx;    // first argmin load() over healthy (min_by_key → FIRST min); -1 when none healthy
+    int32_t first_healthy;   // healthy_indices.first()
+    uint32_t n_healthy;
+    uint32_t imbalanced;     // (max-min) > abs_thr && (max as f32) > (min as f32 * rel_thr)   (cache_aware.rs:669-670)
+    uint64_t min_load, max_load;
+};
+struct FleetView {
+    const FleetDerived* derived;
+    const int32_t* slice_of_id;   // [id] → slice index or -1
+    const uint64_t* load_of_id;   // [id] → load of that slice entry
+    const uint64_t* elig;         // [words] bitset in id space: healthy && circuit_ok && present in the slice
+};
+
+struct FleetRaw {
+    const uint64_t* loads;        // [n_slice]
+    const uint8_t* flags;         // [n_slice] bit0 = is_healthy(), bit1 = circuit_breaker_can_execute()
+    const int32_t* id_of_slice;   // [n_slice] → indexer worker id or -1
+    uint32_t n_slice;
+    uint32_t n_ids;               // interned workers
+    uint32_t words;               // bitset words (id space)
+    uint64_t abs_threshold;
+    float rel_threshold;
+};
+
+void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t* d_slice_of_id, uint64_t* d_load_of_id,
+                          uint64_t* d_elig, cudaStream_t stream);
+
+// Fused K2b (content hashes → jump search over the positional index) + K3 (score → argmax worker).
+// One warp per request.  `max_blocks` bounds the per-warp shared-memory scratch (content hashes of one request).
+struct SelectArgs {
+    const uint32_t* tokens;     // device, ragged
+    const uint32_t* offsets;    // device, n + 1
+    uint32_t n;
+    uint32_t block_size;
+    uint32_t max_blocks;
+    int32_t* out_idx;           // device, n
+    smgx_decision_info* out_info;  // device, n (nullable)
+    uint32_t* err_flag;         // device: set to 1 when a request exceeds max_blocks
+};
+void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const SelectArgs& a, int sm_count, cudaStream_t stream);
+
+// PositionalIndexer::find_matches on precomputed content hashes; one warp, one query.
+void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uint32_t n, bool early_exit, uint32_t* d_scores,
+                         cudaStream_t stream);
+
+// compute_request_content_hashes for one request.
+void launch_content_hashes(const uint32_t* d_tokens, uint32_t n_tokens, uint32_t block_size, uint64_t* d_out, cudaStream_t stream);
+
+void launch_fill(uint32_t* d, uint32_t value, size_t n_words, cudaStream_t stream);
+
+}  // namespace smgx

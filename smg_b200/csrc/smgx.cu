@@ -1,0 +1,698 @@
+// smgx policy object + C ABI (include/smgx.h).
+//
+// Host-side counterpart of CacheAwarePolicy (model_gateway/src/policies/cache_aware.rs:74-101): per-model state
+// keyed by normalize_model_key (policies/mod.rs:151-157), the fleet snapshot select_worker reads from `dyn Worker`
+// (worker/worker.rs:151-153,187,208), the KV-event indexers a KvEventMonitor would own, and a small ring of
+// stream "lanes" that stage request batches into HBM and run the kernels.  Every decision is produced by the
+// kernels in event_kernels.cu; nothing here computes a pick on the CPU.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "event_index.h"
+#include "kernels.h"
+
+namespace smgx {
+
+static std::string norm_model(const char* m) { return (m == nullptr || m[0] == 0) ? std::string("unknown") : std::string(m); }
+
+struct ModelState {
+    // the `&[Arc<dyn Worker>]` slice, in slice order
+    std::vector<std::string> urls;
+    std::vector<uint64_t> loads;
+    std::vector<uint8_t> flags;      // bit0 is_healthy(), bit1 circuit_breaker_can_execute()
+    std::vector<uint64_t> processed; // increment_processed() per slice index
+    // KvEventMonitor state for this model
+    std::unique_ptr<EventIndex> indexer;
+    bool has_learned_bs = false;
+    uint32_t learned_bs = 0;
+    // device copy of the fleet
+    DevBuf d_loads, d_flags, d_id_of_slice, d_derived, d_slice_of_id, d_load_of_id, d_elig;
+    bool fleet_dirty = true;
+    uint64_t seen_workers_version = ~0ULL;
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
+    DevBuf d_tokens, d_offsets, d_out, d_info;
+    bool busy = false;
+    bool has_done = false;
+    uint64_t ticket = 0;
+    // completion bookkeeping for the host-buffer API
+    ModelState* model = nullptr;
+    const int32_t* host_out = nullptr;
+    uint32_t n = 0;
+};
+
+class Policy {
+public:
+    explicit Policy(const smgx_cache_aware_config& c) : cfg(c) {
+        if (cfg.max_batch == 0) cfg.max_batch = 65536;
+        if (cfg.max_tokens_per_request == 0) cfg.max_tokens_per_request = 32768;
+        if (cfg.device_id >= 0) {
+            int count = 0;
+            cudaError_t e = cudaGetDeviceCount(&count);
+            if (e != cudaSuccess || count == 0)
+                throw Error(SMGX_DEVICE_ERROR, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                                   "); smgx has no CPU fallback — use device_id = -1 only for host-mirror tests");
+            if (cfg.device_id >= count) throw Error(SMGX_INVALID_ARGUMENT, "device_id out of range");
+            SMGX_CUDA(cudaSetDevice(cfg.device_id));
+            cudaDeviceProp prop;
+            SMGX_CUDA(cudaGetDeviceProperties(&prop, cfg.device_id));
+            sm_count = prop.multiProcessorCount;
+            l2_bytes = (size_t)prop.l2CacheSize;
+            SMGX_CUDA(cudaStreamCreateWithFlags(&ctrl, cudaStreamNonBlocking));
+            SMGX_CUDA(cudaEventCreateWithFlags(&state_ready, cudaEventDisableTiming));
+            lanes.resize(4);
+            for (auto& l : lanes) {
+                SMGX_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+                SMGX_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+                SMGX_CUDA(cudaEventCreate(&l.t0));
+                SMGX_CUDA(cudaEventCreate(&l.t1));
+            }
+            d_err.reserve(64);
+            SMGX_CUDA(cudaMemset(d_err.ptr, 0, 64));
+        }
+    }
+    ~Policy() {
+        if (cfg.device_id >= 0) {
+            cudaSetDevice(cfg.device_id);
+            cudaDeviceSynchronize();
+            for (auto& l : lanes) {
+                l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release();
+                if (l.done) cudaEventDestroy(l.done);
+                if (l.t0) cudaEventDestroy(l.t0);
+                if (l.t1) cudaEventDestroy(l.t1);
+                if (l.stream) cudaStreamDestroy(l.stream);
+            }
+            for (auto& kv : models) {
+                ModelState& m = *kv.second;
+                m.d_loads.release(); m.d_flags.release(); m.d_id_of_slice.release(); m.d_derived.release();
+                m.d_slice_of_id.release(); m.d_load_of_id.release(); m.d_elig.release();
+                m.indexer.reset();
+            }
+            d_err.release(); d_flush.release(); scratch.release(); scratch2.release();
+            if (state_ready) cudaEventDestroy(state_ready);
+            if (ctrl) cudaStreamDestroy(ctrl);
+        }
+    }
+
+    void use_device() const {
+        if (cfg.device_id < 0)
+            throw Error(SMGX_DEVICE_ERROR, "policy was created with device_id = -1 (host mirror only): no GPU path, no CPU fallback");
+        SMGX_CUDA(cudaSetDevice(cfg.device_id));
+    }
+
+    ModelState& model(const char* key, bool create) {
+        std::string k = norm_model(key);
+        auto it = models.find(k);
+        if (it != models.end()) return *it->second;
+        if (!create) throw Error(SMGX_NOT_FOUND, "unknown model key '" + k + "'");
+        auto& slot = models[k];
+        slot = std::make_unique<ModelState>();
+        return *slot;
+    }
+    EventIndex& indexer(const char* key) {
+        ModelState& m = model(key, false);
+        if (!m.indexer) throw Error(SMGX_NOT_FOUND, "no event indexer for model '" + norm_model(key) + "'");
+        return *m.indexer;
+    }
+
+    // has_event_indexer (cache_aware.rs:723-729)
+    bool has_event_indexer(const ModelState& m) const { return monitor && m.indexer && m.indexer->current_size() > 0; }
+    uint32_t block_size_for(const ModelState& m) const { return m.has_learned_bs ? m.learned_bs : (uint32_t)cfg.block_size; }
+
+    // Bring the device copies (index + fleet) up to date, in `ctrl` stream order, and make every lane wait for it.
+    void sync_state(ModelState& m, EventIndexView* ixv, FleetView* fv) {
+        uint64_t wv0 = m.indexer ? m.indexer->workers_version() : 0;
+        bool pending = m.fleet_dirty || wv0 != m.seen_workers_version || (m.indexer && m.indexer->pending());
+        // updates must not race with kernels still reading the previous state
+        if (pending) for (auto& l : lanes) if (l.has_done) SMGX_CUDA(cudaStreamWaitEvent(ctrl, l.done, 0));
+        EventIndexView v{};
+        if (m.indexer) v = m.indexer->flush(ctrl, &launches);
+        uint32_t n_ids = m.indexer ? m.indexer->n_workers() : 0;
+        uint32_t words = m.indexer ? m.indexer->words() : 1;
+        uint64_t wv = m.indexer ? m.indexer->workers_version() : 0;
+        if (m.fleet_dirty || wv != m.seen_workers_version) {
+            uint32_t ns = (uint32_t)m.urls.size();
+            std::vector<int32_t> id_of_slice(std::max<uint32_t>(ns, 1), -1);
+            for (uint32_t i = 0; i < ns; ++i) id_of_slice[i] = m.indexer ? (int32_t)m.indexer->worker_id(m.urls[i]) : -1;
+            m.d_loads.reserve(std::max<uint32_t>(ns, 1) * 8);
+            m.d_flags.reserve(std::max<uint32_t>(ns, 1));
+            m.d_id_of_slice.reserve(std::max<uint32_t>(ns, 1) * 4);
+            m.d_derived.reserve(sizeof(FleetDerived));
+            m.d_slice_of_id.reserve(std::max<uint32_t>(n_ids, 1) * 4);
+            m.d_load_of_id.reserve(std::max<uint32_t>(n_ids, 1) * 8);
+            m.d_elig.reserve(kMaxWords * 8);
+            if (ns) {
+                SMGX_CUDA(cudaMemcpyAsync(m.d_loads.ptr, m.loads.data(), ns * 8, cudaMemcpyHostToDevice, ctrl));
+                SMGX_CUDA(cudaMemcpyAsync(m.d_flags.ptr, m.flags.data(), ns, cudaMemcpyHostToDevice, ctrl));
+                SMGX_CUDA(cudaMemcpyAsync(m.d_id_of_slice.ptr, id_of_slice.data(), ns * 4, cudaMemcpyHostToDevice, ctrl));
+            }
+            FleetRaw raw;
+            raw.loads = m.d_loads.as<uint64_t>(); raw.flags = m.d_flags.as<uint8_t>(); raw.id_of_slice = m.d_id_of_slice.as<int32_t>();
+            raw.n_slice = ns; raw.n_ids = n_ids; raw.words = words;
+            raw.abs_threshold = cfg.balance_abs_threshold; raw.rel_threshold = cfg.balance_rel_threshold;
+            launch_fleet_prepare(raw, m.d_derived.as<FleetDerived>(), m.d_slice_of_id.as<int32_t>(), m.d_load_of_id.as<uint64_t>(),
+                                 m.d_elig.as<uint64_t>(), ctrl);
+            ++launches;
+            m.fleet_dirty = false;
+            m.seen_workers_version = wv;
+        }
+        if (pending) {
+            SMGX_CUDA(cudaEventRecord(state_ready, ctrl));
+            for (auto& l : lanes) SMGX_CUDA(cudaStreamWaitEvent(l.stream, state_ready, 0));
+        }
+        if (ixv) *ixv = v;
+        if (fv) {
+            fv->derived = m.d_derived.as<FleetDerived>();
+            fv->slice_of_id = m.d_slice_of_id.as<int32_t>();
+            fv->load_of_id = m.d_load_of_id.as<uint64_t>();
+            fv->elig = m.d_elig.as<uint64_t>();
+        }
+    }
+
+    // Enqueue the kernels of one token batch on `lane` (device pointers).
+    void enqueue_tokens(ModelState& m, Lane& lane, const uint32_t* d_tokens, const uint32_t* d_offsets, uint32_t n, uint32_t max_req_tokens,
+                        int32_t* d_out, smgx_decision_info* d_info) {
+        if (!has_event_indexer(m))
+            throw Error(SMGX_UNKNOWN_ERROR,
+                        "model has no populated KV-event indexer: the approximate token-tree mode (cache_aware.rs:834-904) is not part of this "
+                        "build yet — there is no CPU fallback");
+        EventIndexView ixv;
+        FleetView fv;
+        sync_state(m, &ixv, &fv);
+        uint32_t bs = block_size_for(m);
+        SelectArgs a;
+        a.tokens = d_tokens; a.offsets = d_offsets; a.n = n; a.block_size = bs;
+        a.max_blocks = bs ? std::max<uint32_t>(max_req_tokens / bs, 1) : 1;
+        a.out_idx = d_out; a.out_info = d_info; a.err_flag = d_err.as<uint32_t>();
+        launch_event_select(ixv, fv, a, sm_count, lane.stream);
+        ++launches;
+        SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
+        lane.has_done = true;
+    }
+
+    Lane& free_lane() {
+        for (auto& l : lanes) if (!l.busy) return l;
+        throw Error(SMGX_INVALID_ARGUMENT, "all pipeline lanes are in flight; call smgx_wait first");
+    }
+
+    uint64_t submit_host(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info) {
+        SMGX_REQUIRE(n <= cfg.max_batch, "batch larger than max_batch");
+        SMGX_REQUIRE(m.urls.size() > 0 || true, "");
+        Lane& lane = free_lane();
+        uint32_t max_len = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+            max_len = std::max(max_len, offsets[i + 1] - offsets[i]);
+        }
+        SMGX_REQUIRE(max_len <= cfg.max_tokens_per_request, "request longer than max_tokens_per_request");
+        uint64_t total = n ? offsets[n] : 0;
+        uint64_t base = n ? offsets[0] : 0;
+        lane.d_tokens.reserve(std::max<uint64_t>(total - base, 1) * 4 + 16);
+        lane.d_offsets.reserve(((size_t)n + 1) * 4);
+        lane.d_out.reserve(std::max<uint32_t>(n, 1) * 4);
+        if (out_info) lane.d_info.reserve(std::max<uint32_t>(n, 1) * sizeof(smgx_decision_info));
+        if (n) {
+            // tokens are copied from offsets[0]; the kernel indexes with the caller's absolute offsets
+            SMGX_CUDA(cudaMemcpyAsync(lane.d_tokens.ptr, tokens + base, (total - base) * 4, cudaMemcpyHostToDevice, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+            enqueue_tokens(m, lane, lane.d_tokens.as<uint32_t>() - base, lane.d_offsets.as<uint32_t>(), n, std::max<uint32_t>(max_len, 1),
+                           lane.d_out.as<int32_t>(), out_info ? lane.d_info.as<smgx_decision_info>() : nullptr);
+            SMGX_CUDA(cudaMemcpyAsync(out_idx, lane.d_out.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
+            if (out_info)
+                SMGX_CUDA(cudaMemcpyAsync(out_info, lane.d_info.ptr, (size_t)n * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+        }
+        lane.busy = true;
+        lane.ticket = ++ticket_seq;
+        lane.model = &m;
+        lane.host_out = out_idx;
+        lane.n = n;
+        return lane.ticket;
+    }
+
+    void wait(uint64_t ticket) {
+        for (auto& l : lanes) {
+            if (!l.busy || l.ticket != ticket) continue;
+            SMGX_CUDA(cudaStreamSynchronize(l.stream));
+            l.busy = false;
+            // increment_processed(): every event-mode / imbalanced pick increments (cache_aware.rs:437, :767, :829)
+            ModelState& m = *l.model;
+            for (uint32_t i = 0; i < l.n; ++i) {
+                int32_t idx = l.host_out[i];
+                if (idx >= 0 && (size_t)idx < m.processed.size()) ++m.processed[(size_t)idx];
+            }
+            return;
+        }
+        throw Error(SMGX_INVALID_ARGUMENT, "unknown or already completed ticket");
+    }
+
+    smgx_cache_aware_config cfg;
+    int sm_count = 148;
+    size_t l2_bytes = 126u << 20;
+    std::mutex mu;
+    std::map<std::string, std::unique_ptr<ModelState>> models;
+    bool monitor = false;
+    std::vector<Lane> lanes;
+    cudaStream_t ctrl = nullptr;
+    cudaEvent_t state_ready = nullptr;
+    DevBuf d_err, d_flush, scratch, scratch2;
+    uint64_t launches = 0;
+    uint64_t ticket_seq = 0;
+};
+
+}  // namespace smgx
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+using namespace smgx;
+
+struct smgx_policy {
+    Policy impl;
+    explicit smgx_policy(const smgx_cache_aware_config& c) : impl(c) {}
+};
+
+namespace {
+void set_err(char** err, const std::string& msg) {
+    if (!err) return;
+    char* s = (char*)malloc(msg.size() + 1);
+    if (s) memcpy(s, msg.c_str(), msg.size() + 1);
+    *err = s;
+}
+template <class F> smgx_status guard(char** err, F&& f) {
+    if (err) *err = nullptr;
+    try {
+        return f();
+    } catch (const Error& e) {
+        set_err(err, e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_err(err, "out of memory");
+        return SMGX_MEMORY_ERROR;
+    } catch (const std::exception& e) {
+        set_err(err, e.what());
+        return SMGX_UNKNOWN_ERROR;
+    }
+}
+#define NONNULL(p) SMGX_REQUIRE((p) != nullptr, "Invalid arguments: null pointer")
+}  // namespace
+
+extern "C" {
+
+void smgx_default_config(smgx_cache_aware_config* c) {
+    if (!c) return;
+    c->cache_threshold = 0.5f; c->balance_abs_threshold = 32; c->balance_rel_threshold = 1.1f;
+    c->eviction_interval_secs = 30; c->max_tree_size = 10000; c->block_size = 16;
+    c->device_id = 0; c->max_batch = 65536; c->max_tokens_per_request = 32768;
+}
+
+smgx_policy* smgx_policy_create(const smgx_cache_aware_config* cfg, char** err) {
+    smgx_policy* out = nullptr;
+    guard(err, [&]() {
+        NONNULL(cfg);
+        out = new smgx_policy(*cfg);
+        return SMGX_SUCCESS;
+    });
+    return out;
+}
+void smgx_policy_free(smgx_policy* p) { delete p; }
+const char* smgx_policy_name(void) { return "cache_aware"; }
+uint32_t smgx_abi_version(void) { return SMGX_ABI_VERSION; }
+void smgx_free_string(char* s) { free(s); }
+void* smgx_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void smgx_free_pinned(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+// ---- fleet ----
+smgx_status smgx_set_workers(smgx_policy* p, const char* model_key, const char* const* urls, uint32_t n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || urls != nullptr, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        m.urls.clear();
+        for (uint32_t i = 0; i < n; ++i) { NONNULL(urls[i]); m.urls.emplace_back(urls[i]); }
+        m.loads.assign(n, 0);
+        m.flags.assign(n, 3);
+        m.processed.assign(n, 0);
+        m.fleet_dirty = true;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_set_fleet_state(smgx_policy* p, const char* model_key, const uint64_t* loads, const uint8_t* healthy, const uint8_t* circuit_ok,
+                                 uint32_t n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        SMGX_REQUIRE(n == m.urls.size(), "fleet state length does not match the worker slice");
+        for (uint32_t i = 0; i < n; ++i) {
+            if (loads) m.loads[i] = loads[i];
+            uint8_t h = healthy ? (healthy[i] ? 1 : 0) : (m.flags[i] & 1);
+            uint8_t c = circuit_ok ? (circuit_ok[i] ? 2 : 0) : 2;
+            m.flags[i] = h | c;
+        }
+        m.fleet_dirty = true;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_add_worker(smgx_policy* p, const char* model_key, const char* url, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(url);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        if (std::find(m.urls.begin(), m.urls.end(), url) == m.urls.end()) {
+            m.urls.emplace_back(url); m.loads.push_back(0); m.flags.push_back(3); m.processed.push_back(0);
+            m.fleet_dirty = true;
+        }
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_remove_worker(smgx_policy* p, const char* model_key, const char* url, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(url);
+        (void)model_key;  // no-op, as in the reference (cache_aware.rs:285-308): stale entries die by eviction
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_take_processed(smgx_policy* p, const char* model_key, uint64_t* out_counts, uint32_t n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        for (uint32_t i = 0; i < n && i < m.processed.size(); ++i) { if (out_counts) out_counts[i] = m.processed[i]; m.processed[i] = 0; }
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- event index ----
+smgx_status smgx_set_kv_event_monitor(smgx_policy* p, int present, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.monitor = present != 0;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_create(smgx_policy* p, const char* model_key, uint32_t jump_size, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        m.indexer = std::make_unique<EventIndex>(jump_size);
+        m.indexer->device_enabled = p->impl.cfg.device_id >= 0;
+        m.seen_workers_version = ~0ULL;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_set_block_size(smgx_policy* p, const char* model_key, uint32_t block_size, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        m.has_learned_bs = true;
+        m.learned_bs = block_size;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_intern_worker(smgx_policy* p, const char* model_key, const char* url, uint32_t* out_id, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(url); NONNULL(out_id);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        *out_id = p->impl.indexer(model_key).intern_worker(url);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_worker_id(smgx_policy* p, const char* model_key, const char* url, int64_t* out_id, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(url); NONNULL(out_id);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        *out_id = p->impl.indexer(model_key).worker_id(url);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_apply_stored(smgx_policy* p, const char* model_key, uint32_t worker_id, const uint64_t* seq_hashes,
+                                      const uint64_t* content_hashes, uint32_t n_blocks, const uint64_t* parent_seq_hash, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n_blocks == 0 || (seq_hashes && content_hashes), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        smgx_status st = p->impl.indexer(model_key).apply_stored(worker_id, seq_hashes, content_hashes, n_blocks, parent_seq_hash);
+        if (st == SMGX_WORKER_NOT_TRACKED) set_err(err, "worker not tracked in index");          // event_tree.rs:100
+        if (st == SMGX_PARENT_BLOCK_NOT_FOUND) set_err(err, "parent block hash not found for worker");  // :101
+        return st;
+    });
+}
+smgx_status smgx_indexer_apply_removed(smgx_policy* p, const char* model_key, uint32_t worker_id, const uint64_t* seq_hashes, uint32_t n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || seq_hashes, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.indexer(model_key).apply_removed(worker_id, seq_hashes, n);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_apply_cleared(smgx_policy* p, const char* model_key, uint32_t worker_id, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.indexer(model_key).apply_cleared(worker_id);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_remove_worker(smgx_policy* p, const char* model_key, uint32_t worker_id, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.indexer(model_key).remove_worker(worker_id);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_current_size(smgx_policy* p, const char* model_key, uint64_t* out, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        *out = p->impl.indexer(model_key).current_size();
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_indexer_entry_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        *out = p->impl.indexer(model_key).entry_count();
+        return SMGX_SUCCESS;
+    });
+}
+
+smgx_status smgx_content_hashes(smgx_policy* p, const uint32_t* tokens, uint32_t n_tokens, uint32_t block_size, uint64_t* out_hashes,
+                                uint32_t cap, uint32_t* out_n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_n);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        uint32_t nb = block_size ? n_tokens / block_size : 0;
+        *out_n = nb;
+        if (nb == 0) return SMGX_SUCCESS;
+        NONNULL(tokens); NONNULL(out_hashes);
+        SMGX_REQUIRE(cap >= nb, "output capacity too small");
+        Lane& l = P.lanes[0];
+        P.scratch.reserve((size_t)n_tokens * 4);
+        P.scratch2.reserve((size_t)nb * 8);
+        SMGX_CUDA(cudaMemcpyAsync(P.scratch.ptr, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, l.stream));
+        launch_content_hashes(P.scratch.as<uint32_t>(), n_tokens, block_size, P.scratch2.as<uint64_t>(), l.stream);
+        ++P.launches;
+        SMGX_CUDA(cudaMemcpyAsync(out_hashes, P.scratch2.ptr, (size_t)nb * 8, cudaMemcpyDeviceToHost, l.stream));
+        SMGX_CUDA(cudaStreamSynchronize(l.stream));
+        return SMGX_SUCCESS;
+    });
+}
+
+smgx_status smgx_indexer_apply_stored_tokens(smgx_policy* p, const char* model_key, uint32_t worker_id, const uint64_t* seq_hashes,
+                                             const uint32_t* token_ids, uint32_t block_size, uint32_t n_blocks, const uint64_t* parent_seq_hash,
+                                             char** err) {
+    // convert_kv_block hashes token_ids (kv_event_monitor.rs:592-597); done by the content-hash kernel, then apply_stored.
+    if (err) *err = nullptr;
+    if (!p) { set_err(err, "Invalid arguments: null pointer"); return SMGX_INVALID_ARGUMENT; }
+    if (n_blocks == 0) return SMGX_SUCCESS;
+    if (block_size == 0) { set_err(err, "block_size must be > 0"); return SMGX_INVALID_ARGUMENT; }
+    std::vector<uint64_t> hashes(n_blocks);
+    uint32_t got = 0;
+    smgx_status st = smgx_content_hashes(p, token_ids, n_blocks * block_size, block_size, hashes.data(), n_blocks, &got, err);
+    if (st != SMGX_SUCCESS) return st;
+    return smgx_indexer_apply_stored(p, model_key, worker_id, seq_hashes, hashes.data(), n_blocks, parent_seq_hash, err);
+}
+
+smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, const uint64_t* content_hashes, uint32_t n, int early_exit,
+                                      uint32_t* out_scores, uint64_t* out_tree_sizes, uint32_t cap, uint32_t* out_n_workers, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_scores); NONNULL(out_n_workers);
+        SMGX_REQUIRE(n == 0 || content_hashes, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        if (!m.indexer) throw Error(SMGX_NOT_FOUND, "no event indexer for this model");
+        uint32_t nw = m.indexer->n_workers();
+        *out_n_workers = nw;
+        SMGX_REQUIRE(cap >= nw, "output capacity smaller than the worker count");
+        EventIndexView ixv;
+        P.sync_state(m, &ixv, nullptr);
+        Lane& l = P.lanes[0];
+        size_t score_slots = (size_t)std::max<uint32_t>(ixv.words * 64, 64);
+        P.scratch.reserve(std::max<size_t>((size_t)n, 1) * 8);
+        P.scratch2.reserve(score_slots * 4);
+        if (n) SMGX_CUDA(cudaMemcpyAsync(P.scratch.ptr, content_hashes, (size_t)n * 8, cudaMemcpyHostToDevice, l.stream));
+        SMGX_CUDA(cudaMemsetAsync(P.scratch2.ptr, 0, score_slots * 4, l.stream));
+        launch_find_matches(ixv, P.scratch.as<uint64_t>(), n, early_exit != 0, P.scratch2.as<uint32_t>(), l.stream);
+        ++P.launches;
+        std::vector<uint32_t> sc(score_slots);
+        SMGX_CUDA(cudaMemcpyAsync(sc.data(), P.scratch2.ptr, score_slots * 4, cudaMemcpyDeviceToHost, l.stream));
+        std::vector<uint64_t> ts(std::max<uint32_t>(nw, 1));
+        if (nw) SMGX_CUDA(cudaMemcpyAsync(ts.data(), ixv.tree_sizes, (size_t)nw * 8, cudaMemcpyDeviceToHost, l.stream));
+        SMGX_CUDA(cudaStreamSynchronize(l.stream));
+        for (uint32_t w = 0; w < nw; ++w) { out_scores[w] = sc[w]; if (out_tree_sizes) out_tree_sizes[w] = ts[w]; }
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- hot call ----
+uint32_t smgx_pipeline_depth(const smgx_policy* p) { return p ? (uint32_t)p->impl.lanes.size() : 0; }
+
+smgx_status smgx_submit_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                               int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_ticket);
+        SMGX_REQUIRE(n == 0 || (tokens && offsets && out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.use_device();
+        ModelState& m = p->impl.model(model_key, false);
+        *out_ticket = p->impl.submit_host(m, tokens, offsets, n, out_worker_idx, out_info);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.use_device();
+        p->impl.wait(ticket);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                                     int32_t* out_worker_idx, smgx_decision_info* out_info, char** err) {
+    uint64_t t = 0;
+    smgx_status st = smgx_submit_tokens(p, model_key, tokens, offsets, n, out_worker_idx, out_info, &t, err);
+    if (st != SMGX_SUCCESS) return st;
+    return smgx_wait(p, t, err);
+}
+
+smgx_status smgx_select_batch_tokens_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens,
+                                            const uint32_t* d_offsets, uint32_t n, uint32_t max_request_tokens, int32_t* d_out_worker_idx,
+                                            smgx_decision_info* d_out_info, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (d_tokens && d_offsets && d_out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(lane < P.lanes.size(), "lane out of range");
+        ModelState& m = P.model(model_key, false);
+        uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
+        if (n) P.enqueue_tokens(m, P.lanes[lane], d_tokens, d_offsets, n, cap, d_out_worker_idx, d_out_info);
+        return SMGX_SUCCESS;
+    });
+}
+
+void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err) {
+    void* out = nullptr;
+    guard(err, [&]() {
+        NONNULL(p);
+        p->impl.use_device();
+        SMGX_CUDA(cudaMalloc(&out, bytes ? bytes : 1));
+        return SMGX_SUCCESS;
+    });
+    return out;
+}
+void smgx_device_free(smgx_policy* p, void* dptr) {
+    if (p && dptr && p->impl.cfg.device_id >= 0) { cudaSetDevice(p->impl.cfg.device_id); cudaFree(dptr); }
+}
+smgx_status smgx_memcpy_h2d(smgx_policy* p, void* dptr, const void* host, size_t bytes, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(dptr); NONNULL(host);
+        p->impl.use_device();
+        SMGX_CUDA(cudaMemcpy(dptr, host, bytes, cudaMemcpyHostToDevice));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_memcpy_d2h(smgx_policy* p, void* host, const void* dptr, size_t bytes, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(dptr); NONNULL(host);
+        p->impl.use_device();
+        SMGX_CUDA(cudaMemcpy(host, dptr, bytes, cudaMemcpyDeviceToHost));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_synchronize(smgx_policy* p, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        p->impl.use_device();
+        SMGX_CUDA(cudaDeviceSynchronize());
+        uint32_t flag = 0;
+        SMGX_CUDA(cudaMemcpy(&flag, p->impl.d_err.ptr, 4, cudaMemcpyDeviceToHost));
+        if (flag) {
+            SMGX_CUDA(cudaMemset(p->impl.d_err.ptr, 0, 4));
+            throw Error(SMGX_INVALID_ARGUMENT, "a request exceeded max_tokens_per_request on the device-resident path");
+        }
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_timer_start(smgx_policy* p, uint32_t lane, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        p->impl.use_device();
+        SMGX_REQUIRE(lane < p->impl.lanes.size(), "lane out of range");
+        SMGX_CUDA(cudaEventRecord(p->impl.lanes[lane].t0, p->impl.lanes[lane].stream));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_timer_stop_ms(smgx_policy* p, uint32_t lane, float* out_ms, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_ms);
+        p->impl.use_device();
+        SMGX_REQUIRE(lane < p->impl.lanes.size(), "lane out of range");
+        Lane& l = p->impl.lanes[lane];
+        SMGX_CUDA(cudaEventRecord(l.t1, l.stream));
+        SMGX_CUDA(cudaEventSynchronize(l.t1));
+        SMGX_CUDA(cudaEventElapsedTime(out_ms, l.t0, l.t1));
+        return SMGX_SUCCESS;
+    });
+}
+uint64_t smgx_kernel_launches(const smgx_policy* p) { return p ? p->impl.launches : 0; }
+smgx_status smgx_flush_l2(smgx_policy* p, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        Policy& P = p->impl;
+        P.use_device();
+        size_t bytes = std::max<size_t>(P.l2_bytes * 2, 256u << 20);
+        P.d_flush.reserve(bytes);
+        launch_fill(P.d_flush.as<uint32_t>(), (uint32_t)P.launches, bytes / 4, P.lanes[0].stream);
+        ++P.launches;
+        return SMGX_SUCCESS;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+"""Host-side mirror of the reference's plugin surface for the cache-aware path, over the smgx C ABI.
+
+Names, argument meaning and error behaviour follow the reference so the parity tests read like its own tests:
+  * CacheAwareConfig / SelectWorkerInfo / LoadBalancingPolicy   model_gateway/src/policies/mod.rs:43-175
+  * CacheAwarePolicy                                            model_gateway/src/policies/cache_aware.rs
+  * PolicyFactory                                               model_gateway/src/policies/factory.rs:17-93
+  * PositionalIndexer                                           crates/kv_index/src/event_tree.rs:257-760
+  * KvEventMonitor (get_indexer / block_size / set_block_size)  model_gateway/src/worker/kv_event_monitor.rs
+  * the Worker scalars the path reads                           model_gateway/src/worker/worker.rs:109-230
+Every decision comes out of the CUDA kernels; this file only marshals arrays.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+UNKNOWN_MODEL_ID = "unknown"
+
+
+def normalize_model_key(model_id: str) -> str:  # policies/mod.rs:151-157
+    return model_id if model_id else UNKNOWN_MODEL_ID
+
+
+@dataclass
+class CacheAwareConfig:  # policies/mod.rs:94-117
+    cache_threshold: float = 0.5
+    balance_abs_threshold: int = 32
+    balance_rel_threshold: float = 1.1
+    eviction_interval_secs: int = 30
+    max_tree_size: int = 10000
+    block_size: int = 16
+
+
+@dataclass
+class SelectWorkerInfo:  # policies/mod.rs:161-175 (headers / hash_ring are not read by cache_aware)
+    request_text: Optional[str] = None
+    tokens: Optional[Sequence[int]] = None
+
+
+class BasicWorker:
+    """The scalars CacheAwarePolicy reads through `trait Worker` (worker/worker.rs:114,151-153,187,208,217)."""
+
+    def __init__(self, url: str, model_id: str = ""):
+        self._url, self._model_id = url, model_id
+        self._load, self._healthy, self._circuit_ok, self._processed = 0, True, True, 0
+
+    def url(self): return self._url
+    def model_id(self): return self._model_id
+    def load(self): return self._load
+    def is_healthy(self): return self._healthy
+    def circuit_breaker_can_execute(self): return self._circuit_ok
+    def processed(self): return self._processed
+    def increment_load(self): self._load += 1
+    def decrement_load(self): self._load = max(0, self._load - 1)
+    def set_load(self, v): self._load = int(v)
+    def set_healthy(self, ok: bool): self._healthy = bool(ok)      # set_status(Ready) ⇔ True; any other status ⇔ False
+    def set_circuit_ok(self, ok: bool): self._circuit_ok = bool(ok)
+
+
+def _u32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint32))
+
+
+def _u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class _Handle:
+    """Owns one smgx_policy*."""
+
+    def __init__(self, cfg: CacheAwareConfig, device_id: int, max_batch: int = 0, max_tokens_per_request: int = 0):
+        self.L = _lib.load()
+        c = _lib.Config()
+        self.L.smgx_default_config(C.byref(c))
+        c.cache_threshold, c.balance_abs_threshold = cfg.cache_threshold, cfg.balance_abs_threshold
+        c.balance_rel_threshold, c.eviction_interval_secs = cfg.balance_rel_threshold, cfg.eviction_interval_secs
+        c.max_tree_size, c.block_size = cfg.max_tree_size, cfg.block_size
+        c.device_id, c.max_batch, c.max_tokens_per_request = device_id, max_batch, max_tokens_per_request
+        err = _lib.new_err()
+        self.p = self.L.smgx_policy_create(C.byref(c), C.byref(err))
+        if not self.p:
+            _lib.check(_lib.UNKNOWN_ERROR if not err.value else _lib.DEVICE_ERROR, err)
+        self.device_id = device_id
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.L.smgx_policy_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        self.close()
+
+    def call(self, fn, *args):
+        err = _lib.new_err()
+        code = getattr(self.L, fn)(self.p, *args, C.byref(err))
+        _lib.check(code, err)
+
+
+class ApplyError(Exception):  # kv_index::ApplyError (event_tree.rs:88-106)
+    pass
+
+
+class PositionalIndexer:
+    """kv_index::PositionalIndexer bound to (policy handle, model).  Blocks are (seq_hash, content_hash) pairs =
+    StoredBlock (event_tree.rs:81-86); the caller-owned WorkerBlockMap lives inside the library per worker id."""
+
+    def __init__(self, handle: _Handle, model: str, jump_size: int = 32):
+        if jump_size <= 0:
+            raise ValueError("jump_size must be greater than 0")  # event_tree.rs:280
+        self.h, self.model = handle, model.encode()
+        self.h.call("smgx_indexer_create", self.model, jump_size)
+
+    @classmethod
+    def standalone(cls, jump_size: int = 32, device_id: int = 0):
+        """An indexer with a private policy handle (the reference constructs PositionalIndexer::new(jump) directly)."""
+        if jump_size <= 0:
+            raise ValueError("jump_size must be greater than 0")
+        return cls(_Handle(CacheAwareConfig(eviction_interval_secs=0), device_id), UNKNOWN_MODEL_ID, jump_size)
+
+    def intern_worker(self, url: str) -> int:
+        out = C.c_uint32()
+        self.h.call("smgx_indexer_intern_worker", self.model, url.encode(), C.byref(out))
+        return out.value
+
+    def worker_id(self, url: str) -> Optional[int]:
+        out = C.c_int64()
+        self.h.call("smgx_indexer_worker_id", self.model, url.encode(), C.byref(out))
+        return None if out.value < 0 else out.value
+
+    def apply_stored(self, worker_id: int, blocks, parent: Optional[int] = None):
+        seq, con = _u64([b[0] for b in blocks]), _u64([b[1] for b in blocks])
+        par = C.c_uint64(parent) if parent is not None else None
+        try:
+            self.h.call("smgx_indexer_apply_stored", self.model, worker_id, _p(seq), _p(con), len(blocks),
+                        C.cast(C.byref(par), C.c_void_p) if par is not None else None)
+        except _lib.SmgxError as e:
+            if e.code == _lib.WORKER_NOT_TRACKED:
+                raise ApplyError("WorkerNotTracked: " + e.msg)
+            if e.code == _lib.PARENT_BLOCK_NOT_FOUND:
+                raise ApplyError("ParentBlockNotFound: " + e.msg)
+            raise
+
+    def apply_stored_tokens(self, worker_id: int, seq_hashes, token_ids, block_size: int, parent: Optional[int] = None):
+        seq, tok = _u64(seq_hashes), _u32(token_ids)
+        par = C.c_uint64(parent) if parent is not None else None
+        try:
+            self.h.call("smgx_indexer_apply_stored_tokens", self.model, worker_id, _p(seq), _p(tok), block_size, seq.size,
+                        C.cast(C.byref(par), C.c_void_p) if par is not None else None)
+        except _lib.SmgxError as e:
+            if e.code == _lib.WORKER_NOT_TRACKED:
+                raise ApplyError("WorkerNotTracked: " + e.msg)
+            if e.code == _lib.PARENT_BLOCK_NOT_FOUND:
+                raise ApplyError("ParentBlockNotFound: " + e.msg)
+            raise
+
+    def apply_removed(self, worker_id: int, seq_hashes):
+        s = _u64(seq_hashes)
+        self.h.call("smgx_indexer_apply_removed", self.model, worker_id, _p(s), s.size)
+
+    def apply_cleared(self, worker_id: int):
+        self.h.call("smgx_indexer_apply_cleared", self.model, worker_id)
+
+    def remove_worker(self, worker_id: int):
+        self.h.call("smgx_indexer_remove_worker", self.model, worker_id)
+
+    def current_size(self) -> int:
+        out = C.c_uint64()
+        self.h.call("smgx_indexer_current_size", self.model, C.byref(out))
+        return out.value
+
+    def entry_count(self) -> int:
+        out = C.c_uint64()
+        self.h.call("smgx_indexer_entry_count", self.model, C.byref(out))
+        return out.value
+
+    def find_matches(self, content_hashes, early_exit: bool = False):
+        """→ (scores, tree_sizes) dicts keyed by worker id, like OverlapScores (event_tree.rs:112-118).  GPU kernel."""
+        hs = _u64(content_hashes)
+        cap = 2048
+        sc, ts, nw = np.zeros(cap, np.uint32), np.zeros(cap, np.uint64), C.c_uint32()
+        self.h.call("smgx_indexer_find_matches", self.model, _p(hs), hs.size, 1 if early_exit else 0, _p(sc), _p(ts), cap, C.byref(nw))
+        ids = [i for i in range(nw.value) if sc[i] > 0]
+        return {i: int(sc[i]) for i in ids}, {i: int(ts[i]) for i in ids}
+
+
+class KvEventMonitor:
+    """The slice of worker::KvEventMonitor the policy reads: per-model indexers and learned block sizes."""
+
+    def __init__(self, policy: "CacheAwarePolicy", default_block_size: Optional[int] = None):
+        self.policy, self.default_block_size, self.indexers = policy, default_block_size, {}
+
+    def create_indexer(self, model: str, jump_size: int = 64) -> PositionalIndexer:  # DEFAULT_JUMP_SIZE kv_event_monitor.rs:31
+        ix = PositionalIndexer(self.policy._h, model, jump_size)
+        self.indexers[model] = ix
+        return ix
+
+    def get_indexer(self, model: str) -> Optional[PositionalIndexer]:
+        return self.indexers.get(model)
+
+    def set_block_size(self, model: str, block_size: int):
+        self.policy._h.call("smgx_indexer_set_block_size", model.encode(), block_size)
+
+
+class CacheAwarePolicy:
+    """policies::CacheAwarePolicy on the GPU.  select_worker keeps the reference signature; select_worker_batch is the
+    batched form the host batcher uses (all requests see one fleet snapshot)."""
+
+    def __init__(self, config: Optional[CacheAwareConfig] = None, device_id: int = 0, max_batch: int = 0, max_tokens_per_request: int = 0):
+        self.config = config or CacheAwareConfig()
+        self._h = _Handle(self.config, device_id, max_batch, max_tokens_per_request)
+        self._slices = {}   # model → tuple(urls) currently registered
+        self._monitor = None
+
+    @classmethod
+    def with_config(cls, config: CacheAwareConfig, **kw):
+        return cls(config, **kw)
+
+    def close(self):
+        self._h.close()
+
+    # -- LoadBalancingPolicy ------------------------------------------------------------------------------------
+    def name(self) -> str:
+        return _lib.load().smgx_policy_name().decode()
+
+    def needs_request_text(self) -> bool:  # cache_aware.rs:708-710
+        return True
+
+    def on_request_complete(self, worker_url: str, success: bool):  # cache_aware.rs:692-702 (no state)
+        return None
+
+    # -- fleet ---------------------------------------------------------------------------------------------------
+    def _model_of(self, workers: Sequence[BasicWorker]) -> str:
+        for w in workers:  # model of the first healthy worker (cache_aware.rs:659); any worker when none is healthy
+            if w.is_healthy() and w.circuit_breaker_can_execute():
+                return normalize_model_key(w.model_id())
+        return normalize_model_key(workers[0].model_id()) if workers else UNKNOWN_MODEL_ID
+
+    def _register(self, model: str, urls):
+        arr = (C.c_char_p * len(urls))(*[u.encode() for u in urls])
+        self._h.call("smgx_set_workers", model.encode(), arr, len(urls))
+        self._slices[model] = tuple(urls)
+
+    def init_workers(self, workers: Sequence[BasicWorker]):  # cache_aware.rs:219-249
+        by_model = {}
+        for w in workers:
+            by_model.setdefault(normalize_model_key(w.model_id()), []).append(w.url())
+        for model, urls in by_model.items():
+            self._register(model, urls)
+
+    def add_worker(self, worker: BasicWorker):  # cache_aware.rs:252-266
+        self._h.call("smgx_add_worker", normalize_model_key(worker.model_id()).encode(), worker.url().encode())
+
+    def remove_worker_by_url(self, url: str):  # cache_aware.rs:302-308 (no-op)
+        self._h.call("smgx_remove_worker", b"", url.encode())
+
+    def _push_fleet(self, workers: Sequence[BasicWorker]) -> bytes:
+        model = self._model_of(workers)
+        urls = tuple(w.url() for w in workers)
+        if self._slices.get(model) != urls:
+            self._register(model, list(urls))
+        loads = _u64([w.load() for w in workers])
+        healthy = np.ascontiguousarray(np.asarray([1 if w.is_healthy() else 0 for w in workers], dtype=np.uint8))
+        circuit = np.ascontiguousarray(np.asarray([1 if w.circuit_breaker_can_execute() else 0 for w in workers], dtype=np.uint8))
+        self._h.call("smgx_set_fleet_state", model.encode(), _p(loads), _p(healthy), _p(circuit), len(workers))
+        return model.encode()
+
+    # -- KV events -----------------------------------------------------------------------------------------------
+    def kv_event_monitor(self, default_block_size: Optional[int] = None) -> KvEventMonitor:
+        return KvEventMonitor(self, default_block_size)
+
+    def set_kv_event_monitor(self, monitor: Optional[KvEventMonitor]):  # cache_aware.rs:213-215
+        self._monitor = monitor
+        self._h.call("smgx_set_kv_event_monitor", 1 if monitor is not None else 0)
+
+    # -- the pick ------------------------------------------------------------------------------------------------
+    def select_worker(self, workers: Sequence[BasicWorker], info: SelectWorkerInfo) -> Optional[int]:
+        """LoadBalancingPolicy::select_worker (cache_aware.rs:648): index into `workers` or None."""
+        if not workers:
+            return None
+        if info.tokens is None:
+            raise _lib.SmgxError(_lib.UNKNOWN_ERROR, "text (string-tree) routing is not part of this build yet")
+        idx, _ = self.select_worker_batch(workers, [info.tokens])
+        i = int(idx[0])
+        if i >= 0:
+            workers[i]._processed += 1  # mirror of increment_processed(); the library keeps the authoritative counters
+        return None if i < 0 else i
+
+    def select_worker_batch(self, workers: Sequence[BasicWorker], requests=None, tokens=None, offsets=None, want_info: bool = True):
+        """Batch of token requests against one fleet snapshot.  Either `requests` (list of token lists) or a ragged
+        (tokens u32, offsets u32[n+1]) pair.  → (worker_idx int32[n] with -1 = None, info structured array or None)."""
+        model = self._push_fleet(workers)
+        if requests is not None:
+            lens = [len(r) for r in requests]
+            offsets = np.zeros(len(requests) + 1, dtype=np.uint32)
+            np.cumsum(lens, out=offsets[1:])
+            tokens = _u32(np.concatenate([np.asarray(r, dtype=np.uint32) for r in requests]) if sum(lens) else [])
+        tokens, offsets = _u32(tokens), _u32(offsets)
+        n = offsets.size - 1
+        out = np.full(max(n, 1), -1, dtype=np.int32)
+        info = (_lib.DecisionInfo * max(n, 1))() if want_info else None
+        tok_ptr = _p(tokens) if tokens.size else C.cast(C.create_string_buffer(4), C.c_void_p)
+        self._h.call("smgx_select_batch_tokens", model, tok_ptr, _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
+        return out[:n], (info if info is None else [info[i] for i in range(n)])
+
+    def take_processed(self, model: str = UNKNOWN_MODEL_ID, n: Optional[int] = None):
+        n = n if n is not None else len(self._slices.get(model, ()))
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        self._h.call("smgx_take_processed", model.encode(), _p(out), n)
+        return out[:n]
+
+    def kernel_launches(self) -> int:
+        return _lib.load().smgx_kernel_launches(self._h.p)
+
+
+class PolicyFactory:
+    """policies::PolicyFactory for the one policy this library replaces (factory.rs:17-93)."""
+
+    @staticmethod
+    def create_by_name(name: str, **kw):
+        if name.lower() in ("cache_aware", "cacheaware"):  # factory.rs:84
+            return CacheAwarePolicy(CacheAwareConfig(), **kw)
+        return None
+
+    @staticmethod
+    def create_from_config(cache_threshold, balance_abs_threshold, balance_rel_threshold, eviction_interval_secs, max_tree_size, block_size,
+                           **kw):  # factory.rs:22-39 PolicyConfig::CacheAware{..}
+        return CacheAwarePolicy(CacheAwareConfig(cache_threshold, balance_abs_threshold, balance_rel_threshold, eviction_interval_secs,
+                                                 max_tree_size, block_size), **kw)

@@ -15,9 +15,12 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session", autouse=True)
 def _build_oracle():
-    """The oracle (test infrastructure) is compiled on demand; the product library is NOT built here."""
+    """Compile the oracle (test infrastructure) and the product library on demand."""
     so = os.path.join(ROOT, "oracle", "liborc.so")
     srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle")) if f.endswith((".h", ".cc"))]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liborc.so"])
+    # the product library: built here with nvcc (cross-compiles sm_100a without a GPU); travels prebuilt to the GPU box
+    from smg_b200 import build as _b
+    _b.build()
     yield
