@@ -203,22 +203,18 @@ def run_reference(args, rank, world):
     op, _ = populate_oracle(seqs, hashes, W, bs, 64)
     loads = synth.poisson_loads(W, 8, 42)
     op.set_state(loads, [1] * W, [1] * W)
-    cores = os.cpu_count() or 1
-    batches = [synth.ragged(gen_batch(seqs, B, 42 + i, bs)[0]) for i in range(4)]
-    for i in range(args.warmup):
-        tk, off = batches[i % len(batches)]
-        op.select_batch_tokens(tk, off.astype(np.uint64), threads=cores)
-    t = 0.0
-    for i in range(args.steps):
-        tk, off = batches[i % len(batches)]
-        t += op.select_batch_tokens(tk, off.astype(np.uint64), threads=cores)[3]
+    cores = args.threads or os.cpu_count() or 1
+    batches = [synth.ragged(gen_batch(seqs, B, 42 + i, bs)[0]) for i in range(8)]
+    batches = [(tk, off.astype(np.uint64)) for tk, off in batches]
+    op.select_steps_mt(batches, args.warmup, cores)
+    _, t = op.select_steps_mt(batches, args.steps, cores)
     val = args.steps * B / t
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(args), "batch": B, "tokens": T, "workers": W, "mode": "event_driven"},
             "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} batches of {B} requests, read-only event-mode matching sharded over {cores} host threads"},
+                             "sample": f"{args.steps} batches of {B} requests, read-only event-mode matching, each batch sharded over {cores} persistent host threads"},
             "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -239,6 +235,8 @@ def main():
     ap.add_argument("--workers", type=int, default=64)
     ap.add_argument("--sequences", type=int, default=31250)
     ap.add_argument("--ring", type=int, default=32, help="distinct device-resident batches cycled through (ring × batch × tokens × 4 B > L2)")
+    ap.add_argument("--lanes", type=int, default=4, help="stream lanes the timed steps are issued over (1 = strictly serial launches)")
+    ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -308,8 +306,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    n_lanes = max(1, min(args.lanes, L.smgx_pipeline_depth(h.p)))
+
     def step_dev(i):
-        h.call("smgx_select_batch_tokens_device", model, 0, d_tok[i % R], d_off, B, T, d_out[i % R], None)
+        # consecutive steps are issued round-robin over the library's stream lanes, as the host batcher does
+        h.call("smgx_select_batch_tokens_device", model, i % n_lanes, d_tok[i % R], d_off, B, T, d_out[i % R], None)
 
     # ---- kernel-only (inputs resident in HBM) ----
     for i in range(args.warmup):
@@ -320,10 +321,23 @@ def main():
         sampler.start()
     launches0 = pol.kernel_launches()
     ms = C.c_float()
-    h.call("smgx_timer_start", 0)
-    for i in range(args.steps):
-        step_dev(args.warmup + i)
-    h.call("smgx_timer_stop_ms", 0, C.byref(ms))
+    # the K timed steps are handed over in ONE C-ABI call (smgx_select_many_tokens_device): the host cost of a step is
+    # then a C loop iteration, as it would be from the Rust batcher, not a Python→ctypes round trip (~5 µs)
+    K = args.steps
+    order = [(args.warmup + i) % R for i in range(K)]
+    TOK = (C.c_void_p * K)(*[d_tok[j] for j in order])
+    OFF = (C.c_void_p * K)(*[d_off] * K)
+    OUT = (C.c_void_p * K)(*[d_out[j] for j in order])
+    NS = (C.c_uint32 * K)(*[B] * K)
+    if n_lanes == 1:
+        h.call("smgx_timer_start_all")
+        for i in range(K):
+            step_dev(args.warmup + i)
+        h.call("smgx_timer_stop_all_ms", C.byref(ms))
+    else:
+        h.call("smgx_timer_start_all")
+        h.call("smgx_select_many_tokens_device", model, K, TOK, OFF, NS, T, OUT)
+        h.call("smgx_timer_stop_all_ms", C.byref(ms))
     barrier()
     gpu_launches = pol.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -381,8 +395,9 @@ def main():
     p50_us = float(np.percentile(lat, 50) * 1e6)
 
     peak, peak_src = measured_peak()
-    avg_launch_s = ms.value / 1e3 / args.steps
-    achieved = alg_bytes * B / avg_launch_s / 1e9
+    steps_per_launch = args.steps / max(gpu_launches, 1)
+    avg_launch_s = ms.value / 1e3 / max(gpu_launches, 1)
+    achieved = alg_bytes * B * steps_per_launch / avg_launch_s / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,13 +406,17 @@ def main():
                    "index_entries": int(ix.entry_count()), "mode": "event_driven", "parallelism": f"replicas x{world} (no data-path collective)",
                    "l2_hygiene": f"ring of {R} distinct device-resident batches = {R * B * T * 4 / 2**20:.0f} MiB of tokens > L2; index "
                                  f"({ix.entry_count() * 32 / 2**20:.0f} MiB live slots) is the L2-resident working set",
-                   "index_build_s": round(t_pop, 2)},
+                   "index_build_s": round(t_pop, 2),
+                   "issue": (f"K steps handed to smgx_select_many_tokens_device in one call: up to 32 batches per launch (blockIdx.y = batch), "
+                             f"launches alternate over {n_lanes} CUDA stream lanes; CUDA events bracket all lanes") if n_lanes > 1 else
+                            "K launches, one batch each, on one stream"},
         "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(B * T * 4 + (B + 1) * 4), "d2h_bytes_per_step": int(B * 4),
                 "pipeline_depth": int(depth), "timing": "host wall clock around K pipelined submit/wait calls, device synchronised on both sides"},
         "p50_decision_latency_us": p50_us, "p99_decision_latency_us": p99_us,
         "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                     "kernel": "event_select_kernel", "algorithmic_bytes_per_decision": alg_bytes, "mean_reference_probes": mean_pr,
+                     "kernel": "event_select_multi_kernel" if n_lanes > 1 else "event_select_kernel", "steps_per_launch": steps_per_launch,
+                     "algorithmic_bytes_per_decision": alg_bytes, "mean_reference_probes": mean_pr,
                      "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src},
         "clocks": clocks,
     }

@@ -153,6 +153,11 @@ smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err);
 smgx_status smgx_select_batch_tokens_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens,
                                             const uint32_t* d_offsets, uint32_t n, uint32_t max_request_tokens,
                                             int32_t* d_out_worker_idx, smgx_decision_info* d_out_info, char** err);
+/* Several ready device-resident batches at once (what the host batcher hands over when more than one batch is queued):
+ * batch j is enqueued on lane j % smgx_pipeline_depth(), so consecutive batches overlap on the GPU. */
+smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
+                                           const uint32_t* const* d_offsets, const uint32_t* n, uint32_t max_request_tokens,
+                                           int32_t* const* d_out_worker_idx, char** err);
 void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err);
 void smgx_device_free(smgx_policy* p, void* dptr);
 smgx_status smgx_memcpy_h2d(smgx_policy* p, void* dptr, const void* host, size_t bytes, char** err);
@@ -161,6 +166,10 @@ smgx_status smgx_synchronize(smgx_policy* p, char** err);
 /* CUDA-event timing on the launching stream (lane): start/stop bracket whatever is enqueued between them. */
 smgx_status smgx_timer_start(smgx_policy* p, uint32_t lane, char** err);
 smgx_status smgx_timer_stop_ms(smgx_policy* p, uint32_t lane, float* out_ms, char** err);
+/* Same across ALL lanes: start is recorded on lane 0 and every other lane is made to wait for it; stop joins every lane
+ * into lane 0 before recording the end event — so the interval covers work issued round-robin over the lanes. */
+smgx_status smgx_timer_start_all(smgx_policy* p, char** err);
+smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
 /* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
 uint64_t smgx_kernel_launches(const smgx_policy* p);
 /* Writes a buffer larger than L2 (bench hygiene between timed iterations). */

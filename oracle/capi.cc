@@ -5,6 +5,7 @@
  * `--impl reference` legs can drive it through ctypes.  See the class headers for reference file:line.
  */
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <thread>
@@ -231,22 +232,43 @@ double orc_policy_select_batch_tokens(void* h, const uint32_t* tokens, const uin
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
-// Read-only event-mode scoring of a batch with `threads` host threads (the reference's concurrent-read design:
-// select_worker takes &self and the index is only read).  Each thread gets a private copy of the fleet vector
-// (the processed counter is the only thing select_worker writes in event mode).  Returns elapsed seconds.
-double orc_policy_select_batch_tokens_mt(void* h, const uint32_t* tokens, const uint64_t* offsets, size_t n, int32_t* out_idx,
-                                         int threads) {
+// Read-only event-mode scoring with `threads` persistent host threads (the reference's concurrent-read design:
+// select_worker takes &self, the index is only read, requests are spread over a tokio worker pool).  `steps` batches
+// are routed back to back: batch s = tokens/offsets of (s % n_batches); threads are spawned ONCE, every thread owns a
+// fixed shard of each batch, and a spin barrier separates consecutive steps so a "step" keeps its meaning.
+// Each thread gets a private copy of the fleet vector (the processed counter is the only thing select_worker writes
+// in event mode).  Falls back to one thread when the model has no populated indexer (tree modes mutate the tree).
+// Returns elapsed seconds.
+double orc_policy_select_steps_mt(void* h, const uint32_t* const* tokens, const uint64_t* const* offsets, size_t n_batches,
+                                  size_t n, size_t steps, int32_t* out_idx, int threads) {
     auto* b = (PolicyBox*)h;
     if (threads < 1) threads = 1;
+    if (!b->workers.empty()) {
+        std::string model = normalize_model_key(b->workers[0].model_id);
+        if (!b->pol.has_event_indexer(model)) threads = 1;
+    }
+    std::atomic<size_t> arrived{0};
+    std::atomic<size_t> generation{0};
+    auto barrier = [&](size_t& local_gen) {
+        size_t g = local_gen++;
+        if (arrived.fetch_add(1) + 1 == (size_t)threads) { arrived.store(0); generation.store(g + 1); }
+        else { while (generation.load(std::memory_order_acquire) <= g) std::this_thread::yield(); }
+    };
     auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> ts;
     for (int t = 0; t < threads; ++t) {
-        ts.emplace_back([=]() {
+        ts.emplace_back([&, t]() {
             std::vector<Worker> ws = b->workers;
             size_t lo = n * (size_t)t / (size_t)threads, hi = n * (size_t)(t + 1) / (size_t)threads;
-            for (size_t i = lo; i < hi; ++i) {
-                Decision d = b->pol.select_worker(ws, nullptr, tokens + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), true);
-                out_idx[i] = (int32_t)d.idx;
+            size_t gen = 0;
+            for (size_t s = 0; s < steps; ++s) {
+                const uint32_t* tk = tokens[s % n_batches];
+                const uint64_t* off = offsets[s % n_batches];
+                for (size_t i = lo; i < hi; ++i) {
+                    Decision d = b->pol.select_worker(ws, nullptr, tk + off[i], (size_t)(off[i + 1] - off[i]), true);
+                    out_idx[i] = (int32_t)d.idx;
+                }
+                barrier(gen);
             }
         });
     }

@@ -82,7 +82,7 @@ def lib():
         sig("orc_policy_string_tree", vp, vp, cp)
         sig("orc_policy_select", None, vp, cp, sz, C.c_int, vp, sz, C.c_int, vp, vp, sz)
         sig("orc_policy_select_batch_tokens", C.c_double, vp, vp, vp, sz, vp, vp, vp)
-        sig("orc_policy_select_batch_tokens_mt", C.c_double, vp, vp, vp, sz, vp, C.c_int)
+        sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int)
         _lib = L
     return _lib
 
@@ -427,14 +427,26 @@ class CacheAwarePolicy:
                                 1 if tokens is not None else 0, _ptr(out), _ptr(valid), valid.size)
         return Decision(out, [int(v) for v in valid[: int(out[5])]])
 
+    def select_steps_mt(self, batches, steps, threads):
+        """`steps` batches routed back to back by `threads` persistent host threads (event mode, read-only index).
+        batches: list of (tokens u32, offsets u64[n+1]) with equal n.  → (picks of the last step, seconds)."""
+        toks = [_u32(b[0]) for b in batches]
+        offs = [_u64(b[1]) for b in batches]
+        n = offs[0].size - 1
+        TP = (C.c_void_p * len(batches))(*[t.ctypes.data for t in toks])
+        OP = (C.c_void_p * len(batches))(*[o.ctypes.data for o in offs])
+        idx = np.zeros(n, np.int32)
+        secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads)
+        return idx, secs
+
     def select_batch_tokens(self, tokens, offsets, threads=0):
         tk = _u32(tokens)
         off = _u64(offsets)
         n = off.size - 1
         idx = np.zeros(n, np.int32)
         if threads and threads > 1:
-            secs = lib().orc_policy_select_batch_tokens_mt(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), threads)
-            return idx, None, None, secs
+            i2, secs = self.select_steps_mt([(tk, off)], 1, threads)
+            return i2, None, None, secs
         br = np.zeros(n, np.uint8)
         ma = np.zeros(n, np.uint32)
         secs = lib().orc_policy_select_batch_tokens(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), _ptr(br), _ptr(ma))

@@ -91,6 +91,7 @@ def load():
     sig("smgx_submit_tokens", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)
     sig("smgx_wait", st, vp, u64, pp)
     sig("smgx_select_batch_tokens_device", st, vp, cp, u32, vp, vp, u32, u32, vp, vp, pp)
+    sig("smgx_select_many_tokens_device", st, vp, cp, u32, vp, vp, vp, u32, vp, pp)
     sig("smgx_device_alloc", vp, vp, C.c_size_t, pp)
     sig("smgx_device_free", None, vp, vp)
     sig("smgx_memcpy_h2d", st, vp, vp, vp, C.c_size_t, pp)
@@ -98,6 +99,8 @@ def load():
     sig("smgx_synchronize", st, vp, pp)
     sig("smgx_timer_start", st, vp, u32, pp)
     sig("smgx_timer_stop_ms", st, vp, u32, P(C.c_float), pp)
+    sig("smgx_timer_start_all", st, vp, pp)
+    sig("smgx_timer_stop_all_ms", st, vp, P(C.c_float), pp)
     sig("smgx_kernel_launches", u64, vp)
     sig("smgx_flush_l2", st, vp, pp)
     _lib = L

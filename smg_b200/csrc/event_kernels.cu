@@ -173,24 +173,57 @@ __device__ __forceinline__ void scan_drain(const EventIndexView& v, const uint64
 }
 
 // jump_search_matches (event_tree.rs:659-753).  `ch[0..len)` content hashes (shared memory), len ≥ 1.
-// On return `active` holds the survivors (score = len); drained workers were reported through the sink.
+// On return the survivors (score = len) are returned; drained workers were reported through the sink.
+//
+// The jump destinations 0, J, 2J, …, len-1 do not depend on the data (current_pos always advances to next_pos,
+// :721/:733), so they are probed SPECULATIVELY in parallel — one lane per destination, 32 at a time — and the
+// count-only jump test (:720) is then replayed in order from registers.  Only a failed test costs a second
+// memory round trip (scan_drain).  For len ≤ J+1 (BASELINE config 2: 32 blocks, jump 64) that is exactly the
+// reference's two probes, issued concurrently.
 template <bool W1, class Sink>
 __device__ __forceinline__ uint64_t jump_search(const EventIndexView& v, const uint64_t* ch, int len, int lane, Sink& sink, bool early_exit) {
     PrefixCache pc{-1, 0};
-    Slot s;
-    if (!probe(v, 0, ch[0], s)) return 0;
-    uint64_t active;
-    if (!entry_set<W1>(v, s.state, s.payload, ch, 0, lane, pc, active)) return 0;
-    if (!set_any<W1>(active)) return 0;
-    if (early_exit) { sink.on_event(1, active); return 0; }
+    const uint64_t J = v.jump;
+    const int last = len - 1;
+    const int m = last == 0 ? 0 : (int)(((uint64_t)last + J - 1) / J);  // destinations after position 0
+    uint64_t active = 0;
     int cur = 0;
-    while (cur < len - 1 && set_any<W1>(active)) {
-        int next = ((uint32_t)(len - 1 - cur) > v.jump) ? cur + (int)v.jump : len - 1;
-        uint32_t count = 0;
-        uint64_t ws;
-        if (probe(v, (uint32_t)next, ch[next], s) && entry_set<W1>(v, s.state, s.payload, ch, next, lane, pc, ws)) count = set_popc<W1>(ws);
-        if (count != set_popc<W1>(active)) scan_drain<W1>(v, ch, cur + 1, next, lane, active, sink, pc);
-        cur = next;
+    for (int base = 0; base <= m; base += 32) {
+        const int di = base + lane;
+        const bool in_range = di <= m;
+        int dpos = 0;
+        if (in_range) { uint64_t q = (uint64_t)di * J; dpos = q < (uint64_t)last ? (int)q : last; }
+        Slot my{0, 0, SLOT_EMPTY, 0, 0};
+        bool found = false;
+        uint32_t cnt = 0;
+        if (in_range) {
+            found = probe(v, (uint32_t)dpos, ch[dpos], my);
+            if (!W1 && found && my.state == SLOT_SINGLE) cnt = lane_popc_set<W1>(v, my.payload);
+        }
+        const int nloc = (m - base + 1) < 32 ? (m - base + 1) : 32;
+        for (int k = 0; k < nloc; ++k) {
+            const int kd = base + k;
+            int kpos;
+            { uint64_t q = (uint64_t)kd * J; kpos = q < (uint64_t)last ? (int)q : last; }
+            const bool kfound = __shfl_sync(FULL, (int)found, k) != 0;
+            const uint32_t kstate = __shfl_sync(FULL, my.state, k);
+            const uint64_t kpayload = shfl64(my.payload, k);
+            if (kd == 0) {
+                if (!kfound) return 0;
+                if (!entry_set<W1>(v, kstate, kpayload, ch, 0, lane, pc, active)) return 0;
+                if (!set_any<W1>(active)) return 0;
+                if (early_exit) { sink.on_event(1, active); return 0; }
+                continue;
+            }
+            uint32_t count = 0;  // count_workers_at(kpos) (:555-574)
+            if (kfound) {
+                if (kstate == SLOT_SINGLE) count = W1 ? (uint32_t)__popcll(kpayload) : __shfl_sync(FULL, cnt, k);
+                else { uint64_t ws; if (entry_set<W1>(v, kstate, kpayload, ch, kpos, lane, pc, ws)) count = set_popc<W1>(ws); }
+            }
+            if (count != set_popc<W1>(active)) scan_drain<W1>(v, ch, cur + 1, kpos, lane, active, sink, pc);
+            cur = kpos;
+            if (!set_any<W1>(active)) return 0;
+        }
     }
     return active;
 }
@@ -219,24 +252,35 @@ __device__ __forceinline__ void hash_blocks(const uint32_t* __restrict__ tok, ui
 }
 
 // ---- K3: max_by_key((score, Reverse(load), Reverse(tree_size))) with LAST max = highest slice index ---------
+// Per-worker scalars of the fleet snapshot.  W1 (≤ 64 interned workers): lane l keeps workers l and l+32 in
+// registers, so the final pick costs shuffles only; otherwise they are read from the (L1/L2-resident) id-space arrays.
+struct FleetRegs { int32_t sl0, sl1; uint64_t ld0, ld1, ts0, ts1; };
+
 template <bool W1>
-__device__ __forceinline__ int32_t arg_best(const EventIndexView& v, const FleetView& f, uint64_t winset, int lane) {
+__device__ __forceinline__ int32_t arg_best(const EventIndexView& v, const FleetView& f, const FleetRegs& fr, uint64_t winset, int lane) {
     bool have = false;
     uint64_t bl = 0, bt = 0;
     int32_t bs = -1;
-    auto consider = [&](uint32_t id) {
-        int32_t sl = f.slice_of_id[id];
-        uint64_t ld = f.load_of_id[id], ts = v.tree_sizes[id];
+    auto consider = [&](int32_t sl, uint64_t ld, uint64_t ts) {
         bool better = !have || ld < bl || (ld == bl && (ts < bt || (ts == bt && sl > bs)));
         if (better) { have = true; bl = ld; bt = ts; bs = sl; }
     };
     if (W1) {
-        if (__popcll(winset) == 1) return f.slice_of_id[__ffsll((long long)winset) - 1];
-        if ((winset >> lane) & 1) consider((uint32_t)lane);
-        if ((winset >> (lane + 32)) & 1) consider((uint32_t)lane + 32);
+        if (__popcll(winset) == 1) {
+            int id = __ffsll((long long)winset) - 1;
+            int32_t a = __shfl_sync(FULL, fr.sl0, id & 31), b = __shfl_sync(FULL, fr.sl1, id & 31);
+            return id < 32 ? a : b;
+        }
+        if ((winset >> lane) & 1) consider(fr.sl0, fr.ld0, fr.ts0);
+        if ((winset >> (lane + 32)) & 1) consider(fr.sl1, fr.ld1, fr.ts1);
     } else {
         uint64_t w = winset;
-        while (w) { int b = __ffsll((long long)w) - 1; w &= w - 1; consider((uint32_t)(lane * 64 + b)); }
+        while (w) {
+            int b = __ffsll((long long)w) - 1;
+            w &= w - 1;
+            uint32_t id = (uint32_t)(lane * 64 + b);
+            consider(f.slice_of_id[id], f.load_of_id[id], v.tree_sizes[id]);
+        }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -249,6 +293,68 @@ __device__ __forceinline__ int32_t arg_best(const EventIndexView& v, const Fleet
     return bs;
 }
 
+// One request, one warp: the whole pick.
+template <bool W1>
+__device__ __forceinline__ void select_one(const EventIndexView& v, const FleetView& f, const FleetDerived& fd, const FleetRegs& fr, uint64_t elig,
+                                           const uint32_t* __restrict__ tokens, const uint32_t* __restrict__ offsets, uint32_t r,
+                                           uint32_t block_size, uint32_t max_blocks, uint64_t* ch, int lane, int32_t* out_idx,
+                                           smgx_decision_info* out_info, uint32_t* err_flag) {
+    const uint32_t off = offsets[r], ntok = offsets[r + 1] - off;
+    int32_t out = -1;
+    uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+    if (fd.n_healthy == 0) {
+        // None
+    } else if (fd.imbalanced) {
+        out = fd.min_load_idx;
+        branch = SMGX_BR_IMBALANCED_MIN_LOAD;
+    } else {
+        const uint32_t nb = block_size ? ntok / block_size : 0;
+        if (nb > max_blocks) {
+            if (lane == 0) atomicExch(err_flag, 1u);
+            branch = 255;
+        } else {
+            uint64_t winset = 0;
+            uint32_t score = 0;
+            if (nb > 0 && v.n_workers > 0) {
+                hash_blocks(tokens + off, nb, block_size, ch, lane);
+                __syncwarp();
+                SelectSink<W1> sink{elig, 0, 0};
+                uint64_t surv = jump_search<W1>(v, ch, (int)nb, lane, sink, false) & elig;
+                if (set_any<W1>(surv)) { winset = surv; score = nb; }
+                else { winset = sink.last; score = sink.last_score; }
+                __syncwarp();
+            }
+            if (set_any<W1>(winset)) {
+                out = arg_best<W1>(v, f, fr, winset, lane);
+                branch = SMGX_BR_EVENT_OVERLAP;
+                matched = score;
+            } else {
+                out = fd.min_load_idx;
+                branch = SMGX_BR_EVENT_MIN_LOAD;
+            }
+        }
+    }
+    if (lane == 0) {
+        out_idx[r] = out;
+        if (out_info) {
+            smgx_decision_info di;
+            di.matched = matched; di.input = ntok; di.branch = (uint8_t)branch;
+            di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+            out_info[r] = di;
+        }
+    }
+}
+
+template <bool W1>
+__device__ __forceinline__ FleetRegs load_fleet_regs(const EventIndexView& v, const FleetView& f, int lane) {
+    FleetRegs fr{-1, -1, 0, 0, 0, 0};
+    if (W1) {
+        if ((uint32_t)lane < v.n_workers) { fr.sl0 = f.slice_of_id[lane]; fr.ld0 = f.load_of_id[lane]; fr.ts0 = v.tree_sizes[lane]; }
+        if ((uint32_t)lane + 32 < v.n_workers) { fr.sl1 = f.slice_of_id[lane + 32]; fr.ld1 = f.load_of_id[lane + 32]; fr.ts1 = v.tree_sizes[lane + 32]; }
+    }
+    return fr;
+}
+
 template <bool W1>
 __global__ void __launch_bounds__(256) event_select_kernel(EventIndexView v, FleetView f, SelectArgs a) {
     extern __shared__ uint64_t smem_ch[];
@@ -256,53 +362,23 @@ __global__ void __launch_bounds__(256) event_select_kernel(EventIndexView v, Fle
     uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
     const FleetDerived fd = *f.derived;
     const uint64_t elig = W1 ? f.elig[0] : ((uint32_t)lane < v.words ? f.elig[lane] : 0ULL);
+    const FleetRegs fr = load_fleet_regs<W1>(v, f, lane);
+    for (uint32_t r = blockIdx.x * wpc + wic; r < a.n; r += gridDim.x * wpc)
+        select_one<W1>(v, f, fd, fr, elig, a.tokens, a.offsets, r, a.block_size, a.max_blocks, ch, lane, a.out_idx, a.out_info, a.err_flag);
+}
 
-    for (uint32_t r = blockIdx.x * wpc + wic; r < a.n; r += gridDim.x * wpc) {
-        const uint32_t off = a.offsets[r], ntok = a.offsets[r + 1] - off;
-        int32_t out = -1;
-        uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
-        if (fd.n_healthy == 0) {
-            // None
-        } else if (fd.imbalanced) {
-            out = fd.min_load_idx;
-            branch = SMGX_BR_IMBALANCED_MIN_LOAD;
-        } else {
-            const uint32_t nb = a.block_size ? ntok / a.block_size : 0;
-            if (nb > a.max_blocks) {
-                if (lane == 0) atomicExch(a.err_flag, 1u);
-                branch = 255;
-            } else {
-                uint64_t winset = 0;
-                uint32_t score = 0;
-                if (nb > 0 && v.n_workers > 0) {
-                    hash_blocks(a.tokens + off, nb, a.block_size, ch, lane);
-                    __syncwarp();
-                    SelectSink<W1> sink{elig, 0, 0};
-                    uint64_t surv = jump_search<W1>(v, ch, (int)nb, lane, sink, false) & elig;
-                    if (set_any<W1>(surv)) { winset = surv; score = nb; }
-                    else { winset = sink.last; score = sink.last_score; }
-                    __syncwarp();
-                }
-                if (set_any<W1>(winset)) {
-                    out = arg_best<W1>(v, f, winset, lane);
-                    branch = SMGX_BR_EVENT_OVERLAP;
-                    matched = score;
-                } else {
-                    out = fd.min_load_idx;
-                    branch = SMGX_BR_EVENT_MIN_LOAD;
-                }
-            }
-        }
-        if (lane == 0) {
-            a.out_idx[r] = out;
-            if (a.out_info) {
-                smgx_decision_info di;
-                di.matched = matched; di.input = ntok; di.branch = (uint8_t)branch;
-                di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
-                a.out_info[r] = di;
-            }
-        }
-    }
+// blockIdx.y = batch
+template <bool W1>
+__global__ void __launch_bounds__(256) event_select_multi_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    extern __shared__ uint64_t smem_ch[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
+    const FleetDerived fd = *f.derived;
+    const uint64_t elig = W1 ? f.elig[0] : ((uint32_t)lane < v.words ? f.elig[lane] : 0ULL);
+    const FleetRegs fr = load_fleet_regs<W1>(v, f, lane);
+    const BatchDesc& b = a.b[blockIdx.y];
+    for (uint32_t r = blockIdx.x * wpc + wic; r < b.n; r += gridDim.x * wpc)
+        select_one<W1>(v, f, fd, fr, elig, b.tokens, b.offsets, r, a.block_size, a.max_blocks, ch, lane, b.out_idx, b.out_info, a.err_flag);
 }
 
 template <bool W1>
@@ -410,6 +486,23 @@ void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const
     auto k = ix.words == 1 ? event_select_kernel<true> : event_select_kernel<false>;
     if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, wpc * 32, smem, stream>>>(ix, fleet, a);
+    SMGX_CUDA(cudaGetLastError());
+}
+
+void launch_event_select_multi(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.count == 0) return;
+    size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
+    int wpc = 8;
+    while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
+    size_t smem = per_warp * wpc;
+    if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "request too long for the per-warp scratch (max_tokens_per_request)");
+    uint32_t max_n = 0;
+    for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
+    unsigned ctas_x = std::max(1u, (max_n + wpc - 1) / wpc);
+    (void)sm_count;
+    auto k = ix.words == 1 ? event_select_multi_kernel<true> : event_select_multi_kernel<false>;
+    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<dim3(ctas_x, a.count), wpc * 32, smem, stream>>>(ix, fleet, a);
     SMGX_CUDA(cudaGetLastError());
 }
 

@@ -52,6 +52,26 @@ struct SelectArgs {
 };
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const SelectArgs& a, int sm_count, cudaStream_t stream);
 
+// Several batches in ONE launch (blockIdx.y = batch): amortises the launch and keeps every SM full when the host
+// batcher has more than one batch queued.  Descriptors travel in the kernel parameter block (no extra copy).
+constexpr int kMaxMultiBatches = 32;
+struct BatchDesc {
+    const uint32_t* tokens;
+    const uint32_t* offsets;
+    int32_t* out_idx;
+    smgx_decision_info* out_info;
+    uint32_t n;
+    uint32_t pad;
+};
+struct MultiArgs {
+    BatchDesc b[kMaxMultiBatches];
+    uint32_t count;
+    uint32_t block_size;
+    uint32_t max_blocks;
+    uint32_t* err_flag;
+};
+void launch_event_select_multi(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream);
+
 // PositionalIndexer::find_matches on precomputed content hashes; one warp, one query.
 void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uint32_t n, bool early_exit, uint32_t* d_scores,
                          cudaStream_t stream);

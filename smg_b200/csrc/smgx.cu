@@ -617,6 +617,45 @@ smgx_status smgx_select_batch_tokens_device(smgx_policy* p, const char* model_ke
     });
 }
 
+smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
+                                           const uint32_t* const* d_offsets, const uint32_t* n, uint32_t max_request_tokens,
+                                           int32_t* const* d_out_worker_idx, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n_batches == 0 || (d_tokens && d_offsets && n && d_out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
+        if (!P.has_event_indexer(m))
+            throw Error(SMGX_UNKNOWN_ERROR, "model has no populated KV-event indexer (token-tree mode is not part of this build yet)");
+        EventIndexView ixv;
+        FleetView fv;
+        P.sync_state(m, &ixv, &fv);
+        uint32_t bs = P.block_size_for(m);
+        // up to kMaxMultiBatches batches per launch (blockIdx.y = batch); chunks alternate over the stream lanes
+        uint32_t chunk_no = 0;
+        for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxMultiBatches, ++chunk_no) {
+            MultiArgs a;
+            a.count = std::min<uint32_t>(kMaxMultiBatches, n_batches - j0);
+            for (uint32_t k = 0; k < a.count; ++k) {
+                a.b[k].tokens = d_tokens[j0 + k]; a.b[k].offsets = d_offsets[j0 + k]; a.b[k].out_idx = d_out_worker_idx[j0 + k];
+                a.b[k].out_info = nullptr; a.b[k].n = n[j0 + k]; a.b[k].pad = 0;
+            }
+            a.block_size = bs;
+            a.max_blocks = bs ? std::max<uint32_t>(cap / bs, 1) : 1;
+            a.err_flag = P.d_err.as<uint32_t>();
+            Lane& lane = P.lanes[chunk_no % P.lanes.size()];
+            launch_event_select_multi(ixv, fv, a, P.sm_count, lane.stream);
+            ++P.launches;
+            SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
+            lane.has_done = true;
+        }
+        return SMGX_SUCCESS;
+    });
+}
+
 void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err) {
     void* out = nullptr;
     guard(err, [&]() {
@@ -678,6 +717,31 @@ smgx_status smgx_timer_stop_ms(smgx_policy* p, uint32_t lane, float* out_ms, cha
         SMGX_CUDA(cudaEventRecord(l.t1, l.stream));
         SMGX_CUDA(cudaEventSynchronize(l.t1));
         SMGX_CUDA(cudaEventElapsedTime(out_ms, l.t0, l.t1));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_timer_start_all(smgx_policy* p, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_CUDA(cudaEventRecord(P.lanes[0].t0, P.lanes[0].stream));
+        for (size_t i = 1; i < P.lanes.size(); ++i) SMGX_CUDA(cudaStreamWaitEvent(P.lanes[i].stream, P.lanes[0].t0, 0));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_ms);
+        Policy& P = p->impl;
+        P.use_device();
+        for (size_t i = 1; i < P.lanes.size(); ++i) {
+            SMGX_CUDA(cudaEventRecord(P.lanes[i].t1, P.lanes[i].stream));
+            SMGX_CUDA(cudaStreamWaitEvent(P.lanes[0].stream, P.lanes[i].t1, 0));
+        }
+        SMGX_CUDA(cudaEventRecord(P.lanes[0].t1, P.lanes[0].stream));
+        SMGX_CUDA(cudaEventSynchronize(P.lanes[0].t1));
+        SMGX_CUDA(cudaEventElapsedTime(out_ms, P.lanes[0].t0, P.lanes[0].t1));
         return SMGX_SUCCESS;
     });
 }

@@ -270,3 +270,50 @@ def test_index_updates_between_batches_are_visible():
     ix.apply_cleared(w2)
     with pytest.raises(Exception, match="no populated KV-event indexer|token-tree"):
         _sel(pol, ws, [1, 2, 3, 4])                         # empty indexer → falls through to the token tree (:723-729)
+
+
+def test_multi_batch_device_path_matches_oracle():
+    """smgx_select_many_tokens_device (several batches per launch, blockIdx.y = batch) — same picks as the oracle."""
+    import ctypes as C
+    from smg_b200 import CacheAwareConfig, CacheAwarePolicy, _lib
+    W, T, bs, B, NB = 64, 512, 16, 300, 37          # 37 batches → two launches (32 + 5), ragged last sizes
+    cfg = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=1.5, block_size=bs)
+    urls = synth.worker_urls(W)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **cfg), max_tokens_per_request=T)
+    ws = _workers(urls)
+    pol.init_workers(ws)
+    mon = pol.kv_event_monitor(bs)
+    ix = mon.create_indexer("unknown", 64)
+    pol.set_kv_event_monitor(mon)
+    op, oix = _oracle_policy(urls, cfg, 64, bs)
+    seqs = synth.gen_sequences(300, T, 9)
+    for u in urls:
+        assert ix.intern_worker(u) == oix.intern_worker(u)
+    for s_ in range(len(seqs)):
+        hs = orc.compute_request_content_hashes(seqs[s_], bs)
+        blocks = [(s_ * 100 + i + 1, h) for i, h in enumerate(hs)]
+        ix.apply_stored(s_ % W, blocks)
+        oix.apply_stored(s_ % W, blocks)
+    loads = synth.poisson_loads(W, 8, 9)
+    for w, l in zip(ws, loads):
+        w.set_load(int(l))
+    op.set_state(loads, [1] * W, [1] * W)
+    model = pol._push_fleet(ws)
+    h, L = pol._h, _lib.load()
+    err = _lib.new_err()
+    d_tok, d_off, d_out, ns, host = [], [], [], [], []
+    for j in range(NB):
+        n = B - j                                     # different n per batch
+        tokens, offsets = synth.ragged(synth.gen_queries(seqs, n, 100 + j))
+        host.append((tokens, offsets))
+        dt = L.smgx_device_alloc(h.p, tokens.nbytes, C.byref(err)); h.call("smgx_memcpy_h2d", dt, tokens.ctypes.data_as(C.c_void_p), tokens.nbytes)
+        do = L.smgx_device_alloc(h.p, offsets.nbytes, C.byref(err)); h.call("smgx_memcpy_h2d", do, offsets.ctypes.data_as(C.c_void_p), offsets.nbytes)
+        d_tok.append(dt); d_off.append(do); d_out.append(L.smgx_device_alloc(h.p, n * 4, C.byref(err))); ns.append(n)
+    TOK = (C.c_void_p * NB)(*d_tok); OFF = (C.c_void_p * NB)(*d_off); OUT = (C.c_void_p * NB)(*d_out); NS = (C.c_uint32 * NB)(*ns)
+    h.call("smgx_select_many_tokens_device", model, NB, TOK, OFF, NS, T, OUT)
+    h.call("smgx_synchronize")
+    for j in range(NB):
+        got = np.zeros(ns[j], np.int32)
+        h.call("smgx_memcpy_d2h", got.ctypes.data_as(C.c_void_p), d_out[j], ns[j] * 4)
+        want, _, _, _ = op.select_batch_tokens(host[j][0], host[j][1].astype(np.uint64))
+        assert np.array_equal(got, want), j
