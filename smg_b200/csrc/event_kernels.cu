@@ -228,157 +228,270 @@ __device__ __forceinline__ uint64_t jump_search(const EventIndexView& v, const u
     return active;
 }
 
-// ---- K2b part 1: content hashes of a request's blocks into shared memory -----------------------------------
-__device__ __forceinline__ void hash_blocks(const uint32_t* __restrict__ tok, uint32_t nb, uint32_t bs, uint64_t* ch, int lane) {
-    for (uint32_t b = lane; b < nb; b += 32) {
-        const uint32_t* p = tok + (size_t)b * bs;
-        uint64_t h;
-        if (bs == 16) {
-            uint32_t w[16];
-            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-                const uint4* q = reinterpret_cast<const uint4*>(p);
+// ---- K2b part 1: content hashes — a pure streaming kernel ----------------------------------------------------
+// One THREAD per block of tokens (64 B at block_size 16: 4×LDG.128, consecutive threads → consecutive blocks, a warp
+// streams 2 KB).  Hashes land in a scratch laid out [request][max_blocks] that the search kernel reads back from L2.
+// HBM-bound by construction: 4·T bytes in, 8·P bytes out per request, ~110 integer instructions per 64 B.
+template <int BS>
+__device__ __forceinline__ uint64_t hash_block(const uint32_t* __restrict__ p, uint32_t bs) {
+    if (BS == 16) {
+        uint32_t w[16];
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { uint4 t = __ldg(q + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) w[i] = __ldg(p + i);
-            }
-            h = xxh3_16words(w, kSeed);
+            for (int i = 0; i < 4; ++i) { uint4 t = __ldg(q + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
         } else {
-            h = xxh3_words(p, bs, kSeed);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = __ldg(p + i);
         }
-        ch[b] = h;
+        return xxh3_16words(w, kSeed);
+    }
+    return xxh3_words(p, bs, kSeed);
+}
+
+template <int BS>   // BS = 16: the common block size, fully unrolled; BS = 0: any run-time block size
+__global__ void __launch_bounds__(256) hash_blocks_kernel(const __grid_constant__ MultiArgs a) {
+    const BatchDesc& b = a.b[blockIdx.y];
+    const uint64_t total = (uint64_t)b.n * a.max_blocks;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / a.max_blocks), blk = (uint32_t)(t % a.max_blocks);
+        const uint32_t off = __ldg(b.offsets + r), ntok = __ldg(b.offsets + r + 1) - off;
+        const uint32_t bs = BS ? (uint32_t)BS : a.block_size;
+        const uint32_t nb = ntok / bs;
+        if (blk < nb) a.hashes[((uint64_t)b.hash_base + r) * a.max_blocks + blk] = hash_block<BS>(b.tokens + off + (size_t)blk * bs, bs);
     }
 }
 
 // ---- K3: max_by_key((score, Reverse(load), Reverse(tree_size))) with LAST max = highest slice index ---------
-// Per-worker scalars of the fleet snapshot.  W1 (≤ 64 interned workers): lane l keeps workers l and l+32 in
-// registers, so the final pick costs shuffles only; otherwise they are read from the (L1/L2-resident) id-space arrays.
-struct FleetRegs { int32_t sl0, sl1; uint64_t ld0, ld1, ts0, ts1; };
+struct Cand {
+    bool have; uint64_t ld, ts; int32_t sl;
+    __device__ __forceinline__ void consider(int32_t s, uint64_t l, uint64_t t) {
+        bool better = !have || l < ld || (l == ld && (t < ts || (t == ts && s > sl)));
+        if (better) { have = true; ld = l; ts = t; sl = s; }
+    }
+};
 
-template <bool W1>
-__device__ __forceinline__ int32_t arg_best(const EventIndexView& v, const FleetView& f, const FleetRegs& fr, uint64_t winset, int lane) {
-    bool have = false;
-    uint64_t bl = 0, bt = 0;
-    int32_t bs = -1;
-    auto consider = [&](int32_t sl, uint64_t ld, uint64_t ts) {
-        bool better = !have || ld < bl || (ld == bl && (ts < bt || (ts == bt && sl > bs)));
-        if (better) { have = true; bl = ld; bt = ts; bs = sl; }
-    };
-    if (W1) {
-        if (__popcll(winset) == 1) {
-            int id = __ffsll((long long)winset) - 1;
-            int32_t a = __shfl_sync(FULL, fr.sl0, id & 31), b = __shfl_sync(FULL, fr.sl1, id & 31);
-            return id < 32 ? a : b;
+__device__ __forceinline__ void write_pick(const BatchDesc& b, uint32_t r, int32_t out, uint32_t branch, uint32_t matched, uint32_t ntok) {
+    b.out_idx[r] = out;
+    if (b.out_info) {
+        smgx_decision_info di;
+        di.matched = matched; di.input = ntok; di.branch = (uint8_t)branch;
+        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        b.out_info[r] = di;
+    }
+}
+
+// ---- search + pick, fleets of ≤ 64 interned workers: ONE THREAD per request ---------------------------------
+// Worker sets are single u64 words held in the slot itself, so the whole jump search is scalar code: two
+// independent slot loads up front (position 0 and the first jump destination), the count test, and only on a
+// failed test the linear drain (4 probes in flight at a time).  ~30 warp-instructions per request on the common
+// path; the kernel is a few microseconds for 10^5 requests and disappears next to the hash stream.
+struct ThreadSink {
+    uint64_t elig, last; uint32_t last_score;
+    __device__ __forceinline__ void on_event(uint32_t pos, uint64_t set) { uint64_t e = set & elig; if (e) { last = e; last_score = pos; } }
+};
+__device__ __forceinline__ bool finish_probe(const EventIndexView& v, uint32_t pos, uint64_t content, uint32_t h, Slot& s) {
+#pragma unroll 1
+    for (;;) {
+        if (s.state == SLOT_EMPTY) return false;
+        if (s.state != SLOT_TOMB && s.content == content && s.pos == pos) return true;
+        h = (h + 1) & v.mask;
+        s = load_slot(v.slots + h);
+    }
+}
+__device__ __forceinline__ bool t_entry_set(const EventIndexView& v, const Slot& s, const uint64_t* ch, int p, PrefixCache& pc, uint64_t& set) {
+    if (s.state == SLOT_SINGLE) { set = s.payload; return true; }
+    uint64_t want = prefix_at(ch, p, pc);
+    for (uint32_t i = (uint32_t)s.payload; i != kNil;) {
+        MultiNode nd = load_node(v.multi + i);
+        if (nd.prefix == want) { set = nd.payload; return true; }
+        i = nd.next;
+    }
+    return false;
+}
+// The scalar part of jump_search_matches (event_tree.rs:659-753): everything except linear_scan_drain.  A thread runs
+// until it is finished or until a count test fails (:720) — then it parks with the range to drain, and the WARP drains
+// it cooperatively (scan_drain<true>: 32 positions probed in parallel) before the thread resumes.
+struct ThreadSearch {
+    const uint64_t* ch;
+    uint64_t active, last;
+    uint32_t last_score;
+    int len, cur, lo, hi;
+    bool done, need;
+};
+
+__global__ void __launch_bounds__(128) event_search_thread_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    __shared__ int32_t s_slice[64];
+    __shared__ uint64_t s_load[64], s_ts[64];
+    if (threadIdx.x < 64) {
+        bool ok = threadIdx.x < v.n_workers;
+        s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const BatchDesc& b = a.b[blockIdx.y];
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = r < b.n;
+    const FleetDerived fd = *f.derived;
+    const uint64_t elig = f.elig[0];
+    const uint64_t J = v.jump;
+
+    uint32_t ntok = 0, nb = 0, branch = SMGX_BR_NO_HEALTHY;
+    int32_t out = -1;
+    ThreadSearch st{nullptr, 0, 0, 0, 0, 0, 0, 0, true, false};
+    // speculative second probe (first jump destination), consumed by the first count test
+    Slot s1{0, 0, SLOT_EMPTY, 0, 0};
+    uint64_t c1 = 0;
+    uint32_t h1 = 0;
+    int next0 = 0;
+    bool have1 = false;
+    PrefixCache pc{-1, 0};
+    bool searching = false;
+    if (valid) {
+        const uint32_t off = __ldg(b.offsets + r);
+        ntok = __ldg(b.offsets + r + 1) - off;
+        if (fd.n_healthy == 0) {
+        } else if (fd.imbalanced) {
+            out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
+        } else {
+            nb = a.block_size ? ntok / a.block_size : 0;
+            if (nb > a.max_blocks) { atomicExch(a.err_flag, 1u); branch = 255; }
+            else {
+                branch = SMGX_BR_EVENT_MIN_LOAD;   // until an overlap is found
+                if (nb > 0 && v.n_workers > 0) {
+                    st.ch = a.hashes + ((uint64_t)b.hash_base + r) * a.max_blocks;
+                    st.len = (int)nb;
+                    const int last = st.len - 1;
+                    next0 = last == 0 ? 0 : ((uint64_t)last > J ? (int)J : last);
+                    const uint64_t c0 = st.ch[0];
+                    c1 = st.ch[next0];
+                    const uint32_t h0 = slot_hash(0, c0) & v.mask;
+                    h1 = slot_hash((uint32_t)next0, c1) & v.mask;
+                    Slot s0 = load_slot(v.slots + h0);
+                    s1 = load_slot(v.slots + h1);          // both probes in flight together
+                    have1 = last > 0;
+                    if (finish_probe(v, 0, c0, h0, s0) && t_entry_set(v, s0, st.ch, 0, pc, st.active) && st.active) {
+                        st.done = false;
+                        searching = true;
+                    }
+                }
+            }
         }
-        if ((winset >> lane) & 1) consider(fr.sl0, fr.ld0, fr.ts0);
-        if ((winset >> (lane + 32)) & 1) consider(fr.sl1, fr.ld1, fr.ts1);
-    } else {
-        uint64_t w = winset;
-        while (w) {
-            int b = __ffsll((long long)w) - 1;
-            w &= w - 1;
-            uint32_t id = (uint32_t)(lane * 64 + b);
-            consider(f.slice_of_id[id], f.load_of_id[id], v.tree_sizes[id]);
+    }
+    for (;;) {
+        if (!st.done && !st.need) {
+            const int last = st.len - 1;
+            while (st.cur < last && st.active) {
+                const int next = ((uint64_t)(last - st.cur) > J) ? st.cur + (int)J : last;
+                Slot s;
+                bool fnd;
+                if (have1 && next == next0) { fnd = finish_probe(v, (uint32_t)next, c1, h1, s1); s = s1; have1 = false; }
+                else fnd = probe(v, (uint32_t)next, st.ch[next], s);
+                uint32_t count = 0;
+                uint64_t ws;
+                if (fnd && t_entry_set(v, s, st.ch, next, pc, ws)) count = (uint32_t)__popcll(ws);
+                if (count != (uint32_t)__popcll(st.active)) { st.need = true; st.lo = st.cur + 1; st.hi = next; break; }
+                st.cur = next;
+            }
+            if (!st.need) st.done = true;
         }
+        unsigned m = __ballot_sync(FULL, st.need);
+        if (!m) {
+            if (__all_sync(FULL, st.done)) break;
+            continue;
+        }
+        while (m) {
+            const int L = __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint64_t* lch = reinterpret_cast<const uint64_t*>(shfl64(reinterpret_cast<uint64_t>(st.ch), L));
+            const int llo = __shfl_sync(FULL, st.lo, L), lhi = __shfl_sync(FULL, st.hi, L);
+            uint64_t lact = shfl64(st.active, L);
+            SelectSink<true> sk{elig, 0, 0};
+            PrefixCache wpc{-1, 0};
+            scan_drain<true>(v, lch, llo, lhi, lane, lact, sk, wpc);
+            if (lane == L) {
+                st.active = lact;
+                if (sk.last) { st.last = sk.last; st.last_score = sk.last_score; }
+                st.need = false;
+                st.cur = st.hi;
+            }
+        }
+    }
+    if (!valid) return;
+    uint32_t matched = 0;
+    if (searching) {
+        uint64_t winset = st.active & elig;
+        uint32_t score = nb;
+        if (!winset) { winset = st.last; score = st.last_score; }
+        if (winset) {
+            Cand c{false, 0, 0, -1};
+            uint64_t w = winset;
+            while (w) { int id = __ffsll((long long)w) - 1; w &= w - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
+            out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
+        }
+    }
+    if (branch == SMGX_BR_EVENT_MIN_LOAD) out = fd.min_load_idx;
+    write_pick(b, r, out, branch, matched, ntok);
+}
+
+// ---- search + pick, wider fleets (65..2048 interned workers): one WARP per request, one u64 set word per lane ----
+__device__ __forceinline__ int32_t warp_arg_best(const EventIndexView& v, const FleetView& f, uint64_t winset, int lane) {
+    Cand c{false, 0, 0, -1};
+    uint64_t w = winset;
+    while (w) {
+        int bit = __ffsll((long long)w) - 1;
+        w &= w - 1;
+        uint32_t id = (uint32_t)(lane * 64 + bit);
+        c.consider(f.slice_of_id[id], f.load_of_id[id], v.tree_sizes[id]);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
-        bool oh = __shfl_xor_sync(FULL, (int)have, d) != 0;
-        uint64_t ol = shfl64_xor(bl, d), ot = shfl64_xor(bt, d);
-        int32_t os = __shfl_xor_sync(FULL, bs, d);
-        bool better = oh && (!have || ol < bl || (ol == bl && (ot < bt || (ot == bt && os > bs))));
-        if (better) { have = true; bl = ol; bt = ot; bs = os; }
+        bool oh = __shfl_xor_sync(FULL, (int)c.have, d) != 0;
+        uint64_t ol = shfl64_xor(c.ld, d), ot = shfl64_xor(c.ts, d);
+        int32_t os = __shfl_xor_sync(FULL, c.sl, d);
+        if (oh) c.consider(os, ol, ot);
     }
-    return bs;
+    return c.sl;
 }
 
-// One request, one warp: the whole pick.
-template <bool W1>
-__device__ __forceinline__ void select_one(const EventIndexView& v, const FleetView& f, const FleetDerived& fd, const FleetRegs& fr, uint64_t elig,
-                                           const uint32_t* __restrict__ tokens, const uint32_t* __restrict__ offsets, uint32_t r,
-                                           uint32_t block_size, uint32_t max_blocks, uint64_t* ch, int lane, int32_t* out_idx,
-                                           smgx_decision_info* out_info, uint32_t* err_flag) {
-    const uint32_t off = offsets[r], ntok = offsets[r + 1] - off;
-    int32_t out = -1;
-    uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
-    if (fd.n_healthy == 0) {
-        // None
-    } else if (fd.imbalanced) {
-        out = fd.min_load_idx;
-        branch = SMGX_BR_IMBALANCED_MIN_LOAD;
-    } else {
-        const uint32_t nb = block_size ? ntok / block_size : 0;
-        if (nb > max_blocks) {
-            if (lane == 0) atomicExch(err_flag, 1u);
-            branch = 255;
-        } else {
-            uint64_t winset = 0;
-            uint32_t score = 0;
-            if (nb > 0 && v.n_workers > 0) {
-                hash_blocks(tokens + off, nb, block_size, ch, lane);
-                __syncwarp();
-                SelectSink<W1> sink{elig, 0, 0};
-                uint64_t surv = jump_search<W1>(v, ch, (int)nb, lane, sink, false) & elig;
-                if (set_any<W1>(surv)) { winset = surv; score = nb; }
-                else { winset = sink.last; score = sink.last_score; }
-                __syncwarp();
-            }
-            if (set_any<W1>(winset)) {
-                out = arg_best<W1>(v, f, fr, winset, lane);
-                branch = SMGX_BR_EVENT_OVERLAP;
-                matched = score;
-            } else {
-                out = fd.min_load_idx;
-                branch = SMGX_BR_EVENT_MIN_LOAD;
-            }
-        }
-    }
-    if (lane == 0) {
-        out_idx[r] = out;
-        if (out_info) {
-            smgx_decision_info di;
-            di.matched = matched; di.input = ntok; di.branch = (uint8_t)branch;
-            di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
-            out_info[r] = di;
-        }
-    }
-}
-
-template <bool W1>
-__device__ __forceinline__ FleetRegs load_fleet_regs(const EventIndexView& v, const FleetView& f, int lane) {
-    FleetRegs fr{-1, -1, 0, 0, 0, 0};
-    if (W1) {
-        if ((uint32_t)lane < v.n_workers) { fr.sl0 = f.slice_of_id[lane]; fr.ld0 = f.load_of_id[lane]; fr.ts0 = v.tree_sizes[lane]; }
-        if ((uint32_t)lane + 32 < v.n_workers) { fr.sl1 = f.slice_of_id[lane + 32]; fr.ld1 = f.load_of_id[lane + 32]; fr.ts1 = v.tree_sizes[lane + 32]; }
-    }
-    return fr;
-}
-
-template <bool W1>
-__global__ void __launch_bounds__(256) event_select_kernel(EventIndexView v, FleetView f, SelectArgs a) {
+__global__ void __launch_bounds__(256) event_search_warp_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
     extern __shared__ uint64_t smem_ch[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
     const FleetDerived fd = *f.derived;
-    const uint64_t elig = W1 ? f.elig[0] : ((uint32_t)lane < v.words ? f.elig[lane] : 0ULL);
-    const FleetRegs fr = load_fleet_regs<W1>(v, f, lane);
-    for (uint32_t r = blockIdx.x * wpc + wic; r < a.n; r += gridDim.x * wpc)
-        select_one<W1>(v, f, fd, fr, elig, a.tokens, a.offsets, r, a.block_size, a.max_blocks, ch, lane, a.out_idx, a.out_info, a.err_flag);
-}
-
-// blockIdx.y = batch
-template <bool W1>
-__global__ void __launch_bounds__(256) event_select_multi_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
-    extern __shared__ uint64_t smem_ch[];
-    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
-    const FleetDerived fd = *f.derived;
-    const uint64_t elig = W1 ? f.elig[0] : ((uint32_t)lane < v.words ? f.elig[lane] : 0ULL);
-    const FleetRegs fr = load_fleet_regs<W1>(v, f, lane);
+    const uint64_t elig = (uint32_t)lane < v.words ? f.elig[lane] : 0ULL;
     const BatchDesc& b = a.b[blockIdx.y];
-    for (uint32_t r = blockIdx.x * wpc + wic; r < b.n; r += gridDim.x * wpc)
-        select_one<W1>(v, f, fd, fr, elig, b.tokens, b.offsets, r, a.block_size, a.max_blocks, ch, lane, b.out_idx, b.out_info, a.err_flag);
+    for (uint32_t r = blockIdx.x * wpc + wic; r < b.n; r += gridDim.x * wpc) {
+        const uint32_t off = b.offsets[r], ntok = b.offsets[r + 1] - off;
+        int32_t out = -1;
+        uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+        if (fd.n_healthy == 0) {
+        } else if (fd.imbalanced) {
+            out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
+        } else {
+            const uint32_t nb = a.block_size ? ntok / a.block_size : 0;
+            if (nb > a.max_blocks) { if (lane == 0) atomicExch(a.err_flag, 1u); branch = 255; }
+            else {
+                uint64_t winset = 0;
+                uint32_t score = 0;
+                if (nb > 0 && v.n_workers > 0) {
+                    const uint64_t* gh = a.hashes + ((uint64_t)b.hash_base + r) * a.max_blocks;
+                    for (uint32_t i = lane; i < nb; i += 32) ch[i] = gh[i];
+                    __syncwarp();
+                    SelectSink<false> sink{elig, 0, 0};
+                    uint64_t surv = jump_search<false>(v, ch, (int)nb, lane, sink, false) & elig;
+                    if (set_any<false>(surv)) { winset = surv; score = nb; }
+                    else { winset = sink.last; score = sink.last_score; }
+                    __syncwarp();
+                }
+                if (set_any<false>(winset)) { out = warp_arg_best(v, f, winset, lane); branch = SMGX_BR_EVENT_OVERLAP; matched = score; }
+                else { out = fd.min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD; }
+            }
+        }
+        if (lane == 0) write_pick(b, r, out, branch, matched, ntok);
+    }
 }
 
 template <bool W1>
@@ -470,40 +583,34 @@ void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t*
     SMGX_CUDA(cudaGetLastError());
 }
 
-void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const SelectArgs& a, int sm_count, cudaStream_t stream) {
-    if (a.n == 0) return;
-    // warps per CTA bounded by the shared-memory scratch (8 B per block per warp)
-    size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
-    int wpc = 8;
-    while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
-    size_t smem = per_warp * wpc;
-    if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "request too long for the per-warp scratch (max_tokens_per_request)");
-    unsigned ctas_needed = (a.n + wpc - 1) / wpc;
-    // resident CTAs per SM: 2048 threads / (wpc*32), also bounded by shared memory (227 KB)
-    unsigned per_sm = std::min<unsigned>(2048 / (wpc * 32), (unsigned)std::max<size_t>(1, (220 * 1024) / std::max<size_t>(smem, 1)));
-    unsigned cap = (unsigned)sm_count * std::max(1u, per_sm);
-    unsigned grid = std::min(ctas_needed, cap);   // grid-stride beyond one full wave
-    auto k = ix.words == 1 ? event_select_kernel<true> : event_select_kernel<false>;
-    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, wpc * 32, smem, stream>>>(ix, fleet, a);
-    SMGX_CUDA(cudaGetLastError());
-}
-
-void launch_event_select_multi(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
+void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
     if (a.count == 0) return;
-    size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
-    int wpc = 8;
-    while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
-    size_t smem = per_warp * wpc;
-    if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "request too long for the per-warp scratch (max_tokens_per_request)");
     uint32_t max_n = 0;
     for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
-    unsigned ctas_x = std::max(1u, (max_n + wpc - 1) / wpc);
-    (void)sm_count;
-    auto k = ix.words == 1 ? event_select_multi_kernel<true> : event_select_multi_kernel<false>;
-    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<dim3(ctas_x, a.count), wpc * 32, smem, stream>>>(ix, fleet, a);
+    if (max_n == 0) return;
+    // K2b hashes: one thread per block slot, capped at a few waves (grid-stride beyond that)
+    if (a.block_size) {
+        uint64_t threads = (uint64_t)max_n * a.max_blocks;
+        unsigned gx = (unsigned)std::min<uint64_t>((threads + 255) / 256, (uint64_t)sm_count * 64);
+        if (a.block_size == 16) hash_blocks_kernel<16><<<dim3(std::max(1u, gx), a.count), 256, 0, stream>>>(a);
+        else hash_blocks_kernel<0><<<dim3(std::max(1u, gx), a.count), 256, 0, stream>>>(a);
+        SMGX_CUDA(cudaGetLastError());
+        ++*launches;
+    }
+    if (ix.words == 1) {
+        event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
+    } else {
+        size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
+        int wpc = 8;
+        while (wpc > 1 && per_warp * wpc > 96 * 1024) wpc >>= 1;
+        size_t smem = per_warp * wpc;
+        if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "request too long for the per-warp scratch (max_tokens_per_request)");
+        unsigned gx = std::min<unsigned>((max_n + wpc - 1) / wpc, (unsigned)sm_count * 16);
+        if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        event_search_warp_kernel<<<dim3(std::max(1u, gx), a.count), wpc * 32, smem, stream>>>(ix, fleet, a);
+    }
     SMGX_CUDA(cudaGetLastError());
+    ++*launches;
 }
 
 void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uint32_t n, bool early_exit, uint32_t* d_scores,

@@ -38,39 +38,31 @@ struct FleetRaw {
 void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t* d_slice_of_id, uint64_t* d_load_of_id,
                           uint64_t* d_elig, cudaStream_t stream);
 
-// Fused K2b (content hashes → jump search over the positional index) + K3 (score → argmax worker).
-// One warp per request.  `max_blocks` bounds the per-warp shared-memory scratch (content hashes of one request).
-struct SelectArgs {
-    const uint32_t* tokens;     // device, ragged
-    const uint32_t* offsets;    // device, n + 1
-    uint32_t n;
-    uint32_t block_size;
-    uint32_t max_blocks;
-    int32_t* out_idx;           // device, n
-    smgx_decision_info* out_info;  // device, n (nullable)
-    uint32_t* err_flag;         // device: set to 1 when a request exceeds max_blocks
-};
-void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const SelectArgs& a, int sm_count, cudaStream_t stream);
-
-// Several batches in ONE launch (blockIdx.y = batch): amortises the launch and keeps every SM full when the host
-// batcher has more than one batch queued.  Descriptors travel in the kernel parameter block (no extra copy).
+// The event-driven pick for up to kMaxMultiBatches batches per launch (blockIdx.y = batch; descriptors travel in the
+// kernel parameter block).  Two kernels in stream order:
+//   hash_blocks_kernel           K2b part 1: XXH3 content hash of every full block, one thread per block, streaming
+//   event_search_{thread,warp}   K2b part 2 + K3: jump search over the positional index + argmax worker
+//                                (one thread per request for fleets ≤ 64 interned workers, one warp per request above)
+// `hashes` is a scratch of sum(n) × max_blocks u64 laid out [request][max_blocks]; it is written and read back within
+// microseconds, i.e. out of L2.
 constexpr int kMaxMultiBatches = 32;
 struct BatchDesc {
-    const uint32_t* tokens;
-    const uint32_t* offsets;
-    int32_t* out_idx;
-    smgx_decision_info* out_info;
+    const uint32_t* tokens;        // device, ragged
+    const uint32_t* offsets;       // device, n + 1
+    int32_t* out_idx;              // device, n
+    smgx_decision_info* out_info;  // device, n (nullable)
     uint32_t n;
-    uint32_t pad;
+    uint32_t hash_base;            // first row of this batch in the hash scratch
 };
 struct MultiArgs {
     BatchDesc b[kMaxMultiBatches];
     uint32_t count;
     uint32_t block_size;
-    uint32_t max_blocks;
-    uint32_t* err_flag;
+    uint32_t max_blocks;           // row length of the hash scratch = max blocks per request
+    uint64_t* hashes;
+    uint32_t* err_flag;            // device: set to 1 when a request exceeds max_blocks
 };
-void launch_event_select_multi(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream);
+void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
 
 // PositionalIndexer::find_matches on precomputed content hashes; one warp, one query.
 void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uint32_t n, bool early_exit, uint32_t* d_scores,

@@ -40,7 +40,7 @@ struct ModelState {
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
-    DevBuf d_tokens, d_offsets, d_out, d_info;
+    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash;
     bool busy = false;
     bool has_done = false;
     uint64_t ticket = 0;
@@ -85,7 +85,7 @@ public:
             cudaSetDevice(cfg.device_id);
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
-                l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release();
+                l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 if (l.done) cudaEventDestroy(l.done);
                 if (l.t0) cudaEventDestroy(l.t0);
                 if (l.t1) cudaEventDestroy(l.t1);
@@ -178,9 +178,8 @@ public:
         }
     }
 
-    // Enqueue the kernels of one token batch on `lane` (device pointers).
-    void enqueue_tokens(ModelState& m, Lane& lane, const uint32_t* d_tokens, const uint32_t* d_offsets, uint32_t n, uint32_t max_req_tokens,
-                        int32_t* d_out, smgx_decision_info* d_info) {
+    // Enqueue the kernels of up to kMaxMultiBatches token batches on `lane` (device pointers).
+    void enqueue_batches(ModelState& m, Lane& lane, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens) {
         if (!has_event_indexer(m))
             throw Error(SMGX_UNKNOWN_ERROR,
                         "model has no populated KV-event indexer: the approximate token-tree mode (cache_aware.rs:834-904) is not part of this "
@@ -189,14 +188,24 @@ public:
         FleetView fv;
         sync_state(m, &ixv, &fv);
         uint32_t bs = block_size_for(m);
-        SelectArgs a;
-        a.tokens = d_tokens; a.offsets = d_offsets; a.n = n; a.block_size = bs;
+        MultiArgs a;
+        a.count = count;
+        a.block_size = bs;
         a.max_blocks = bs ? std::max<uint32_t>(max_req_tokens / bs, 1) : 1;
-        a.out_idx = d_out; a.out_info = d_info; a.err_flag = d_err.as<uint32_t>();
-        launch_event_select(ixv, fv, a, sm_count, lane.stream);
-        ++launches;
+        uint64_t rows = 0;
+        for (uint32_t k = 0; k < count; ++k) { a.b[k] = descs[k]; a.b[k].hash_base = (uint32_t)rows; rows += descs[k].n; }
+        SMGX_REQUIRE(rows < (1ull << 32), "too many requests in one launch");
+        lane.d_hash.reserve(std::max<uint64_t>(rows, 1) * a.max_blocks * 8);
+        a.hashes = lane.d_hash.as<uint64_t>();
+        a.err_flag = d_err.as<uint32_t>();
+        launch_event_select(ixv, fv, a, sm_count, lane.stream, &launches);
         SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
         lane.has_done = true;
+    }
+    void enqueue_tokens(ModelState& m, Lane& lane, const uint32_t* d_tokens, const uint32_t* d_offsets, uint32_t n, uint32_t max_req_tokens,
+                        int32_t* d_out, smgx_decision_info* d_info) {
+        BatchDesc d{d_tokens, d_offsets, d_out, d_info, n, 0};
+        enqueue_batches(m, lane, &d, 1, max_req_tokens);
     }
 
     Lane& free_lane() {
@@ -628,29 +637,13 @@ smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key
         P.use_device();
         ModelState& m = P.model(model_key, false);
         uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
-        if (!P.has_event_indexer(m))
-            throw Error(SMGX_UNKNOWN_ERROR, "model has no populated KV-event indexer (token-tree mode is not part of this build yet)");
-        EventIndexView ixv;
-        FleetView fv;
-        P.sync_state(m, &ixv, &fv);
-        uint32_t bs = P.block_size_for(m);
         // up to kMaxMultiBatches batches per launch (blockIdx.y = batch); chunks alternate over the stream lanes
         uint32_t chunk_no = 0;
         for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxMultiBatches, ++chunk_no) {
-            MultiArgs a;
-            a.count = std::min<uint32_t>(kMaxMultiBatches, n_batches - j0);
-            for (uint32_t k = 0; k < a.count; ++k) {
-                a.b[k].tokens = d_tokens[j0 + k]; a.b[k].offsets = d_offsets[j0 + k]; a.b[k].out_idx = d_out_worker_idx[j0 + k];
-                a.b[k].out_info = nullptr; a.b[k].n = n[j0 + k]; a.b[k].pad = 0;
-            }
-            a.block_size = bs;
-            a.max_blocks = bs ? std::max<uint32_t>(cap / bs, 1) : 1;
-            a.err_flag = P.d_err.as<uint32_t>();
-            Lane& lane = P.lanes[chunk_no % P.lanes.size()];
-            launch_event_select_multi(ixv, fv, a, P.sm_count, lane.stream);
-            ++P.launches;
-            SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
-            lane.has_done = true;
+            BatchDesc d[kMaxMultiBatches];
+            uint32_t cnt = std::min<uint32_t>(kMaxMultiBatches, n_batches - j0);
+            for (uint32_t k = 0; k < cnt; ++k) d[k] = BatchDesc{d_tokens[j0 + k], d_offsets[j0 + k], d_out_worker_idx[j0 + k], nullptr, n[j0 + k], 0};
+            P.enqueue_batches(m, P.lanes[chunk_no % P.lanes.size()], d, cnt, cap);
         }
         return SMGX_SUCCESS;
     });
