@@ -131,6 +131,27 @@ smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, con
 smgx_status smgx_content_hashes(smgx_policy* p, const uint32_t* tokens, uint32_t n_tokens, uint32_t block_size,
                                 uint64_t* out_hashes, uint32_t cap, uint32_t* out_n, char** err);
 
+/* ---- tokenizer: Tokenizer::encode for tiktoken-style models (crates/tokenizer/src/tiktoken.rs) ----------------- */
+/* TiktokenTokenizer::from_file (tiktoken.rs:219-268): `path` holds lines of `base64(token) rank` (load_tiktoken_bpe, :346-367);
+ * `special_strs/special_ids` = the added_tokens_decoder entries that become CoreBPE's special-token encoder (:234-238).
+ * The pre-tokenizer is CL100K_BASE_PATTERN (:28).  One tokenizer per model key. */
+smgx_status smgx_tokenizer_load_tiktoken_file(smgx_policy* p, const char* model_key, const char* path, const char* const* special_strs,
+                                              const uint32_t* special_ids, uint32_t n_special, char** err);
+/* Same from memory: token i = blob[tok_offsets[i] .. tok_offsets[i+1]) with rank ranks[i]. */
+smgx_status smgx_tokenizer_load_tiktoken(smgx_policy* p, const char* model_key, const uint8_t* blob, const uint32_t* tok_offsets,
+                                         const uint32_t* ranks, uint32_t n_tokens, const char* const* special_strs,
+                                         const uint32_t* special_ids, uint32_t n_special, char** err);
+/* Encoder::encode_batch (tiktoken.rs:464-469) on the GPU: text i = text[offsets[i] .. offsets[i+1]) (UTF-8, already
+ * chat-template-rendered; special-token strings are recognised, tiktoken.rs:446-460).  Writes the ragged token ids and
+ * out_tok_offsets[n+1]; `cap_tokens` = capacity of out_tokens (≥ total text bytes is always enough). */
+smgx_status smgx_tokenize_batch(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                uint32_t* out_tokens, uint32_t* out_tok_offsets, uint32_t cap_tokens, char** err);
+/* The whole hot path in one call: tokenize on the device → cache-aware pick; the token ids never visit the host unless
+ * out_tokens / out_tok_offsets are given (the gateway forwards them to the engine). */
+smgx_status smgx_select_batch_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                   int32_t* out_worker_idx, smgx_decision_info* out_info, uint32_t* out_tokens,
+                                   uint32_t* out_tok_offsets, uint32_t cap_tokens, char** err);
+
 /* ---- the hot call: LoadBalancingPolicy::select_worker, batched (cache_aware.rs:648-690) -------------------- */
 /* n requests, request i = tokens[offsets[i] .. offsets[i+1]) (SelectWorkerInfo.tokens = Some).  All requests see the
  * fleet snapshot and index state current at submission.  out_worker_idx[i] = index into the slice given to

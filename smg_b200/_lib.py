@@ -86,6 +86,10 @@ def load():
     sig("smgx_indexer_entry_count", st, vp, cp, P(u64), pp)
     sig("smgx_indexer_find_matches", st, vp, cp, vp, u32, C.c_int, vp, vp, u32, P(u32), pp)
     sig("smgx_content_hashes", st, vp, vp, u32, u32, vp, u32, P(u32), pp)
+    sig("smgx_tokenizer_load_tiktoken_file", st, vp, cp, cp, P(cp), vp, u32, pp)
+    sig("smgx_tokenizer_load_tiktoken", st, vp, cp, vp, vp, vp, u32, P(cp), vp, u32, pp)
+    sig("smgx_tokenize_batch", st, vp, cp, vp, vp, u32, vp, vp, u32, pp)
+    sig("smgx_select_batch_text", st, vp, cp, vp, vp, u32, vp, vp, vp, vp, u32, pp)
     sig("smgx_select_batch_tokens", st, vp, cp, vp, vp, u32, vp, vp, pp)
     sig("smgx_pipeline_depth", u32, vp)
     sig("smgx_submit_tokens", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)

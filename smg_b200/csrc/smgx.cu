@@ -16,6 +16,7 @@
 #include "common.h"
 #include "event_index.h"
 #include "kernels.h"
+#include "tokenizer.h"
 
 namespace smgx {
 
@@ -29,6 +30,7 @@ struct ModelState {
     std::vector<uint64_t> processed; // increment_processed() per slice index
     // KvEventMonitor state for this model
     std::unique_ptr<EventIndex> indexer;
+    std::unique_ptr<Tokenizer> tokenizer;   // TokenizerRegistry entry for this model
     bool has_learned_bs = false;
     uint32_t learned_bs = 0;
     // device copy of the fleet
@@ -40,7 +42,8 @@ struct ModelState {
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
-    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash;
+    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff;
+    Tokenizer::Scratch tok_scratch;
     bool busy = false;
     bool has_done = false;
     uint64_t ticket = 0;
@@ -86,6 +89,8 @@ public:
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
                 l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
+                l.d_text.release(); l.d_toff.release();
+                l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
                 if (l.done) cudaEventDestroy(l.done);
                 if (l.t0) cudaEventDestroy(l.t0);
                 if (l.t1) cudaEventDestroy(l.t1);
@@ -96,6 +101,7 @@ public:
                 m.d_loads.release(); m.d_flags.release(); m.d_id_of_slice.release(); m.d_derived.release();
                 m.d_slice_of_id.release(); m.d_load_of_id.release(); m.d_elig.release();
                 m.indexer.reset();
+                m.tokenizer.reset();
             }
             d_err.release(); d_flush.release(); scratch.release(); scratch2.release();
             if (state_ready) cudaEventDestroy(state_ready);
@@ -573,6 +579,130 @@ smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, con
         if (nw) SMGX_CUDA(cudaMemcpyAsync(ts.data(), ixv.tree_sizes, (size_t)nw * 8, cudaMemcpyDeviceToHost, l.stream));
         SMGX_CUDA(cudaStreamSynchronize(l.stream));
         for (uint32_t w = 0; w < nw; ++w) { out_scores[w] = sc[w]; if (out_tree_sizes) out_tree_sizes[w] = ts[w]; }
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- tokenizer ----
+static std::vector<std::pair<std::string, uint32_t>> collect_specials(const char* const* strs, const uint32_t* ids, uint32_t n) {
+    std::vector<std::pair<std::string, uint32_t>> sp;
+    SMGX_REQUIRE(n == 0 || (strs && ids), "Invalid arguments: null pointer");
+    for (uint32_t i = 0; i < n; ++i) { SMGX_REQUIRE(strs[i] != nullptr, "Invalid arguments: null pointer"); sp.emplace_back(strs[i], ids[i]); }
+    return sp;
+}
+smgx_status smgx_tokenizer_load_tiktoken_file(smgx_policy* p, const char* model_key, const char* path, const char* const* special_strs,
+                                              const uint32_t* special_ids, uint32_t n_special, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(path);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        bool dev = p->impl.cfg.device_id >= 0;
+        if (dev) p->impl.use_device();
+        ModelState& m = p->impl.model(model_key, true);
+        m.tokenizer.reset(Tokenizer::from_tiktoken_file(path, collect_specials(special_strs, special_ids, n_special), dev));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tokenizer_load_tiktoken(smgx_policy* p, const char* model_key, const uint8_t* blob, const uint32_t* tok_offsets,
+                                         const uint32_t* ranks, uint32_t n_tokens, const char* const* special_strs,
+                                         const uint32_t* special_ids, uint32_t n_special, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(blob); NONNULL(tok_offsets); NONNULL(ranks);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        bool dev = p->impl.cfg.device_id >= 0;
+        if (dev) p->impl.use_device();
+        std::vector<std::string> toks(n_tokens);
+        std::vector<uint32_t> rk(ranks, ranks + n_tokens);
+        for (uint32_t i = 0; i < n_tokens; ++i) toks[i].assign((const char*)blob + tok_offsets[i], tok_offsets[i + 1] - tok_offsets[i]);
+        ModelState& m = p->impl.model(model_key, true);
+        m.tokenizer.reset(new Tokenizer(toks, rk, collect_specials(special_strs, special_ids, n_special), dev));
+        return SMGX_SUCCESS;
+    });
+}
+
+// H2D the ragged text and tokenise it on `lane`; returns the device token buffers (valid until the lane is reused).
+static void tokenize_on_lane(Policy& P, ModelState& m, Lane& lane, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                             uint32_t* max_text_len) {
+    if (!m.tokenizer) throw Error(SMGX_NOT_FOUND, "no tokenizer loaded for this model");
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+        mx = std::max(mx, offsets[i + 1] - offsets[i]);
+    }
+    *max_text_len = mx;
+    const uint32_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
+    lane.d_text.reserve(std::max<uint32_t>(total, 1) + 16);
+    lane.d_offsets.reserve(((size_t)n + 1) * 4);
+    lane.d_toff.reserve(((size_t)n + 1) * 4);
+    lane.d_tokens.reserve((size_t)std::max<uint32_t>(total, 1) * 4 + 16);
+    if (n == 0) return;
+    if (total) SMGX_CUDA(cudaMemcpyAsync(lane.d_text.ptr, text + base, total, cudaMemcpyHostToDevice, lane.stream));
+    SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+    // kernels index text with the caller's absolute offsets
+    m.tokenizer->encode_batch(lane.d_text.as<uint8_t>() - base, lane.d_offsets.as<uint32_t>(), n, total + base, lane.d_tokens.as<uint32_t>(),
+                              lane.d_toff.as<uint32_t>(), lane.tok_scratch, lane.stream, &P.launches);
+}
+
+static void copy_tokens_out(Lane& lane, uint32_t n, uint32_t* out_tokens, uint32_t* out_tok_offsets, uint32_t cap_tokens) {
+    std::vector<uint32_t> toff_local;
+    uint32_t* toff = out_tok_offsets;
+    if (!toff) { toff_local.resize((size_t)n + 1); toff = toff_local.data(); }
+    SMGX_CUDA(cudaMemcpyAsync(toff, lane.d_toff.ptr, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, lane.stream));
+    SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+    if (out_tokens) {
+        SMGX_REQUIRE(toff[n] <= cap_tokens, "out_tokens capacity too small");
+        if (toff[n]) SMGX_CUDA(cudaMemcpyAsync(out_tokens, lane.d_tokens.ptr, (size_t)toff[n] * 4, cudaMemcpyDeviceToHost, lane.stream));
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+    }
+}
+
+smgx_status smgx_tokenize_batch(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                uint32_t* out_tokens, uint32_t* out_tok_offsets, uint32_t cap_tokens, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_tok_offsets);
+        SMGX_REQUIRE(n == 0 || (text && offsets && out_tokens), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        Lane& lane = P.free_lane();
+        uint32_t mx = 0;
+        if (n == 0) { out_tok_offsets[0] = 0; return SMGX_SUCCESS; }
+        tokenize_on_lane(P, m, lane, text, offsets, n, &mx);
+        copy_tokens_out(lane, n, out_tokens, out_tok_offsets, cap_tokens);
+        return SMGX_SUCCESS;
+    });
+}
+
+smgx_status smgx_select_batch_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                   int32_t* out_worker_idx, smgx_decision_info* out_info, uint32_t* out_tokens, uint32_t* out_tok_offsets,
+                                   uint32_t cap_tokens, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (text && offsets && out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(n <= P.cfg.max_batch, "batch larger than max_batch");
+        ModelState& m = P.model(model_key, false);
+        if (n == 0) { if (out_tok_offsets) out_tok_offsets[0] = 0; return SMGX_SUCCESS; }
+        Lane& lane = P.free_lane();
+        uint32_t mx = 0;
+        tokenize_on_lane(P, m, lane, text, offsets, n, &mx);
+        SMGX_REQUIRE(mx <= P.cfg.max_tokens_per_request, "request longer than max_tokens_per_request");
+        lane.d_out.reserve((size_t)n * 4);
+        if (out_info) lane.d_info.reserve((size_t)n * sizeof(smgx_decision_info));
+        // a request of b bytes has at most b tokens → bounds the per-request hash row
+        P.enqueue_tokens(m, lane, lane.d_tokens.as<uint32_t>(), lane.d_toff.as<uint32_t>(), n, std::max<uint32_t>(mx, 1), lane.d_out.as<int32_t>(),
+                         out_info ? lane.d_info.as<smgx_decision_info>() : nullptr);
+        SMGX_CUDA(cudaMemcpyAsync(out_worker_idx, lane.d_out.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
+        if (out_info)
+            SMGX_CUDA(cudaMemcpyAsync(out_info, lane.d_info.ptr, (size_t)n * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+        if (out_tokens || out_tok_offsets) copy_tokens_out(lane, n, out_tokens, out_tok_offsets, cap_tokens);
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+        for (uint32_t i = 0; i < n; ++i) {
+            int32_t idx = out_worker_idx[i];
+            if (idx >= 0 && (size_t)idx < m.processed.size()) ++m.processed[(size_t)idx];
+        }
         return SMGX_SUCCESS;
     });
 }

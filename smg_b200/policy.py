@@ -208,6 +208,37 @@ class KvEventMonitor:
         self.policy._h.call("smgx_indexer_set_block_size", model.encode(), block_size)
 
 
+class TiktokenTokenizer:
+    """tokenizer::TiktokenTokenizer (crates/tokenizer/src/tiktoken.rs:132) on the GPU, bound to (policy handle, model).
+    encode() keeps the reference's behaviour of always recognising special-token strings (tiktoken.rs:444-462)."""
+
+    def __init__(self, handle: _Handle, model: str, path: str, special_tokens=None):
+        self.h, self.model = handle, model.encode()
+        sp = list((special_tokens or {}).items())
+        strs = (C.c_char_p * max(len(sp), 1))(*[k.encode() for k, _ in sp]) if sp else None
+        ids = _u32([v for _, v in sp])
+        self.h.call("smgx_tokenizer_load_tiktoken_file", self.model, path.encode(), strs, _p(ids), len(sp))
+
+    @staticmethod
+    def _ragged(texts):
+        blobs = [t.encode("utf-8") for t in texts]
+        offsets = np.zeros(len(blobs) + 1, dtype=np.uint32)
+        np.cumsum([len(b) for b in blobs], out=offsets[1:])
+        data = np.frombuffer(b"".join(blobs) or b"\0", dtype=np.uint8).copy()
+        return data, offsets
+
+    def encode_batch(self, texts, add_special_tokens: bool = False):
+        data, offsets = self._ragged(texts)
+        n = len(texts)
+        cap = int(offsets[-1]) + 1
+        out, toff = np.zeros(cap, np.uint32), np.zeros(n + 1, np.uint32)
+        self.h.call("smgx_tokenize_batch", self.model, _p(data), _p(offsets), n, _p(out), _p(toff), cap)
+        return [out[toff[i]:toff[i + 1]].tolist() for i in range(n)]
+
+    def encode(self, text: str, add_special_tokens: bool = False):
+        return self.encode_batch([text])[0]
+
+
 class CacheAwarePolicy:
     """policies::CacheAwarePolicy on the GPU.  select_worker keeps the reference signature; select_worker_batch is the
     batched form the host batcher uses (all requests see one fleet snapshot)."""
@@ -308,6 +339,25 @@ class CacheAwarePolicy:
         tok_ptr = _p(tokens) if tokens.size else C.cast(C.create_string_buffer(4), C.c_void_p)
         self._h.call("smgx_select_batch_tokens", model, tok_ptr, _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
         return out[:n], (info if info is None else [info[i] for i in range(n)])
+
+    # -- tokenizer + text-in pick (the whole hot path on the device) ------------------------------------------------
+    def load_tiktoken_tokenizer(self, path: str, special_tokens=None, model: str = UNKNOWN_MODEL_ID) -> TiktokenTokenizer:
+        return TiktokenTokenizer(self._h, model, path, special_tokens)
+
+    def select_worker_batch_text(self, workers: Sequence[BasicWorker], texts, want_tokens: bool = True):
+        """Chat-template-rendered texts → (worker_idx, info, token lists): tokenise on the GPU, then the cache-aware pick,
+        without the tokens visiting the host in between (preparation.rs:134 + worker_selection.rs:157 in one call)."""
+        model = self._push_fleet(workers)
+        data, offsets = TiktokenTokenizer._ragged(texts)
+        n = len(texts)
+        out = np.full(max(n, 1), -1, dtype=np.int32)
+        info = (_lib.DecisionInfo * max(n, 1))()
+        cap = int(offsets[-1]) + 1
+        toks, toff = (np.zeros(cap, np.uint32), np.zeros(n + 1, np.uint32)) if want_tokens else (None, None)
+        self._h.call("smgx_select_batch_text", model, _p(data), _p(offsets), n, _p(out), C.cast(info, C.c_void_p),
+                     _p(toks) if want_tokens else None, _p(toff) if want_tokens else None, cap)
+        tokens = [toks[toff[i]:toff[i + 1]].tolist() for i in range(n)] if want_tokens else None
+        return out[:n], [info[i] for i in range(n)], tokens
 
     def take_processed(self, model: str = UNKNOWN_MODEL_ID, n: Optional[int] = None):
         n = n if n is not None else len(self._slices.get(model, ()))
