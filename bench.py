@@ -238,6 +238,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=4, help="stream lanes the timed steps are issued over (1 = strictly serial launches)")
     ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--text-in", action="store_true", help="also measure the text-in path (GPU tokenize → pick)")
+    ap.add_argument("--text-docs", type=int, default=8192)
+    ap.add_argument("--text-bytes", type=int, default=2048)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -429,11 +432,132 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(seqs, hashes, args, bs)
+    if rank == 0 and world == 1 and args.text_in:
+        line["text_in"] = text_in_leg(args, local_rank)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def text_corpus_docs(n_docs, target_bytes, seed):
+    """Synthetic chat-like documents of ~target_bytes UTF-8 bytes built from source-code and prose lines available offline."""
+    import glob
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lines = []
+    for f in sorted(glob.glob("/usr/lib/python3*/[a-z]*.py"))[:200]:
+        try:
+            lines += [ln for ln in open(f, encoding="utf-8", errors="ignore").read().split("\n") if 8 < len(ln) < 200]
+        except OSError:
+            pass
+    if len(lines) < 1000:
+        lines = ["the quick brown fox jumps over the lazy dog number %d" % i for i in range(5000)]
+    docs = []
+    for _ in range(n_docs):
+        parts, size = ["<|im_start|>system\nYou are a helpful assistant.<|im_end|>\n<|im_start|>user\n"], 80
+        while size < target_bytes:
+            ln = lines[int(rng.integers(0, len(lines)))]
+            parts.append(ln + "\n")
+            size += len(ln.encode()) + 1
+        docs.append("".join(parts) + "<|im_end|>\n<|im_start|>assistant\n")
+    return docs, lines
+
+
+def text_in_leg(args, local_rank):
+    """The whole hot path from TEXT: tokenize (GPU BPE) → event-driven pick, through smgx_select_batch_text with host
+    buffers.  Its own policy/index: N documents of ~2 KB, worker = i mod W, same 80/10/10 query mix."""
+    import json as _json
+    from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, synth
+    gold = os.path.join(ROOT, "tests", "golden")
+    specials = _json.load(open(os.path.join(gold, "bpe_vectors.json")))["specials"]
+    B, W, bs = args.batch, args.workers, 16
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), device_id=local_rank, max_batch=B, max_tokens_per_request=8192)
+    tok = pol.load_tiktoken_tokenizer(os.path.join(gold, "synth_vocab.tiktoken"), specials)
+    ws = [BasicWorker(u) for u in synth.worker_urls(W)]
+    for w, l in zip(ws, synth.poisson_loads(W, 8, 42)):
+        w.set_load(int(l))
+    pol.init_workers(ws)
+    mon = pol.kv_event_monitor(bs)
+    ix = mon.create_indexer("unknown", 64)
+    pol.set_kv_event_monitor(mon)
+    n_docs = args.text_docs
+    docs, lines = text_corpus_docs(n_docs, args.text_bytes, 42)
+    for u in synth.worker_urls(W):
+        ix.intern_worker(u)
+    seq = 1
+    n_tok_total = 0
+    for s0 in range(0, n_docs, 2048):
+        ids = tok.encode_batch(docs[s0:s0 + 2048])
+        for k, t in enumerate(ids):
+            nb = len(t) // bs
+            n_tok_total += len(t)
+            if nb:
+                ix.apply_stored_tokens((s0 + k) % W, np.arange(seq, seq + nb, dtype=np.uint64), np.asarray(t[: nb * bs], np.uint32), bs)
+                seq += nb
+    rng = np.random.Generator(np.random.PCG64(777))
+    batches = []
+    for _ in range(4):
+        texts = []
+        for _i in range(B):
+            u = rng.random()
+            d = docs[int(rng.integers(0, n_docs))]
+            if u < 0.8:
+                texts.append(d)
+            elif u < 0.9:
+                cut = int(rng.integers(100, max(101, len(d) - 100)))
+                texts.append(d[:cut] + " ".join(lines[int(rng.integers(0, len(lines)))] for _ in range(8)))
+            else:
+                texts.append("".join(lines[int(rng.integers(0, len(lines)))] + "\n" for _ in range(max(1, args.text_bytes // 60))))
+        blob = [t.encode() for t in texts]
+        offs = np.zeros(B + 1, np.uint32); np.cumsum([len(x) for x in blob], out=offs[1:])
+        batches.append((texts, np.frombuffer(b"".join(blob), dtype=np.uint8).copy(), offs))
+    h, L = pol._h, __import__("smg_b200")._lib.load()
+    model = pol._push_fleet(ws)
+    pins = []
+    for texts, data, offs in batches:
+        pd = L.smgx_alloc_pinned(data.nbytes); C.memmove(pd, data.ctypes.data, data.nbytes)
+        po = L.smgx_alloc_pinned(offs.nbytes); C.memmove(po, offs.ctypes.data, offs.nbytes)
+        pins.append((pd, po, int(offs[-1])))
+    out = L.smgx_alloc_pinned(B * 4)
+    cap = max(p[2] for p in pins) + 16
+    otok = L.smgx_alloc_pinned(cap * 4)
+    otoff = L.smgx_alloc_pinned((B + 1) * 4)
+
+    def run(k, with_tokens):
+        t0 = time.perf_counter()
+        for i in range(k):
+            pd, po, _ = pins[i % len(pins)]
+            h.call("smgx_select_batch_text", model, pd, po, B, out, None, otok if with_tokens else None, otoff if with_tokens else None, cap)
+        return time.perf_counter() - t0
+
+    run(2 * len(pins), True)
+    run(len(pins), False)
+    k = max(10, min(args.steps, 40))
+    t_picks = run(k, False)
+    t_full = run(k, True)
+    mean_bytes = float(np.mean([p[2] for p in pins])) / B
+    res = {"unit": "decisions/s", "picks_only": {"value": k * B / t_picks}, "picks_and_tokens_to_host": {"value": k * B / t_full},
+           "steps": k, "mean_text_bytes_per_request": mean_bytes, "mean_tokens_per_request": n_tok_total / n_docs,
+           "bytes_per_token": args.text_bytes / max(1.0, n_tok_total / n_docs), "index_docs": n_docs, "index_entries": int(ix.entry_count()),
+           "h2d_bytes_per_step": int(np.mean([p[2] for p in pins])) + (B + 1) * 4,
+           "call": "smgx_select_batch_text (GPU BPE tokenize → hash → search → pick), one synchronous call per step, pinned host buffers"}
+    try:
+        import tiktoken
+        from oracle import bpe_ref
+        ranks = bpe_ref.load_tiktoken_bpe(os.path.join(gold, "synth_vocab.tiktoken"))
+        enc = tiktoken.Encoding("synth", pat_str=bpe_ref.CL100K_BASE_PATTERN, mergeable_ranks=ranks, special_tokens=specials)
+        nthreads = os.cpu_count() or 1
+        texts = batches[0][0]
+        enc.encode_batch(texts[:256], num_threads=nthreads, allowed_special="all")
+        t0 = time.perf_counter()
+        ids = enc.encode_batch(texts, num_threads=nthreads, allowed_special="all")
+        dt = time.perf_counter() - t0
+        res["cpu_tokenize_baseline"] = {"value": B / dt, "unit": "requests/s", "tokens_per_s": sum(len(x) for x in ids) / dt, "cores": nthreads,
+                                        "kind": "tiktoken 0.12 (OpenAI Rust CoreBPE, the algorithm tiktoken-rs ports) encode_batch, tokenize step only"}
+    except Exception as e:  # noqa: BLE001
+        res["cpu_tokenize_baseline"] = {"unavailable": str(e)[:100]}
+    return res
 
 
 def cpu_baseline(seqs, hashes, args, bs):

@@ -50,18 +50,21 @@ SMGX_HD uint8_t char_class(uint32_t cp, const UnicodeView& u) {
 }
 SMGX_HD bool is_newline(uint32_t cp) { return cp == '\n' || cp == '\r'; }
 
-// End (byte index) of the regex match that starts at byte i of s[0..n).  i < n.
-SMGX_HD uint32_t next_piece_cl100k(const uint8_t* s, uint32_t i, uint32_t n, const UnicodeView& u) {
+// End (byte index) of the regex match that starts at byte i of s[0..n).  i < n and i is not a slice end.
+// tiktoken runs the regex only on the ordinary text between two special tokens; `stop` (nullable) marks the first byte of
+// every special with the value 2, and such a byte acts as the end of the string (for the run scans and for `(?!\S)`).
+SMGX_HD uint32_t next_piece_cl100k(const uint8_t* s, uint32_t i, uint32_t n, const UnicodeView& u, const uint8_t* stop = nullptr) {
+#define SMGX_AT_END(j) ((j) >= n || (stop != nullptr && stop[(j)] == 2))
     uint32_t len0;
     const uint32_t cp0 = utf8_decode(s, i, n, len0);
     const uint8_t cls0 = char_class(cp0, u);
 
-    // 1. (?i:'s|'t|'re|'ve|'m|'ll|'d) — Unicode-aware case folding adds U+017F (ſ) for 's' and U+212A (K) for nothing used here
-    if (cp0 == '\'' && i + 1 < n) {
+    // 1. (?i:'s|'t|'re|'ve|'m|'ll|'d) — Unicode-aware case folding adds U+017F (ſ) for 's'
+    if (cp0 == '\'' && !SMGX_AT_END(i + 1)) {
         const uint32_t c1 = s[i + 1] | 0x20;
         if (s[i + 1] < 0x80) {
             if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') return i + 2;
-            if (i + 2 < n && s[i + 2] < 0x80) {
+            if (!SMGX_AT_END(i + 2) && s[i + 2] < 0x80) {
                 const uint32_t c2 = s[i + 2] | 0x20;
                 if ((c1 == 'r' && c2 == 'e') || (c1 == 'v' && c2 == 'e') || (c1 == 'l' && c2 == 'l')) return i + 3;
             }
@@ -76,14 +79,14 @@ SMGX_HD uint32_t next_piece_cl100k(const uint8_t* s, uint32_t i, uint32_t n, con
         bool ok = cls0 == CH_LETTER;
         if (!ok && cls0 != CH_NUMBER && !is_newline(cp0)) {
             uint32_t k = i + len0;
-            if (k < n) {
+            if (!SMGX_AT_END(k)) {
                 uint32_t l1;
                 uint32_t cp1 = utf8_decode(s, k, n, l1);
                 if (char_class(cp1, u) == CH_LETTER) { j = k; ok = true; }
             }
         }
         if (ok) {
-            while (j < n) {
+            while (!SMGX_AT_END(j)) {
                 uint32_t l;
                 uint32_t cp = utf8_decode(s, j, n, l);
                 if (char_class(cp, u) != CH_LETTER) break;
@@ -95,7 +98,7 @@ SMGX_HD uint32_t next_piece_cl100k(const uint8_t* s, uint32_t i, uint32_t n, con
     // 3. \p{N}{1,3}
     if (cls0 == CH_NUMBER) {
         uint32_t j = i + len0;
-        for (int c = 1; c < 3 && j < n; ++c) {
+        for (int c = 1; c < 3 && !SMGX_AT_END(j); ++c) {
             uint32_t l;
             uint32_t cp = utf8_decode(s, j, n, l);
             if (char_class(cp, u) != CH_NUMBER) break;
@@ -107,25 +110,25 @@ SMGX_HD uint32_t next_piece_cl100k(const uint8_t* s, uint32_t i, uint32_t n, con
     {
         uint32_t j = i;
         bool ok = cls0 == CH_OTHER;
-        if (!ok && cp0 == ' ' && i + 1 < n) {
+        if (!ok && cp0 == ' ' && !SMGX_AT_END(i + 1)) {
             uint32_t l1;
             uint32_t cp1 = utf8_decode(s, i + 1, n, l1);
             if (char_class(cp1, u) == CH_OTHER) { j = i + 1; ok = true; }
         }
         if (ok) {
-            while (j < n) {
+            while (!SMGX_AT_END(j)) {
                 uint32_t l;
                 uint32_t cp = utf8_decode(s, j, n, l);
                 if (char_class(cp, u) != CH_OTHER) break;
                 j += l;
             }
-            while (j < n && (s[j] == '\n' || s[j] == '\r')) ++j;
+            while (!SMGX_AT_END(j) && (s[j] == '\n' || s[j] == '\r')) ++j;
             return j;
         }
     }
     // 5-7. whitespace run starting at i (cls0 == CH_SPACE)
     uint32_t j = i, last_nl_end = 0, last_start = i, count = 0;
-    while (j < n) {
+    while (!SMGX_AT_END(j)) {
         uint32_t l;
         uint32_t cp = utf8_decode(s, j, n, l);
         if (char_class(cp, u) != CH_SPACE) break;
@@ -135,9 +138,10 @@ SMGX_HD uint32_t next_piece_cl100k(const uint8_t* s, uint32_t i, uint32_t n, con
         if (is_newline(cp)) last_nl_end = j;
     }
     if (last_nl_end) return last_nl_end;   // 5. \s*[\r\n]+  : greedy \s* backtracks to the last newline of the run
-    if (j == n) return j;                  // 6. \s+(?!\S)   : run reaches the end of the text
+    if (SMGX_AT_END(j)) return j;          // 6. \s+(?!\S)   : run reaches the end of the (slice of) text
     if (count >= 2) return last_start;     // 6.             : give back one char so that whitespace follows
     return j;                              // 7. \s+
+#undef SMGX_AT_END
 }
 
 // ---- vocabulary tables ---------------------------------------------------------------------------------------

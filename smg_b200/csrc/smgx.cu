@@ -91,6 +91,7 @@ public:
                 l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
+                l.tok_scratch.pieces.release(); l.tok_scratch.n_pieces.release();
                 if (l.done) cudaEventDestroy(l.done);
                 if (l.t0) cudaEventDestroy(l.t0);
                 if (l.t1) cudaEventDestroy(l.t1);
@@ -638,7 +639,7 @@ static void tokenize_on_lane(Policy& P, ModelState& m, Lane& lane, const uint8_t
     if (total) SMGX_CUDA(cudaMemcpyAsync(lane.d_text.ptr, text + base, total, cudaMemcpyHostToDevice, lane.stream));
     SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
     // kernels index text with the caller's absolute offsets
-    m.tokenizer->encode_batch(lane.d_text.as<uint8_t>() - base, lane.d_offsets.as<uint32_t>(), n, total + base, lane.d_tokens.as<uint32_t>(),
+    m.tokenizer->encode_batch(lane.d_text.as<uint8_t>() - base, lane.d_offsets.as<uint32_t>(), n, base, total + base, mx, lane.d_tokens.as<uint32_t>(),
                               lane.d_toff.as<uint32_t>(), lane.tok_scratch, lane.stream, &P.launches);
 }
 

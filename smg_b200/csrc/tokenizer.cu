@@ -15,64 +15,121 @@ namespace {
 
 constexpr uint32_t kInvalidTok = 0xFFFFFFFFu;
 
-// K1a: one thread per request walks its text once: special tokens are cut out first (tiktoken `encode`: the regex only
-// ever sees the text between two specials), then piece starts are flagged for the BPE kernel.
-//   flags[i] = 1  piece of ordinary text starts at byte i ; 2 = first byte of a special token ; 3 = inside a special token
-//   tmp_ids  = special id at a special's first byte, INVALID on its other bytes
-//   totals[r] = number of special tokens of request r (the BPE kernel adds the ordinary tokens)
-__global__ void __launch_bounds__(128) pretokenize_kernel(BpeView v, const uint8_t* __restrict__ text, const uint32_t* __restrict__ offsets,
-                                                          uint32_t n, uint8_t* __restrict__ flags, uint32_t* __restrict__ tmp_ids,
-                                                          uint32_t* __restrict__ totals) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- K1a: pre-tokenisation, parallel over bytes ---------------------------------------------------------------
+// Grid: blockIdx.y = request, blockIdx.x = 256-byte chunk of that request, one thread per byte.
+// Special tokens first (tiktoken `encode`: the regex only ever sees the text between two specials):
+//   special_candidates_kernel   does a special string start at this byte?  (longest at a position)
+//   special_resolve_kernel      one warp per request: accept candidates left to right, dropping those inside an accepted span
+//   flags: 0 ordinary byte, 1 piece start, 2 first byte of a special, 3 inside a special, 4 unresolved candidate
+__global__ void __launch_bounds__(256) special_candidates_kernel(BpeView v, const uint8_t* __restrict__ text, const uint32_t* __restrict__ offsets,
+                                                                 uint8_t* __restrict__ flags, uint32_t* __restrict__ tmp_ids,
+                                                                 uint64_t* __restrict__ tmp_rk) {
+    const uint32_t r = blockIdx.y, beg = offsets[r], rend = offsets[r + 1];
+    const uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rend) return;
+    const uint8_t c = text[i];
+    if (!((v.special_first[c >> 5] >> (c & 31)) & 1)) return;
+    uint32_t len, id;
+    if (special_at(v, text, i, rend, len, id)) { flags[i] = 4; tmp_ids[i] = id; tmp_rk[i] = len; }
+}
+__global__ void __launch_bounds__(256) special_resolve_kernel(const uint32_t* __restrict__ offsets, uint32_t n, uint8_t* __restrict__ flags,
+                                                              uint32_t* __restrict__ tmp_ids, const uint64_t* __restrict__ tmp_rk,
+                                                              uint32_t* __restrict__ totals) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
     const uint32_t beg = offsets[r], end = offsets[r + 1];
-    const uint8_t* s = text + beg;
-    const uint32_t len = end - beg;
-    uint32_t i = 0, n_special = 0;
-    while (i < len) {
-        // next special token at or after i
-        uint32_t sp = len, sp_len = 0, sp_id = 0;
-        if (v.n_special) {
-            for (uint32_t k = i; k < len; ++k) {
-                if (special_at(v, s, k, len, sp_len, sp_id)) { sp = k; break; }
+    uint32_t skip_until = beg, count = 0;
+    for (uint32_t base = beg; base < end; base += 32) {
+        const uint32_t i = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, i < end && flags[i] == 4);
+        while (m) {
+            const int k = __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint32_t p = base + k;
+            if (p < skip_until) { if (lane == 0) flags[p] = 0; continue; }   // starts inside an accepted special
+            const uint32_t len = (uint32_t)tmp_rk[p];
+            for (uint32_t j = lane; j < len; j += 32) {
+                flags[p + j] = j == 0 ? 2 : 3;
+                if (j) tmp_ids[p + j] = 0xFFFFFFFFu;
             }
+            skip_until = p + len;
+            ++count;
         }
-        // ordinary text [i, sp): regex pieces, with sp acting as the end of the string
-        while (i < sp) {
-            flags[beg + i] = 1;
-            i = next_piece_cl100k(s, i, sp, v.uni);
-        }
-        if (sp < len) {
-            tmp_ids[beg + sp] = sp_id;
-            flags[beg + sp] = 2;
-            for (uint32_t k = 1; k < sp_len; ++k) { tmp_ids[beg + sp + k] = kInvalidTok; flags[beg + sp + k] = 3; }
-            ++n_special;
-            i = sp + sp_len;
-        }
+        __syncwarp();
     }
-    totals[r] = n_special;
+    if (lane == 0) totals[r] = count;
 }
 
-// K1b: one thread per flagged byte = one piece.  Whole-piece vocabulary hit → one token; otherwise byte-pair merge in
-// place (ids in tmp_ids[i..], pair ranks in tmp_rk[i..]).  Unused slots of the piece are set INVALID for the compaction.
-__global__ void __launch_bounds__(256) bpe_pieces_kernel(BpeView v, const uint8_t* __restrict__ text, const uint32_t* __restrict__ offsets,
-                                                         uint32_t n, uint32_t total_bytes, const uint8_t* __restrict__ flags,
-                                                         uint32_t* __restrict__ tmp_ids, uint64_t* __restrict__ tmp_rk,
-                                                         uint32_t* __restrict__ totals) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_bytes; i += gridDim.x * blockDim.x) {
-        if (flags[i] != 1) continue;
-        // request of byte i: last r with offsets[r] <= i
-        uint32_t lo = 0, hi = n;
-        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (offsets[m] <= i) lo = m; else hi = m; }
-        const uint32_t r = lo, rend = offsets[r + 1];
-        uint32_t e = i + 1;
-        while (e < rend && flags[e] == 0) ++e;   // piece ends at the next piece start / special / request end
-        const uint32_t plen = e - i;
+// The regex scan itself.  Positions where a piece MUST start whatever came before — the end of a letter run (every
+// alternative that consumes a letter stops at the end of the run or hands over to one that does), both ends of a digit
+// run (digits are consumed by \p{N}{1,3} only), the start of the request and the byte after a special — cut the text
+// into short independent segments; one thread per such "anchor" replays the hand-compiled regex until the next anchor
+// and appends every piece it finds to a dense piece list (CTA-staged, one global atomic per CTA).
+struct Piece { uint32_t start, len, req; };
+
+__device__ __forceinline__ uint32_t prev_cp(const uint8_t* s, uint32_t i, uint32_t lo) {   // code point ending right before byte i
+    uint32_t j = i - 1;
+    while (j > lo && (s[j] & 0xC0) == 0x80) --j;
+    uint32_t l;
+    return utf8_decode(s, j, i, l);
+}
+__device__ __forceinline__ bool is_anchor(const uint8_t* s, uint32_t i, uint32_t beg, const uint8_t* flags, const UnicodeView& u) {
+    if (i == beg) return true;
+    if (flags[i - 1] >= 2) return true;                      // byte after a special token
+    uint32_t l;
+    const uint8_t c = char_class(utf8_decode(s, i, i + 4, l), u);   // valid UTF-8: a lead byte's continuation bytes exist
+    const uint8_t pc = char_class(prev_cp(s, i, beg), u);
+    return (pc == CH_LETTER && c != CH_LETTER) || (c == CH_NUMBER) != (pc == CH_NUMBER);
+}
+__global__ void __launch_bounds__(256) pretokenize_kernel(BpeView v, const uint8_t* __restrict__ text, const uint32_t* __restrict__ offsets,
+                                                          uint8_t* __restrict__ flags, Piece* __restrict__ pieces, uint32_t* __restrict__ n_pieces) {
+    __shared__ Piece s_list[320];
+    __shared__ uint32_t s_count, s_base;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const uint32_t r = blockIdx.y, beg = offsets[r], rend = offsets[r + 1];
+    const uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rend && (text[i] & 0xC0) != 0x80 && flags[i] < 2 && is_anchor(text, i, beg, flags, v.uni)) {
+        // replay the regex from this anchor up to the next one; a special's first byte (flags == 2) is the end of the slice
+        uint32_t p = i;
+        for (;;) {
+            flags[p] = 1;
+            const uint32_t q = next_piece_cl100k(text, p, rend, v.uni, flags);
+            const uint32_t slot = atomicAdd(&s_count, 1u);
+            if (slot < 320) s_list[slot] = Piece{p, q - p, r};
+            else { uint32_t g = atomicAdd(n_pieces, 1u); pieces[g] = Piece{p, q - p, r}; }   // overflow: straight to the global list
+            if (q >= rend || flags[q] == 2 || is_anchor(text, q, beg, flags, v.uni)) break;
+            p = q;
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = s_count < 320 ? s_count : 320;
+    if (threadIdx.x == 0 && cnt) s_base = atomicAdd(n_pieces, cnt);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) pieces[s_base + k] = s_list[k];
+}
+
+// K1b: one thread per piece (dense list).  Whole-piece vocabulary hit → one token; otherwise tiktoken's byte-pair merge —
+// in thread-local arrays for pieces of ≤ 24 bytes, in place in the global scratch beyond that.  Unused slots of the piece
+// are set INVALID for the compaction.
+__global__ void __launch_bounds__(256) bpe_pieces_kernel(BpeView v, const uint8_t* __restrict__ text, const Piece* __restrict__ pieces,
+                                                         const uint32_t* __restrict__ n_pieces, uint32_t* __restrict__ tmp_ids,
+                                                         uint64_t* __restrict__ tmp_rk, uint32_t* __restrict__ totals) {
+    const uint32_t np = *n_pieces;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) {
+        const Piece pc = pieces[t];
+        const uint32_t i = pc.start, plen = pc.len;
         uint32_t k, id;
         if (piece_lookup(v, text + i, plen, id)) { tmp_ids[i] = id; k = 1; }
-        else k = byte_pair_merge(v, text + i, plen, tmp_ids + i, tmp_rk + i);
-        for (uint32_t j = i + k; j < e; ++j) tmp_ids[j] = kInvalidTok;
-        atomicAdd(&totals[r], k);
+        else if (plen <= 24) {
+            uint32_t ids[24];
+            uint64_t rk[24];
+            k = byte_pair_merge(v, text + i, plen, ids, rk);
+            for (uint32_t j = 0; j < k; ++j) tmp_ids[i + j] = ids[j];
+        } else k = byte_pair_merge(v, text + i, plen, tmp_ids + i, tmp_rk + i);
+        for (uint32_t j = i + k; j < i + plen; ++j) tmp_ids[j] = kInvalidTok;
+        atomicAdd(&totals[pc.req], k);
     }
 }
 
@@ -259,27 +316,45 @@ Tokenizer::~Tokenizer() {
     d_uni_lo_.release(); d_uni_hi_.release(); d_uni_cls_.release();
 }
 
-void Tokenizer::encode_batch(const uint8_t* d_text, const uint32_t* d_offsets, uint32_t n, uint32_t total_bytes, uint32_t* d_tokens,
-                             uint32_t* d_tok_offsets, Scratch& sc, cudaStream_t stream, uint64_t* launches) const {
+void Tokenizer::encode_batch(const uint8_t* d_text, const uint32_t* d_offsets, uint32_t n, uint32_t first_byte, uint32_t total_bytes, uint32_t max_len,
+                             uint32_t* d_tokens, uint32_t* d_tok_offsets, Scratch& sc, cudaStream_t stream, uint64_t* launches) const {
     if (!device_) throw Error(SMGX_DEVICE_ERROR, "tokenizer was loaded without a device (host-mirror policy): no GPU path, no CPU fallback");
     if (n == 0) return;
     sc.flags.reserve(std::max<uint32_t>(total_bytes, 1));
     sc.tmp_ids.reserve((size_t)std::max<uint32_t>(total_bytes, 1) * 4);
     sc.tmp_rk.reserve((size_t)std::max<uint32_t>(total_bytes, 1) * 8);
     sc.totals.reserve((size_t)n * 4);
+    sc.pieces.reserve((size_t)std::max<uint32_t>(total_bytes - first_byte, 1) * sizeof(Piece));
+    sc.n_pieces.reserve(16);
     if (total_bytes) {
         SMGX_CUDA(cudaMemsetAsync(sc.flags.ptr, 0, total_bytes, stream));
     }
-    pretokenize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(dview_, d_text, d_offsets, n, sc.flags.as<uint8_t>(), sc.tmp_ids.as<uint32_t>(),
-                                                          sc.totals.as<uint32_t>());
-    SMGX_CUDA(cudaGetLastError());
-    ++*launches;
-    if (total_bytes) {
-        unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)total_bytes + 255) / 256, 148ull * 32);
-        bpe_pieces_kernel<<<grid, 256, 0, stream>>>(dview_, d_text, d_offsets, n, total_bytes, sc.flags.as<uint8_t>(), sc.tmp_ids.as<uint32_t>(),
-                                                  sc.tmp_rk.as<uint64_t>(), sc.totals.as<uint32_t>());
-        SMGX_CUDA(cudaGetLastError());
-        ++*launches;
+    {
+        const dim3 grid2((max_len + 255) / 256, n);
+        if (dview_.n_special && max_len) {
+            special_candidates_kernel<<<grid2, 256, 0, stream>>>(dview_, d_text, d_offsets, sc.flags.as<uint8_t>(), sc.tmp_ids.as<uint32_t>(),
+                                                               sc.tmp_rk.as<uint64_t>());
+            SMGX_CUDA(cudaGetLastError());
+            ++*launches;
+            special_resolve_kernel<<<(unsigned)(((uint64_t)n * 32 + 255) / 256), 256, 0, stream>>>(d_offsets, n, sc.flags.as<uint8_t>(), sc.tmp_ids.as<uint32_t>(),
+                                                                                               sc.tmp_rk.as<uint64_t>(), sc.totals.as<uint32_t>());
+            SMGX_CUDA(cudaGetLastError());
+            ++*launches;
+        } else {
+            SMGX_CUDA(cudaMemsetAsync(sc.totals.ptr, 0, (size_t)n * 4, stream));
+        }
+        SMGX_CUDA(cudaMemsetAsync(sc.n_pieces.ptr, 0, 4, stream));
+        if (max_len) {
+            pretokenize_kernel<<<grid2, 256, 0, stream>>>(dview_, d_text, d_offsets, sc.flags.as<uint8_t>(), sc.pieces.as<Piece>(), sc.n_pieces.as<uint32_t>());
+            SMGX_CUDA(cudaGetLastError());
+            ++*launches;
+            // one thread per piece; the piece count lives on the device, so size the grid for the worst case the text allows
+            unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)(total_bytes - first_byte) / 2 + 255) / 256 + 1, 148ull * 16);
+            bpe_pieces_kernel<<<grid, 256, 0, stream>>>(dview_, d_text, sc.pieces.as<Piece>(), sc.n_pieces.as<uint32_t>(), sc.tmp_ids.as<uint32_t>(),
+                                                      sc.tmp_rk.as<uint64_t>(), sc.totals.as<uint32_t>());
+            SMGX_CUDA(cudaGetLastError());
+            ++*launches;
+        }
     }
     scan_counts_kernel<<<1, 1024, 0, stream>>>(sc.totals.as<uint32_t>(), n, d_tok_offsets);
     SMGX_CUDA(cudaGetLastError());

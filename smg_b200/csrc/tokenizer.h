@@ -24,12 +24,14 @@ public:
     uint32_t n_pairs() const { return n_pairs_; }
 
     // Scratch needed for a batch of `total_bytes` of text and `n` requests.
-    struct Scratch { DevBuf flags, tmp_ids, tmp_rk, totals; };
+    struct Scratch { DevBuf flags, tmp_ids, tmp_rk, totals, pieces, n_pieces; };
 
     // Enqueue pre-tokenise + BPE + compaction on `stream`.
     //   d_text/d_offsets (n+1): ragged UTF-8; d_tokens: capacity ≥ total_bytes u32; d_tok_offsets: n+1 u32 (written).
-    void encode_batch(const uint8_t* d_text, const uint32_t* d_offsets, uint32_t n, uint32_t total_bytes, uint32_t* d_tokens,
-                      uint32_t* d_tok_offsets, Scratch& sc, cudaStream_t stream, uint64_t* launches) const;
+    // Text bytes live at d_text[first_byte .. total_bytes) (absolute offsets as given in d_offsets).
+    // `max_len` = longest request in bytes (sizes the 2-D grids).
+    void encode_batch(const uint8_t* d_text, const uint32_t* d_offsets, uint32_t n, uint32_t first_byte, uint32_t total_bytes, uint32_t max_len,
+                      uint32_t* d_tokens, uint32_t* d_tok_offsets, Scratch& sc, cudaStream_t stream, uint64_t* launches) const;
 
 private:
     BpeView dview_{};
