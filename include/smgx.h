@@ -131,6 +131,22 @@ smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, con
 smgx_status smgx_content_hashes(smgx_policy* p, const uint32_t* tokens, uint32_t n_tokens, uint32_t block_size,
                                 uint64_t* out_hashes, uint32_t cap, uint32_t* out_n, char** err);
 
+/* ---- approximate token tree: kv_index::TokenTree (crates/kv_index/src/token_tree.rs) ----------------------------- */
+/* TokenTree::with_policy (:359): 0 LRU, 1 LFU, 2 FIFO, 3 MRU, 4 FILO, 5 Priority.  smgx_set_workers creates an LRU tree
+ * per model (init_workers, cache_aware.rs:231-247); call this to (re)create it with another eviction policy. */
+smgx_status smgx_tree_create(smgx_policy* p, const char* model_key, int eviction_policy, char** err);
+smgx_status smgx_tree_insert_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, uint32_t n, const char* tenant, char** err); /* :401 */
+/* match_prefix_with_counts (:615) on the GPU, incl. its touch side effects; out_tenant receives the tenant URL ("empty" when
+ * nothing matched). */
+smgx_status smgx_tree_match_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, uint32_t n, uint32_t* out_matched,
+                                   uint32_t* out_input, char* out_tenant, uint32_t tenant_cap, char** err);
+smgx_status smgx_tree_evict_tenant(smgx_policy* p, const char* model_key, const char* tenant, uint64_t max_tokens, char** err);  /* :798 */
+smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err);          /* CacheAwarePolicy::evict_cache (cache_aware.rs:311) */
+smgx_status smgx_tree_tenant_size(smgx_policy* p, const char* model_key, const char* tenant, uint64_t* out, char** err);           /* :988 */
+smgx_status smgx_tree_clear(smgx_policy* p, const char* model_key, char** err);                                                     /* :997 */
+/* iter_entries (:1039) as text, one line per entry "tok,tok,…|tenant=ts;tenant=ts"; *out_text is callee-allocated (smgx_free_string). */
+smgx_status smgx_tree_entries(smgx_policy* p, const char* model_key, char** out_text, char** err);
+
 /* ---- tokenizer: Tokenizer::encode for tiktoken-style models (crates/tokenizer/src/tiktoken.rs) ----------------- */
 /* TiktokenTokenizer::from_file (tiktoken.rs:219-268): `path` holds lines of `base64(token) rank` (load_tiktoken_bpe, :346-367);
  * `special_strs/special_ids` = the added_tokens_decoder entries that become CoreBPE's special-token encoder (:234-238).

@@ -86,6 +86,14 @@ def load():
     sig("smgx_indexer_entry_count", st, vp, cp, P(u64), pp)
     sig("smgx_indexer_find_matches", st, vp, cp, vp, u32, C.c_int, vp, vp, u32, P(u32), pp)
     sig("smgx_content_hashes", st, vp, vp, u32, u32, vp, u32, P(u32), pp)
+    sig("smgx_tree_create", st, vp, cp, C.c_int, pp)
+    sig("smgx_tree_insert_tokens", st, vp, cp, vp, u32, cp, pp)
+    sig("smgx_tree_match_tokens", st, vp, cp, vp, u32, P(u32), P(u32), vp, u32, pp)
+    sig("smgx_tree_evict_tenant", st, vp, cp, cp, u64, pp)
+    sig("smgx_evict_cache", st, vp, u64, pp)
+    sig("smgx_tree_tenant_size", st, vp, cp, cp, P(u64), pp)
+    sig("smgx_tree_clear", st, vp, cp, pp)
+    sig("smgx_tree_entries", st, vp, cp, P(C.c_void_p), pp)
     sig("smgx_tokenizer_load_tiktoken_file", st, vp, cp, cp, P(cp), vp, u32, pp)
     sig("smgx_tokenizer_load_tiktoken", st, vp, cp, vp, vp, vp, u32, P(cp), vp, u32, pp)
     sig("smgx_tokenize_batch", st, vp, cp, vp, vp, u32, vp, vp, u32, pp)

@@ -17,6 +17,8 @@
 #include "event_index.h"
 #include "kernels.h"
 #include "tokenizer.h"
+#include "token_tree.h"
+#include <unordered_set>
 
 namespace smgx {
 
@@ -31,18 +33,22 @@ struct ModelState {
     // KvEventMonitor state for this model
     std::unique_ptr<EventIndex> indexer;
     std::unique_ptr<Tokenizer> tokenizer;   // TokenizerRegistry entry for this model
+    std::unique_ptr<TokenTreeIndex> token_tree;   // token_trees[model] (cache_aware.rs:79)
+    DevBuf d_slice_of_tenant;
+    uint64_t seen_tenants_version = ~0ULL;
     bool has_learned_bs = false;
     uint32_t learned_bs = 0;
     // device copy of the fleet
     DevBuf d_loads, d_flags, d_id_of_slice, d_derived, d_slice_of_id, d_load_of_id, d_elig;
     bool fleet_dirty = true;
+    bool fleet_dirty_tenant = true;
     uint64_t seen_workers_version = ~0ULL;
 };
 
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
-    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff;
+    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
     bool has_done = false;
@@ -89,7 +95,7 @@ public:
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
                 l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
-                l.d_text.release(); l.d_toff.release();
+                l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
                 l.tok_scratch.pieces.release(); l.tok_scratch.n_pieces.release();
                 if (l.done) cudaEventDestroy(l.done);
@@ -103,6 +109,8 @@ public:
                 m.d_slice_of_id.release(); m.d_load_of_id.release(); m.d_elig.release();
                 m.indexer.reset();
                 m.tokenizer.reset();
+                m.token_tree.reset();
+                m.d_slice_of_tenant.release();
             }
             d_err.release(); d_flush.release(); scratch.release(); scratch2.release();
             if (state_ready) cudaEventDestroy(state_ready);
@@ -215,6 +223,115 @@ public:
         enqueue_batches(m, lane, &d, 1, max_req_tokens);
     }
 
+    TokenTreeIndex& tree_of(ModelState& m, bool create) {
+        if (!m.token_tree) {
+            if (!create) throw Error(SMGX_NOT_FOUND, "no token tree for this model (call smgx_set_workers first)");
+            m.token_tree = std::make_unique<TokenTreeIndex>(&tenants, &token_ts, EVP_LRU);
+            m.token_tree->device_enabled = cfg.device_id >= 0;
+        }
+        return *m.token_tree;
+    }
+    // fleet-side lookup the tree pick needs: tenant id → first slice index with that URL (`position(|w| w.url() == tenant)`)
+    void sync_tenant_map(ModelState& m) {
+        if (!m.fleet_dirty_tenant && m.seen_tenants_version == tenants.version) return;
+        std::vector<int32_t> sl(std::max<size_t>(tenants.names.size(), 1), -1);
+        for (size_t i = m.urls.size(); i-- > 0;) {
+            int64_t t = tenants.find(m.urls[i]);
+            if (t >= 0) sl[(size_t)t] = (int32_t)i;   // iterating downwards leaves the FIRST position
+        }
+        m.d_slice_of_tenant.reserve(sl.size() * 4);
+        SMGX_CUDA(cudaMemcpyAsync(m.d_slice_of_tenant.ptr, sl.data(), sl.size() * 4, cudaMemcpyHostToDevice, ctrl));
+        SMGX_CUDA(cudaStreamSynchronize(ctrl));
+        m.fleet_dirty_tenant = false;
+        m.seen_tenants_version = tenants.version;
+    }
+    bool host_imbalanced(const ModelState& m) const {   // same f32 test as fleet_prepare_kernel (cache_aware.rs:669-670); used for mode dispatch only
+        if (m.loads.empty()) return false;
+        uint64_t mn = ~0ULL, mx = 0;
+        for (uint64_t l : m.loads) { mn = std::min(mn, l); mx = std::max(mx, l); }
+        volatile float fmax = (float)mx;
+        volatile float fprod = (float)mn * cfg.balance_rel_threshold;
+        return (mx - mn) > cfg.balance_abs_threshold && fmax > fprod;
+    }
+
+    // Approximate-token-tree mode (cache_aware.rs:834-904) and the imbalanced path's tree update (:380-402).
+    // Requests are processed in contiguous segments whose first-page keys are pairwise distinct: such requests touch
+    // disjoint subtrees, so matching a whole segment against one snapshot on the GPU and then applying touches + inserts
+    // on the host in request order reproduces the reference's one-by-one semantics exactly (timestamps included).
+    void tree_select(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info,
+                     bool decide, int32_t* out_tenant) {
+        TokenTreeIndex& tree = tree_of(m, true);
+        Lane& lane = lanes[0];
+        const uint64_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
+        lane.d_tokens.reserve(std::max<uint64_t>(total, 1) * 4 + 16);
+        lane.d_offsets.reserve(((size_t)n + 1) * 4);
+        lane.d_out.reserve(std::max<uint32_t>(n, 1) * 4);
+        lane.d_info.reserve(std::max<uint32_t>(n, 1) * sizeof(smgx_decision_info));
+        lane.d_path.reserve((size_t)std::max<uint32_t>(n, 1) * kPathCap * 4);
+        lane.d_path_len.reserve(std::max<uint32_t>(n, 1) * 4);
+        lane.d_tenant.reserve(std::max<uint32_t>(n, 1) * 4);
+        if (n == 0) return;
+        if (total) SMGX_CUDA(cudaMemcpyAsync(lane.d_tokens.ptr, tokens + base, total * 4, cudaMemcpyHostToDevice, lane.stream));
+        SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+        std::vector<smgx_decision_info> info(n);
+        std::vector<uint32_t> path((size_t)n * kPathCap), path_len(n);
+        std::vector<int32_t> ten(n);
+        std::unordered_set<uint64_t> seen;
+        uint32_t seg = 0;
+        while (seg < n) {
+            seen.clear();
+            uint32_t end = seg;
+            while (end < n) {
+                const uint32_t len = offsets[end + 1] - offsets[end];
+                if (len >= kPage) {
+                    uint64_t sum = 0;
+                    const uint32_t* pg = tokens + offsets[end];
+                    for (uint32_t i = 0; i < kPage; ++i) sum += ((uint64_t)pg[i] + 1) * page_mult(i);
+                    if (!seen.insert(page_finish(sum, 0)).second) break;
+                }
+                ++end;
+            }
+            EventIndexView ixv;
+            FleetView fv;
+            sync_state(m, &ixv, &fv);
+            sync_tenant_map(m);
+            TokenTreeView tv = tree.flush(lane.stream, &launches);
+            TreeSelectArgs a;
+            a.tokens = lane.d_tokens.as<uint32_t>() - base; a.offsets = lane.d_offsets.as<uint32_t>();
+            a.first = seg; a.count = end - seg;
+            a.out_idx = lane.d_out.as<int32_t>(); a.out_info = lane.d_info.as<smgx_decision_info>();
+            a.out_path = lane.d_path.as<uint32_t>(); a.out_path_len = lane.d_path_len.as<uint32_t>(); a.out_tenant = lane.d_tenant.as<int32_t>();
+            a.cache_threshold = cfg.cache_threshold; a.decide = decide ? 1 : 0;
+            launch_tree_select(tv, fv, m.d_slice_of_tenant.as<int32_t>(), m.d_flags.as<uint8_t>(), (uint32_t)tenants.names.size(), a, lane.stream);
+            ++launches;
+            const uint32_t cnt = end - seg;
+            SMGX_CUDA(cudaMemcpyAsync(out_idx + seg, lane.d_out.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(info.data() + seg, lane.d_info.as<smgx_decision_info>() + seg, (size_t)cnt * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(path.data() + (size_t)seg * kPathCap, lane.d_path.as<uint32_t>() + (size_t)seg * kPathCap, (size_t)cnt * kPathCap * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(path_len.data() + seg, lane.d_path_len.as<uint32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(ten.data() + seg, lane.d_tenant.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+            for (uint32_t r = seg; r < end; ++r) {
+                const uint32_t* tk = tokens + offsets[r];
+                const uint32_t len = offsets[r + 1] - offsets[r];
+                if (decide && info[r].branch == SMGX_BR_NO_HEALTHY) continue;   // returns None before touching anything (:653-655)
+                // match side effects: touch_tenant on every matched node, in order (:685-689)
+                if (path_len[r] <= kPathCap) tree.apply_match_touches(path.data() + (size_t)r * kPathCap, path_len[r]);
+                else { TreeMatch hm = tree.match_prefix_host(tk, len, false); tree.apply_match_touches(hm.path.data(), (uint32_t)hm.path.size()); }
+                if (!decide) continue;
+                const uint8_t br = info[r].branch;
+                if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
+                    const size_t idx = (size_t)out_idx[r];
+                    tree.insert_tokens(tk, len, tenants.intern(m.urls[idx]));   // :868 / :396
+                    if (idx < m.processed.size()) ++m.processed[idx];
+                }
+            }
+            seg = end;
+        }
+        if (out_info) memcpy(out_info, info.data(), (size_t)n * sizeof(smgx_decision_info));
+        if (out_tenant) memcpy(out_tenant, ten.data(), (size_t)n * 4);
+    }
+
     Lane& free_lane() {
         for (auto& l : lanes) if (!l.busy) return l;
         throw Error(SMGX_INVALID_ARGUMENT, "all pipeline lanes are in flight; call smgx_wait first");
@@ -222,6 +339,14 @@ public:
 
     uint64_t submit_host(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info) {
         SMGX_REQUIRE(n <= cfg.max_batch, "batch larger than max_batch");
+        if (!has_event_indexer(m) || (host_imbalanced(m) && m.token_tree)) {
+            // approximate token tree (or the imbalanced path's tree update): completes synchronously
+            for (uint32_t i = 0; i < n; ++i) SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+            tree_select(m, tokens, offsets, n, out_idx, out_info, true, nullptr);
+            Lane& l = free_lane();
+            l.busy = true; l.ticket = ++ticket_seq; l.model = &m; l.host_out = out_idx; l.n = 0;   // n = 0: processed already counted
+            return l.ticket;
+        }
         SMGX_REQUIRE(m.urls.size() > 0 || true, "");
         Lane& lane = free_lane();
         uint32_t max_len = 0;
@@ -270,6 +395,8 @@ public:
         throw Error(SMGX_INVALID_ARGUMENT, "unknown or already completed ticket");
     }
 
+    TenantTable tenants;         // TENANT_INTERN_POOL (token_tree.rs:160-176)
+    uint64_t token_ts = 0;       // GLOBAL_TIMESTAMP (token_tree.rs:179), shared by every token tree of the policy
     smgx_cache_aware_config cfg;
     int sm_count = 148;
     size_t l2_bytes = 126u << 20;
@@ -363,6 +490,9 @@ smgx_status smgx_set_workers(smgx_policy* p, const char* model_key, const char* 
         m.flags.assign(n, 3);
         m.processed.assign(n, 0);
         m.fleet_dirty = true;
+        m.fleet_dirty_tenant = true;
+        p->impl.tree_of(m, true);                                   // init_workers creates the trees (cache_aware.rs:231-247)
+        for (auto& u : m.urls) p->impl.tenants.intern(u);
         return SMGX_SUCCESS;
     });
 }
@@ -391,6 +521,9 @@ smgx_status smgx_add_worker(smgx_policy* p, const char* model_key, const char* u
         if (std::find(m.urls.begin(), m.urls.end(), url) == m.urls.end()) {
             m.urls.emplace_back(url); m.loads.push_back(0); m.flags.push_back(3); m.processed.push_back(0);
             m.fleet_dirty = true;
+            m.fleet_dirty_tenant = true;
+            p->impl.tree_of(m, true);
+            p->impl.tenants.intern(url);
         }
         return SMGX_SUCCESS;
     });
@@ -580,6 +713,118 @@ smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, con
         if (nw) SMGX_CUDA(cudaMemcpyAsync(ts.data(), ixv.tree_sizes, (size_t)nw * 8, cudaMemcpyDeviceToHost, l.stream));
         SMGX_CUDA(cudaStreamSynchronize(l.stream));
         for (uint32_t w = 0; w < nw; ++w) { out_scores[w] = sc[w]; if (out_tree_sizes) out_tree_sizes[w] = ts[w]; }
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- approximate token tree: kv_index::TokenTree (crates/kv_index/src/token_tree.rs) ----
+smgx_status smgx_tree_create(smgx_policy* p, const char* model_key, int eviction_policy, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(eviction_policy >= 0 && eviction_policy <= 5, "unknown eviction policy");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        m.token_tree = std::make_unique<TokenTreeIndex>(&p->impl.tenants, &p->impl.token_ts, (EvictPolicy)eviction_policy);
+        m.token_tree->device_enabled = p->impl.cfg.device_id >= 0;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_insert_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, uint32_t n, const char* tenant, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(tenant);
+        SMGX_REQUIRE(n == 0 || tokens, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        TokenTreeIndex& t = p->impl.tree_of(m, true);
+        if (n >= kPage) t.insert_tokens(tokens, n, p->impl.tenants.intern(tenant));   // shorter inputs return before interning (:403-410)
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_match_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, uint32_t n, uint32_t* out_matched,
+                                   uint32_t* out_input, char* out_tenant, uint32_t tenant_cap, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_matched); NONNULL(out_input);
+        SMGX_REQUIRE(n == 0 || tokens, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, true);
+        P.tree_of(m, true);
+        uint32_t offs[2] = {0, n};
+        uint32_t dummy = 0;
+        int32_t idx = -1, ten = -1;
+        smgx_decision_info di{};
+        P.tree_select(m, n ? tokens : &dummy, offs, 1, &idx, &di, false, &ten);
+        *out_matched = di.matched;
+        *out_input = di.input;
+        if (out_tenant && tenant_cap) {
+            std::string name = "empty";
+            if (ten >= 0) name = P.tenants.names[(size_t)ten];
+            else if (n < kPage) { int32_t rt = m.token_tree->any_tenant(0); if (rt >= 0) name = P.tenants.names[(size_t)rt]; }   // :620-629
+            size_t k = std::min<size_t>(name.size(), tenant_cap - 1);
+            memcpy(out_tenant, name.data(), k);
+            out_tenant[k] = 0;
+        }
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_evict_tenant(smgx_policy* p, const char* model_key, const char* tenant, uint64_t max_tokens, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(tenant);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        int64_t t = p->impl.tenants.find(tenant);
+        if (t >= 0 && m.token_tree) m.token_tree->evict_tenant((uint32_t)t, (size_t)max_tokens);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err) {   // CacheAwarePolicy::evict_cache (cache_aware.rs:311-352)
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        for (auto& kv : p->impl.models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_tenant_size(smgx_policy* p, const char* model_key, const char* tenant, uint64_t* out, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(tenant); NONNULL(out);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        int64_t t = p->impl.tenants.find(tenant);
+        *out = (t >= 0 && m.token_tree) ? m.token_tree->tenant_token_size((uint32_t)t) : 0;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_clear(smgx_policy* p, const char* model_key, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        if (m.token_tree) m.token_tree->clear();
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_entries(smgx_policy* p, const char* model_key, char** out_text, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_text);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        std::string s;
+        if (m.token_tree) {
+            std::vector<std::pair<std::vector<uint32_t>, std::vector<std::pair<uint32_t, uint64_t>>>> es;
+            m.token_tree->entries(es);
+            for (auto& e : es) {
+                for (size_t i = 0; i < e.first.size(); ++i) { if (i) s.push_back(','); s += std::to_string(e.first[i]); }
+                s.push_back('|');
+                for (size_t i = 0; i < e.second.size(); ++i) { if (i) s.push_back(';'); s += p->impl.tenants.names[e.second[i].first] + "=" + std::to_string(e.second[i].second); }
+                s.push_back('\n');
+            }
+        }
+        char* c = (char*)malloc(s.size() + 1);
+        if (!c) throw std::bad_alloc();
+        memcpy(c, s.c_str(), s.size() + 1);
+        *out_text = c;
         return SMGX_SUCCESS;
     });
 }

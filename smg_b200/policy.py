@@ -208,6 +208,66 @@ class KvEventMonitor:
         self.policy._h.call("smgx_indexer_set_block_size", model.encode(), block_size)
 
 
+class TokenMatchResult:  # kv_index::PrefixMatchResult (token_tree.rs:137-144)
+    def __init__(self, tenant, matched, inp):
+        self.tenant, self.matched_token_count, self.input_token_count = tenant, matched, inp
+
+
+LRU, LFU, FIFO, MRU, FILO, PRIORITY = range(6)   # kv_index::EvictionPolicy (token_tree.rs:60-75)
+
+
+class TokenTree:
+    """kv_index::TokenTree bound to (policy handle, model): mutations on the host-authoritative tree inside the library,
+    match_prefix_with_counts on the GPU mirror."""
+
+    def __init__(self, handle: _Handle, model: str = UNKNOWN_MODEL_ID, policy: int = LRU):
+        self.h, self.model = handle, model.encode()
+        self.h.call("smgx_tree_create", self.model, policy)
+
+    @classmethod
+    def standalone(cls, policy: int = LRU, device_id: int = 0):
+        return cls(_Handle(CacheAwareConfig(eviction_interval_secs=0), device_id), UNKNOWN_MODEL_ID, policy)
+
+    def insert_tokens(self, tokens, tenant: str):
+        t = _u32(tokens)
+        self.h.call("smgx_tree_insert_tokens", self.model, _p(t), t.size, tenant.encode())
+
+    def match_prefix_with_counts(self, tokens) -> TokenMatchResult:
+        t = _u32(tokens)
+        m, n = C.c_uint32(), C.c_uint32()
+        buf = C.create_string_buffer(1024)
+        self.h.call("smgx_tree_match_tokens", self.model, _p(t), t.size, C.byref(m), C.byref(n), C.cast(buf, C.c_void_p), 1024)
+        return TokenMatchResult(buf.value.decode(), m.value, n.value)
+
+    def evict_tenant(self, tenant: str, max_tokens: int):
+        self.h.call("smgx_tree_evict_tenant", self.model, tenant.encode(), max_tokens)
+
+    def evict_tenant_by_size(self, max_size: int):
+        self.h.call("smgx_evict_cache", max_size)
+
+    def tenant_token_size(self, tenant: str) -> int:
+        out = C.c_uint64()
+        self.h.call("smgx_tree_tenant_size", self.model, tenant.encode(), C.byref(out))
+        return out.value
+
+    def clear(self):
+        self.h.call("smgx_tree_clear", self.model)
+
+    def entries(self):
+        out = C.c_void_p()
+        self.h.call("smgx_tree_entries", self.model, C.byref(out))
+        text = C.cast(out, C.c_char_p).value.decode()
+        self.h.L.smgx_free_string(out)
+        res = []
+        for line in text.split("\n"):
+            if not line:
+                continue
+            toks, tens = line.split("|")
+            res.append(([int(x) for x in toks.split(",")] if toks else [],
+                        [(kv.rsplit("=", 1)[0], int(kv.rsplit("=", 1)[1])) for kv in tens.split(";") if kv]))
+        return res
+
+
 class TiktokenTokenizer:
     """tokenizer::TiktokenTokenizer (crates/tokenizer/src/tiktoken.rs:132) on the GPU, bound to (policy handle, model).
     encode() keeps the reference's behaviour of always recognising special-token strings (tiktoken.rs:444-462)."""
@@ -358,6 +418,14 @@ class CacheAwarePolicy:
                      _p(toks) if want_tokens else None, _p(toff) if want_tokens else None, cap)
         tokens = [toks[toff[i]:toff[i + 1]].tolist() for i in range(n)] if want_tokens else None
         return out[:n], [info[i] for i in range(n)], tokens
+
+    def evict_cache(self, max_size: int):  # cache_aware.rs:311-352
+        self._h.call("smgx_evict_cache", max_size)
+
+    def token_tree(self, model: str = UNKNOWN_MODEL_ID) -> TokenTree:
+        t = TokenTree.__new__(TokenTree)
+        t.h, t.model = self._h, model.encode()
+        return t
 
     def take_processed(self, model: str = UNKNOWN_MODEL_ID, n: Optional[int] = None):
         n = n if n is not None else len(self._slices.get(model, ()))
