@@ -74,6 +74,24 @@ typedef struct smgx_decision_info {
     uint8_t reserved[3];
 } smgx_decision_info;
 
+/* Worker-id-sharded fleets (BASELINE config 4: 4096 workers, 512 per GPU).  Each shard holds a contiguous
+ * range of the global worker slice and emits, per request, its best local candidate; the shards' candidates are exchanged
+ * (all-gather, 24 B per request per shard) and merged with smgx_shard_reduce_device on every rank. */
+typedef struct smgx_shard_candidate {
+    uint32_t score;      /* overlap blocks of the shard's best eligible worker; 0 = no eligible overlap in this shard */
+    uint32_t local_idx;  /* its index in the SHARD's slice */
+    uint64_t load;       /* tie-breaks of score_overlap (cache_aware.rs:806-818) */
+    uint64_t tree_size;
+} smgx_shard_candidate;
+typedef struct smgx_shard_fleet {   /* the select_worker prologue of one shard (cache_aware.rs:651-670) */
+    int32_t min_load_idx;    /* first argmin load() over the shard's healthy workers, -1 if none */
+    int32_t first_healthy;
+    uint32_t n_healthy;
+    uint32_t imbalanced;     /* shard-local; the merged gate is recomputed from min_load / max_load */
+    uint64_t min_load, max_load;
+    uint64_t min_healthy_load;
+} smgx_shard_fleet;
+
 typedef struct smgx_policy smgx_policy;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -195,6 +213,16 @@ smgx_status smgx_select_batch_tokens_device(smgx_policy* p, const char* model_ke
 smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
                                            const uint32_t* const* d_offsets, const uint32_t* n, uint32_t max_request_tokens,
                                            int32_t* const* d_out_worker_idx, char** err);
+/* Sharded event-driven pick, step 1 (every rank, on its shard): per-request best local candidate + the shard's fleet summary.
+ * All pointers are device pointers. */
+smgx_status smgx_shard_candidates_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens,
+                                         const uint32_t* d_offsets, uint32_t n, uint32_t max_request_tokens,
+                                         smgx_shard_candidate* d_out_cand, smgx_shard_fleet* d_out_fleet, char** err);
+/* Step 2 (every rank, after the exchange): d_cands = [world][n], d_fleets = [world], global_base[g] = global slice index of
+ * shard g's first worker (host array).  Writes global slice indices (−1 = None). */
+smgx_status smgx_shard_reduce_device(smgx_policy* p, uint32_t lane, const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets,
+                                     const uint32_t* global_base, uint32_t world, uint32_t n, int32_t* d_out_worker_idx,
+                                     smgx_decision_info* d_out_info, char** err);
 void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err);
 void smgx_device_free(smgx_policy* p, void* dptr);
 smgx_status smgx_memcpy_h2d(smgx_policy* p, void* dptr, const void* host, size_t bytes, char** err);

@@ -349,11 +349,12 @@ __global__ void __launch_bounds__(128) event_search_thread_kernel(EventIndexView
     bool have1 = false;
     PrefixCache pc{-1, 0};
     bool searching = false;
+    const bool cand_mode = b.cand != nullptr;   // sharded fleet: the healthy/imbalance shortcuts are global decisions (reduce step)
     if (valid) {
         const uint32_t off = __ldg(b.offsets + r);
         ntok = __ldg(b.offsets + r + 1) - off;
-        if (fd.n_healthy == 0) {
-        } else if (fd.imbalanced) {
+        if (!cand_mode && fd.n_healthy == 0) {
+        } else if (!cand_mode && fd.imbalanced) {
             out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
         } else {
             nb = a.block_size ? ntok / a.block_size : 0;
@@ -421,23 +422,29 @@ __global__ void __launch_bounds__(128) event_search_thread_kernel(EventIndexView
     }
     if (!valid) return;
     uint32_t matched = 0;
+    Cand c{false, 0, 0, -1};
     if (searching) {
         uint64_t winset = st.active & elig;
         uint32_t score = nb;
         if (!winset) { winset = st.last; score = st.last_score; }
         if (winset) {
-            Cand c{false, 0, 0, -1};
             uint64_t w = winset;
             while (w) { int id = __ffsll((long long)w) - 1; w &= w - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
             out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
         }
+    }
+    if (cand_mode) {
+        smgx_shard_candidate sc;
+        sc.score = c.have ? matched : 0; sc.local_idx = c.have ? (uint32_t)c.sl : 0xFFFFFFFFu; sc.load = c.ld; sc.tree_size = c.ts;
+        b.cand[r] = sc;
+        return;
     }
     if (branch == SMGX_BR_EVENT_MIN_LOAD) out = fd.min_load_idx;
     write_pick(b, r, out, branch, matched, ntok);
 }
 
 // ---- search + pick, wider fleets (65..2048 interned workers): one WARP per request, one u64 set word per lane ----
-__device__ __forceinline__ int32_t warp_arg_best(const EventIndexView& v, const FleetView& f, uint64_t winset, int lane) {
+__device__ __forceinline__ Cand warp_arg_best(const EventIndexView& v, const FleetView& f, uint64_t winset, int lane) {
     Cand c{false, 0, 0, -1};
     uint64_t w = winset;
     while (w) {
@@ -453,7 +460,7 @@ __device__ __forceinline__ int32_t warp_arg_best(const EventIndexView& v, const 
         int32_t os = __shfl_xor_sync(FULL, c.sl, d);
         if (oh) c.consider(os, ol, ot);
     }
-    return c.sl;
+    return c;
 }
 
 __global__ void __launch_bounds__(256) event_search_warp_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
@@ -463,12 +470,14 @@ __global__ void __launch_bounds__(256) event_search_warp_kernel(EventIndexView v
     const FleetDerived fd = *f.derived;
     const uint64_t elig = (uint32_t)lane < v.words ? f.elig[lane] : 0ULL;
     const BatchDesc& b = a.b[blockIdx.y];
+    const bool cand_mode = b.cand != nullptr;
     for (uint32_t r = blockIdx.x * wpc + wic; r < b.n; r += gridDim.x * wpc) {
         const uint32_t off = b.offsets[r], ntok = b.offsets[r + 1] - off;
         int32_t out = -1;
         uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
-        if (fd.n_healthy == 0) {
-        } else if (fd.imbalanced) {
+        Cand best{false, 0, 0, -1};
+        if (!cand_mode && fd.n_healthy == 0) {
+        } else if (!cand_mode && fd.imbalanced) {
             out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
         } else {
             const uint32_t nb = a.block_size ? ntok / a.block_size : 0;
@@ -486,9 +495,17 @@ __global__ void __launch_bounds__(256) event_search_warp_kernel(EventIndexView v
                     else { winset = sink.last; score = sink.last_score; }
                     __syncwarp();
                 }
-                if (set_any<false>(winset)) { out = warp_arg_best(v, f, winset, lane); branch = SMGX_BR_EVENT_OVERLAP; matched = score; }
+                if (set_any<false>(winset)) { best = warp_arg_best(v, f, winset, lane); out = best.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score; }
                 else { out = fd.min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD; }
             }
+        }
+        if (cand_mode) {
+            if (lane == 0) {
+                smgx_shard_candidate sc;
+                sc.score = best.have ? matched : 0; sc.local_idx = best.have ? (uint32_t)best.sl : 0xFFFFFFFFu; sc.load = best.ld; sc.tree_size = best.ts;
+                b.cand[r] = sc;
+            }
+            continue;
         }
         if (lane == 0) write_pick(b, r, out, branch, matched, ntok);
     }
@@ -568,6 +585,7 @@ __global__ void __launch_bounds__(256) fleet_prepare_kernel(FleetRaw raw, FleetD
         d.n_healthy = s_nh[0];
         d.min_load_idx = s_nh[0] ? s_hidx[0] : -1;
         d.first_healthy = s_nh[0] ? s_fh[0] : -1;
+        d.min_healthy_load = s_nh[0] ? s_hl[0] : 0;
         // usize→f32 casts round to nearest-even; the product is an f32 multiply (no FMA contraction possible here)
         float fmax = __ull2float_rn(mx0), fmin = __ull2float_rn(mn0);
         d.imbalanced = ((mx0 - mn0) > raw.abs_threshold && fmax > __fmul_rn(fmin, raw.rel_threshold)) ? 1u : 0u;
@@ -627,6 +645,62 @@ void launch_content_hashes(const uint32_t* d_tokens, uint32_t n_tokens, uint32_t
     uint32_t nb = block_size ? n_tokens / block_size : 0;
     if (!nb) return;
     content_hashes_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d_tokens, n_tokens, block_size, d_out);
+    SMGX_CUDA(cudaGetLastError());
+}
+
+namespace {
+// Merge step of the worker-id-sharded pick: one thread per request walks the shards in rank order (= global slice order),
+// keeping max_by_key((score, Reverse(load), Reverse(tree_size))) with LAST max — the same comparison score_overlap makes over
+// the whole fleet (cache_aware.rs:806-818); the prologue (healthy count, min/max load, f32 imbalance gate, first min load) is
+// re-derived from the shards' summaries.
+__global__ void __launch_bounds__(256) shard_reduce_kernel(const smgx_shard_candidate* __restrict__ cands, const smgx_shard_fleet* __restrict__ fleets,
+                                                           const uint32_t* __restrict__ gbase, uint32_t world, uint32_t n, uint64_t abs_thr,
+                                                           float rel_thr, int32_t* __restrict__ out_idx, smgx_decision_info* __restrict__ out_info) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint64_t mn = ~0ULL, mx = 0, hl = ~0ULL;
+    uint32_t n_healthy = 0;
+    int32_t min_idx = -1;
+    for (uint32_t g = 0; g < world; ++g) {
+        const smgx_shard_fleet f = fleets[g];
+        mn = f.min_load < mn ? f.min_load : mn;
+        mx = f.max_load > mx ? f.max_load : mx;
+        n_healthy += f.n_healthy;
+        if (f.n_healthy && f.min_healthy_load < hl) { hl = f.min_healthy_load; min_idx = (int32_t)(gbase[g] + (uint32_t)f.min_load_idx); }   // strict <: FIRST min
+    }
+    int32_t out = -1;
+    uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+    if (n_healthy) {
+        const bool imbalanced = (mx - mn) > abs_thr && __ull2float_rn(mx) > __fmul_rn(__ull2float_rn(mn), rel_thr);
+        if (imbalanced) { out = min_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD; }
+        else {
+            bool have = false;
+            uint32_t bs = 0; uint64_t bl = 0, bt = 0; int32_t bi = -1;
+            for (uint32_t g = 0; g < world; ++g) {
+                const smgx_shard_candidate c = cands[(size_t)g * n + r];
+                if (c.score == 0 || c.local_idx == 0xFFFFFFFFu) continue;
+                const bool ge = !have || c.score > bs || (c.score == bs && (c.load < bl || (c.load == bl && c.tree_size <= bt)));   // >= : LAST max
+                if (ge) { have = true; bs = c.score; bl = c.load; bt = c.tree_size; bi = (int32_t)(gbase[g] + c.local_idx); }
+            }
+            if (have) { out = bi; branch = SMGX_BR_EVENT_OVERLAP; matched = bs; }
+            else { out = min_idx; branch = SMGX_BR_EVENT_MIN_LOAD; }
+        }
+    }
+    out_idx[r] = out;
+    if (out_info) {
+        smgx_decision_info di;
+        di.matched = matched; di.input = 0; di.branch = (uint8_t)branch;
+        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        out_info[r] = di;
+    }
+}
+}  // namespace
+
+void launch_shard_reduce(const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets, const uint32_t* d_global_base, uint32_t world,
+                         uint32_t n, uint64_t abs_threshold, float rel_threshold, int32_t* d_out_idx, smgx_decision_info* d_out_info,
+                         cudaStream_t stream) {
+    if (!n) return;
+    shard_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_cands, d_fleets, d_global_base, world, n, abs_threshold, rel_threshold, d_out_idx, d_out_info);
     SMGX_CUDA(cudaGetLastError());
 }
 

@@ -16,7 +16,9 @@ struct FleetDerived {
     uint32_t n_healthy;
     uint32_t imbalanced;     // (max-min) > abs_thr && (max as f32) > (min as f32 * rel_thr)   (cache_aware.rs:669-670)
     uint64_t min_load, max_load;
+    uint64_t min_healthy_load;   // load of min_load_idx (lets worker-id shards be merged)
 };
+static_assert(sizeof(FleetDerived) == sizeof(smgx_shard_fleet), "smgx_shard_fleet mirrors FleetDerived");
 struct FleetView {
     const FleetDerived* derived;
     const int32_t* slice_of_id;   // [id] → slice index or -1
@@ -53,6 +55,7 @@ struct BatchDesc {
     smgx_decision_info* out_info;  // device, n (nullable)
     uint32_t n;
     uint32_t hash_base;            // first row of this batch in the hash scratch
+    smgx_shard_candidate* cand;    // non-null: worker-id-sharded fleet — emit this shard's best candidate instead of a pick
 };
 struct MultiArgs {
     BatchDesc b[kMaxMultiBatches];
@@ -72,5 +75,10 @@ void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uin
 void launch_content_hashes(const uint32_t* d_tokens, uint32_t n_tokens, uint32_t block_size, uint64_t* d_out, cudaStream_t stream);
 
 void launch_fill(uint32_t* d, uint32_t value, size_t n_words, cudaStream_t stream);
+
+// Merge of per-shard candidates (worker-id-sharded fleets): [world][n] candidates + [world] fleet summaries → picks.
+void launch_shard_reduce(const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets, const uint32_t* d_global_base, uint32_t world,
+                         uint32_t n, uint64_t abs_threshold, float rel_threshold, int32_t* d_out_idx, smgx_decision_info* d_out_info,
+                         cudaStream_t stream);
 
 }  // namespace smgx

@@ -112,7 +112,7 @@ public:
                 m.token_tree.reset();
                 m.d_slice_of_tenant.release();
             }
-            d_err.release(); d_flush.release(); scratch.release(); scratch2.release();
+            d_err.release(); d_flush.release(); scratch.release(); scratch2.release(); d_gbase.release();
             if (state_ready) cudaEventDestroy(state_ready);
             if (ctrl) cudaStreamDestroy(ctrl);
         }
@@ -195,7 +195,9 @@ public:
 
     // Enqueue the kernels of up to kMaxMultiBatches token batches on `lane` (device pointers).
     void enqueue_batches(ModelState& m, Lane& lane, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens) {
-        if (!has_event_indexer(m))
+        const bool cand_mode = count && descs[0].cand != nullptr;   // a worker-id shard may legitimately hold no blocks yet
+        if (cand_mode && !m.indexer) throw Error(SMGX_NOT_FOUND, "no event indexer for this model");
+        if (!cand_mode && !has_event_indexer(m))
             throw Error(SMGX_UNKNOWN_ERROR,
                         "model has no populated KV-event indexer: the approximate token-tree mode (cache_aware.rs:834-904) is not part of this "
                         "build yet — there is no CPU fallback");
@@ -219,7 +221,7 @@ public:
     }
     void enqueue_tokens(ModelState& m, Lane& lane, const uint32_t* d_tokens, const uint32_t* d_offsets, uint32_t n, uint32_t max_req_tokens,
                         int32_t* d_out, smgx_decision_info* d_info) {
-        BatchDesc d{d_tokens, d_offsets, d_out, d_info, n, 0};
+        BatchDesc d{d_tokens, d_offsets, d_out, d_info, n, 0, nullptr};
         enqueue_batches(m, lane, &d, 1, max_req_tokens);
     }
 
@@ -406,7 +408,7 @@ public:
     std::vector<Lane> lanes;
     cudaStream_t ctrl = nullptr;
     cudaEvent_t state_ready = nullptr;
-    DevBuf d_err, d_flush, scratch, scratch2;
+    DevBuf d_err, d_flush, scratch, scratch2, d_gbase;
     uint64_t launches = 0;
     uint64_t ticket_seq = 0;
 };
@@ -1018,9 +1020,51 @@ smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key
         for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxMultiBatches, ++chunk_no) {
             BatchDesc d[kMaxMultiBatches];
             uint32_t cnt = std::min<uint32_t>(kMaxMultiBatches, n_batches - j0);
-            for (uint32_t k = 0; k < cnt; ++k) d[k] = BatchDesc{d_tokens[j0 + k], d_offsets[j0 + k], d_out_worker_idx[j0 + k], nullptr, n[j0 + k], 0};
+            for (uint32_t k = 0; k < cnt; ++k) d[k] = BatchDesc{d_tokens[j0 + k], d_offsets[j0 + k], d_out_worker_idx[j0 + k], nullptr, n[j0 + k], 0, nullptr};
             P.enqueue_batches(m, P.lanes[chunk_no % P.lanes.size()], d, cnt, cap);
         }
+        return SMGX_SUCCESS;
+    });
+}
+
+smgx_status smgx_shard_candidates_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens, const uint32_t* d_offsets,
+                                         uint32_t n, uint32_t max_request_tokens, smgx_shard_candidate* d_out_cand, smgx_shard_fleet* d_out_fleet,
+                                         char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(d_out_cand); NONNULL(d_out_fleet);
+        SMGX_REQUIRE(n == 0 || (d_tokens && d_offsets), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(lane < P.lanes.size(), "lane out of range");
+        ModelState& m = P.model(model_key, false);
+        uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
+        Lane& L = P.lanes[lane];
+        if (n) {
+            BatchDesc d{d_tokens, d_offsets, nullptr, nullptr, n, 0, d_out_cand};
+            P.enqueue_batches(m, L, &d, 1, cap);
+        }
+        // the shard's select_worker prologue, as computed by fleet_prepare_kernel for this fleet snapshot
+        SMGX_CUDA(cudaMemcpyAsync(d_out_fleet, m.d_derived.ptr, sizeof(smgx_shard_fleet), cudaMemcpyDeviceToDevice, L.stream));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_shard_reduce_device(smgx_policy* p, uint32_t lane, const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets,
+                                     const uint32_t* global_base, uint32_t world, uint32_t n, int32_t* d_out_worker_idx,
+                                     smgx_decision_info* d_out_info, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(d_cands); NONNULL(d_fleets); NONNULL(global_base); NONNULL(d_out_worker_idx);
+        SMGX_REQUIRE(world >= 1 && world <= 64, "world out of range");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(lane < P.lanes.size(), "lane out of range");
+        Lane& L = P.lanes[lane];
+        P.d_gbase.reserve(64 * 4);
+        SMGX_CUDA(cudaMemcpyAsync(P.d_gbase.ptr, global_base, (size_t)world * 4, cudaMemcpyHostToDevice, L.stream));
+        launch_shard_reduce(d_cands, d_fleets, P.d_gbase.as<uint32_t>(), world, n, P.cfg.balance_abs_threshold, P.cfg.balance_rel_threshold,
+                            d_out_worker_idx, d_out_info, L.stream);
+        ++P.launches;
         return SMGX_SUCCESS;
     });
 }
