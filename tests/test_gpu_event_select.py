@@ -268,8 +268,8 @@ def test_index_updates_between_batches_are_visible():
     ix.apply_removed(w1, [1])
     assert _sel(pol, ws, [1, 2, 3, 4]) == 1
     ix.apply_cleared(w2)
-    with pytest.raises(Exception, match="no populated KV-event indexer|token-tree"):
-        _sel(pol, ws, [1, 2, 3, 4])                         # empty indexer → falls through to the token tree (:723-729)
+    idx, info = pol.select_worker_batch(ws, [[1, 2, 3, 4]])   # empty indexer → falls through to the token tree (:723-729)
+    assert idx[0] == 1 and orc.BRANCHES[info[0].branch] == "tree_min_load"
 
 
 def test_multi_batch_device_path_matches_oracle():
