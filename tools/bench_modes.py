@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the headline bench line): approximate token-tree mode and the worker-id-sharded event mode.
+Writes one JSON object per mode to stdout.  Run on the GPU box:
+
+    python tools/bench_modes.py tree                       # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_modes.py sharded
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CFG = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=1.5, block_size=16)
+
+
+def tree_population(n_trunks, rng):
+    """SURVEY §8d config-2 tree shape, scaled: trunks of 8 pages × 32 branches of 8 pages × 32 leaves of 16 pages (512-token paths)."""
+    paths = []
+    for _ in range(n_trunks):
+        trunk = rng.integers(0, 50000, size=128, dtype=np.uint32)
+        for _b in range(32):
+            branch = rng.integers(0, 50000, size=128, dtype=np.uint32)
+            for _l in range(32):
+                paths.append(np.concatenate([trunk, branch, rng.integers(0, 50000, size=256, dtype=np.uint32)]))
+    return paths
+
+
+def tree_mode():
+    from oracle import orc
+    from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, synth
+    W, B, n_trunks = 64, 4096, int(os.environ.get("TRUNKS", "20"))
+    rng = np.random.default_rng(42)
+    paths = tree_population(n_trunks, rng)
+    urls = synth.worker_urls(W)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), max_batch=B, max_tokens_per_request=512)
+    ws = [BasicWorker(u) for u in urls]
+    for w, l in zip(ws, synth.poisson_loads(W, 8, 42)):
+        w.set_load(int(l))
+    pol.init_workers(ws)
+    tree = pol.token_tree()
+    orc.reset_globals()
+    op = orc.CacheAwarePolicy(eviction_interval_secs=0, **CFG)
+    op.set_workers(urls)
+    op.set_state([w.load() for w in ws], [1] * W, [1] * W)
+    ot = op.token_tree()
+    t0 = time.time()
+    for i, p in enumerate(paths):
+        tree.insert_tokens(p, urls[i % W])
+    t_build = time.time() - t0
+    for i, p in enumerate(paths):
+        ot.insert_tokens(p, urls[i % W])
+
+    def batch(seed):
+        r = np.random.default_rng(seed)
+        reqs = []
+        for _ in range(B):
+            u = r.random()
+            p = paths[int(r.integers(0, len(paths)))]
+            if u < 0.8:
+                reqs.append(p)
+            elif u < 0.9:
+                k = 16 * int(r.integers(1, 32))
+                reqs.append(np.concatenate([p[:k], r.integers(0, 50000, size=512 - k, dtype=np.uint32)]))
+            else:
+                reqs.append(r.integers(0, 50000, size=512, dtype=np.uint32))
+        flat = np.concatenate(reqs).astype(np.uint32)
+        return flat, (np.arange(B + 1, dtype=np.uint64) * 512).astype(np.uint32)
+
+    batches = [batch(100 + i) for i in range(4)]
+    # parity of the first batch, then timing
+    idx, _ = pol.select_worker_batch(ws, tokens=batches[0][0], offsets=batches[0][1])
+    want, _, _, t_cpu0 = op.select_batch_tokens(batches[0][0], batches[0][1].astype(np.uint64))
+    assert np.array_equal(idx, want), "tree-mode picks differ from the oracle"
+    t0 = time.perf_counter()
+    for b in batches[1:]:
+        pol.select_worker_batch(ws, tokens=b[0], offsets=b[1], want_info=False)
+    t_gpu = time.perf_counter() - t0
+    t_cpu = sum(op.select_batch_tokens(b[0], b[1].astype(np.uint64))[3] for b in batches[1:])
+    n = 3 * B
+    return {"mode": "approximate token tree (cache_aware.rs:834-904): GPU match+pick per conflict-free segment, host insert in request order",
+            "workers": W, "batch": B, "tree_paths": len(paths), "tree_nodes_approx": n_trunks * (1 + 32 + 1024), "tree_build_s": round(t_build, 2),
+            "smgx_decisions_per_s": n / t_gpu, "oracle_1core_decisions_per_s": n / t_cpu, "parity_first_batch": True,
+            "kernel_launches": pol.kernel_launches()}
+
+
+def sharded_mode():
+    import torch
+    import torch.distributed as dist
+    from smg_b200 import CacheAwareConfig, _lib, synth
+    from smg_b200.sharding import CAND_BYTES, FLEET_BYTES, ShardedEventRouter
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    W = 512 * world                    # config 4: 512 workers per GPU
+    B, T, bs = 4096, 512, 16
+    urls = synth.worker_urls(W)
+    router = ShardedEventRouter(urls, rank, world, CacheAwareConfig(eviction_interval_secs=0, **CFG), jump_size=64, device_id=local,
+                                max_batch=B, max_tokens_per_request=T)
+    n_seq = 31250
+    seqs = synth.gen_sequences(n_seq, T, 44)
+    flat = np.ascontiguousarray(seqs.reshape(-1))
+    P = T // bs
+    hashes = np.zeros(n_seq * P, np.uint64)
+    got = C.c_uint32()
+    for off in range(0, flat.size, 4096 * T):
+        part = flat[off:off + 4096 * T]
+        router.policy._h.call("smgx_content_hashes", part.ctypes.data_as(C.c_void_p), part.size, bs, hashes[off // bs:].ctypes.data_as(C.c_void_p),
+                              part.size // bs, C.byref(got))
+    ids = np.arange(1, n_seq * P + 1, dtype=np.uint64)
+    for s in range(n_seq):
+        g = s % W
+        if router.owns(g):
+            router.policy._h.call("smgx_indexer_apply_stored", router.indexer.model, router.local_id(g), ids[s * P:(s + 1) * P].ctypes.data_as(C.c_void_p),
+                                  hashes[s * P:(s + 1) * P].ctypes.data_as(C.c_void_p), P, None)
+    router.set_fleet_state(synth.poisson_loads(W, 8, 44), np.ones(W, np.uint8))
+    h, L = router._h, _lib.load()
+    q = synth.gen_queries(seqs, B, 44)
+    tokens, offsets = synth.ragged(q)
+    d_tok = torch.from_numpy(tokens.view(np.int32)).cuda()
+    d_off = torch.from_numpy(offsets.view(np.int32)).cuda()
+    cand = torch.empty(B * CAND_BYTES, dtype=torch.uint8, device="cuda")
+    fleet = torch.empty(FLEET_BYTES, dtype=torch.uint8, device="cuda")
+    all_c = torch.empty(world * B * CAND_BYTES, dtype=torch.uint8, device="cuda")
+    all_f = torch.empty(world * FLEET_BYTES, dtype=torch.uint8, device="cuda")
+    out = torch.empty(B, dtype=torch.int32, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())
+
+    def step():
+        h.call("smgx_shard_candidates_device", router.model, 0, vp(d_tok), vp(d_off), B, T, vp(cand), vp(fleet))
+        h.call("smgx_synchronize")                    # the library's lane stream → torch's stream
+        dist.all_gather_into_tensor(all_c, cand)
+        dist.all_gather_into_tensor(all_f, fleet)
+        torch.cuda.synchronize()
+        h.call("smgx_shard_reduce_device", 0, vp(all_c), vp(all_f), router.gbase.ctypes.data_as(C.c_void_p), world, B, vp(out), None)
+        h.call("smgx_synchronize")
+
+    for _ in range(5):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    K = 50
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    picks = out.cpu().numpy()
+    res = None
+    if rank == 0:
+        res = {"mode": "worker-id-sharded event pick (config 4 shape): candidates kernel per shard → NCCL all-gather (24 B/request/shard) → merge kernel",
+               "n_gpus": world, "workers": W, "workers_per_gpu": 512, "batch": B, "index_entries_total": n_seq * P,
+               "decisions_per_s": K * B / float(dt.item()), "ms_per_step": 1e3 * float(dt.item()) / K,
+               "picks_in_range": bool(picks.min() >= 0 and picks.max() < W), "distinct_workers_picked": int(len(set(picks.tolist())))}
+    dist.barrier()
+    dist.destroy_process_group()
+    return res
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "tree"
+    r = tree_mode() if mode == "tree" else sharded_mode()
+    if r is not None:
+        print(json.dumps(r), flush=True)
