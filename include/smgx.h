@@ -64,7 +64,18 @@ typedef struct smgx_cache_aware_config {
     int32_t device_id;                /* CUDA ordinal; -1 = host-mirror only (index writers work, every select fails) */
     uint32_t max_batch;               /* largest n accepted by one select call (sizes device staging); 0 → 65536 */
     uint32_t max_tokens_per_request;  /* sizes per-warp scratch; 0 → 32768 */
+    uint32_t tree_batch_mode;         /* smgx_tree_batch_mode; tree modes only (the event-driven mode never writes on the path) */
 } smgx_cache_aware_config;
+
+/* How a batch of tree-mode requests (token tree / string tree: every routed request also inserts) is serialised.
+ * select_worker takes &self and runs on many tokio tasks at once; it is not atomic, and the reference promises eventual
+ * consistency only between concurrent match and insert (token_tree.rs:1035-1037).
+ *   SEQUENTIAL: results equal calling select_worker one request at a time, in batch order (timestamps included).  The GPU walks
+ *               maximal runs of requests that cannot see each other's inserts (distinct first page / first char) per launch.
+ *   SNAPSHOT:   every request of the batch walks and decides against the pre-batch tree (one launch), then the match side
+ *               effects and the inserts are applied in batch order — the interleaving "all reads, then each task's writes" of
+ *               concurrent select_worker calls.  Identical to SEQUENTIAL whenever no two requests of a batch share a first page. */
+typedef enum smgx_tree_batch_mode { SMGX_TREE_BATCH_SEQUENTIAL = 0, SMGX_TREE_BATCH_SNAPSHOT = 1 } smgx_tree_batch_mode;
 
 /* Per-request detail, optional output of the select calls. */
 typedef struct smgx_decision_info {
@@ -164,6 +175,31 @@ smgx_status smgx_tree_tenant_size(smgx_policy* p, const char* model_key, const c
 smgx_status smgx_tree_clear(smgx_policy* p, const char* model_key, char** err);                                                     /* :997 */
 /* iter_entries (:1039) as text, one line per entry "tok,tok,…|tenant=ts;tenant=ts"; *out_text is callee-allocated (smgx_free_string). */
 smgx_status smgx_tree_entries(smgx_policy* p, const char* model_key, char** out_text, char** err);
+smgx_status smgx_set_tree_batch_mode(smgx_policy* p, uint32_t mode, char** err);
+
+/* ---- string tree: kv_index::Tree (crates/kv_index/src/string_tree.rs), HTTP text routing ----------------------- */
+/* Text is UTF-8 (Rust &str); counts are Unicode scalar values.  Mutations run on the host-authoritative tree inside the
+ * library; smgx_stree_match walks the GPU mirror.  One tree per model key, created by smgx_set_workers / on first use. */
+smgx_status smgx_stree_insert_text(smgx_policy* p, const char* model_key, const uint8_t* text, uint32_t n_bytes, const char* tenant, char** err); /* :393 */
+/* match_prefix_with_counts (:561-649): matched / input char counts and the tenant ("empty" when the node has none). */
+smgx_status smgx_stree_match(smgx_policy* p, const char* model_key, const uint8_t* text, uint32_t n_bytes, uint32_t* out_matched_chars,
+                             uint32_t* out_input_chars, char* out_tenant, uint32_t tenant_cap, char** err);
+/* prefix_match_tenant (:659-720) — not on the routing path; host walk.  Returns the matched prefix length in bytes. */
+smgx_status smgx_stree_prefix_match_tenant(smgx_policy* p, const char* model_key, const uint8_t* text, uint32_t n_bytes, const char* tenant,
+                                           uint32_t* out_matched_bytes, char** err);
+/* "tenant=chars\n" lines: maintained != 0 → get_tenant_char_count (:855), else get_used_size_per_tenant (:862). smgx_free_string. */
+smgx_status smgx_stree_sizes(smgx_policy* p, const char* model_key, int maintained, char** out_text, char** err);
+/* iter_entries (:1116-1221), pre-order, children in char order: records "path \x1f tenant=epoch;... \x1e". smgx_free_string. */
+smgx_status smgx_stree_entries(smgx_policy* p, const char* model_key, char** out_text, uint64_t* out_len, char** err);
+smgx_status smgx_stree_clear(smgx_policy* p, const char* model_key, char** err);
+smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err);
+
+/* ---- HTTP text routing: select_worker with info.request_text = Some(text), info.tokens = None ------------------ */
+/* select_worker_with_text (cache_aware.rs:907-974) and the imbalanced path's string-tree update (:403-425) for a batch:
+ * request i = text[offsets[i] .. offsets[i+1]) (valid UTF-8).  match_rate = matched chars / input chars (f32, strict >).
+ * out_info[i].matched / .input are char counts.  Batch serialisation: smgx_tree_batch_mode. */
+smgx_status smgx_select_batch_request_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                           int32_t* out_worker_idx, smgx_decision_info* out_info, char** err);
 
 /* ---- tokenizer: Tokenizer::encode for tiktoken-style models (crates/tokenizer/src/tiktoken.rs) ----------------- */
 /* TiktokenTokenizer::from_file (tiktoken.rs:219-268): `path` holds lines of `base64(token) rank` (load_tiktoken_bpe, :346-367);

@@ -18,8 +18,17 @@
  * Not restated: the mesh hash_index side effect (cache_aware.rs:397-401, 881-886, 950-956; blake3) — it never
  * feeds back into the pick. The "no tree for model → rand" branch (:896-903, :965-973) returns healthy[0] and
  * reports the whole healthy set as valid.
+ *
+ * "Snapshot batches" (begin_snapshot_batch / end_snapshot_batch): select_worker takes &self and is called from many
+ * tokio tasks at once; it is not atomic — a task's read-only walk, its match side effects and its insert can interleave
+ * with other tasks' (the reference promises eventual consistency only, token_tree.rs:1035-1037).  One admissible
+ * interleaving of a batch of concurrent calls is: every call performs its read-only walk + decision against the same
+ * tree state, then each call, in request order, applies its match side effects and its insert.  Between
+ * begin/end the policy executes exactly that interleaving (side effects are queued and replayed by end_snapshot_batch).
+ * With no intra-batch conflicts it is identical, timestamps included, to calling select_worker one by one.
  */
 #pragma once
+#include <functional>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -132,6 +141,13 @@ public:
         return with_text(ws, text ? *text : empty, healthy, model);
     }
 
+    void begin_snapshot_batch() { deferring_ = true; deferred_.clear(); }
+    void end_snapshot_batch() {
+        deferring_ = false;
+        for (auto& f : deferred_) f();
+        deferred_.clear();
+    }
+
     bool has_event_indexer(const std::string& model) const {  // :723-729
         if (!monitor_) return false;
         auto it = indexers_.find(model);
@@ -180,15 +196,17 @@ private:
         size_t idx = first_min_load(ws, healthy);
         if (has_tokens) {
             if (TokenTree* t = token_tree(model)) {
-                TokenMatch m = t->match_prefix_with_counts(tokens, n);
+                TokenMatch m = match_tokens(t, tokens, n);
                 d.matched = m.matched; d.input = m.input;
-                t->insert_tokens(tokens, n, ws[idx].url);
+                std::string url = ws[idx].url;
+                run_or_defer([t, tokens, n, url] { t->insert_tokens(tokens, n, url); });
             }
         } else if (text) {
             if (StringTree* t = string_tree(model)) {
-                StringMatch m = t->match_prefix_with_counts(*text);
+                StringMatch m = match_text(t, *text);
                 d.matched = m.matched; d.input = m.input;
-                t->insert_text(*text, ws[idx].url);
+                std::string url = ws[idx].url, tx = *text;
+                run_or_defer([t, tx, url] { t->insert_text(tx, url); });
             }
         }
         ws[idx].processed++;
@@ -252,17 +270,39 @@ private:
                          const std::string& model) {
         TokenTree* t = token_tree(model);
         if (!t) return random_healthy(healthy);
-        TokenMatch m = t->match_prefix_with_counts(tokens, n);
-        return tree_decide<TokenTree>(ws, m, healthy, [&](const std::string& url) { t->insert_tokens(tokens, n, url); });
+        TokenMatch m = match_tokens(t, tokens, n);
+        return tree_decide<TokenTree>(ws, m, healthy, [&](const std::string& url) {
+            run_or_defer([t, tokens, n, url] { t->insert_tokens(tokens, n, url); });   // `tokens` outlives the batch call
+        });
     }
     // cache_aware.rs:907-974
     Decision with_text(std::vector<Worker>& ws, const std::string& text, const std::vector<size_t>& healthy,
                        const std::string& model) {
         StringTree* t = string_tree(model);
         if (!t) return random_healthy(healthy);
-        StringMatch m = t->match_prefix_with_counts(text);
-        return tree_decide<StringTree>(ws, m, healthy, [&](const std::string& url) { t->insert_text(text, url); });
+        StringMatch m = match_text(t, text);
+        return tree_decide<StringTree>(ws, m, healthy, [&](const std::string& url) {
+            std::string tx = text;
+            run_or_defer([t, tx, url] { t->insert_text(tx, url); });
+        });
     }
+    // match + its side effects: immediate, or (snapshot batch) read-only now and side effects queued
+    TokenMatch match_tokens(TokenTree* t, const uint32_t* tokens, size_t n) {
+        if (!deferring_) return t->match_prefix_with_counts(tokens, n);
+        auto touches = std::make_shared<std::vector<TokenTree::PendingTouch>>();
+        TokenMatch m = t->match_prefix_with_counts(tokens, n, touches.get());
+        deferred_.push_back([t, touches] { t->apply_touches(*touches); });
+        return m;
+    }
+    StringMatch match_text(StringTree* t, const std::string& text) {
+        if (!deferring_) return t->match_prefix_with_counts(text);
+        auto eff = std::make_shared<StringTree::PendingEffect>();
+        StringMatch m = t->match_prefix_with_counts(text, eff.get());
+        deferred_.push_back([t, eff] { t->apply_match_effects(*eff); });
+        return m;
+    }
+    void run_or_defer(std::function<void()> f) { if (deferring_) deferred_.push_back(std::move(f)); else f(); }
+
     static Decision random_healthy(const std::vector<size_t>& healthy) {
         Decision d;
         d.idx = (int64_t)healthy[0]; d.branch = BR_NO_TREE_RANDOM;
@@ -271,6 +311,8 @@ private:
     }
 
     CacheAwareConfig cfg_;
+    bool deferring_ = false;
+    std::vector<std::function<void()>> deferred_;
     std::map<std::string, std::unique_ptr<StringTree>> string_trees_;
     std::map<std::string, std::unique_ptr<TokenTree>> token_trees_;
     bool monitor_ = false;

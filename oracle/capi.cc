@@ -232,6 +232,40 @@ double orc_policy_select_batch_tokens(void* h, const uint32_t* tokens, const uin
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// Same, as one "snapshot batch" (cache_aware.h): every request walks/decides against the pre-batch trees, then the
+// match side effects and inserts are applied in request order.
+double orc_policy_select_batch_tokens_snapshot(void* h, const uint32_t* tokens, const uint64_t* offsets, size_t n, int32_t* out_idx,
+                                               uint8_t* out_branch, uint32_t* out_matched) {
+    auto* b = (PolicyBox*)h;
+    auto t0 = std::chrono::steady_clock::now();
+    b->pol.begin_snapshot_batch();
+    for (size_t i = 0; i < n; ++i) {
+        Decision d = b->pol.select_worker(b->workers, nullptr, tokens + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), true);
+        out_idx[i] = (int32_t)d.idx;
+        if (out_branch) out_branch[i] = (uint8_t)d.branch;
+        if (out_matched) out_matched[i] = (uint32_t)d.matched;
+    }
+    b->pol.end_snapshot_batch();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// Batch of text requests (HTTP routing, cache_aware.rs:907-974): ragged UTF-8, offsets[n+1]; snapshot != 0 → snapshot batch.
+double orc_policy_select_batch_text(void* h, const char* text, const uint64_t* offsets, size_t n, int snapshot, int32_t* out_idx,
+                                    uint8_t* out_branch, uint32_t* out_matched, uint32_t* out_input) {
+    auto* b = (PolicyBox*)h;
+    auto t0 = std::chrono::steady_clock::now();
+    if (snapshot) b->pol.begin_snapshot_batch();
+    for (size_t i = 0; i < n; ++i) {
+        std::string t(text + offsets[i], (size_t)(offsets[i + 1] - offsets[i]));
+        Decision d = b->pol.select_worker(b->workers, &t, nullptr, 0, false);
+        out_idx[i] = (int32_t)d.idx;
+        if (out_branch) out_branch[i] = (uint8_t)d.branch;
+        if (out_matched) out_matched[i] = (uint32_t)d.matched;
+        if (out_input) out_input[i] = (uint32_t)d.input;
+    }
+    if (snapshot) b->pol.end_snapshot_batch();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 // Read-only event-mode scoring with `threads` persistent host threads (the reference's concurrent-read design:
 // select_worker takes &self, the index is only read, requests are spread over a tokio worker pool).  `steps` batches
 // are routed back to back: batch s = tokens/offsets of (s % n_batches); threads are spawned ONCE, every thread owns a

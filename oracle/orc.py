@@ -82,6 +82,8 @@ def lib():
         sig("orc_policy_string_tree", vp, vp, cp)
         sig("orc_policy_select", None, vp, cp, sz, C.c_int, vp, sz, C.c_int, vp, vp, sz)
         sig("orc_policy_select_batch_tokens", C.c_double, vp, vp, vp, sz, vp, vp, vp)
+        sig("orc_policy_select_batch_tokens_snapshot", C.c_double, vp, vp, vp, sz, vp, vp, vp)
+        sig("orc_policy_select_batch_text", C.c_double, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp)
         sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int)
         _lib = L
     return _lib
@@ -296,10 +298,8 @@ class Tree:
 
     def prefix_match_tenant(self, text, tenant):
         b = text.encode()
-        n = lib().orc_stree_prefix_match_tenant(self.h, b, len(b), tenant.encode(), None, 0)
-        # the call above already touched the timestamp; size known → fetch via a second read-only-equivalent call
-        buf = C.create_string_buffer(len(b) + 1)
-        lib().orc_stree_prefix_match_tenant(self.h, b, len(b), tenant.encode(), C.cast(buf, C.c_void_p), len(b) + 1)
+        buf = C.create_string_buffer(len(b) + 1)   # one call: it draws an epoch (string_tree.rs:713-717)
+        n = lib().orc_stree_prefix_match_tenant(self.h, b, len(b), tenant.encode(), C.cast(buf, C.c_void_p), len(b) + 1)
         return buf.raw[:n].decode()
 
     def force_cached_tenant(self, text, tenant):
@@ -439,7 +439,19 @@ class CacheAwarePolicy:
         secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads)
         return idx, secs
 
-    def select_batch_tokens(self, tokens, offsets, threads=0):
+    def select_batch_text(self, texts, snapshot=False):
+        """texts: list of str.  Returns (idx, branch, matched_chars, input_chars, secs)."""
+        enc = [t.encode("utf-8") for t in texts]
+        blob = b"".join(enc)
+        off = np.zeros(len(enc) + 1, np.uint64)
+        np.cumsum([len(e) for e in enc], out=off[1:])
+        n = len(enc)
+        idx = np.zeros(n, np.int32); br = np.zeros(n, np.uint8); ma = np.zeros(n, np.uint32); inp = np.zeros(n, np.uint32)
+        buf = C.create_string_buffer(blob, len(blob) + 1)
+        secs = lib().orc_policy_select_batch_text(self.h, buf, _ptr(off), n, 1 if snapshot else 0, _ptr(idx), _ptr(br), _ptr(ma), _ptr(inp))
+        return idx, br, ma, inp, secs
+
+    def select_batch_tokens(self, tokens, offsets, threads=0, snapshot=False):
         tk = _u32(tokens)
         off = _u64(offsets)
         n = off.size - 1
@@ -449,5 +461,6 @@ class CacheAwarePolicy:
             return i2, None, None, secs
         br = np.zeros(n, np.uint8)
         ma = np.zeros(n, np.uint32)
-        secs = lib().orc_policy_select_batch_tokens(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), _ptr(br), _ptr(ma))
+        fn = lib().orc_policy_select_batch_tokens_snapshot if snapshot else lib().orc_policy_select_batch_tokens
+        secs = fn(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), _ptr(br), _ptr(ma))
         return idx, br, ma, secs

@@ -135,8 +135,19 @@ public:
         prev->tenants[tenant] = epoch;
     }
 
+    // Deferred form of the match's side effects (:598-637), for the batch-snapshot execution (cache_aware.h): the walk
+    // records the terminal node and the tenant it read; apply_match_effects replays the cache fill, the epoch draw and
+    // the 1-in-8 timestamp refresh later, in request order.
+    struct PendingEffect { void* node = nullptr; std::string tenant; bool fill_cache = false; };
+    void apply_match_effects(const PendingEffect& e) {
+        Node* cur = (Node*)e.node;
+        if (e.fill_cache) { cur->has_last = true; cur->last_tenant = e.tenant; }
+        uint64_t epoch = next_epoch();
+        if ((epoch & 0x7) == 0 && e.tenant != "empty") cur->tenants[e.tenant] = epoch;
+    }
+
     // string_tree.rs:561-649
-    StringMatch match_prefix_with_counts(const std::string& text_utf8) {
+    StringMatch match_prefix_with_counts(const std::string& text_utf8, PendingEffect* defer = nullptr) {
         std::u32string text = utf8_decode(text_utf8);
         StringMatch r;
         size_t off = 0;
@@ -163,11 +174,13 @@ public:
                 r.tenant = cur->tenants.begin()->first;
                 for (auto& kv : cur->tenants) r.valid.push_back(kv.first);
             }
-            cur->has_last = true; cur->last_tenant = r.tenant;  // cache populated even with "empty"
+            if (defer) defer->fill_cache = true;
+            else { cur->has_last = true; cur->last_tenant = r.tenant; }  // cache populated even with "empty"
         }
+        r.input = text.size();
+        if (defer) { defer->node = cur; defer->tenant = r.tenant; return r; }
         uint64_t epoch = next_epoch();
         if ((epoch & 0x7) == 0 && r.tenant != "empty") cur->tenants[r.tenant] = epoch;
-        r.input = text.size();
         return r;
     }
 

@@ -150,8 +150,15 @@ public:
         if (added > 0) tenant_tokens_[tenant] += added;
     }
 
+    // Deferred form of the touch inside the match (:685-689), for the batch-snapshot execution (cache_aware.h, "snapshot batches"):
+    // the walk records (node, tenant) instead of touching; apply_touches replays them later in request order.
+    struct PendingTouch { void* node; std::string tenant; };
+    void apply_touches(const std::vector<PendingTouch>& ts) {
+        for (auto& t : ts) touch((Node*)t.node, t.tenant, policy_ == EV_LFU);
+    }
+
     // token_tree.rs:615-740
-    TokenMatch match_prefix_with_counts(const uint32_t* toks, size_t n) {
+    TokenMatch match_prefix_with_counts(const uint32_t* toks, size_t n, std::vector<PendingTouch>* defer = nullptr) {
         TokenMatch r;
         r.input = n;
         size_t aligned = align_to_page(n);
@@ -178,7 +185,7 @@ public:
             if (m == 0) break;
             std::string t; std::vector<std::string> valid;
             if (!any_tenant(child, t, valid)) break;  // no tenants → stop before counting (:682-683)
-            touch(child, t, lfu);
+            if (defer) defer->push_back(PendingTouch{child, t}); else touch(child, t, lfu);
             r.nodes_visited++;
             r.matched += m;
             r.tenant = t; r.valid = valid; have = true;

@@ -18,7 +18,7 @@ BRANCHES = ["no_healthy", "imbalanced_min_load", "event_overlap", "event_min_loa
 class Config(C.Structure):
     _fields_ = [("cache_threshold", C.c_float), ("balance_abs_threshold", C.c_uint64), ("balance_rel_threshold", C.c_float),
                 ("eviction_interval_secs", C.c_uint64), ("max_tree_size", C.c_uint64), ("block_size", C.c_uint64),
-                ("device_id", C.c_int32), ("max_batch", C.c_uint32), ("max_tokens_per_request", C.c_uint32)]
+                ("device_id", C.c_int32), ("max_batch", C.c_uint32), ("max_tokens_per_request", C.c_uint32), ("tree_batch_mode", C.c_uint32)]
 
 
 class DecisionInfo(C.Structure):
@@ -94,6 +94,15 @@ def load():
     sig("smgx_tree_tenant_size", st, vp, cp, cp, P(u64), pp)
     sig("smgx_tree_clear", st, vp, cp, pp)
     sig("smgx_tree_entries", st, vp, cp, P(C.c_void_p), pp)
+    sig("smgx_set_tree_batch_mode", st, vp, u32, pp)
+    sig("smgx_stree_insert_text", st, vp, cp, vp, u32, cp, pp)
+    sig("smgx_stree_match", st, vp, cp, vp, u32, P(u32), P(u32), vp, u32, pp)
+    sig("smgx_stree_prefix_match_tenant", st, vp, cp, vp, u32, cp, P(u32), pp)
+    sig("smgx_stree_sizes", st, vp, cp, C.c_int, P(C.c_void_p), pp)
+    sig("smgx_stree_entries", st, vp, cp, P(C.c_void_p), P(u64), pp)
+    sig("smgx_stree_clear", st, vp, cp, pp)
+    sig("smgx_stree_node_count", st, vp, cp, P(u64), pp)
+    sig("smgx_select_batch_request_text", st, vp, cp, vp, vp, u32, vp, vp, pp)
     sig("smgx_tokenizer_load_tiktoken_file", st, vp, cp, cp, P(cp), vp, u32, pp)
     sig("smgx_tokenizer_load_tiktoken", st, vp, cp, vp, vp, vp, u32, P(cp), vp, u32, pp)
     sig("smgx_tokenize_batch", st, vp, cp, vp, vp, u32, vp, vp, u32, pp)

@@ -18,6 +18,8 @@
 #include "kernels.h"
 #include "tokenizer.h"
 #include "token_tree.h"
+#include "string_tree.h"
+#include <unordered_map>
 #include <unordered_set>
 
 namespace smgx {
@@ -34,6 +36,7 @@ struct ModelState {
     std::unique_ptr<EventIndex> indexer;
     std::unique_ptr<Tokenizer> tokenizer;   // TokenizerRegistry entry for this model
     std::unique_ptr<TokenTreeIndex> token_tree;   // token_trees[model] (cache_aware.rs:79)
+    std::unique_ptr<StringTreeIndex> string_tree; // string_trees[model] (cache_aware.rs:78)
     DevBuf d_slice_of_tenant;
     uint64_t seen_tenants_version = ~0ULL;
     bool has_learned_bs = false;
@@ -48,7 +51,7 @@ struct ModelState {
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
-    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant;
+    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
     bool has_done = false;
@@ -64,6 +67,7 @@ public:
     explicit Policy(const smgx_cache_aware_config& c) : cfg(c) {
         if (cfg.max_batch == 0) cfg.max_batch = 65536;
         if (cfg.max_tokens_per_request == 0) cfg.max_tokens_per_request = 32768;
+        tree_batch_mode = cfg.tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT ? SMGX_TREE_BATCH_SNAPSHOT : SMGX_TREE_BATCH_SEQUENTIAL;
         if (cfg.device_id >= 0) {
             int count = 0;
             cudaError_t e = cudaGetDeviceCount(&count);
@@ -96,6 +100,7 @@ public:
             for (auto& l : lanes) {
                 l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
+                l.d_path_tenant.release(); l.d_fill.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
                 l.tok_scratch.pieces.release(); l.tok_scratch.n_pieces.release();
                 if (l.done) cudaEventDestroy(l.done);
@@ -110,6 +115,7 @@ public:
                 m.indexer.reset();
                 m.tokenizer.reset();
                 m.token_tree.reset();
+                m.string_tree.reset();
                 m.d_slice_of_tenant.release();
             }
             d_err.release(); d_flush.release(); scratch.release(); scratch2.release(); d_gbase.release();
@@ -257,41 +263,50 @@ public:
     }
 
     // Approximate-token-tree mode (cache_aware.rs:834-904) and the imbalanced path's tree update (:380-402).
-    // Requests are processed in contiguous segments whose first-page keys are pairwise distinct: such requests touch
-    // disjoint subtrees, so matching a whole segment against one snapshot on the GPU and then applying touches + inserts
-    // on the host in request order reproduces the reference's one-by-one semantics exactly (timestamps included).
+    // SMGX_TREE_BATCH_SEQUENTIAL: requests are processed in contiguous segments whose first-page keys are pairwise distinct:
+    // such requests touch disjoint subtrees, so matching a whole segment against one snapshot on the GPU and then applying
+    // touches + inserts on the host in request order reproduces the reference's one-by-one semantics exactly (timestamps
+    // included).  SMGX_TREE_BATCH_SNAPSHOT: the whole batch is one segment — every request walks and decides against the
+    // pre-batch tree, then the side effects are applied in request order: one admissible interleaving of concurrent
+    // select_worker calls (include/smgx.h), identical to SEQUENTIAL when no two requests of the batch share a first page.
     void tree_select(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info,
                      bool decide, int32_t* out_tenant) {
         TokenTreeIndex& tree = tree_of(m, true);
         Lane& lane = lanes[0];
         const uint64_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
+        const uint32_t n1 = std::max<uint32_t>(n, 1);
         lane.d_tokens.reserve(std::max<uint64_t>(total, 1) * 4 + 16);
         lane.d_offsets.reserve(((size_t)n + 1) * 4);
-        lane.d_out.reserve(std::max<uint32_t>(n, 1) * 4);
-        lane.d_info.reserve(std::max<uint32_t>(n, 1) * sizeof(smgx_decision_info));
-        lane.d_path.reserve((size_t)std::max<uint32_t>(n, 1) * kPathCap * 4);
-        lane.d_path_len.reserve(std::max<uint32_t>(n, 1) * 4);
-        lane.d_tenant.reserve(std::max<uint32_t>(n, 1) * 4);
+        lane.d_out.reserve(n1 * 4);
+        lane.d_info.reserve(n1 * sizeof(smgx_decision_info));
+        lane.d_path.reserve((size_t)n1 * kPathCap * 4);
+        lane.d_path_tenant.reserve((size_t)n1 * kPathCap * 4);
+        lane.d_path_len.reserve(n1 * 4);
+        lane.d_tenant.reserve(n1 * 4);
         if (n == 0) return;
         if (total) SMGX_CUDA(cudaMemcpyAsync(lane.d_tokens.ptr, tokens + base, total * 4, cudaMemcpyHostToDevice, lane.stream));
         SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
         std::vector<smgx_decision_info> info(n);
         std::vector<uint32_t> path((size_t)n * kPathCap), path_len(n);
-        std::vector<int32_t> ten(n);
+        std::vector<int32_t> path_ten((size_t)n * kPathCap), ten(n);
         std::unordered_set<uint64_t> seen;
+        const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
         uint32_t seg = 0;
         while (seg < n) {
-            seen.clear();
             uint32_t end = seg;
-            while (end < n) {
-                const uint32_t len = offsets[end + 1] - offsets[end];
-                if (len >= kPage) {
-                    uint64_t sum = 0;
-                    const uint32_t* pg = tokens + offsets[end];
-                    for (uint32_t i = 0; i < kPage; ++i) sum += ((uint64_t)pg[i] + 1) * page_mult(i);
-                    if (!seen.insert(page_finish(sum, 0)).second) break;
+            if (snapshot) end = n;
+            else {
+                seen.clear();
+                while (end < n) {
+                    const uint32_t len = offsets[end + 1] - offsets[end];
+                    if (len >= kPage) {
+                        uint64_t sum = 0;
+                        const uint32_t* pg = tokens + offsets[end];
+                        for (uint32_t i = 0; i < kPage; ++i) sum += ((uint64_t)pg[i] + 1) * page_mult(i);
+                        if (!seen.insert(page_finish(sum, 0)).second) break;
+                    }
+                    ++end;
                 }
-                ++end;
             }
             EventIndexView ixv;
             FleetView fv;
@@ -302,7 +317,8 @@ public:
             a.tokens = lane.d_tokens.as<uint32_t>() - base; a.offsets = lane.d_offsets.as<uint32_t>();
             a.first = seg; a.count = end - seg;
             a.out_idx = lane.d_out.as<int32_t>(); a.out_info = lane.d_info.as<smgx_decision_info>();
-            a.out_path = lane.d_path.as<uint32_t>(); a.out_path_len = lane.d_path_len.as<uint32_t>(); a.out_tenant = lane.d_tenant.as<int32_t>();
+            a.out_path = lane.d_path.as<uint32_t>(); a.out_path_tenant = lane.d_path_tenant.as<int32_t>();
+            a.out_path_len = lane.d_path_len.as<uint32_t>(); a.out_tenant = lane.d_tenant.as<int32_t>();
             a.cache_threshold = cfg.cache_threshold; a.decide = decide ? 1 : 0;
             launch_tree_select(tv, fv, m.d_slice_of_tenant.as<int32_t>(), m.d_flags.as<uint8_t>(), (uint32_t)tenants.names.size(), a, lane.stream);
             ++launches;
@@ -310,21 +326,119 @@ public:
             SMGX_CUDA(cudaMemcpyAsync(out_idx + seg, lane.d_out.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(info.data() + seg, lane.d_info.as<smgx_decision_info>() + seg, (size_t)cnt * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(path.data() + (size_t)seg * kPathCap, lane.d_path.as<uint32_t>() + (size_t)seg * kPathCap, (size_t)cnt * kPathCap * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(path_ten.data() + (size_t)seg * kPathCap, lane.d_path_tenant.as<int32_t>() + (size_t)seg * kPathCap, (size_t)cnt * kPathCap * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(path_len.data() + seg, lane.d_path_len.as<uint32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(ten.data() + seg, lane.d_tenant.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+            // walks deeper than the kernel reports: recover the node list from the same (still unmodified) tree state
+            std::unordered_map<uint32_t, TreeMatch> deep;
+            for (uint32_t r = seg; r < end; ++r)
+                if (path_len[r] > kPathCap) deep.emplace(r, tree.match_prefix_host(tokens + offsets[r], offsets[r + 1] - offsets[r], false));
             for (uint32_t r = seg; r < end; ++r) {
                 const uint32_t* tk = tokens + offsets[r];
                 const uint32_t len = offsets[r + 1] - offsets[r];
                 if (decide && info[r].branch == SMGX_BR_NO_HEALTHY) continue;   // returns None before touching anything (:653-655)
                 // match side effects: touch_tenant on every matched node, in order (:685-689)
-                if (path_len[r] <= kPathCap) tree.apply_match_touches(path.data() + (size_t)r * kPathCap, path_len[r]);
-                else { TreeMatch hm = tree.match_prefix_host(tk, len, false); tree.apply_match_touches(hm.path.data(), (uint32_t)hm.path.size()); }
+                if (path_len[r] <= kPathCap) tree.apply_match_touches(path.data() + (size_t)r * kPathCap, path_ten.data() + (size_t)r * kPathCap, path_len[r]);
+                else { const TreeMatch& hm = deep.at(r); tree.apply_match_touches(hm.path.data(), hm.path_tenants.data(), (uint32_t)hm.path.size()); }
                 if (!decide) continue;
                 const uint8_t br = info[r].branch;
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
                     const size_t idx = (size_t)out_idx[r];
                     tree.insert_tokens(tk, len, tenants.intern(m.urls[idx]));   // :868 / :396
+                    if (idx < m.processed.size()) ++m.processed[idx];
+                }
+            }
+            seg = end;
+        }
+        if (out_info) memcpy(out_info, info.data(), (size_t)n * sizeof(smgx_decision_info));
+        if (out_tenant) memcpy(out_tenant, ten.data(), (size_t)n * 4);
+    }
+
+    StringTreeIndex& stree_of(ModelState& m) {
+        if (!m.string_tree) {
+            m.string_tree = std::make_unique<StringTreeIndex>(&tenants, &string_epoch);
+            m.string_tree->device_enabled = cfg.device_id >= 0;
+        }
+        return *m.string_tree;
+    }
+
+    // HTTP text mode (select_worker_with_text, cache_aware.rs:907-974, and the imbalanced path's tree update :403-425) on the
+    // char-level string tree.  Same batching contract as tree_select; in SEQUENTIAL mode two requests conflict when they
+    // start with the same char under the root (they then share a subtree) or when both end on the root itself.
+    void text_select(ModelState& m, const uint8_t* text, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info,
+                     bool decide, int32_t* out_tenant) {
+        StringTreeIndex& tree = stree_of(m);
+        Lane& lane = lanes[0];
+        const uint64_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
+        const uint32_t n1 = std::max<uint32_t>(n, 1);
+        lane.d_text.reserve(std::max<uint64_t>(total, 1) + 16);
+        lane.d_offsets.reserve(((size_t)n + 1) * 4);
+        lane.d_out.reserve(n1 * 4);
+        lane.d_info.reserve(n1 * sizeof(smgx_decision_info));
+        lane.d_path_len.reserve(n1 * 4);
+        lane.d_tenant.reserve(n1 * 4);
+        lane.d_fill.reserve(n1);
+        if (n == 0) return;
+        if (total) SMGX_CUDA(cudaMemcpyAsync(lane.d_text.ptr, text + base, total, cudaMemcpyHostToDevice, lane.stream));
+        SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+        std::vector<smgx_decision_info> info(n);
+        std::vector<uint32_t> node(n);
+        std::vector<int32_t> ten(n);
+        std::vector<uint8_t> fill(n);
+        std::unordered_set<uint64_t> seen;
+        const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
+        uint32_t seg = 0;
+        while (seg < n) {
+            uint32_t end = seg;
+            if (snapshot) end = n;
+            else {
+                seen.clear();
+                while (end < n) {
+                    const uint32_t len = offsets[end + 1] - offsets[end];
+                    uint64_t key = ~0ULL;   // walk ends on the root: empty text or no child under the first char
+                    if (len) {
+                        uint32_t cl;
+                        const uint32_t cp = utf8_first(text + offsets[end], &cl);
+                        if (tree.root_has_child(cp)) key = cp;
+                    }
+                    if (!seen.insert(key).second) break;
+                    if (key == ~0ULL && len) {   // this request's insert creates the root child for its first char
+                        uint32_t cl;
+                        if (!seen.insert(utf8_first(text + offsets[end], &cl)).second) break;
+                    }
+                    ++end;
+                }
+                if (end == seg) ++end;
+            }
+            EventIndexView ixv;
+            FleetView fv;
+            sync_state(m, &ixv, &fv);
+            sync_tenant_map(m);
+            StringTreeView tv = tree.flush(lane.stream, &launches);
+            StringSelectArgs a;
+            a.text = lane.d_text.as<uint8_t>() - base; a.offsets = lane.d_offsets.as<uint32_t>();
+            a.first = seg; a.count = end - seg;
+            a.out_idx = lane.d_out.as<int32_t>(); a.out_info = lane.d_info.as<smgx_decision_info>();
+            a.out_node = lane.d_path_len.as<uint32_t>(); a.out_tenant = lane.d_tenant.as<int32_t>(); a.out_fill = lane.d_fill.as<uint8_t>();
+            a.cache_threshold = cfg.cache_threshold; a.decide = decide ? 1 : 0;
+            launch_string_select(tv, fv, m.d_slice_of_tenant.as<int32_t>(), m.d_flags.as<uint8_t>(), (uint32_t)tenants.names.size(), a, lane.stream);
+            ++launches;
+            const uint32_t cnt = end - seg;
+            SMGX_CUDA(cudaMemcpyAsync(out_idx + seg, lane.d_out.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(info.data() + seg, lane.d_info.as<smgx_decision_info>() + seg, (size_t)cnt * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(node.data() + seg, lane.d_path_len.as<uint32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(ten.data() + seg, lane.d_tenant.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(fill.data() + seg, lane.d_fill.as<uint8_t>() + seg, (size_t)cnt, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+            for (uint32_t r = seg; r < end; ++r) {
+                if (decide && info[r].branch == SMGX_BR_NO_HEALTHY) continue;
+                tree.apply_match_effects(node[r], ten[r], fill[r] != 0);   // cache fill, epoch draw, 1-in-8 refresh (:598-637)
+                if (!decide) continue;
+                const uint8_t br = info[r].branch;
+                if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
+                    const size_t idx = (size_t)out_idx[r];
+                    tree.insert_text(text + offsets[r], offsets[r + 1] - offsets[r], tenants.intern(m.urls[idx]));   // :938 / :421
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -399,6 +513,8 @@ public:
 
     TenantTable tenants;         // TENANT_INTERN_POOL (token_tree.rs:160-176)
     uint64_t token_ts = 0;       // GLOBAL_TIMESTAMP (token_tree.rs:179), shared by every token tree of the policy
+    uint64_t string_epoch = 0;   // EPOCH_COUNTER (string_tree.rs:239), shared by every string tree of the policy
+    uint32_t tree_batch_mode = SMGX_TREE_BATCH_SEQUENTIAL;
     smgx_cache_aware_config cfg;
     int sm_count = 148;
     size_t l2_bytes = 126u << 20;
@@ -456,7 +572,7 @@ void smgx_default_config(smgx_cache_aware_config* c) {
     if (!c) return;
     c->cache_threshold = 0.5f; c->balance_abs_threshold = 32; c->balance_rel_threshold = 1.1f;
     c->eviction_interval_secs = 30; c->max_tree_size = 10000; c->block_size = 16;
-    c->device_id = 0; c->max_batch = 65536; c->max_tokens_per_request = 32768;
+    c->device_id = 0; c->max_batch = 65536; c->max_tokens_per_request = 32768; c->tree_batch_mode = SMGX_TREE_BATCH_SEQUENTIAL;
 }
 
 smgx_policy* smgx_policy_create(const smgx_cache_aware_config* cfg, char** err) {
@@ -494,7 +610,8 @@ smgx_status smgx_set_workers(smgx_policy* p, const char* model_key, const char* 
         m.fleet_dirty = true;
         m.fleet_dirty_tenant = true;
         p->impl.tree_of(m, true);                                   // init_workers creates the trees (cache_aware.rs:231-247)
-        for (auto& u : m.urls) p->impl.tenants.intern(u);
+        StringTreeIndex& st = p->impl.stree_of(m);
+        for (auto& u : m.urls) st.insert_text(nullptr, 0, p->impl.tenants.intern(u));   // tree.insert_text("", url) (:239, :275)
         return SMGX_SUCCESS;
     });
 }
@@ -524,9 +641,9 @@ smgx_status smgx_add_worker(smgx_policy* p, const char* model_key, const char* u
             m.urls.emplace_back(url); m.loads.push_back(0); m.flags.push_back(3); m.processed.push_back(0);
             m.fleet_dirty = true;
             m.fleet_dirty_tenant = true;
-            p->impl.tree_of(m, true);
-            p->impl.tenants.intern(url);
         }
+        p->impl.tree_of(m, true);
+        p->impl.stree_of(m).insert_text(nullptr, 0, p->impl.tenants.intern(url));   // add_worker_by_url (:269-283)
         return SMGX_SUCCESS;
     });
 }
@@ -784,7 +901,8 @@ smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err) {   
     return guard(err, [&]() {
         NONNULL(p);
         std::lock_guard<std::mutex> g(p->impl.mu);
-        for (auto& kv : p->impl.models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);
+        for (auto& kv : p->impl.models) if (kv.second->string_tree) kv.second->string_tree->evict_tenant_by_size((size_t)max_size);   // :317-321
+        for (auto& kv : p->impl.models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);     // :322-326
         return SMGX_SUCCESS;
     });
 }
@@ -937,6 +1055,18 @@ smgx_status smgx_select_batch_text(smgx_policy* p, const char* model_key, const 
         uint32_t mx = 0;
         tokenize_on_lane(P, m, lane, text, offsets, n, &mx);
         SMGX_REQUIRE(mx <= P.cfg.max_tokens_per_request, "request longer than max_tokens_per_request");
+        if (!P.has_event_indexer(m) || (P.host_imbalanced(m) && m.token_tree)) {
+            // approximate token tree on the tokens just produced: the host-side updater needs them, so they come back first
+            std::vector<uint32_t> toff(n + 1);
+            SMGX_CUDA(cudaMemcpyAsync(toff.data(), lane.d_toff.ptr, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+            std::vector<uint32_t> toks(std::max<uint32_t>(toff[n], 1));
+            if (toff[n]) SMGX_CUDA(cudaMemcpy(toks.data(), lane.d_tokens.ptr, (size_t)toff[n] * 4, cudaMemcpyDeviceToHost));
+            if (out_tok_offsets) memcpy(out_tok_offsets, toff.data(), ((size_t)n + 1) * 4);
+            if (out_tokens) { SMGX_REQUIRE(toff[n] <= cap_tokens, "token output buffer too small"); memcpy(out_tokens, toks.data(), (size_t)toff[n] * 4); }
+            P.tree_select(m, toks.data(), toff.data(), n, out_worker_idx, out_info, true, nullptr);
+            return SMGX_SUCCESS;
+        }
         lane.d_out.reserve((size_t)n * 4);
         if (out_info) lane.d_info.reserve((size_t)n * sizeof(smgx_decision_info));
         // a request of b bytes has at most b tokens → bounds the per-request hash row
@@ -951,6 +1081,143 @@ smgx_status smgx_select_batch_text(smgx_policy* p, const char* model_key, const 
             int32_t idx = out_worker_idx[i];
             if (idx >= 0 && (size_t)idx < m.processed.size()) ++m.processed[(size_t)idx];
         }
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- string tree: kv_index::Tree (crates/kv_index/src/string_tree.rs) ----
+static char* dup_cstr(const std::string& s) {
+    char* c = (char*)malloc(s.size() + 1);
+    if (!c) throw std::bad_alloc();
+    memcpy(c, s.data(), s.size());
+    c[s.size()] = 0;
+    return c;
+}
+smgx_status smgx_stree_insert_text(smgx_policy* p, const char* model_key, const uint8_t* text, uint32_t n_bytes, const char* tenant, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(tenant);
+        SMGX_REQUIRE(n_bytes == 0 || text, "Invalid arguments: null pointer");
+        SMGX_REQUIRE(StringTreeIndex::valid_utf8(text, n_bytes), "text is not valid UTF-8");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        p->impl.stree_of(m).insert_text(text, n_bytes, p->impl.tenants.intern(tenant));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_match(smgx_policy* p, const char* model_key, const uint8_t* text, uint32_t n_bytes, uint32_t* out_matched_chars,
+                             uint32_t* out_input_chars, char* out_tenant, uint32_t tenant_cap, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_matched_chars); NONNULL(out_input_chars);
+        SMGX_REQUIRE(n_bytes == 0 || text, "Invalid arguments: null pointer");
+        SMGX_REQUIRE(StringTreeIndex::valid_utf8(text, n_bytes), "text is not valid UTF-8");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, true);
+        uint32_t offs[2] = {0, n_bytes};
+        uint8_t dummy = 0;
+        int32_t idx = -1, ten = -1;
+        smgx_decision_info di{};
+        P.text_select(m, n_bytes ? text : &dummy, offs, 1, &idx, &di, false, &ten);
+        *out_matched_chars = di.matched;
+        *out_input_chars = di.input;
+        if (out_tenant && tenant_cap) {
+            const std::string name = ten >= 0 ? P.tenants.names[(size_t)ten] : std::string("empty");
+            const size_t k = std::min<size_t>(name.size(), tenant_cap - 1);
+            memcpy(out_tenant, name.data(), k);
+            out_tenant[k] = 0;
+        }
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_prefix_match_tenant(smgx_policy* p, const char* model_key, const uint8_t* text, uint32_t n_bytes, const char* tenant,
+                                           uint32_t* out_matched_bytes, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(tenant); NONNULL(out_matched_bytes);
+        SMGX_REQUIRE(n_bytes == 0 || text, "Invalid arguments: null pointer");
+        SMGX_REQUIRE(StringTreeIndex::valid_utf8(text, n_bytes), "text is not valid UTF-8");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        uint8_t dummy = 0;
+        *out_matched_bytes = (uint32_t)p->impl.stree_of(m).prefix_match_tenant(n_bytes ? text : &dummy, n_bytes, p->impl.tenants.find(tenant)).size();
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_sizes(smgx_policy* p, const char* model_key, int maintained, char** out_text, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_text);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        StringTreeIndex& t = p->impl.stree_of(m);
+        std::string s;
+        for (auto& kv : (maintained ? t.tenant_char_counts() : t.used_size_per_tenant())) s += kv.first + "=" + std::to_string(kv.second) + "\n";
+        *out_text = dup_cstr(s);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_entries(smgx_policy* p, const char* model_key, char** out_text, uint64_t* out_len, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_text); NONNULL(out_len);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        std::vector<std::pair<std::string, std::vector<std::pair<uint32_t, uint64_t>>>> es;
+        p->impl.stree_of(m).entries(es);
+        std::string s;
+        for (auto& e : es) {
+            s += e.first; s.push_back('\x1f');
+            for (size_t i = 0; i < e.second.size(); ++i) { if (i) s.push_back(';'); s += p->impl.tenants.names[e.second[i].first] + "=" + std::to_string(e.second[i].second); }
+            s.push_back('\x1e');
+        }
+        *out_text = dup_cstr(s);
+        *out_len = s.size();
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_clear(smgx_policy* p, const char* model_key, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        if (m.string_tree) m.string_tree->clear();
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        *out = m.string_tree ? m.string_tree->node_count() : 0;
+        return SMGX_SUCCESS;
+    });
+}
+
+smgx_status smgx_set_tree_batch_mode(smgx_policy* p, uint32_t mode, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(mode == SMGX_TREE_BATCH_SEQUENTIAL || mode == SMGX_TREE_BATCH_SNAPSHOT, "unknown tree batch mode");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.tree_batch_mode = mode;
+        return SMGX_SUCCESS;
+    });
+}
+
+// select_worker with info.request_text = Some(text), info.tokens = None (HTTP routers): string tree (cache_aware.rs:688-689, :907-974)
+smgx_status smgx_select_batch_request_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                           int32_t* out_worker_idx, smgx_decision_info* out_info, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (text && offsets && out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(n <= P.cfg.max_batch, "batch larger than max_batch");
+        ModelState& m = P.model(model_key, false);
+        for (uint32_t i = 0; i < n; ++i) {
+            SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+            SMGX_REQUIRE(StringTreeIndex::valid_utf8(text + offsets[i], offsets[i + 1] - offsets[i]), "request text is not valid UTF-8");
+        }
+        P.text_select(m, text, offsets, n, out_worker_idx, out_info, true, nullptr);
         return SMGX_SUCCESS;
     });
 }

@@ -1,0 +1,545 @@
+// K2c — char-level string tree: host tree + device mirror + the match/decide kernel.  See string_tree.h.
+#include "string_tree.h"
+
+#include <algorithm>
+#include <cstring>
+#include <queue>
+
+#include "kernels.h"
+
+namespace smgx {
+
+// =================================================================================================================
+// host tree
+// =================================================================================================================
+StringTreeIndex::StringTreeIndex(TenantTable* tenants, uint64_t* epoch) : tenants_(tenants), epoch_(epoch) {
+    nodes_.emplace_back();
+    table_.assign(1024, StrChildSlot{0, 0, 0});
+    mask_ = 1023;
+}
+StringTreeIndex::~StringTreeIndex() {
+    d_bytes_.release(); d_headers_.release(); d_table_.release(); d_stage_.release(); stage_.release();
+    if (stage_done_) cudaEventDestroy(stage_done_);
+}
+
+bool StringTreeIndex::valid_utf8(const uint8_t* s, size_t n) {   // Rust `&str` is valid UTF-8 by construction; the C ABI checks
+    size_t i = 0;
+    while (i < n) {
+        const uint8_t c = s[i];
+        size_t len;
+        if (c < 0x80) { ++i; continue; }
+        else if (c >= 0xC2 && c <= 0xDF) len = 2;
+        else if (c >= 0xE0 && c <= 0xEF) len = 3;
+        else if (c >= 0xF0 && c <= 0xF4) len = 4;
+        else return false;
+        if (i + len > n) return false;
+        for (size_t k = 1; k < len; ++k) if ((s[i + k] & 0xC0) != 0x80) return false;
+        if (len == 3) {
+            if (c == 0xE0 && s[i + 1] < 0xA0) return false;
+            if (c == 0xED && s[i + 1] > 0x9F) return false;   // surrogates
+        } else if (len == 4) {
+            if (c == 0xF0 && s[i + 1] < 0x90) return false;
+            if (c == 0xF4 && s[i + 1] > 0x8F) return false;
+        }
+        i += len;
+    }
+    return true;
+}
+
+int64_t StringTreeIndex::find_child(uint32_t parent, uint32_t cp) const {
+    const uint64_t key = str_child_key(parent, cp);
+    uint32_t idx = str_child_home(key) & mask_;
+    for (;;) {
+        const StrChildSlot& s = table_[idx];
+        if (s.key == 0) return -1;
+        if (s.key == key && s.child < kTombChild) return idx;
+        idx = (idx + 1) & mask_;
+    }
+}
+void StringTreeIndex::table_rebuild(uint32_t cap) {
+    std::vector<StrChildSlot> old;
+    old.swap(table_);
+    table_.assign(cap, StrChildSlot{0, 0, 0});
+    mask_ = cap - 1;
+    table_live_ = table_tombs_ = 0;
+    for (const StrChildSlot& s : old) {
+        if (s.key == 0 || s.child >= kTombChild) continue;
+        uint32_t idx = str_child_home(s.key) & mask_;
+        while (table_[idx].key != 0) idx = (idx + 1) & mask_;
+        table_[idx] = s;
+        ++table_live_;
+    }
+    full_dirty_ = true;
+    dirty_slots_.clear();
+}
+void StringTreeIndex::table_insert(uint32_t parent, uint32_t cp, uint32_t child) {
+    if ((table_live_ + table_tombs_ + 1) * 2 > table_.size()) {
+        uint32_t cap = (uint32_t)table_.size();
+        while ((table_live_ + 1) * 4 > cap) cap *= 2;
+        table_rebuild(cap);
+    }
+    const uint64_t key = str_child_key(parent, cp);
+    uint32_t idx = str_child_home(key) & mask_;
+    int64_t tomb = -1;
+    while (table_[idx].key != 0) {
+        if (table_[idx].child == kTombChild && tomb < 0) tomb = idx;
+        idx = (idx + 1) & mask_;
+    }
+    if (tomb >= 0) { idx = (uint32_t)tomb; --table_tombs_; }
+    table_[idx] = StrChildSlot{key, child, 0};
+    ++table_live_;
+    mark_slot(idx);
+}
+void StringTreeIndex::table_set(uint32_t parent, uint32_t cp, uint32_t child) {
+    const int64_t s = find_child(parent, cp);
+    if (s < 0) { table_insert(parent, cp, child); return; }
+    table_[(size_t)s].child = child;
+    mark_slot((uint32_t)s);
+}
+void StringTreeIndex::table_erase(uint32_t parent, uint32_t cp) {
+    const int64_t s = find_child(parent, cp);
+    if (s < 0) return;
+    table_[(size_t)s].child = kTombChild;
+    --table_live_;
+    ++table_tombs_;
+    mark_slot((uint32_t)s);
+}
+
+uint32_t StringTreeIndex::new_node(uint64_t off, uint32_t bytes, uint32_t chars, uint32_t parent, uint32_t first_cp) {
+    uint32_t id;
+    if (!free_nodes_.empty()) { id = free_nodes_.back(); free_nodes_.pop_back(); nodes_[id] = Node(); }
+    else {
+        id = (uint32_t)nodes_.size();
+        const size_t before = nodes_.capacity();
+        nodes_.emplace_back();
+        if (nodes_.capacity() != before) full_dirty_ = true;
+    }
+    Node& nd = nodes_[id];
+    nd.label_off = off; nd.label_bytes = bytes; nd.label_chars = chars; nd.parent = parent; nd.first_cp = first_cp;
+    ++live_nodes_;
+    mark_node(id);
+    return id;
+}
+void StringTreeIndex::free_node(uint32_t id) {
+    Node& nd = nodes_[id];
+    nd.alive = false; nd.tenants.clear(); nd.kids.clear(); nd.last_tenant = -1;
+    free_nodes_.push_back(id);
+    --live_nodes_;
+    mark_node(id);
+}
+int64_t StringTreeIndex::find_tenant(const Node& nd, uint32_t t) {
+    for (size_t i = 0; i < nd.tenants.size(); ++i) if (nd.tenants[i].first == t) return (int64_t)i;
+    return -1;
+}
+void StringTreeIndex::set_tenant(Node& nd, uint32_t t, uint64_t ts) {
+    const int64_t i = find_tenant(nd, t);
+    if (i >= 0) nd.tenants[(size_t)i].second = ts; else nd.tenants.emplace_back(t, ts);
+}
+void StringTreeIndex::erase_tenant(Node& nd, uint32_t t) {
+    const int64_t i = find_tenant(nd, t);
+    if (i >= 0) nd.tenants.erase(nd.tenants.begin() + i);
+}
+// tenant the match reports for a node (:598-627): valid cached last_tenant, else "first in DashMap order" = smallest name
+int32_t StringTreeIndex::any_tenant(const Node& nd) const {
+    if (cache_valid(nd)) return nd.last_tenant;
+    int32_t best = -1;
+    for (auto& kv : nd.tenants) if (best < 0 || tenants_->rank[kv.first] < tenants_->rank[(uint32_t)best]) best = (int32_t)kv.first;
+    return best;
+}
+void StringTreeIndex::kids_insert(Node& nd, uint32_t cp, uint32_t child) {
+    auto it = std::lower_bound(nd.kids.begin(), nd.kids.end(), std::make_pair(cp, 0u));
+    if (it != nd.kids.end() && it->first == cp) it->second = child; else nd.kids.insert(it, {cp, child});
+}
+void StringTreeIndex::kids_erase(Node& nd, uint32_t cp) {
+    auto it = std::lower_bound(nd.kids.begin(), nd.kids.end(), std::make_pair(cp, 0u));
+    if (it != nd.kids.end() && it->first == cp) nd.kids.erase(it);
+}
+
+static inline uint32_t count_chars(const uint8_t* s, size_t n) {
+    uint32_t c = 0;
+    for (size_t i = 0; i < n; ++i) c += (s[i] & 0xC0) != 0x80;
+    return c;
+}
+// shared prefix of two valid UTF-8 strings, in bytes, ending on a char boundary (shared_prefix_count :311-338)
+static inline size_t shared_prefix_bytes(const uint8_t* a, size_t na, const uint8_t* b, size_t nb) {
+    const size_t lim = std::min(na, nb);
+    size_t i = 0;
+    while (i < lim && a[i] == b[i]) ++i;
+    if (i < lim) while (i > 0 && (a[i] & 0xC0) == 0x80) --i;   // mismatch inside a char: back to its first byte
+    return i;
+}
+
+// Tree::insert_text (string_tree.rs:393-557)
+void StringTreeIndex::insert_text(const uint8_t* s, size_t n, uint32_t tenant) {
+    if (find_tenant(nodes_[0], tenant) < 0) { nodes_[0].tenants.emplace_back(tenant, 0); mark_node(0); }
+    tenant_chars_.emplace(tenant, 0);
+    size_t off = 0;
+    uint32_t prev = 0;
+    while (off < n) {
+        uint32_t cl;
+        const uint32_t cp = utf8_first(s + off, &cl);
+        const int64_t slot = find_child(prev, cp);
+        if (slot < 0) {   // vacant: one leaf with the whole remaining text, owned and cached by the inserting tenant (:413-441)
+            const uint32_t chars = count_chars(s + off, n - off);
+            const uint64_t epoch = next_epoch();
+            const uint64_t boff = bytes_.size();
+            bytes_.insert(bytes_.end(), s + off, s + n);
+            const uint32_t leaf = new_node(boff, (uint32_t)(n - off), chars, prev, cp);
+            nodes_[leaf].last_tenant = (int32_t)tenant;
+            nodes_[leaf].tenants.emplace_back(tenant, epoch);
+            tenant_chars_[tenant] += chars;
+            table_insert(prev, cp, leaf);
+            kids_insert(nodes_[prev], cp, leaf);
+            return;
+        }
+        const uint32_t m = table_[(size_t)slot].child;
+        const size_t shared = shared_prefix_bytes(s + off, n - off, label(nodes_[m]), nodes_[m].label_bytes);
+        if (shared < nodes_[m].label_bytes) {   // split: a NEW intermediate takes the shared prefix and clones tenants + cache (:455-510)
+            const uint32_t shared_chars = count_chars(s + off, shared);
+            const uint64_t moff = nodes_[m].label_off;
+            const uint32_t nn = new_node(moff, (uint32_t)shared, shared_chars, prev, cp);
+            nodes_[nn].tenants = nodes_[m].tenants;
+            nodes_[nn].last_tenant = nodes_[m].last_tenant;
+            Node& mm = nodes_[m];
+            mm.label_off = moff + shared; mm.label_bytes -= (uint32_t)shared; mm.label_chars -= shared_chars; mm.parent = nn;
+            uint32_t l2;
+            mm.first_cp = utf8_first(label(mm), &l2);
+            mark_node(m);
+            kids_insert(nodes_[nn], mm.first_cp, m);
+            table_set(prev, cp, nn);
+            kids_insert(nodes_[prev], cp, nn);
+            table_insert(nn, mm.first_cp, m);
+            if (find_tenant(nodes_[nn], tenant) < 0) {
+                tenant_chars_[tenant] += shared_chars;
+                nodes_[nn].tenants.emplace_back(tenant, 0);
+            }
+            prev = nn;
+        } else {
+            Node& mm = nodes_[m];
+            if (find_tenant(mm, tenant) < 0) {
+                tenant_chars_[tenant] += mm.label_chars;
+                mm.tenants.emplace_back(tenant, 0);
+                mark_node(m);
+            }
+            prev = m;
+        }
+        off += shared;
+    }
+    const uint64_t epoch = next_epoch();
+    set_tenant(nodes_[prev], tenant, epoch);
+    mark_node(prev);
+}
+
+// side effects of Tree::match_prefix_with_counts on the node the walk ended on (:598-637)
+void StringTreeIndex::apply_match_effects(uint32_t node, int32_t tenant, bool fill_cache) {
+    Node& nd = nodes_[node];
+    if (fill_cache) { nd.last_tenant = tenant; mark_node(node); }   // tenant < 0 ("empty") leaves the cache invalid, like caching "empty"
+    const uint64_t epoch = next_epoch();
+    if ((epoch & 0x7) == 0 && tenant >= 0) set_tenant(nd, (uint32_t)tenant, epoch);
+}
+
+// Tree::prefix_match_tenant (:659-720)
+std::string StringTreeIndex::prefix_match_tenant(const uint8_t* s, size_t n, int64_t tenant) {
+    size_t off = 0;
+    uint32_t prev = 0;
+    while (off < n) {
+        uint32_t cl;
+        const uint32_t cp = utf8_first(s + off, &cl);
+        const int64_t slot = find_child(prev, cp);
+        if (slot < 0) break;
+        const uint32_t m = table_[(size_t)slot].child;
+        if (tenant < 0 || find_tenant(nodes_[m], (uint32_t)tenant) < 0) break;
+        const size_t shared = shared_prefix_bytes(s + off, n - off, label(nodes_[m]), nodes_[m].label_bytes);
+        off += shared;
+        prev = m;
+        if (shared != nodes_[m].label_bytes) break;
+    }
+    if (tenant >= 0 && find_tenant(nodes_[prev], (uint32_t)tenant) >= 0) set_tenant(nodes_[prev], (uint32_t)tenant, next_epoch());
+    return std::string((const char*)s, off);
+}
+
+std::vector<uint32_t> StringTreeIndex::leaf_of(uint32_t node) const {
+    const Node& nd = nodes_[node];
+    std::vector<uint32_t> out;
+    for (auto& kv : nd.tenants) {
+        bool in_child = false;
+        for (auto& k : nd.kids) if (find_tenant(nodes_[k.second], kv.first) >= 0) { in_child = true; break; }
+        if (!in_child) out.push_back(kv.first);
+    }
+    std::sort(out.begin(), out.end(), [&](uint32_t a, uint32_t b) { return tenants_->rank[a] < tenants_->rank[b]; });
+    return out;
+}
+
+// Tree::evict_tenant_by_size (:745-849): one global min-heap over (epoch) of every tenant-leaf; ties in discovery order
+void StringTreeIndex::evict_tenant_by_size(size_t max_size) {
+    struct Ent { uint64_t ts, seq; uint32_t tenant, node; };
+    auto cmp = [](const Ent& a, const Ent& b) { return a.ts != b.ts ? a.ts > b.ts : a.seq > b.seq; };
+    std::priority_queue<Ent, std::vector<Ent>, decltype(cmp)> pq(cmp);
+    uint64_t seq = 0;
+    auto ts_of = [&](uint32_t node, uint32_t t) { const int64_t i = find_tenant(nodes_[node], t); return i >= 0 ? nodes_[node].tenants[(size_t)i].second : 0; };
+    std::vector<uint32_t> stack{0};
+    while (!stack.empty()) {
+        const uint32_t cur = stack.back(); stack.pop_back();
+        for (auto& k : nodes_[cur].kids) stack.push_back(k.second);
+        for (uint32_t t : leaf_of(cur)) pq.push(Ent{ts_of(cur, t), seq++, t, cur});
+    }
+    std::vector<uint32_t> graveyard;
+    while (!pq.empty()) {
+        const Ent e = pq.top(); pq.pop();
+        auto sz = tenant_chars_.find(e.tenant);
+        if (sz != tenant_chars_.end() && sz->second <= max_size) continue;
+        Node& node = nodes_[e.node];
+        bool still_leaf = find_tenant(node, e.tenant) >= 0;
+        if (still_leaf) for (auto& k : node.kids) if (find_tenant(nodes_[k.second], e.tenant) >= 0) { still_leaf = false; break; }
+        if (!still_leaf) continue;
+        const size_t node_len = node.label_chars;
+        if (sz != tenant_chars_.end()) sz->second = sz->second >= node_len ? sz->second - node_len : 0;
+        erase_tenant(node, e.tenant);
+        mark_node(e.node);
+        const uint32_t parent = node.parent;
+        if (node.kids.empty() && node.tenants.empty() && parent != kNoNode && node.label_bytes > 0) {
+            table_erase(parent, node.first_cp);
+            kids_erase(nodes_[parent], node.first_cp);
+            graveyard.push_back(e.node);
+        }
+        if (parent != kNoNode && find_tenant(nodes_[parent], e.tenant) >= 0) {
+            bool child_has = false;
+            for (auto& k : nodes_[parent].kids) if (find_tenant(nodes_[k.second], e.tenant) >= 0) { child_has = true; break; }
+            if (!child_has) pq.push(Ent{ts_of(parent, e.tenant), seq++, e.tenant, parent});
+        }
+    }
+    for (uint32_t g : graveyard) free_node(g);
+}
+
+size_t StringTreeIndex::tenant_char_size(uint32_t tenant) const {
+    auto it = tenant_chars_.find(tenant);
+    return it == tenant_chars_.end() ? 0 : it->second;
+}
+std::map<std::string, size_t> StringTreeIndex::tenant_char_counts() const {
+    std::map<std::string, size_t> out;
+    for (auto& kv : tenant_chars_) out[tenants_->names[kv.first]] = kv.second;
+    return out;
+}
+std::map<std::string, size_t> StringTreeIndex::used_size_per_tenant() const {
+    std::map<std::string, size_t> out;
+    for (uint32_t i = 0; i < nodes_.size(); ++i) {
+        const Node& nd = nodes_[i];
+        if (!nd.alive) continue;
+        for (auto& kv : nd.tenants) out[tenants_->names[kv.first]] += nd.label_chars;
+    }
+    return out;
+}
+void StringTreeIndex::clear() {
+    nodes_.clear(); nodes_.emplace_back();
+    free_nodes_.clear(); live_nodes_ = 0;
+    bytes_.clear(); uploaded_bytes_ = 0;
+    table_.assign(1024, StrChildSlot{0, 0, 0}); mask_ = 1023; table_live_ = table_tombs_ = 0;
+    tenant_chars_.clear();
+    full_dirty_ = true; dirty_nodes_.clear(); dirty_slots_.clear();
+}
+void StringTreeIndex::entries(std::vector<std::pair<std::string, std::vector<std::pair<uint32_t, uint64_t>>>>& out) const {
+    struct Frame { uint32_t node; size_t path_len; };
+    std::string path;
+    // explicit pre-order, children in char order
+    std::vector<std::pair<uint32_t, size_t>> stack{{0, 0}};
+    while (!stack.empty()) {
+        auto [id, plen] = stack.back(); stack.pop_back();
+        const Node& nd = nodes_[id];
+        path.resize(plen);
+        path.append((const char*)label(nd), nd.label_bytes);
+        if (!nd.tenants.empty()) {
+            std::vector<std::pair<uint32_t, uint64_t>> ts(nd.tenants.begin(), nd.tenants.end());
+            std::sort(ts.begin(), ts.end(), [&](auto& a, auto& b) { return tenants_->rank[a.first] < tenants_->rank[b.first]; });
+            out.push_back({path, ts});
+        }
+        for (size_t k = nd.kids.size(); k-- > 0;) stack.push_back({nd.kids[k].second, path.size()});
+    }
+}
+
+// =================================================================================================================
+// device mirror
+// =================================================================================================================
+namespace {
+__global__ void scatter_slots_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[idx[t]] = src[t];
+}
+__global__ void scatter_headers_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { const size_t d = (size_t)idx[t] * 2; dst[d] = src[(size_t)t * 2]; dst[d + 1] = src[(size_t)t * 2 + 1]; }
+}
+}  // namespace
+
+StrHeader StringTreeIndex::header_of(uint32_t id) const {
+    const Node& nd = nodes_[id];
+    StrHeader h{};
+    h.label_off = nd.label_off;
+    h.label_bytes = nd.alive ? nd.label_bytes : 0;
+    h.label_chars = nd.alive ? nd.label_chars : 0;
+    h.any_tenant = nd.alive ? any_tenant(nd) : -1;
+    h.cache_valid = nd.alive && cache_valid(nd) ? 1u : 0u;
+    return h;
+}
+
+StringTreeView StringTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
+    if (!device_enabled) throw Error(SMGX_DEVICE_ERROR, "policy was created with device_id = -1 (host mirror only): no GPU path, no CPU fallback");
+    if (tenants_version_seen != tenants_->version) { full_dirty_ = true; tenants_version_seen = tenants_->version; }
+    if (bytes_.size() + 16 > d_bytes_.cap) {
+        if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
+        SMGX_CUDA(cudaDeviceSynchronize());
+        d_bytes_.reserve(std::max<size_t>(bytes_.capacity() * 2, 4096) + 16);
+        uploaded_bytes_ = 0;
+    }
+    if (uploaded_bytes_ < bytes_.size()) {
+        SMGX_CUDA(cudaMemcpyAsync(d_bytes_.as<uint8_t>() + uploaded_bytes_, bytes_.data() + uploaded_bytes_, bytes_.size() - uploaded_bytes_,
+                                  cudaMemcpyHostToDevice, stream));
+        SMGX_CUDA(cudaStreamSynchronize(stream));   // bytes_ may reallocate before the copy engine reads it
+        uploaded_bytes_ = bytes_.size();
+    }
+    if (!full_dirty_ && dirty_nodes_.size() + dirty_slots_.size() > table_.size() / 8) full_dirty_ = true;
+    if (full_dirty_) {
+        if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
+        SMGX_CUDA(cudaDeviceSynchronize());
+        std::vector<StrHeader> hdr(nodes_.size());
+        for (uint32_t i = 0; i < nodes_.size(); ++i) hdr[i] = header_of(i);
+        d_headers_.reserve(std::max<size_t>(nodes_.capacity(), 16) * sizeof(StrHeader));
+        d_table_.reserve(table_.size() * sizeof(StrChildSlot));
+        SMGX_CUDA(cudaMemcpyAsync(d_headers_.ptr, hdr.data(), hdr.size() * sizeof(StrHeader), cudaMemcpyHostToDevice, stream));
+        SMGX_CUDA(cudaMemcpyAsync(d_table_.ptr, table_.data(), table_.size() * sizeof(StrChildSlot), cudaMemcpyHostToDevice, stream));
+        SMGX_CUDA(cudaStreamSynchronize(stream));
+        full_dirty_ = false;
+        dirty_nodes_.clear(); dirty_slots_.clear();
+    } else if (!dirty_nodes_.empty() || !dirty_slots_.empty()) {
+        if (!stage_done_) SMGX_CUDA(cudaEventCreateWithFlags(&stage_done_, cudaEventDisableTiming));
+        if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
+        auto uniq = [](std::vector<uint32_t>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
+        uniq(dirty_nodes_); uniq(dirty_slots_);
+        const size_t nn = dirty_nodes_.size(), ns = dirty_slots_.size();
+        const size_t off_ni = 0, off_si = nn * 4, off_nr = ((off_si + ns * 4 + 15) / 16) * 16, off_sr = off_nr + nn * 32, total = off_sr + ns * 16;
+        stage_.reserve(total);
+        d_stage_.reserve(total);
+        char* st = stage_.as<char>();
+        memcpy(st + off_ni, dirty_nodes_.data(), nn * 4);
+        memcpy(st + off_si, dirty_slots_.data(), ns * 4);
+        for (size_t i = 0; i < nn; ++i) { const StrHeader h = header_of(dirty_nodes_[i]); memcpy(st + off_nr + i * 32, &h, 32); }
+        for (size_t i = 0; i < ns; ++i) memcpy(st + off_sr + i * 16, &table_[dirty_slots_[i]], 16);
+        SMGX_CUDA(cudaMemcpyAsync(d_stage_.ptr, st, total, cudaMemcpyHostToDevice, stream));
+        char* ds = d_stage_.as<char>();
+        if (nn) { scatter_headers_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, stream>>>(d_headers_.as<uint4>(), (const uint32_t*)(ds + off_ni), (const uint4*)(ds + off_nr), (uint32_t)nn); ++*launches; }
+        if (ns) { scatter_slots_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, stream>>>(d_table_.as<uint4>(), (const uint32_t*)(ds + off_si), (const uint4*)(ds + off_sr), (uint32_t)ns); ++*launches; }
+        SMGX_CUDA(cudaGetLastError());
+        SMGX_CUDA(cudaEventRecord(stage_done_, stream));
+        stage_pending_ = true;
+        dirty_nodes_.clear(); dirty_slots_.clear();
+    }
+    return StringTreeView{d_bytes_.as<uint8_t>(), d_headers_.as<StrHeader>(), d_table_.as<StrChildSlot>(), mask_};
+}
+
+// =================================================================================================================
+// K2c + K3: longest char-aligned prefix walk + pick, one warp per request
+// =================================================================================================================
+namespace {
+constexpr unsigned FULLM = 0xffffffffu;
+
+// number of chars (non-continuation bytes) in s[0..n), warp-cooperative; result on every lane
+__device__ __forceinline__ uint32_t warp_count_chars(const uint8_t* __restrict__ s, uint32_t n, int lane) {
+    uint32_t c = 0;
+    for (uint32_t i = lane; i < n; i += 32) c += (s[i] & 0xC0) != 0x80;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULLM, c, d);
+    return c;
+}
+
+__global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, FleetView f, const int32_t* __restrict__ slice_of_tenant,
+                                                            const uint8_t* __restrict__ flags, uint32_t n_tenants, StringSelectArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= a.count) return;
+    const uint32_t r = a.first + w;
+    const uint32_t off = a.offsets[r], nbytes = a.offsets[r + 1] - off;
+    const uint8_t* s = a.text + off;
+    const uint32_t input_chars = warp_count_chars(s, nbytes, lane);
+
+    uint32_t cur = 0, pos = 0, matched = 0, terminal = 0;
+    while (pos < nbytes) {
+        uint32_t cl;
+        const uint32_t cp = utf8_first(s + pos, &cl);   // every lane reads the same ≤ 4 bytes (broadcast)
+        const uint64_t key = str_child_key(cur, cp);
+        uint32_t idx = str_child_home(key) & tv.child_mask;
+        uint32_t child = kNoNode;
+        for (;;) {   // warp-uniform probe
+            const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(tv.children + idx));
+            const uint64_t skey = ((uint64_t)s4.y << 32) | s4.x;
+            if (skey == 0) break;
+            if (skey == key && s4.z < kTombChild) { child = s4.z; break; }
+            idx = (idx + 1) & tv.child_mask;
+        }
+        if (child == kNoNode) break;
+        const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(tv.headers + child));
+        const uint64_t label_off = ((uint64_t)h4.y << 32) | h4.x;
+        const uint32_t label_bytes = h4.z, label_chars = h4.w;
+        const uint8_t* lab = tv.bytes + label_off;
+        const uint32_t L = min(label_bytes, nbytes - pos);
+        // common byte prefix, 128 bytes per step (4 consecutive bytes per lane)
+        uint32_t common = L;
+        for (uint32_t c = 0; c < L; c += 128) {
+            const uint32_t b = c + (uint32_t)lane * 4;
+            uint32_t first = 4;
+#pragma unroll
+            for (int k = 3; k >= 0; --k) if (b + k < L && __ldg(lab + b + k) != s[pos + b + k]) first = (uint32_t)k;
+            const unsigned mm = __ballot_sync(FULLM, first < 4);
+            if (mm) {
+                const int src = __ffs((int)mm) - 1;
+                common = c + (uint32_t)src * 4 + __shfl_sync(FULLM, first, src);
+                break;
+            }
+        }
+        if (common < L) while (common > 0 && (s[pos + common] & 0xC0) == 0x80) --common;   // mismatch inside a char
+        const uint32_t shared_chars = common == label_bytes ? label_chars : warp_count_chars(s + pos, common, lane);
+        matched += shared_chars;
+        terminal = child;                       // a partial edge match still selects that child (:582-586)
+        if (common != label_bytes) break;
+        pos += common;
+        cur = child;
+    }
+    if (lane != 0) return;
+    const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(tv.headers + terminal) + 1);
+    const int32_t tenant = (int32_t)t4.x;
+    a.out_node[r] = terminal;
+    a.out_tenant[r] = tenant;
+    a.out_fill[r] = t4.y ? 0 : 1;
+    int32_t out = -1;
+    uint32_t branch = SMGX_BR_NO_HEALTHY;
+    if (a.decide) {
+        const FleetDerived fd = *f.derived;
+        if (fd.n_healthy == 0) {
+        } else if (fd.imbalanced) {
+            out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
+        } else {
+            // match_rate = matched_char_count as f32 / input_char_count as f32, 0 chars → 0.0, strict > (cache_aware.rs:917-927)
+            const float rate = input_chars == 0 ? 0.0f : __fdiv_rn(__uint2float_rn(matched), __uint2float_rn(input_chars));
+            if (rate > a.cache_threshold) {
+                const int32_t sl = (tenant >= 0 && (uint32_t)tenant < n_tenants) ? slice_of_tenant[tenant] : -1;
+                if (sl >= 0 && (flags[sl] & 1)) { out = sl; branch = SMGX_BR_TREE_MATCH; }
+                else { out = fd.first_healthy; branch = SMGX_BR_TREE_FALLBACK_FIRST_HEALTHY; }
+            } else { out = fd.min_load_idx; branch = SMGX_BR_TREE_MIN_LOAD; }
+        }
+    }
+    a.out_idx[r] = out;
+    if (a.out_info) {
+        smgx_decision_info di;
+        di.matched = matched; di.input = input_chars; di.branch = (uint8_t)branch;
+        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        a.out_info[r] = di;
+    }
+}
+}  // namespace
+
+void launch_string_select(const StringTreeView& tv, const FleetView& fleet, const int32_t* d_slice_of_tenant, const uint8_t* d_flags,
+                          uint32_t n_tenants, const StringSelectArgs& a, cudaStream_t stream) {
+    if (a.count == 0) return;
+    string_select_kernel<<<(unsigned)(((uint64_t)a.count * 32 + 255) / 256), 256, 0, stream>>>(tv, fleet, d_slice_of_tenant, d_flags, n_tenants, a);
+    SMGX_CUDA(cudaGetLastError());
+}
+
+}  // namespace smgx

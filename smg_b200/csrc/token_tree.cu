@@ -249,7 +249,7 @@ void TokenTreeIndex::insert_tokens(const uint32_t* toks, size_t n, uint32_t tena
 
 // TokenTree::match_prefix_with_counts (token_tree.rs:615-740), host walk
 TreeMatch TokenTreeIndex::match_prefix_host(const uint32_t* toks, size_t n, bool do_touch) {
-    TreeMatch r{-1, 0, (uint32_t)n, {}};
+    TreeMatch r{-1, 0, (uint32_t)n, {}, {}};
     const size_t aligned = (n / kPage) * kPage;
     if (aligned == 0) { r.tenant = any_tenant(0); return r; }
     const uint32_t* rem = toks;
@@ -271,11 +271,15 @@ TreeMatch TokenTreeIndex::match_prefix_host(const uint32_t* toks, size_t n, bool
         r.matched += (uint32_t)m;
         r.tenant = t;
         r.path.push_back(child);
+        r.path_tenants.push_back(t);
         if (m < nodes_[child].label_len) break;
         rem += m; rem_len -= m;
         cur = child;
     }
     return r;
+}
+void TokenTreeIndex::apply_match_touches(const uint32_t* path, const int32_t* path_tenants, uint32_t path_len) {
+    for (uint32_t d = 0; d < path_len; ++d) if (path_tenants[d] >= 0) touch(path[d], (uint32_t)path_tenants[d]);
 }
 void TokenTreeIndex::apply_match_touches(const uint32_t* path, uint32_t path_len) {
     for (uint32_t d = 0; d < path_len; ++d) {
@@ -550,7 +554,10 @@ __global__ void __launch_bounds__(256) tree_select_kernel(TokenTreeView tv, Flee
         if (hd.any_tenant < 0) break;                  // node without tenants ends the walk before being counted (:682-683)
         matched += m;
         tenant = hd.any_tenant;
-        if (lane == 0 && depth < kPathCap) a.out_path[(size_t)r * kPathCap + depth] = child;
+        if (lane == 0 && depth < kPathCap) {
+            a.out_path[(size_t)r * kPathCap + depth] = child;
+            a.out_path_tenant[(size_t)r * kPathCap + depth] = hd.any_tenant;
+        }
         ++depth;
         if (m < hd.label_len) break;                   // partial edge match (:691-696)
         pos += m;

@@ -60,7 +60,7 @@ struct TenantTable {
     int64_t find(const std::string& s) const { auto it = ids.find(s); return it == ids.end() ? -1 : (int64_t)it->second; }
 };
 
-struct TreeMatch { int32_t tenant; uint32_t matched; uint32_t input; std::vector<uint32_t> path; };
+struct TreeMatch { int32_t tenant; uint32_t matched; uint32_t input; std::vector<uint32_t> path; std::vector<int32_t> path_tenants; };
 
 class TokenTreeIndex {
 public:
@@ -71,6 +71,7 @@ public:
     void insert_tokens(const uint32_t* toks, size_t n, uint32_t tenant);                    // :401-609
     TreeMatch match_prefix_host(const uint32_t* toks, size_t n, bool touch);                // :615-740 (host walk; used for paths deeper than kPathCap)
     void apply_match_touches(const uint32_t* path, uint32_t path_len);                      // touch_tenant on the matched nodes, in order (:685-689)
+    void apply_match_touches(const uint32_t* path, const int32_t* path_tenants, uint32_t path_len);   // same, with the tenants the walk read
     void evict_tenant(uint32_t tenant, size_t max_tokens);                                  // :798-863
     void evict_tenant_by_size(size_t max_size);                                             // :1011-1024
     size_t tenant_token_size(uint32_t tenant) const;
@@ -145,6 +146,7 @@ struct TreeSelectArgs {
     int32_t* out_idx;            // [n]
     smgx_decision_info* out_info;  // [n]
     uint32_t* out_path;          // [n][kPathCap]
+    int32_t* out_path_tenant;    // [n][kPathCap] any-tenant each matched node had when it was read
     uint32_t* out_path_len;      // [n] (total matched nodes, may exceed kPathCap)
     int32_t* out_tenant;         // [n] any-tenant of the deepest matched node (−1 = "empty")
     float cache_threshold;

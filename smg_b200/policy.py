@@ -75,7 +75,7 @@ def _p(a):
 class _Handle:
     """Owns one smgx_policy*."""
 
-    def __init__(self, cfg: CacheAwareConfig, device_id: int, max_batch: int = 0, max_tokens_per_request: int = 0):
+    def __init__(self, cfg: CacheAwareConfig, device_id: int, max_batch: int = 0, max_tokens_per_request: int = 0, tree_batch_mode: int = 0):
         self.L = _lib.load()
         c = _lib.Config()
         self.L.smgx_default_config(C.byref(c))
@@ -83,6 +83,7 @@ class _Handle:
         c.balance_rel_threshold, c.eviction_interval_secs = cfg.balance_rel_threshold, cfg.eviction_interval_secs
         c.max_tree_size, c.block_size = cfg.max_tree_size, cfg.block_size
         c.device_id, c.max_batch, c.max_tokens_per_request = device_id, max_batch, max_tokens_per_request
+        c.tree_batch_mode = tree_batch_mode
         err = _lib.new_err()
         self.p = self.L.smgx_policy_create(C.byref(c), C.byref(err))
         if not self.p:
@@ -268,6 +269,87 @@ class TokenTree:
         return res
 
 
+class StringMatchResult:  # kv_index::PrefixMatchResult of the string tree (string_tree.rs:47-54)
+    def __init__(self, tenant, matched, inp):
+        self.tenant, self.matched_char_count, self.input_char_count = tenant, matched, inp
+
+
+class Tree:
+    """kv_index::Tree (char-level string tree, HTTP text routing) bound to (policy handle, model): mutations on the
+    host-authoritative tree inside the library, match_prefix_with_counts on the GPU mirror."""
+
+    def __init__(self, handle: _Handle, model: str = UNKNOWN_MODEL_ID):
+        self.h, self.model = handle, model.encode()
+
+    @classmethod
+    def standalone(cls, device_id: int = 0):
+        return cls(_Handle(CacheAwareConfig(eviction_interval_secs=0), device_id), UNKNOWN_MODEL_ID)
+
+    @staticmethod
+    def _b(text: str):
+        b = text.encode("utf-8")
+        return (np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(0, np.uint8)), len(b)
+
+    def insert_text(self, text: str, tenant: str):
+        a, n = self._b(text)
+        self.h.call("smgx_stree_insert_text", self.model, _p(a), n, tenant.encode())
+
+    def match_prefix_with_counts(self, text: str) -> StringMatchResult:
+        a, n = self._b(text)
+        m, k = C.c_uint32(), C.c_uint32()
+        buf = C.create_string_buffer(1024)
+        self.h.call("smgx_stree_match", self.model, _p(a), n, C.byref(m), C.byref(k), C.cast(buf, C.c_void_p), 1024)
+        return StringMatchResult(buf.value.decode(), m.value, k.value)
+
+    def prefix_match_tenant(self, text: str, tenant: str) -> str:
+        a, n = self._b(text)
+        out = C.c_uint32()
+        self.h.call("smgx_stree_prefix_match_tenant", self.model, _p(a), n, tenant.encode(), C.byref(out))
+        return text.encode("utf-8")[: out.value].decode("utf-8")
+
+    def evict_tenant_by_size(self, max_size: int):
+        self.h.call("smgx_evict_cache", max_size)
+
+    def _sizes(self, maintained: int):
+        out = C.c_void_p()
+        self.h.call("smgx_stree_sizes", self.model, maintained, C.byref(out))
+        text = C.cast(out, C.c_char_p).value.decode()
+        self.h.L.smgx_free_string(out)
+        res = {}
+        for line in text.split("\n"):
+            if line:
+                k, v = line.rsplit("=", 1)
+                res[k] = int(v)
+        return res
+
+    def get_used_size_per_tenant(self):
+        return self._sizes(0)
+
+    def get_tenant_char_count(self):
+        return self._sizes(1)
+
+    def node_count(self) -> int:
+        out = C.c_uint64()
+        self.h.call("smgx_stree_node_count", self.model, C.byref(out))
+        return out.value
+
+    def clear(self):
+        self.h.call("smgx_stree_clear", self.model)
+
+    def entries(self):
+        out, ln = C.c_void_p(), C.c_uint64()
+        self.h.call("smgx_stree_entries", self.model, C.byref(out), C.byref(ln))
+        raw = C.string_at(out, ln.value).decode("utf-8")
+        self.h.L.smgx_free_string(out)
+        res = []
+        for rec in raw.split("\x1e"):
+            if not rec:
+                continue
+            path, tens = rec.split("\x1f")
+            res.append((path, [(kv.rsplit("=", 1)[0], int(kv.rsplit("=", 1)[1])) for kv in tens.split(";") if kv]))
+        return res
+
+
 class TiktokenTokenizer:
     """tokenizer::TiktokenTokenizer (crates/tokenizer/src/tiktoken.rs:132) on the GPU, bound to (policy handle, model).
     encode() keeps the reference's behaviour of always recognising special-token strings (tiktoken.rs:444-462)."""
@@ -299,13 +381,17 @@ class TiktokenTokenizer:
         return self.encode_batch([text])[0]
 
 
+TREE_BATCH_MODES = {"sequential": 0, "snapshot": 1}   # smgx_tree_batch_mode (include/smgx.h)
+
+
 class CacheAwarePolicy:
     """policies::CacheAwarePolicy on the GPU.  select_worker keeps the reference signature; select_worker_batch is the
     batched form the host batcher uses (all requests see one fleet snapshot)."""
 
-    def __init__(self, config: Optional[CacheAwareConfig] = None, device_id: int = 0, max_batch: int = 0, max_tokens_per_request: int = 0):
+    def __init__(self, config: Optional[CacheAwareConfig] = None, device_id: int = 0, max_batch: int = 0, max_tokens_per_request: int = 0,
+                 tree_batch_mode: str = "sequential"):
         self.config = config or CacheAwareConfig()
-        self._h = _Handle(self.config, device_id, max_batch, max_tokens_per_request)
+        self._h = _Handle(self.config, device_id, max_batch, max_tokens_per_request, TREE_BATCH_MODES[tree_batch_mode])
         self._slices = {}   # model → tuple(urls) currently registered
         self._monitor = None
 
@@ -375,9 +461,10 @@ class CacheAwarePolicy:
         """LoadBalancingPolicy::select_worker (cache_aware.rs:648): index into `workers` or None."""
         if not workers:
             return None
-        if info.tokens is None:
-            raise _lib.SmgxError(_lib.UNKNOWN_ERROR, "text (string-tree) routing is not part of this build yet")
-        idx, _ = self.select_worker_batch(workers, [info.tokens])
+        if info.tokens is None:   # HTTP routers: string tree on request_text.unwrap_or("") (cache_aware.rs:688-689)
+            idx, _ = self.select_worker_batch_request_text(workers, [info.request_text or ""])
+        else:
+            idx, _ = self.select_worker_batch(workers, [info.tokens])
         i = int(idx[0])
         if i >= 0:
             workers[i]._processed += 1  # mirror of increment_processed(); the library keeps the authoritative counters
@@ -399,6 +486,20 @@ class CacheAwarePolicy:
         tok_ptr = _p(tokens) if tokens.size else C.cast(C.create_string_buffer(4), C.c_void_p)
         self._h.call("smgx_select_batch_tokens", model, tok_ptr, _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
         return out[:n], (info if info is None else [info[i] for i in range(n)])
+
+    def select_worker_batch_request_text(self, workers: Sequence[BasicWorker], texts, want_info: bool = True):
+        """Batch of HTTP-mode requests (request_text, no tokens) against one fleet snapshot: string-tree walk + pick on the
+        GPU (select_worker_with_text, cache_aware.rs:907-974).  → (worker_idx int32[n], info list with char counts)."""
+        model = self._push_fleet(workers)
+        data, offsets = TiktokenTokenizer._ragged(texts)
+        n = len(texts)
+        out = np.full(max(n, 1), -1, dtype=np.int32)
+        info = (_lib.DecisionInfo * max(n, 1))() if want_info else None
+        self._h.call("smgx_select_batch_request_text", model, _p(data), _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
+        return out[:n], (info if info is None else [info[i] for i in range(n)])
+
+    def set_tree_batch_mode(self, mode: str):
+        self._h.call("smgx_set_tree_batch_mode", TREE_BATCH_MODES[mode])
 
     # -- tokenizer + text-in pick (the whole hot path on the device) ------------------------------------------------
     def load_tiktoken_tokenizer(self, path: str, special_tokens=None, model: str = UNKNOWN_MODEL_ID) -> TiktokenTokenizer:
@@ -426,6 +527,9 @@ class CacheAwarePolicy:
         t = TokenTree.__new__(TokenTree)
         t.h, t.model = self._h, model.encode()
         return t
+
+    def string_tree(self, model: str = UNKNOWN_MODEL_ID) -> "Tree":
+        return Tree(self._h, model)
 
     def take_processed(self, model: str = UNKNOWN_MODEL_ID, n: Optional[int] = None):
         n = n if n is not None else len(self._slices.get(model, ()))

@@ -32,15 +32,17 @@ def test_policy_scenarios_on_gpu(name):
     SC.ALL[name](_mk_policy)
 
 
+@pytest.mark.parametrize("mode", ["sequential", "snapshot"])
 @pytest.mark.parametrize("seed,n_workers,shape", [(1, 8, "trunks"), (2, 64, "trunks"), (3, 16, "zipf"), (4, 5, "ragged")])
-def test_random_stream_parity_with_sequential_oracle(seed, n_workers, shape):
+def test_random_stream_parity_with_oracle(seed, n_workers, shape, mode):
     """Batches of requests (with repeated / shared prefixes inside a batch) routed through the GPU path must equal the
-    oracle called one request at a time with the same frozen fleet snapshot: pick, branch and matched tokens."""
+    oracle with the same frozen fleet snapshot — called one request at a time (sequential batch mode, the reference's
+    one-by-one semantics) or as one snapshot batch (snapshot mode): pick, branch and matched tokens."""
     from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy
     rng = np.random.default_rng(seed)
     cfg = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=1.5, block_size=16)
     urls = synth.worker_urls(n_workers)
-    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **cfg))
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **cfg), tree_batch_mode=mode)
     ws = [BasicWorker(u) for u in urls]
     pol.init_workers(ws)
     orc.reset_globals()
@@ -74,6 +76,14 @@ def test_random_stream_parity_with_sequential_oracle(seed, n_workers, shape):
         op.set_state(loads, healthy, [1] * n_workers)
         reqs = [make_request() for _ in range(int(rng.integers(1, 70)))]
         idx, info = pol.select_worker_batch(ws, reqs)
+        if mode == "snapshot":
+            flat = np.concatenate(reqs).astype(np.uint32) if sum(len(r) for r in reqs) else np.zeros(0, np.uint32)
+            off = np.zeros(len(reqs) + 1, np.uint64)
+            np.cumsum([len(r) for r in reqs], out=off[1:])
+            want, br, ma, _ = op.select_batch_tokens(flat, off, snapshot=True)
+            for i in range(len(reqs)):
+                assert want[i] == idx[i] and br[i] == info[i].branch and ma[i] == info[i].matched, (batch_no, i)
+            continue
         for i, r in enumerate(reqs):
             d = op.select_worker(tokens=r)
             assert (d.idx if d.idx is not None else -1) == idx[i], (batch_no, i, d.branch, orc.BRANCHES[info[i].branch])

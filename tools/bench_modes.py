@@ -37,7 +37,8 @@ def tree_mode():
     rng = np.random.default_rng(42)
     paths = tree_population(n_trunks, rng)
     urls = synth.worker_urls(W)
-    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), max_batch=B, max_tokens_per_request=512)
+    bmode = os.environ.get("TREE_BATCH_MODE", "sequential")
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), max_batch=B, max_tokens_per_request=512, tree_batch_mode=bmode)
     ws = [BasicWorker(u) for u in urls]
     for w, l in zip(ws, synth.poisson_loads(W, 8, 42)):
         w.set_load(int(l))
@@ -74,18 +75,60 @@ def tree_mode():
     batches = [batch(100 + i) for i in range(4)]
     # parity of the first batch, then timing
     idx, _ = pol.select_worker_batch(ws, tokens=batches[0][0], offsets=batches[0][1])
-    want, _, _, t_cpu0 = op.select_batch_tokens(batches[0][0], batches[0][1].astype(np.uint64))
+    snap = bmode == "snapshot"
+    want, _, _, t_cpu0 = op.select_batch_tokens(batches[0][0], batches[0][1].astype(np.uint64), snapshot=snap)
     assert np.array_equal(idx, want), "tree-mode picks differ from the oracle"
     t0 = time.perf_counter()
     for b in batches[1:]:
         pol.select_worker_batch(ws, tokens=b[0], offsets=b[1], want_info=False)
     t_gpu = time.perf_counter() - t0
-    t_cpu = sum(op.select_batch_tokens(b[0], b[1].astype(np.uint64))[3] for b in batches[1:])
+    t_cpu = sum(op.select_batch_tokens(b[0], b[1].astype(np.uint64), snapshot=snap)[3] for b in batches[1:])
     n = 3 * B
-    return {"mode": "approximate token tree (cache_aware.rs:834-904): GPU match+pick per conflict-free segment, host insert in request order",
+    assert pol.token_tree().entries() == op.token_tree().entries(), "trees diverged"
+    return {"mode": "approximate token tree (cache_aware.rs:834-904): GPU walk+pick, host-side touches+inserts in request order", "tree_batch_mode": bmode,
             "workers": W, "batch": B, "tree_paths": len(paths), "tree_nodes_approx": n_trunks * (1 + 32 + 1024), "tree_build_s": round(t_build, 2),
             "smgx_decisions_per_s": n / t_gpu, "oracle_1core_decisions_per_s": n / t_cpu, "parity_first_batch": True,
             "kernel_launches": pol.kernel_launches()}
+
+
+def text_mode():
+    """HTTP text (string-tree) mode: chat-style routing texts with shared system prompts, ~2 KB each."""
+    import random
+    from oracle import orc
+    from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, synth
+    W, B = 64, int(os.environ.get("BATCH", "1024"))
+    bmode = os.environ.get("TREE_BATCH_MODE", "sequential")
+    urls = synth.worker_urls(W)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), max_batch=B, tree_batch_mode=bmode)
+    ws = [BasicWorker(u) for u in urls]
+    for w, l in zip(ws, synth.poisson_loads(W, 8, 42)):
+        w.set_load(int(l))
+    pol.init_workers(ws)
+    orc.reset_globals()
+    op = orc.CacheAwarePolicy(eviction_interval_secs=0, **CFG)
+    op.set_workers(urls)
+    op.set_state([w.load() for w in ws], [1] * W, [1] * W)
+    r = random.Random(7)
+    words = ["cache", "aware", "router", "prefix", "radix", "tree", "worker", "tenant", "load", "balance", "token", "你好", "été", "GPU"]
+    systems = [" ".join(r.choice(words) for _ in range(200)) for _ in range(32)]      # ≈1.2 KB shared prefixes
+    def batch():
+        return [r.choice(systems) + " " + " ".join(r.choice(words) for _ in range(r.randrange(20, 160))) for _ in range(B)]
+    batches = [batch() for _ in range(4)]
+    snap = bmode == "snapshot"
+    idx, _ = pol.select_worker_batch_request_text(ws, batches[0])
+    want = op.select_batch_text(batches[0], snapshot=snap)[0]
+    assert np.array_equal(idx, want), "text-mode picks differ from the oracle"
+    t0 = time.perf_counter()
+    for b in batches[1:]:
+        pol.select_worker_batch_request_text(ws, b, want_info=False)
+    t_gpu = time.perf_counter() - t0
+    t_cpu = sum(op.select_batch_text(b, snapshot=snap)[4] for b in batches[1:])
+    assert pol.string_tree().entries() == op.string_tree().entries(), "trees diverged"
+    n = 3 * B
+    return {"mode": "HTTP text / string tree (cache_aware.rs:907-974): GPU walk+pick, host-side match effects + inserts in request order",
+            "tree_batch_mode": bmode, "workers": W, "batch": B, "mean_request_bytes": int(np.mean([len(t.encode()) for t in batches[1]])),
+            "smgx_decisions_per_s": n / t_gpu, "oracle_1core_decisions_per_s": n / t_cpu, "parity_first_batch": True,
+            "trees_identical_after": True, "kernel_launches": pol.kernel_launches()}
 
 
 def sharded_mode():
@@ -164,6 +207,6 @@ def sharded_mode():
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "tree"
-    r = tree_mode() if mode == "tree" else sharded_mode()
+    r = {"tree": tree_mode, "text": text_mode, "sharded": sharded_mode}[mode]()
     if r is not None:
         print(json.dumps(r), flush=True)
