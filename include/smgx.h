@@ -82,7 +82,8 @@ typedef struct smgx_decision_info {
     uint32_t matched;   /* event mode: overlap score in blocks; tree modes: matched tokens / chars */
     uint32_t input;     /* request length in tokens / chars                                        */
     uint8_t branch;     /* smgx_branch                                                             */
-    uint8_t reserved[3];
+    uint8_t nodes;      /* tree modes: nodes the walk counted (saturates at 255); 0 in event mode  */
+    uint8_t reserved[2];
 } smgx_decision_info;
 
 /* Worker-id-sharded fleets (BASELINE config 4: 4096 workers, 512 per GPU).  Each shard holds a contiguous
@@ -169,6 +170,15 @@ smgx_status smgx_tree_insert_tokens(smgx_policy* p, const char* model_key, const
  * nothing matched). */
 smgx_status smgx_tree_match_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, uint32_t n, uint32_t* out_matched,
                                    uint32_t* out_input, char* out_tenant, uint32_t tenant_cap, char** err);
+/* n inserts in one call (tree build / replay): sequence i = tokens[offsets[i] .. offsets[i+1]) for tenants[i]. */
+smgx_status smgx_tree_insert_tokens_batch(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint64_t* offsets, uint32_t n,
+                                          const char* const* tenants, char** err);
+/* Read-only walk + pick (match_prefix_with_counts without its touches, then the select_worker_with_tokens decision) of
+ * device-resident batches against the current tree; batch j runs on lane j % smgx_pipeline_depth().  The walk kernel on
+ * its own — bench and capacity planning; routing goes through the select calls, which also apply the side effects. */
+smgx_status smgx_tree_walk_many_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
+                                       const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx,
+                                       smgx_decision_info* const* d_out_info, char** err);
 smgx_status smgx_tree_evict_tenant(smgx_policy* p, const char* model_key, const char* tenant, uint64_t max_tokens, char** err);  /* :798 */
 smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err);          /* CacheAwarePolicy::evict_cache (cache_aware.rs:311) */
 smgx_status smgx_tree_tenant_size(smgx_policy* p, const char* model_key, const char* tenant, uint64_t* out, char** err);           /* :988 */

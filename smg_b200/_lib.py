@@ -22,7 +22,7 @@ class Config(C.Structure):
 
 
 class DecisionInfo(C.Structure):
-    _fields_ = [("matched", C.c_uint32), ("input", C.c_uint32), ("branch", C.c_uint8), ("reserved", C.c_uint8 * 3)]
+    _fields_ = [("matched", C.c_uint32), ("input", C.c_uint32), ("branch", C.c_uint8), ("nodes", C.c_uint8), ("reserved", C.c_uint8 * 2)]
 
 
 class SmgxError(RuntimeError):
@@ -88,6 +88,8 @@ def load():
     sig("smgx_content_hashes", st, vp, vp, u32, u32, vp, u32, P(u32), pp)
     sig("smgx_tree_create", st, vp, cp, C.c_int, pp)
     sig("smgx_tree_insert_tokens", st, vp, cp, vp, u32, cp, pp)
+    sig("smgx_tree_insert_tokens_batch", st, vp, cp, vp, vp, u32, P(cp), pp)
+    sig("smgx_tree_walk_many_device", st, vp, cp, u32, vp, vp, vp, vp, vp, pp)
     sig("smgx_tree_match_tokens", st, vp, cp, vp, u32, P(u32), P(u32), vp, u32, pp)
     sig("smgx_tree_evict_tenant", st, vp, cp, cp, u64, pp)
     sig("smgx_evict_cache", st, vp, u64, pp)

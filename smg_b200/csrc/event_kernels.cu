@@ -276,7 +276,7 @@ __device__ __forceinline__ void write_pick(const BatchDesc& b, uint32_t r, int32
     if (b.out_info) {
         smgx_decision_info di;
         di.matched = matched; di.input = ntok; di.branch = (uint8_t)branch;
-        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        di.nodes = 0; di.reserved[0] = di.reserved[1] = 0;
         b.out_info[r] = di;
     }
 }
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const smgx_shard_cand
     if (out_info) {
         smgx_decision_info di;
         di.matched = matched; di.input = 0; di.branch = (uint8_t)branch;
-        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        di.nodes = 0; di.reserved[0] = di.reserved[1] = 0;
         out_info[r] = di;
     }
 }

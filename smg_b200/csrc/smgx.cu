@@ -300,10 +300,7 @@ public:
                 while (end < n) {
                     const uint32_t len = offsets[end + 1] - offsets[end];
                     if (len >= kPage) {
-                        uint64_t sum = 0;
-                        const uint32_t* pg = tokens + offsets[end];
-                        for (uint32_t i = 0; i < kPage; ++i) sum += ((uint64_t)pg[i] + 1) * page_mult(i);
-                        if (!seen.insert(page_finish(sum, 0)).second) break;
+                        if (!seen.insert(page_key_host(tokens + offsets[end], 0)).second) break;
                     }
                     ++end;
                 }
@@ -515,6 +512,7 @@ public:
     uint64_t token_ts = 0;       // GLOBAL_TIMESTAMP (token_tree.rs:179), shared by every token tree of the policy
     uint64_t string_epoch = 0;   // EPOCH_COUNTER (string_tree.rs:239), shared by every string tree of the policy
     uint32_t tree_batch_mode = SMGX_TREE_BATCH_SEQUENTIAL;
+    uint32_t walk_chunk_seq = 0;
     smgx_cache_aware_config cfg;
     int sm_count = 148;
     size_t l2_bytes = 126u << 20;
@@ -856,6 +854,60 @@ smgx_status smgx_tree_insert_tokens(smgx_policy* p, const char* model_key, const
         ModelState& m = p->impl.model(model_key, true);
         TokenTreeIndex& t = p->impl.tree_of(m, true);
         if (n >= kPage) t.insert_tokens(tokens, n, p->impl.tenants.intern(tenant));   // shorter inputs return before interning (:403-410)
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_tree_insert_tokens_batch(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint64_t* offsets, uint32_t n,
+                                          const char* const* tenants, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (tokens && offsets && tenants), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        TokenTreeIndex& t = p->impl.tree_of(m, true);
+        for (uint32_t i = 0; i < n; ++i) {
+            NONNULL(tenants[i]);
+            SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+            const uint64_t len = offsets[i + 1] - offsets[i];
+            if (len >= kPage) t.insert_tokens(tokens + offsets[i], (size_t)len, p->impl.tenants.intern(tenants[i]));
+        }
+        return SMGX_SUCCESS;
+    });
+}
+// Read-only walk + pick of device-resident batches against the current tree (no touches, no inserts): the K2a kernel by itself.
+smgx_status smgx_tree_walk_many_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
+                                       const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx,
+                                       smgx_decision_info* const* d_out_info, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n_batches == 0 || (d_tokens && d_offsets && n && d_out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        TokenTreeIndex& tree = P.tree_of(m, false);
+        EventIndexView ixv;
+        FleetView fv;
+        P.sync_state(m, &ixv, &fv);
+        P.sync_tenant_map(m);
+        if (tree.pending()) {   // mirror update in ctrl-stream order, then every lane waits for it
+            for (auto& l : P.lanes) if (l.has_done) SMGX_CUDA(cudaStreamWaitEvent(P.ctrl, l.done, 0));
+            tree.flush(P.ctrl, &P.launches);
+            SMGX_CUDA(cudaEventRecord(P.state_ready, P.ctrl));
+            for (auto& l : P.lanes) SMGX_CUDA(cudaStreamWaitEvent(l.stream, P.state_ready, 0));
+        }
+        const TokenTreeView tv = tree.flush(P.ctrl, &P.launches);   // nothing pending: returns the view
+        for (uint32_t j = 0; j < n_batches; ++j) {   // one launch per batch, round-robin over the stream lanes
+            Lane& lane = P.lanes[(P.walk_chunk_seq++) % P.lanes.size()];
+            TreeSelectArgs a{};
+            a.tokens = d_tokens[j]; a.offsets = d_offsets[j]; a.first = 0; a.count = n[j];
+            a.out_idx = d_out_worker_idx[j]; a.out_info = d_out_info ? d_out_info[j] : nullptr;
+            a.cache_threshold = P.cfg.cache_threshold; a.decide = 1;
+            launch_tree_select(tv, fv, m.d_slice_of_tenant.as<int32_t>(), m.d_flags.as<uint8_t>(), (uint32_t)P.tenants.names.size(), a, lane.stream);
+            ++P.launches;
+            SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
+            lane.has_done = true;
+        }
         return SMGX_SUCCESS;
     });
 }

@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
     const uint8_t* s = a.text + off;
     const uint32_t input_chars = warp_count_chars(s, nbytes, lane);
 
-    uint32_t cur = 0, pos = 0, matched = 0, terminal = 0;
+    uint32_t cur = 0, pos = 0, matched = 0, terminal = 0, visited = 0;
     while (pos < nbytes) {
         uint32_t cl;
         const uint32_t cp = utf8_first(s + pos, &cl);   // every lane reads the same ≤ 4 bytes (broadcast)
@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
         const uint32_t shared_chars = common == label_bytes ? label_chars : warp_count_chars(s + pos, common, lane);
         matched += shared_chars;
         terminal = child;                       // a partial edge match still selects that child (:582-586)
+        ++visited;
         if (common != label_bytes) break;
         pos += common;
         cur = child;
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
     if (a.out_info) {
         smgx_decision_info di;
         di.matched = matched; di.input = input_chars; di.branch = (uint8_t)branch;
-        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        di.nodes = (uint8_t)min(visited, 255u); di.reserved[0] = di.reserved[1] = 0;
         a.out_info[r] = di;
     }
 }

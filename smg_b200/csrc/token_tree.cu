@@ -6,6 +6,9 @@
 #include <cstring>
 #include <queue>
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace smgx {
@@ -39,14 +42,12 @@ TokenTreeIndex::TokenTreeIndex(TenantTable* tenants, uint64_t* global_ts, EvictP
     mask_ = 1023;
 }
 TokenTreeIndex::~TokenTreeIndex() {
-    d_tokens_.release(); d_headers_.release(); d_table_.release(); d_stage_.release(); stage_.release();
+    d_tokens_.release(); d_table_.release(); d_stage_.release(); stage_.release();
     if (stage_done_) cudaEventDestroy(stage_done_);
 }
 
 uint64_t TokenTreeIndex::key_of(uint32_t parent, const uint32_t* page) const {
-    uint64_t sum = 0;
-    for (uint32_t i = 0; i < kPage; ++i) sum += ((uint64_t)page[i] + 1) * page_mult(i);
-    return page_finish(sum, parent);
+    return page_key_host(page, parent);
 }
 int64_t TokenTreeIndex::find_child(uint32_t parent, const uint32_t* page) const {
     const uint64_t h = key_of(parent, page);
@@ -70,6 +71,7 @@ void TokenTreeIndex::table_rebuild(uint32_t cap) {
         uint32_t idx = (uint32_t)(s.key >> 32) & mask_;
         while (table_[idx].key != 0) idx = (idx + 1) & mask_;
         table_[idx] = s;
+        nodes_[s.child].slot = idx;
         ++table_live_;
     }
     full_dirty_ = true;
@@ -90,18 +92,14 @@ void TokenTreeIndex::table_insert(uint32_t parent, const uint32_t* page, uint32_
     }
     if (tomb >= 0) { idx = (uint32_t)tomb; --table_tombs_; }
     table_[idx] = ChildSlot{h, parent, child};
+    nodes_[child].slot = idx;
     ++table_live_;
     mark_slot(idx);
-}
-void TokenTreeIndex::table_replace(uint32_t parent, const uint32_t* page, uint32_t child) {
-    int64_t s = find_child(parent, page);
-    if (s < 0) { table_insert(parent, page, child); return; }
-    table_[(size_t)s].child = child;
-    mark_slot((uint32_t)s);
 }
 void TokenTreeIndex::table_erase(uint32_t parent, const uint32_t* page) {
     int64_t s = find_child(parent, page);
     if (s < 0) return;
+    if (nodes_[table_[(size_t)s].child].slot == (uint32_t)s) nodes_[table_[(size_t)s].child].slot = kNoNode;
     table_[(size_t)s].child = kTombChild;
     --table_live_;
     ++table_tombs_;
@@ -222,7 +220,9 @@ void TokenTreeIndex::insert_tokens(const uint32_t* toks, size_t n, uint32_t tena
         mark_node(child);
         nodes_[mid].kids.push_back(child);
         for (auto& k : nodes_[cur].kids) if (k == child) { k = mid; break; }
-        table_replace(cur, rem, mid);                              // same page key, now → intermediate
+        table_[(size_t)slot].child = mid;                          // same page key, now → intermediate
+        nodes_[mid].slot = (uint32_t)slot;
+        mark_slot((uint32_t)slot);
         table_insert(mid, tokens_.data() + child_off + common, child);
         if (common >= rem_len) {                                   // input is a prefix of the edge (:475-523)
             touch(mid, tenant);
@@ -430,21 +430,27 @@ void TokenTreeIndex::entries(std::vector<std::pair<std::vector<uint32_t>, std::v
 // device mirror
 // =================================================================================================================
 namespace {
-__global__ void scatter16_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) dst[idx[t]] = src[t];
+__global__ void scatter32_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { const size_t d = (size_t)idx[t] * 2; dst[d] = src[(size_t)t * 2]; dst[d + 1] = src[(size_t)t * 2 + 1]; }
 }
 }  // namespace
+
+TreeSlot TokenTreeIndex::device_slot(uint32_t i) const {
+    const ChildSlot& c = table_[i];
+    TreeSlot t{c.key, c.parent, c.child, 0, 0, -1};
+    if (c.key != 0 && c.child < kTombChild) {
+        const Node& nd = nodes_[c.child];
+        t.label_off = nd.label_off;
+        t.label_len = nd.alive ? nd.label_len : 0;
+        t.any_tenant = nd.alive ? any_tenant(c.child) : -1;
+    }
+    return t;
+}
 
 TokenTreeView TokenTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
     if (!device_enabled) throw Error(SMGX_DEVICE_ERROR, "policy was created with device_id = -1 (host mirror only): no GPU path, no CPU fallback");
     if (tenants_version_seen != tenants_->version) { full_dirty_ = true; tenants_version_seen = tenants_->version; }
-    auto header_of = [&](uint32_t id) {
-        const Node& nd = nodes_[id];
-        TreeHeader h;
-        h.label_off = nd.label_off; h.label_len = nd.alive ? nd.label_len : 0; h.any_tenant = nd.alive ? any_tenant(id) : -1;
-        return h;
-    };
     // token arena: append-only
     if (tokens_.size() * 4 > d_tokens_.cap) {
         if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
@@ -457,43 +463,42 @@ TokenTreeView TokenTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
                                   (tokens_.size() - uploaded_tokens_) * 4, cudaMemcpyHostToDevice, stream));
         uploaded_tokens_ = tokens_.size();
     }
-    if (!full_dirty_ && dirty_nodes_.size() + dirty_slots_.size() > table_.size() / 8) full_dirty_ = true;
+    // a node whose header changed dirties the slot that points at it
+    for (uint32_t id : dirty_nodes_) if (id < nodes_.size() && nodes_[id].slot != kNoNode) dirty_slots_.push_back(nodes_[id].slot);
+    dirty_nodes_.clear();
+    if (!full_dirty_ && dirty_slots_.size() > table_.size() / 8) full_dirty_ = true;
     if (full_dirty_) {
         if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
         SMGX_CUDA(cudaDeviceSynchronize());
-        std::vector<TreeHeader> hdr(nodes_.size());
-        for (uint32_t i = 0; i < nodes_.size(); ++i) hdr[i] = header_of(i);
-        d_headers_.reserve(std::max<size_t>(nodes_.capacity(), 16) * sizeof(TreeHeader));
-        d_table_.reserve(table_.size() * sizeof(ChildSlot));
-        SMGX_CUDA(cudaMemcpyAsync(d_headers_.ptr, hdr.data(), hdr.size() * sizeof(TreeHeader), cudaMemcpyHostToDevice, stream));
-        SMGX_CUDA(cudaMemcpyAsync(d_table_.ptr, table_.data(), table_.size() * sizeof(ChildSlot), cudaMemcpyHostToDevice, stream));
-        SMGX_CUDA(cudaStreamSynchronize(stream));   // `hdr` is a temporary
+        std::vector<TreeSlot> dev(table_.size());
+        for (uint32_t i = 0; i < table_.size(); ++i) dev[i] = device_slot(i);
+        d_table_.reserve(table_.size() * sizeof(TreeSlot));
+        SMGX_CUDA(cudaMemcpyAsync(d_table_.ptr, dev.data(), dev.size() * sizeof(TreeSlot), cudaMemcpyHostToDevice, stream));
+        SMGX_CUDA(cudaStreamSynchronize(stream));   // `dev` is a temporary
         full_dirty_ = false;
-        dirty_nodes_.clear(); dirty_slots_.clear();
-    } else if (!dirty_nodes_.empty() || !dirty_slots_.empty()) {
+        dirty_slots_.clear();
+    } else if (!dirty_slots_.empty()) {
         if (!stage_done_) SMGX_CUDA(cudaEventCreateWithFlags(&stage_done_, cudaEventDisableTiming));
         if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
-        auto uniq = [](std::vector<uint32_t>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
-        uniq(dirty_nodes_); uniq(dirty_slots_);
-        const size_t nn = dirty_nodes_.size(), ns = dirty_slots_.size();
-        const size_t off_ni = 0, off_si = nn * 4, off_nr = ((off_si + ns * 4 + 15) / 16) * 16, off_sr = off_nr + nn * 16, total = off_sr + ns * 16;
+        std::sort(dirty_slots_.begin(), dirty_slots_.end());
+        dirty_slots_.erase(std::unique(dirty_slots_.begin(), dirty_slots_.end()), dirty_slots_.end());
+        const size_t ns = dirty_slots_.size();
+        const size_t off_r = ((ns * 4 + 15) / 16) * 16, total = off_r + ns * 32;
         stage_.reserve(total);
         d_stage_.reserve(total);
         char* st = stage_.as<char>();
-        memcpy(st + off_ni, dirty_nodes_.data(), nn * 4);
-        memcpy(st + off_si, dirty_slots_.data(), ns * 4);
-        for (size_t i = 0; i < nn; ++i) { TreeHeader h = header_of(dirty_nodes_[i]); memcpy(st + off_nr + i * 16, &h, 16); }
-        for (size_t i = 0; i < ns; ++i) memcpy(st + off_sr + i * 16, &table_[dirty_slots_[i]], 16);
+        memcpy(st, dirty_slots_.data(), ns * 4);
+        for (size_t i = 0; i < ns; ++i) { const TreeSlot t = device_slot(dirty_slots_[i]); memcpy(st + off_r + i * 32, &t, 32); }
         SMGX_CUDA(cudaMemcpyAsync(d_stage_.ptr, st, total, cudaMemcpyHostToDevice, stream));
         char* ds = d_stage_.as<char>();
-        if (nn) { scatter16_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, stream>>>(d_headers_.as<uint4>(), (const uint32_t*)(ds + off_ni), (const uint4*)(ds + off_nr), (uint32_t)nn); ++*launches; }
-        if (ns) { scatter16_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, stream>>>(d_table_.as<uint4>(), (const uint32_t*)(ds + off_si), (const uint4*)(ds + off_sr), (uint32_t)ns); ++*launches; }
+        scatter32_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, stream>>>(d_table_.as<uint4>(), (const uint32_t*)ds, (const uint4*)(ds + off_r), (uint32_t)ns);
+        ++*launches;
         SMGX_CUDA(cudaGetLastError());
         SMGX_CUDA(cudaEventRecord(stage_done_, stream));
         stage_pending_ = true;
-        dirty_nodes_.clear(); dirty_slots_.clear();
+        dirty_slots_.clear();
     }
-    return TokenTreeView{d_tokens_.as<uint32_t>(), d_headers_.as<TreeHeader>(), d_table_.as<ChildSlot>(), mask_};
+    return TokenTreeView{d_tokens_.as<uint32_t>(), d_table_.as<TreeSlot>(), mask_};
 }
 
 // =================================================================================================================
@@ -502,70 +507,107 @@ TokenTreeView TokenTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
 namespace {
 constexpr unsigned FULLM = 0xffffffffu;
 
-__global__ void __launch_bounds__(256) tree_select_kernel(TokenTreeView tv, FleetView f, const int32_t* __restrict__ slice_of_tenant,
-                                                          const uint8_t* __restrict__ flags, uint32_t n_tenants, TreeSelectArgs a) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= a.count) return;
-    const uint32_t r = a.first + w;
+constexpr uint32_t kWin = 512;   // request tokens staged per warp in shared memory (one BASELINE config-2 request)
+
+// One warp per request.  At the HBM roofline an SM sub-partition has ≈730 issue slots per 512-token request, so the walk is
+// written for few instructions as much as for few dependent reads:
+//   * the request is staged in shared memory with every load issued at once (off the hash → probe → label chain);
+//   * the page key is two 32-bit multilinear sums, one redux.sync each;
+//   * the child's header rides in the 32 B slot: a probe hit needs no second dependent read;
+//   * labels are compared 256 tokens per round as OR-of-XORs; the exact mismatch position is only computed when there is one.
+template <int TILE, class Tile>
+__device__ __forceinline__ void tree_walk_request(const Tile& tile, uint32_t* __restrict__ win, const TokenTreeView& tv, const FleetView& f,
+                                                  const int32_t* __restrict__ slice_of_tenant, const uint8_t* __restrict__ flags, uint32_t n_tenants,
+                                                  const TreeSelectArgs& a, uint32_t r) {
+    static_assert(TILE == 32, "the walk uses one warp per request");
+    const int rank = (int)tile.thread_rank();
     const uint32_t off = a.offsets[r], ntok = a.offsets[r + 1] - off;
     const uint32_t* tok = a.tokens + off;
     const uint32_t aligned = (ntok / kPage) * kPage;
-    const uint64_t mult = page_mult((uint32_t)lane & 15);
+    const uint32_t mult = rank < 16 ? page_mult1((uint32_t)rank) : page_mult2((uint32_t)rank - 16);
+    const uint32_t salt_add = rank < 16 ? 1u : 0u, salt_xor = rank < 16 ? 0u : 0x9E3779B9u;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(tok) & 15) == 0;
+    uint32_t wbase = 0, wend = 0;
+    auto load_window = [&](uint32_t start) {   // stage request tokens [start, start + kWin)
+        __syncwarp();
+        wbase = start;
+        wend = min(start + kWin, aligned);
+        const uint32_t n = wend - wbase;
+        if (vec_ok) for (uint32_t j = (uint32_t)rank * 4; j < n; j += 128) *reinterpret_cast<uint4*>(win + j) = *reinterpret_cast<const uint4*>(tok + wbase + j);
+        else for (uint32_t j = rank; j < n; j += 32) win[j] = tok[wbase + j];
+        __syncwarp();
+    };
+    load_window(0);
 
     uint32_t cur = 0, pos = 0, matched = 0, depth = 0;
     int32_t tenant = -1;
     while (aligned - pos >= kPage) {
-        // hash of (cur, next 16 tokens): lanes 0..15 hold one token each
-        uint64_t part = lane < 16 ? ((uint64_t)tok[pos + lane] + 1) * mult : 0;
-#pragma unroll
-        for (int d = 8; d; d >>= 1) {
-            uint32_t lo = __shfl_xor_sync(FULLM, (uint32_t)part, d), hi = __shfl_xor_sync(FULLM, (uint32_t)(part >> 32), d);
-            part += ((uint64_t)hi << 32) | lo;
-        }
-        const uint64_t sum = ((uint64_t)__shfl_sync(FULLM, (uint32_t)(part >> 32), 0) << 32) | __shfl_sync(FULLM, (uint32_t)part, 0);
-        const uint64_t key = page_finish(sum, cur);
+        if (pos < wbase || pos + kPage > wend) load_window(pos);
+        // key of (cur, next 16 tokens): lanes 0-15 feed the first sum, lanes 16-31 the second
+        const uint32_t t = win[pos - wbase + (rank & 15)];
+        const uint32_t term = ((t + salt_add) ^ salt_xor) * mult;
+        const uint32_t h1 = __reduce_add_sync(FULLM, rank < 16 ? term : 0u);
+        const uint32_t h2 = __reduce_add_sync(FULLM, rank < 16 ? 0u : term);
+        const uint64_t key = page_finish(h1, h2, cur);
         uint32_t idx = (uint32_t)(key >> 32) & tv.child_mask;
-        uint32_t child = kNoNode;
-        uint32_t m = 0;
-        TreeHeader hd{0, 0, -1};
+        uint32_t child = kNoNode, m = 0, label_len = 0;
+        int32_t any = -1;
         for (;;) {   // warp-uniform probe
-            const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(tv.children + idx));
-            const uint64_t skey = ((uint64_t)s4.y << 32) | s4.x;
+            const uint4* sp = reinterpret_cast<const uint4*>(tv.slots + idx);
+            const uint4 sa = __ldg(sp);
+            const uint64_t skey = ((uint64_t)sa.y << 32) | sa.x;
             if (skey == 0) break;
-            if (skey == key && s4.z == cur && s4.w < kTombChild) {
-                const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(tv.headers + s4.w));
-                hd.label_off = ((uint64_t)h4.y << 32) | h4.x; hd.label_len = h4.z; hd.any_tenant = (int32_t)h4.w;
-                // compare the edge label with the request, 32 tokens per step
-                const uint32_t L = min(hd.label_len, aligned - pos);
+            if (skey == key && sa.z == cur && sa.w < kTombChild) {
+                const uint4 sb = __ldg(sp + 1);   // same 32 B sector as sa
+                const uint64_t label_off = ((uint64_t)sb.y << 32) | sb.x;
+                label_len = sb.z; any = (int32_t)sb.w;
+                const uint32_t L = min(label_len, aligned - pos);
+                const uint32_t* lab = tv.tokens + label_off;   // always 16 B aligned: the arena only grows and splits by whole pages
                 uint32_t common = L;
-                for (uint32_t c = 0; c < L; c += 32) {
-                    const uint32_t j = c + lane;
-                    const bool ne = j < L && __ldg(tv.tokens + hd.label_off + j) != tok[pos + j];
-                    const unsigned mm = __ballot_sync(FULLM, ne);
-                    if (mm) { common = c + (uint32_t)__ffs((int)mm) - 1; break; }
+                for (uint32_t c = 0; c < L; c += 256) {
+                    if (pos + c < wbase || pos + c + min(256u, L - c) > wend) load_window(pos + c);
+                    const uint32_t j0 = c + (uint32_t)rank * 4, j1 = j0 + 128;
+                    uint32_t d0 = 0, d1 = 0;
+                    if (j0 < L) {
+                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(lab + j0)), y = *reinterpret_cast<const uint4*>(win + (pos + j0 - wbase));
+                        d0 = (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w);
+                    }
+                    if (j1 < L) {
+                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(lab + j1)), y = *reinterpret_cast<const uint4*>(win + (pos + j1 - wbase));
+                        d1 = (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w);
+                    }
+                    const unsigned m0 = __ballot_sync(FULLM, d0 != 0), m1 = __ballot_sync(FULLM, d1 != 0);
+                    if (m0 | m1) {   // first differing token: only now look inside the quad (re-read, it is in cache)
+                        const bool lo = m0 != 0;
+                        const int src = __ffs((int)(lo ? m0 : m1)) - 1;
+                        const uint32_t jq = c + (lo ? 0u : 128u) + (uint32_t)src * 4;
+                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(lab + jq)), y = *reinterpret_cast<const uint4*>(win + (pos + jq - wbase));
+                        common = jq + (x.x != y.x ? 0u : x.y != y.y ? 1u : x.z != y.z ? 2u : 3u);
+                        break;
+                    }
                 }
                 m = (common / kPage) * kPage;
-                if (m > 0) { child = s4.w; break; }   // m == 0: different page under the same 64-bit key — keep probing
+                if (m > 0) { child = sa.w; break; }   // m == 0: different page under the same 64-bit key — keep probing
+                if (pos < wbase || pos + kPage > wend) load_window(pos);
             }
             idx = (idx + 1) & tv.child_mask;
         }
         if (child == kNoNode) break;
-        if (hd.any_tenant < 0) break;                  // node without tenants ends the walk before being counted (:682-683)
+        if (any < 0) break;                            // node without tenants ends the walk before being counted (:682-683)
         matched += m;
-        tenant = hd.any_tenant;
-        if (lane == 0 && depth < kPathCap) {
+        tenant = any;
+        if (rank == 0 && depth < kPathCap && a.out_path) {
             a.out_path[(size_t)r * kPathCap + depth] = child;
-            a.out_path_tenant[(size_t)r * kPathCap + depth] = hd.any_tenant;
+            a.out_path_tenant[(size_t)r * kPathCap + depth] = any;
         }
         ++depth;
-        if (m < hd.label_len) break;                   // partial edge match (:691-696)
+        if (m < label_len) break;                      // partial edge match (:691-696)
         pos += m;
         cur = child;
     }
-    if (lane != 0) return;
-    a.out_path_len[r] = depth;
-    a.out_tenant[r] = tenant;
+    if (rank != 0) return;
+    if (a.out_path_len) a.out_path_len[r] = depth;
+    if (a.out_tenant) a.out_tenant[r] = tenant;
     int32_t out = -1;
     uint32_t branch = SMGX_BR_NO_HEALTHY;
     if (a.decide) {
@@ -587,16 +629,30 @@ __global__ void __launch_bounds__(256) tree_select_kernel(TokenTreeView tv, Flee
     if (a.out_info) {
         smgx_decision_info di;
         di.matched = matched; di.input = ntok; di.branch = (uint8_t)branch;
-        di.reserved[0] = di.reserved[1] = di.reserved[2] = 0;
+        di.nodes = (uint8_t)min(depth, 255u);
+        di.reserved[0] = di.reserved[1] = 0;
         a.out_info[r] = di;
     }
 }
+
+// one tile per request of one segment (the select path: first/count of one batch)
+template <int TILE>
+__global__ void __launch_bounds__(256, 5) tree_select_kernel(TokenTreeView tv, FleetView f, const int32_t* __restrict__ slice_of_tenant,
+                                                          const uint8_t* __restrict__ flags, uint32_t n_tenants, TreeSelectArgs a) {
+    namespace cg = cooperative_groups;
+    const auto tile = cg::tiled_partition<TILE>(cg::this_thread_block());
+    __shared__ __align__(16) uint32_t win_all[8][kWin];
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / TILE;
+    if (w >= a.count) return;
+    tree_walk_request<TILE>(tile, win_all[threadIdx.x >> 5], tv, f, slice_of_tenant, flags, n_tenants, a, a.first + w);
+}
+
 }  // namespace
 
 void launch_tree_select(const TokenTreeView& tv, const FleetView& fleet, const int32_t* d_slice_of_tenant, const uint8_t* d_flags,
                         uint32_t n_tenants, const TreeSelectArgs& a, cudaStream_t stream) {
     if (a.count == 0) return;
-    tree_select_kernel<<<(unsigned)(((uint64_t)a.count * 32 + 255) / 256), 256, 0, stream>>>(tv, fleet, d_slice_of_tenant, d_flags, n_tenants, a);
+    tree_select_kernel<32><<<(unsigned)(((uint64_t)a.count * 32 + 255) / 256), 256, 0, stream>>>(tv, fleet, d_slice_of_tenant, d_flags, n_tenants, a);
     SMGX_CUDA(cudaGetLastError());
 }
 

@@ -6,9 +6,10 @@
 // whole conflict-free segment of requests (match_prefix_with_counts :615-740) and the pick run on the GPU against the
 // mirror:
 //   tokens   [n] u32          append-only arena of edge labels; a split re-slices, it never copies
-//   headers  [nodes] 16 B     { u64 label_off; u32 label_len; i32 any_tenant }   any_tenant = get_any_tenant() (:268-284)
-//                             evaluated on the host whenever the node's tenants / last_tenant change (−1 = no tenants)
-//   children [cap] 16 B       open-addressed { u64 key; u32 parent; u32 child }, key = hash(parent, 16-token page key)
+//   slots    [cap] 32 B       open-addressed { u64 key; u32 parent; u32 child; u64 label_off; u32 label_len; i32 any_tenant },
+//                             key = hash(parent, 16-token page key); the child's header is embedded so a probe hit needs no
+//                             second dependent read.  any_tenant = get_any_tenant() (:268-284), evaluated on the host whenever
+//                             the node's tenants / last_tenant change (−1 = no tenants)
 // Device-side insertion is the §8(f) "next" item; DESIGN.md explains the segment scheme that keeps sequential semantics.
 #pragma once
 #include <cstdint>
@@ -26,26 +27,33 @@ constexpr uint32_t kNoNode = 0xFFFFFFFFu;
 constexpr uint32_t kTombChild = 0xFFFFFFFEu;
 constexpr uint32_t kPathCap = 8;          // matched nodes reported per request by the kernel (deeper paths are re-walked on the host)
 
-struct alignas(16) TreeHeader { uint64_t label_off; uint32_t label_len; int32_t any_tenant; };
-struct alignas(16) ChildSlot { uint64_t key; uint32_t parent; uint32_t child; };  // key 0 = empty
+struct alignas(16) ChildSlot { uint64_t key; uint32_t parent; uint32_t child; };  // host table entry; key 0 = empty
+// device table entry: the child's header rides in the slot, so one 32 B read resolves a probe AND yields the label location
+struct alignas(16) TreeSlot { uint64_t key; uint32_t parent; uint32_t child; uint64_t label_off; uint32_t label_len; int32_t any_tenant; };
+static_assert(sizeof(TreeSlot) == 32, "device slot layout");
 
 struct TokenTreeView {
     const uint32_t* tokens;
-    const TreeHeader* headers;
-    const ChildSlot* children;
+    const TreeSlot* slots;
     uint32_t child_mask;
 };
 
-// hash of (parent node, first 16 tokens of the edge) — identical on host and device (device sums the 16 products by shuffles)
-__host__ __device__ inline uint64_t page_mult(uint32_t i) {
-    uint64_t x = (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ULL;
-    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32;
-    return x | 1ULL;
+// key of (parent node, first 16 tokens of the edge) — identical on host and device.  Two multilinear 32-bit hashes of the page
+// (odd per-position multipliers) are summed across the warp with one redux.sync each, then mixed with the parent id.  A key
+// collision is harmless: both sides still compare the page itself.
+__host__ __device__ inline uint32_t page_mult1(uint32_t i) { uint32_t x = (i + 1) * 0x9E3779B9u; x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13; return x | 1u; }
+__host__ __device__ inline uint32_t page_mult2(uint32_t i) { uint32_t x = (i + 17) * 0xC2B2AE35u; x ^= x >> 16; x *= 0x27D4EB2Fu; x ^= x >> 14; return x | 1u; }
+__host__ __device__ inline uint64_t page_finish(uint32_t h1, uint32_t h2, uint32_t parent) {
+    uint32_t a = h1 ^ (parent * 0x85EBCA6Bu + 0xC2B2AE35u);
+    a ^= a >> 16; a *= 0x7FEB352Du; a ^= a >> 15; a *= 0x846CA68Bu; a ^= a >> 16;
+    uint32_t b = h2 + parent * 0x27D4EB2Fu;
+    b ^= b >> 15; b *= 0x2C1B3C6Du; b ^= b >> 12; b *= 0x297A2D39u; b ^= b >> 15;
+    return (((uint64_t)a << 32) | b) | 1ULL;   // never 0 (0 marks an empty slot)
 }
-__host__ __device__ inline uint64_t page_finish(uint64_t sum, uint32_t parent) {
-    uint64_t x = sum ^ (((uint64_t)parent + 1) * 0xD6E8FEB86659FD93ULL);
-    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDULL; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ULL; x ^= x >> 33;
-    return x | 1ULL;   // never 0 (0 marks an empty slot)
+inline uint64_t page_key_host(const uint32_t* page, uint32_t parent) {
+    uint32_t h1 = 0, h2 = 0;
+    for (uint32_t i = 0; i < kPage; ++i) { h1 += (page[i] + 1u) * page_mult1(i); h2 += (page[i] ^ 0x9E3779B9u) * page_mult2(i); }
+    return page_finish(h1, h2, parent);
 }
 
 enum EvictPolicy : int { EVP_LRU = 0, EVP_LFU = 1, EVP_FIFO = 2, EVP_MRU = 3, EVP_FILO = 4, EVP_PRIORITY = 5 };
@@ -99,12 +107,12 @@ private:
         int32_t priority = 0;
         std::vector<uint32_t> kids;                            // child node ids (for eviction / iteration)
         bool alive = true;
+        uint32_t slot = kNoNode;                               // table_ index of the entry that points at this node
     };
     uint64_t next_ts() { return (*global_ts_)++; }
     uint64_t key_of(uint32_t parent, const uint32_t* page) const;
     int64_t find_child(uint32_t parent, const uint32_t* page) const;
     void table_insert(uint32_t parent, const uint32_t* page, uint32_t child);
-    void table_replace(uint32_t parent, const uint32_t* page, uint32_t child);
     void table_erase(uint32_t parent, const uint32_t* page);
     void table_rebuild(uint32_t cap);
     uint32_t new_node(uint64_t off, uint32_t len, uint32_t parent, bool draw_ts);
@@ -128,7 +136,8 @@ private:
     uint64_t table_live_ = 0, table_tombs_ = 0;
     std::unordered_map<uint32_t, size_t> tenant_tokens_;   // tenant_token_count (token_tree.rs:328)
 
-    DevBuf d_tokens_, d_headers_, d_table_, d_stage_;
+    DevBuf d_tokens_, d_table_, d_stage_;
+    TreeSlot device_slot(uint32_t i) const;
     PinBuf stage_;
     cudaEvent_t stage_done_ = nullptr;
     bool stage_pending_ = false;

@@ -91,6 +91,96 @@ def tree_mode():
             "kernel_launches": pol.kernel_launches()}
 
 
+def treewalk_mode():
+    """K2a by itself at BASELINE config-2 scale: read-only walk + pick of HBM-resident batches against a ≈1.06 M-node tree
+    (TRUNKS trunks of 8 pages × 32 branches of 8 pages × 32 leaves of 16 pages; labels ≈1.07 GB at TRUNKS=1000)."""
+    from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, _lib, synth
+    W, B, T = 64, 4096, 512
+    n_trunks = int(os.environ.get("TRUNKS", "1000"))
+    ring, steps, per_call = int(os.environ.get("RING", "32")), int(os.environ.get("STEPS", "20")), int(os.environ.get("PER_CALL", "8"))
+    rng = np.random.default_rng(42)
+    urls = synth.worker_urls(W)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), max_batch=B, max_tokens_per_request=T)
+    ws = [BasicWorker(u) for u in urls]
+    for w, l in zip(ws, synth.poisson_loads(W, 8, 42)):
+        w.set_load(int(l))
+    pol.init_workers(ws)
+    model = pol._push_fleet(ws)
+    h = pol._h
+    t0 = time.time()
+    sample = []
+    url_c = [u.encode() for u in urls]
+    off = (np.arange(1025, dtype=np.uint64) * T)
+    for tr in range(n_trunks):
+        trunk = rng.integers(0, 50000, size=128, dtype=np.uint32)
+        paths = np.empty((32, 32, T), np.uint32)
+        paths[:, :, :128] = trunk
+        paths[:, :, 128:256] = rng.integers(0, 50000, size=(32, 1, 128), dtype=np.uint32)
+        paths[:, :, 256:] = rng.integers(0, 50000, size=(32, 32, 256), dtype=np.uint32)
+        flat = np.ascontiguousarray(paths.reshape(-1))
+        tens = (C.c_char_p * 1024)(*[url_c[(tr * 1024 + i) % W] for i in range(1024)])
+        h.call("smgx_tree_insert_tokens_batch", model, flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), 1024, tens)
+        for i in rng.integers(0, 1024, size=max(1, 40000 // n_trunks)):
+            sample.append(flat[i * T:(i + 1) * T].copy())
+    t_build = time.time() - t0
+    sample = np.stack(sample)
+
+    def batch(seed):
+        r = np.random.default_rng(seed)
+        q = sample[r.integers(0, len(sample), size=B)].copy()
+        u = r.random(B)
+        for i in np.nonzero((u >= 0.8) & (u < 0.9))[0]:
+            k = 16 * int(r.integers(1, 32))
+            q[i, k:] = r.integers(0, 50000, size=T - k, dtype=np.uint32)
+        nov = np.nonzero(u >= 0.9)[0]
+        q[nov] = r.integers(0, 50000, size=(len(nov), T), dtype=np.uint32)
+        return np.ascontiguousarray(q.reshape(-1))
+
+    L = _lib.load()
+    err = _lib.new_err()
+    offs = (np.arange(B + 1, dtype=np.uint64) * T).astype(np.uint32)
+    d_off = L.smgx_device_alloc(h.p, offs.nbytes, C.byref(err))
+    h.call("smgx_memcpy_h2d", d_off, offs.ctypes.data_as(C.c_void_p), offs.nbytes)
+    d_tok, d_out, d_info, infos = [], [], [], None
+    for j in range(ring):
+        q = batch(1000 + j)
+        p = L.smgx_device_alloc(h.p, q.nbytes, C.byref(err)); h.call("smgx_memcpy_h2d", p, q.ctypes.data_as(C.c_void_p), q.nbytes)
+        d_tok.append(p)
+        d_out.append(L.smgx_device_alloc(h.p, B * 4, C.byref(err)))
+        d_info.append(L.smgx_device_alloc(h.p, B * 12, C.byref(err)))
+    arr = lambda xs: (C.c_void_p * len(xs))(*xs)
+    ns = (C.c_uint32 * per_call)(*([B] * per_call))
+
+    def call(j0, want_info):
+        js = [(j0 + k) % ring for k in range(per_call)]
+        h.call("smgx_tree_walk_many_device", model, per_call, arr([d_tok[j] for j in js]), arr([d_off] * per_call), ns,
+               arr([d_out[j] for j in js]), arr([d_info[j] for j in js]) if want_info else None)
+
+    for w in range(3):
+        call(w * per_call, True)
+    h.call("smgx_synchronize")
+    info = np.zeros(B, dtype=[("matched", "<u4"), ("input", "<u4"), ("branch", "u1"), ("nodes", "u1"), ("r", "u1", 2)])
+    h.call("smgx_memcpy_d2h", info.ctypes.data_as(C.c_void_p), d_info[0], B * 12)
+    # algorithmic bytes / decision (SURVEY §8d, K2a): 4·T request tokens + 4·M label tokens compared + 96·N visited nodes
+    alg = float(np.mean(4.0 * info["input"] + 4.0 * info["matched"] + 96.0 * info["nodes"]))
+    h.call("smgx_timer_start_all")
+    for s in range(steps):
+        call(s * per_call, False)
+    ms = C.c_float()
+    h.call("smgx_timer_stop_all_ms", C.byref(ms))
+    n = steps * per_call * B
+    dps = n / (ms.value * 1e-3)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6486.8))
+    return {"mode": "K2a token-tree walk + pick kernel only (read-only, HBM-resident requests; tree_select_kernel)",
+            "workers": W, "batch": B, "tokens_per_request": T, "tree_nodes": n_trunks * (1 + 32 + 1024), "label_bytes": n_trunks * 266368 * 4,
+            "tree_build_s": round(t_build, 1), "ring_batches": ring, "batches_per_call": per_call,
+            "decisions_per_s": dps, "ms_per_batch": ms.value / (steps * per_call),
+            "mix": {"matched_mean": float(info["matched"].mean()), "nodes_mean": float(info["nodes"].mean()),
+                    "branches": {str(k): int(v) for k, v in zip(*np.unique(info["branch"], return_counts=True))}},
+            "roofline": {"bound": "hbm", "alg_bytes_per_decision": alg, "achieved": alg * dps / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * dps / 1e9 / peak}}
+
+
 def text_mode():
     """HTTP text (string-tree) mode: chat-style routing texts with shared system prompts, ~2 KB each."""
     import random
@@ -207,6 +297,6 @@ def sharded_mode():
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "tree"
-    r = {"tree": tree_mode, "text": text_mode, "sharded": sharded_mode}[mode]()
+    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "sharded": sharded_mode}[mode]()
     if r is not None:
         print(json.dumps(r), flush=True)
