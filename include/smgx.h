@@ -204,6 +204,18 @@ smgx_status smgx_stree_entries(smgx_policy* p, const char* model_key, char** out
 smgx_status smgx_stree_clear(smgx_policy* p, const char* model_key, char** err);
 smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err);
 
+/* ---- mesh path hashes and the hash_index side effect (crates/mesh/src/hash.rs:22-52; cache_aware.rs:95-101) ------------- */
+/* hash_token_path / hash_node_path for a batch on the GPU: BLAKE3 of the little-endian u32 ids (or the UTF-8 bytes) of request i,
+ * low 8 digest bytes little-endian, 0 remapped to 1.  The tree-mode select calls compute these themselves and record
+ * hash(full request) → matched prefix, exactly where the reference does (:397-401, :420-424, :881-886, :950-956);
+ * smgx_evict_cache clears a model's map when it outgrows max_size (:335-351). */
+smgx_status smgx_hash_token_paths(smgx_policy* p, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err);
+smgx_status smgx_hash_node_paths(smgx_policy* p, const uint8_t* text, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err);
+/* text_kind 0: token_tree map (values are u32 ids), 1: string_tree map (values are UTF-8 bytes). */
+smgx_status smgx_hash_index_size(smgx_policy* p, const char* model_key, int text_kind, uint64_t* out, char** err);
+smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_kind, uint64_t path_hash, void* out, uint32_t cap_bytes,
+                                uint32_t* out_bytes, int* out_found, char** err);
+
 /* ---- HTTP text routing: select_worker with info.request_text = Some(text), info.tokens = None ------------------ */
 /* select_worker_with_text (cache_aware.rs:907-974) and the imbalanced path's string-tree update (:403-425) for a batch:
  * request i = text[offsets[i] .. offsets[i+1]) (valid UTF-8).  match_rate = matched chars / input chars (f32, strict >).

@@ -15,8 +15,9 @@
  * Pinned by the reference's unit tests ported in tests/test_oracle_cache_aware.py (cache_aware.rs:999-2015,
  * mod.rs:192-262).
  *
- * Not restated: the mesh hash_index side effect (cache_aware.rs:397-401, 881-886, 950-956; blake3) — it never
- * feeds back into the pick. The "no tree for model → rand" branch (:896-903, :965-973) returns healthy[0] and
+ * The mesh hash_index side effect (cache_aware.rs:397-401, 420-424, 881-886, 950-956) — blake3 path hash of the FULL request
+ * → copy of the matched prefix — is restated too (hash_index_tokens / hash_index_text); it never feeds back into the pick.
+ * The "no tree for model → rand" branch (:896-903, :965-973) returns healthy[0] and
  * reports the whole healthy set as valid.
  *
  * "Snapshot batches" (begin_snapshot_batch / end_snapshot_batch): select_worker takes &self and is called from many
@@ -35,6 +36,7 @@
 #include <string>
 #include <vector>
 
+#include "blake3_ref.h"
 #include "positional_indexer.h"
 #include "string_tree.h"
 #include "token_tree.h"
@@ -95,6 +97,8 @@ public:
     void evict_cache(size_t max_size) {  // :311-331
         for (auto& kv : string_trees_) kv.second->evict_tenant_by_size(max_size);
         for (auto& kv : token_trees_) kv.second->evict_tenant_by_size(max_size);
+        for (auto& kv : hash_index_text_) if (kv.second.size() > max_size) kv.second.clear();      // :335-351
+        for (auto& kv : hash_index_tokens_) if (kv.second.size() > max_size) kv.second.clear();
     }
 
     // KvEventMonitor surface the policy reads (worker/kv_event_monitor.rs get_indexer / block_size)
@@ -148,6 +152,9 @@ public:
         deferred_.clear();
     }
 
+    const std::map<uint64_t, std::vector<uint32_t>>& hash_index_tokens(const std::string& model) { return hash_index_tokens_[model]; }
+    const std::map<uint64_t, std::string>& hash_index_text(const std::string& model) { return hash_index_text_[model]; }
+
     bool has_event_indexer(const std::string& model) const {  // :723-729
         if (!monitor_) return false;
         auto it = indexers_.find(model);
@@ -200,6 +207,7 @@ private:
                 d.matched = m.matched; d.input = m.input;
                 std::string url = ws[idx].url;
                 run_or_defer([t, tokens, n, url] { t->insert_tokens(tokens, n, url); });
+                hash_index_tokens_[model][hash_token_path(tokens, n)] = std::vector<uint32_t>(tokens, tokens + m.matched);   // :397-401
             }
         } else if (text) {
             if (StringTree* t = string_tree(model)) {
@@ -207,6 +215,7 @@ private:
                 d.matched = m.matched; d.input = m.input;
                 std::string url = ws[idx].url, tx = *text;
                 run_or_defer([t, tx, url] { t->insert_text(tx, url); });
+                hash_index_text_[model][hash_node_path(tx)] = utf8_encode(utf8_decode(tx).substr(0, m.matched));               // :420-424
             }
         }
         ws[idx].processed++;
@@ -273,6 +282,7 @@ private:
         TokenMatch m = match_tokens(t, tokens, n);
         return tree_decide<TokenTree>(ws, m, healthy, [&](const std::string& url) {
             run_or_defer([t, tokens, n, url] { t->insert_tokens(tokens, n, url); });   // `tokens` outlives the batch call
+            hash_index_tokens_[model][hash_token_path(tokens, n)] = std::vector<uint32_t>(tokens, tokens + m.matched);          // :881-886
         });
     }
     // cache_aware.rs:907-974
@@ -284,6 +294,7 @@ private:
         return tree_decide<StringTree>(ws, m, healthy, [&](const std::string& url) {
             std::string tx = text;
             run_or_defer([t, tx, url] { t->insert_text(tx, url); });
+            hash_index_text_[model][hash_node_path(tx)] = utf8_encode(utf8_decode(tx).substr(0, m.matched));                    // :950-956
         });
     }
     // match + its side effects: immediate, or (snapshot batch) read-only now and side effects queued
@@ -311,6 +322,8 @@ private:
     }
 
     CacheAwareConfig cfg_;
+    std::map<std::string, std::map<uint64_t, std::vector<uint32_t>>> hash_index_tokens_;   // hash_index[model].token_tree (cache_aware.rs:95-101)
+    std::map<std::string, std::map<uint64_t, std::string>> hash_index_text_;              // hash_index[model].string_tree
     bool deferring_ = false;
     std::vector<std::function<void()>> deferred_;
     std::map<std::string, std::unique_ptr<StringTree>> string_trees_;

@@ -266,6 +266,23 @@ double orc_policy_select_batch_text(void* h, const char* text, const uint64_t* o
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- blake3 path hashes + hash_index ----
+void orc_blake3(const uint8_t* data, size_t n, uint8_t* digest32) { b3::hash(data, n, digest32); }
+uint64_t orc_hash_path_bytes(const uint8_t* data, size_t n) { return hash_path_bytes(data, n); }
+uint64_t orc_hash_token_path(const uint32_t* toks, size_t n) { return hash_token_path(toks, n); }
+// "hash=len:elem,elem,...\n" (tokens) or "hash=<utf8 prefix>\x1e" (text) for every entry, ascending by hash
+size_t orc_policy_hash_index(void* h, const char* model, int text_kind, char* out, size_t cap) {
+    auto* b = (PolicyBox*)h;
+    std::string s;
+    if (text_kind) for (auto& kv : b->pol.hash_index_text(model)) { s += std::to_string(kv.first) + "=" + kv.second; s.push_back('\x1e'); }
+    else for (auto& kv : b->pol.hash_index_tokens(model)) {
+        s += std::to_string(kv.first) + "=";
+        for (size_t i = 0; i < kv.second.size(); ++i) { if (i) s.push_back(','); s += std::to_string(kv.second[i]); }
+        s.push_back('\x1e');
+    }
+    return copy_str(s, out, cap);
+}
+
 // Read-only event-mode scoring with `threads` persistent host threads (the reference's concurrent-read design:
 // select_worker takes &self, the index is only read, requests are spread over a tokio worker pool).  `steps` batches
 // are routed back to back: batch s = tokens/offsets of (s % n_batches); threads are spawned ONCE, every thread owns a

@@ -84,6 +84,10 @@ def lib():
         sig("orc_policy_select_batch_tokens", C.c_double, vp, vp, vp, sz, vp, vp, vp)
         sig("orc_policy_select_batch_tokens_snapshot", C.c_double, vp, vp, vp, sz, vp, vp, vp)
         sig("orc_policy_select_batch_text", C.c_double, vp, vp, vp, sz, C.c_int, vp, vp, vp, vp)
+        sig("orc_blake3", None, vp, sz, vp)
+        sig("orc_hash_path_bytes", C.c_uint64, vp, sz)
+        sig("orc_hash_token_path", C.c_uint64, vp, sz)
+        sig("orc_policy_hash_index", sz, vp, cp, C.c_int, vp, sz)
         sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int)
         _lib = L
     return _lib
@@ -108,6 +112,22 @@ def reset_globals():
 def xxh3_64(data: bytes, seed: int = 0) -> int:
     buf = C.create_string_buffer(data, len(data))
     return lib().orc_xxh3_64(C.cast(buf, C.c_void_p), len(data), seed)
+
+
+def blake3_digest(data: bytes) -> bytes:
+    out = C.create_string_buffer(32)
+    lib().orc_blake3(C.c_char_p(data), len(data), C.cast(out, C.c_void_p))
+    return out.raw
+
+
+def hash_node_path(text: str) -> int:       # crates/mesh/src/hash.rs:22-30
+    b = text.encode("utf-8")
+    return lib().orc_hash_path_bytes(C.c_char_p(b), len(b))
+
+
+def hash_token_path(tokens) -> int:         # crates/mesh/src/hash.rs:40-52
+    t = _u32(tokens)
+    return lib().orc_hash_token_path(_ptr(t), t.size)
 
 
 def compute_content_hash(tokens) -> int:
@@ -438,6 +458,19 @@ class CacheAwarePolicy:
         idx = np.zeros(n, np.int32)
         secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads)
         return idx, secs
+
+    def hash_index(self, kind="tokens", model="unknown"):
+        """hash_index[model].token_tree / .string_tree (cache_aware.rs:95-101): {path hash: matched prefix}."""
+        tk = 1 if kind == "text" else 0
+        n = lib().orc_policy_hash_index(self.h, model.encode(), tk, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().orc_policy_hash_index(self.h, model.encode(), tk, C.cast(buf, C.c_void_p), n + 1)
+        out = {}
+        for rec in buf.raw[:n].decode("utf-8").split("\x1e"):
+            if rec:
+                k, v = rec.split("=", 1)
+                out[int(k)] = v if tk else [int(x) for x in v.split(",") if x]
+        return out
 
     def select_batch_text(self, texts, snapshot=False):
         """texts: list of str.  Returns (idx, branch, matched_chars, input_chars, secs)."""

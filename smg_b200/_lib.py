@@ -96,6 +96,10 @@ def load():
     sig("smgx_tree_tenant_size", st, vp, cp, cp, P(u64), pp)
     sig("smgx_tree_clear", st, vp, cp, pp)
     sig("smgx_tree_entries", st, vp, cp, P(C.c_void_p), pp)
+    sig("smgx_hash_token_paths", st, vp, vp, vp, u32, vp, pp)
+    sig("smgx_hash_node_paths", st, vp, vp, vp, u32, vp, pp)
+    sig("smgx_hash_index_size", st, vp, cp, C.c_int, P(u64), pp)
+    sig("smgx_hash_index_get", st, vp, cp, C.c_int, u64, vp, u32, P(u32), P(C.c_int), pp)
     sig("smgx_set_tree_batch_mode", st, vp, u32, pp)
     sig("smgx_stree_insert_text", st, vp, cp, vp, u32, cp, pp)
     sig("smgx_stree_match", st, vp, cp, vp, u32, P(u32), P(u32), vp, u32, pp)

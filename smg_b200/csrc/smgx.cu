@@ -19,6 +19,7 @@
 #include "tokenizer.h"
 #include "token_tree.h"
 #include "string_tree.h"
+#include "blake3.h"
 #include <unordered_map>
 #include <unordered_set>
 
@@ -37,6 +38,9 @@ struct ModelState {
     std::unique_ptr<Tokenizer> tokenizer;   // TokenizerRegistry entry for this model
     std::unique_ptr<TokenTreeIndex> token_tree;   // token_trees[model] (cache_aware.rs:79)
     std::unique_ptr<StringTreeIndex> string_tree; // string_trees[model] (cache_aware.rs:78)
+    // hash_index[model] (cache_aware.rs:95-101): blake3 path hash of the full request → copy of the matched prefix
+    std::unordered_map<uint64_t, std::vector<uint32_t>> hash_index_tokens;
+    std::unordered_map<uint64_t, std::string> hash_index_text;
     DevBuf d_slice_of_tenant;
     uint64_t seen_tenants_version = ~0ULL;
     bool has_learned_bs = false;
@@ -51,7 +55,7 @@ struct ModelState {
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
-    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill;
+    DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill, d_chunk_start, d_cv, d_hashes;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
     bool has_done = false;
@@ -100,7 +104,7 @@ public:
             for (auto& l : lanes) {
                 l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
-                l.d_path_tenant.release(); l.d_fill.release();
+                l.d_path_tenant.release(); l.d_fill.release(); l.d_chunk_start.release(); l.d_cv.release(); l.d_hashes.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
                 l.tok_scratch.pieces.release(); l.tok_scratch.n_pieces.release();
                 if (l.done) cudaEventDestroy(l.done);
@@ -289,6 +293,8 @@ public:
         std::vector<smgx_decision_info> info(n);
         std::vector<uint32_t> path((size_t)n * kPathCap), path_len(n);
         std::vector<int32_t> path_ten((size_t)n * kPathCap), ten(n);
+        std::vector<uint64_t> path_hash;   // hash_token_path of every request, for the hash_index side effect (:881-886, :397-401)
+        if (decide) enqueue_path_hashes(lane, reinterpret_cast<const uint8_t*>(lane.d_tokens.as<uint32_t>() - base), lane.d_offsets.as<uint32_t>(), offsets, n, 4, path_hash);
         std::unordered_set<uint64_t> seen;
         const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
         uint32_t seg = 0;
@@ -343,6 +349,7 @@ public:
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
                     const size_t idx = (size_t)out_idx[r];
                     tree.insert_tokens(tk, len, tenants.intern(m.urls[idx]));   // :868 / :396
+                    m.hash_index_tokens[path_hash[r]].assign(tk, tk + info[r].matched);
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -350,6 +357,30 @@ public:
         }
         if (out_info) memcpy(out_info, info.data(), (size_t)n * sizeof(smgx_decision_info));
         if (out_tenant) memcpy(out_tenant, ten.data(), (size_t)n * 4);
+    }
+
+    // smg_mesh::hash_token_path / hash_node_path (crates/mesh/src/hash.rs:22-52) of every request of a batch that is already
+    // on the device: enqueues the blake3 kernels and the copy back on `lane`; `out` is valid after the next stream sync.
+    void enqueue_path_hashes(Lane& lane, const uint8_t* d_data, const uint32_t* d_offsets, const uint32_t* offsets, uint32_t n, uint32_t elem_bytes,
+                             std::vector<uint64_t>& out) {
+        out.assign(n, 0);
+        if (n == 0) return;
+        std::vector<uint32_t> chunk_start(n + 1);
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            chunk_start[i] = (uint32_t)total;
+            const uint64_t bytes = (uint64_t)(offsets[i + 1] - offsets[i]) * elem_bytes;
+            total += std::max<uint64_t>(1, (bytes + 1023) / 1024);
+        }
+        SMGX_REQUIRE(total < (1ull << 32), "too many blake3 chunks in one batch");
+        chunk_start[n] = (uint32_t)total;
+        lane.d_chunk_start.reserve(((size_t)n + 1) * 4);
+        lane.d_cv.reserve((size_t)total * 32);
+        lane.d_hashes.reserve((size_t)n * 8);
+        SMGX_CUDA(cudaMemcpyAsync(lane.d_chunk_start.ptr, chunk_start.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+        launch_blake3_paths(d_data, d_offsets, elem_bytes, lane.d_chunk_start.as<uint32_t>(), n, (uint32_t)total, lane.d_cv.as<uint32_t>(),
+                            lane.d_hashes.as<uint64_t>(), lane.stream, &launches);
+        SMGX_CUDA(cudaMemcpyAsync(out.data(), lane.d_hashes.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, lane.stream));
     }
 
     StringTreeIndex& stree_of(ModelState& m) {
@@ -383,6 +414,8 @@ public:
         std::vector<uint32_t> node(n);
         std::vector<int32_t> ten(n);
         std::vector<uint8_t> fill(n);
+        std::vector<uint64_t> path_hash;   // hash_node_path of every request (:950-956, :420-424)
+        if (decide) enqueue_path_hashes(lane, lane.d_text.as<uint8_t>() - base, lane.d_offsets.as<uint32_t>(), offsets, n, 1, path_hash);
         std::unordered_set<uint64_t> seen;
         const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
         uint32_t seg = 0;
@@ -435,7 +468,12 @@ public:
                 const uint8_t br = info[r].branch;
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
                     const size_t idx = (size_t)out_idx[r];
-                    tree.insert_text(text + offsets[r], offsets[r + 1] - offsets[r], tenants.intern(m.urls[idx]));   // :938 / :421
+                    const uint8_t* tx = text + offsets[r];
+                    const uint32_t nb = offsets[r + 1] - offsets[r];
+                    tree.insert_text(tx, nb, tenants.intern(m.urls[idx]));   // :938 / :421
+                    uint32_t pb = 0, chars = 0;   // text.chars().take(matched_char_count): byte length of the matched prefix
+                    while (pb < nb && chars < info[r].matched) { ++pb; while (pb < nb && (tx[pb] & 0xC0) == 0x80) ++pb; ++chars; }
+                    m.hash_index_text[path_hash[r]].assign((const char*)tx, pb);
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -955,6 +993,10 @@ smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err) {   
         std::lock_guard<std::mutex> g(p->impl.mu);
         for (auto& kv : p->impl.models) if (kv.second->string_tree) kv.second->string_tree->evict_tenant_by_size((size_t)max_size);   // :317-321
         for (auto& kv : p->impl.models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);     // :322-326
+        for (auto& kv : p->impl.models) {   // per model, per tree kind (:335-351)
+            if (kv.second->hash_index_text.size() > max_size) kv.second->hash_index_text.clear();
+            if (kv.second->hash_index_tokens.size() > max_size) kv.second->hash_index_tokens.clear();
+        }
         return SMGX_SUCCESS;
     });
 }
@@ -1240,6 +1282,62 @@ smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_
         std::lock_guard<std::mutex> g(p->impl.mu);
         ModelState& m = p->impl.model(model_key, false);
         *out = m.string_tree ? m.string_tree->node_count() : 0;
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- mesh path hashes + hash_index (crates/mesh/src/hash.rs:22-52; cache_aware.rs:95-101) ----
+static smgx_status hash_paths(smgx_policy* p, const uint8_t* data, const uint32_t* offsets, uint32_t n, uint32_t elem_bytes, uint64_t* out, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (offsets && out), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        if (n == 0) return SMGX_SUCCESS;
+        for (uint32_t i = 0; i < n; ++i) SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+        Lane& lane = P.lanes[0];
+        const uint64_t base = (uint64_t)offsets[0] * elem_bytes, total = (uint64_t)(offsets[n] - offsets[0]) * elem_bytes;
+        SMGX_REQUIRE(total == 0 || data, "Invalid arguments: null pointer");
+        lane.d_text.reserve(std::max<uint64_t>(total, 1) + 16);
+        lane.d_offsets.reserve(((size_t)n + 1) * 4);
+        if (total) SMGX_CUDA(cudaMemcpyAsync(lane.d_text.ptr, data + base, total, cudaMemcpyHostToDevice, lane.stream));
+        SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+        std::vector<uint64_t> h;
+        P.enqueue_path_hashes(lane, lane.d_text.as<uint8_t>() - base, lane.d_offsets.as<uint32_t>(), offsets, n, elem_bytes, h);
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+        memcpy(out, h.data(), (size_t)n * 8);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_hash_token_paths(smgx_policy* p, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err) {
+    return hash_paths(p, reinterpret_cast<const uint8_t*>(tokens), offsets, n, 4, out_hashes, err);
+}
+smgx_status smgx_hash_node_paths(smgx_policy* p, const uint8_t* text, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err) {
+    return hash_paths(p, text, offsets, n, 1, out_hashes, err);
+}
+smgx_status smgx_hash_index_size(smgx_policy* p, const char* model_key, int text_kind, uint64_t* out, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        *out = text_kind ? m.hash_index_text.size() : m.hash_index_tokens.size();
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_kind, uint64_t path_hash, void* out, uint32_t cap_bytes,
+                                uint32_t* out_bytes, int* out_found, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_bytes); NONNULL(out_found);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        *out_found = 0; *out_bytes = 0;
+        const void* src = nullptr;
+        size_t nb = 0;
+        if (text_kind) { auto it = m.hash_index_text.find(path_hash); if (it != m.hash_index_text.end()) { src = it->second.data(); nb = it->second.size(); *out_found = 1; } }
+        else { auto it = m.hash_index_tokens.find(path_hash); if (it != m.hash_index_tokens.end()) { src = it->second.data(); nb = it->second.size() * 4; *out_found = 1; } }
+        *out_bytes = (uint32_t)nb;
+        if (*out_found && out && nb <= cap_bytes && nb) memcpy(out, src, nb);
         return SMGX_SUCCESS;
     });
 }

@@ -498,6 +498,39 @@ class CacheAwarePolicy:
         self._h.call("smgx_select_batch_request_text", model, _p(data), _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
         return out[:n], (info if info is None else [info[i] for i in range(n)])
 
+    # -- mesh path hashes / hash_index (crates/mesh/src/hash.rs; cache_aware.rs:95-101) ---------------------------------
+    def hash_token_paths(self, requests):
+        lens = [len(r) for r in requests]
+        offsets = np.zeros(len(requests) + 1, dtype=np.uint32)
+        np.cumsum(lens, out=offsets[1:])
+        tokens = _u32(np.concatenate([np.asarray(r, dtype=np.uint32) for r in requests]) if sum(lens) else [])
+        out = np.zeros(max(len(requests), 1), np.uint64)
+        self._h.call("smgx_hash_token_paths", _p(tokens), _p(offsets), len(requests), _p(out))
+        return out[:len(requests)]
+
+    def hash_node_paths(self, texts):
+        data, offsets = TiktokenTokenizer._ragged(texts)
+        out = np.zeros(max(len(texts), 1), np.uint64)
+        self._h.call("smgx_hash_node_paths", _p(data), _p(offsets), len(texts), _p(out))
+        return out[:len(texts)]
+
+    def hash_index_size(self, kind: str = "tokens", model: str = UNKNOWN_MODEL_ID) -> int:
+        out = C.c_uint64()
+        self._h.call("smgx_hash_index_size", model.encode(), 1 if kind == "text" else 0, C.byref(out))
+        return out.value
+
+    def hash_index_get(self, path_hash: int, kind: str = "tokens", model: str = UNKNOWN_MODEL_ID):
+        """hash_index[model].token_tree / .string_tree lookup → matched-prefix copy (list of ids / str) or None."""
+        nb, found = C.c_uint32(), C.c_int()
+        tk = 1 if kind == "text" else 0
+        self._h.call("smgx_hash_index_get", model.encode(), tk, int(path_hash), None, 0, C.byref(nb), C.byref(found))
+        if not found.value:
+            return None
+        buf = np.zeros(max(nb.value, 1), np.uint8)
+        self._h.call("smgx_hash_index_get", model.encode(), tk, int(path_hash), _p(buf), nb.value, C.byref(nb), C.byref(found))
+        raw = buf[:nb.value].tobytes()
+        return raw.decode("utf-8") if tk else np.frombuffer(raw, dtype=np.uint32).tolist()
+
     def set_tree_batch_mode(self, mode: str):
         self._h.call("smgx_set_tree_batch_mode", TREE_BATCH_MODES[mode])
 

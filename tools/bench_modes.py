@@ -95,7 +95,7 @@ def treewalk_mode():
     """K2a by itself at BASELINE config-2 scale: read-only walk + pick of HBM-resident batches against a ≈1.06 M-node tree
     (TRUNKS trunks of 8 pages × 32 branches of 8 pages × 32 leaves of 16 pages; labels ≈1.07 GB at TRUNKS=1000)."""
     from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, _lib, synth
-    W, B, T = 64, 4096, 512
+    W, B, T = 64, int(os.environ.get("BATCH", "4096")), 512
     n_trunks = int(os.environ.get("TRUNKS", "1000"))
     ring, steps, per_call = int(os.environ.get("RING", "32")), int(os.environ.get("STEPS", "20")), int(os.environ.get("PER_CALL", "8"))
     rng = np.random.default_rng(42)
