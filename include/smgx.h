@@ -281,6 +281,18 @@ smgx_status smgx_shard_candidates_device(smgx_policy* p, const char* model_key, 
 smgx_status smgx_shard_reduce_device(smgx_policy* p, uint32_t lane, const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets,
                                      const uint32_t* global_base, uint32_t world, uint32_t n, int32_t* d_out_worker_idx,
                                      smgx_decision_info* d_out_info, char** err);
+
+/* Peer-memory exchange (one process per GPU, NVLink): instead of handing the candidates to a collective, every rank creates one
+ * symmetric gather buffer, the ranks swap CUDA IPC handles once (any host channel), and from then on one asynchronous call per
+ * batch runs, in stream order and without host synchronisation: candidate kernels → stores into every rank's buffer + release
+ * flag → wait for every rank's flag → merge.  All ranks must issue the same sequence of fused calls.  A peer that does not show up
+ * within ≈20 s is reported by smgx_synchronize. */
+#define SMGX_IPC_HANDLE_BYTES 64
+smgx_status smgx_shard_exchange_create(smgx_policy* p, uint32_t world, uint32_t rank, uint32_t max_batch, uint8_t* out_handle /* 64 B */, char** err);
+smgx_status smgx_shard_exchange_connect(smgx_policy* p, const uint8_t* handles /* world × 64 B, rank order */, char** err);
+smgx_status smgx_shard_select_fused_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens, const uint32_t* d_offsets,
+                                           uint32_t n, uint32_t max_request_tokens, const uint32_t* global_base /* host, world */,
+                                           int32_t* d_out_worker_idx, smgx_decision_info* d_out_info, char** err);
 void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err);
 void smgx_device_free(smgx_policy* p, void* dptr);
 smgx_status smgx_memcpy_h2d(smgx_policy* p, void* dptr, const void* host, size_t bytes, char** err);

@@ -121,6 +121,9 @@ def load():
     sig("smgx_select_many_tokens_device", st, vp, cp, u32, vp, vp, vp, u32, vp, pp)
     sig("smgx_shard_candidates_device", st, vp, cp, u32, vp, vp, u32, u32, vp, vp, pp)
     sig("smgx_shard_reduce_device", st, vp, u32, vp, vp, vp, u32, u32, vp, vp, pp)
+    sig("smgx_shard_exchange_create", st, vp, u32, u32, u32, vp, pp)
+    sig("smgx_shard_exchange_connect", st, vp, vp, pp)
+    sig("smgx_shard_select_fused_device", st, vp, cp, u32, vp, vp, u32, u32, vp, vp, vp, pp)
     sig("smgx_device_alloc", vp, vp, C.c_size_t, pp)
     sig("smgx_device_free", None, vp, vp)
     sig("smgx_memcpy_h2d", st, vp, vp, vp, C.c_size_t, pp)

@@ -653,16 +653,43 @@ namespace {
 // keeping max_by_key((score, Reverse(load), Reverse(tree_size))) with LAST max — the same comparison score_overlap makes over
 // the whole fleet (cache_aware.rs:806-818); the prologue (healthy count, min/max load, f32 imbalance gate, first min load) is
 // re-derived from the shards' summaries.
-__global__ void __launch_bounds__(256) shard_reduce_kernel(const smgx_shard_candidate* __restrict__ cands, const smgx_shard_fleet* __restrict__ fleets,
-                                                           const uint32_t* __restrict__ gbase, uint32_t world, uint32_t n, uint64_t abs_thr,
-                                                           float rel_thr, int32_t* __restrict__ out_idx, smgx_decision_info* __restrict__ out_info) {
+// `flags` non-null (peer-memory exchange): cands / fleets are this rank's gather buffer, written by the peers over NVLink; the CTA
+// first waits until every peer's flag has reached `seq` (acquire at system scope), and the data is read past L1 (ld.cg) because
+// the same buffer held other values two steps ago.  fleet_stride: bytes between two shards' summaries.
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) shard_reduce_kernel(const smgx_shard_candidate* cands, const uint8_t* fleets, uint32_t fleet_stride,
+                                                           const uint32_t* __restrict__ gbase, uint32_t world, uint32_t n, uint32_t cand_stride,
+                                                           uint64_t abs_thr, float rel_thr, int32_t* __restrict__ out_idx,
+                                                           smgx_decision_info* __restrict__ out_info, const uint64_t* flags, uint64_t seq,
+                                                           uint32_t* err_flag) {
+    if (flags) {
+        if (threadIdx.x < world) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(flags + threadIdx.x) < seq) {
+                if (clock64() - t0 > 40000000000LL) { if (err_flag) atomicExch(err_flag, 2u); break; }   // ≈20 s: a peer never arrived
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     uint64_t mn = ~0ULL, mx = 0, hl = ~0ULL;
     uint32_t n_healthy = 0;
     int32_t min_idx = -1;
     for (uint32_t g = 0; g < world; ++g) {
-        const smgx_shard_fleet f = fleets[g];
+        smgx_shard_fleet f;
+        {
+            const uint64_t* fp = reinterpret_cast<const uint64_t*>(fleets + (size_t)g * fleet_stride);
+            uint64_t w[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) w[i] = __ldcg(fp + i);
+            memcpy(&f, w, sizeof(f));
+        }
         mn = f.min_load < mn ? f.min_load : mn;
         mx = f.max_load > mx ? f.max_load : mx;
         n_healthy += f.n_healthy;
@@ -677,7 +704,14 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const smgx_shard_cand
             bool have = false;
             uint32_t bs = 0; uint64_t bl = 0, bt = 0; int32_t bi = -1;
             for (uint32_t g = 0; g < world; ++g) {
-                const smgx_shard_candidate c = cands[(size_t)g * n + r];
+                smgx_shard_candidate c;
+                {
+                    const uint64_t* cp = reinterpret_cast<const uint64_t*>(cands + (size_t)g * cand_stride + r);
+                    uint64_t w[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) w[i] = __ldcg(cp + i);
+                    memcpy(&c, w, sizeof(c));
+                }
                 if (c.score == 0 || c.local_idx == 0xFFFFFFFFu) continue;
                 const bool ge = !have || c.score > bs || (c.score == bs && (c.load < bl || (c.load == bl && c.tree_size <= bt)));   // >= : LAST max
                 if (ge) { have = true; bs = c.score; bl = c.load; bt = c.tree_size; bi = (int32_t)(gbase[g] + c.local_idx); }
@@ -694,13 +728,58 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const smgx_shard_cand
         out_info[r] = di;
     }
 }
+
+// Push this shard's candidates + summary into EVERY rank's gather buffer (slot `rank`) over peer memory, then raise this rank's
+// flag there: the CTAs write their share, fence at system scope and count themselves in; the last one to arrive publishes `seq`.
+__global__ void __launch_bounds__(256) shard_push_kernel(const uint64_t* __restrict__ cand_words, uint32_t n_words, const uint64_t* __restrict__ fleet_words,
+                                                         uint8_t* const* __restrict__ peer_parity_base, uint32_t world, uint32_t rank, size_t cand_off,
+                                                         size_t cand_slot_bytes, size_t fleet_off, uint32_t fleet_stride, size_t flag_off, uint64_t seq,
+                                                         uint32_t* __restrict__ arrive) {
+    const uint32_t q = blockIdx.y;
+    uint8_t* base = peer_parity_base[q];
+    uint64_t* dst = reinterpret_cast<uint64_t*>(base + cand_off + (size_t)rank * cand_slot_bytes);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) dst[i] = cand_words[i];
+    if (blockIdx.x == 0 && threadIdx.x < 5) reinterpret_cast<uint64_t*>(base + fleet_off + (size_t)rank * fleet_stride)[threadIdx.x] = fleet_words[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(arrive, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < world) {
+            uint64_t* f = reinterpret_cast<uint64_t*>(peer_parity_base[threadIdx.x] + flag_off) + rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+        }
+        if (threadIdx.x == 0) *arrive = 0;
+    }
+}
 }  // namespace
+
+void launch_shard_push(const smgx_shard_candidate* d_cand, uint32_t n, const smgx_shard_fleet* d_fleet, uint8_t* const* d_peer_parity_base, uint32_t world,
+                       uint32_t rank, size_t cand_off, size_t cand_slot_bytes, size_t fleet_off, uint32_t fleet_stride, size_t flag_off, uint64_t seq,
+                       uint32_t* d_arrive, cudaStream_t stream) {
+    const uint32_t n_words = n * 3;   // 24 B per candidate
+    dim3 grid(std::max<uint32_t>(1, std::min<uint32_t>((n_words + 255) / 256, 64)), world);
+    shard_push_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint64_t*>(d_cand), n_words, reinterpret_cast<const uint64_t*>(d_fleet),
+                                               d_peer_parity_base, world, rank, cand_off, cand_slot_bytes, fleet_off, fleet_stride, flag_off, seq, d_arrive);
+    SMGX_CUDA(cudaGetLastError());
+}
 
 void launch_shard_reduce(const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets, const uint32_t* d_global_base, uint32_t world,
                          uint32_t n, uint64_t abs_threshold, float rel_threshold, int32_t* d_out_idx, smgx_decision_info* d_out_info,
                          cudaStream_t stream) {
     if (!n) return;
-    shard_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_cands, d_fleets, d_global_base, world, n, abs_threshold, rel_threshold, d_out_idx, d_out_info);
+    shard_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_cands, reinterpret_cast<const uint8_t*>(d_fleets), (uint32_t)sizeof(smgx_shard_fleet),
+                                                             d_global_base, world, n, n, abs_threshold, rel_threshold, d_out_idx, d_out_info, nullptr, 0, nullptr);
+    SMGX_CUDA(cudaGetLastError());
+}
+void launch_shard_reduce_wait(const uint8_t* d_parity_base, size_t cand_off, uint32_t cand_stride, size_t fleet_off, uint32_t fleet_stride, size_t flag_off,
+                              uint64_t seq, const uint32_t* d_global_base, uint32_t world, uint32_t n, uint64_t abs_threshold, float rel_threshold,
+                              int32_t* d_out_idx, smgx_decision_info* d_out_info, uint32_t* d_err, cudaStream_t stream) {
+    shard_reduce_kernel<<<std::max<uint32_t>(1, (n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const smgx_shard_candidate*>(d_parity_base + cand_off), d_parity_base + fleet_off, fleet_stride, d_global_base, world, n, cand_stride,
+        abs_threshold, rel_threshold, d_out_idx, d_out_info, reinterpret_cast<const uint64_t*>(d_parity_base + flag_off), seq, d_err);
     SMGX_CUDA(cudaGetLastError());
 }
 

@@ -75,6 +75,13 @@ void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uin
 void launch_content_hashes(const uint32_t* d_tokens, uint32_t n_tokens, uint32_t block_size, uint64_t* d_out, cudaStream_t stream);
 
 void launch_fill(uint32_t* d, uint32_t value, size_t n_words, cudaStream_t stream);
+// peer-memory exchange of the sharded pick (smgx.cu: Exchange)
+void launch_shard_push(const smgx_shard_candidate* d_cand, uint32_t n, const smgx_shard_fleet* d_fleet, uint8_t* const* d_peer_parity_base, uint32_t world,
+                       uint32_t rank, size_t cand_off, size_t cand_slot_bytes, size_t fleet_off, uint32_t fleet_stride, size_t flag_off, uint64_t seq,
+                       uint32_t* d_arrive, cudaStream_t stream);
+void launch_shard_reduce_wait(const uint8_t* d_parity_base, size_t cand_off, uint32_t cand_stride, size_t fleet_off, uint32_t fleet_stride, size_t flag_off,
+                              uint64_t seq, const uint32_t* d_global_base, uint32_t world, uint32_t n, uint64_t abs_threshold, float rel_threshold,
+                              int32_t* d_out_idx, smgx_decision_info* d_out_info, uint32_t* d_err, cudaStream_t stream);
 
 // Merge of per-shard candidates (worker-id-sharded fleets): [world][n] candidates + [world] fleet summaries → picks.
 void launch_shard_reduce(const smgx_shard_candidate* d_cands, const smgx_shard_fleet* d_fleets, const uint32_t* d_global_base, uint32_t world,

@@ -122,6 +122,8 @@ public:
                 m.string_tree.reset();
                 m.d_slice_of_tenant.release();
             }
+            for (uint32_t q = 0; q < xch.peer.size(); ++q) if (q < xch.opened.size() && xch.opened[q] && xch.peer[q]) cudaIpcCloseMemHandle(xch.peer[q]);
+            xch.local.release(); xch.d_bases.release(); xch.d_cand.release(); xch.d_fleet.release(); xch.d_arrive.release(); xch.d_gbase.release();
             d_err.release(); d_flush.release(); scratch.release(); scratch2.release(); d_gbase.release();
             if (state_ready) cudaEventDestroy(state_ready);
             if (ctrl) cudaStreamDestroy(ctrl);
@@ -545,6 +547,19 @@ public:
         }
         throw Error(SMGX_INVALID_ARGUMENT, "unknown or already completed ticket");
     }
+
+    // Peer-memory exchange of the worker-id-sharded pick: every rank owns one symmetric gather buffer (two parities);
+    // rank g's candidates are stored straight into slot g of every rank's buffer over NVLink (CUDA IPC mappings).
+    struct Exchange {
+        uint32_t world = 0, rank = 0, max_batch = 0;
+        DevBuf local, d_bases, d_cand, d_fleet, d_arrive, d_gbase;
+        std::vector<uint8_t*> peer;       // peer[q] = rank q's buffer as mapped here (own = local.ptr)
+        std::vector<bool> opened;
+        uint64_t seq = 0;
+        size_t flag_off = 0, fleet_off = 0, cand_off = 0, parity_stride = 0, cand_slot_bytes = 0;
+        static constexpr uint32_t kFleetStride = 64;
+        bool connected = false;
+    } xch;
 
     TenantTable tenants;         // TENANT_INTERN_POOL (token_tree.rs:160-176)
     uint64_t token_ts = 0;       // GLOBAL_TIMESTAMP (token_tree.rs:179), shared by every token tree of the policy
@@ -1486,6 +1501,105 @@ smgx_status smgx_shard_reduce_device(smgx_policy* p, uint32_t lane, const smgx_s
     });
 }
 
+// ---- peer-memory exchange for sharded fleets ----
+smgx_status smgx_shard_exchange_create(smgx_policy* p, uint32_t world, uint32_t rank, uint32_t max_batch, uint8_t* out_handle, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_handle);
+        SMGX_REQUIRE(world >= 1 && world <= 64 && rank < world && max_batch > 0, "bad exchange geometry");
+        static_assert(sizeof(cudaIpcMemHandle_t) == SMGX_IPC_HANDLE_BYTES, "IPC handle size");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        auto& x = P.xch;
+        SMGX_REQUIRE(x.world == 0, "exchange already created");
+        x.world = world; x.rank = rank; x.max_batch = max_batch;
+        auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+        x.flag_off = 0;
+        x.fleet_off = up((size_t)world * 8);
+        x.cand_off = x.fleet_off + up((size_t)world * Policy::Exchange::kFleetStride);
+        x.cand_slot_bytes = ((size_t)max_batch + 31) / 32 * 32 * sizeof(smgx_shard_candidate);   // 32 candidates = 768 B: keeps slots 256 B aligned
+        x.parity_stride = x.cand_off + (size_t)world * x.cand_slot_bytes;
+        x.local.reserve(2 * x.parity_stride);
+        SMGX_CUDA(cudaMemset(x.local.ptr, 0, 2 * x.parity_stride));
+        x.d_bases.reserve(2 * 64 * sizeof(void*));
+        x.d_cand.reserve((size_t)max_batch * sizeof(smgx_shard_candidate));
+        x.d_fleet.reserve(64);
+        x.d_arrive.reserve(64);
+        x.d_gbase.reserve(64 * 4);
+        SMGX_CUDA(cudaMemset(x.d_arrive.ptr, 0, 64));
+        SMGX_CUDA(cudaDeviceSynchronize());
+        cudaIpcMemHandle_t h;
+        SMGX_CUDA(cudaIpcGetMemHandle(&h, x.local.ptr));
+        memcpy(out_handle, &h, sizeof(h));
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_shard_exchange_connect(smgx_policy* p, const uint8_t* handles, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(handles);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        auto& x = P.xch;
+        SMGX_REQUIRE(x.world > 0 && !x.connected, "create the exchange first (once)");
+        x.peer.assign(x.world, nullptr);
+        x.opened.assign(x.world, false);
+        for (uint32_t q = 0; q < x.world; ++q) {
+            if (q == x.rank) { x.peer[q] = x.local.as<uint8_t>(); continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)q * SMGX_IPC_HANDLE_BYTES, sizeof(h));
+            void* ptr = nullptr;
+            SMGX_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            x.peer[q] = (uint8_t*)ptr;
+            x.opened[q] = true;
+        }
+        std::vector<uint8_t*> bases(2 * 64, nullptr);   // [parity][rank]
+        for (uint32_t par = 0; par < 2; ++par) for (uint32_t q = 0; q < x.world; ++q) bases[par * 64 + q] = x.peer[q] + par * x.parity_stride;
+        SMGX_CUDA(cudaMemcpy(x.d_bases.ptr, bases.data(), bases.size() * sizeof(void*), cudaMemcpyHostToDevice));
+        x.connected = true;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_shard_select_fused_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens, const uint32_t* d_offsets,
+                                           uint32_t n, uint32_t max_request_tokens, const uint32_t* global_base, int32_t* d_out_worker_idx,
+                                           smgx_decision_info* d_out_info, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(global_base); NONNULL(d_out_worker_idx);
+        SMGX_REQUIRE(n == 0 || (d_tokens && d_offsets), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        auto& x = P.xch;
+        SMGX_REQUIRE(x.connected, "peer-memory exchange is not connected");
+        SMGX_REQUIRE(n <= x.max_batch, "batch larger than the exchange was created for");
+        SMGX_REQUIRE(lane < P.lanes.size(), "lane out of range");
+        ModelState& m = P.model(model_key, false);
+        const uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
+        Lane& L = P.lanes[lane];
+        if (!x.seq) SMGX_CUDA(cudaMemcpyAsync(x.d_gbase.ptr, global_base, (size_t)x.world * 4, cudaMemcpyHostToDevice, L.stream));
+        const uint64_t seq = ++x.seq;
+        const uint32_t par = (uint32_t)(seq & 1);
+        if (n) {
+            BatchDesc d{d_tokens, d_offsets, nullptr, nullptr, n, 0, x.d_cand.as<smgx_shard_candidate>()};
+            P.enqueue_batches(m, L, &d, 1, cap);
+        } else {
+            EventIndexView ixv; FleetView fv;
+            P.sync_state(m, &ixv, &fv);
+        }
+        // stream order on this lane: candidates → push into every rank's buffer + flag → wait for every rank's flag → merge
+        launch_shard_push(x.d_cand.as<smgx_shard_candidate>(), n, m.d_derived.as<smgx_shard_fleet>(),
+                          reinterpret_cast<uint8_t* const*>(x.d_bases.as<uint8_t*>() + par * 64), x.world, x.rank, x.cand_off, x.cand_slot_bytes, x.fleet_off,
+                          Policy::Exchange::kFleetStride, x.flag_off, seq, x.d_arrive.as<uint32_t>(), L.stream);
+        launch_shard_reduce_wait(x.local.as<uint8_t>() + par * x.parity_stride, x.cand_off, (uint32_t)(x.cand_slot_bytes / sizeof(smgx_shard_candidate)),
+                                 x.fleet_off, Policy::Exchange::kFleetStride, x.flag_off, seq, x.d_gbase.as<uint32_t>(), x.world, n,
+                                 P.cfg.balance_abs_threshold, P.cfg.balance_rel_threshold, d_out_worker_idx, d_out_info, P.d_err.as<uint32_t>(), L.stream);
+        P.launches += 2;
+        SMGX_CUDA(cudaEventRecord(L.done, L.stream));
+        L.has_done = true;
+        return SMGX_SUCCESS;
+    });
+}
+
 void* smgx_device_alloc(smgx_policy* p, size_t bytes, char** err) {
     void* out = nullptr;
     guard(err, [&]() {
@@ -1524,6 +1638,7 @@ smgx_status smgx_synchronize(smgx_policy* p, char** err) {
         SMGX_CUDA(cudaMemcpy(&flag, p->impl.d_err.ptr, 4, cudaMemcpyDeviceToHost));
         if (flag) {
             SMGX_CUDA(cudaMemset(p->impl.d_err.ptr, 0, 4));
+            if (flag == 2) throw Error(SMGX_DEVICE_ERROR, "peer-memory exchange: a rank did not publish its candidates in time");
             throw Error(SMGX_INVALID_ARGUMENT, "a request exceeded max_tokens_per_request on the device-resident path");
         }
         return SMGX_SUCCESS;

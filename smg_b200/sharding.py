@@ -37,7 +37,41 @@ class ShardedEventRouter:
         for w in self.workers:                       # local ids follow local slice order
             self.indexer.intern_worker(w.url())
         self.gbase = np.asarray([r[0] for r in self.ranges], dtype=np.uint32)
+        self._max_batch = max_batch
         self._h, self._L = self.policy._h, _lib.load()
+
+    def connect_peers(self, all_gather_bytes):
+        """Peer-memory exchange (smgx_shard_exchange_*): `all_gather_bytes(np.uint8[64]) -> np.uint8[world*64]` swaps the CUDA IPC
+        handles once; afterwards select_fused needs no collective and no host synchronisation between the kernels."""
+        handle = np.zeros(64, np.uint8)
+        self._h.call("smgx_shard_exchange_create", self.world, self.rank, self._max_batch, handle.ctypes.data_as(C.c_void_p))
+        handles = np.ascontiguousarray(all_gather_bytes(handle), dtype=np.uint8)
+        self._h.call("smgx_shard_exchange_connect", handles.ctypes.data_as(C.c_void_p))
+
+    def select_fused_device(self, d_tokens, d_offsets, n: int, max_request_tokens: int, d_out, lane: int = 0):
+        """Device pointers in, asynchronous on `lane`: candidates → stores into every rank's gather buffer → wait → merge."""
+        self._h.call("smgx_shard_select_fused_device", self.model, lane, d_tokens, d_offsets, n, max_request_tokens,
+                     self.gbase.ctypes.data_as(C.c_void_p), d_out, None)
+
+    def select_fused(self, tokens, offsets, max_request_tokens: int):
+        """Host arrays in/out around select_fused_device (tests)."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = offsets.size - 1
+        h, L = self._h, self._L
+        err = _lib.new_err()
+        alloc = lambda nbytes: L.smgx_device_alloc(h.p, max(nbytes, 16), C.byref(err))
+        d_tok, d_off, d_out = alloc(tokens.nbytes), alloc(offsets.nbytes), alloc(n * 4)
+        if tokens.size:
+            h.call("smgx_memcpy_h2d", d_tok, tokens.ctypes.data_as(C.c_void_p), tokens.nbytes)
+        h.call("smgx_memcpy_h2d", d_off, offsets.ctypes.data_as(C.c_void_p), offsets.nbytes)
+        self.select_fused_device(d_tok, d_off, n, max_request_tokens, d_out)
+        h.call("smgx_synchronize")
+        out = np.zeros(max(n, 1), np.int32)
+        h.call("smgx_memcpy_d2h", out.ctypes.data_as(C.c_void_p), d_out, n * 4)
+        for d in (d_tok, d_off, d_out):
+            L.smgx_device_free(h.p, d)
+        return out[:n]
 
     def owns(self, global_idx: int) -> bool:
         return self.lo <= global_idx < self.hi

@@ -1,5 +1,6 @@
 """Worker-id-sharded pick (BASELINE config 4 shape, scaled down): 2 and 4 ranks, each owning a contiguous range of the fleet,
-candidates exchanged with a gloo all-gather, merged on every rank — picks must equal the oracle run on the WHOLE fleet.
+candidates exchanged with a gloo all-gather AND through the peer-memory exchange (CUDA IPC mappings, stores + flags, no collective),
+merged on every rank — picks must equal the oracle run on the WHOLE fleet.
 Ranks share cuda:0 when the box has fewer GPUs than ranks (NCCL would refuse that; the exchange is plumbing)."""
 import os
 import sys
@@ -54,6 +55,7 @@ def _worker(rank, world, port, n_workers, seed, ret):
         outs = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(outs, t)
         return np.concatenate([o.numpy() for o in outs])
+    router.connect_peers(all_gather)          # CUDA IPC handles travel over the same gloo channel, once
     ok = True
     for round_no in range(3):
         loads = synth.poisson_loads(n_workers, 8, seed + round_no)
@@ -67,13 +69,15 @@ def _worker(rank, world, port, n_workers, seed, ret):
         flat = np.concatenate(reqs).astype(np.uint32)
         offs = np.zeros(B + 1, np.uint32); np.cumsum(lens, out=offs[1:])
         got = router.select(flat, offs, T, all_gather)
+        fused = router.select_fused(flat, offs, T)           # peer-memory exchange: same picks on every rank
+        ok = ok and np.array_equal(got, fused)
         if rank == 0:
             op.set_state(loads, healthy, [1] * n_workers)
             want, br, _, _ = op.select_batch_tokens(flat, offs.astype(np.uint64))
             ok = ok and np.array_equal(got, want)
             if round_no < 2:
                 ok = ok and (np.asarray(br) == 2).sum() > B // 10
-    ret[rank] = bool(ok) if rank == 0 else True
+    ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -90,4 +94,4 @@ def test_sharded_pick_matches_oracle_on_whole_fleet(world, n_workers, seed):
     for p in procs:
         p.join(300)
     assert all(p.exitcode == 0 for p in procs)
-    assert ret.get(0) is True
+    assert all(ret.get(r) is True for r in range(world))

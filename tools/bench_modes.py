@@ -263,7 +263,21 @@ def sharded_mode():
     out = torch.empty(B, dtype=torch.int32, device="cuda")
     vp = lambda t: C.c_void_p(t.data_ptr())
 
+    fused = os.environ.get("FUSED", "1") != "0"
+    if fused:
+        def ag(arr):
+            t = torch.from_numpy(arr.copy()).cuda()
+            out = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(out, t)
+            return out.cpu().numpy()
+        router.connect_peers(ag)
+
+    def step_fused():
+        router.select_fused_device(vp(d_tok), vp(d_off), B, T, vp(out))      # asynchronous; stream order does the rest
+
     def step():
+        if fused:
+            return step_fused()
         h.call("smgx_shard_candidates_device", router.model, 0, vp(d_tok), vp(d_off), B, T, vp(cand), vp(fleet))
         h.call("smgx_synchronize")                    # the library's lane stream → torch's stream
         dist.all_gather_into_tensor(all_c, cand)
@@ -274,19 +288,33 @@ def sharded_mode():
 
     for _ in range(5):
         step()
+    h.call("smgx_synchronize")
+    ref_picks = None
+    if fused:   # same picks as the collective path
+        fused = False
+        step()
+        ref_picks = out.cpu().numpy().copy()
+        fused = True
+        step()
+        h.call("smgx_synchronize")
+        assert np.array_equal(out.cpu().numpy(), ref_picks), "fused exchange and all-gather path disagree"
     dist.barrier()
     torch.cuda.synchronize()
-    K = 50
+    K = int(os.environ.get("STEPS", "200"))
     t0 = time.perf_counter()
     for _ in range(K):
         step()
+    h.call("smgx_synchronize")
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     picks = out.cpu().numpy()
     res = None
     if rank == 0:
-        res = {"mode": "worker-id-sharded event pick (config 4 shape): candidates kernel per shard → NCCL all-gather (24 B/request/shard) → merge kernel",
+        res = {"mode": "worker-id-sharded event pick (config 4 shape): candidates kernels per shard → " +
+                       ("peer-memory exchange (stores into every rank's gather buffer over NVLink + flags) → merge kernel, one stream, no host sync"
+                        if fused else "NCCL all-gather (24 B/request/shard) → merge kernel"),
+               "exchange": "peer-memory" if fused else "nccl",
                "n_gpus": world, "workers": W, "workers_per_gpu": 512, "batch": B, "index_entries_total": n_seq * P,
                "decisions_per_s": K * B / float(dt.item()), "ms_per_step": 1e3 * float(dt.item()) / K,
                "picks_in_range": bool(picks.min() >= 0 and picks.max() < W), "distinct_workers_picked": int(len(set(picks.tolist())))}
