@@ -70,8 +70,9 @@ typedef struct smgx_cache_aware_config {
 /* How a batch of tree-mode requests (token tree / string tree: every routed request also inserts) is serialised.
  * select_worker takes &self and runs on many tokio tasks at once; it is not atomic, and the reference promises eventual
  * consistency only between concurrent match and insert (token_tree.rs:1035-1037).
- *   SEQUENTIAL: results equal calling select_worker one request at a time, in batch order (timestamps included).  The GPU walks
- *               maximal runs of requests that cannot see each other's inserts (distinct first page / first char) per launch.
+ *   SEQUENTIAL: results equal calling select_worker one request at a time, in batch order (timestamps included).  Run
+ *               optimistically: the GPU walks the rest of the batch against one snapshot, the host commits requests in order up to
+ *               the first one a preceding insert really affected, and the walk restarts there.
  *   SNAPSHOT:   every request of the batch walks and decides against the pre-batch tree (one launch), then the match side
  *               effects and the inserts are applied in batch order — the interleaving "all reads, then each task's writes" of
  *               concurrent select_worker calls.  Identical to SEQUENTIAL whenever no two requests of a batch share a first page. */

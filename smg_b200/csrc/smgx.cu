@@ -20,6 +20,7 @@
 #include "token_tree.h"
 #include "string_tree.h"
 #include "blake3.h"
+#include <cstdio>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -297,22 +298,14 @@ public:
         std::vector<int32_t> path_ten((size_t)n * kPathCap), ten(n);
         std::vector<uint64_t> path_hash;   // hash_token_path of every request, for the hash_index side effect (:881-886, :397-401)
         if (decide) enqueue_path_hashes(lane, reinterpret_cast<const uint8_t*>(lane.d_tokens.as<uint32_t>() - base), lane.d_offsets.as<uint32_t>(), offsets, n, 4, path_hash);
-        std::unordered_set<uint64_t> seen;
         const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
+        // SEQUENTIAL is run optimistically: the rest of the batch is walked against one snapshot, then the host replays the
+        // requests in order and stops at the first one whose snapshot walk is no longer what a walk at that moment would
+        // return — a path node was split, the node the walk stopped under gained a child for the next page, or (when the pick
+        // used it) the deepest node's tenant changed.  Everything before it is committed; the walk restarts from there.
         uint32_t seg = 0;
         while (seg < n) {
-            uint32_t end = seg;
-            if (snapshot) end = n;
-            else {
-                seen.clear();
-                while (end < n) {
-                    const uint32_t len = offsets[end + 1] - offsets[end];
-                    if (len >= kPage) {
-                        if (!seen.insert(page_key_host(tokens + offsets[end], 0)).second) break;
-                    }
-                    ++end;
-                }
-            }
+            const uint32_t end = n;
             EventIndexView ixv;
             FleetView fv;
             sync_state(m, &ixv, &fv);
@@ -335,17 +328,36 @@ public:
             SMGX_CUDA(cudaMemcpyAsync(path_len.data() + seg, lane.d_path_len.as<uint32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(ten.data() + seg, lane.d_tenant.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+            tree.begin_chunk();
             // walks deeper than the kernel reports: recover the node list from the same (still unmodified) tree state
             std::unordered_map<uint32_t, TreeMatch> deep;
-            for (uint32_t r = seg; r < end; ++r)
-                if (path_len[r] > kPathCap) deep.emplace(r, tree.match_prefix_host(tokens + offsets[r], offsets[r + 1] - offsets[r], false));
-            for (uint32_t r = seg; r < end; ++r) {
+            if (snapshot)
+                for (uint32_t r = seg; r < end; ++r)
+                    if (path_len[r] > kPathCap) deep.emplace(r, tree.match_prefix_host(tokens + offsets[r], offsets[r + 1] - offsets[r], false));
+            uint32_t r = seg;
+            for (; r < end; ++r) {
                 const uint32_t* tk = tokens + offsets[r];
                 const uint32_t len = offsets[r + 1] - offsets[r];
                 if (decide && info[r].branch == SMGX_BR_NO_HEALTHY) continue;   // returns None before touching anything (:653-655)
+                const uint32_t* pth = path.data() + (size_t)r * kPathCap;
+                if (!snapshot && r > seg) {   // is the snapshot walk still the walk the reference would do now?
+                    bool valid = path_len[r] <= kPathCap;
+                    uint64_t sum_len = 0;
+                    for (uint32_t d = 0; valid && d < path_len[r]; ++d) { valid = !tree.split_in_chunk(pth[d]); sum_len += tree.label_len_of(pth[d]); }
+                    const uint8_t br = info[r].branch;
+                    if (valid && path_len[r] && (br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_FALLBACK_FIRST_HEALTHY))
+                        valid = tree.any_tenant(pth[path_len[r] - 1]) == ten[r];                       // the pick read this tenant
+                    const uint32_t aligned = (len / kPage) * kPage;
+                    if (valid && sum_len == info[r].matched && aligned - info[r].matched >= kPage)     // stopped under a node: still no child for the next page?
+                        valid = !tree.has_child(path_len[r] ? pth[path_len[r] - 1] : 0, tk + info[r].matched);
+                    if (!valid) break;
+                }
                 // match side effects: touch_tenant on every matched node, in order (:685-689)
-                if (path_len[r] <= kPathCap) tree.apply_match_touches(path.data() + (size_t)r * kPathCap, path_ten.data() + (size_t)r * kPathCap, path_len[r]);
-                else { const TreeMatch& hm = deep.at(r); tree.apply_match_touches(hm.path.data(), hm.path_tenants.data(), (uint32_t)hm.path.size()); }
+                if (snapshot) {
+                    if (path_len[r] <= kPathCap) tree.apply_match_touches(pth, path_ten.data() + (size_t)r * kPathCap, path_len[r]);
+                    else { const TreeMatch& hm = deep.at(r); tree.apply_match_touches(hm.path.data(), hm.path_tenants.data(), (uint32_t)hm.path.size()); }
+                } else if (path_len[r] <= kPathCap) tree.apply_match_touches(pth, path_len[r]);        // tenants as they are now
+                else { TreeMatch hm = tree.match_prefix_host(tk, len, false); tree.apply_match_touches(hm.path.data(), (uint32_t)hm.path.size()); }
                 if (!decide) continue;
                 const uint8_t br = info[r].branch;
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
@@ -355,7 +367,7 @@ public:
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
-            seg = end;
+            seg = r;
         }
         if (out_info) memcpy(out_info, info.data(), (size_t)n * sizeof(smgx_decision_info));
         if (out_tenant) memcpy(out_tenant, ten.data(), (size_t)n * 4);
@@ -418,31 +430,10 @@ public:
         std::vector<uint8_t> fill(n);
         std::vector<uint64_t> path_hash;   // hash_node_path of every request (:950-956, :420-424)
         if (decide) enqueue_path_hashes(lane, lane.d_text.as<uint8_t>() - base, lane.d_offsets.as<uint32_t>(), offsets, n, 1, path_hash);
-        std::unordered_set<uint64_t> seen;
         const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
         uint32_t seg = 0;
-        while (seg < n) {
-            uint32_t end = seg;
-            if (snapshot) end = n;
-            else {
-                seen.clear();
-                while (end < n) {
-                    const uint32_t len = offsets[end + 1] - offsets[end];
-                    uint64_t key = ~0ULL;   // walk ends on the root: empty text or no child under the first char
-                    if (len) {
-                        uint32_t cl;
-                        const uint32_t cp = utf8_first(text + offsets[end], &cl);
-                        if (tree.root_has_child(cp)) key = cp;
-                    }
-                    if (!seen.insert(key).second) break;
-                    if (key == ~0ULL && len) {   // this request's insert creates the root child for its first char
-                        uint32_t cl;
-                        if (!seen.insert(utf8_first(text + offsets[end], &cl)).second) break;
-                    }
-                    ++end;
-                }
-                if (end == seg) ++end;
-            }
+        while (seg < n) {   // SEQUENTIAL runs optimistically, as in tree_select
+            const uint32_t end = n;
             EventIndexView ixv;
             FleetView fv;
             sync_state(m, &ixv, &fv);
@@ -463,9 +454,29 @@ public:
             SMGX_CUDA(cudaMemcpyAsync(ten.data() + seg, lane.d_tenant.as<int32_t>() + seg, (size_t)cnt * 4, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(fill.data() + seg, lane.d_fill.as<uint8_t>() + seg, (size_t)cnt, cudaMemcpyDeviceToHost, lane.stream));
             SMGX_CUDA(cudaStreamSynchronize(lane.stream));
-            for (uint32_t r = seg; r < end; ++r) {
+            tree.begin_chunk();
+            uint32_t r = seg;
+            for (; r < end; ++r) {
                 if (decide && info[r].branch == SMGX_BR_NO_HEALTHY) continue;
-                tree.apply_match_effects(node[r], ten[r], fill[r] != 0);   // cache fill, epoch draw, 1-in-8 refresh (:598-637)
+                if (!snapshot && r > seg) {   // is the snapshot walk still the walk the reference would do now?
+                    bool valid = true;
+                    uint64_t sum_chars = 0;
+                    for (uint32_t nd = node[r]; valid && nd != 0 && nd != kNoNode; nd = tree.parent_of(nd)) { valid = !tree.split_in_chunk(nd); sum_chars += tree.label_chars_of(nd); }
+                    const uint8_t br = info[r].branch;
+                    if (valid && (br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_FALLBACK_FIRST_HEALTHY)) valid = tree.any_tenant_of(node[r]) == ten[r];
+                    if (valid && sum_chars == info[r].matched && info[r].matched < info[r].input) {   // stopped under a node: still no child for the next char?
+                        const uint8_t* tx = text + offsets[r];
+                        const uint32_t nb = offsets[r + 1] - offsets[r];
+                        uint32_t pb = 0, chars = 0;
+                        while (pb < nb && chars < info[r].matched) { ++pb; while (pb < nb && (tx[pb] & 0xC0) == 0x80) ++pb; ++chars; }
+                        uint32_t cl;
+                        if (pb < nb) valid = !tree.has_child(node[r], utf8_first(tx + pb, &cl));
+                    }
+                    if (!valid) break;
+                }
+                // cache fill, epoch draw, 1-in-8 refresh (:598-637): SNAPSHOT replays what the walk read, SEQUENTIAL what the node holds now
+                if (snapshot) tree.apply_match_effects(node[r], ten[r], fill[r] != 0);
+                else tree.apply_match_effects(node[r], tree.any_tenant_of(node[r]), !tree.cache_valid_of(node[r]));
                 if (!decide) continue;
                 const uint8_t br = info[r].branch;
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
@@ -479,7 +490,7 @@ public:
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
-            seg = end;
+            seg = r;
         }
         if (out_info) memcpy(out_info, info.data(), (size_t)n * sizeof(smgx_decision_info));
         if (out_tenant) memcpy(out_tenant, ten.data(), (size_t)n * 4);

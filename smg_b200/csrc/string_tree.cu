@@ -200,6 +200,7 @@ void StringTreeIndex::insert_text(const uint8_t* s, size_t n, uint32_t tenant) {
             const uint32_t nn = new_node(moff, (uint32_t)shared, shared_chars, prev, cp);
             nodes_[nn].tenants = nodes_[m].tenants;
             nodes_[nn].last_tenant = nodes_[m].last_tenant;
+            nodes_[nn].split_epoch = nodes_[m].split_epoch = chunk_epoch_;
             Node& mm = nodes_[m];
             mm.label_off = moff + shared; mm.label_bytes -= (uint32_t)shared; mm.label_chars -= shared_chars; mm.parent = nn;
             uint32_t l2;

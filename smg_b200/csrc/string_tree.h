@@ -67,6 +67,14 @@ public:
     void clear();
     void entries(std::vector<std::pair<std::string, std::vector<std::pair<uint32_t, uint64_t>>>>& out) const;   // :1116-1221
     bool root_has_child(uint32_t cp) const { return find_child(0, cp) >= 0; }
+    // optimistic batching (smgx.cu text_select)
+    void begin_chunk() { ++chunk_epoch_; }
+    bool split_in_chunk(uint32_t node) const { return nodes_[node].split_epoch == chunk_epoch_; }
+    uint32_t parent_of(uint32_t node) const { return nodes_[node].parent; }
+    uint32_t label_chars_of(uint32_t node) const { return nodes_[node].label_chars; }
+    bool has_child(uint32_t node, uint32_t cp) const { return find_child(node, cp) >= 0; }
+    int32_t any_tenant_of(uint32_t node) const { return any_tenant(nodes_[node]); }
+    bool cache_valid_of(uint32_t node) const { return cache_valid(nodes_[node]); }
     static bool valid_utf8(const uint8_t* s, size_t n);
 
     // ---- device mirror ----
@@ -84,6 +92,7 @@ private:
         int32_t last_tenant = -1;
         std::vector<std::pair<uint32_t, uint32_t>> kids;      // (first char, child), ascending by char
         bool alive = true;
+        uint64_t split_epoch = 0;                             // chunk in which this node was last split (or created by a split)
     };
     uint64_t next_epoch() { return (*epoch_)++; }
     int64_t find_child(uint32_t parent, uint32_t cp) const;
@@ -108,6 +117,7 @@ private:
 
     TenantTable* tenants_;
     uint64_t* epoch_;
+    uint64_t chunk_epoch_ = 1;
     std::vector<Node> nodes_;   // nodes_[0] = root
     std::vector<uint32_t> free_nodes_;
     size_t live_nodes_ = 0;     // excludes the root

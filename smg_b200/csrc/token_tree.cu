@@ -214,6 +214,7 @@ void TokenTreeIndex::insert_tokens(const uint32_t* toks, size_t n, uint32_t tena
         nodes_[mid].hit_count = nodes_[child].hit_count;
         nodes_[mid].creation_time = nodes_[child].creation_time;
         nodes_[mid].priority = nodes_[child].priority;
+        nodes_[mid].split_epoch = nodes_[child].split_epoch = chunk_epoch_;
         nodes_[child].label_off = child_off + common;
         nodes_[child].label_len = child_len - (uint32_t)common;
         nodes_[child].parent = mid;

@@ -25,7 +25,7 @@ namespace smgx {
 constexpr uint32_t kPage = 16;            // token_tree.rs:44
 constexpr uint32_t kNoNode = 0xFFFFFFFFu;
 constexpr uint32_t kTombChild = 0xFFFFFFFEu;
-constexpr uint32_t kPathCap = 8;          // matched nodes reported per request by the kernel (deeper paths are re-walked on the host)
+constexpr uint32_t kPathCap = 32;         // matched nodes reported per request by the kernel (deeper paths are re-walked on the host)
 
 struct alignas(16) ChildSlot { uint64_t key; uint32_t parent; uint32_t child; };  // host table entry; key 0 = empty
 // device table entry: the child's header rides in the slot, so one 32 B read resolves a probe AND yields the label location
@@ -87,6 +87,11 @@ public:
     size_t node_count() const { return live_nodes_; }
     void entries(std::vector<std::pair<std::vector<uint32_t>, std::vector<std::pair<uint32_t, uint64_t>>>>& out) const;  // iter_entries :1039
     int32_t any_tenant(uint32_t node) const;
+    // optimistic batching (smgx.cu tree_select): nodes split since begin_chunk(), a node's label length, child lookup
+    void begin_chunk() { ++chunk_epoch_; }
+    bool split_in_chunk(uint32_t node) const { return nodes_[node].split_epoch == chunk_epoch_; }
+    uint32_t label_len_of(uint32_t node) const { return nodes_[node].label_len; }
+    bool has_child(uint32_t node, const uint32_t* page) const { return find_child(node, page) >= 0; }
 
     // ---- device mirror ----
     TokenTreeView flush(cudaStream_t stream, uint64_t* launches);
@@ -108,6 +113,7 @@ private:
         std::vector<uint32_t> kids;                            // child node ids (for eviction / iteration)
         bool alive = true;
         uint32_t slot = kNoNode;                               // table_ index of the entry that points at this node
+        uint64_t split_epoch = 0;                              // chunk in which this node was last split (or created by a split)
     };
     uint64_t next_ts() { return (*global_ts_)++; }
     uint64_t key_of(uint32_t parent, const uint32_t* page) const;
@@ -126,6 +132,7 @@ private:
 
     TenantTable* tenants_;
     uint64_t* global_ts_;
+    uint64_t chunk_epoch_ = 1;
     EvictPolicy policy_;
     std::vector<Node> nodes_;            // nodes_[0] = root
     std::vector<uint32_t> free_nodes_;
