@@ -234,6 +234,14 @@ smgx_status smgx_tokenizer_load_tiktoken_file(smgx_policy* p, const char* model_
 smgx_status smgx_tokenizer_load_tiktoken(smgx_policy* p, const char* model_key, const uint8_t* blob, const uint32_t* tok_offsets,
                                          const uint32_t* ranks, uint32_t n_tokens, const char* const* special_strs,
                                          const uint32_t* special_ids, uint32_t n_special, char** err);
+/* HuggingFaceTokenizer (crates/tokenizer/src/huggingface.rs:310-316 → crate `tokenizers`), byte-level BPE family whose tokenizer.json
+ * has: no normalizer; pre_tokenizer = Split(Regex = the pattern above, Isolated) + ByteLevel(use_regex = false) — Llama 3 and kin;
+ * model.type = "BPE" without dropout / unk / byte_fallback.  The caller parses the JSON (serde_json in the gateway,
+ * smg_b200/policy.py here) and hands over: token i = blob[tok_offsets[i] .. tok_offsets[i+1]) as RAW bytes (byte-level chars mapped
+ * back) with id ids[i]; `merges` = n_merges (left id, right id) pairs in priority order; model.ignore_merges; added_tokens as specials. */
+smgx_status smgx_tokenizer_load_bpe_merges(smgx_policy* p, const char* model_key, const uint8_t* blob, const uint32_t* tok_offsets, const uint32_t* ids,
+                                           uint32_t n_tokens, const uint32_t* merges, uint32_t n_merges, int ignore_merges,
+                                           const char* const* special_strs, const uint32_t* special_ids, uint32_t n_special, char** err);
 /* Encoder::encode_batch (tiktoken.rs:464-469) on the GPU: text i = text[offsets[i] .. offsets[i+1]) (UTF-8, already
  * chat-template-rendered; special-token strings are recognised, tiktoken.rs:446-460).  Writes the ragged token ids and
  * out_tok_offsets[n+1]; `cap_tokens` = capacity of out_tokens (≥ total text bytes is always enough). */

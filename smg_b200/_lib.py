@@ -111,6 +111,7 @@ def load():
     sig("smgx_select_batch_request_text", st, vp, cp, vp, vp, u32, vp, vp, pp)
     sig("smgx_tokenizer_load_tiktoken_file", st, vp, cp, cp, P(cp), vp, u32, pp)
     sig("smgx_tokenizer_load_tiktoken", st, vp, cp, vp, vp, vp, u32, P(cp), vp, u32, pp)
+    sig("smgx_tokenizer_load_bpe_merges", st, vp, cp, vp, vp, vp, u32, vp, u32, C.c_int, P(cp), vp, u32, pp)
     sig("smgx_tokenize_batch", st, vp, cp, vp, vp, u32, vp, vp, u32, pp)
     sig("smgx_select_batch_text", st, vp, cp, vp, vp, u32, vp, vp, vp, vp, u32, pp)
     sig("smgx_select_batch_tokens", st, vp, cp, vp, vp, u32, vp, vp, pp)

@@ -160,6 +160,7 @@ struct BpeView {
     const SpecialTok* specials;
     uint32_t n_special;
     uint32_t special_first[8];    // bitmap of first bytes of special strings
+    uint32_t whole_piece;         // 1: a piece that is a vocabulary entry becomes that token without merging (tiktoken; HF ignore_merges)
     UnicodeView uni;
 };
 

@@ -1105,6 +1105,26 @@ smgx_status smgx_tokenizer_load_tiktoken(smgx_policy* p, const char* model_key, 
     });
 }
 
+smgx_status smgx_tokenizer_load_bpe_merges(smgx_policy* p, const char* model_key, const uint8_t* blob, const uint32_t* tok_offsets, const uint32_t* ids,
+                                           uint32_t n_tokens, const uint32_t* merges, uint32_t n_merges, int ignore_merges, const char* const* special_strs,
+                                           const uint32_t* special_ids, uint32_t n_special, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(blob); NONNULL(tok_offsets); NONNULL(ids);
+        SMGX_REQUIRE(n_merges == 0 || merges, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        bool dev = p->impl.cfg.device_id >= 0;
+        if (dev) p->impl.use_device();
+        std::vector<std::string> toks(n_tokens);
+        std::vector<uint32_t> id(ids, ids + n_tokens);
+        for (uint32_t i = 0; i < n_tokens; ++i) toks[i].assign((const char*)blob + tok_offsets[i], tok_offsets[i + 1] - tok_offsets[i]);
+        std::vector<std::pair<uint32_t, uint32_t>> mg(n_merges);
+        for (uint32_t i = 0; i < n_merges; ++i) mg[i] = {merges[2 * i], merges[2 * i + 1]};
+        ModelState& m = p->impl.model(model_key, true);
+        m.tokenizer.reset(new Tokenizer(toks, id, mg, ignore_merges != 0, collect_specials(special_strs, special_ids, n_special), dev));
+        return SMGX_SUCCESS;
+    });
+}
+
 // H2D the ragged text and tokenise it on `lane`; returns the device token buffers (valid until the lane is reused).
 static void tokenize_on_lane(Policy& P, ModelState& m, Lane& lane, const uint8_t* text, const uint32_t* offsets, uint32_t n,
                              uint32_t* max_text_len) {

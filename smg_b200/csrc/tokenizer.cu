@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) bpe_pieces_kernel(BpeView v, const uint8_
         const Piece pc = pieces[t];
         const uint32_t i = pc.start, plen = pc.len;
         uint32_t k, id;
-        if (piece_lookup(v, text + i, plen, id)) { tmp_ids[i] = id; k = 1; }
+        if (v.whole_piece && piece_lookup(v, text + i, plen, id)) { tmp_ids[i] = id; k = 1; }
         else if (plen <= 24) {
             uint32_t ids[24];
             uint64_t rk[24];
@@ -223,6 +223,16 @@ Tokenizer* Tokenizer::from_tiktoken_file(const std::string& path, const std::vec
 Tokenizer::Tokenizer(const std::vector<std::string>& tokens, const std::vector<uint32_t>& ranks,
                      const std::vector<std::pair<std::string, uint32_t>>& specials, bool device)
     : device_(device) {
+    build(tokens, ranks, nullptr, true, specials);
+}
+Tokenizer::Tokenizer(const std::vector<std::string>& tokens, const std::vector<uint32_t>& ids, const std::vector<std::pair<uint32_t, uint32_t>>& merges,
+                     bool ignore_merges, const std::vector<std::pair<std::string, uint32_t>>& specials, bool device)
+    : device_(device) {
+    build(tokens, ids, &merges, ignore_merges, specials);
+}
+
+void Tokenizer::build(const std::vector<std::string>& tokens, const std::vector<uint32_t>& ranks, const std::vector<std::pair<uint32_t, uint32_t>>* merges,
+                      bool whole_piece, const std::vector<std::pair<std::string, uint32_t>>& specials) {
     SMGX_REQUIRE(tokens.size() == ranks.size() && !tokens.empty(), "empty vocabulary");
     std::unordered_map<std::string, uint32_t> enc;
     enc.reserve(tokens.size() * 2);
@@ -254,26 +264,43 @@ Tokenizer::Tokenizer(const std::vector<std::string>& tokens, const std::vector<u
         while (pieces[h].hash) h = (h + 1) & pmask;
         pieces[h] = PieceSlot{hsh, kv.second, (uint32_t)kv.first.size(), off, 0};
     }
-    // pair table: every split of every token into two vocab entries (rank of the concatenation = tiktoken's merge priority)
-    std::vector<std::pair<uint64_t, uint32_t>> pair_list;
-    for (auto& kv : enc) {
-        const std::string& t = kv.first;
-        for (size_t k = 1; k < t.size(); ++k) {
-            auto l = enc.find(t.substr(0, k));
-            if (l == enc.end()) continue;
-            auto r = enc.find(t.substr(k));
-            if (r == enc.end()) continue;
-            pair_list.push_back({((uint64_t)l->second << 32) | r->second, kv.second});
+    // pair table (left id, right id) → (priority, merged id)
+    struct PairRec { uint64_t key; uint32_t rank, id; };
+    std::vector<PairRec> pair_list;
+    if (!merges) {
+        // tiktoken: every split of every token into two vocab entries (rank of the concatenation = the merge priority)
+        for (auto& kv : enc) {
+            const std::string& t = kv.first;
+            for (size_t k = 1; k < t.size(); ++k) {
+                auto l = enc.find(t.substr(0, k));
+                if (l == enc.end()) continue;
+                auto r = enc.find(t.substr(k));
+                if (r == enc.end()) continue;
+                pair_list.push_back({((uint64_t)l->second << 32) | r->second, kv.second, kv.second});
+            }
+        }
+    } else {
+        // HuggingFace BPE: only the listed pairs merge, in list order; the merged token is the concatenation (models/bpe/model.rs)
+        std::unordered_map<uint32_t, const std::string*> by_id;
+        for (auto& kv : enc) by_id[kv.second] = &kv.first;
+        for (size_t k = 0; k < merges->size(); ++k) {
+            auto l = by_id.find((*merges)[k].first), r = by_id.find((*merges)[k].second);
+            if (l == by_id.end() || r == by_id.end()) throw Error(SMGX_TOKENIZATION_ERROR, "merge refers to an unknown token id");
+            auto t = enc.find(*l->second + *r->second);
+            if (t == enc.end()) throw Error(SMGX_TOKENIZATION_ERROR, "merge result is not in the vocabulary");
+            pair_list.push_back({((uint64_t)l->first << 32) | r->first, (uint32_t)k, t->second});
         }
     }
     n_pairs_ = (uint32_t)pair_list.size();
     std::vector<PairSlot> pairs(pow2_at_least(pair_list.size() * 2 + 2), PairSlot{kPairEmpty, kRankMax, 0});
     uint32_t qmask = (uint32_t)pairs.size() - 1;
     for (auto& pr : pair_list) {
-        uint32_t h = (uint32_t)(mix64(pr.first) >> 32) & qmask;
-        while (pairs[h].key != kPairEmpty && pairs[h].key != pr.first) h = (h + 1) & qmask;
-        pairs[h] = PairSlot{pr.first, pr.second, pr.second};
+        uint32_t h = (uint32_t)(mix64(pr.key) >> 32) & qmask;
+        while (pairs[h].key != kPairEmpty && pairs[h].key != pr.key) h = (h + 1) & qmask;
+        if (pairs[h].key == pr.key && pairs[h].rank <= pr.rank) continue;   // a repeated pair keeps its first (best) priority
+        pairs[h] = PairSlot{pr.key, pr.rank, pr.id};
     }
+    dview_.whole_piece = whole_piece ? 1u : 0u;
     // specials
     std::vector<SpecialTok> sp;
     uint32_t first_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -16,6 +16,10 @@ public:
     // tokens[i] = bytes of the vocab entry with rank/id ranks[i]; specials = (string, id)
     Tokenizer(const std::vector<std::string>& tokens, const std::vector<uint32_t>& ranks,
               const std::vector<std::pair<std::string, uint32_t>>& specials, bool device);
+    // HuggingFace `tokenizers` BPE (byte-level): merge priority = position in `merges` (pairs of ids), only listed pairs merge;
+    // ignore_merges = look the whole piece up in the vocabulary first (models::bpe ignore_merges, Llama 3).
+    Tokenizer(const std::vector<std::string>& tokens, const std::vector<uint32_t>& ids, const std::vector<std::pair<uint32_t, uint32_t>>& merges,
+              bool ignore_merges, const std::vector<std::pair<std::string, uint32_t>>& specials, bool device);
     ~Tokenizer();
     static Tokenizer* from_tiktoken_file(const std::string& path, const std::vector<std::pair<std::string, uint32_t>>& specials, bool device);
 
@@ -34,6 +38,8 @@ public:
                       uint32_t* d_tokens, uint32_t* d_tok_offsets, Scratch& sc, cudaStream_t stream, uint64_t* launches) const;
 
 private:
+    void build(const std::vector<std::string>& tokens, const std::vector<uint32_t>& ranks, const std::vector<std::pair<uint32_t, uint32_t>>* merges,
+               bool whole_piece, const std::vector<std::pair<std::string, uint32_t>>& specials);
     BpeView dview_{};
     uint32_t vocab_size_ = 0, n_pairs_ = 0;
     bool device_ = false;

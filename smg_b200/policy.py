@@ -381,6 +381,67 @@ class TiktokenTokenizer:
         return self.encode_batch([text])[0]
 
 
+LLAMA3_SPLIT_PATTERN = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+")
+
+
+def _byte_level_decoder():
+    """Inverse of the GPT-2 bytes_to_unicode table used by `tokenizers`' ByteLevel pre-tokenizer (pre_tokenizers/byte_level.rs)."""
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(ord("\xa1"), ord("\xac") + 1)) + list(range(ord("\xae"), ord("\xff") + 1))
+    cs = bs[:]
+    n = 0
+    for b in range(256):
+        if b not in bs:
+            bs.append(b)
+            cs.append(256 + n)
+            n += 1
+    return {chr(c): b for b, c in zip(bs, cs)}
+
+
+class HuggingFaceTokenizer(TiktokenTokenizer):
+    """tokenizer::HuggingFaceTokenizer (crates/tokenizer/src/huggingface.rs) for the byte-level BPE family the GPU path covers:
+    tokenizer.json with no normalizer, Split(Llama-3 / cl100k regex, Isolated) + ByteLevel(use_regex=False), model BPE without
+    dropout / unk / byte_fallback.  Anything else is refused loudly — there is no CPU tokenizer behind this."""
+
+    def __init__(self, handle: _Handle, model: str, path: str):   # noqa: D401 — does not call the tiktoken loader
+        import json
+        self.h, self.model = handle, model.encode()
+        j = json.load(open(path, encoding="utf-8"))
+        mdl = j.get("model") or {}
+        if mdl.get("type") != "BPE" or mdl.get("dropout") or mdl.get("unk_token") or mdl.get("byte_fallback") or \
+                mdl.get("continuing_subword_prefix") or mdl.get("end_of_word_suffix"):
+            raise ValueError("tokenizer.json: only plain byte-level BPE models are supported on the GPU path")
+        if j.get("normalizer") is not None:
+            raise ValueError("tokenizer.json: normalizers are not supported on the GPU path")
+        pre = j.get("pre_tokenizer") or {}
+        steps = pre.get("pretokenizers", [pre]) if pre.get("type") == "Sequence" else [pre]
+        kinds = [s.get("type") for s in steps]
+        split = [s for s in steps if s.get("type") == "Split"]
+        bl = [s for s in steps if s.get("type") == "ByteLevel"]
+        if kinds != ["Split", "ByteLevel"] or split[0].get("pattern", {}).get("Regex") != LLAMA3_SPLIT_PATTERN or \
+                str(split[0].get("behavior")).lower() != "isolated" or split[0].get("invert") or bl[0].get("use_regex") or bl[0].get("add_prefix_space"):
+            raise ValueError("tokenizer.json: pre_tokenizer must be Split(Llama-3 regex, Isolated) + ByteLevel(use_regex=False)")
+        dec = _byte_level_decoder()
+        vocab = mdl["vocab"]
+        toks = [bytes(dec[c] for c in s) for s in vocab]
+        ids = _u32(list(vocab.values()))
+        merges = []
+        for mg in mdl.get("merges", []):
+            a, b = mg.split(" ") if isinstance(mg, str) else mg
+            merges += [vocab[a], vocab[b]]
+        offs = np.zeros(len(toks) + 1, dtype=np.uint32)
+        np.cumsum([len(t) for t in toks], out=offs[1:])
+        blob = np.frombuffer(b"".join(toks), dtype=np.uint8).copy()
+        added = [(a["content"], a["id"]) for a in j.get("added_tokens", [])]
+        for a in j.get("added_tokens", []):
+            if a.get("lstrip") or a.get("rstrip") or a.get("single_word") or a.get("normalized"):
+                raise ValueError("tokenizer.json: added tokens with lstrip / rstrip / single_word / normalized are not supported")
+        strs = (C.c_char_p * max(len(added), 1))(*[k.encode() for k, _ in added]) if added else None
+        sp_ids = _u32([v for _, v in added])
+        mg = _u32(merges)
+        self.h.call("smgx_tokenizer_load_bpe_merges", self.model, _p(blob), _p(offs), _p(ids), len(toks), _p(mg), len(merges) // 2,
+                    1 if mdl.get("ignore_merges") else 0, strs, _p(sp_ids), len(added))
+
+
 TREE_BATCH_MODES = {"sequential": 0, "snapshot": 1}   # smgx_tree_batch_mode (include/smgx.h)
 
 
@@ -537,6 +598,9 @@ class CacheAwarePolicy:
     # -- tokenizer + text-in pick (the whole hot path on the device) ------------------------------------------------
     def load_tiktoken_tokenizer(self, path: str, special_tokens=None, model: str = UNKNOWN_MODEL_ID) -> TiktokenTokenizer:
         return TiktokenTokenizer(self._h, model, path, special_tokens)
+
+    def load_hf_tokenizer(self, path: str, model: str = UNKNOWN_MODEL_ID) -> HuggingFaceTokenizer:
+        return HuggingFaceTokenizer(self._h, model, path)
 
     def select_worker_batch_text(self, workers: Sequence[BasicWorker], texts, want_tokens: bool = True):
         """Chat-template-rendered texts → (worker_idx, info, token lists): tokenise on the GPU, then the cache-aware pick,

@@ -103,3 +103,46 @@ def test_text_in_pick_equals_tokens_in_pick_and_oracle():
     want, br, _, _ = op.select_batch_tokens(flat, offs)
     assert np.array_equal(idx_text, want)
     assert (np.asarray(br) == 2).sum() > 100      # most requests hit a cached system prompt
+
+
+# ---- HuggingFace tokenizer.json (byte-level BPE, Llama-3-style pre-tokenizer) -------------------------------------------------
+@pytest.mark.parametrize("fixture", ["hf_llama3_style_tokenizer.json", "hf_plain_bpe_tokenizer.json"])
+def test_hf_tokenizer_json_matches_tokenizers_crate(fixture):
+    """tests/golden/hf_bpe_vectors.json was produced by the Python bindings of the `tokenizers` crate (the engine behind the
+    reference's HuggingFaceTokenizer, huggingface.rs:310-316) from the committed tokenizer.json fixtures — one with
+    ignore_merges (Llama 3), one without."""
+    from smg_b200 import CacheAwareConfig, CacheAwarePolicy
+    g = json.load(open(os.path.join(GOLD, "hf_bpe_vectors.json")))
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0))
+    tok = pol.load_hf_tokenizer(os.path.join(GOLD, fixture))
+    got = tok.encode_batch(g["texts"])
+    for t, ids, want in zip(g["texts"], got, g["ids"][fixture]):
+        assert ids == want, repr(t[:80])
+
+
+def test_hf_tokenizer_live_tokenizers_random_texts():
+    tokenizers = pytest.importorskip("tokenizers")
+    from smg_b200 import CacheAwareConfig, CacheAwarePolicy
+    path = os.path.join(GOLD, "hf_llama3_style_tokenizer.json")
+    ref = tokenizers.Tokenizer.from_file(path)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0))
+    tok = pol.load_hf_tokenizer(path)
+    rng = random.Random(9)
+    alphabet = "abcdefghij the quick XYZ 0123456789\n\t\r'.,!?-_(){}[]<|>eot_idbegin_of_text" + "éßüï你好世界\U0001f44b\U0001f30d ١٢٣"
+    texts = ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, 400))) for _ in range(400)]
+    texts += ["<|begin_of_text|>" + "hello world " * 50 + "<|eot_id|>", "don't DON'T I'LL we'Ve 'S", "   \n\n  \n x  \n", "12345678901234567890"]
+    got = tok.encode_batch(texts)
+    want = [e.ids for e in ref.encode_batch(texts, add_special_tokens=False)]
+    for t, a, b in zip(texts, got, want):
+        assert a == b, repr(t[:80])
+
+
+def test_hf_loader_refuses_unsupported_tokenizer_json(tmp_path):
+    from smg_b200 import CacheAwareConfig, CacheAwarePolicy
+    j = json.load(open(os.path.join(GOLD, "hf_llama3_style_tokenizer.json")))
+    j["normalizer"] = {"type": "NFC"}
+    p = tmp_path / "tok.json"
+    p.write_text(json.dumps(j))
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0))
+    with pytest.raises(ValueError):
+        pol.load_hf_tokenizer(str(p))
