@@ -107,7 +107,7 @@ public:
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
                 l.d_path_tenant.release(); l.d_fill.release(); l.d_chunk_start.release(); l.d_cv.release(); l.d_hashes.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
-                l.tok_scratch.pieces.release(); l.tok_scratch.n_pieces.release();
+                l.tok_scratch.pieces.release(); l.tok_scratch.n_pieces.release(); l.tok_scratch.miss.release();
                 if (l.done) cudaEventDestroy(l.done);
                 if (l.t0) cudaEventDestroy(l.t0);
                 if (l.t1) cudaEventDestroy(l.t1);

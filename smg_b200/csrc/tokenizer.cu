@@ -85,22 +85,39 @@ __device__ __forceinline__ bool is_anchor(const uint8_t* s, uint32_t i, uint32_t
 __global__ void __launch_bounds__(256) pretokenize_kernel(BpeView v, const uint8_t* __restrict__ text, const uint32_t* __restrict__ offsets,
                                                           uint8_t* __restrict__ flags, Piece* __restrict__ pieces, uint32_t* __restrict__ n_pieces) {
     __shared__ Piece s_list[320];
+    __shared__ uint32_t s_anchor[256];
+    __shared__ uint32_t s_wcnt[8];
     __shared__ uint32_t s_count, s_base;
     if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
     const uint32_t r = blockIdx.y, beg = offsets[r], rend = offsets[r + 1];
     const uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rend && (text[i] & 0xC0) != 0x80 && flags[i] < 2 && is_anchor(text, i, beg, flags, v.uni)) {
-        // replay the regex from this anchor up to the next one; a special's first byte (flags == 2) is the end of the slice
-        uint32_t p = i;
-        for (;;) {
-            flags[p] = 1;
-            const uint32_t q = next_piece_cl100k(text, p, rend, v.uni, flags);
-            const uint32_t slot = atomicAdd(&s_count, 1u);
-            if (slot < 320) s_list[slot] = Piece{p, q - p, r};
-            else { uint32_t g = atomicAdd(n_pieces, 1u); pieces[g] = Piece{p, q - p, r}; }   // overflow: straight to the global list
-            if (q >= rend || flags[q] == 2 || is_anchor(text, q, beg, flags, v.uni)) break;
-            p = q;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // phase 1 (every thread, one byte each): is this byte an anchor?  Anchors are then packed densely, so that phase 2 — the
+    // serial regex replay — runs with full warps instead of one live lane in six.
+    const bool anchor = i < rend && (text[i] & 0xC0) != 0x80 && flags[i] < 2 && is_anchor(text, i, beg, flags, v.uni);
+    const unsigned bal = __ballot_sync(0xffffffffu, anchor);
+    if (lane == 0) s_wcnt[wid] = (uint32_t)__popc(bal);
+    __syncthreads();
+    uint32_t before = 0, n_anchor = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = s_wcnt[w]; if (w < wid) before += c; n_anchor += c; }
+    if (anchor) s_anchor[before + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    // phase 2: thread k replays the regex from the k-th anchor up to the next one; a special's first byte (flags == 2) ends the
+    // slice.  The warp iterates in lockstep (one piece per live lane and round).
+    if ((uint32_t)(wid * 32) < n_anchor) {
+        bool live = threadIdx.x < n_anchor;
+        uint32_t p = live ? s_anchor[threadIdx.x] : 0;
+        while (__any_sync(0xffffffffu, live)) {
+            if (live) {
+                flags[p] = 1;
+                const uint32_t q = next_piece_cl100k(text, p, rend, v.uni, flags);
+                const uint32_t slot = atomicAdd(&s_count, 1u);
+                if (slot < 320) s_list[slot] = Piece{p, q - p, r};
+                else { const uint32_t g = atomicAdd(n_pieces, 1u); pieces[g] = Piece{p, q - p, r}; }   // overflow: straight to the global list
+                if (q >= rend || flags[q] == 2 || is_anchor(text, q, beg, flags, v.uni)) live = false;
+                else p = q;
+            }
         }
     }
     __syncthreads();
@@ -110,26 +127,186 @@ __global__ void __launch_bounds__(256) pretokenize_kernel(BpeView v, const uint8
     for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) pieces[s_base + k] = s_list[k];
 }
 
-// K1b: one thread per piece (dense list).  Whole-piece vocabulary hit → one token; otherwise tiktoken's byte-pair merge —
-// in thread-local arrays for pieces of ≤ 24 bytes, in place in the global scratch beyond that.  Unused slots of the piece
-// are set INVALID for the compaction.
-__global__ void __launch_bounds__(256) bpe_pieces_kernel(BpeView v, const uint8_t* __restrict__ text, const Piece* __restrict__ pieces,
-                                                         const uint32_t* __restrict__ n_pieces, uint32_t* __restrict__ tmp_ids,
-                                                         uint64_t* __restrict__ tmp_rk, uint32_t* __restrict__ totals) {
-    const uint32_t np = *n_pieces;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) {
-        const Piece pc = pieces[t];
+// K1b: BPE over the dense piece list, three kernels so that every one of them runs on full warps:
+//   bpe_lookup_kernel   thread per piece: whole-piece vocabulary hit → one token (most pieces of natural text); misses are appended to
+//                       two lists — pieces of ≤ kSmemSyms bytes and longer ones (warp-aggregated atomics)
+//   bpe_merge_kernel    thread per short miss: tiktoken's byte-pair merge with symbols and pair ranks in shared memory (column per
+//                       thread); the warp runs the merge loop in lockstep, one merge per live lane and round
+//   bpe_long_kernel     warp per long miss (indentation runs, rules of dashes, URLs …): up to 32 bytes one symbol per lane, the
+//                       leftmost-lowest-rank pair found with one redux.sync per merge, the tail shifted down by shuffles; up to 256
+//                       bytes a linked list in shared memory with a strided minimum scan; beyond that (very rare) lane 0 merges in
+//                       place in the global scratch
+// Unused slots of a piece are set INVALID for the compaction.  counters: [0] pieces, [1] short misses, [2] long misses.
+constexpr uint32_t kSmemSyms = 15;
+constexpr uint32_t kLongSyms = 256;   // longest piece the warp-per-piece kernel keeps in shared memory
+__global__ void __launch_bounds__(256) bpe_lookup_kernel(BpeView v, const uint8_t* __restrict__ text, const Piece* __restrict__ pieces,
+                                                         uint32_t* __restrict__ counters, uint32_t* __restrict__ tmp_ids, uint32_t* __restrict__ totals,
+                                                         uint32_t* __restrict__ miss_short, uint32_t* __restrict__ miss_long) {
+    const uint32_t np = counters[0];
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < np; t0 += stride) {
+        const uint32_t t = t0 + threadIdx.x;
+        int kind = 0;   // 1 short miss, 2 long miss
+        if (t < np) {
+            const Piece pc = pieces[t];
+            uint32_t id;
+            if (v.whole_piece && piece_lookup(v, text + pc.start, pc.len, id)) {
+                tmp_ids[pc.start] = id;
+                for (uint32_t j = pc.start + 1; j < pc.start + pc.len; ++j) tmp_ids[j] = kInvalidTok;
+                atomicAdd(&totals[pc.req], 1u);
+            } else kind = pc.len <= kSmemSyms ? 1 : 2;
+        }
+#pragma unroll
+        for (int k = 1; k <= 2; ++k) {
+            const unsigned bal = __ballot_sync(0xffffffffu, kind == k);
+            if (!bal) continue;
+            uint32_t base = 0;
+            if (lane == __ffs((int)bal) - 1) base = atomicAdd(&counters[k], (uint32_t)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs((int)bal) - 1);
+            if (kind == k) (k == 1 ? miss_short : miss_long)[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bpe_merge_kernel(BpeView v, const uint8_t* __restrict__ text, const Piece* __restrict__ pieces,
+                                                        const uint32_t* __restrict__ counters, const uint32_t* __restrict__ miss_short,
+                                                        uint32_t* __restrict__ tmp_ids, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_id[kSmemSyms][256];     // symbol ids
+    __shared__ uint32_t s_rank[kSmemSyms][256];   // rank of the pair (i, i+1); kRankMax = no merge
+    __shared__ uint32_t s_mid[kSmemSyms][256];    // id that pair merges into
+    const uint32_t n = counters[1], tid = threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < n; t0 += stride) {   // t0 is CTA-uniform: whole warps stay in the loop together
+        const bool valid = t0 + tid < n;
+        Piece pc{0, 0, 0};
+        if (valid) pc = pieces[miss_short[t0 + tid]];
         const uint32_t i = pc.start, plen = pc.len;
-        uint32_t k, id;
-        if (v.whole_piece && piece_lookup(v, text + i, plen, id)) { tmp_ids[i] = id; k = 1; }
-        else if (plen <= 24) {
-            uint32_t ids[24];
-            uint64_t rk[24];
-            k = byte_pair_merge(v, text + i, plen, ids, rk);
-            for (uint32_t j = 0; j < k; ++j) tmp_ids[i + j] = ids[j];
-        } else k = byte_pair_merge(v, text + i, plen, tmp_ids + i, tmp_rk + i);
-        for (uint32_t j = i + k; j < i + plen; ++j) tmp_ids[j] = kInvalidTok;
-        atomicAdd(&totals[pc.req], k);
+        uint32_t m = plen;
+        if (valid) {
+            for (uint32_t j = 0; j < plen; ++j) s_id[j][tid] = v.byte_token[text[i + j]];
+            for (uint32_t j = 0; j + 1 < plen; ++j) {
+                const uint64_t pr = pair_lookup(v, s_id[j][tid], s_id[j + 1][tid]);
+                s_rank[j][tid] = (uint32_t)(pr >> 32); s_mid[j][tid] = (uint32_t)pr;
+            }
+        }
+        bool merging = valid && plen >= 2;
+        while (__any_sync(0xffffffffu, merging)) {
+            if (merging) {
+                uint32_t best = kRankMax, bi = 0;
+                for (uint32_t j = 0; j + 1 < m; ++j) { const uint32_t rk = s_rank[j][tid]; if (rk < best) { best = rk; bi = j; } }   // leftmost minimum
+                if (best == kRankMax) merging = false;
+                else {
+                    s_id[bi][tid] = s_mid[bi][tid];
+                    for (uint32_t j = bi + 1; j + 1 < m; ++j) { s_id[j][tid] = s_id[j + 1][tid]; s_rank[j][tid] = s_rank[j + 1][tid]; s_mid[j][tid] = s_mid[j + 1][tid]; }
+                    --m;
+                    if (bi + 1 < m) { const uint64_t pr = pair_lookup(v, s_id[bi][tid], s_id[bi + 1][tid]); s_rank[bi][tid] = (uint32_t)(pr >> 32); s_mid[bi][tid] = (uint32_t)pr; }
+                    else s_rank[bi][tid] = kRankMax;
+                    if (bi > 0) { const uint64_t pr = pair_lookup(v, s_id[bi - 1][tid], s_id[bi][tid]); s_rank[bi - 1][tid] = (uint32_t)(pr >> 32); s_mid[bi - 1][tid] = (uint32_t)pr; }
+                    if (m < 2) merging = false;
+                }
+            }
+        }
+        if (valid) {
+            for (uint32_t j = 0; j < m; ++j) tmp_ids[i + j] = s_id[j][tid];
+            for (uint32_t j = i + m; j < i + plen; ++j) tmp_ids[j] = kInvalidTok;
+            atomicAdd(&totals[pc.req], m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bpe_long_kernel(BpeView v, const uint8_t* __restrict__ text, const Piece* __restrict__ pieces,
+                                                       const uint32_t* __restrict__ counters, const uint32_t* __restrict__ miss_long,
+                                                       uint32_t* __restrict__ tmp_ids, uint64_t* __restrict__ tmp_rk, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_id[8][kLongSyms], s_rank[8][kLongSyms], s_mid[8][kLongSyms];
+    __shared__ uint16_t s_nxt[8][kLongSyms], s_prv[8][kLongSyms];
+    const uint32_t n = counters[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t nw = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nw) {
+        const Piece pc = pieces[miss_long[k]];
+        const uint32_t i = pc.start, plen = pc.len;
+        uint32_t m;
+        if (plen <= 32) {
+            m = plen;
+            uint32_t id = (uint32_t)lane < plen ? v.byte_token[text[i + lane]] : 0;
+            uint32_t nid = __shfl_down_sync(0xffffffffu, id, 1);
+            uint32_t rank = kRankMax, mid = 0;
+            if ((uint32_t)lane + 1 < m) { const uint64_t pr = pair_lookup(v, id, nid); rank = (uint32_t)(pr >> 32); mid = (uint32_t)pr; }
+            for (;;) {
+                // ranks are vocabulary positions (< 2^27), so rank * 32 + lane orders by rank, then by position
+                const uint32_t key = ((uint32_t)lane + 1 < m && rank != kRankMax) ? ((rank << 5) | (uint32_t)lane) : 0xFFFFFFFFu;
+                const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+                if (kmin == 0xFFFFFFFFu) break;
+                const int bi = (int)(kmin & 31u);
+                if (lane == bi) id = mid;
+                const uint32_t id_dn = __shfl_down_sync(0xffffffffu, id, 1), rank_dn = __shfl_down_sync(0xffffffffu, rank, 1), mid_dn = __shfl_down_sync(0xffffffffu, mid, 1);
+                if (lane > bi) { id = id_dn; rank = rank_dn; mid = mid_dn; }
+                --m;
+                nid = __shfl_down_sync(0xffffffffu, id, 1);
+                if (lane == bi || lane == bi - 1) {
+                    rank = kRankMax;
+                    if ((uint32_t)lane + 1 < m) { const uint64_t pr = pair_lookup(v, id, nid); rank = (uint32_t)(pr >> 32); mid = (uint32_t)pr; }
+                }
+            }
+            if ((uint32_t)lane < plen) tmp_ids[i + lane] = (uint32_t)lane < m ? id : kInvalidTok;
+        } else if (plen <= kLongSyms) {
+            // 33 … kLongSyms bytes: symbols stay in place in shared memory, linked by next/prev indices (list order = index order, so
+            // "leftmost" = smallest index); a merge unlinks one symbol and re-ranks two pairs; the minimum is a strided scan + 2 redux
+            uint32_t* w_id = s_id[wid]; uint32_t* w_rank = s_rank[wid]; uint32_t* w_mid = s_mid[wid];
+            uint16_t* w_nxt = s_nxt[wid]; uint16_t* w_prv = s_prv[wid];
+            for (uint32_t j = lane; j < plen; j += 32) { w_id[j] = v.byte_token[text[i + j]]; w_nxt[j] = (uint16_t)(j + 1); w_prv[j] = (uint16_t)(j ? j - 1 : 0xFFFF); }
+            __syncwarp();
+            for (uint32_t j = lane; j < plen; j += 32) {
+                uint32_t rk = kRankMax, md = 0;
+                if (j + 1 < plen) { const uint64_t pr = pair_lookup(v, w_id[j], w_id[j + 1]); rk = (uint32_t)(pr >> 32); md = (uint32_t)pr; }
+                w_rank[j] = rk; w_mid[j] = md;
+            }
+            __syncwarp();
+            m = plen;
+            for (;;) {
+                uint32_t best = kRankMax, bpos = 0xFFFFFFFFu;
+                for (uint32_t j = lane; j < plen; j += 32) { const uint32_t rk = w_rank[j]; if (rk < best) { best = rk; bpos = j; } }   // ascending j: leftmost per lane
+                const uint32_t rmin = __reduce_min_sync(0xffffffffu, best);
+                if (rmin == kRankMax) break;
+                const uint32_t b = __reduce_min_sync(0xffffffffu, best == rmin ? bpos : 0xFFFFFFFFu);
+                const uint32_t c = w_nxt[b], d = w_nxt[c], a = w_prv[b];
+                __syncwarp();
+                if (lane == 0) {
+                    w_id[b] = w_mid[b]; w_nxt[b] = (uint16_t)d; w_rank[c] = kRankMax; w_id[c] = kInvalidTok;
+                    if (d < plen) w_prv[d] = (uint16_t)b;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    uint32_t rk = kRankMax, md = 0;
+                    if (d < plen) { const uint64_t pr = pair_lookup(v, w_id[b], w_id[d]); rk = (uint32_t)(pr >> 32); md = (uint32_t)pr; }
+                    w_rank[b] = rk; w_mid[b] = md;
+                } else if (lane == 1 && a != 0xFFFF) {
+                    const uint64_t pr = pair_lookup(v, w_id[a], w_id[b]);
+                    w_rank[a] = (uint32_t)(pr >> 32); w_mid[a] = (uint32_t)pr;
+                }
+                --m;
+                __syncwarp();
+            }
+            uint32_t written = 0;   // compact the surviving symbols to the front of the piece's slots
+            for (uint32_t base = 0; base < plen; base += 32) {
+                const uint32_t j = base + lane;
+                const bool alive = j < plen && w_id[j] != kInvalidTok;
+                const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                if (alive) tmp_ids[i + written + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = w_id[j];
+                written += (uint32_t)__popc(bal);
+            }
+            for (uint32_t j = written + lane; j < plen; j += 32) tmp_ids[i + j] = kInvalidTok;
+            __syncwarp();
+        } else {
+            m = 0;
+            if (lane == 0) {
+                m = byte_pair_merge(v, text + i, plen, tmp_ids + i, tmp_rk + i);
+                for (uint32_t j = i + m; j < i + plen; ++j) tmp_ids[j] = kInvalidTok;
+            }
+            m = __shfl_sync(0xffffffffu, m, 0);
+        }
+        if (lane == 0) atomicAdd(&totals[pc.req], m);
     }
 }
 
@@ -245,6 +422,7 @@ void Tokenizer::build(const std::vector<std::string>& tokens, const std::vector<
     }
     for (auto& sp : specials) max_id = std::max(max_id, sp.second);
     vocab_size_ = max_id + 1;
+    SMGX_REQUIRE(vocab_size_ < (1u << 27), "vocabulary too large (merge ranks are packed into 27 bits)");
 
     std::vector<uint32_t> byte_token(256);
     for (int b = 0; b < 256; ++b) {
@@ -353,6 +531,7 @@ void Tokenizer::encode_batch(const uint8_t* d_text, const uint32_t* d_offsets, u
     sc.totals.reserve((size_t)n * 4);
     sc.pieces.reserve((size_t)std::max<uint32_t>(total_bytes - first_byte, 1) * sizeof(Piece));
     sc.n_pieces.reserve(16);
+    sc.miss.reserve(((size_t)std::max<uint32_t>(total_bytes - first_byte, 1) + 1) * 8);
     if (total_bytes) {
         SMGX_CUDA(cudaMemsetAsync(sc.flags.ptr, 0, total_bytes, stream));
     }
@@ -370,17 +549,22 @@ void Tokenizer::encode_batch(const uint8_t* d_text, const uint32_t* d_offsets, u
         } else {
             SMGX_CUDA(cudaMemsetAsync(sc.totals.ptr, 0, (size_t)n * 4, stream));
         }
-        SMGX_CUDA(cudaMemsetAsync(sc.n_pieces.ptr, 0, 4, stream));
+        SMGX_CUDA(cudaMemsetAsync(sc.n_pieces.ptr, 0, 16, stream));
         if (max_len) {
             pretokenize_kernel<<<grid2, 256, 0, stream>>>(dview_, d_text, d_offsets, sc.flags.as<uint8_t>(), sc.pieces.as<Piece>(), sc.n_pieces.as<uint32_t>());
             SMGX_CUDA(cudaGetLastError());
             ++*launches;
-            // one thread per piece; the piece count lives on the device, so size the grid for the worst case the text allows
-            unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)(total_bytes - first_byte) / 2 + 255) / 256 + 1, 148ull * 16);
-            bpe_pieces_kernel<<<grid, 256, 0, stream>>>(dview_, d_text, sc.pieces.as<Piece>(), sc.n_pieces.as<uint32_t>(), sc.tmp_ids.as<uint32_t>(),
-                                                      sc.tmp_rk.as<uint64_t>(), sc.totals.as<uint32_t>());
+            // the piece count lives on the device, so the grids are sized for the worst case the text allows and stride over the lists
+            const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)(total_bytes - first_byte) / 2 + 255) / 256 + 1, 148ull * 16);
+            uint32_t* cnt = sc.n_pieces.as<uint32_t>();
+            uint32_t* miss_short = sc.miss.as<uint32_t>();
+            uint32_t* miss_long = miss_short + (total_bytes - first_byte) + 1;
+            bpe_lookup_kernel<<<grid, 256, 0, stream>>>(dview_, d_text, sc.pieces.as<Piece>(), cnt, sc.tmp_ids.as<uint32_t>(), sc.totals.as<uint32_t>(), miss_short, miss_long);
+            bpe_merge_kernel<<<std::min(grid, 148u * 4), 256, 0, stream>>>(dview_, d_text, sc.pieces.as<Piece>(), cnt, miss_short, sc.tmp_ids.as<uint32_t>(), sc.totals.as<uint32_t>());
+            bpe_long_kernel<<<std::min(grid, 148u * 8), 256, 0, stream>>>(dview_, d_text, sc.pieces.as<Piece>(), cnt, miss_long, sc.tmp_ids.as<uint32_t>(),
+                                                                    sc.tmp_rk.as<uint64_t>(), sc.totals.as<uint32_t>());
             SMGX_CUDA(cudaGetLastError());
-            ++*launches;
+            *launches += 3;
         }
     }
     scan_counts_kernel<<<1, 1024, 0, stream>>>(sc.totals.as<uint32_t>(), n, d_tok_offsets);

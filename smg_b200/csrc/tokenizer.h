@@ -28,7 +28,7 @@ public:
     uint32_t n_pairs() const { return n_pairs_; }
 
     // Scratch needed for a batch of `total_bytes` of text and `n` requests.
-    struct Scratch { DevBuf flags, tmp_ids, tmp_rk, totals, pieces, n_pieces; };
+    struct Scratch { DevBuf flags, tmp_ids, tmp_rk, totals, pieces, n_pieces, miss; };
 
     // Enqueue pre-tokenise + BPE + compaction on `stream`.
     //   d_text/d_offsets (n+1): ragged UTF-8; d_tokens: capacity ≥ total_bytes u32; d_tok_offsets: n+1 u32 (written).

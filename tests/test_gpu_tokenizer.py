@@ -146,3 +146,19 @@ def test_hf_loader_refuses_unsupported_tokenizer_json(tmp_path):
     pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0))
     with pytest.raises(ValueError):
         pol.load_hf_tokenizer(str(p))
+
+
+def test_piece_length_classes_vs_oracle():
+    """Pieces of every length class take a different merge kernel (≤ 15 bytes: shared-memory columns; 16-32: one symbol per lane;
+    33-256: linked list in shared memory; longer: in place in the global scratch) — all must agree with the oracle."""
+    pol, tok, g = _policy_and_tok()
+    ranks = bpe_ref.load_tiktoken_bpe(VOCAB)
+    enc = bpe_ref.CoreBPE(ranks, g["specials"])
+    rng = random.Random(17)
+    texts = []
+    for k in list(range(1, 70)) + [100, 127, 128, 129, 200, 255, 256, 257, 300, 1000]:
+        texts += [" " * k + "x", "-" * k, "ab" * k, "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(k)),
+                  "".join(rng.choice("éßü你好") for _ in range(k)), "=" * k + "\n" * (k % 5), "a" * k + " " + "b" * k]
+    got = tok.encode_batch(texts)
+    for t, ids in zip(texts, got):
+        assert ids == enc.encode_with_special_tokens(t), (len(t), repr(t[:40]))
