@@ -267,6 +267,10 @@ smgx_status smgx_submit_tokens(smgx_policy* p, const char* model_key, const uint
                                int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err);
 smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err);
 
+/* Same for rendered text (smgx_select_batch_text without the token read-back): H2D, GPU tokenize, pick and D2H ride one lane. */
+smgx_status smgx_submit_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                             int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err);
+
 /* Device-resident form (inputs already in HBM; used by bench.py's kernel-only leg and by callers that tokenize on
  * the GPU).  Pointers are device pointers on the policy's device; asynchronous on the policy's stream `lane`
  * (0 ≤ lane < smgx_pipeline_depth()).  `max_request_tokens` bounds the longest request of the batch (sizes the per-warp

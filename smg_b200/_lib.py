@@ -118,6 +118,7 @@ def load():
     sig("smgx_pipeline_depth", u32, vp)
     sig("smgx_submit_tokens", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)
     sig("smgx_wait", st, vp, u64, pp)
+    sig("smgx_submit_text", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)
     sig("smgx_select_batch_tokens_device", st, vp, cp, u32, vp, vp, u32, u32, vp, vp, pp)
     sig("smgx_select_many_tokens_device", st, vp, cp, u32, vp, vp, vp, u32, vp, pp)
     sig("smgx_shard_candidates_device", st, vp, cp, u32, vp, vp, u32, u32, vp, vp, pp)

@@ -1418,6 +1418,54 @@ smgx_status smgx_select_batch_request_text(smgx_policy* p, const char* model_key
     });
 }
 
+// Pipelined text-in pick: H2D of the text, tokenize, hash, search and the D2H of the picks are enqueued on one lane and the call
+// returns; smgx_wait(ticket) completes it.  Event-driven mode only runs asynchronously — the tree modes need the tokens on the host
+// for their updater and complete inside the call (the ticket is then already done).
+smgx_status smgx_submit_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                             int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_ticket);
+        SMGX_REQUIRE(n == 0 || (text && offsets && out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(n <= P.cfg.max_batch, "batch larger than max_batch");
+        ModelState& m = P.model(model_key, false);
+        Lane& lane = P.free_lane();
+        uint32_t mx = 0;
+        if (n) tokenize_on_lane(P, m, lane, text, offsets, n, &mx);
+        SMGX_REQUIRE(mx <= P.cfg.max_tokens_per_request, "request longer than max_tokens_per_request");
+        if (n && (!P.has_event_indexer(m) || (P.host_imbalanced(m) && m.token_tree))) {
+            std::vector<uint32_t> toff(n + 1);
+            SMGX_CUDA(cudaMemcpyAsync(toff.data(), lane.d_toff.ptr, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, lane.stream));
+            SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+            std::vector<uint32_t> toks(std::max<uint32_t>(toff[n], 1));
+            if (toff[n]) SMGX_CUDA(cudaMemcpy(toks.data(), lane.d_tokens.ptr, (size_t)toff[n] * 4, cudaMemcpyDeviceToHost));
+            P.tree_select(m, toks.data(), toff.data(), n, out_worker_idx, out_info, true, nullptr);
+            Lane& l2 = P.free_lane();
+            l2.busy = true; l2.ticket = ++P.ticket_seq; l2.model = &m; l2.host_out = out_worker_idx; l2.n = 0;   // processed already counted
+            *out_ticket = l2.ticket;
+            return SMGX_SUCCESS;
+        }
+        if (n) {
+            lane.d_out.reserve((size_t)n * 4);
+            if (out_info) lane.d_info.reserve((size_t)n * sizeof(smgx_decision_info));
+            P.enqueue_tokens(m, lane, lane.d_tokens.as<uint32_t>(), lane.d_toff.as<uint32_t>(), n, std::max<uint32_t>(mx, 1), lane.d_out.as<int32_t>(),
+                             out_info ? lane.d_info.as<smgx_decision_info>() : nullptr);
+            SMGX_CUDA(cudaMemcpyAsync(out_worker_idx, lane.d_out.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
+            if (out_info)
+                SMGX_CUDA(cudaMemcpyAsync(out_info, lane.d_info.ptr, (size_t)n * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+        }
+        lane.busy = true;
+        lane.ticket = ++P.ticket_seq;
+        lane.model = &m;
+        lane.host_out = out_worker_idx;
+        lane.n = n;
+        *out_ticket = lane.ticket;
+        return SMGX_SUCCESS;
+    });
+}
+
 // ---- hot call ----
 uint32_t smgx_pipeline_depth(const smgx_policy* p) { return p ? (uint32_t)p->impl.lanes.size() : 0; }
 

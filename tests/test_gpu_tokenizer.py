@@ -103,6 +103,23 @@ def test_text_in_pick_equals_tokens_in_pick_and_oracle():
     want, br, _, _ = op.select_batch_tokens(flat, offs)
     assert np.array_equal(idx_text, want)
     assert (np.asarray(br) == 2).sum() > 100      # most requests hit a cached system prompt
+    # pipelined form: four sub-batches in flight over the stream lanes give the same picks
+    import ctypes as C
+    from smg_b200.policy import TiktokenTokenizer
+    model = pol._push_fleet(ws)
+    parts = [texts[i::4] for i in range(4)]
+    bufs, tickets = [], []
+    for part in parts:
+        data, offsets = TiktokenTokenizer._ragged(part)
+        out = np.full(len(part), -7, np.int32)
+        t = C.c_uint64()
+        pol._h.call("smgx_submit_text", model, data.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), len(part),
+                    out.ctypes.data_as(C.c_void_p), None, C.byref(t))
+        bufs.append((data, offsets, out)); tickets.append(t.value)
+    for t in tickets:
+        pol._h.call("smgx_wait", t)
+    for i, (_, _, out) in enumerate(bufs):
+        assert np.array_equal(out, idx_text[i::4])
 
 
 # ---- HuggingFace tokenizer.json (byte-level BPE, Llama-3-style pre-tokenizer) -------------------------------------------------
