@@ -82,41 +82,176 @@ __device__ __forceinline__ bool is_anchor(const uint8_t* s, uint32_t i, uint32_t
     const uint8_t pc = char_class(prev_cp(s, i, beg), u);
     return (pc == CH_LETTER && c != CH_LETTER) || (c == CH_NUMBER) != (pc == CH_NUMBER);
 }
+// Window form of next_piece_cl100k: the CTA's 256-byte window is classified ONCE into shared memory (phase 0 of the kernel:
+// s_cls[k] = class | utf-8 length << 4 for a lead byte, kCont for a continuation byte; s_stop[k] = first byte of a special) and
+// the regex then runs on classes instead of decoding and binary-searching every code point again.  Same alternatives, same order,
+// same analytic resolution of the look-ahead as next_piece_cl100k; whenever a decision needs a byte beyond the window (and the
+// window does not end the request) it returns kBail and the caller falls back to the global-memory matcher for that piece.
+constexpr uint8_t kCont = 0x0F;
+constexpr uint32_t kBail = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t next_piece_window(const uint8_t* __restrict__ s_txt, const uint8_t* __restrict__ s_cls, const uint8_t* __restrict__ s_stop,
+                                                      uint32_t k, uint32_t W, bool ends_text) {
+#define WIN_NEED(j) do { if ((j) >= W && !ends_text) return kBail; } while (0)
+#define WIN_END(j) ((j) >= W || s_stop[(j)])
+    const uint8_t c0 = s_cls[k] & 0x0F;
+    const uint32_t len0 = s_cls[k] >> 4;
+    const uint8_t b0 = s_txt[k];
+    // 1. (?i:'s|'t|'re|'ve|'m|'ll|'d)  (+ U+017F for 's')
+    if (b0 == '\'') {
+        WIN_NEED(k + 1);
+        if (!WIN_END(k + 1)) {
+            const uint8_t b1 = s_txt[k + 1];
+            if (b1 < 0x80) {
+                const uint32_t c1 = b1 | 0x20;
+                if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') return k + 2;
+                WIN_NEED(k + 2);
+                if (!WIN_END(k + 2) && s_txt[k + 2] < 0x80) {
+                    const uint32_t c2 = s_txt[k + 2] | 0x20;
+                    if ((c1 == 'r' && c2 == 'e') || (c1 == 'v' && c2 == 'e') || (c1 == 'l' && c2 == 'l')) return k + 3;
+                }
+            } else {
+                WIN_NEED(k + 2);
+                if (k + 2 < W && b1 == 0xC5 && s_txt[k + 2] == 0xBF) return k + 3;   // 'ſ
+            }
+        }
+    }
+    const bool nl0 = b0 == '\n' || b0 == '\r';
+    // 2. [^\r\n\p{L}\p{N}]?\p{L}+
+    {
+        uint32_t j = k;
+        bool ok = c0 == CH_LETTER;
+        if (!ok && c0 != CH_NUMBER && !nl0) {
+            const uint32_t k1 = k + len0;
+            WIN_NEED(k1);
+            if (!WIN_END(k1) && (s_cls[k1] & 0x0F) == CH_LETTER) { j = k1; ok = true; }
+        }
+        if (ok) {
+            for (;;) {
+                WIN_NEED(j);
+                if (WIN_END(j) || (s_cls[j] & 0x0F) != CH_LETTER) break;
+                j += s_cls[j] >> 4;
+            }
+            return j;
+        }
+    }
+    // 3. \p{N}{1,3}
+    if (c0 == CH_NUMBER) {
+        uint32_t j = k + len0;
+        for (int c = 1; c < 3; ++c) {
+            WIN_NEED(j);
+            if (WIN_END(j) || (s_cls[j] & 0x0F) != CH_NUMBER) break;
+            j += s_cls[j] >> 4;
+        }
+        return j;
+    }
+    // 4.  ?[^\s\p{L}\p{N}]+[\r\n]*
+    {
+        uint32_t j = k;
+        bool ok = c0 == CH_OTHER;
+        if (!ok && b0 == ' ') {
+            WIN_NEED(k + 1);
+            if (!WIN_END(k + 1) && (s_cls[k + 1] & 0x0F) == CH_OTHER) { j = k + 1; ok = true; }
+        }
+        if (ok) {
+            for (;;) {
+                WIN_NEED(j);
+                if (WIN_END(j) || (s_cls[j] & 0x0F) != CH_OTHER) break;
+                j += s_cls[j] >> 4;
+            }
+            for (;;) {
+                WIN_NEED(j);
+                if (WIN_END(j) || !(s_txt[j] == '\n' || s_txt[j] == '\r')) break;
+                ++j;
+            }
+            return j;
+        }
+    }
+    // 5-7. whitespace run starting at k
+    uint32_t j = k, last_nl_end = 0, last_start = k, count = 0;
+    for (;;) {
+        WIN_NEED(j);
+        if (WIN_END(j) || (s_cls[j] & 0x0F) != CH_SPACE) break;
+        last_start = j;
+        const bool nl = s_txt[j] == '\n' || s_txt[j] == '\r';
+        j += s_cls[j] >> 4;
+        ++count;
+        if (nl) last_nl_end = j;
+    }
+    if (last_nl_end) return last_nl_end;   // 5. \s*[\r\n]+
+    if (WIN_END(j)) return j;              // 6. \s+(?!\S): the run reaches the end of the (slice of) text
+    if (count >= 2) return last_start;     // 6. give back one char so that whitespace follows
+    return j;                              // 7. \s+
+#undef WIN_NEED
+#undef WIN_END
+}
+
 __global__ void __launch_bounds__(256) pretokenize_kernel(BpeView v, const uint8_t* __restrict__ text, const uint32_t* __restrict__ offsets,
                                                           uint8_t* __restrict__ flags, Piece* __restrict__ pieces, uint32_t* __restrict__ n_pieces) {
     __shared__ Piece s_list[320];
     __shared__ uint32_t s_anchor[256];
     __shared__ uint32_t s_wcnt[8];
     __shared__ uint32_t s_count, s_base;
+    __shared__ uint8_t s_txt[256], s_cls[256], s_stop[256], s_flag[256];
     if (threadIdx.x == 0) s_count = 0;
     const uint32_t r = blockIdx.y, beg = offsets[r], rend = offsets[r + 1];
-    const uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cstart = beg + blockIdx.x * blockDim.x;
+    const uint32_t i = cstart + threadIdx.x;
+    const uint32_t W = cstart < rend ? min(256u, rend - cstart) : 0;
+    const bool ends_text = cstart + W == rend;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // phase 1 (every thread, one byte each): is this byte an anchor?  Anchors are then packed densely, so that phase 2 — the
-    // serial regex replay — runs with full warps instead of one live lane in six.
-    const bool anchor = i < rend && (text[i] & 0xC0) != 0x80 && flags[i] < 2 && is_anchor(text, i, beg, flags, v.uni);
+    // phase 0 (every thread, one byte each): classify the window once
+    if (threadIdx.x < W) {
+        const uint8_t b = text[i], fl = flags[i];
+        s_txt[threadIdx.x] = b;
+        s_flag[threadIdx.x] = fl;
+        s_stop[threadIdx.x] = fl == 2;
+        if ((b & 0xC0) == 0x80) s_cls[threadIdx.x] = kCont;
+        else { uint32_t l; const uint32_t cp = utf8_decode(text, i, rend, l); s_cls[threadIdx.x] = (uint8_t)(char_class(cp, v.uni) | (l << 4)); }
+    }
+    __syncthreads();
+    // anchor test on the window (is_anchor on classes); the char before the window is classified from global memory
+    auto anchor_at = [&](uint32_t k) -> bool {   // k < W, lead byte, not inside a special
+        const uint32_t gi = cstart + k;
+        if (gi == beg) return true;
+        if ((k ? s_flag[k - 1] : flags[gi - 1]) >= 2) return true;
+        const uint8_t c = s_cls[k] & 0x0F;
+        uint8_t pc;
+        int q = (int)k - 1;
+        while (q >= 0 && s_cls[q] == kCont) --q;
+        if (q >= 0) pc = s_cls[q] & 0x0F;
+        else pc = char_class(prev_cp(text, gi, beg), v.uni);
+        return (pc == CH_LETTER && c != CH_LETTER) || (c == CH_NUMBER) != (pc == CH_NUMBER);
+    };
+    // phase 1: which bytes are anchors?  They are then packed densely, so that phase 2 — the serial regex replay — runs with full
+    // warps instead of one live lane in six.
+    const bool anchor = threadIdx.x < W && s_cls[threadIdx.x] != kCont && s_flag[threadIdx.x] < 2 && anchor_at(threadIdx.x);
     const unsigned bal = __ballot_sync(0xffffffffu, anchor);
     if (lane == 0) s_wcnt[wid] = (uint32_t)__popc(bal);
     __syncthreads();
     uint32_t before = 0, n_anchor = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { const uint32_t c = s_wcnt[w]; if (w < wid) before += c; n_anchor += c; }
-    if (anchor) s_anchor[before + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = i;
+    if (anchor) s_anchor[before + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = threadIdx.x;
     __syncthreads();
     // phase 2: thread k replays the regex from the k-th anchor up to the next one; a special's first byte (flags == 2) ends the
     // slice.  The warp iterates in lockstep (one piece per live lane and round).
     if ((uint32_t)(wid * 32) < n_anchor) {
         bool live = threadIdx.x < n_anchor;
-        uint32_t p = live ? s_anchor[threadIdx.x] : 0;
+        uint32_t p = live ? cstart + s_anchor[threadIdx.x] : 0;
         while (__any_sync(0xffffffffu, live)) {
             if (live) {
                 flags[p] = 1;
-                const uint32_t q = next_piece_cl100k(text, p, rend, v.uni, flags);
+                uint32_t q = kBail;
+                if (p - cstart < W) { const uint32_t e = next_piece_window(s_txt, s_cls, s_stop, p - cstart, W, ends_text); if (e != kBail) q = cstart + e; }
+                if (q == kBail) q = next_piece_cl100k(text, p, rend, v.uni, flags);   // the piece looks beyond the window
                 const uint32_t slot = atomicAdd(&s_count, 1u);
                 if (slot < 320) s_list[slot] = Piece{p, q - p, r};
                 else { const uint32_t g = atomicAdd(n_pieces, 1u); pieces[g] = Piece{p, q - p, r}; }   // overflow: straight to the global list
-                if (q >= rend || flags[q] == 2 || is_anchor(text, q, beg, flags, v.uni)) live = false;
-                else p = q;
+                bool stop;
+                if (q >= rend) stop = true;
+                else if (q - cstart < W) stop = s_flag[q - cstart] == 2 || anchor_at(q - cstart);
+                else stop = flags[q] == 2 || is_anchor(text, q, beg, flags, v.uni);
+                if (stop) live = false; else p = q;
             }
         }
     }
