@@ -40,9 +40,13 @@ struct ModelState {
     std::unique_ptr<TokenTreeIndex> token_tree;   // token_trees[model] (cache_aware.rs:79)
     std::unique_ptr<StringTreeIndex> string_tree; // string_trees[model] (cache_aware.rs:78)
     // hash_index[model] (cache_aware.rs:95-101): blake3 path hash of the full request → copy of the matched prefix
-    std::unordered_map<uint64_t, std::vector<uint32_t>> hash_index_tokens;
-    std::unordered_map<uint64_t, std::string> hash_index_text;
+    // values live in append-only arenas (one allocation-free copy per routed request); an overwritten entry's old bytes are
+    // reclaimed when evict_cache clears the map
+    std::unordered_map<uint64_t, std::pair<uint64_t, uint32_t>> hash_index_tokens, hash_index_text;   // hash → (arena offset, length)
+    std::vector<uint32_t> hash_arena_tokens;
+    std::string hash_arena_text;
     DevBuf d_slice_of_tenant;
+    std::vector<uint32_t> tenant_of_slice;        // tenant id of urls[i]
     uint64_t seen_tenants_version = ~0ULL;
     bool has_learned_bs = false;
     uint32_t learned_bs = 0;
@@ -249,6 +253,8 @@ public:
     // fleet-side lookup the tree pick needs: tenant id → first slice index with that URL (`position(|w| w.url() == tenant)`)
     void sync_tenant_map(ModelState& m) {
         if (!m.fleet_dirty_tenant && m.seen_tenants_version == tenants.version) return;
+        m.tenant_of_slice.resize(m.urls.size());
+        for (size_t i = 0; i < m.urls.size(); ++i) m.tenant_of_slice[i] = tenants.intern(m.urls[i]);   // the inverse, for the insert's tenant
         std::vector<int32_t> sl(std::max<size_t>(tenants.names.size(), 1), -1);
         for (size_t i = m.urls.size(); i-- > 0;) {
             int64_t t = tenants.find(m.urls[i]);
@@ -362,8 +368,9 @@ public:
                 const uint8_t br = info[r].branch;
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
                     const size_t idx = (size_t)out_idx[r];
-                    tree.insert_tokens(tk, len, tenants.intern(m.urls[idx]));   // :868 / :396
-                    m.hash_index_tokens[path_hash[r]].assign(tk, tk + info[r].matched);
+                    tree.insert_tokens(tk, len, m.tenant_of_slice[idx]);   // :868 / :396
+                    m.hash_index_tokens[path_hash[r]] = {m.hash_arena_tokens.size(), info[r].matched};
+                    m.hash_arena_tokens.insert(m.hash_arena_tokens.end(), tk, tk + info[r].matched);
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -483,10 +490,11 @@ public:
                     const size_t idx = (size_t)out_idx[r];
                     const uint8_t* tx = text + offsets[r];
                     const uint32_t nb = offsets[r + 1] - offsets[r];
-                    tree.insert_text(tx, nb, tenants.intern(m.urls[idx]));   // :938 / :421
+                    tree.insert_text(tx, nb, m.tenant_of_slice[idx]);   // :938 / :421
                     uint32_t pb = 0, chars = 0;   // text.chars().take(matched_char_count): byte length of the matched prefix
                     while (pb < nb && chars < info[r].matched) { ++pb; while (pb < nb && (tx[pb] & 0xC0) == 0x80) ++pb; ++chars; }
-                    m.hash_index_text[path_hash[r]].assign((const char*)tx, pb);
+                    m.hash_index_text[path_hash[r]] = {m.hash_arena_text.size(), pb};
+                    m.hash_arena_text.append((const char*)tx, pb);
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -1020,8 +1028,8 @@ smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err) {   
         for (auto& kv : p->impl.models) if (kv.second->string_tree) kv.second->string_tree->evict_tenant_by_size((size_t)max_size);   // :317-321
         for (auto& kv : p->impl.models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);     // :322-326
         for (auto& kv : p->impl.models) {   // per model, per tree kind (:335-351)
-            if (kv.second->hash_index_text.size() > max_size) kv.second->hash_index_text.clear();
-            if (kv.second->hash_index_tokens.size() > max_size) kv.second->hash_index_tokens.clear();
+            if (kv.second->hash_index_text.size() > max_size) { kv.second->hash_index_text.clear(); kv.second->hash_arena_text.clear(); }
+            if (kv.second->hash_index_tokens.size() > max_size) { kv.second->hash_index_tokens.clear(); kv.second->hash_arena_tokens.clear(); }
         }
         return SMGX_SUCCESS;
     });
@@ -1380,8 +1388,8 @@ smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_
         *out_found = 0; *out_bytes = 0;
         const void* src = nullptr;
         size_t nb = 0;
-        if (text_kind) { auto it = m.hash_index_text.find(path_hash); if (it != m.hash_index_text.end()) { src = it->second.data(); nb = it->second.size(); *out_found = 1; } }
-        else { auto it = m.hash_index_tokens.find(path_hash); if (it != m.hash_index_tokens.end()) { src = it->second.data(); nb = it->second.size() * 4; *out_found = 1; } }
+        if (text_kind) { auto it = m.hash_index_text.find(path_hash); if (it != m.hash_index_text.end()) { src = m.hash_arena_text.data() + it->second.first; nb = it->second.second; *out_found = 1; } }
+        else { auto it = m.hash_index_tokens.find(path_hash); if (it != m.hash_index_tokens.end()) { src = m.hash_arena_tokens.data() + it->second.first; nb = (size_t)it->second.second * 4; *out_found = 1; } }
         *out_bytes = (uint32_t)nb;
         if (*out_found && out && nb <= cap_bytes && nb) memcpy(out, src, nb);
         return SMGX_SUCCESS;

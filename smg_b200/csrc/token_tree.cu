@@ -158,16 +158,18 @@ int32_t TokenTreeIndex::any_tenant(uint32_t node) const {
 void TokenTreeIndex::refresh_all_any_tenant() { full_dirty_ = true; }
 
 size_t TokenTreeIndex::tenant_token_size(uint32_t tenant) const {
-    auto it = tenant_tokens_.find(tenant);
-    return it == tenant_tokens_.end() ? 0 : it->second;
+    return tenant < tenant_tokens_.size() ? tenant_tokens_[tenant] : 0;
 }
 
 // TokenTree::insert_tokens (token_tree.rs:401-609)
 void TokenTreeIndex::insert_tokens(const uint32_t* toks, size_t n, uint32_t tenant) {
     const size_t aligned = (n / kPage) * kPage;
     if (aligned == 0) return;
-    if (!has_tenant(nodes_[0], tenant)) nodes_[0].tenants.emplace_back(tenant, 0);
-    tenant_tokens_.emplace(tenant, 0);
+    if (tenant >= tenant_known_.size()) { tenant_known_.resize(tenant + 1, 0); tenant_tokens_.resize(tenant + 1, 0); }
+    if (!tenant_known_[tenant]) {   // first insert for this tenant: root entry + token counter (:412-420)
+        tenant_known_[tenant] = 1;
+        if (!has_tenant(nodes_[0], tenant)) nodes_[0].tenants.emplace_back(tenant, 0);
+    }
     const uint32_t* rem = toks;
     size_t rem_len = aligned;
     uint32_t cur = 0;
@@ -191,12 +193,11 @@ void TokenTreeIndex::insert_tokens(const uint32_t* toks, size_t n, uint32_t tena
         const uint32_t child = table_[(size_t)slot].child;
         const uint32_t child_len = nodes_[child].label_len;
         size_t common = 0;
-        {
+        {   // only whole equal pages count (:455-463), so compare page by page
             const uint32_t* lab = label(nodes_[child]);
-            const size_t lim = std::min<size_t>(rem_len, child_len);
-            while (common < lim && rem[common] == lab[common]) ++common;
+            const size_t lim = std::min<size_t>(rem_len, child_len) / kPage * kPage;
+            while (common < lim && memcmp(rem + common, lab + common, kPage * 4) == 0) common += kPage;
         }
-        common = (common / kPage) * kPage;
         if (common == 0) break;
         if (common == child_len) {   // full edge match → descend; `advance` is counted even for an existing owner (:467-474)
             touch(child, tenant);
@@ -377,12 +378,11 @@ void TokenTreeIndex::evict_tenant(uint32_t tenant, size_t max_tokens) {
         if (promoted >= 0) { heap.push({prio((uint32_t)promoted, promoted_ts), leaf_nodes.size()}); leaf_nodes.push_back((uint32_t)promoted); }
     }
     for (uint32_t g : graveyard) free_node(g);
-    auto it = tenant_tokens_.find(tenant);
-    if (it != tenant_tokens_.end()) it->second = it->second >= evicted ? it->second - evicted : 0;
+    if (tenant < tenant_tokens_.size()) tenant_tokens_[tenant] = tenant_tokens_[tenant] >= evicted ? tenant_tokens_[tenant] - evicted : 0;
 }
 void TokenTreeIndex::evict_tenant_by_size(size_t max_size) {
     std::vector<uint32_t> over;
-    for (auto& kv : tenant_tokens_) if (kv.second > max_size) over.push_back(kv.first);
+    for (uint32_t t = 0; t < tenant_tokens_.size(); ++t) if (tenant_known_[t] && tenant_tokens_[t] > max_size) over.push_back(t);
     std::sort(over.begin(), over.end(), [&](uint32_t a, uint32_t b) { return tenants_->names[a] < tenants_->names[b]; });
     for (uint32_t t : over) evict_tenant(t, max_size);
 }
@@ -397,7 +397,7 @@ void TokenTreeIndex::clear() {
     table_.assign(1024, ChildSlot{0, 0, 0});
     mask_ = 1023;
     table_live_ = table_tombs_ = 0;
-    tenant_tokens_.clear();
+    tenant_tokens_.clear(); tenant_known_.clear();
     full_dirty_ = true;
     dirty_nodes_.clear(); dirty_slots_.clear();
 }
@@ -465,7 +465,7 @@ TokenTreeView TokenTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
         uploaded_tokens_ = tokens_.size();
     }
     // a node whose header changed dirties the slot that points at it
-    for (uint32_t id : dirty_nodes_) if (id < nodes_.size() && nodes_[id].slot != kNoNode) dirty_slots_.push_back(nodes_[id].slot);
+    for (uint32_t id : dirty_nodes_) if (id < nodes_.size() && nodes_[id].slot != kNoNode) mark_slot(nodes_[id].slot);
     dirty_nodes_.clear();
     if (!full_dirty_ && dirty_slots_.size() > table_.size() / 8) full_dirty_ = true;
     if (full_dirty_) {
@@ -481,9 +481,7 @@ TokenTreeView TokenTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
     } else if (!dirty_slots_.empty()) {
         if (!stage_done_) SMGX_CUDA(cudaEventCreateWithFlags(&stage_done_, cudaEventDisableTiming));
         if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
-        std::sort(dirty_slots_.begin(), dirty_slots_.end());
-        dirty_slots_.erase(std::unique(dirty_slots_.begin(), dirty_slots_.end()), dirty_slots_.end());
-        const size_t ns = dirty_slots_.size();
+        const size_t ns = dirty_slots_.size();   // unique by construction (mark_slot stamps)
         const size_t off_r = ((ns * 4 + 15) / 16) * 16, total = off_r + ns * 32;
         stage_.reserve(total);
         d_stage_.reserve(total);
@@ -499,6 +497,7 @@ TokenTreeView TokenTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
         stage_pending_ = true;
         dirty_slots_.clear();
     }
+    if (++flush_gen_ == 0) { flush_gen_ = 1; std::fill(slot_stamp_.begin(), slot_stamp_.end(), 0u); }
     return TokenTreeView{d_tokens_.as<uint32_t>(), d_table_.as<TreeSlot>(), mask_};
 }
 

@@ -51,8 +51,9 @@ __host__ __device__ inline uint64_t page_finish(uint32_t h1, uint32_t h2, uint32
     return (((uint64_t)a << 32) | b) | 1ULL;   // never 0 (0 marks an empty slot)
 }
 inline uint64_t page_key_host(const uint32_t* page, uint32_t parent) {
+    static const struct Mults { uint32_t m1[kPage], m2[kPage]; Mults() { for (uint32_t i = 0; i < kPage; ++i) { m1[i] = page_mult1(i); m2[i] = page_mult2(i); } } } M;
     uint32_t h1 = 0, h2 = 0;
-    for (uint32_t i = 0; i < kPage; ++i) { h1 += (page[i] + 1u) * page_mult1(i); h2 += (page[i] ^ 0x9E3779B9u) * page_mult2(i); }
+    for (uint32_t i = 0; i < kPage; ++i) { h1 += (page[i] + 1u) * M.m1[i]; h2 += (page[i] ^ 0x9E3779B9u) * M.m2[i]; }
     return page_finish(h1, h2, parent);
 }
 
@@ -127,7 +128,11 @@ private:
     bool has_tenant(const Node& nd, uint32_t t) const;
     void set_tenant_ts(Node& nd, uint32_t t, uint64_t ts);
     void mark_node(uint32_t id) { if (!full_dirty_) dirty_nodes_.push_back(id); }
-    void mark_slot(uint32_t i) { if (!full_dirty_) dirty_slots_.push_back(i); }
+    void mark_slot(uint32_t i) {   // each slot at most once per flush generation: no sort / unique at flush time
+        if (full_dirty_) return;
+        if (slot_stamp_.size() < table_.size()) slot_stamp_.assign(table_.size(), 0);
+        if (slot_stamp_[i] != flush_gen_) { slot_stamp_[i] = flush_gen_; dirty_slots_.push_back(i); }
+    }
     const uint32_t* label(const Node& nd) const { return tokens_.data() + nd.label_off; }
 
     TenantTable* tenants_;
@@ -141,7 +146,10 @@ private:
     std::vector<ChildSlot> table_;
     uint32_t mask_ = 0;
     uint64_t table_live_ = 0, table_tombs_ = 0;
-    std::unordered_map<uint32_t, size_t> tenant_tokens_;   // tenant_token_count (token_tree.rs:328)
+    std::vector<size_t> tenant_tokens_;                    // tenant_token_count (token_tree.rs:328), indexed by tenant id
+    std::vector<uint8_t> tenant_known_;                    // … and whether the tenant has an entry at all
+    std::vector<uint32_t> slot_stamp_;
+    uint32_t flush_gen_ = 1;
 
     DevBuf d_tokens_, d_table_, d_stage_;
     TreeSlot device_slot(uint32_t i) const;
