@@ -240,7 +240,7 @@ def workload_name(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="smgx", choices=["smgx", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
