@@ -211,11 +211,11 @@ def run_reference(args, rank, world):
         # "all the host threads it can use": SMT siblings / other tenants can make the full logical-CPU count slower than
         # fewer threads, so calibrate over {all, 1/2, 1/4} logical CPUs on 3 steps each and keep the fastest.
         ncpu = os.cpu_count() or 1
-        cands = sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4)}, reverse=True)
+        cands = sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), max(1, ncpu // 8)}, reverse=True)
         best = None
         for c in cands:
-            op.select_steps_mt(batches, 1, c)
-            t_c = op.select_steps_mt(batches, 3, c)[1]
+            op.select_steps_mt(batches, 4, c)
+            t_c = min(op.select_steps_mt(batches, 24, c)[1] for _ in range(2))   # best of two 24-step probes per candidate
             if best is None or t_c < best[0]:
                 best = (t_c, c)
         cores = best[1]
