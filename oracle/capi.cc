@@ -286,12 +286,13 @@ size_t orc_policy_hash_index(void* h, const char* model, int text_kind, char* ou
 // Read-only event-mode scoring with `threads` persistent host threads (the reference's concurrent-read design:
 // select_worker takes &self, the index is only read, requests are spread over a tokio worker pool).  `steps` batches
 // are routed back to back: batch s = tokens/offsets of (s % n_batches); threads are spawned ONCE, every thread owns a
-// fixed shard of each batch, and a spin barrier separates consecutive steps so a "step" keeps its meaning.
+// fixed shard of each batch; with step_barrier != 0 a barrier separates consecutive steps (a "step" completes before the next starts,
+// as on the GPU side), with 0 the threads run free — the throughput a pool of independent tasks reaches.
 // Each thread gets a private copy of the fleet vector (the processed counter is the only thing select_worker writes
 // in event mode).  Falls back to one thread when the model has no populated indexer (tree modes mutate the tree).
 // Returns elapsed seconds.
 double orc_policy_select_steps_mt(void* h, const uint32_t* const* tokens, const uint64_t* const* offsets, size_t n_batches,
-                                  size_t n, size_t steps, int32_t* out_idx, int threads) {
+                                  size_t n, size_t steps, int32_t* out_idx, int threads, int step_barrier) {
     auto* b = (PolicyBox*)h;
     if (threads < 1) threads = 1;
     if (!b->workers.empty()) {
@@ -319,7 +320,7 @@ double orc_policy_select_steps_mt(void* h, const uint32_t* const* tokens, const 
                     Decision d = b->pol.select_worker(ws, nullptr, tk + off[i], (size_t)(off[i + 1] - off[i]), true);
                     out_idx[i] = (int32_t)d.idx;
                 }
-                barrier(gen);
+                if (step_barrier) barrier(gen);   // 0: free-running threads, as independent tokio tasks are — the CPU's best throughput
             }
         });
     }

@@ -88,7 +88,7 @@ def lib():
         sig("orc_hash_path_bytes", C.c_uint64, vp, sz)
         sig("orc_hash_token_path", C.c_uint64, vp, sz)
         sig("orc_policy_hash_index", sz, vp, cp, C.c_int, vp, sz)
-        sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int)
+        sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int, C.c_int)
         _lib = L
     return _lib
 
@@ -447,7 +447,7 @@ class CacheAwarePolicy:
                                 1 if tokens is not None else 0, _ptr(out), _ptr(valid), valid.size)
         return Decision(out, [int(v) for v in valid[: int(out[5])]])
 
-    def select_steps_mt(self, batches, steps, threads):
+    def select_steps_mt(self, batches, steps, threads, step_barrier=False):
         """`steps` batches routed back to back by `threads` persistent host threads (event mode, read-only index).
         batches: list of (tokens u32, offsets u64[n+1]) with equal n.  → (picks of the last step, seconds)."""
         toks = [_u32(b[0]) for b in batches]
@@ -456,7 +456,7 @@ class CacheAwarePolicy:
         TP = (C.c_void_p * len(batches))(*[t.ctypes.data for t in toks])
         OP = (C.c_void_p * len(batches))(*[o.ctypes.data for o in offs])
         idx = np.zeros(n, np.int32)
-        secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads)
+        secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads, 1 if step_barrier else 0)
         return idx, secs
 
     def hash_index(self, kind="tokens", model="unknown"):
