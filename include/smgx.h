@@ -58,7 +58,8 @@ typedef struct smgx_cache_aware_config {
     float cache_threshold;            /* default 0.5  */
     uint64_t balance_abs_threshold;   /* default 32   */
     float balance_rel_threshold;      /* default 1.1  */
-    uint64_t eviction_interval_secs;  /* default 30; 0 = no background eviction (the caller drives smgx_evict_cache) */
+    uint64_t eviction_interval_secs;  /* default 30: a background thread bounds every tree to max_tree_size at this period, as the
+                                         reference does (cache_aware.rs:126-199); 0 = none (the caller drives smgx_evict_cache) */
     uint64_t max_tree_size;           /* default 10000 */
     uint64_t block_size;              /* default 16   */
     int32_t device_id;                /* CUDA ordinal; -1 = host-mirror only (index writers work, every select fails) */

@@ -9,7 +9,10 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -103,6 +106,7 @@ public:
         }
     }
     ~Policy() {
+        stop_eviction_thread();
         if (cfg.device_id >= 0) {
             cudaSetDevice(cfg.device_id);
             cudaDeviceSynchronize();
@@ -504,6 +508,35 @@ public:
         if (out_tenant) memcpy(out_tenant, ten.data(), (size_t)n * 4);
     }
 
+    // CacheAwarePolicy::evict_cache (cache_aware.rs:311-352); caller holds `mu`
+    void evict_all(uint64_t max_size) {
+        for (auto& kv : models) if (kv.second->string_tree) kv.second->string_tree->evict_tenant_by_size((size_t)max_size);   // :317-321
+        for (auto& kv : models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);     // :322-326
+        for (auto& kv : models) {   // per model, per tree kind (:335-351)
+            if (kv.second->hash_index_text.size() > max_size) { kv.second->hash_index_text.clear(); kv.second->hash_arena_text.clear(); }
+            if (kv.second->hash_index_tokens.size() > max_size) { kv.second->hash_index_tokens.clear(); kv.second->hash_arena_tokens.clear(); }
+        }
+    }
+    // The reference's background eviction thread (cache_aware.rs:126-199): every eviction_interval_secs, bound every tree to
+    // max_tree_size.  Host-side tree maintenance only — it issues no CUDA work; the mirrors pick the changes up at the next flush.
+    void start_eviction_thread() {
+        if (cfg.eviction_interval_secs == 0) return;
+        evictor = std::thread([this]() {
+            std::unique_lock<std::mutex> lk(evict_mu);
+            while (!evict_stop) {
+                if (evict_cv.wait_for(lk, std::chrono::seconds(cfg.eviction_interval_secs), [this] { return evict_stop; })) break;
+                std::lock_guard<std::mutex> g(mu);
+                evict_all(cfg.max_tree_size);
+            }
+        });
+    }
+    void stop_eviction_thread() {
+        if (!evictor.joinable()) return;
+        { std::lock_guard<std::mutex> lk(evict_mu); evict_stop = true; }
+        evict_cv.notify_all();
+        evictor.join();
+    }
+
     Lane& free_lane() {
         for (auto& l : lanes) if (!l.busy) return l;
         throw Error(SMGX_INVALID_ARGUMENT, "all pipeline lanes are in flight; call smgx_wait first");
@@ -589,6 +622,10 @@ public:
     int sm_count = 148;
     size_t l2_bytes = 126u << 20;
     std::mutex mu;
+    std::thread evictor;
+    std::mutex evict_mu;
+    std::condition_variable evict_cv;
+    bool evict_stop = false;
     std::map<std::string, std::unique_ptr<ModelState>> models;
     bool monitor = false;
     std::vector<Lane> lanes;
@@ -608,7 +645,7 @@ using namespace smgx;
 
 struct smgx_policy {
     Policy impl;
-    explicit smgx_policy(const smgx_cache_aware_config& c) : impl(c) {}
+    explicit smgx_policy(const smgx_cache_aware_config& c) : impl(c) { impl.start_eviction_thread(); }
 };
 
 namespace {
@@ -1025,12 +1062,7 @@ smgx_status smgx_evict_cache(smgx_policy* p, uint64_t max_size, char** err) {   
     return guard(err, [&]() {
         NONNULL(p);
         std::lock_guard<std::mutex> g(p->impl.mu);
-        for (auto& kv : p->impl.models) if (kv.second->string_tree) kv.second->string_tree->evict_tenant_by_size((size_t)max_size);   // :317-321
-        for (auto& kv : p->impl.models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);     // :322-326
-        for (auto& kv : p->impl.models) {   // per model, per tree kind (:335-351)
-            if (kv.second->hash_index_text.size() > max_size) { kv.second->hash_index_text.clear(); kv.second->hash_arena_text.clear(); }
-            if (kv.second->hash_index_tokens.size() > max_size) { kv.second->hash_index_tokens.clear(); kv.second->hash_arena_tokens.clear(); }
-        }
+        p->impl.evict_all(max_size);
         return SMGX_SUCCESS;
     });
 }

@@ -46,3 +46,18 @@ def test_match_without_device_fails_loudly():
     t.insert_text("hello", "a")
     with pytest.raises(SmgxError):
         t.match_prefix_with_counts("hello")     # no CPU fallback for the walk
+
+
+def test_background_eviction_thread_bounds_the_trees():
+    """eviction_interval_secs > 0 starts the reference's periodic eviction (cache_aware.rs:126-199) inside the library."""
+    import time
+    h = _Handle(CacheAwareConfig(eviction_interval_secs=1, max_tree_size=40), -1)
+    t = Tree(h)
+    for i in range(60):
+        t.insert_text(f"entry number {i:03d} with some tail", "http://w0:8000")
+    assert t.get_used_size_per_tenant()["http://w0:8000"] > 40
+    deadline = time.time() + 6
+    while time.time() < deadline and t.get_used_size_per_tenant().get("http://w0:8000", 0) > 40:
+        time.sleep(0.2)
+    assert t.get_used_size_per_tenant().get("http://w0:8000", 0) <= 40
+    h.close()          # joins the thread
