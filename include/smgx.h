@@ -38,6 +38,7 @@ typedef enum smgx_status {
     SMGX_WORKER_NOT_TRACKED = 10,    /* kv_index ApplyError::WorkerNotTracked    (event_tree.rs:90-95) */
     SMGX_PARENT_BLOCK_NOT_FOUND = 11,/* kv_index ApplyError::ParentBlockNotFound (event_tree.rs:90-95) */
     SMGX_NOT_FOUND = 12,         /* unknown model key / no indexer for the model                      */
+    SMGX_BUSY = 13,              /* every pipeline lane has a submission in flight: smgx_wait one, then retry (the synchronous calls do) */
     SMGX_UNKNOWN_ERROR = 99
 } smgx_status;
 

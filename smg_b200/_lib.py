@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libsmgx.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "smgx.h")
 
 SUCCESS, INVALID_ARGUMENT, TOKENIZATION_ERROR, MEMORY_ERROR, DEVICE_ERROR = 0, 1, 2, 4, 5
-WORKER_NOT_TRACKED, PARENT_BLOCK_NOT_FOUND, NOT_FOUND, UNKNOWN_ERROR = 10, 11, 12, 99
+WORKER_NOT_TRACKED, PARENT_BLOCK_NOT_FOUND, NOT_FOUND, BUSY, UNKNOWN_ERROR = 10, 11, 12, 13, 99
 
 BRANCHES = ["no_healthy", "imbalanced_min_load", "event_overlap", "event_min_load", "tree_match", "tree_min_load",
             "tree_fallback_first_healthy", "no_tree_random"]

@@ -539,7 +539,7 @@ public:
 
     Lane& free_lane() {
         for (auto& l : lanes) if (!l.busy) return l;
-        throw Error(SMGX_INVALID_ARGUMENT, "all pipeline lanes are in flight; call smgx_wait first");
+        throw Error(SMGX_BUSY, "all pipeline lanes are in flight; call smgx_wait first");
     }
 
     uint64_t submit_host(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info) {
@@ -1219,9 +1219,22 @@ smgx_status smgx_tokenize_batch(smgx_policy* p, const char* model_key, const uin
     });
 }
 
+static smgx_status select_batch_text_once(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                          int32_t* out_worker_idx, smgx_decision_info* out_info, uint32_t* out_tokens, uint32_t* out_tok_offsets,
+                                          uint32_t cap_tokens, char** err);
 smgx_status smgx_select_batch_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
                                    int32_t* out_worker_idx, smgx_decision_info* out_info, uint32_t* out_tokens, uint32_t* out_tok_offsets,
                                    uint32_t cap_tokens, char** err) {
+    for (;;) {   // synchronous: wait for a lane when other threads hold them all
+        const smgx_status st = select_batch_text_once(p, model_key, text, offsets, n, out_worker_idx, out_info, out_tokens, out_tok_offsets, cap_tokens, err);
+        if (st != SMGX_BUSY) return st;
+        if (err && *err) { smgx_free_string(*err); *err = nullptr; }
+        std::this_thread::yield();
+    }
+}
+static smgx_status select_batch_text_once(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
+                                          int32_t* out_worker_idx, smgx_decision_info* out_info, uint32_t* out_tokens, uint32_t* out_tok_offsets,
+                                          uint32_t cap_tokens, char** err) {
     return guard(err, [&]() {
         NONNULL(p);
         SMGX_REQUIRE(n == 0 || (text && offsets && out_worker_idx), "Invalid arguments: null pointer");
@@ -1524,16 +1537,29 @@ smgx_status smgx_submit_tokens(smgx_policy* p, const char* model_key, const uint
 smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err) {
     return guard(err, [&]() {
         NONNULL(p);
+        // the stream is synchronised WITHOUT the policy mutex, so other threads keep submitting while this one waits
+        cudaStream_t stream = nullptr;
+        {
+            std::lock_guard<std::mutex> g(p->impl.mu);
+            p->impl.use_device();
+            for (auto& l : p->impl.lanes) if (l.busy && l.ticket == ticket) stream = l.stream;
+        }
+        if (stream) SMGX_CUDA(cudaStreamSynchronize(stream));
         std::lock_guard<std::mutex> g(p->impl.mu);
-        p->impl.use_device();
-        p->impl.wait(ticket);
+        p->impl.wait(ticket);   // finds the lane again; its stream is idle now
         return SMGX_SUCCESS;
     });
 }
 smgx_status smgx_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
                                      int32_t* out_worker_idx, smgx_decision_info* out_info, char** err) {
     uint64_t t = 0;
-    smgx_status st = smgx_submit_tokens(p, model_key, tokens, offsets, n, out_worker_idx, out_info, &t, err);
+    smgx_status st;
+    for (;;) {   // a synchronous call simply waits for a lane when other threads hold them all
+        st = smgx_submit_tokens(p, model_key, tokens, offsets, n, out_worker_idx, out_info, &t, err);
+        if (st != SMGX_BUSY) break;
+        if (err && *err) { smgx_free_string(*err); *err = nullptr; }
+        std::this_thread::yield();
+    }
     if (st != SMGX_SUCCESS) return st;
     return smgx_wait(p, t, err);
 }

@@ -317,3 +317,57 @@ def test_multi_batch_device_path_matches_oracle():
         h.call("smgx_memcpy_d2h", got.ctypes.data_as(C.c_void_p), d_out[j], ns[j] * 4)
         want, _, _, _ = op.select_batch_tokens(host[j][0], host[j][1].astype(np.uint64))
         assert np.array_equal(got, want), j
+
+
+def test_concurrent_callers_share_the_pipeline():
+    """select_worker is called from many tokio tasks at once: 8 threads hammer the synchronous batch call on one policy —
+    more threads than stream lanes — and every batch must equal the single-threaded answer."""
+    import threading
+    from smg_b200 import CacheAwareConfig, CacheAwarePolicy
+    cfg = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=1.5, block_size=16)
+    urls = synth.worker_urls(16)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **cfg))
+    ws = _workers(urls)
+    pol.init_workers(ws)
+    mon = pol.kv_event_monitor(16)
+    ix = mon.create_indexer("unknown", 8)
+    pol.set_kv_event_monitor(mon)
+    seqs = synth.gen_sequences(64, 256, 3)
+    for u in urls:
+        ix.intern_worker(u)
+    sid = 1
+    for s in range(64):
+        hs = orc.compute_request_content_hashes(seqs[s], 16)
+        ix.apply_stored(s % 16, [(sid + i, hs[i]) for i in range(len(hs))])
+        sid += len(hs)
+    batches = []
+    for k in range(8):
+        q = synth.gen_queries(seqs, 200, 100 + k, block=16)
+        tokens, offsets = synth.ragged(q)
+        batches.append((tokens, offsets))
+    model = pol._push_fleet(ws)
+    import ctypes as C
+
+    def run(tokens, offsets):
+        out = np.full(200, -9, np.int32)
+        pol._h.call("smgx_select_batch_tokens", model, tokens.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), 200,
+                    out.ctypes.data_as(C.c_void_p), None)
+        return out
+
+    want = [run(t, o) for t, o in batches]
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(30):
+                if not np.array_equal(run(*batches[k]), want[k]):
+                    errors.append(k)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
