@@ -155,6 +155,23 @@ smgx_status smgx_indexer_apply_cleared(smgx_policy* p, const char* model_key, ui
 smgx_status smgx_indexer_remove_worker(smgx_policy* p, const char* model_key, uint32_t worker_id, char** err);  /* :426-435 */
 smgx_status smgx_indexer_current_size(smgx_policy* p, const char* model_key, uint64_t* out, char** err);        /* :438-444 */
 smgx_status smgx_indexer_entry_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err);         /* index.len() */
+/* KvEventMonitor::apply_event for a batch (worker/kv_event_monitor.rs:525-597; proto crates/grpc_client/proto/common.proto:41-58).
+ * Event e of kind STORED carries blocks [first_block, first_block + n_blocks) of the flat block arrays: block j has the engine's
+ * block_hash[j] (i64, reinterpreted as u64 like SequenceHash::from) and token_ids[block_tok_offsets[j] .. block_tok_offsets[j+1]);
+ * REMOVED uses block_hash[...] only; CLEARED nothing.  Content hashes of all stored blocks are computed in one GPU launch; events are
+ * applied in order; a Stored event whose parent is unknown is retried as a fresh chain, as the reference does (*out_fallbacks counts). */
+typedef enum smgx_kv_event_kind { SMGX_KV_STORED = 0, SMGX_KV_REMOVED = 1, SMGX_KV_CLEARED = 2 } smgx_kv_event_kind;
+typedef struct smgx_kv_event {
+    uint32_t kind;               /* smgx_kv_event_kind */
+    uint32_t worker_id;          /* from smgx_indexer_intern_worker */
+    uint32_t first_block, n_blocks;
+    int64_t parent_block_hash;   /* KvBlocksStored.parent_block_hash */
+    uint32_t has_parent;
+    uint32_t reserved;
+} smgx_kv_event;
+smgx_status smgx_kv_events_apply(smgx_policy* p, const char* model_key, const smgx_kv_event* events, uint32_t n_events, const int64_t* block_hashes,
+                                 const uint32_t* block_tok_offsets, const uint32_t* token_ids, uint32_t n_blocks, uint32_t* out_fallbacks, char** err);
+
 /* find_matches (:461) on the GPU: `content_hashes` (host) → per-worker overlap.  out_scores[w] = 0 means "absent from
  * OverlapScores.scores"; out_tree_sizes[w] is valid where out_scores[w] > 0.  Arrays hold `cap` entries (≥ worker count). */
 smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, const uint64_t* content_hashes, uint32_t n,

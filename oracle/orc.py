@@ -213,6 +213,31 @@ class PositionalIndexer:
         return ({int(ids[i]): int(sc[i]) for i in range(n)}, {int(ids[i]): int(ts[i]) for i in range(n)})
 
 
+def apply_kv_events(indexer: "PositionalIndexer", worker_id: int, events):
+    """KvEventMonitor::apply_event over one batch (model_gateway/src/worker/kv_event_monitor.rs:525-597): Stored → convert_kv_block
+    (content hash of the block's own token_ids, i64 block hashes reinterpreted as u64 :592-597) + apply_stored with the fresh-chain
+    retry on ApplyError (:559-571); Removed → apply_removed; Cleared → apply_cleared.  Returns the number of fallbacks."""
+    fallbacks = 0
+    for ev in events:
+        if "stored" in ev:
+            st = ev["stored"]
+            blocks = [(int(b["block_hash"]) & 0xFFFFFFFFFFFFFFFF, compute_content_hash(b.get("token_ids", []))) for b in st.get("blocks", [])]
+            parent = st.get("parent_block_hash")
+            try:
+                indexer.apply_stored(worker_id, blocks, None if parent is None else int(parent) & 0xFFFFFFFFFFFFFFFF)
+            except ApplyError:
+                fallbacks += 1
+                try:
+                    indexer.apply_stored(worker_id, blocks, None)
+                except ApplyError:
+                    pass
+        elif "removed" in ev:
+            indexer.apply_removed(worker_id, [int(h) & 0xFFFFFFFFFFFFFFFF for h in ev["removed"].get("block_hashes", [])])
+        elif "cleared" in ev:
+            indexer.apply_cleared(worker_id)
+    return fallbacks
+
+
 class TokenMatch:
     def __init__(self, tenant, matched, inp, nodes, edge, valid):
         self.tenant, self.matched_token_count, self.input_token_count = tenant, matched, inp

@@ -21,6 +21,11 @@ class Config(C.Structure):
                 ("device_id", C.c_int32), ("max_batch", C.c_uint32), ("max_tokens_per_request", C.c_uint32), ("tree_batch_mode", C.c_uint32)]
 
 
+class KvEvent(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("worker_id", C.c_uint32), ("first_block", C.c_uint32), ("n_blocks", C.c_uint32),
+                ("parent_block_hash", C.c_int64), ("has_parent", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class DecisionInfo(C.Structure):
     _fields_ = [("matched", C.c_uint32), ("input", C.c_uint32), ("branch", C.c_uint8), ("nodes", C.c_uint8), ("reserved", C.c_uint8 * 2)]
 
@@ -84,6 +89,7 @@ def load():
     sig("smgx_indexer_remove_worker", st, vp, cp, u32, pp)
     sig("smgx_indexer_current_size", st, vp, cp, P(u64), pp)
     sig("smgx_indexer_entry_count", st, vp, cp, P(u64), pp)
+    sig("smgx_kv_events_apply", st, vp, cp, vp, u32, vp, vp, vp, u32, P(u32), pp)
     sig("smgx_indexer_find_matches", st, vp, cp, vp, u32, C.c_int, vp, vp, u32, P(u32), pp)
     sig("smgx_content_hashes", st, vp, vp, u32, u32, vp, u32, P(u32), pp)
     sig("smgx_tree_create", st, vp, cp, C.c_int, pp)

@@ -529,6 +529,13 @@ __global__ void content_hashes_kernel(const uint32_t* __restrict__ tokens, uint3
     if (b < nb) out[b] = xxh3_words(tokens + (size_t)b * bs, bs, kSeed);
 }
 
+// convert_kv_block for a batch of KV events (kv_event_monitor.rs:592-597): block j carries token_ids[offs[j] .. offs[j+1]) — any length,
+// also empty — and its content hash is XXH3-64(seed 1337) over their little-endian bytes.  One thread per block.
+__global__ void content_hashes_ragged_kernel(const uint32_t* __restrict__ tokens, const uint32_t* __restrict__ offs, uint32_t n_blocks, uint64_t* out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_blocks) out[j] = xxh3_words(tokens + offs[j], offs[j + 1] - offs[j], kSeed);
+}
+
 __global__ void fill_kernel(uint32_t* d, uint32_t value, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -780,6 +787,12 @@ void launch_shard_reduce_wait(const uint8_t* d_parity_base, size_t cand_off, uin
     shard_reduce_kernel<<<std::max<uint32_t>(1, (n + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const smgx_shard_candidate*>(d_parity_base + cand_off), d_parity_base + fleet_off, fleet_stride, d_global_base, world, n, cand_stride,
         abs_threshold, rel_threshold, d_out_idx, d_out_info, reinterpret_cast<const uint64_t*>(d_parity_base + flag_off), seq, d_err);
+    SMGX_CUDA(cudaGetLastError());
+}
+
+void launch_content_hashes_ragged(const uint32_t* d_tokens, const uint32_t* d_offs, uint32_t n_blocks, uint64_t* d_out, cudaStream_t stream) {
+    if (!n_blocks) return;
+    content_hashes_ragged_kernel<<<(n_blocks + 127) / 128, 128, 0, stream>>>(d_tokens, d_offs, n_blocks, d_out);
     SMGX_CUDA(cudaGetLastError());
 }
 

@@ -74,6 +74,7 @@ void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uin
 // compute_request_content_hashes for one request.
 void launch_content_hashes(const uint32_t* d_tokens, uint32_t n_tokens, uint32_t block_size, uint64_t* d_out, cudaStream_t stream);
 
+void launch_content_hashes_ragged(const uint32_t* d_tokens, const uint32_t* d_offs, uint32_t n_blocks, uint64_t* d_out, cudaStream_t stream);
 void launch_fill(uint32_t* d, uint32_t value, size_t n_words, cudaStream_t stream);
 // peer-memory exchange of the sharded pick (smgx.cu: Exchange)
 void launch_shard_push(const smgx_shard_candidate* d_cand, uint32_t n, const smgx_shard_fleet* d_fleet, uint8_t* const* d_peer_parity_base, uint32_t world,

@@ -910,6 +910,62 @@ smgx_status smgx_indexer_apply_stored_tokens(smgx_policy* p, const char* model_k
     return smgx_indexer_apply_stored(p, model_key, worker_id, seq_hashes, hashes.data(), n_blocks, parent_seq_hash, err);
 }
 
+// KvEventMonitor::apply_event for a batch of events of one model (worker/kv_event_monitor.rs:525-597): every stored block's
+// token_ids are hashed in ONE kernel launch (convert_kv_block :592-597), then the events are applied in order on the
+// host-authoritative index — Stored with the fresh-chain retry on WorkerNotTracked / ParentBlockNotFound (:559-571), Removed, Cleared.
+smgx_status smgx_kv_events_apply(smgx_policy* p, const char* model_key, const smgx_kv_event* events, uint32_t n_events, const int64_t* block_hashes,
+                                 const uint32_t* block_tok_offsets, const uint32_t* token_ids, uint32_t n_blocks, uint32_t* out_fallbacks, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n_events == 0 || events, "Invalid arguments: null pointer");
+        SMGX_REQUIRE(n_blocks == 0 || (block_hashes && block_tok_offsets), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        EventIndex& ix = P.indexer(model_key);
+        std::vector<uint64_t> content(n_blocks);
+        uint32_t n_stored = 0;
+        for (uint32_t e = 0; e < n_events; ++e) {
+            SMGX_REQUIRE(events[e].kind <= SMGX_KV_CLEARED, "unknown event kind");
+            if (events[e].kind != SMGX_KV_CLEARED) SMGX_REQUIRE((uint64_t)events[e].first_block + events[e].n_blocks <= n_blocks, "event block range out of bounds");
+            if (events[e].kind == SMGX_KV_STORED) n_stored += events[e].n_blocks;
+        }
+        if (n_stored) {   // hash every block of the batch (removed events' slots are hashed too when they carry tokens; they are ignored below)
+            P.use_device();
+            for (uint32_t j = 0; j < n_blocks; ++j) SMGX_REQUIRE(block_tok_offsets[j + 1] >= block_tok_offsets[j], "block token offsets must be non-decreasing");
+            const uint32_t n_tok = block_tok_offsets[n_blocks];
+            SMGX_REQUIRE(n_tok == 0 || token_ids, "Invalid arguments: null pointer");
+            Lane& l = P.lanes[0];
+            P.scratch.reserve(std::max<size_t>((size_t)n_tok, 1) * 4 + ((size_t)n_blocks + 1) * 4 + 64);
+            P.scratch2.reserve((size_t)n_blocks * 8);
+            uint32_t* d_tok = P.scratch.as<uint32_t>();
+            uint32_t* d_off = d_tok + std::max<uint32_t>(n_tok, 1);
+            if (n_tok) SMGX_CUDA(cudaMemcpyAsync(d_tok, token_ids, (size_t)n_tok * 4, cudaMemcpyHostToDevice, l.stream));
+            SMGX_CUDA(cudaMemcpyAsync(d_off, block_tok_offsets, ((size_t)n_blocks + 1) * 4, cudaMemcpyHostToDevice, l.stream));
+            launch_content_hashes_ragged(d_tok, d_off, n_blocks, P.scratch2.as<uint64_t>(), l.stream);
+            ++P.launches;
+            SMGX_CUDA(cudaMemcpyAsync(content.data(), P.scratch2.ptr, (size_t)n_blocks * 8, cudaMemcpyDeviceToHost, l.stream));
+            SMGX_CUDA(cudaStreamSynchronize(l.stream));
+        }
+        uint32_t fallbacks = 0;
+        std::vector<uint64_t> seq;
+        for (uint32_t e = 0; e < n_events; ++e) {
+            const smgx_kv_event& ev = events[e];
+            if (ev.kind == SMGX_KV_CLEARED) { ix.apply_cleared(ev.worker_id); continue; }
+            seq.resize(ev.n_blocks);
+            for (uint32_t j = 0; j < ev.n_blocks; ++j) seq[j] = (uint64_t)block_hashes[ev.first_block + j];   // SequenceHash::from(i64): bit reinterpretation (:643)
+            if (ev.kind == SMGX_KV_REMOVED) { ix.apply_removed(ev.worker_id, seq.data(), ev.n_blocks); continue; }
+            const uint64_t parent = (uint64_t)ev.parent_block_hash;
+            smgx_status st = ix.apply_stored(ev.worker_id, seq.data(), content.data() + ev.first_block, ev.n_blocks, ev.has_parent ? &parent : nullptr);
+            if (st == SMGX_WORKER_NOT_TRACKED || st == SMGX_PARENT_BLOCK_NOT_FOUND) {   // cold start or parent evicted: start a new chain
+                ++fallbacks;
+                ix.apply_stored(ev.worker_id, seq.data(), content.data() + ev.first_block, ev.n_blocks, nullptr);
+            }
+        }
+        if (out_fallbacks) *out_fallbacks = fallbacks;
+        return SMGX_SUCCESS;
+    });
+}
+
 smgx_status smgx_indexer_find_matches(smgx_policy* p, const char* model_key, const uint64_t* content_hashes, uint32_t n, int early_exit,
                                       uint32_t* out_scores, uint64_t* out_tree_sizes, uint32_t cap, uint32_t* out_n_workers, char** err) {
     return guard(err, [&]() {

@@ -196,6 +196,7 @@ class KvEventMonitor:
 
     def __init__(self, policy: "CacheAwarePolicy", default_block_size: Optional[int] = None):
         self.policy, self.default_block_size, self.indexers = policy, default_block_size, {}
+        self._learned = {}
 
     def create_indexer(self, model: str, jump_size: int = 64) -> PositionalIndexer:  # DEFAULT_JUMP_SIZE kv_event_monitor.rs:31
         ix = PositionalIndexer(self.policy._h, model, jump_size)
@@ -207,6 +208,44 @@ class KvEventMonitor:
 
     def set_block_size(self, model: str, block_size: int):
         self.policy._h.call("smgx_indexer_set_block_size", model.encode(), block_size)
+
+    def apply_events(self, model: str, worker_id: int, events):
+        """One KvEventBatch of a worker's stream (kv_event_monitor.rs:513-517, apply_event :525-597) through smgx_kv_events_apply.
+        `events`: dicts shaped like the proto — {"stored": {"blocks": [{"block_hash", "token_ids", "block_size"}...],
+        "parent_block_hash": int | None}}, {"removed": {"block_hashes": [...]}} or {"cleared": {}}.  The first stored block with
+        block_size > 0 teaches the model's block size once (learn_block_size :270-296).  Returns the number of fresh-chain fallbacks."""
+        evs, hashes, toks, offs = [], [], [], [0]
+        for ev in events:
+            if "stored" in ev:
+                st = ev["stored"]
+                blocks = st.get("blocks", [])
+                if blocks and not self._learned.get(model) and blocks[0].get("block_size", 0) > 0:
+                    self.set_block_size(model, int(blocks[0]["block_size"]))
+                    self._learned[model] = True
+                parent = st.get("parent_block_hash")
+                evs.append((0, len(hashes), len(blocks), 0 if parent is None else int(parent), 0 if parent is None else 1))
+                for b in blocks:
+                    hashes.append(int(b["block_hash"]))
+                    toks.extend(int(t) for t in b.get("token_ids", []))
+                    offs.append(len(toks))
+            elif "removed" in ev:
+                hs = [int(h) for h in ev["removed"].get("block_hashes", [])]
+                evs.append((1, len(hashes), len(hs), 0, 0))
+                for h in hs:
+                    hashes.append(h)
+                    offs.append(len(toks))
+            elif "cleared" in ev:
+                evs.append((2, 0, 0, 0, 0))
+        arr = (_lib.KvEvent * max(len(evs), 1))()
+        for i, (k, fb, nb, par, hp) in enumerate(evs):
+            arr[i].kind, arr[i].worker_id, arr[i].first_block, arr[i].n_blocks = k, worker_id, fb, nb
+            arr[i].parent_block_hash, arr[i].has_parent = par, hp
+        h64 = np.ascontiguousarray(np.asarray([x if x < 2**63 else x - 2**64 for x in hashes] or [0], dtype=np.int64))
+        t32, o32 = _u32(toks), _u32(offs)
+        fallbacks = C.c_uint32()
+        self.policy._h.call("smgx_kv_events_apply", model.encode(), C.cast(arr, C.c_void_p), len(evs), _p(h64), _p(o32), _p(t32) if t32.size else None,
+                            len(hashes), C.byref(fallbacks))
+        return fallbacks.value
 
 
 class TokenMatchResult:  # kv_index::PrefixMatchResult (token_tree.rs:137-144)

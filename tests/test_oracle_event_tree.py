@@ -60,3 +60,28 @@ def test_xxh3_against_live_xxhash_if_present():
         assert orc.xxh3_64(d, 1337) == xxhash.xxh3_64_intdigest(d, seed=1337)
     toks = [rng.getrandbits(32) for _ in range(16)]
     assert orc.compute_content_hash(toks) == xxhash.xxh3_64_intdigest(struct.pack("<16I", *toks), seed=1337)
+
+
+def test_apply_kv_events_reference_cases():
+    """orc.apply_kv_events restates KvEventMonitor::apply_event; pinned by the reference's tests (kv_event_monitor.rs:629-760)."""
+    def blk(h, toks):
+        return {"block_hash": h, "token_ids": toks, "block_size": len(toks)}
+    ix = orc.PositionalIndexer(64)
+    w = ix.intern_worker("http://w1:8000")
+    assert orc.apply_kv_events(ix, w, [{"stored": {"blocks": [blk(1, [10, 20, 30, 40]), blk(2, [50, 60, 70, 80])], "parent_block_hash": None}}]) == 0
+    assert ix.current_size() == 2                                                        # test_apply_stored_no_parent
+    ix = orc.PositionalIndexer(64)
+    w = ix.intern_worker("http://w1:8000")
+    orc.apply_kv_events(ix, w, [{"stored": {"blocks": [blk(1, [10, 20, 30, 40])], "parent_block_hash": None}}])
+    assert orc.apply_kv_events(ix, w, [{"stored": {"blocks": [blk(2, [50, 60, 70, 80])], "parent_block_hash": 1}}]) == 0
+    assert ix.current_size() == 2                                                        # test_apply_stored_with_parent
+    ix = orc.PositionalIndexer(64)
+    w = ix.intern_worker("http://new-worker:8000")
+    assert orc.apply_kv_events(ix, w, [{"stored": {"blocks": [blk(1, [10, 20, 30, 40])], "parent_block_hash": 999}}]) == 1
+    assert ix.current_size() == 1                                                        # test_apply_stored_fallback_on_worker_not_tracked
+    orc.apply_kv_events(ix, w, [{"stored": {"blocks": [blk(-1, [1, 2])], "parent_block_hash": 1}}])      # −1 ≡ u64::MAX (:643)
+    assert orc.apply_kv_events(ix, w, [{"stored": {"blocks": [blk(5, [3, 4])], "parent_block_hash": 2**64 - 1}}]) == 0
+    orc.apply_kv_events(ix, w, [{"removed": {"block_hashes": [5]}}])
+    assert ix.current_size() == 2
+    orc.apply_kv_events(ix, w, [{"cleared": {}}])
+    assert ix.current_size() == 0

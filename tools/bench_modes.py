@@ -221,6 +221,51 @@ def text_mode():
             "trees_identical_after": True, "kernel_launches": pol.kernel_launches()}
 
 
+def ingest_mode():
+    """KV-event ingest: batches of 1024 Stored events (one 512-token sequence = 32 blocks of 16 tokens each, for worker
+    i mod 64) through smgx_kv_events_apply — token_ids hashed in one GPU launch per batch, index writers on the host — vs the oracle's
+    apply_event path on one core (hash on the CPU, then apply_stored)."""
+    from oracle import orc
+    from smg_b200 import CacheAwareConfig, CacheAwarePolicy, _lib, synth
+    W, E, P, bs = 64, 1024, 32, 16
+    n_batches = int(os.environ.get("BATCHES", "16"))
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG))
+    mon = pol.kv_event_monitor(bs)
+    ix = mon.create_indexer("unknown", 64)
+    pol.set_kv_event_monitor(mon)
+    oix = orc.PositionalIndexer(64)
+    for u in synth.worker_urls(W):
+        ix.intern_worker(u); oix.intern_worker(u)
+    seqs = synth.gen_sequences(E * n_batches, P * bs, 7)
+    Lo = orc.lib()
+    t_gpu = t_cpu = 0.0
+    offs = (np.arange(E * P + 1, dtype=np.uint64) * bs).astype(np.uint32)
+    for b in range(n_batches):
+        toks = np.ascontiguousarray(seqs[b * E:(b + 1) * E].reshape(-1))
+        hashes = np.arange(1 + b * E * P, 1 + (b + 1) * E * P, dtype=np.int64)
+        evs = (_lib.KvEvent * E)()
+        for e in range(E):
+            evs[e].kind, evs[e].worker_id, evs[e].first_block, evs[e].n_blocks, evs[e].has_parent = 0, (b * E + e) % W, e * P, P, 0
+        fb = C.c_uint32()
+        t0 = time.perf_counter()
+        pol._h.call("smgx_kv_events_apply", b"unknown", C.cast(evs, C.c_void_p), E, hashes.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                    toks.ctypes.data_as(C.c_void_p), E * P, C.byref(fb))
+        t_gpu += time.perf_counter() - t0
+        content = np.zeros(E * P, np.uint64)
+        useq = hashes.view(np.uint64)
+        t0 = time.perf_counter()
+        for e in range(E):
+            row = toks[e * P * bs:(e + 1) * P * bs]
+            Lo.orc_request_content_hashes(row.ctypes.data_as(C.c_void_p), P * bs, bs, content[e * P:].ctypes.data_as(C.c_void_p), P)
+            Lo.orc_indexer_apply_stored(oix.h, (b * E + e) % W, useq[e * P:].ctypes.data_as(C.c_void_p), content[e * P:].ctypes.data_as(C.c_void_p), P, 0, 0)
+        t_cpu += time.perf_counter() - t0
+    assert ix.current_size() == oix.current_size() and ix.entry_count() == oix.entry_count()
+    n_ev = E * n_batches
+    return {"mode": "KV-event ingest: smgx_kv_events_apply (token_ids hashed on the GPU, one launch per 1024-event batch; index writers on the host mirror)",
+            "events": n_ev, "blocks_per_event": P, "tokens_per_block": bs, "smgx_events_per_s": n_ev / t_gpu, "smgx_blocks_per_s": n_ev * P / t_gpu,
+            "oracle_1core_events_per_s": n_ev / t_cpu, "index_entries_after": int(ix.entry_count()), "state_equal": True}
+
+
 def sharded_mode():
     import torch
     import torch.distributed as dist
@@ -325,6 +370,6 @@ def sharded_mode():
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "tree"
-    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "sharded": sharded_mode}[mode]()
+    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "ingest": ingest_mode, "sharded": sharded_mode}[mode]()
     if r is not None:
         print(json.dumps(r), flush=True)
