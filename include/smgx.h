@@ -221,6 +221,10 @@ smgx_status smgx_stree_prefix_match_tenant(smgx_policy* p, const char* model_key
 smgx_status smgx_stree_sizes(smgx_policy* p, const char* model_key, int maintained, char** out_text, char** err);
 /* iter_entries (:1116-1221), pre-order, children in char order: records "path \x1f tenant=epoch;... \x1e". smgx_free_string. */
 smgx_status smgx_stree_entries(smgx_policy* p, const char* model_key, char** out_text, uint64_t* out_len, char** err);
+/* Read-only walk + pick of device-resident text batches (the string-tree kernel on its own — bench); d_out_node[j][i] = node the walk ended on. */
+smgx_status smgx_stree_walk_many_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint8_t* const* d_text,
+                                        const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx,
+                                        smgx_decision_info* const* d_out_info, uint32_t* const* d_out_node, char** err);
 smgx_status smgx_stree_clear(smgx_policy* p, const char* model_key, char** err);
 smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err);
 

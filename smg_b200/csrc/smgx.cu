@@ -1497,6 +1497,44 @@ smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_
     });
 }
 
+// Read-only walk + pick of device-resident text batches against the current string tree: the K2c kernel by itself (bench).
+smgx_status smgx_stree_walk_many_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint8_t* const* d_text,
+                                        const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx,
+                                        smgx_decision_info* const* d_out_info, uint32_t* const* d_out_node, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n_batches == 0 || (d_text && d_offsets && n && d_out_worker_idx && d_out_node), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        StringTreeIndex& tree = P.stree_of(m);
+        EventIndexView ixv;
+        FleetView fv;
+        P.sync_state(m, &ixv, &fv);
+        P.sync_tenant_map(m);
+        for (auto& l : P.lanes) if (l.has_done) SMGX_CUDA(cudaStreamWaitEvent(P.ctrl, l.done, 0));
+        const StringTreeView tv = tree.flush(P.ctrl, &P.launches);
+        SMGX_CUDA(cudaEventRecord(P.state_ready, P.ctrl));
+        for (auto& l : P.lanes) SMGX_CUDA(cudaStreamWaitEvent(l.stream, P.state_ready, 0));
+        for (uint32_t j = 0; j < n_batches; ++j) {
+            Lane& lane = P.lanes[(P.walk_chunk_seq++) % P.lanes.size()];
+            lane.d_tenant.reserve((size_t)std::max<uint32_t>(n[j], 1) * 4);
+            lane.d_fill.reserve(std::max<uint32_t>(n[j], 1));
+            StringSelectArgs a{};
+            a.text = d_text[j]; a.offsets = d_offsets[j]; a.first = 0; a.count = n[j];
+            a.out_idx = d_out_worker_idx[j]; a.out_info = d_out_info ? d_out_info[j] : nullptr;
+            a.out_node = d_out_node[j]; a.out_tenant = lane.d_tenant.as<int32_t>(); a.out_fill = lane.d_fill.as<uint8_t>();
+            a.cache_threshold = P.cfg.cache_threshold; a.decide = 1;
+            launch_string_select(tv, fv, m.d_slice_of_tenant.as<int32_t>(), m.d_flags.as<uint8_t>(), (uint32_t)P.tenants.names.size(), a, lane.stream);
+            ++P.launches;
+            SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
+            lane.has_done = true;
+        }
+        return SMGX_SUCCESS;
+    });
+}
+
 smgx_status smgx_set_tree_batch_mode(smgx_policy* p, uint32_t mode, char** err) {
     return guard(err, [&]() {
         NONNULL(p);

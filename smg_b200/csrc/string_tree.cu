@@ -442,29 +442,91 @@ StringTreeView StringTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
 namespace {
 constexpr unsigned FULLM = 0xffffffffu;
 
-// number of chars (non-continuation bytes) in s[0..n), warp-cooperative; result on every lane
-__device__ __forceinline__ uint32_t warp_count_chars(const uint8_t* __restrict__ s, uint32_t n, int lane) {
-    uint32_t c = 0;
-    for (uint32_t i = lane; i < n; i += 32) c += (s[i] & 0xC0) != 0x80;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULLM, c, d);
-    return c;
+// continuation bytes (10xxxxxx) in the 4 bytes of w
+__device__ __forceinline__ uint32_t cont_bytes(uint32_t w) { return (uint32_t)__popc((w >> 7) & ~(w >> 6) & 0x01010101u); }
+
+// 16 bytes starting at the arbitrarily aligned address `p`, from the two aligned 16-byte chunks around it.  The byte shift is the
+// same for every lane of a warp whose addresses differ by multiples of 16, so the switch is warp-uniform.
+__device__ __forceinline__ uint4 shift16(const uint4 lo, const uint4 hi, uint32_t s) {
+    const uint32_t r = (s & 3) * 8;
+    uint32_t w0, w1, w2, w3, w4;
+    switch (s >> 2) {
+        case 0: w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
+        case 1: w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
+        case 2: w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
+        default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
+    }
+    return make_uint4(__funnelshift_r(w0, w1, r), __funnelshift_r(w1, w2, r), __funnelshift_r(w2, w3, r), __funnelshift_r(w3, w4, r));
+}
+__device__ __forceinline__ uint4 load16_global(const uint8_t* p) {
+    const uint32_t s = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+    const uint4* a = reinterpret_cast<const uint4*>(p - s);
+    const uint4 lo = __ldg(a);
+    if (s == 0) return lo;
+    return shift16(lo, __ldg(a + 1), s);
+}
+__device__ __forceinline__ uint4 load16_shared(const uint8_t* p) {   // p inside a 16-byte-aligned shared array with 16 bytes of slack
+    const uint32_t s = (uint32_t)(__cvta_generic_to_shared(p) & 15);
+    const uint4* a = reinterpret_cast<const uint4*>(p - s);
+    const uint4 lo = a[0];
+    if (s == 0) return lo;
+    return shift16(lo, a[1], s);
 }
 
+constexpr uint32_t kTxtWin = 4096;   // request bytes staged per warp (a whole chat-sized request)
+
+// One warp per request.  The request is staged in shared memory 16 bytes per lane and load (char count taken on the way), labels
+// are compared 512 bytes per step — 16 bytes per lane from the label (global, any alignment) against 16 from the staged request
+// (shared, any alignment), both assembled from aligned 16-byte loads by a warp-uniform byte shift.
 __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, FleetView f, const int32_t* __restrict__ slice_of_tenant,
                                                             const uint8_t* __restrict__ flags, uint32_t n_tenants, StringSelectArgs a) {
+    __shared__ __align__(16) uint8_t win_all[8][kTxtWin + 32];
     const int lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= a.count) return;
     const uint32_t r = a.first + w;
     const uint32_t off = a.offsets[r], nbytes = a.offsets[r + 1] - off;
     const uint8_t* s = a.text + off;
-    const uint32_t input_chars = warp_count_chars(s, nbytes, lane);
+    uint8_t* win = win_all[threadIdx.x >> 5];
+    uint32_t wbase = 0, wend = 0, wshift = 0;   // request bytes [wbase, wend) are staged; byte wbase sits at win[wshift]
+    auto load_window = [&](uint32_t start) {
+        __syncwarp();
+        const uint8_t* g0 = s + start;
+        wshift = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15);
+        wbase = start;
+        wend = min(nbytes, start + kTxtWin - 16);
+        const uint32_t span = wshift + (wend - wbase);                      // bytes to copy from the aligned address below g0
+        const uint4* src = reinterpret_cast<const uint4*>(g0 - wshift);
+        for (uint32_t c = lane; c * 16 < span; c += 32) reinterpret_cast<uint4*>(win)[c] = __ldg(src + c);   // only chunks that hold request bytes
+        __syncwarp();
+    };
+    auto rq = [&](uint32_t pos) -> const uint8_t* { return win + wshift + (pos - wbase); };   // staged request byte `pos`
+    // chars of the whole request = bytes − continuation bytes, streamed 16 bytes per lane (head / tail chunks byte by byte)
+    uint32_t cont = 0;
+    {
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 15);
+        const uint4* src = reinterpret_cast<const uint4*>(s - sh);
+        const uint32_t span = sh + nbytes;
+        for (uint32_t c = lane; c * 16 < span; c += 32) {
+            const uint4 v = __ldg(src + c);
+            const uint32_t lo = c * 16, hi = lo + 16;
+            if (lo >= sh && hi <= span) cont += cont_bytes(v.x) + cont_bytes(v.y) + cont_bytes(v.z) + cont_bytes(v.w);
+            else {
+                const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+                for (uint32_t k = 0; k < 16; ++k) { const uint32_t g = lo + k; if (g >= sh && g < span) cont += (((ws[k >> 2] >> (8 * (k & 3))) & 0xC0) == 0x80); }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) cont += __shfl_xor_sync(FULLM, cont, d);
+    }
+    const uint32_t input_chars = nbytes - cont;
+    if (nbytes) load_window(0);
 
     uint32_t cur = 0, pos = 0, matched = 0, terminal = 0, visited = 0;
     while (pos < nbytes) {
+        if (pos < wbase || pos + 4 > wend) { if (!(pos >= wbase && wend == nbytes)) load_window(pos); }
         uint32_t cl;
-        const uint32_t cp = utf8_first(s + pos, &cl);   // every lane reads the same ≤ 4 bytes (broadcast)
+        const uint32_t cp = utf8_first(rq(pos), &cl);   // every lane reads the same ≤ 4 staged bytes
         const uint64_t key = str_child_key(cur, cp);
         uint32_t idx = str_child_home(key) & tv.child_mask;
         uint32_t child = kNoNode;
@@ -481,22 +543,43 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
         const uint32_t label_bytes = h4.z, label_chars = h4.w;
         const uint8_t* lab = tv.bytes + label_off;
         const uint32_t L = min(label_bytes, nbytes - pos);
-        // common byte prefix, 128 bytes per step (4 consecutive bytes per lane)
         uint32_t common = L;
-        for (uint32_t c = 0; c < L; c += 128) {
-            const uint32_t b = c + (uint32_t)lane * 4;
-            uint32_t first = 4;
+        for (uint32_t c = 0; c < L; c += 512) {
+            if (pos + c < wbase || pos + c + min(512u, L - c) > wend) load_window(pos + c);
+            const uint32_t b = c + (uint32_t)lane * 16;
+            uint32_t first = 16;   // index of my first differing byte
+            if (b < L) {
+                const uint4 x = load16_global(lab + b), y = load16_shared(rq(pos + b));
+                const uint32_t nv = min(16u, L - b);
+                const uint32_t dw[4] = {x.x ^ y.x, x.y ^ y.y, x.z ^ y.z, x.w ^ y.w};
 #pragma unroll
-            for (int k = 3; k >= 0; --k) if (b + k < L && __ldg(lab + b + k) != s[pos + b + k]) first = (uint32_t)k;
-            const unsigned mm = __ballot_sync(FULLM, first < 4);
+                for (int k = 3; k >= 0; --k) if (dw[k]) first = (uint32_t)k * 4 + ((uint32_t)__ffs((int)dw[k]) - 1) / 8;
+                if (first >= nv) first = 16;
+            }
+            const unsigned mm = __ballot_sync(FULLM, first < 16);
             if (mm) {
                 const int src = __ffs((int)mm) - 1;
-                common = c + (uint32_t)src * 4 + __shfl_sync(FULLM, first, src);
+                common = c + (uint32_t)src * 16 + __shfl_sync(FULLM, first, src);
                 break;
             }
         }
-        if (common < L) while (common > 0 && (s[pos + common] & 0xC0) == 0x80) --common;   // mismatch inside a char
-        const uint32_t shared_chars = common == label_bytes ? label_chars : warp_count_chars(s + pos, common, lane);
+        if (common < L) {   // mismatch inside a char: back to its first byte (at most 3 bytes back)
+            const uint32_t back = min(common, 4u);
+            if (pos + common - back < wbase || pos + common >= wend) load_window(pos + common - back);
+            while (common > 0 && (*rq(pos + common) & 0xC0) == 0x80) --common;
+        }
+        uint32_t shared_chars = label_chars;
+        if (common != label_bytes) {   // chars in the matched part of the edge
+            uint32_t cb = 0;
+            for (uint32_t c0 = 0; c0 < common; c0 += 2048) {
+                const uint32_t c1 = min(common, c0 + 2048);
+                if (pos + c0 < wbase || pos + c1 > wend) load_window(pos + c0);
+                for (uint32_t i = c0 + lane; i < c1; i += 32) cb += (*rq(pos + i) & 0xC0) == 0x80;
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) cb += __shfl_xor_sync(FULLM, cb, d);
+            shared_chars = common - cb;
+        }
         matched += shared_chars;
         terminal = child;                       // a partial edge match still selects that child (:582-586)
         ++visited;

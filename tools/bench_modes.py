@@ -221,6 +221,96 @@ def text_mode():
             "trees_identical_after": True, "kernel_launches": pol.kernel_launches()}
 
 
+def textwalk_mode():
+    """K2c by itself: read-only walk + pick of HBM-resident text batches against a string tree of DOCS chat-shaped documents
+    (32 shared ≈1.2 KB system prompts + distinct tails, ≈2 KB each)."""
+    import random
+    from smg_b200 import BasicWorker, CacheAwareConfig, CacheAwarePolicy, _lib, synth
+    W, B = 64, 4096
+    n_docs = int(os.environ.get("DOCS", "100000"))
+    ring, steps, per_call = int(os.environ.get("RING", "32")), int(os.environ.get("STEPS", "20")), int(os.environ.get("PER_CALL", "8"))
+    urls = synth.worker_urls(W)
+    pol = CacheAwarePolicy(CacheAwareConfig(eviction_interval_secs=0, **CFG), max_batch=B)
+    ws = [BasicWorker(u) for u in urls]
+    for w, l in zip(ws, synth.poisson_loads(W, 8, 42)):
+        w.set_load(int(l))
+    pol.init_workers(ws)
+    model = pol._push_fleet(ws)
+    h, L = pol._h, _lib.load()
+    r = random.Random(7)
+    words = ["cache", "aware", "router", "prefix", "radix", "tree", "worker", "tenant", "load", "balance", "token", "你好", "été", "GPU", "latency", "batch"]
+    systems = [" ".join(r.choice(words) for _ in range(200)) for _ in range(32)]
+    def doc():
+        return r.choice(systems) + " " + " ".join(r.choice(words) for _ in range(r.randrange(60, 160)))
+    docs = [doc() for _ in range(n_docs)]
+    tree = pol.string_tree()
+    t0 = time.time()
+    for i, d in enumerate(docs):
+        tree.insert_text(d, urls[i % W])
+    t_build = time.time() - t0
+
+    def batch(seed):
+        rr = random.Random(seed)
+        out = []
+        for _ in range(B):
+            u = rr.random()
+            d = docs[rr.randrange(n_docs)]
+            if u < 0.8:
+                out.append(d)
+            elif u < 0.9:
+                out.append(d[: rr.randrange(100, len(d))] + " novel tail " + " ".join(rr.choice(words) for _ in range(40)))
+            else:
+                out.append(" ".join(rr.choice(words[::-1]) for _ in range(300)))
+        blobs = [t.encode() for t in out]
+        offs = np.zeros(B + 1, np.uint32)
+        np.cumsum([len(b) for b in blobs], out=offs[1:])
+        return np.frombuffer(b"".join(blobs), np.uint8).copy(), offs
+
+    err = _lib.new_err()
+    d_txt, d_off, d_out, d_info, d_node = [], [], [], [], []
+    total_bytes = 0
+    for j in range(ring):
+        data, offs = batch(500 + j)
+        total_bytes += data.size
+        pt = L.smgx_device_alloc(h.p, data.nbytes + 16, C.byref(err)); h.call("smgx_memcpy_h2d", pt, data.ctypes.data_as(C.c_void_p), data.nbytes)
+        po = L.smgx_device_alloc(h.p, offs.nbytes, C.byref(err)); h.call("smgx_memcpy_h2d", po, offs.ctypes.data_as(C.c_void_p), offs.nbytes)
+        d_txt.append(pt); d_off.append(po)
+        d_out.append(L.smgx_device_alloc(h.p, B * 4, C.byref(err)))
+        d_info.append(L.smgx_device_alloc(h.p, B * 12, C.byref(err)))
+        d_node.append(L.smgx_device_alloc(h.p, B * 4, C.byref(err)))
+    arr = lambda xs: (C.c_void_p * len(xs))(*xs)
+    ns = (C.c_uint32 * per_call)(*([B] * per_call))
+
+    def call(j0, want_info):
+        js = [(j0 + k) % ring for k in range(per_call)]
+        h.call("smgx_stree_walk_many_device", model, per_call, arr([d_txt[j] for j in js]), arr([d_off[j] for j in js]), ns,
+               arr([d_out[j] for j in js]), arr([d_info[j] for j in js]) if want_info else None, arr([d_node[j] for j in js]))
+
+    for w in range(3):
+        call(w * per_call, True)
+    h.call("smgx_synchronize")
+    info = np.zeros(B, dtype=[("matched", "<u4"), ("input", "<u4"), ("branch", "u1"), ("nodes", "u1"), ("r", "u1", 2)])
+    h.call("smgx_memcpy_d2h", info.ctypes.data_as(C.c_void_p), d_info[0], B * 12)
+    mean_bytes = total_bytes / (ring * B)
+    # algorithmic bytes / decision: request bytes + label bytes compared (≈ matched chars × bytes/char) + 48 B per visited node
+    bpc = mean_bytes / max(1.0, float(info["input"].mean()))
+    alg = float(mean_bytes + info["matched"].mean() * bpc + 48.0 * info["nodes"].mean())
+    h.call("smgx_timer_start_all")
+    for s_ in range(steps):
+        call(s_ * per_call, False)
+    ms = C.c_float()
+    h.call("smgx_timer_stop_all_ms", C.byref(ms))
+    n = steps * per_call * B
+    dps = n / (ms.value * 1e-3)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6486.8))
+    return {"mode": "K2c string-tree walk + pick kernel only (read-only, HBM-resident text; string_select_kernel)", "workers": W, "batch": B,
+            "tree_docs": n_docs, "tree_nodes": int(tree.node_count()), "tree_build_s": round(t_build, 1), "mean_request_bytes": mean_bytes,
+            "decisions_per_s": dps, "ms_per_batch": ms.value / (steps * per_call),
+            "mix": {"matched_chars_mean": float(info["matched"].mean()), "input_chars_mean": float(info["input"].mean()), "nodes_mean": float(info["nodes"].mean())},
+            "roofline": {"bound": "hbm", "alg_bytes_per_decision": alg, "achieved": alg * dps / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * dps / 1e9 / peak}}
+
+
 def ingest_mode():
     """KV-event ingest: batches of 1024 Stored events (one 512-token sequence = 32 blocks of 16 tokens each, for worker
     i mod 64) through smgx_kv_events_apply — token_ids hashed in one GPU launch per batch, index writers on the host — vs the oracle's
@@ -370,6 +460,6 @@ def sharded_mode():
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "tree"
-    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "ingest": ingest_mode, "sharded": sharded_mode}[mode]()
+    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "textwalk": textwalk_mode, "ingest": ingest_mode, "sharded": sharded_mode}[mode]()
     if r is not None:
         print(json.dumps(r), flush=True)
