@@ -18,7 +18,7 @@ StringTreeIndex::StringTreeIndex(TenantTable* tenants, uint64_t* epoch) : tenant
     mask_ = 1023;
 }
 StringTreeIndex::~StringTreeIndex() {
-    d_bytes_.release(); d_headers_.release(); d_table_.release(); d_stage_.release(); stage_.release();
+    d_bytes_.release(); d_table_.release(); d_stage_.release(); stage_.release();
     if (stage_done_) cudaEventDestroy(stage_done_);
 }
 
@@ -67,6 +67,7 @@ void StringTreeIndex::table_rebuild(uint32_t cap) {
         uint32_t idx = str_child_home(s.key) & mask_;
         while (table_[idx].key != 0) idx = (idx + 1) & mask_;
         table_[idx] = s;
+        nodes_[s.child].slot = idx;
         ++table_live_;
     }
     full_dirty_ = true;
@@ -87,6 +88,7 @@ void StringTreeIndex::table_insert(uint32_t parent, uint32_t cp, uint32_t child)
     }
     if (tomb >= 0) { idx = (uint32_t)tomb; --table_tombs_; }
     table_[idx] = StrChildSlot{key, child, 0};
+    nodes_[child].slot = idx;
     ++table_live_;
     mark_slot(idx);
 }
@@ -94,11 +96,13 @@ void StringTreeIndex::table_set(uint32_t parent, uint32_t cp, uint32_t child) {
     const int64_t s = find_child(parent, cp);
     if (s < 0) { table_insert(parent, cp, child); return; }
     table_[(size_t)s].child = child;
+    nodes_[child].slot = (uint32_t)s;
     mark_slot((uint32_t)s);
 }
 void StringTreeIndex::table_erase(uint32_t parent, uint32_t cp) {
     const int64_t s = find_child(parent, cp);
     if (s < 0) return;
+    if (nodes_[table_[(size_t)s].child].slot == (uint32_t)s) nodes_[table_[(size_t)s].child].slot = kNoNode;
     table_[(size_t)s].child = kTombChild;
     --table_live_;
     ++table_tombs_;
@@ -361,25 +365,23 @@ void StringTreeIndex::entries(std::vector<std::pair<std::string, std::vector<std
 // device mirror
 // =================================================================================================================
 namespace {
-__global__ void scatter_slots_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) dst[idx[t]] = src[t];
-}
-__global__ void scatter_headers_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
+__global__ void scatter32_kernel(uint4* __restrict__ dst, const uint32_t* __restrict__ idx, const uint4* __restrict__ src, uint32_t n) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) { const size_t d = (size_t)idx[t] * 2; dst[d] = src[(size_t)t * 2]; dst[d + 1] = src[(size_t)t * 2 + 1]; }
 }
 }  // namespace
 
-StrHeader StringTreeIndex::header_of(uint32_t id) const {
-    const Node& nd = nodes_[id];
-    StrHeader h{};
-    h.label_off = nd.label_off;
-    h.label_bytes = nd.alive ? nd.label_bytes : 0;
-    h.label_chars = nd.alive ? nd.label_chars : 0;
-    h.any_tenant = nd.alive ? any_tenant(nd) : -1;
-    h.cache_valid = nd.alive && cache_valid(nd) ? 1u : 0u;
-    return h;
+StrSlot StringTreeIndex::device_slot(uint32_t i) const {
+    const StrChildSlot& c = table_[i];
+    StrSlot t{c.key, c.child, 0, 0, 0, -1};
+    if (c.key != 0 && c.child < kTombChild) {
+        const Node& nd = nodes_[c.child];
+        t.label_off = nd.label_off;
+        t.label_bytes = nd.alive ? nd.label_bytes : 0;
+        t.label_chars = (nd.alive ? nd.label_chars : 0) | (nd.alive && cache_valid(nd) ? kCacheValidBit : 0u);
+        t.any_tenant = nd.alive ? any_tenant(nd) : -1;
+    }
+    return t;
 }
 
 StringTreeView StringTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
@@ -394,46 +396,43 @@ StringTreeView StringTreeIndex::flush(cudaStream_t stream, uint64_t* launches) {
     if (uploaded_bytes_ < bytes_.size()) {
         SMGX_CUDA(cudaMemcpyAsync(d_bytes_.as<uint8_t>() + uploaded_bytes_, bytes_.data() + uploaded_bytes_, bytes_.size() - uploaded_bytes_,
                                   cudaMemcpyHostToDevice, stream));
-        SMGX_CUDA(cudaStreamSynchronize(stream));   // bytes_ may reallocate before the copy engine reads it
-        uploaded_bytes_ = bytes_.size();
+        uploaded_bytes_ = bytes_.size();   // pageable source: the runtime has staged the bytes before the call returns
     }
-    if (!full_dirty_ && dirty_nodes_.size() + dirty_slots_.size() > table_.size() / 8) full_dirty_ = true;
+    // a node whose header changed dirties the slot that points at it (the root has none: its state travels in the view)
+    for (uint32_t id : dirty_nodes_) if (id < nodes_.size() && nodes_[id].slot != kNoNode) mark_slot(nodes_[id].slot);
+    dirty_nodes_.clear();
+    if (!full_dirty_ && dirty_slots_.size() > table_.size() / 8) full_dirty_ = true;
     if (full_dirty_) {
         if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
         SMGX_CUDA(cudaDeviceSynchronize());
-        std::vector<StrHeader> hdr(nodes_.size());
-        for (uint32_t i = 0; i < nodes_.size(); ++i) hdr[i] = header_of(i);
-        d_headers_.reserve(std::max<size_t>(nodes_.capacity(), 16) * sizeof(StrHeader));
-        d_table_.reserve(table_.size() * sizeof(StrChildSlot));
-        SMGX_CUDA(cudaMemcpyAsync(d_headers_.ptr, hdr.data(), hdr.size() * sizeof(StrHeader), cudaMemcpyHostToDevice, stream));
-        SMGX_CUDA(cudaMemcpyAsync(d_table_.ptr, table_.data(), table_.size() * sizeof(StrChildSlot), cudaMemcpyHostToDevice, stream));
-        SMGX_CUDA(cudaStreamSynchronize(stream));
+        std::vector<StrSlot> dev(table_.size());
+        for (uint32_t i = 0; i < table_.size(); ++i) dev[i] = device_slot(i);
+        d_table_.reserve(table_.size() * sizeof(StrSlot));
+        SMGX_CUDA(cudaMemcpyAsync(d_table_.ptr, dev.data(), dev.size() * sizeof(StrSlot), cudaMemcpyHostToDevice, stream));
+        SMGX_CUDA(cudaStreamSynchronize(stream));   // `dev` is a temporary
         full_dirty_ = false;
-        dirty_nodes_.clear(); dirty_slots_.clear();
-    } else if (!dirty_nodes_.empty() || !dirty_slots_.empty()) {
+        dirty_slots_.clear();
+    } else if (!dirty_slots_.empty()) {
         if (!stage_done_) SMGX_CUDA(cudaEventCreateWithFlags(&stage_done_, cudaEventDisableTiming));
         if (stage_pending_) { SMGX_CUDA(cudaEventSynchronize(stage_done_)); stage_pending_ = false; }
-        auto uniq = [](std::vector<uint32_t>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); };
-        uniq(dirty_nodes_); uniq(dirty_slots_);
-        const size_t nn = dirty_nodes_.size(), ns = dirty_slots_.size();
-        const size_t off_ni = 0, off_si = nn * 4, off_nr = ((off_si + ns * 4 + 15) / 16) * 16, off_sr = off_nr + nn * 32, total = off_sr + ns * 16;
+        const size_t ns = dirty_slots_.size();   // unique by construction (mark_slot stamps)
+        const size_t off_r = ((ns * 4 + 15) / 16) * 16, total = off_r + ns * 32;
         stage_.reserve(total);
         d_stage_.reserve(total);
         char* st = stage_.as<char>();
-        memcpy(st + off_ni, dirty_nodes_.data(), nn * 4);
-        memcpy(st + off_si, dirty_slots_.data(), ns * 4);
-        for (size_t i = 0; i < nn; ++i) { const StrHeader h = header_of(dirty_nodes_[i]); memcpy(st + off_nr + i * 32, &h, 32); }
-        for (size_t i = 0; i < ns; ++i) memcpy(st + off_sr + i * 16, &table_[dirty_slots_[i]], 16);
+        memcpy(st, dirty_slots_.data(), ns * 4);
+        for (size_t i = 0; i < ns; ++i) { const StrSlot t = device_slot(dirty_slots_[i]); memcpy(st + off_r + i * 32, &t, 32); }
         SMGX_CUDA(cudaMemcpyAsync(d_stage_.ptr, st, total, cudaMemcpyHostToDevice, stream));
         char* ds = d_stage_.as<char>();
-        if (nn) { scatter_headers_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, stream>>>(d_headers_.as<uint4>(), (const uint32_t*)(ds + off_ni), (const uint4*)(ds + off_nr), (uint32_t)nn); ++*launches; }
-        if (ns) { scatter_slots_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, stream>>>(d_table_.as<uint4>(), (const uint32_t*)(ds + off_si), (const uint4*)(ds + off_sr), (uint32_t)ns); ++*launches; }
+        scatter32_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, stream>>>(d_table_.as<uint4>(), (const uint32_t*)ds, (const uint4*)(ds + off_r), (uint32_t)ns);
+        ++*launches;
         SMGX_CUDA(cudaGetLastError());
         SMGX_CUDA(cudaEventRecord(stage_done_, stream));
         stage_pending_ = true;
-        dirty_nodes_.clear(); dirty_slots_.clear();
+        dirty_slots_.clear();
     }
-    return StringTreeView{d_bytes_.as<uint8_t>(), d_headers_.as<StrHeader>(), d_table_.as<StrChildSlot>(), mask_};
+    if (++flush_gen_ == 0) { flush_gen_ = 1; std::fill(slot_stamp_.begin(), slot_stamp_.end(), 0u); }
+    return StringTreeView{d_bytes_.as<uint8_t>(), d_table_.as<StrSlot>(), mask_, any_tenant(nodes_[0]), cache_valid(nodes_[0]) ? 1u : 0u};
 }
 
 // =================================================================================================================
@@ -523,6 +522,8 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
     if (nbytes) load_window(0);
 
     uint32_t cur = 0, pos = 0, matched = 0, terminal = 0, visited = 0;
+    int32_t term_tenant = tv.root_tenant;       // tenant / cache flag of the node the walk currently ends on
+    uint32_t term_cache = tv.root_cache_valid;
     while (pos < nbytes) {
         if (pos < wbase || pos + 4 > wend) { if (!(pos >= wbase && wend == nbytes)) load_window(pos); }
         uint32_t cl;
@@ -530,17 +531,20 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
         const uint64_t key = str_child_key(cur, cp);
         uint32_t idx = str_child_home(key) & tv.child_mask;
         uint32_t child = kNoNode;
-        for (;;) {   // warp-uniform probe
-            const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(tv.children + idx));
+        uint4 s4, h4{};
+        for (;;) {   // warp-uniform probe; a hit carries the child's header in the same 32 B
+            const uint4* sp = reinterpret_cast<const uint4*>(tv.slots + idx);
+            s4 = __ldg(sp);
             const uint64_t skey = ((uint64_t)s4.y << 32) | s4.x;
             if (skey == 0) break;
-            if (skey == key && s4.z < kTombChild) { child = s4.z; break; }
+            if (skey == key && s4.z < kTombChild) { child = s4.z; h4 = __ldg(sp + 1); break; }
             idx = (idx + 1) & tv.child_mask;
         }
         if (child == kNoNode) break;
-        const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(tv.headers + child));
         const uint64_t label_off = ((uint64_t)h4.y << 32) | h4.x;
-        const uint32_t label_bytes = h4.z, label_chars = h4.w;
+        const uint32_t label_bytes = s4.w, label_chars = h4.z & ~kCacheValidBit;
+        term_tenant = (int32_t)h4.w;
+        term_cache = (h4.z & kCacheValidBit) ? 1u : 0u;
         const uint8_t* lab = tv.bytes + label_off;
         const uint32_t L = min(label_bytes, nbytes - pos);
         uint32_t common = L;
@@ -588,11 +592,10 @@ __global__ void __launch_bounds__(256) string_select_kernel(StringTreeView tv, F
         cur = child;
     }
     if (lane != 0) return;
-    const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(tv.headers + terminal) + 1);
-    const int32_t tenant = (int32_t)t4.x;
+    const int32_t tenant = term_tenant;
     a.out_node[r] = terminal;
     a.out_tenant[r] = tenant;
-    a.out_fill[r] = t4.y ? 0 : 1;
+    a.out_fill[r] = term_cache ? 0 : 1;
     int32_t out = -1;
     uint32_t branch = SMGX_BR_NO_HEALTHY;
     if (a.decide) {

@@ -5,10 +5,10 @@
 // Mutations (insert_text :393-557, the match's cache fill / epoch draw / 1-in-8 refresh :598-637, eviction :745-849) run on
 // the host in request order; the longest-prefix walk and the pick run on the GPU against the mirror:
 //   bytes    [n] u8           append-only arena of UTF-8 edge labels; a split re-slices at a char boundary, it never copies
-//   headers  [nodes] 32 B     { u64 label_off; u32 label_bytes; u32 label_chars; i32 any_tenant; u32 cache_valid; .. }
-//                             any_tenant = cached last_tenant when still present, else the "first in DashMap order"
-//                             (lexicographically smallest), −1 = no tenants; cache_valid says which
-//   children [cap] 16 B       open-addressed { u64 key; u32 child; u32 _ }, key = ((parent << 21) | first char) + 1 — injective
+//   slots    [cap] 32 B       open-addressed { u64 key; u32 child; u32 label_bytes; u64 label_off; u32 label_chars | cache bit; i32 any_tenant },
+//                             key = ((parent << 21) | first char) + 1 — injective; the child's header is embedded.
+//                             any_tenant = cached last_tenant when still present (cache bit set), else the "first in DashMap
+//                             order" (lexicographically smallest), −1 = no tenants
 // Working in UTF-8 bytes is exact: two valid UTF-8 strings that agree on a lead byte agree on the char's length, so the
 // common prefix in chars is the common prefix in bytes rounded down to a char boundary.
 #pragma once
@@ -23,15 +23,19 @@
 
 namespace smgx {
 
-struct alignas(16) StrHeader { uint64_t label_off; uint32_t label_bytes; uint32_t label_chars; int32_t any_tenant; uint32_t cache_valid; uint32_t pad0, pad1; };
-struct alignas(16) StrChildSlot { uint64_t key; uint32_t child; uint32_t pad; };   // key 0 = empty
-static_assert(sizeof(StrHeader) == 32 && sizeof(StrChildSlot) == 16, "mirror layouts");
+struct alignas(16) StrChildSlot { uint64_t key; uint32_t child; uint32_t pad; };   // host table entry; key 0 = empty
+// device table entry: the child's header rides in the slot (one dependent read less per node of the walk).
+// label_chars bit 31 = the node's last_tenant cache is valid (any_tenant came from it)
+struct alignas(16) StrSlot { uint64_t key; uint32_t child; uint32_t label_bytes; uint64_t label_off; uint32_t label_chars; int32_t any_tenant; };
+static_assert(sizeof(StrSlot) == 32 && sizeof(StrChildSlot) == 16, "mirror layouts");
+constexpr uint32_t kCacheValidBit = 0x80000000u;
 
 struct StringTreeView {
     const uint8_t* bytes;
-    const StrHeader* headers;
-    const StrChildSlot* children;
+    const StrSlot* slots;
     uint32_t child_mask;
+    int32_t root_tenant;        // the root has no slot: its any-tenant and cache flag travel with the view
+    uint32_t root_cache_valid;
 };
 
 __host__ __device__ inline uint64_t str_child_key(uint32_t parent, uint32_t cp) { return (((uint64_t)parent << 21) | cp) + 1; }
@@ -93,6 +97,7 @@ private:
         std::vector<std::pair<uint32_t, uint32_t>> kids;      // (first char, child), ascending by char
         bool alive = true;
         uint64_t split_epoch = 0;                             // chunk in which this node was last split (or created by a split)
+        uint32_t slot = kNoNode;                              // table_ index of the entry that points at this node
     };
     uint64_t next_epoch() { return (*epoch_)++; }
     int64_t find_child(uint32_t parent, uint32_t cp) const;
@@ -111,9 +116,13 @@ private:
     void kids_erase(Node& nd, uint32_t cp);
     std::vector<uint32_t> leaf_of(uint32_t node) const;   // tenants present here and in no child, ascending by name (:724-743)
     void mark_node(uint32_t id) { if (!full_dirty_) dirty_nodes_.push_back(id); }
-    void mark_slot(uint32_t i) { if (!full_dirty_) dirty_slots_.push_back(i); }
+    void mark_slot(uint32_t i) {   // each slot at most once per flush generation
+        if (full_dirty_) return;
+        if (slot_stamp_.size() < table_.size()) slot_stamp_.assign(table_.size(), 0);
+        if (slot_stamp_[i] != flush_gen_) { slot_stamp_[i] = flush_gen_; dirty_slots_.push_back(i); }
+    }
     const uint8_t* label(const Node& nd) const { return bytes_.data() + nd.label_off; }
-    StrHeader header_of(uint32_t id) const;
+    StrSlot device_slot(uint32_t i) const;
 
     TenantTable* tenants_;
     uint64_t* epoch_;
@@ -127,7 +136,9 @@ private:
     uint64_t table_live_ = 0, table_tombs_ = 0;
     std::unordered_map<uint32_t, size_t> tenant_chars_;   // tenant_char_count (:251)
 
-    DevBuf d_bytes_, d_headers_, d_table_, d_stage_;
+    DevBuf d_bytes_, d_table_, d_stage_;
+    std::vector<uint32_t> slot_stamp_;
+    uint32_t flush_gen_ = 1;
     PinBuf stage_;
     cudaEvent_t stage_done_ = nullptr;
     bool stage_pending_ = false;
