@@ -159,15 +159,26 @@ void StringTreeIndex::kids_erase(Node& nd, uint32_t cp) {
     if (it != nd.kids.end() && it->first == cp) nd.kids.erase(it);
 }
 
-static inline uint32_t count_chars(const uint8_t* s, size_t n) {
-    uint32_t c = 0;
-    for (size_t i = 0; i < n; ++i) c += (s[i] & 0xC0) != 0x80;
-    return c;
+static inline uint32_t count_chars(const uint8_t* s, size_t n) {   // bytes − continuation bytes (10xxxxxx), 8 at a time
+    size_t i = 0, cont = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, s + i, 8);
+        cont += (size_t)__builtin_popcountll((w >> 7) & ~(w >> 6) & 0x0101010101010101ULL);
+    }
+    for (; i < n; ++i) cont += (s[i] & 0xC0) == 0x80;
+    return (uint32_t)(n - cont);
 }
 // shared prefix of two valid UTF-8 strings, in bytes, ending on a char boundary (shared_prefix_count :311-338)
 static inline size_t shared_prefix_bytes(const uint8_t* a, size_t na, const uint8_t* b, size_t nb) {
     const size_t lim = std::min(na, nb);
     size_t i = 0;
+    while (i + 8 <= lim) {   // 8 bytes at a time; the first differing byte from the lowest set bit of the XOR (little endian)
+        uint64_t x, y;
+        memcpy(&x, a + i, 8); memcpy(&y, b + i, 8);
+        if (x != y) { i += (size_t)(__builtin_ctzll(x ^ y) >> 3); break; }
+        i += 8;
+    }
     while (i < lim && a[i] == b[i]) ++i;
     if (i < lim) while (i > 0 && (a[i] & 0xC0) == 0x80) --i;   // mismatch inside a char: back to its first byte
     return i;

@@ -587,12 +587,14 @@ class CacheAwarePolicy:
         self._h.call("smgx_select_batch_tokens", model, tok_ptr, _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
         return out[:n], (info if info is None else [info[i] for i in range(n)])
 
-    def select_worker_batch_request_text(self, workers: Sequence[BasicWorker], texts, want_info: bool = True):
+    def select_worker_batch_request_text(self, workers: Sequence[BasicWorker], texts=None, want_info: bool = True, data=None, offsets=None):
         """Batch of HTTP-mode requests (request_text, no tokens) against one fleet snapshot: string-tree walk + pick on the
-        GPU (select_worker_with_text, cache_aware.rs:907-974).  → (worker_idx int32[n], info list with char counts)."""
+        GPU (select_worker_with_text, cache_aware.rs:907-974).  Either `texts` (list of str) or a ragged UTF-8 pair
+        (data uint8, offsets uint32[n+1]).  → (worker_idx int32[n], info list with char counts)."""
         model = self._push_fleet(workers)
-        data, offsets = TiktokenTokenizer._ragged(texts)
-        n = len(texts)
+        if texts is not None:
+            data, offsets = TiktokenTokenizer._ragged(texts)
+        n = offsets.size - 1
         out = np.full(max(n, 1), -1, dtype=np.int32)
         info = (_lib.DecisionInfo * max(n, 1))() if want_info else None
         self._h.call("smgx_select_batch_request_text", model, _p(data), _p(offsets), n, _p(out), C.cast(info, C.c_void_p) if info is not None else None)
