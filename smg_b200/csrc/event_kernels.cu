@@ -286,10 +286,6 @@ __device__ __forceinline__ void write_pick(const BatchDesc& b, uint32_t r, int32
 // independent slot loads up front (position 0 and the first jump destination), the count test, and only on a
 // failed test the linear drain (4 probes in flight at a time).  ~30 warp-instructions per request on the common
 // path; the kernel is a few microseconds for 10^5 requests and disappears next to the hash stream.
-struct ThreadSink {
-    uint64_t elig, last; uint32_t last_score;
-    __device__ __forceinline__ void on_event(uint32_t pos, uint64_t set) { uint64_t e = set & elig; if (e) { last = e; last_score = pos; } }
-};
 __device__ __forceinline__ bool finish_probe(const EventIndexView& v, uint32_t pos, uint64_t content, uint32_t h, Slot& s) {
 #pragma unroll 1
     for (;;) {
