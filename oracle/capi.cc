@@ -11,6 +11,7 @@
 #include <thread>
 
 #include "cache_aware.h"
+#include "prefix_hash.h"
 
 using namespace orc;
 
@@ -325,6 +326,54 @@ double orc_policy_select_steps_mt(void* h, const uint32_t* const* tokens, const 
         });
     }
     for (auto& th : ts) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- prefix_hash policy + hash ring (prefix_hash.h) ----
+void* orc_ring_new(const char* const* urls, size_t n) {
+    std::vector<std::string> u;
+    for (size_t i = 0; i < n; ++i) u.emplace_back(urls[i]);
+    return new HashRing(u);
+}
+void orc_ring_free(void* r) { delete (HashRing*)r; }
+size_t orc_ring_len(void* r) { return ((HashRing*)r)->len(); }
+size_t orc_ring_worker_count(void* r) { return ((HashRing*)r)->worker_count(); }
+uint64_t orc_ring_hash_position(const char* s, size_t n) { return HashRing::hash_position(std::string(s, n)); }
+size_t orc_ring_entries(void* r, uint64_t* pos, uint32_t* url, size_t cap) {
+    const auto& e = ((HashRing*)r)->entries();
+    for (size_t i = 0; i < e.size() && i < cap; ++i) { pos[i] = e[i].pos; url[i] = e[i].url; }
+    return e.size();
+}
+// healthy[u] per constructor URL; returns the URL index or -1
+int64_t orc_ring_find_healthy(void* r, const char* key, size_t n, const uint8_t* healthy) {
+    auto* ring = (HashRing*)r;
+    std::unordered_map<std::string, bool> h;
+    for (size_t u = 0; u < ring->worker_count(); ++u) h[ring->url(u)] = healthy[u] != 0;
+    return ring->find_healthy(std::string(key, n), [&](const std::string& url) { return h[url]; });
+}
+uint64_t orc_prefix_hash(const uint32_t* tokens, size_t n, size_t prefix_token_count) {
+    PrefixHashConfig c; c.prefix_token_count = prefix_token_count;
+    return PrefixHashPolicy(c).compute_prefix_hash(tokens, n);
+}
+int orc_prefix_load_ok(double load_factor, uint64_t worker_load, uint64_t total, size_t n) {
+    PrefixHashConfig c; c.load_factor = load_factor;
+    return PrefixHashPolicy(c).load_ok(worker_load, total, n) ? 1 : 0;
+}
+// One batch against one fleet snapshot.  ring may be null (info.hash_ring = None); has_tokens 0 = info.tokens None for every request.
+// Returns elapsed seconds.
+double orc_prefix_select_batch(size_t prefix_token_count, double load_factor, const char* const* urls, const uint64_t* loads, const uint8_t* healthy,
+                               size_t n_workers, void* ring, const uint32_t* tokens, const uint64_t* offsets, size_t n, int has_tokens,
+                               int32_t* out_idx, uint8_t* out_branch) {
+    PrefixHashConfig c; c.prefix_token_count = prefix_token_count; c.load_factor = load_factor;
+    PrefixHashPolicy pol(c);
+    std::vector<PrefixWorker> ws(n_workers);
+    for (size_t i = 0; i < n_workers; ++i) { ws[i].url = urls[i]; ws[i].load = loads[i]; ws[i].healthy = healthy[i] != 0; }
+    auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < n; ++i) {
+        PrefixBranch br;
+        out_idx[i] = (int32_t)pol.select_worker(ws, has_tokens ? tokens + offsets[i] : nullptr, (size_t)(offsets[i + 1] - offsets[i]), (HashRing*)ring, &br);
+        if (out_branch) out_branch[i] = (uint8_t)br;
+    }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 

@@ -89,6 +89,16 @@ def lib():
         sig("orc_hash_token_path", C.c_uint64, vp, sz)
         sig("orc_policy_hash_index", sz, vp, cp, C.c_int, vp, sz)
         sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int, C.c_int)
+        sig("orc_ring_new", vp, P(cp), sz)
+        sig("orc_ring_free", None, vp)
+        sig("orc_ring_len", sz, vp)
+        sig("orc_ring_worker_count", sz, vp)
+        sig("orc_ring_hash_position", u64, cp, sz)
+        sig("orc_ring_entries", sz, vp, vp, vp, sz)
+        sig("orc_ring_find_healthy", i64, vp, cp, sz, vp)
+        sig("orc_prefix_hash", u64, vp, sz, sz)
+        sig("orc_prefix_load_ok", C.c_int, C.c_double, u64, u64, sz)
+        sig("orc_prefix_select_batch", C.c_double, sz, C.c_double, P(cp), vp, vp, sz, vp, vp, vp, sz, C.c_int, vp, vp)
         _lib = L
     return _lib
 
@@ -522,3 +532,83 @@ class CacheAwarePolicy:
         fn = lib().orc_policy_select_batch_tokens_snapshot if snapshot else lib().orc_policy_select_batch_tokens
         secs = fn(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), _ptr(br), _ptr(ma))
         return idx, br, ma, secs
+
+
+# ---- prefix_hash policy + consistent hash ring (oracle/prefix_hash.h) ----
+PREFIX_BRANCHES = ["no_healthy_workers", "no_tokens", "ring_hit", "load_balance_walk", "fallback_least_load"]   # prefix_hash.rs:70-83
+
+
+class HashRing:                              # model_gateway/src/worker/hash_ring.rs
+    def __init__(self, urls):
+        self.urls = list(urls)
+        enc = [u.encode() for u in self.urls]
+        arr = (C.c_char_p * max(len(enc), 1))(*enc)
+        self._h = lib().orc_ring_new(arr, len(enc))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_ring_free(self._h)
+            self._h = None
+
+    @staticmethod
+    def hash_position(s: str) -> int:        # :78-86
+        b = s.encode("utf-8")
+        return lib().orc_ring_hash_position(b, len(b))
+
+    def is_empty(self):
+        return len(self) == 0
+
+    def __len__(self):
+        return lib().orc_ring_len(self._h)
+
+    def worker_count(self):
+        return lib().orc_ring_worker_count(self._h)
+
+    def entries(self):
+        n = len(self)
+        pos = np.zeros(max(n, 1), np.uint64)
+        url = np.zeros(max(n, 1), np.uint32)
+        lib().orc_ring_entries(self._h, _ptr(pos), _ptr(url), n)
+        return pos[:n], url[:n]
+
+    def find_healthy_url(self, key: str, is_healthy):   # :102-134
+        if not self.urls:
+            return None
+        h = np.array([1 if is_healthy(u) else 0 for u in self.urls], np.uint8)
+        b = key.encode("utf-8")
+        i = lib().orc_ring_find_healthy(self._h, b, len(b), _ptr(h))
+        return None if i < 0 else self.urls[i]
+
+
+class PrefixHashPolicy:                      # model_gateway/src/policies/prefix_hash.rs
+    def __init__(self, prefix_token_count=256, load_factor=1.25):
+        self.prefix_token_count, self.load_factor = int(prefix_token_count), float(load_factor)
+
+    def name(self):
+        return "prefix_hash"
+
+    def compute_prefix_hash(self, tokens) -> int:
+        t = _u32(tokens)
+        return lib().orc_prefix_hash(_ptr(t), t.size, self.prefix_token_count)
+
+    def load_ok(self, worker_load, total_load, num_workers) -> bool:
+        return bool(lib().orc_prefix_load_ok(self.load_factor, int(worker_load), int(total_load), int(num_workers)))
+
+    def select_batch(self, urls, loads, healthy, ring, tokens, offsets, has_tokens=True):
+        """One batch against one fleet snapshot → (idx, branch, seconds).  ring None = info.hash_ring None."""
+        enc = [u.encode() for u in urls]
+        arr = (C.c_char_p * max(len(enc), 1))(*enc)
+        ld, hl = _u64(loads), np.ascontiguousarray(np.asarray(healthy, np.uint8))
+        tk, off = _u32(tokens), _u64(offsets)
+        n = off.size - 1
+        idx = np.full(max(n, 1), -1, np.int32)
+        br = np.zeros(max(n, 1), np.uint8)
+        secs = lib().orc_prefix_select_batch(self.prefix_token_count, self.load_factor, arr, _ptr(ld), _ptr(hl), len(enc),
+                                             ring._h if ring is not None else None, _ptr(tk), _ptr(off), n, 1 if has_tokens else 0, _ptr(idx), _ptr(br))
+        return idx[:n], br[:n], secs
+
+    def select_worker(self, urls, loads, healthy, ring, tokens):
+        """select_worker_impl (:203-222): tokens None = info.tokens None.  → (idx or None, branch name)"""
+        t = _u32(tokens if tokens is not None else [])
+        idx, br, _ = self.select_batch(urls, loads, healthy, ring, t, np.array([0, t.size], np.uint64), has_tokens=tokens is not None)
+        return (None if idx[0] < 0 else int(idx[0])), PREFIX_BRANCHES[int(br[0])]
