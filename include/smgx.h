@@ -240,6 +240,43 @@ smgx_status smgx_hash_index_size(smgx_policy* p, const char* model_key, int text
 smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_kind, uint64_t path_hash, void* out, uint32_t cap_bytes,
                                 uint32_t* out_bytes, int* out_found, char** err);
 
+/* ---- adjacent policy on the same plumbing: prefix_hash (model_gateway/src/policies/prefix_hash.rs) ---- */
+/* Which branch of PrefixHashPolicy::select_worker_impl produced the result (prefix_hash.rs:61-83), reported in
+ * smgx_decision_info.branch by the smgx_prefix_hash_* calls (matched = 0, input = request length in tokens). */
+typedef enum smgx_prefix_branch {
+    SMGX_PH_NO_HEALTHY_WORKERS = 0,   /* empty slice or no is_healthy() worker → None (:143-145, :208-210) */
+    SMGX_PH_NO_TOKENS = 1,            /* info.tokens None or empty → None               (:213-216)          */
+    SMGX_PH_RING_HIT = 2,             /* ring worker passes load_ok                      (:169-171)          */
+    SMGX_PH_LOAD_BALANCE_WALK = 3,    /* ring worker overloaded → least loaded acceptable worker, else itself (:173-187) */
+    SMGX_PH_FALLBACK_LEAST_LOAD = 4   /* no ring / ring lookup failed → least loaded healthy (:192-199)      */
+} smgx_prefix_branch;
+/* PrefixHashConfig (prefix_hash.rs:38-58): defaults 256 tokens / 1.25. */
+smgx_status smgx_prefix_hash_configure(smgx_policy* p, uint64_t prefix_token_count, double load_factor, char** err);
+/* info.hash_ring for `model_key`: HashRing::new(urls) (worker/hash_ring.rs:45-70) — 150 virtual nodes per URL at
+ * blake3("{url}#{vnode}")[..8] (hashed on the GPU), sorted by position (equal positions keep insertion order).  The ring is
+ * independent of the worker slice, as in the reference (the registry rebuilds it when workers come and go); n = 0 gives the empty
+ * ring, smgx_hash_ring_clear gives hash_ring = None. */
+smgx_status smgx_hash_ring_set(smgx_policy* p, const char* model_key, const char* const* urls, uint32_t n, char** err);
+smgx_status smgx_hash_ring_clear(smgx_policy* p, const char* model_key, char** err);
+/* The sorted entries: out_pos[i], out_url[i] (index into the urls of smgx_hash_ring_set); *out_len = HashRing::len(). */
+smgx_status smgx_hash_ring_entries(smgx_policy* p, const char* model_key, uint64_t* out_pos, uint32_t* out_url, uint32_t cap, uint32_t* out_len, char** err);
+/* HashRing::find_healthy_url (hash_ring.rs:102-134) for n keys: key i = keys[key_offsets[i] .. key_offsets[i+1]) (any bytes),
+ * url_ok[u] = is_healthy(url u of the ring).  out_url[i] = ring URL index or -1 (None). */
+smgx_status smgx_hash_ring_find_healthy(smgx_policy* p, const char* model_key, const uint8_t* keys, const uint32_t* key_offsets, uint32_t n,
+                                        const uint8_t* url_ok, int32_t* out_url, char** err);
+/* compute_prefix_hash (prefix_hash.rs:106-113) of every request: xxh3_64 of the first min(len, prefix_token_count) token ids. */
+smgx_status smgx_prefix_hashes(smgx_policy* p, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err);
+/* PrefixHashPolicy::select_worker (prefix_hash.rs:225-229) for a batch against the worker slice and fleet snapshot of `model_key`
+ * (smgx_set_workers / smgx_set_fleet_state; only is_healthy() and load() are read, :140, :148) and the model's ring.
+ * has_tokens[i] = 0 means info.tokens = None for request i (NULL: every request carries tokens).  Host buffers; only the hashed
+ * prefix of each request crosses PCIe. */
+smgx_status smgx_prefix_hash_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                                                 const uint8_t* has_tokens, int32_t* out_worker_idx, smgx_decision_info* out_info, char** err);
+/* Device-resident form, up to 32 batches per launch (batch k = d_tokens[k], d_offsets[k], n[k] → d_out_worker_idx[k]); asynchronous
+ * on lane 0 — bracket with smgx_timer_* / smgx_synchronize. */
+smgx_status smgx_prefix_hash_select_many_tokens_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
+                                                       const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx, char** err);
+
 /* ---- HTTP text routing: select_worker with info.request_text = Some(text), info.tokens = None ------------------ */
 /* select_worker_with_text (cache_aware.rs:907-974) and the imbalanced path's string-tree update (:403-425) for a batch:
  * request i = text[offsets[i] .. offsets[i+1]) (valid UTF-8).  match_rate = matched chars / input chars (f32, strict >).

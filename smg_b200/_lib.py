@@ -104,6 +104,14 @@ def load():
     sig("smgx_tree_entries", st, vp, cp, P(C.c_void_p), pp)
     sig("smgx_hash_token_paths", st, vp, vp, vp, u32, vp, pp)
     sig("smgx_hash_node_paths", st, vp, vp, vp, u32, vp, pp)
+    sig("smgx_prefix_hash_configure", st, vp, u64, C.c_double, pp)
+    sig("smgx_hash_ring_set", st, vp, cp, P(cp), u32, pp)
+    sig("smgx_hash_ring_clear", st, vp, cp, pp)
+    sig("smgx_hash_ring_entries", st, vp, cp, vp, vp, u32, P(u32), pp)
+    sig("smgx_hash_ring_find_healthy", st, vp, cp, vp, vp, u32, vp, vp, pp)
+    sig("smgx_prefix_hashes", st, vp, vp, vp, u32, vp, pp)
+    sig("smgx_prefix_hash_select_batch_tokens", st, vp, cp, vp, vp, u32, vp, vp, vp, pp)
+    sig("smgx_prefix_hash_select_many_tokens_device", st, vp, cp, u32, vp, vp, vp, vp, pp)
     sig("smgx_hash_index_size", st, vp, cp, C.c_int, P(u64), pp)
     sig("smgx_hash_index_get", st, vp, cp, C.c_int, u64, vp, u32, P(u32), P(C.c_int), pp)
     sig("smgx_set_tree_batch_mode", st, vp, u32, pp)

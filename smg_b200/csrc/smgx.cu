@@ -23,6 +23,7 @@
 #include "token_tree.h"
 #include "string_tree.h"
 #include "blake3.h"
+#include "prefix_hash.h"
 #include <cstdio>
 #include <unordered_map>
 #include <unordered_set>
@@ -58,6 +59,14 @@ struct ModelState {
     bool fleet_dirty = true;
     bool fleet_dirty_tenant = true;
     uint64_t seen_workers_version = ~0ULL;
+    // prefix_hash policy (policies/prefix_hash.rs): info.hash_ring of this model (worker/hash_ring.rs) and its device copies
+    bool has_ring = false;
+    std::vector<std::string> ring_urls;
+    std::vector<uint64_t> ring_pos;       // sorted positions
+    std::vector<uint32_t> ring_url;       // entry → index into ring_urls
+    DevBuf d_ring_pos, d_ring_slice, d_ring_url, d_dup_prev, d_pf_loads, d_pf_flags, d_pf_derived;
+    bool pf_struct_dirty = true;          // slice or ring changed: entry → slice map must be rebuilt
+    bool pf_state_dirty = true;           // loads / health changed: fleet summary must be recomputed
 };
 
 struct Lane {
@@ -387,7 +396,7 @@ public:
     // smg_mesh::hash_token_path / hash_node_path (crates/mesh/src/hash.rs:22-52) of every request of a batch that is already
     // on the device: enqueues the blake3 kernels and the copy back on `lane`; `out` is valid after the next stream sync.
     void enqueue_path_hashes(Lane& lane, const uint8_t* d_data, const uint32_t* d_offsets, const uint32_t* offsets, uint32_t n, uint32_t elem_bytes,
-                             std::vector<uint64_t>& out) {
+                             std::vector<uint64_t>& out, bool remap_zero = true) {
         out.assign(n, 0);
         if (n == 0) return;
         std::vector<uint32_t> chunk_start(n + 1);
@@ -404,9 +413,99 @@ public:
         lane.d_hashes.reserve((size_t)n * 8);
         SMGX_CUDA(cudaMemcpyAsync(lane.d_chunk_start.ptr, chunk_start.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
         launch_blake3_paths(d_data, d_offsets, elem_bytes, lane.d_chunk_start.as<uint32_t>(), n, (uint32_t)total, lane.d_cv.as<uint32_t>(),
-                            lane.d_hashes.as<uint64_t>(), lane.stream, &launches);
+                            lane.d_hashes.as<uint64_t>(), lane.stream, &launches, remap_zero);
         SMGX_CUDA(cudaMemcpyAsync(out.data(), lane.d_hashes.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, lane.stream));
     }
+
+    // ---- prefix_hash policy ----
+    // blake3(bytes)[..8] (LE) of n byte strings, on the GPU: ring positions of virtual nodes and of routing keys (hash_ring.rs:78-86)
+    void ring_positions(const std::string& blob, const std::vector<uint32_t>& offs, std::vector<uint64_t>& out) {
+        const uint32_t n = (uint32_t)offs.size() - 1;
+        out.assign(n, 0);
+        if (n == 0) return;
+        Lane& lane = lanes[0];
+        lane.d_text.reserve(std::max<size_t>(blob.size(), 1) + 16);
+        lane.d_offsets.reserve(((size_t)n + 1) * 4);
+        if (!blob.empty()) SMGX_CUDA(cudaMemcpyAsync(lane.d_text.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice, lane.stream));
+        SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offs.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
+        enqueue_path_hashes(lane, lane.d_text.as<uint8_t>(), lane.d_offsets.as<uint32_t>(), offs.data(), n, 1, out, false);
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+    }
+    // HashRing::new (hash_ring.rs:45-70)
+    void ring_set(ModelState& m, const char* const* urls, uint32_t n) {
+        std::string blob;
+        std::vector<uint32_t> offs{0};
+        for (uint32_t u = 0; u < n; ++u)
+            for (uint32_t v = 0; v < kVirtualNodesPerWorker; ++v) {
+                blob += urls[u]; blob += '#'; blob += std::to_string(v);   // format!("{url}#{vnode}")
+                SMGX_REQUIRE(blob.size() < (1ull << 32), "ring too large");
+                offs.push_back((uint32_t)blob.size());
+            }
+        std::vector<uint64_t> pos;
+        ring_positions(blob, offs, pos);
+        std::vector<uint32_t> order(pos.size());
+        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pos[a] < pos[b]; });
+        m.ring_urls.clear();
+        for (uint32_t u = 0; u < n; ++u) m.ring_urls.emplace_back(urls[u]);
+        m.ring_pos.resize(order.size());
+        m.ring_url.resize(order.size());
+        for (uint32_t i = 0; i < order.size(); ++i) { m.ring_pos[i] = pos[order[i]]; m.ring_url[i] = order[i] / kVirtualNodesPerWorker; }
+        m.has_ring = true;
+        m.pf_struct_dirty = true;
+    }
+    // device copies for the prefix_hash kernels, in lane-0 stream order
+    void sync_prefix(ModelState& m, RingView* rv, PrefixFleetView* fv) {
+        Lane& lane = lanes[0];
+        const uint32_t ns = (uint32_t)m.urls.size(), len = m.has_ring ? (uint32_t)m.ring_pos.size() : 0;
+        if (m.pf_struct_dirty) {
+            // `healthy_url_map` (prefix_hash.rs:155-159) collects url → (idx, worker) over the healthy workers in slice order, later
+            // duplicates overwriting earlier ones: a ring URL resolves to the LAST healthy slice index carrying it.  last_of / dup_prev
+            // give the kernel that chain without knowing the health flags.
+            std::unordered_map<std::string, int32_t> last_of;
+            std::vector<int32_t> dup_prev(std::max<uint32_t>(ns, 1), -1);
+            for (uint32_t i = 0; i < ns; ++i) {
+                auto it = last_of.find(m.urls[i]);
+                if (it != last_of.end()) { dup_prev[i] = it->second; it->second = (int32_t)i; }
+                else last_of.emplace(m.urls[i], (int32_t)i);
+            }
+            std::vector<int32_t> slice_of_url(std::max<size_t>(m.ring_urls.size(), 1), -1), ring_slice(std::max<uint32_t>(len, 1), -1);
+            for (size_t u = 0; u < m.ring_urls.size(); ++u) { auto it = last_of.find(m.ring_urls[u]); if (it != last_of.end()) slice_of_url[u] = it->second; }
+            for (uint32_t e = 0; e < len; ++e) ring_slice[e] = slice_of_url[m.ring_url[e]];
+            m.d_ring_pos.reserve(std::max<uint32_t>(len, 1) * 8);
+            m.d_ring_slice.reserve(std::max<uint32_t>(len, 1) * 4);
+            m.d_ring_url.reserve(std::max<uint32_t>(len, 1) * 4);
+            m.d_dup_prev.reserve(std::max<uint32_t>(ns, 1) * 4);
+            if (len) {
+                SMGX_CUDA(cudaMemcpyAsync(m.d_ring_pos.ptr, m.ring_pos.data(), (size_t)len * 8, cudaMemcpyHostToDevice, lane.stream));
+                SMGX_CUDA(cudaMemcpyAsync(m.d_ring_slice.ptr, ring_slice.data(), (size_t)len * 4, cudaMemcpyHostToDevice, lane.stream));
+                SMGX_CUDA(cudaMemcpyAsync(m.d_ring_url.ptr, m.ring_url.data(), (size_t)len * 4, cudaMemcpyHostToDevice, lane.stream));
+            }
+            if (ns) SMGX_CUDA(cudaMemcpyAsync(m.d_dup_prev.ptr, dup_prev.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, lane.stream));
+            SMGX_CUDA(cudaStreamSynchronize(lane.stream));   // the staging vectors die here
+            m.pf_struct_dirty = false;
+            m.pf_state_dirty = true;
+        }
+        if (m.pf_state_dirty) {
+            m.d_pf_loads.reserve(std::max<uint32_t>(ns, 1) * 8);
+            m.d_pf_flags.reserve(std::max<uint32_t>(ns, 1));
+            m.d_pf_derived.reserve(sizeof(PrefixDerived));
+            if (ns) {
+                SMGX_CUDA(cudaMemcpyAsync(m.d_pf_loads.ptr, m.loads.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, lane.stream));
+                SMGX_CUDA(cudaMemcpyAsync(m.d_pf_flags.ptr, m.flags.data(), ns, cudaMemcpyHostToDevice, lane.stream));   // pageable source: staged before return
+            }
+            launch_prefix_fleet_prepare(m.d_pf_loads.as<uint64_t>(), m.d_pf_flags.as<uint8_t>(), ns, prefix_load_factor, m.d_pf_derived.as<PrefixDerived>(),
+                                        lane.stream);
+            ++launches;
+            m.pf_state_dirty = false;
+        }
+        rv->pos = m.d_ring_pos.as<uint64_t>(); rv->slice = m.d_ring_slice.as<int32_t>(); rv->len = len; rv->has_ring = m.has_ring ? 1u : 0u;
+        fv->loads = m.d_pf_loads.as<uint64_t>(); fv->flags = m.d_pf_flags.as<uint8_t>(); fv->dup_prev = m.d_dup_prev.as<int32_t>();
+        fv->derived = m.d_pf_derived.as<PrefixDerived>(); fv->n_slice = ns;
+    }
+    uint64_t prefix_token_count = 256;   // PrefixHashConfig::default() (prefix_hash.rs:52-58)
+    double prefix_load_factor = 1.25;
+    PinBuf pf_stage, pf_out;             // pinned staging of the host-buffer prefix_hash call
 
     StringTreeIndex& stree_of(ModelState& m) {
         if (!m.string_tree) {
@@ -716,6 +815,7 @@ smgx_status smgx_set_workers(smgx_policy* p, const char* model_key, const char* 
         m.processed.assign(n, 0);
         m.fleet_dirty = true;
         m.fleet_dirty_tenant = true;
+        m.pf_struct_dirty = m.pf_state_dirty = true;
         p->impl.tree_of(m, true);                                   // init_workers creates the trees (cache_aware.rs:231-247)
         StringTreeIndex& st = p->impl.stree_of(m);
         for (auto& u : m.urls) st.insert_text(nullptr, 0, p->impl.tenants.intern(u));   // tree.insert_text("", url) (:239, :275)
@@ -736,6 +836,7 @@ smgx_status smgx_set_fleet_state(smgx_policy* p, const char* model_key, const ui
             m.flags[i] = h | c;
         }
         m.fleet_dirty = true;
+        m.pf_state_dirty = true;
         return SMGX_SUCCESS;
     });
 }
@@ -748,6 +849,7 @@ smgx_status smgx_add_worker(smgx_policy* p, const char* model_key, const char* u
             m.urls.emplace_back(url); m.loads.push_back(0); m.flags.push_back(3); m.processed.push_back(0);
             m.fleet_dirty = true;
             m.fleet_dirty_tenant = true;
+            m.pf_struct_dirty = m.pf_state_dirty = true;
         }
         p->impl.tree_of(m, true);
         p->impl.stree_of(m).insert_text(nullptr, 0, p->impl.tenants.intern(url));   // add_worker_by_url (:269-283)
@@ -1493,6 +1595,190 @@ smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_
         else { auto it = m.hash_index_tokens.find(path_hash); if (it != m.hash_index_tokens.end()) { src = m.hash_arena_tokens.data() + it->second.first; nb = (size_t)it->second.second * 4; *out_found = 1; } }
         *out_bytes = (uint32_t)nb;
         if (*out_found && out && nb <= cap_bytes && nb) memcpy(out, src, nb);
+        return SMGX_SUCCESS;
+    });
+}
+
+// ---- adjacent policy: prefix_hash (model_gateway/src/policies/prefix_hash.rs) over the consistent hash ring (worker/hash_ring.rs) ----
+smgx_status smgx_prefix_hash_configure(smgx_policy* p, uint64_t prefix_token_count, double load_factor, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(load_factor == load_factor, "load_factor is NaN");
+        SMGX_REQUIRE(prefix_token_count <= 0xFFFFFFFFull, "prefix_token_count out of range");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.prefix_token_count = prefix_token_count;
+        p->impl.prefix_load_factor = load_factor;
+        for (auto& kv : p->impl.models) kv.second->pf_state_dirty = true;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_hash_ring_set(smgx_policy* p, const char* model_key, const char* const* urls, uint32_t n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || urls != nullptr, "Invalid arguments: null pointer");
+        for (uint32_t i = 0; i < n; ++i) NONNULL(urls[i]);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        P.ring_set(P.model(model_key, true), urls, n);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_hash_ring_clear(smgx_policy* p, const char* model_key, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        m.has_ring = false; m.ring_urls.clear(); m.ring_pos.clear(); m.ring_url.clear();
+        m.pf_struct_dirty = true;
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_hash_ring_entries(smgx_policy* p, const char* model_key, uint64_t* out_pos, uint32_t* out_url, uint32_t cap, uint32_t* out_len, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_len);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, false);
+        if (!m.has_ring) throw Error(SMGX_NOT_FOUND, "no hash ring for this model");
+        *out_len = (uint32_t)m.ring_pos.size();
+        for (uint32_t i = 0; i < m.ring_pos.size() && i < cap; ++i) { if (out_pos) out_pos[i] = m.ring_pos[i]; if (out_url) out_url[i] = m.ring_url[i]; }
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_hash_ring_find_healthy(smgx_policy* p, const char* model_key, const uint8_t* keys, const uint32_t* key_offsets, uint32_t n,
+                                        const uint8_t* url_ok, int32_t* out_url, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (key_offsets && out_url), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        if (!m.has_ring) throw Error(SMGX_NOT_FOUND, "no hash ring for this model");
+        SMGX_REQUIRE(m.ring_urls.empty() || url_ok, "Invalid arguments: null pointer");
+        if (n == 0) return SMGX_SUCCESS;
+        for (uint32_t i = 0; i < n; ++i) SMGX_REQUIRE(key_offsets[i + 1] >= key_offsets[i], "offsets must be non-decreasing");
+        SMGX_REQUIRE(key_offsets[n] == key_offsets[0] || keys, "Invalid arguments: null pointer");
+        std::string blob(reinterpret_cast<const char*>(keys) + key_offsets[0], key_offsets[n] - key_offsets[0]);
+        std::vector<uint32_t> offs(n + 1);
+        for (uint32_t i = 0; i <= n; ++i) offs[i] = key_offsets[i] - key_offsets[0];
+        std::vector<uint64_t> kp;
+        P.ring_positions(blob, offs, kp);
+        RingView rv; PrefixFleetView fv;
+        P.sync_prefix(m, &rv, &fv);
+        Lane& lane = P.lanes[0];
+        const uint32_t nu = (uint32_t)m.ring_urls.size();
+        P.scratch.reserve((size_t)n * 8 + std::max<uint32_t>(nu, 1) + 16);
+        P.scratch2.reserve((size_t)n * 4);
+        uint64_t* d_kp = P.scratch.as<uint64_t>();
+        uint8_t* d_ok = reinterpret_cast<uint8_t*>(d_kp + n);
+        SMGX_CUDA(cudaMemcpyAsync(d_kp, kp.data(), (size_t)n * 8, cudaMemcpyHostToDevice, lane.stream));
+        if (nu) SMGX_CUDA(cudaMemcpyAsync(d_ok, url_ok, nu, cudaMemcpyHostToDevice, lane.stream));
+        launch_ring_find(rv.pos, m.d_ring_url.as<uint32_t>(), rv.len, d_kp, d_ok, n, P.scratch2.as<int32_t>(), lane.stream);
+        ++P.launches;
+        SMGX_CUDA(cudaMemcpyAsync(out_url, P.scratch2.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+        return SMGX_SUCCESS;
+    });
+}
+
+// host-buffer forms: only the hashed prefix of each request is staged (pinned) and copied
+static smgx_status prefix_host_call(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, const uint8_t* has_tokens,
+                                    int32_t* out_idx, smgx_decision_info* out_info, uint64_t* out_hash, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || offsets, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        if (n == 0) return SMGX_SUCCESS;
+        SMGX_REQUIRE(n <= P.cfg.max_batch, "batch larger than max_batch");
+        const uint32_t k = (uint32_t)P.prefix_token_count, keep = std::max(k, 1u);   // ≥ 1 token kept so that "tokens is empty" survives the packing
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) { SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing"); total += std::min(offsets[i + 1] - offsets[i], keep); }
+        SMGX_REQUIRE(total == 0 || tokens, "Invalid arguments: null pointer");
+        const size_t off_bytes = ((size_t)n + 1) * 4, flag_bytes = has_tokens ? (((size_t)n + 3) & ~(size_t)3) : 0;
+        P.pf_stage.reserve(total * 4 + off_bytes + flag_bytes + 16);
+        uint32_t* h_tok = P.pf_stage.as<uint32_t>();
+        uint32_t* h_off = h_tok + total;
+        uint8_t* h_flag = reinterpret_cast<uint8_t*>(h_off + n + 1);
+        uint64_t at = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t use = std::min(offsets[i + 1] - offsets[i], keep);
+            h_off[i] = (uint32_t)at;
+            if (use) memcpy(h_tok + at, tokens + offsets[i], (size_t)use * 4);
+            at += use;
+        }
+        h_off[n] = (uint32_t)at;
+        if (has_tokens) memcpy(h_flag, has_tokens, n);
+        ModelState* m = out_idx ? &P.model(model_key, false) : nullptr;
+        Lane& lane = P.lanes[0];
+        const size_t in_bytes = total * 4 + off_bytes + flag_bytes;
+        lane.d_tokens.reserve(in_bytes + 16);
+        lane.d_out.reserve((size_t)n * 4);
+        lane.d_info.reserve((size_t)n * sizeof(smgx_decision_info));
+        lane.d_hashes.reserve((size_t)n * 8);
+        SMGX_CUDA(cudaMemcpyAsync(lane.d_tokens.ptr, P.pf_stage.ptr, in_bytes, cudaMemcpyHostToDevice, lane.stream));
+        RingView rv{nullptr, nullptr, 0, 0};
+        PrefixFleetView fv{nullptr, nullptr, nullptr, nullptr, 0};
+        if (m) P.sync_prefix(*m, &rv, &fv);
+        PrefixArgs a;
+        a.count = 1; a.prefix_tokens = k;
+        uint32_t* d_tok = lane.d_tokens.as<uint32_t>();
+        a.b[0].tokens = d_tok; a.b[0].offsets = d_tok + total;
+        a.b[0].has_tokens = has_tokens ? reinterpret_cast<const uint8_t*>(d_tok + total + n + 1) : nullptr;
+        a.b[0].out_idx = out_idx ? lane.d_out.as<int32_t>() : nullptr;
+        a.b[0].out_info = out_info ? lane.d_info.as<smgx_decision_info>() : nullptr;
+        a.b[0].out_hash = out_hash ? lane.d_hashes.as<uint64_t>() : nullptr;
+        a.b[0].n = n;
+        launch_prefix_select(rv, fv, a, lane.stream);
+        ++P.launches;
+        const size_t hash_at = ((size_t)n * (4 + sizeof(smgx_decision_info)) + 7) & ~(size_t)7;
+        P.pf_out.reserve(hash_at + (size_t)n * 8);
+        int32_t* h_idx = P.pf_out.as<int32_t>();
+        smgx_decision_info* h_info = reinterpret_cast<smgx_decision_info*>(h_idx + n);
+        uint64_t* h_hash = reinterpret_cast<uint64_t*>(P.pf_out.as<uint8_t>() + hash_at);
+        if (out_idx) SMGX_CUDA(cudaMemcpyAsync(h_idx, lane.d_out.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
+        if (out_info) SMGX_CUDA(cudaMemcpyAsync(h_info, lane.d_info.ptr, (size_t)n * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+        if (out_hash) SMGX_CUDA(cudaMemcpyAsync(h_hash, lane.d_hashes.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, lane.stream));
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+        if (out_idx) memcpy(out_idx, h_idx, (size_t)n * 4);
+        if (out_info) {
+            memcpy(out_info, h_info, (size_t)n * sizeof(smgx_decision_info));
+            for (uint32_t i = 0; i < n; ++i) out_info[i].input = offsets[i + 1] - offsets[i];   // the kernel saw the packed prefix only
+        }
+        if (out_hash) memcpy(out_hash, h_hash, (size_t)n * 8);
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_prefix_hashes(smgx_policy* p, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err) {
+    if (n && !out_hashes) { if (err) *err = dup_cstr("Invalid arguments: null pointer"); return SMGX_INVALID_ARGUMENT; }
+    return prefix_host_call(p, "", tokens, offsets, n, nullptr, nullptr, nullptr, out_hashes, err);
+}
+smgx_status smgx_prefix_hash_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                                                 const uint8_t* has_tokens, int32_t* out_worker_idx, smgx_decision_info* out_info, char** err) {
+    if (n && !out_worker_idx) { if (err) *err = dup_cstr("Invalid arguments: null pointer"); return SMGX_INVALID_ARGUMENT; }
+    return prefix_host_call(p, model_key, tokens, offsets, n, has_tokens, out_worker_idx, out_info, nullptr, err);
+}
+smgx_status smgx_prefix_hash_select_many_tokens_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint32_t* const* d_tokens,
+                                                       const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n_batches == 0 || (d_tokens && d_offsets && n && d_out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        RingView rv; PrefixFleetView fv;
+        P.sync_prefix(m, &rv, &fv);
+        for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxPrefixBatches) {
+            PrefixArgs a;
+            a.count = std::min<uint32_t>(kMaxPrefixBatches, n_batches - j0);
+            a.prefix_tokens = (uint32_t)P.prefix_token_count;
+            for (uint32_t k = 0; k < a.count; ++k) a.b[k] = PrefixBatch{d_tokens[j0 + k], d_offsets[j0 + k], nullptr, d_out_worker_idx[j0 + k], nullptr, nullptr, n[j0 + k]};
+            launch_prefix_select(rv, fv, a, P.lanes[0].stream);
+            ++P.launches;
+        }
         return SMGX_SUCCESS;
     });
 }

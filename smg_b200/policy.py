@@ -35,9 +35,10 @@ class CacheAwareConfig:  # policies/mod.rs:94-117
 
 
 @dataclass
-class SelectWorkerInfo:  # policies/mod.rs:161-175 (headers / hash_ring are not read by cache_aware)
+class SelectWorkerInfo:  # policies/mod.rs:161-175 (headers are not read on this path; hash_ring only by prefix_hash)
     request_text: Optional[str] = None
     tokens: Optional[Sequence[int]] = None
+    hash_ring: Optional["HashRing"] = None
 
 
 class BasicWorker:
@@ -679,6 +680,159 @@ class CacheAwarePolicy:
         return _lib.load().smgx_kernel_launches(self._h.p)
 
 
+# ---- adjacent policy on the same plumbing: prefix_hash ---------------------------------------------------------
+PREFIX_BRANCHES = ["no_healthy_workers", "no_tokens", "ring_hit", "load_balance_walk", "fallback_least_load"]   # prefix_hash.rs:70-83
+
+
+@dataclass
+class PrefixHashConfig:  # policies/prefix_hash.rs:38-58
+    prefix_token_count: int = 256
+    load_factor: float = 1.25
+
+
+class HashRing:
+    """worker::HashRing (model_gateway/src/worker/hash_ring.rs): 150 virtual nodes per URL at blake3("{url}#{vnode}")[..8], hashed on
+    the GPU and kept sorted inside the library.  Bound to (policy handle, model) like the registry's per-model ring."""
+    _seq = 0
+
+    def __init__(self, urls, handle: Optional[_Handle] = None, model: Optional[str] = None, device_id: int = 0):
+        self._h = handle or _Handle(CacheAwareConfig(eviction_interval_secs=0), device_id)
+        if model is None:
+            HashRing._seq += 1
+            model = f"__ring_{HashRing._seq}"
+        self.model = normalize_model_key(model).encode()
+        self.urls = [str(u) for u in urls]
+        enc = [u.encode() for u in self.urls]
+        arr = (C.c_char_p * max(len(enc), 1))(*enc)
+        self._h.call("smgx_hash_ring_set", self.model, arr, len(enc))
+
+    def entries(self):
+        n = C.c_uint32(0)
+        self._h.call("smgx_hash_ring_entries", self.model, None, None, 0, C.byref(n))
+        pos, url = np.zeros(max(n.value, 1), np.uint64), np.zeros(max(n.value, 1), np.uint32)
+        self._h.call("smgx_hash_ring_entries", self.model, _p(pos), _p(url), n.value, C.byref(n))
+        return pos[:n.value], url[:n.value]
+
+    def __len__(self):  # HashRing::len (:142-144)
+        n = C.c_uint32(0)
+        self._h.call("smgx_hash_ring_entries", self.model, None, None, 0, C.byref(n))
+        return n.value
+
+    def is_empty(self):
+        return len(self) == 0
+
+    def worker_count(self):  # :147-149
+        return len(self) // 150
+
+    def find_healthy_urls(self, keys, is_healthy):
+        """find_healthy_url (:102-134) for a batch of keys on the GPU → list of URL or None."""
+        data, offsets = TiktokenTokenizer._ragged(list(keys))
+        ok = np.ascontiguousarray(np.asarray([1 if is_healthy(u) else 0 for u in self.urls] or [0], dtype=np.uint8))
+        n = offsets.size - 1
+        out = np.full(max(n, 1), -1, np.int32)
+        self._h.call("smgx_hash_ring_find_healthy", self.model, _p(data), _p(offsets), n, _p(ok), _p(out))
+        return [None if i < 0 else self.urls[i] for i in out[:n]]
+
+    def find_healthy_url(self, key: str, is_healthy):
+        return self.find_healthy_urls([key], is_healthy)[0]
+
+
+class PrefixHashPolicy:
+    """policies::PrefixHashPolicy (prefix_hash.rs:87-235) on the GPU: XXH3 of the first N tokens → ring lookup → bounded-load check."""
+
+    def __init__(self, config: Optional[PrefixHashConfig] = None, device_id: int = 0, max_batch: int = 0):
+        self.config = config or PrefixHashConfig()
+        self._h = _Handle(CacheAwareConfig(eviction_interval_secs=0), device_id, max_batch)
+        self._h.call("smgx_prefix_hash_configure", int(self.config.prefix_token_count), float(self.config.load_factor))
+        self._slices = {}
+        self._ring_of = {}
+
+    @classmethod
+    def with_defaults(cls, **kw):  # :100-103
+        return cls(PrefixHashConfig(), **kw)
+
+    def name(self) -> str:  # :231-233
+        return "prefix_hash"
+
+    def needs_request_text(self) -> bool:  # trait default (policies/mod.rs:77-79)
+        return False
+
+    def on_request_complete(self, worker_url: str, success: bool):  # trait default: no state
+        return None
+
+    def hash_ring(self, urls, model: str = UNKNOWN_MODEL_ID) -> HashRing:
+        """The registry's per-model ring (worker/registry.rs get_hash_ring), bound to this policy's device state."""
+        ring = HashRing(urls, handle=self._h, model=model)
+        self._ring_of[ring.model] = ring
+        return ring
+
+    def compute_prefix_hashes(self, requests):  # compute_prefix_hash (:106-113) for a batch
+        tokens, offsets = _ragged_tokens(requests)
+        n = offsets.size - 1
+        out = np.zeros(max(n, 1), np.uint64)
+        self._h.call("smgx_prefix_hashes", _tok_ptr(tokens), _p(offsets), n, _p(out))
+        return out[:n]
+
+    def _push_fleet(self, workers, ring: Optional[HashRing]) -> bytes:
+        # the ring is per model in the reference (SelectWorkerInfo.hash_ring comes from the registry keyed by model id); a policy
+        # without a ring for the call uses the model's own state with the ring cleared
+        model = ring.model if ring is not None else normalize_model_key(workers[0].model_id() if workers else "").encode()
+        if ring is not None and ring._h is not self._h:
+            raise ValueError("hash ring belongs to another policy handle: build it with PrefixHashPolicy.hash_ring()")
+        if ring is None and model in self._ring_of:
+            self._h.call("smgx_hash_ring_clear", model)
+            del self._ring_of[model]
+        urls = tuple(w.url() for w in workers)
+        if self._slices.get(model) != urls:
+            enc = [u.encode() for u in urls]
+            arr = (C.c_char_p * max(len(enc), 1))(*enc)
+            self._h.call("smgx_set_workers", model, arr, len(enc))
+            self._slices[model] = urls
+        loads = _u64([w.load() for w in workers])
+        healthy = np.ascontiguousarray(np.asarray([1 if w.is_healthy() else 0 for w in workers] or [0], dtype=np.uint8))
+        self._h.call("smgx_set_fleet_state", model, _p(loads) if len(workers) else None, _p(healthy), None, len(workers))
+        return model
+
+    def select_worker_batch(self, workers, requests=None, ring: Optional[HashRing] = None, tokens=None, offsets=None, has_tokens=None):
+        """One batch against one fleet snapshot → (idx int32[n] with -1 = None, branch names)."""
+        model = self._push_fleet(workers, ring)
+        if requests is not None:
+            has_tokens = [0 if r is None else 1 for r in requests]
+            tokens, offsets = _ragged_tokens([[] if r is None else r for r in requests])
+            if all(has_tokens):
+                has_tokens = None
+        tokens, offsets = _u32(tokens), _u32(offsets)
+        n = offsets.size - 1
+        out = np.full(max(n, 1), -1, np.int32)
+        info = (_lib.DecisionInfo * max(n, 1))()
+        flags = None if has_tokens is None else np.ascontiguousarray(np.asarray(has_tokens, np.uint8))
+        self._h.call("smgx_prefix_hash_select_batch_tokens", model, _tok_ptr(tokens), _p(offsets), n, _p(flags) if flags is not None else None, _p(out),
+                     C.cast(info, C.c_void_p))
+        return out[:n], [PREFIX_BRANCHES[info[i].branch] for i in range(n)]
+
+    def select_worker_impl(self, workers, info: SelectWorkerInfo):  # :203-222 → (Option<usize>, Branch)
+        idx, br = self.select_worker_batch(workers, [info.tokens], ring=info.hash_ring)
+        return (None if idx[0] < 0 else int(idx[0])), br[0]
+
+    def select_worker(self, workers, info: SelectWorkerInfo) -> Optional[int]:  # LoadBalancingPolicy::select_worker (:225-229)
+        return self.select_worker_impl(workers, info)[0]
+
+    def kernel_launches(self) -> int:
+        return int(self._h.L.smgx_kernel_launches(self._h.p))
+
+
+def _ragged_tokens(requests):
+    lens = [len(r) for r in requests]
+    offsets = np.zeros(len(requests) + 1, dtype=np.uint32)
+    np.cumsum(lens, out=offsets[1:])
+    tokens = _u32(np.concatenate([np.asarray(r, dtype=np.uint32) for r in requests]) if sum(lens) else [])
+    return tokens, offsets
+
+
+def _tok_ptr(tokens):
+    return _p(tokens) if tokens.size else C.cast(C.create_string_buffer(4), C.c_void_p)
+
+
 class PolicyFactory:
     """policies::PolicyFactory for the one policy this library replaces (factory.rs:17-93)."""
 
@@ -686,6 +840,8 @@ class PolicyFactory:
     def create_by_name(name: str, **kw):
         if name.lower() in ("cache_aware", "cacheaware"):  # factory.rs:84
             return CacheAwarePolicy(CacheAwareConfig(), **kw)
+        if name.lower() in ("prefix_hash", "prefixhash"):  # factory.rs:90
+            return PrefixHashPolicy.with_defaults(**kw)
         return None
 
     @staticmethod
