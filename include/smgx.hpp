@@ -9,6 +9,7 @@
 //   struct CacheAwarePolicy            policies/cache_aware.rs:74-352, 648-710       → smgx::CacheAwarePolicy
 //   kv_index::PositionalIndexer        crates/kv_index/src/event_tree.rs:257-444     → smgx::PositionalIndexer
 //   worker::KvEventMonitor (the slice the policy reads + apply_event)                 → smgx::KvEventMonitor
+//   struct PrefixHashPolicy / HashRing  policies/prefix_hash.rs:87-235, worker/hash_ring.rs:29-150 → smgx::PrefixHashPolicy / smgx::HashRing
 // Header-only; link with -lsmgx.  All work happens in the library's CUDA kernels — there is no CPU fallback behind these classes.
 #pragma once
 #include <cstdint>
@@ -65,9 +66,11 @@ struct CacheAwareConfig {   // policies/mod.rs:94-117 (+Default)
     size_t block_size = 16;
 };
 
-struct SelectWorkerInfo {   // policies/mod.rs:161-175 (headers / hash_ring are not read by cache_aware)
+class HashRing;
+struct SelectWorkerInfo {   // policies/mod.rs:161-175 (headers are not read on this path; hash_ring only by prefix_hash)
     std::optional<std::string> request_text;
     std::optional<std::vector<uint32_t>> tokens;
+    std::shared_ptr<HashRing> hash_ring;
 };
 
 class Worker {   // the scalars CacheAwarePolicy reads through `trait Worker`
@@ -307,6 +310,99 @@ private:
     CacheAwareConfig config_;
     std::shared_ptr<detail::Handle> h_;
     std::shared_ptr<KvEventMonitor> monitor_;
+    std::map<std::string, std::vector<std::string>> slices_;
+};
+
+// ---- adjacent policy on the same plumbing: prefix_hash (policies/prefix_hash.rs) over worker::HashRing (worker/hash_ring.rs) ----
+struct PrefixHashConfig {   // prefix_hash.rs:38-58
+    size_t prefix_token_count = 256;
+    double load_factor = 1.25;
+};
+
+class HashRing {   // per-model ring, built (hashed + sorted) inside the library
+public:
+    HashRing(std::shared_ptr<detail::Handle> h, std::string model, const std::vector<std::string>& urls) : h_(std::move(h)), model_(std::move(model)), urls_(urls) {
+        std::vector<const char*> c;
+        for (auto& u : urls_) c.push_back(u.c_str());
+        char* err = nullptr;
+        detail::check(smgx_hash_ring_set(h_->p, model_.c_str(), c.data(), (uint32_t)c.size(), &err), err);
+    }
+    size_t len() const { uint32_t n = 0; char* err = nullptr; detail::check(smgx_hash_ring_entries(h_->p, model_.c_str(), nullptr, nullptr, 0, &n, &err), err); return n; }   // :142-144
+    bool is_empty() const { return len() == 0; }
+    size_t worker_count() const { return len() / 150; }   // :147-149
+    // find_healthy_url (:102-134); the predicate is evaluated once per ring URL, the walk runs on the GPU
+    template <class F> std::optional<std::string> find_healthy_url(const std::string& key, F is_healthy) const {
+        std::vector<uint8_t> ok(urls_.size() ? urls_.size() : 1, 0);
+        for (size_t u = 0; u < urls_.size(); ++u) ok[u] = is_healthy(urls_[u]) ? 1 : 0;
+        const uint32_t offs[2] = {0, (uint32_t)key.size()};
+        int32_t out = -1;
+        char* err = nullptr;
+        detail::check(smgx_hash_ring_find_healthy(h_->p, model_.c_str(), (const uint8_t*)key.data(), offs, 1, ok.data(), &out, &err), err);
+        return out < 0 ? std::nullopt : std::optional<std::string>(urls_[(size_t)out]);
+    }
+    const std::string& model() const { return model_; }
+    const std::shared_ptr<detail::Handle>& handle() const { return h_; }
+private:
+    std::shared_ptr<detail::Handle> h_;
+    std::string model_;
+    std::vector<std::string> urls_;
+};
+
+class PrefixHashPolicy : public LoadBalancingPolicy {   // prefix_hash.rs:87-235
+public:
+    explicit PrefixHashPolicy(const PrefixHashConfig& config = PrefixHashConfig(), int device_id = 0, uint32_t max_batch = 0) : config_(config) {
+        smgx_cache_aware_config c;
+        smgx_default_config(&c);
+        c.eviction_interval_secs = 0; c.device_id = device_id; c.max_batch = max_batch;
+        h_ = std::make_shared<detail::Handle>(c);
+        char* err = nullptr;
+        detail::check(smgx_prefix_hash_configure(h_->p, config.prefix_token_count, config.load_factor, &err), err);
+    }
+    static PrefixHashPolicy with_defaults() { return PrefixHashPolicy(); }   // :100-103
+    const char* name() const override { return "prefix_hash"; }              // :231-233
+    // the registry's per-model ring (SelectWorkerInfo.hash_ring), bound to this policy's device state
+    std::shared_ptr<HashRing> hash_ring(const std::vector<std::string>& urls, const std::string& model = UNKNOWN_MODEL_ID) {
+        return std::make_shared<HashRing>(h_, normalize_model_key(model), urls);
+    }
+    std::vector<Decision> select_worker_batch(const Workers& workers, const std::vector<std::optional<std::vector<uint32_t>>>& requests,
+                                              const std::shared_ptr<HashRing>& ring) {
+        if (ring && ring->handle() != h_) throw std::invalid_argument("hash ring belongs to another policy: build it with PrefixHashPolicy::hash_ring()");
+        const std::string model = ring ? ring->model() : normalize_model_key(workers.empty() ? "" : workers[0]->model_id());
+        char* err = nullptr;
+        if (!ring) detail::check(smgx_hash_ring_clear(h_->p, model.c_str(), &err), err);
+        std::vector<std::string> urls;
+        for (auto& w : workers) urls.push_back(w->url());
+        auto it = slices_.find(model);
+        if (it == slices_.end() || it->second != urls) {
+            std::vector<const char*> c;
+            for (auto& u : urls) c.push_back(u.c_str());
+            detail::check(smgx_set_workers(h_->p, model.c_str(), c.data(), (uint32_t)c.size(), &err), err);
+            slices_[model] = urls;
+        }
+        std::vector<uint64_t> loads;
+        std::vector<uint8_t> healthy;
+        for (auto& w : workers) { loads.push_back(w->load()); healthy.push_back(w->is_healthy()); }   // only load() and is_healthy() are read (:140, :148)
+        detail::check(smgx_set_fleet_state(h_->p, model.c_str(), loads.data(), healthy.data(), nullptr, (uint32_t)workers.size(), &err), err);
+        std::vector<uint32_t> toks, offs{0};
+        std::vector<uint8_t> has;
+        for (auto& r : requests) { if (r) toks.insert(toks.end(), r->begin(), r->end()); has.push_back(r ? 1 : 0); offs.push_back((uint32_t)toks.size()); }
+        if (toks.empty()) toks.push_back(0);
+        std::vector<int32_t> idx(requests.size(), -1);
+        std::vector<smgx_decision_info> info(requests.size());
+        detail::check(smgx_prefix_hash_select_batch_tokens(h_->p, model.c_str(), toks.data(), offs.data(), (uint32_t)requests.size(), has.data(), idx.data(), info.data(),
+                                                           &err), err);
+        std::vector<Decision> out(idx.size());
+        for (size_t i = 0; i < idx.size(); ++i) out[i] = Decision{idx[i], info[i]};
+        return out;
+    }
+    // LoadBalancingPolicy::select_worker (:225-229)
+    std::optional<size_t> select_worker(const Workers& workers, const SelectWorkerInfo& info) override {
+        const Decision d = select_worker_batch(workers, {info.tokens}, info.hash_ring)[0];
+        return d.idx < 0 ? std::nullopt : std::optional<size_t>((size_t)d.idx);
+    }
+private:
+    PrefixHashConfig config_;
+    std::shared_ptr<detail::Handle> h_;
     std::map<std::string, std::vector<std::string>> slices_;
 };
 

@@ -1,11 +1,9 @@
-// prefix_hash policy on the GPU (model_gateway/src/policies/prefix_hash.rs:106-222) — one launch per batch (or per ≤ 32 batches):
+// prefix_hash policy on the GPU (model_gateway/src/policies/prefix_hash.rs:106-222) — two launches per batch (or per ≤ 32 batches):
 //
-//   phase 1  compute_prefix_hash (:106-113): XXH3-64 (seed 0) of the first min(n, prefix_token_count) tokens, ONE WARP PER REQUEST.
-//            Above 240 bytes XXH3 accumulates 64-byte stripes into eight 64-bit lanes with plain additions, so the stripes of a
-//            1 KiB block are summed in any order: lane (g, i) = (lane >> 3, lane & 7) takes accumulator i of stripes g, g+4, g+8, g+12,
-//            the warp reads 256 contiguous bytes per step (8 B per lane, coalesced), and three shuffle steps fold the partial sums.
+//   K-prefix-1  compute_prefix_hash (:106-113): XXH3-64 (seed 0) of the first min(n, prefix_token_count) tokens, EIGHT LANES PER REQUEST
+//            (lane i owns XXH3's accumulator i; see xxh3_group), four requests per warp.
 //            This is the only HBM traffic of the policy: ≤ prefix_token_count × 4 bytes per request, read once.
-//   phase 2  one thread per request: format!("{prefix_hash:016x}") → blake3 of those 16 bytes (one compression, hash_ring.rs:78-86)
+//   K-prefix-2  one thread per request: format!("{prefix_hash:016x}") → blake3 of those 16 bytes (one compression, hash_ring.rs:78-86)
 //            → partition_point over the sorted ring (:110) → clockwise walk to the first healthy worker of the slice (:119-131)
 //            → load_ok / least-loaded fallback against the fleet summary computed once per snapshot (prefix_hash.rs:116-127, :164-197).
 //            Ring (150 entries per worker) and fleet arrays are a few hundred KB and stay in L2.
@@ -21,34 +19,28 @@ constexpr int kReqPerCta = 32;
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 
-__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) { return __shfl_xor_sync(0xFFFFFFFFu, v, m); }
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-
 // inputs of ≤ 240 bytes take XXH3's short forms: a handful of dependent multiplies, done by every lane on the same words
-__device__ __noinline__ uint64_t xxh3_small(const uint32_t* __restrict__ w, uint32_t n) { return xxh3_words(w, n, 0); }
+__device__ __noinline__ uint64_t xxh3_small(const uint32_t* __restrict__ w, uint32_t n) { return xxh3_words_upto60(w, n, 0); }
 
-__device__ __forceinline__ uint64_t ld64(const uint32_t* __restrict__ p, bool aligned) {
-    if (aligned) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); return mk64(v.x, v.y); }
-    return mk64(__ldg(p), __ldg(p + 1));
-}
-
-struct LaneKeys {      // the slices of the default secret this lane ever reads (seed 0: the secret is used as is)
-    uint64_t stripe[4];   // accumulate: secret bytes 8·(s + i), s = g + 4·it
-    uint64_t last;        // last stripe: secret bytes 121 + 8·i
-    uint64_t scramble;    // secret bytes 128 + 8·i
-    uint64_t merge0, merge1;   // final merge of accumulators (2j, 2j+1), j = lane & 3: secret bytes 11 + 16·j, +8
-    uint64_t init;        // initial accumulator i
+// ---- XXH3-64 (seed 0) of n > 60 words by a group of 8 lanes: lane i owns accumulator i for every stripe ----
+// Above 240 bytes XXH3 folds 64-byte stripes into eight 64-bit accumulators; accumulator i of a stripe needs data qword i (multiply)
+// and qword i ^ 1 (add).  Lane i of the group therefore reads qword i of every stripe (the group reads one whole stripe, 64 contiguous
+// bytes, per instruction), keeps acc[i] and the running sum of its own data, and hands that sum to lane i ^ 1 once per 1 KiB block.
+// Four requests share a warp, so every load / xor / multiply instruction serves four requests and the fixed tail (merge + avalanche)
+// is paid once per four.
+struct GroupKeys {
+    uint64_t last;             // last stripe: secret bytes 121 + 8·i
+    uint64_t scramble;         // secret bytes 128 + 8·i
+    uint64_t merge0, merge1;   // final merge of accumulators (2j, 2j+1), j = i & 3: secret bytes 11 + 16·j, +8
+    uint64_t init;             // initial accumulator i
 };
 
-__device__ __forceinline__ LaneKeys lane_keys(int lane) {
-    const int i = lane & 7, g = lane >> 3, j = lane & 3;
-    LaneKeys k;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) k.stripe[it] = sec64(8 * (g + 4 * it + i));
+__device__ __forceinline__ GroupKeys group_keys(int i) {
+    GroupKeys k;
     k.last = sec64_unaligned(121 + 8 * i);
     k.scramble = sec64(128 + 8 * i);
-    k.merge0 = sec64_unaligned(11 + 16 * j);
-    k.merge1 = sec64_unaligned(19 + 16 * j);
+    k.merge0 = sec64_unaligned(11 + 16 * (i & 3));
+    k.merge1 = sec64_unaligned(19 + 16 * (i & 3));
     const uint64_t init[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
     k.init = init[0];
 #pragma unroll
@@ -56,55 +48,54 @@ __device__ __forceinline__ LaneKeys lane_keys(int lane) {
     return k;
 }
 
-// XXH3-64, seed 0, of n > 60 words at w; every lane returns the hash
-__device__ __forceinline__ uint64_t xxh3_long_warp(const uint32_t* __restrict__ w, uint32_t n, int lane, const LaneKeys& k) {
-    const int i = lane & 7, g = lane >> 3;
+template <bool kAligned>
+__device__ __forceinline__ uint64_t ldq(const uint32_t* __restrict__ p) {
+    if (kAligned) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); return mk64(v.x, v.y); }
+    return mk64(__ldg(p), __ldg(p + 1));
+}
+
+// s_sec: the default secret as 24 qwords in shared memory (stripe s, accumulator i reads qword s + i)
+template <bool kAligned>
+__device__ __forceinline__ uint64_t xxh3_group(const uint32_t* __restrict__ w, uint32_t n, int i, uint32_t gmask, const GroupKeys& k,
+                                               const uint64_t* __restrict__ s_sec) {
     const uint32_t len = n * 4;
     const uint32_t nb_blocks = (len - 1) >> 10;
-    const bool al = (reinterpret_cast<uintptr_t>(w) & 7) == 0;
     uint64_t acc = k.init;
-    for (uint32_t b = 0; b < nb_blocks; ++b) {
-        const uint32_t* bw = w + b * 256 + g * 16 + 2 * i;
+    const uint32_t* p = w + 2 * i;
+    for (uint32_t b = 0; b < nb_blocks; ++b, p += 256) {
         uint64_t A = 0, B = 0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const uint64_t dv = ld64(bw + it * 64, al), dk = dv ^ k.stripe[it];
+        for (int st = 0; st < 16; ++st) {
+            const uint64_t dv = ldq<kAligned>(p + st * 16), dk = dv ^ s_sec[st + i];
             A += (dk & 0xFFFFFFFFULL) * (dk >> 32);
             B += dv;
         }
-        uint64_t t = A + shfl_xor64(B, 1);   // acc[i ^ 1] += data: the neighbour's data sum lands here
-        t += shfl_xor64(t, 8);
-        t += shfl_xor64(t, 16);
-        acc += t;
+        acc += A + __shfl_xor_sync(gmask, B, 1);
         acc = (acc ^ (acc >> 47) ^ k.scramble) * P32_1;
     }
     const uint32_t nst = ((len - 1) - (nb_blocks << 10)) >> 6;   // whole stripes of the last, partial block (0..15)
-    const uint32_t* bw = w + nb_blocks * 256 + g * 16 + 2 * i;
     uint64_t A = 0, B = 0;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        if ((uint32_t)(g + 4 * it) < nst) {
-            const uint64_t dv = ld64(bw + it * 64, al), dk = dv ^ k.stripe[it];
+    for (int st = 0; st < 15; ++st) {
+        if ((uint32_t)st < nst) {
+            const uint64_t dv = ldq<kAligned>(p + st * 16), dk = dv ^ s_sec[st + i];
             A += (dk & 0xFFFFFFFFULL) * (dk >> 32);
             B += dv;
         }
     }
-    if (g == 0) {   // the last 64 bytes of the input against secret bytes [121, 185)
+    {   // the last 64 bytes of the input against secret bytes [121, 185)
         const uint32_t* lw = w + n - 16 + 2 * i;
-        const uint64_t dv = ld64(lw, (reinterpret_cast<uintptr_t>(lw) & 7) == 0), dk = dv ^ k.last;
+        const uint64_t dv = (reinterpret_cast<uintptr_t>(lw) & 7) == 0 ? ldq<true>(lw) : ldq<false>(lw), dk = dv ^ k.last;
         A += (dk & 0xFFFFFFFFULL) * (dk >> 32);
         B += dv;
     }
-    uint64_t t = A + shfl_xor64(B, 1);
-    t += shfl_xor64(t, 8);
-    t += shfl_xor64(t, 16);
-    acc += t;
-    // merge: len·P64_1 + Σ_j mul128_fold64(acc[2j] ^ k0_j, acc[2j+1] ^ k1_j); lane & 3 = j, lanes 0..7 hold acc[0..7]
-    const int j = lane & 3;
-    const uint64_t a0 = shfl64(acc, 2 * j), a1 = shfl64(acc, 2 * j + 1);
+    acc += A + __shfl_xor_sync(gmask, B, 1);
+    // merge: len·P64_1 + Σ_j mul128_fold64(acc[2j] ^ k0_j, acc[2j+1] ^ k1_j); lane j = i & 3 takes pair j
+    const int lane = threadIdx.x & 31, base = lane & ~7, j = i & 3;
+    const uint64_t a0 = __shfl_sync(gmask, acc, base + 2 * j), a1 = __shfl_sync(gmask, acc, base + 2 * j + 1);
     uint64_t r = mul128_fold64(a0 ^ k.merge0, a1 ^ k.merge1);
-    r += shfl_xor64(r, 1);
-    r += shfl_xor64(r, 2);
+    r += __shfl_xor_sync(gmask, r, 1);
+    r += __shfl_xor_sync(gmask, r, 2);
     return avalanche((uint64_t)len * P64_1 + r);
 }
 
@@ -112,35 +103,44 @@ __device__ __forceinline__ bool load_ok(uint64_t load, const PrefixDerived& d) {
     return d.all_ok || (double)load <= d.threshold;
 }
 
-__global__ void __launch_bounds__(kThreads) prefix_select_kernel(const RingView ring, const PrefixFleetView fleet, const __grid_constant__ PrefixArgs a) {
+// K-prefix-1: compute_prefix_hash of every request → bt.hash[r].  8 lanes per request, 4 requests per warp, 2 rounds per warp.
+__global__ void __launch_bounds__(kThreads) prefix_hash_kernel(const __grid_constant__ PrefixArgs a) {
     const PrefixBatch& bt = a.b[blockIdx.y];
     const uint32_t first = blockIdx.x * kReqPerCta;
     if (first >= bt.n) return;
-    __shared__ uint64_t s_hash[kReqPerCta];
-    __shared__ uint32_t s_len[kReqPerCta];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const LaneKeys keys = lane_keys(lane);
-    // ---- phase 1: one warp per request ----
-    for (uint32_t q = warp; q < kReqPerCta; q += kWarps) {
-        const uint32_t r = first + q;
-        if (r >= bt.n) break;
-        const uint32_t beg = __ldg(bt.offsets + r), n = __ldg(bt.offsets + r + 1) - beg;
+    __shared__ uint64_t s_sec[24];
+    if (threadIdx.x < 24) s_sec[threadIdx.x] = sec64(8 * threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, i = lane & 7;
+    const uint32_t gmask = 0xFFu << (8 * sub);
+    const GroupKeys keys = group_keys(i);
+    constexpr int kRounds = kReqPerCta / (kWarps * 4);
+#pragma unroll 1
+    for (int round = 0; round < kRounds; ++round) {
+        const uint32_t r = first + (warp * kRounds + round) * 4 + sub;
+        const bool valid = r < bt.n;
+        uint32_t beg = 0, n = 0;
+        if (valid) { beg = __ldg(bt.offsets + r); n = __ldg(bt.offsets + r + 1) - beg; }
         const uint32_t use = min(n, a.prefix_tokens);
         const uint32_t* w = bt.tokens + beg;
+        const bool al = (reinterpret_cast<uintptr_t>(w) & 7) == 0;
+        const bool all_al = __all_sync(0xFFFFFFFFu, al || !valid || use <= 60);
+        if (!valid) continue;
         uint64_t h;
-        if (use > 60) h = xxh3_long_warp(w, use, lane, keys);
-        else h = xxh3_small(w, use);
-        if (lane == 0) { s_hash[q] = h; s_len[q] = n; }
+        if (use <= 60) h = xxh3_small(w, use);
+        else if (all_al) h = xxh3_group<true>(w, use, i, gmask, keys, s_sec);
+        else h = xxh3_group<false>(w, use, i, gmask, keys, s_sec);
+        if (i == 0) bt.hash[r] = h;
     }
-    __syncthreads();
-    // ---- phase 2: one thread per request ----
-    if (threadIdx.x >= kReqPerCta) return;
-    const uint32_t r = first + threadIdx.x;
-    if (r >= bt.n) return;
-    const uint64_t ph = s_hash[threadIdx.x];
-    const uint32_t n_tok = s_len[threadIdx.x];
-    if (bt.out_hash) bt.out_hash[r] = ph;
-    if (!bt.out_idx) return;
+}
+
+// K-prefix-2: one thread per request: ring lookup + bounded-load pick from bt.hash[r]
+__global__ void __launch_bounds__(kThreads) prefix_pick_kernel(const RingView ring, const PrefixFleetView fleet, const __grid_constant__ PrefixArgs a) {
+    const PrefixBatch& bt = a.b[blockIdx.y];
+    const uint32_t r = blockIdx.x * kThreads + threadIdx.x;
+    if (r >= bt.n || !bt.out_idx) return;
+    const uint64_t ph = bt.hash[r];
+    const uint32_t n_tok = __ldg(bt.offsets + r + 1) - __ldg(bt.offsets + r);
     const PrefixDerived d = *fleet.derived;
     int32_t idx = -1;
     uint8_t branch;
@@ -170,8 +170,12 @@ __global__ void __launch_bounds__(kThreads) prefix_select_kernel(const RingView 
             for (int q = 0; q < 8; ++q) cv[q] = b3::kIV[q];
             b3::compress(cv, m, 0, 16, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT);
             const uint64_t key_pos = mk64(cv[0], cv[1]);
-            uint32_t lo = 0, hi = ring.len;   // partition_point(|pos| pos < key_pos)
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(ring.pos + mid) < key_pos) lo = mid + 1; else hi = mid; }
+            // partition_point(|pos| pos < key_pos): positions are uniform 64-bit hashes, so a table of "first entry at or above
+            // bucket b's lower bound" (2+ buckets per entry) lands within an entry or two of the answer — two dependent loads, not 14
+            const uint32_t bk = (uint32_t)(key_pos >> ring.bucket_shift);
+            uint32_t lo = __ldg(ring.bucket + bk);
+            const uint32_t hi = __ldg(ring.bucket + bk + 1);
+            while (lo < hi && __ldg(ring.pos + lo) < key_pos) ++lo;
             uint32_t e = lo == ring.len ? 0 : lo;
             for (uint32_t step = 0; step < ring.len; ++step) {
                 int32_t s = __ldg(ring.slice + e);
@@ -270,13 +274,16 @@ void launch_prefix_fleet_prepare(const uint64_t* d_loads, const uint8_t* d_flags
     SMGX_CUDA(cudaGetLastError());
 }
 
-void launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet, const PrefixArgs& a, cudaStream_t stream) {
+uint32_t launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet, const PrefixArgs& a, cudaStream_t stream) {
     uint32_t max_n = 0;
     for (uint32_t k = 0; k < a.count; ++k) max_n = max_n > a.b[k].n ? max_n : a.b[k].n;
-    if (max_n == 0 || a.count == 0) return;
-    dim3 grid((max_n + kReqPerCta - 1) / kReqPerCta, a.count);
-    prefix_select_kernel<<<grid, kThreads, 0, stream>>>(ring, fleet, a);
+    if (max_n == 0 || a.count == 0) return 0;
+    prefix_hash_kernel<<<dim3((max_n + kReqPerCta - 1) / kReqPerCta, a.count), kThreads, 0, stream>>>(a);
+    bool pick = false;
+    for (uint32_t k = 0; k < a.count; ++k) pick = pick || a.b[k].out_idx != nullptr;
+    if (pick) prefix_pick_kernel<<<dim3((max_n + kThreads - 1) / kThreads, a.count), kThreads, 0, stream>>>(ring, fleet, a);
     SMGX_CUDA(cudaGetLastError());
+    return pick ? 2u : 1u;
 }
 
 void launch_ring_find(const uint64_t* d_ring_pos, const uint32_t* d_ring_url, uint32_t len, const uint64_t* d_key_pos, const uint8_t* d_url_ok, uint32_t n,

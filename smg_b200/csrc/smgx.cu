@@ -64,7 +64,8 @@ struct ModelState {
     std::vector<std::string> ring_urls;
     std::vector<uint64_t> ring_pos;       // sorted positions
     std::vector<uint32_t> ring_url;       // entry → index into ring_urls
-    DevBuf d_ring_pos, d_ring_slice, d_ring_url, d_dup_prev, d_pf_loads, d_pf_flags, d_pf_derived;
+    DevBuf d_ring_pos, d_ring_slice, d_ring_url, d_ring_bucket, d_dup_prev, d_pf_loads, d_pf_flags, d_pf_derived;
+    uint32_t ring_bucket_shift = 63;
     bool pf_struct_dirty = true;          // slice or ring changed: entry → slice map must be rebuilt
     bool pf_state_dirty = true;           // loads / health changed: fleet summary must be recomputed
 };
@@ -472,6 +473,19 @@ public:
             std::vector<int32_t> slice_of_url(std::max<size_t>(m.ring_urls.size(), 1), -1), ring_slice(std::max<uint32_t>(len, 1), -1);
             for (size_t u = 0; u < m.ring_urls.size(); ++u) { auto it = last_of.find(m.ring_urls[u]); if (it != last_of.end()) slice_of_url[u] = it->second; }
             for (uint32_t e = 0; e < len; ++e) ring_slice[e] = slice_of_url[m.ring_url[e]];
+            uint32_t kbits = 1;
+            while ((1ull << kbits) < 2ull * len && kbits < 31) ++kbits;
+            const uint32_t nbk = 1u << kbits;
+            std::vector<uint32_t> bucket(nbk + 1);
+            for (uint32_t b = 0, e = 0; b <= nbk; ++b) {
+                if (b == nbk) { bucket[b] = len; break; }
+                const uint64_t lower = (uint64_t)b << (64 - kbits);
+                while (e < len && m.ring_pos[e] < lower) ++e;
+                bucket[b] = e;
+            }
+            m.ring_bucket_shift = 64 - kbits;
+            m.d_ring_bucket.reserve(bucket.size() * 4);
+            SMGX_CUDA(cudaMemcpyAsync(m.d_ring_bucket.ptr, bucket.data(), bucket.size() * 4, cudaMemcpyHostToDevice, lane.stream));
             m.d_ring_pos.reserve(std::max<uint32_t>(len, 1) * 8);
             m.d_ring_slice.reserve(std::max<uint32_t>(len, 1) * 4);
             m.d_ring_url.reserve(std::max<uint32_t>(len, 1) * 4);
@@ -500,6 +514,7 @@ public:
             m.pf_state_dirty = false;
         }
         rv->pos = m.d_ring_pos.as<uint64_t>(); rv->slice = m.d_ring_slice.as<int32_t>(); rv->len = len; rv->has_ring = m.has_ring ? 1u : 0u;
+        rv->bucket = m.d_ring_bucket.as<uint32_t>(); rv->bucket_shift = m.ring_bucket_shift;
         fv->loads = m.d_pf_loads.as<uint64_t>(); fv->flags = m.d_pf_flags.as<uint8_t>(); fv->dup_prev = m.d_dup_prev.as<int32_t>();
         fv->derived = m.d_pf_derived.as<PrefixDerived>(); fv->n_slice = ns;
     }
@@ -1719,7 +1734,7 @@ static smgx_status prefix_host_call(smgx_policy* p, const char* model_key, const
         lane.d_info.reserve((size_t)n * sizeof(smgx_decision_info));
         lane.d_hashes.reserve((size_t)n * 8);
         SMGX_CUDA(cudaMemcpyAsync(lane.d_tokens.ptr, P.pf_stage.ptr, in_bytes, cudaMemcpyHostToDevice, lane.stream));
-        RingView rv{nullptr, nullptr, 0, 0};
+        RingView rv{nullptr, nullptr, 0, 0, nullptr, 63};
         PrefixFleetView fv{nullptr, nullptr, nullptr, nullptr, 0};
         if (m) P.sync_prefix(*m, &rv, &fv);
         PrefixArgs a;
@@ -1729,10 +1744,9 @@ static smgx_status prefix_host_call(smgx_policy* p, const char* model_key, const
         a.b[0].has_tokens = has_tokens ? reinterpret_cast<const uint8_t*>(d_tok + total + n + 1) : nullptr;
         a.b[0].out_idx = out_idx ? lane.d_out.as<int32_t>() : nullptr;
         a.b[0].out_info = out_info ? lane.d_info.as<smgx_decision_info>() : nullptr;
-        a.b[0].out_hash = out_hash ? lane.d_hashes.as<uint64_t>() : nullptr;
+        a.b[0].hash = lane.d_hashes.as<uint64_t>();
         a.b[0].n = n;
-        launch_prefix_select(rv, fv, a, lane.stream);
-        ++P.launches;
+        P.launches += launch_prefix_select(rv, fv, a, lane.stream);
         const size_t hash_at = ((size_t)n * (4 + sizeof(smgx_decision_info)) + 7) & ~(size_t)7;
         P.pf_out.reserve(hash_at + (size_t)n * 8);
         int32_t* h_idx = P.pf_out.as<int32_t>();
@@ -1771,13 +1785,20 @@ smgx_status smgx_prefix_hash_select_many_tokens_device(smgx_policy* p, const cha
         ModelState& m = P.model(model_key, false);
         RingView rv; PrefixFleetView fv;
         P.sync_prefix(m, &rv, &fv);
+        uint64_t total = 0;
+        for (uint32_t j = 0; j < n_batches; ++j) total += n[j];
+        Lane& lane = P.lanes[0];
+        lane.d_hashes.reserve(std::max<uint64_t>(total, 1) * 8);   // prefix hashes between the two kernels; stream order keeps reuse safe
+        uint64_t at = 0;
         for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxPrefixBatches) {
             PrefixArgs a;
             a.count = std::min<uint32_t>(kMaxPrefixBatches, n_batches - j0);
             a.prefix_tokens = (uint32_t)P.prefix_token_count;
-            for (uint32_t k = 0; k < a.count; ++k) a.b[k] = PrefixBatch{d_tokens[j0 + k], d_offsets[j0 + k], nullptr, d_out_worker_idx[j0 + k], nullptr, nullptr, n[j0 + k]};
-            launch_prefix_select(rv, fv, a, P.lanes[0].stream);
-            ++P.launches;
+            for (uint32_t k = 0; k < a.count; ++k) {
+                a.b[k] = PrefixBatch{d_tokens[j0 + k], d_offsets[j0 + k], nullptr, d_out_worker_idx[j0 + k], nullptr, lane.d_hashes.as<uint64_t>() + at, n[j0 + k]};
+                at += n[j0 + k];
+            }
+            P.launches += launch_prefix_select(rv, fv, a, lane.stream);
         }
         return SMGX_SUCCESS;
     });

@@ -151,7 +151,8 @@ SMGX_HD void acc512(uint64_t (&acc)[8], const uint32_t* in /*16 words*/, const u
     }
 }
 
-SMGX_HD uint64_t xxh3_words(const uint32_t* w, uint32_t n, uint64_t seed) {
+// n ≤ 60 words (≤ 240 bytes): the short and mid-size forms
+SMGX_HD uint64_t xxh3_words_upto60(const uint32_t* w, uint32_t n, uint64_t seed) {
     const uint64_t len = (uint64_t)n * 4;
     if (n == 0) return xxh64_avalanche(seed ^ (sec64(56) ^ sec64(64)));
     if (n <= 2) {  // 4..8 bytes
@@ -186,7 +187,7 @@ SMGX_HD uint64_t xxh3_words(const uint32_t* w, uint32_t n, uint64_t seed) {
         acc += mix16(w[n - 4], w[n - 3], w[n - 2], w[n - 1], 16, seed);
         return avalanche(acc);
     }
-    if (n <= 60) {  // 132..240 bytes
+    {  // 132..240 bytes
         uint64_t acc = len * P64_1;
         uint32_t rounds = n / 4;
         for (uint32_t i = 0; i < 8; ++i) acc += mix16(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3], 16 * i, seed);
@@ -196,6 +197,11 @@ SMGX_HD uint64_t xxh3_words(const uint32_t* w, uint32_t n, uint64_t seed) {
         acc += mix16_unaligned(w[n - 4], w[n - 3], w[n - 2], w[n - 1], 136 - 17, seed);
         return avalanche(acc);
     }
+}
+
+SMGX_HD uint64_t xxh3_words(const uint32_t* w, uint32_t n, uint64_t seed) {
+    if (n <= 60) return xxh3_words_upto60(w, n, seed);
+    const uint64_t len = (uint64_t)n * 4;
     // > 240 bytes: stripes of 64 B against the seed-derived secret
     uint64_t cs[24];
 #pragma unroll

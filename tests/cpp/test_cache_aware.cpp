@@ -11,6 +11,7 @@
 
 #include "../../include/smgx.hpp"
 #include "../../oracle/cache_aware.h"
+#include "../../oracle/prefix_hash.h"
 
 static int g_fail = 0, g_checks = 0;
 #define CHECK(cond)                                                                                \
@@ -338,6 +339,88 @@ static void test_tree_streams_match_oracle() {
     }
 }
 
+// ---- prefix_hash (policies/prefix_hash.rs tests :236-414) -------------------------------------------------------------------------
+static Workers three_workers() {
+    return Workers{std::make_shared<BasicWorker>("http://w1:8000"), std::make_shared<BasicWorker>("http://w2:8000"), std::make_shared<BasicWorker>("http://w3:8000")};
+}
+static const std::vector<std::string> kW3 = {"http://w1:8000", "http://w2:8000", "http://w3:8000"};
+
+static void test_prefix_hash_consistent_routing() {   // prefix_hash.rs:262-284
+    smgx::PrefixHashPolicy policy({}, g_device);
+    Workers ws = three_workers();
+    SelectWorkerInfo info = toks({1, 2, 3, 4, 5, 6, 7, 8, 9, 10});
+    info.hash_ring = policy.hash_ring(kW3);
+    auto first = policy.select_worker(ws, info);
+    CHECK(first.has_value());
+    for (int k = 0; k < 10; ++k) CHECK(policy.select_worker(ws, info) == first);
+    CHECK(std::string(policy.name()) == "prefix_hash");
+    CHECK(!policy.needs_request_text());
+}
+
+static void test_prefix_hash_no_tokens_and_no_healthy() {   // prefix_hash.rs:341-386
+    smgx::PrefixHashPolicy policy({}, g_device);
+    Workers ws{std::make_shared<BasicWorker>("http://w1:8000")};
+    auto ring = policy.hash_ring({"http://w1:8000"});
+    auto d = policy.select_worker_batch(ws, {std::vector<uint32_t>{}, std::nullopt}, ring);
+    CHECK_EQ(d[0].idx, -1); CHECK_EQ(d[0].info.branch, SMGX_PH_NO_TOKENS);
+    CHECK_EQ(d[1].idx, -1); CHECK_EQ(d[1].info.branch, SMGX_PH_NO_TOKENS);
+    bw(ws, 0).set_healthy(false);
+    d = policy.select_worker_batch(ws, {std::vector<uint32_t>{1, 2, 3}}, ring);
+    CHECK_EQ(d[0].idx, -1); CHECK_EQ(d[0].info.branch, SMGX_PH_NO_HEALTHY_WORKERS);
+}
+
+static void test_hash_ring_surface() {   // hash_ring.rs:152-198
+    smgx::PrefixHashPolicy policy({}, g_device);
+    auto empty = policy.hash_ring({}, "empty");
+    CHECK(empty->is_empty());
+    CHECK(!empty->find_healthy_url("any-key", [](const std::string&) { return true; }).has_value());
+    auto ring = policy.hash_ring({"http://a", "http://b", "http://c"}, "abc");
+    CHECK_EQ(ring->len(), 450);
+    CHECK_EQ(ring->worker_count(), 3);
+    orc::HashRing oring({"http://a", "http://b", "http://c"});
+    for (int k = 0; k < 50; ++k) {
+        const std::string key = "routing-key-" + std::to_string(k);
+        auto got = ring->find_healthy_url(key, [](const std::string& u) { return u != "http://a"; });
+        int64_t want = oring.find_healthy(key, [](const std::string& u) { return u != "http://a"; });
+        CHECK(got.has_value() && want >= 0 && *got == oring.url((size_t)want));
+    }
+    CHECK(!ring->find_healthy_url("k", [](const std::string&) { return false; }).has_value());
+}
+
+static void test_prefix_hash_stream_matches_oracle() {
+    const uint32_t W = 40;
+    std::mt19937_64 rng(4242);
+    smgx::PrefixHashConfig cfg; cfg.prefix_token_count = 128; cfg.load_factor = 1.1;
+    smgx::PrefixHashPolicy policy(cfg, g_device);
+    orc::PrefixHashConfig ocfg; ocfg.prefix_token_count = 128; ocfg.load_factor = 1.1;
+    orc::PrefixHashPolicy opol(ocfg);
+    Workers ws;
+    std::vector<std::string> urls;
+    for (uint32_t i = 0; i < W; ++i) { urls.push_back("http://w" + std::to_string(i) + ":8000"); ws.push_back(std::make_shared<BasicWorker>(urls.back(), "m")); }
+    auto ring = policy.hash_ring(urls, "m");
+    orc::HashRing oring(urls);
+    for (int round = 0; round < 4; ++round) {
+        std::vector<orc::PrefixWorker> ows(W);
+        for (uint32_t w = 0; w < W; ++w) {
+            bw(ws, w).set_load(rng() % (round == 0 ? 1 : 25)); bw(ws, w).set_healthy(rng() % 5 != 0);
+            ows[w].url = urls[w]; ows[w].load = ws[w]->load(); ows[w].healthy = ws[w]->is_healthy();
+        }
+        std::vector<std::optional<std::vector<uint32_t>>> reqs;
+        for (int r = 0; r < 300; ++r) {
+            std::vector<uint32_t> t(rng() % 400);
+            for (auto& x : t) x = (uint32_t)(rng() % 128000);
+            if (r % 50 == 7) reqs.push_back(std::nullopt); else reqs.push_back(std::move(t));
+        }
+        auto got = policy.select_worker_batch(ws, reqs, round == 3 ? nullptr : ring);
+        for (size_t r = 0; r < reqs.size(); ++r) {
+            orc::PrefixBranch br;
+            const int64_t want = opol.select_worker(ows, reqs[r] ? reqs[r]->data() : nullptr, reqs[r] ? reqs[r]->size() : 0, round == 3 ? nullptr : &oring, &br);
+            CHECK_EQ(got[r].idx, want);
+            CHECK_EQ(got[r].info.branch, br);
+        }
+    }
+}
+
 // ---- host-only subset -----------------------------------------------------------------------------------------------------------------
 static void test_policy_surface() {   // cache_aware.rs:704-710, mod.rs:106-117
     CacheAwareConfig d;
@@ -424,6 +507,10 @@ int main(int argc, char** argv) {
         {"kv_events_fresh_chain_fallback", test_kv_events_fresh_chain_fallback, true},
         {"event_stream_matches_oracle", test_event_stream_matches_oracle, true},
         {"tree_streams_match_oracle", test_tree_streams_match_oracle, true},
+        {"prefix_hash_consistent_routing", test_prefix_hash_consistent_routing, true},
+        {"prefix_hash_no_tokens_and_no_healthy", test_prefix_hash_no_tokens_and_no_healthy, true},
+        {"hash_ring_surface", test_hash_ring_surface, true},
+        {"prefix_hash_stream_matches_oracle", test_prefix_hash_stream_matches_oracle, true},
     };
     int ran = 0;
     for (const T& t : tests) {

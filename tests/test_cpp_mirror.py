@@ -32,4 +32,4 @@ def test_cpp_mirror_host_subset():
 @pytest.mark.gpu
 def test_cpp_mirror_full():
     out = _run([])
-    assert "0 failures" in out and "16 tests" in out, out
+    assert "0 failures" in out and "20 tests" in out, out

@@ -313,6 +313,94 @@ def textwalk_mode():
             "roofline": {"bound": "hbm", "alg_bytes_per_decision": alg, "achieved": alg * dps / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * dps / 1e9 / peak}}
 
 
+def prefix_mode():
+    """Adjacent policy: prefix_hash on the config-2 fleet shape — 64 workers, 512-token requests, batches of 4096,
+    default PrefixHashConfig (first 256 tokens hashed).  Kernel-only (HBM-resident ring of batches larger than L2), through the C ABI
+    with host buffers, and the oracle on one host core."""
+    from oracle import orc
+    from smg_b200 import BasicWorker, PrefixHashPolicy, _lib, synth
+    W, B, T = 64, int(os.environ.get("BATCH", "4096")), 512
+    ring_n, steps, per_call = int(os.environ.get("RING", "32")), int(os.environ.get("STEPS", "50")), int(os.environ.get("PER_CALL", "32"))
+    urls = synth.worker_urls(W)
+    pol = PrefixHashPolicy(max_batch=B)
+    ws = [BasicWorker(u) for u in urls]
+    loads = synth.poisson_loads(W, 8, 42)
+    for w, l in zip(ws, loads):
+        w.set_load(int(l))
+    ring = pol.hash_ring(urls)
+    model = pol._push_fleet(ws, ring)
+    h = pol._h
+    L = _lib.load()
+    err = _lib.new_err()
+    offs = (np.arange(B + 1, dtype=np.uint64) * T).astype(np.uint32)
+    d_off = L.smgx_device_alloc(h.p, offs.nbytes, C.byref(err))
+    h.call("smgx_memcpy_h2d", d_off, offs.ctypes.data_as(C.c_void_p), offs.nbytes)
+    # shared system prompts: 256 distinct 256-token prefixes, Zipf-popular, each followed by a unique 256-token tail
+    rng = np.random.default_rng(42)
+    prefixes = rng.integers(0, 128000, size=(256, 256), dtype=np.uint32)
+    zw = 1.0 / np.arange(1, 257) ** 1.1
+    zw /= zw.sum()
+    host, d_tok, d_out = [], [], []
+    for j in range(ring_n):
+        q = rng.integers(0, 128000, size=(B, T), dtype=np.uint32)
+        shared = rng.random(B) < 0.7
+        q[shared, :256] = prefixes[rng.choice(256, size=int(shared.sum()), p=zw)]
+        q = np.ascontiguousarray(q.reshape(-1))
+        host.append(q)
+        ptr = L.smgx_device_alloc(h.p, q.nbytes, C.byref(err)); h.call("smgx_memcpy_h2d", ptr, q.ctypes.data_as(C.c_void_p), q.nbytes)
+        d_tok.append(ptr)
+        d_out.append(L.smgx_device_alloc(h.p, B * 4, C.byref(err)))
+    arr = lambda xs: (C.c_void_p * len(xs))(*xs)
+    ns = (C.c_uint32 * per_call)(*([B] * per_call))
+
+    def call(j0):
+        js = [(j0 + k) % ring_n for k in range(per_call)]
+        h.call("smgx_prefix_hash_select_many_tokens_device", model, per_call, arr([d_tok[j] for j in js]), arr([d_off] * per_call), ns, arr([d_out[j] for j in js]))
+
+    for w in range(3):
+        call(w * per_call)
+    h.call("smgx_synchronize")
+    l0 = pol.kernel_launches()
+    h.call("smgx_timer_start", 0)
+    for s in range(steps):
+        call(s * per_call)
+    ms = C.c_float()
+    h.call("smgx_timer_stop_ms", 0, C.byref(ms))
+    launches = pol.kernel_launches() - l0
+    n = steps * per_call * B
+    dps = n / (ms.value * 1e-3)
+    got = np.zeros(B, np.int32)
+    h.call("smgx_memcpy_d2h", got.ctypes.data_as(C.c_void_p), d_out[0], B * 4)
+    # oracle: one core, same batch; also the parity check of this run
+    opol, oring = orc.PrefixHashPolicy(), orc.HashRing(urls)
+    oidx, obr, secs = opol.select_batch(urls, loads, [1] * W, oring, host[0], offs.astype(np.uint64))
+    assert np.array_equal(got, oidx), "GPU picks differ from the oracle"
+    cpu_secs = min(opol.select_batch(urls, loads, [1] * W, oring, host[j], offs.astype(np.uint64))[2] for j in range(1, 4))
+    # through the C ABI with host buffers (pageable numpy arrays in, results out), synchronous calls
+    e_steps = int(os.environ.get("E2E_STEPS", "200"))
+    out = np.zeros(B, np.int32)
+    for j in range(3):
+        h.call("smgx_prefix_hash_select_batch_tokens", model, host[j].ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), B, None,
+               out.ctypes.data_as(C.c_void_p), None)
+    t0 = time.perf_counter()
+    for s in range(e_steps):
+        h.call("smgx_prefix_hash_select_batch_tokens", model, host[s % ring_n].ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), B, None,
+               out.ctypes.data_as(C.c_void_p), None)
+    e2e = e_steps * B / (time.perf_counter() - t0)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6486.8))
+    alg = 256 * 4 + 4 + 4   # hashed prefix + offset + pick
+    return {"mode": "prefix_hash policy (prefix_select_kernel): XXH3 of the first 256 tokens → blake3 ring lookup → bounded-load pick",
+            "workers": W, "batch": B, "tokens_per_request": T, "prefix_token_count": 256, "ring_entries": len(ring), "ring_batches": ring_n,
+            "input_bytes_resident": ring_n * B * T * 4, "batches_per_launch": per_call, "launches": int(launches),
+            "decisions_per_s": dps, "ms_per_batch": ms.value / (steps * per_call),
+            "branches": {orc.PREFIX_BRANCHES[int(k)]: int(v) for k, v in zip(*np.unique(obr, return_counts=True))},
+            "distinct_workers_picked": int(len(set(got.tolist()))),
+            "e2e_host_buffers_decisions_per_s": e2e, "h2d_bytes_per_step": B * 256 * 4 + (B + 1) * 4, "d2h_bytes_per_step": B * 4,
+            "cpu_baseline": {"value": B / cpu_secs, "unit": "decisions/s", "cores": 1, "kind": "port", "sample": "3 batches of 4096, best"},
+            "roofline": {"bound": "hbm", "alg_bytes_per_decision": alg, "achieved": alg * dps / 1e9, "peak": peak, "unit": "GB/s", "frac": alg * dps / 1e9 / peak}}
+
+
 def ingest_mode():
     """KV-event ingest: batches of 1024 Stored events (one 512-token sequence = 32 blocks of 16 tokens each, for worker
     i mod 64) through smgx_kv_events_apply — token_ids hashed in one GPU launch per batch, index writers on the host — vs the oracle's
@@ -462,6 +550,6 @@ def sharded_mode():
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "tree"
-    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "textwalk": textwalk_mode, "ingest": ingest_mode, "sharded": sharded_mode}[mode]()
+    r = {"tree": tree_mode, "treewalk": treewalk_mode, "text": text_mode, "textwalk": textwalk_mode, "ingest": ingest_mode, "sharded": sharded_mode, "prefix": prefix_mode}[mode]()
     if r is not None:
         print(json.dumps(r), flush=True)
