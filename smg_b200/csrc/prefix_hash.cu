@@ -290,14 +290,21 @@ void launch_prefix_fleet_prepare(const uint64_t* d_loads, const uint8_t* d_flags
     SMGX_CUDA(cudaGetLastError());
 }
 
-uint32_t launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet, const PrefixArgs& a, cudaStream_t stream) {
+uint32_t launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet, const PrefixArgs& a, cudaStream_t stream, cudaStream_t pick_stream,
+                              cudaEvent_t hashes_ready) {
     uint32_t max_n = 0;
     for (uint32_t k = 0; k < a.count; ++k) max_n = max_n > a.b[k].n ? max_n : a.b[k].n;
     if (max_n == 0 || a.count == 0) return 0;
     prefix_hash_kernel<<<dim3((max_n + kReqPerCta - 1) / kReqPerCta, a.count), kThreads, 0, stream>>>(a);
     bool pick = false;
     for (uint32_t k = 0; k < a.count; ++k) pick = pick || a.b[k].out_idx != nullptr;
-    if (pick) prefix_pick_kernel<<<dim3((max_n + kThreads - 1) / kThreads, a.count), kThreads, 0, stream>>>(ring, fleet, a);
+    if (pick) {
+        if (pick_stream != stream) {   // the latency-bound pick runs beside the next group's bandwidth-bound hash kernel
+            SMGX_CUDA(cudaEventRecord(hashes_ready, stream));
+            SMGX_CUDA(cudaStreamWaitEvent(pick_stream, hashes_ready, 0));
+        }
+        prefix_pick_kernel<<<dim3((max_n + kThreads - 1) / kThreads, a.count), kThreads, 0, pick_stream>>>(ring, fleet, a);
+    }
     SMGX_CUDA(cudaGetLastError());
     return pick ? 2u : 1u;
 }

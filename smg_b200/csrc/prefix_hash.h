@@ -48,7 +48,9 @@ struct PrefixArgs { PrefixBatch b[kMaxPrefixBatches]; uint32_t count; uint32_t p
 
 void launch_prefix_fleet_prepare(const uint64_t* d_loads, const uint8_t* d_flags, uint32_t n_slice, double load_factor, PrefixDerived* d_out, cudaStream_t stream);
 // returns the number of kernels launched (1: hashes only, 2: hashes + picks)
-uint32_t launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet, const PrefixArgs& a, cudaStream_t stream);
+// pick_stream == stream: both kernels in order on one stream; otherwise the pick kernel is ordered after `hashes_ready` on pick_stream
+uint32_t launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet, const PrefixArgs& a, cudaStream_t stream, cudaStream_t pick_stream,
+                              cudaEvent_t hashes_ready);
 // HashRing::find_healthy_url for precomputed key positions and a per-ring-URL predicate; out[i] = ring URL index or -1
 void launch_ring_find(const uint64_t* d_ring_pos, const uint32_t* d_ring_url, uint32_t len, const uint64_t* d_key_pos, const uint8_t* d_url_ok, uint32_t n,
                       int32_t* d_out, cudaStream_t stream);

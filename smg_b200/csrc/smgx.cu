@@ -140,7 +140,15 @@ public:
                 m.token_tree.reset();
                 m.string_tree.reset();
                 m.d_slice_of_tenant.release();
+                m.d_ring_pos.release(); m.d_ring_slice.release(); m.d_ring_url.release(); m.d_ring_bucket.release(); m.d_dup_prev.release();
+                m.d_pf_loads.release(); m.d_pf_flags.release(); m.d_pf_derived.release();
             }
+            for (int b = 0; b < 2; ++b) {
+                pf_hash_buf[b].release();
+                if (pf_hash_ev[b]) cudaEventDestroy(pf_hash_ev[b]);
+                if (pf_pick_ev[b]) cudaEventDestroy(pf_pick_ev[b]);
+            }
+            pf_stage.release(); pf_out.release();
             for (uint32_t q = 0; q < xch.peer.size(); ++q) if (q < xch.opened.size() && xch.opened[q] && xch.peer[q]) cudaIpcCloseMemHandle(xch.peer[q]);
             xch.local.release(); xch.d_bases.release(); xch.d_cand.release(); xch.d_fleet.release(); xch.d_arrive.release(); xch.d_gbase.release();
             d_err.release(); d_flush.release(); scratch.release(); scratch2.release(); d_gbase.release();
@@ -459,6 +467,8 @@ public:
     void sync_prefix(ModelState& m, RingView* rv, PrefixFleetView* fv) {
         Lane& lane = lanes[0];
         const uint32_t ns = (uint32_t)m.urls.size(), len = m.has_ring ? (uint32_t)m.ring_pos.size() : 0;
+        if (m.pf_struct_dirty || m.pf_state_dirty)   // pick kernels still running on the side lane read the arrays about to be replaced
+            for (int b = 0; b < 2; ++b) if (pf_pick_pending[b]) SMGX_CUDA(cudaStreamWaitEvent(lane.stream, pf_pick_ev[b], 0));
         if (m.pf_struct_dirty) {
             // `healthy_url_map` (prefix_hash.rs:155-159) collects url → (idx, worker) over the healthy workers in slice order, later
             // duplicates overwriting earlier ones: a ring URL resolves to the LAST healthy slice index carrying it.  last_of / dup_prev
@@ -521,6 +531,10 @@ public:
     uint64_t prefix_token_count = 256;   // PrefixHashConfig::default() (prefix_hash.rs:52-58)
     double prefix_load_factor = 1.25;
     PinBuf pf_stage, pf_out;             // pinned staging of the host-buffer prefix_hash call
+    DevBuf pf_hash_buf[2];               // prefix hashes between the hash and pick kernels of the device-resident path
+    cudaEvent_t pf_hash_ev[2] = {nullptr, nullptr}, pf_pick_ev[2] = {nullptr, nullptr};
+    bool pf_pick_pending[2] = {false, false};
+    uint64_t pf_group = 0;
 
     StringTreeIndex& stree_of(ModelState& m) {
         if (!m.string_tree) {
@@ -1746,7 +1760,7 @@ static smgx_status prefix_host_call(smgx_policy* p, const char* model_key, const
         a.b[0].out_info = out_info ? lane.d_info.as<smgx_decision_info>() : nullptr;
         a.b[0].hash = lane.d_hashes.as<uint64_t>();
         a.b[0].n = n;
-        P.launches += launch_prefix_select(rv, fv, a, lane.stream);
+        P.launches += launch_prefix_select(rv, fv, a, lane.stream, lane.stream, nullptr);
         const size_t hash_at = ((size_t)n * (4 + sizeof(smgx_decision_info)) + 7) & ~(size_t)7;
         P.pf_out.reserve(hash_at + (size_t)n * 8);
         int32_t* h_idx = P.pf_out.as<int32_t>();
@@ -1785,20 +1799,28 @@ smgx_status smgx_prefix_hash_select_many_tokens_device(smgx_policy* p, const cha
         ModelState& m = P.model(model_key, false);
         RingView rv; PrefixFleetView fv;
         P.sync_prefix(m, &rv, &fv);
-        uint64_t total = 0;
-        for (uint32_t j = 0; j < n_batches; ++j) total += n[j];
+        // Groups of ≤ 32 batches: hash kernel on lane 0, pick kernel on lane 1 behind an event, so that the pick of group g runs beside
+        // the hash kernel of group g + 1.  The hashes travel through two alternating scratch buffers; a buffer is reused only after
+        // the pick that read it has finished (event wait on lane 0).
         Lane& lane = P.lanes[0];
-        lane.d_hashes.reserve(std::max<uint64_t>(total, 1) * 8);   // prefix hashes between the two kernels; stream order keeps reuse safe
-        uint64_t at = 0;
+        Lane& side = P.lanes.size() > 1 ? P.lanes[1] : P.lanes[0];
         for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxPrefixBatches) {
             PrefixArgs a;
             a.count = std::min<uint32_t>(kMaxPrefixBatches, n_batches - j0);
             a.prefix_tokens = (uint32_t)P.prefix_token_count;
+            uint64_t total = 0;
+            for (uint32_t k = 0; k < a.count; ++k) total += n[j0 + k];
+            const uint32_t b = (uint32_t)(P.pf_group++ & 1);
+            if (!P.pf_hash_ev[b]) { SMGX_CUDA(cudaEventCreateWithFlags(&P.pf_hash_ev[b], cudaEventDisableTiming)); SMGX_CUDA(cudaEventCreateWithFlags(&P.pf_pick_ev[b], cudaEventDisableTiming)); }
+            if (P.pf_pick_pending[b]) SMGX_CUDA(cudaStreamWaitEvent(lane.stream, P.pf_pick_ev[b], 0));
+            if (total * 8 > P.pf_hash_buf[b].cap) { SMGX_CUDA(cudaDeviceSynchronize()); P.pf_hash_buf[b].reserve(total * 8); }
+            uint64_t at = 0;
             for (uint32_t k = 0; k < a.count; ++k) {
-                a.b[k] = PrefixBatch{d_tokens[j0 + k], d_offsets[j0 + k], nullptr, d_out_worker_idx[j0 + k], nullptr, lane.d_hashes.as<uint64_t>() + at, n[j0 + k]};
+                a.b[k] = PrefixBatch{d_tokens[j0 + k], d_offsets[j0 + k], nullptr, d_out_worker_idx[j0 + k], nullptr, P.pf_hash_buf[b].as<uint64_t>() + at, n[j0 + k]};
                 at += n[j0 + k];
             }
-            P.launches += launch_prefix_select(rv, fv, a, lane.stream);
+            P.launches += launch_prefix_select(rv, fv, a, lane.stream, side.stream, P.pf_hash_ev[b]);
+            if (&side != &lane) { SMGX_CUDA(cudaEventRecord(P.pf_pick_ev[b], side.stream)); P.pf_pick_pending[b] = true; }
         }
         return SMGX_SUCCESS;
     });

@@ -361,11 +361,11 @@ def prefix_mode():
         call(w * per_call)
     h.call("smgx_synchronize")
     l0 = pol.kernel_launches()
-    h.call("smgx_timer_start", 0)
+    h.call("smgx_timer_start_all")           # the pick kernels run on a side lane: time across all lanes
     for s in range(steps):
         call(s * per_call)
     ms = C.c_float()
-    h.call("smgx_timer_stop_ms", 0, C.byref(ms))
+    h.call("smgx_timer_stop_all_ms", C.byref(ms))
     launches = pol.kernel_launches() - l0
     n = steps * per_call * B
     dps = n / (ms.value * 1e-3)
@@ -390,7 +390,7 @@ def prefix_mode():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6486.8))
     alg = 256 * 4 + 4 + 4   # hashed prefix + offset + pick
-    return {"mode": "prefix_hash policy (prefix_select_kernel): XXH3 of the first 256 tokens → blake3 ring lookup → bounded-load pick",
+    return {"mode": "prefix_hash policy (prefix_hash_kernel + prefix_pick_kernel): XXH3 of the first 256 tokens → blake3 ring lookup → bounded-load pick",
             "workers": W, "batch": B, "tokens_per_request": T, "prefix_token_count": 256, "ring_entries": len(ring), "ring_batches": ring_n,
             "input_bytes_resident": ring_n * B * T * 4, "batches_per_launch": per_call, "launches": int(launches),
             "decisions_per_s": dps, "ms_per_batch": ms.value / (steps * per_call),
