@@ -171,6 +171,25 @@ size_t orc_stree_entries(void* h, char* out, size_t cap) {
     return copy_str(s, out, cap);
 }
 
+// mesh wire format (snapshot.rs): bincode bytes of Tree::snapshot(); load = from_snapshot, merge = merge_snapshot. 0 = decode error
+size_t orc_stree_snapshot_bytes(void* h, char* out, size_t cap) {
+    std::string b = StringTree::snapshot_to_bytes(((StringTree*)h)->snapshot());
+    if (out && cap >= b.size()) memcpy(out, b.data(), b.size());
+    return b.size();
+}
+int orc_stree_load_snapshot_bytes(void* h, const char* bytes, size_t n) {
+    StringTree::TreeSnapshot snap;
+    if (!StringTree::snapshot_from_bytes(std::string(bytes, n), snap)) return 0;
+    ((StringTree*)h)->load_snapshot(snap);
+    return 1;
+}
+int orc_stree_merge_snapshot_bytes(void* h, const char* bytes, size_t n) {
+    StringTree::TreeSnapshot snap;
+    if (!StringTree::snapshot_from_bytes(std::string(bytes, n), snap)) return 0;
+    ((StringTree*)h)->merge_snapshot(snap);
+    return 1;
+}
+
 // ---- CacheAwarePolicy ----
 void* orc_policy_new(float cache_threshold, uint64_t abs_thr, float rel_thr, uint64_t evict_secs, uint64_t max_tree, uint64_t block_size) {
     CacheAwareConfig c;

@@ -68,6 +68,9 @@ def lib():
         sig("orc_stree_used_sizes", sz, vp, vp, sz)
         sig("orc_stree_char_counts", sz, vp, vp, sz)
         sig("orc_stree_entries", sz, vp, vp, sz)
+        sig("orc_stree_snapshot_bytes", sz, vp, vp, sz)
+        sig("orc_stree_load_snapshot_bytes", C.c_int, vp, vp, sz)
+        sig("orc_stree_merge_snapshot_bytes", C.c_int, vp, vp, sz)
         sig("orc_policy_new", vp, C.c_float, u64, C.c_float, u64, u64, u64)
         sig("orc_policy_free", None, vp)
         sig("orc_policy_set_workers", None, vp, P(cp), P(cp), sz, C.c_int)
@@ -404,6 +407,59 @@ class Tree:
             path, tens = rec.split("\x1f")
             out.append((path, [(kv.rsplit("=", 1)[0], int(kv.rsplit("=", 1)[1])) for kv in tens.split(";") if kv]))
         return out
+
+    # ---- mesh wire format: kv_index::snapshot::TreeSnapshot (snapshot.rs) ----
+    def snapshot_bytes(self) -> bytes:       # Tree::snapshot().to_bytes() (string_tree.rs:1066, snapshot.rs:44)
+        n = lib().orc_stree_snapshot_bytes(self.h, None, 0)
+        buf = C.create_string_buffer(max(n, 1))
+        lib().orc_stree_snapshot_bytes(self.h, C.cast(buf, C.c_void_p), n)
+        return buf.raw[:n]
+
+    @classmethod
+    def from_snapshot_bytes(cls, data: bytes):   # TreeSnapshot::from_bytes + Tree::from_snapshot (:1228)
+        t = cls()
+        if not lib().orc_stree_load_snapshot_bytes(t.h, data, len(data)):
+            raise ValueError("bincode: malformed TreeSnapshot")
+        return t
+
+    def merge_snapshot_bytes(self, data: bytes):   # Tree::merge_snapshot (:1318)
+        if not lib().orc_stree_merge_snapshot_bytes(self.h, data, len(data)):
+            raise ValueError("bincode: malformed TreeSnapshot")
+
+
+def decode_snapshot(data: bytes):
+    """bincode 1.3 (default options) TreeSnapshot → [(edge, [(tenant, epoch)], child_count)], in plain Python (an independent reader
+    of the wire format for the tests)."""
+    import struct
+    at, out = 0, []
+    (n,) = struct.unpack_from("<Q", data, at); at += 8
+    for _ in range(n):
+        (ln,) = struct.unpack_from("<Q", data, at); at += 8
+        edge = data[at:at + ln].decode("utf-8"); at += ln
+        (nt,) = struct.unpack_from("<Q", data, at); at += 8
+        tens = []
+        for _ in range(nt):
+            (tl,) = struct.unpack_from("<Q", data, at); at += 8
+            name = data[at:at + tl].decode("utf-8"); at += tl
+            (ep,) = struct.unpack_from("<Q", data, at); at += 8
+            tens.append((name, ep))
+        (cc,) = struct.unpack_from("<I", data, at); at += 4
+        out.append((edge, tens, cc))
+    assert at == len(data)
+    return out
+
+
+def encode_snapshot(nodes) -> bytes:
+    import struct
+    b = struct.pack("<Q", len(nodes))
+    for edge, tens, cc in nodes:
+        e = edge.encode("utf-8")
+        b += struct.pack("<Q", len(e)) + e + struct.pack("<Q", len(tens))
+        for name, ep in tens:
+            t = name.encode("utf-8")
+            b += struct.pack("<Q", len(t)) + t + struct.pack("<Q", ep)
+        b += struct.pack("<I", cc)
+    return b
 
 
 BRANCHES = ["no_healthy", "imbalanced_min_load", "event_overlap", "event_min_load", "tree_match", "tree_min_load",

@@ -7,6 +7,10 @@
  *     :393-557 insert_text                 :561-649 match_prefix_with_counts (1-in-8 timestamp refresh :633-637)
  *     :659-720 prefix_match_tenant         :724-743 leaf_of   :745-849 evict_tenant_by_size
  *     :855-885 size accounting             :888-972 evict_by_tenant / remove_tenant_all
+ *     :1066-1102 snapshot (pre-order, children in char order)   :1228-1309 from_snapshot / restore_node
+ *     :1318-1545 merge_snapshot / merge_tree / merge_nodes (three edge cases)   :1563-1578 clone_subtree
+ *   crates/kv_index/src/snapshot.rs :18-52 TreeSnapshot / SnapshotNode, bincode = "1.3" default options (restated from its
+ *     published format: u64 little-endian lengths for Vec / String, fixed-width little-endian integers)
  * Pinned by the reference's unit tests ported in tests/test_oracle_string_tree.py (string_tree.rs:1704-2600).
  *
  * Text is held as Unicode scalar values (char32_t) so "char counts" are exact; the reference's ASCII byte
@@ -312,6 +316,191 @@ public:
         std::u32string path;
         walk_entries(root_, path, out);
     }
+
+    // ---- mesh wire format: snapshot.rs + string_tree.rs:1052-1578 ----
+    struct SnapshotNode { std::string edge; std::vector<std::pair<std::string, uint64_t>> tenants; uint32_t child_count = 0; };
+    using TreeSnapshot = std::vector<SnapshotNode>;
+
+    TreeSnapshot snapshot() const {  // :1066-1102; tenants in name order (deterministic stand-in for DashMap iteration)
+        TreeSnapshot out;
+        snapshot_node(root_, out);
+        return out;
+    }
+    static std::string snapshot_to_bytes(const TreeSnapshot& snap) {  // bincode::serialize (snapshot.rs:44-46)
+        std::string b;
+        put64(b, snap.size());
+        for (auto& n : snap) {
+            put64(b, n.edge.size()); b += n.edge;
+            put64(b, n.tenants.size());
+            for (auto& t : n.tenants) { put64(b, t.first.size()); b += t.first; put64(b, t.second); }
+            for (int i = 0; i < 4; ++i) b.push_back((char)((n.child_count >> (8 * i)) & 0xFF));
+        }
+        return b;
+    }
+    static bool snapshot_from_bytes(const std::string& b, TreeSnapshot& out) {  // bincode::deserialize (:49-51); false = Err
+        size_t at = 0;
+        uint64_t n;
+        out.clear();
+        if (!get64(b, at, n)) return false;
+        for (uint64_t i = 0; i < n; ++i) {
+            SnapshotNode nd;
+            uint64_t len, nt;
+            if (!get64(b, at, len) || b.size() - at < len) return false;
+            nd.edge = b.substr(at, len); at += len;
+            if (!get64(b, at, nt)) return false;
+            for (uint64_t k = 0; k < nt; ++k) {
+                uint64_t tl, ep;
+                if (!get64(b, at, tl) || b.size() - at < tl) return false;
+                std::string name = b.substr(at, tl); at += tl;
+                if (!get64(b, at, ep)) return false;
+                nd.tenants.push_back({name, ep});
+            }
+            if (b.size() - at < 4) return false;
+            nd.child_count = 0;
+            for (int k = 0; k < 4; ++k) nd.child_count |= (uint32_t)(unsigned char)b[at + k] << (8 * k);
+            at += 4;
+            out.push_back(std::move(nd));
+        }
+        return at == b.size();
+    }
+    // Tree::from_snapshot (:1228-1243) into THIS (emptied) tree
+    void load_snapshot(const TreeSnapshot& snap) {
+        clear();
+        if (snap.empty()) return;
+        size_t idx = 0;
+        restore_node(root_, snap, idx);
+    }
+    // :1318-1336
+    void merge_snapshot(const TreeSnapshot& snap) {
+        if (snap.empty()) return;
+        StringTree remote;
+        remote.load_snapshot(snap);
+        merge_nodes(root_, remote.root_);
+    }
+
+private:
+    static void put64(std::string& b, uint64_t v) { for (int i = 0; i < 8; ++i) b.push_back((char)((v >> (8 * i)) & 0xFF)); }
+    static bool get64(const std::string& b, size_t& at, uint64_t& v) {
+        if (b.size() - at < 8) return false;
+        v = 0;
+        for (int i = 0; i < 8; ++i) v |= (uint64_t)(unsigned char)b[at + i] << (8 * i);
+        at += 8;
+        return true;
+    }
+    static void snapshot_node(const Node* nd, TreeSnapshot& out) {  // :1072-1102
+        SnapshotNode sn;
+        sn.edge = utf8_encode(nd->text);
+        sn.tenants.assign(nd->tenants.begin(), nd->tenants.end());
+        sn.child_count = (uint32_t)nd->children.size();
+        out.push_back(std::move(sn));
+        for (auto& kv : nd->children) snapshot_node(kv.second, out);   // std::map: ascending char = children.sort_by_key (:1091)
+    }
+    void restore_node(Node* target, const TreeSnapshot& nodes, size_t& idx) {  // :1245-1309
+        if (idx >= nodes.size()) return;
+        const SnapshotNode& sn = nodes[idx++];
+        target->text = utf8_decode(sn.edge);
+        for (auto& t : sn.tenants) {
+            target->tenants[t.first] = t.second;
+            tenant_chars_[t.first] += target->text.size();   // and_modify(+=).or_insert: once per listed tenant, duplicates included
+        }
+        for (uint32_t c = 0; c < sn.child_count; ++c) {
+            if (idx >= nodes.size()) break;
+            std::u32string edge = utf8_decode(nodes[idx].edge);
+            if (edge.empty()) { skip_snapshot(nodes, idx); continue; }   // :1280-1296
+            Node* child = new Node();
+            child->parent = target;
+            restore_node(child, nodes, idx);
+            auto it = target->children.find(edge[0]);
+            if (it != target->children.end()) free_subtree(it->second);   // DashMap::insert replaces
+            target->children[edge[0]] = child;
+        }
+    }
+    static void skip_snapshot(const TreeSnapshot& nodes, size_t& idx) {
+        if (idx >= nodes.size()) return;
+        uint32_t cc = nodes[idx++].child_count;
+        for (uint32_t i = 0; i < cc; ++i) skip_snapshot(nodes, idx);
+    }
+    // remote wins on a newer epoch; a tenant new to the node adds `chars` to its size (:1343-1369, :1392-1414, :1479-1500)
+    void merge_tenants(Node* local, const Node* remote, size_t chars) {
+        for (auto& kv : remote->tenants) {
+            auto it = local->tenants.find(kv.first);
+            const bool is_new = it == local->tenants.end();
+            if (is_new || kv.second > it->second) {
+                local->tenants[kv.first] = kv.second;
+                if (is_new) tenant_chars_[kv.first] += chars;
+            }
+        }
+    }
+    static Node* clone_subtree(const Node* nd, Node* parent) {  // :1563-1578
+        Node* c = new Node();
+        c->text = nd->text; c->tenants = nd->tenants; c->parent = parent; c->has_last = nd->has_last; c->last_tenant = nd->last_tenant;
+        for (auto& kv : nd->children) c->children[kv.first] = clone_subtree(kv.second, c);
+        return c;
+    }
+    void accumulate_tenant_counts(const Node* nd) {  // :1548-1561
+        for (auto& kv : nd->tenants) tenant_chars_[kv.first] += nd->text.size();
+        for (auto& kv : nd->children) accumulate_tenant_counts(kv.second);
+    }
+    // a copy of remote_child whose edge starts `skip` chars in (the "trimmed" / "remainder" nodes of cases 2 and 3)
+    static Node* clone_trimmed(const Node* remote_child, size_t skip, Node* parent) {
+        Node* c = new Node();
+        c->text = remote_child->text.substr(skip);
+        c->tenants = remote_child->tenants; c->parent = parent; c->has_last = remote_child->has_last; c->last_tenant = remote_child->last_tenant;
+        for (auto& kv : remote_child->children) c->children[kv.first] = clone_subtree(kv.second, c);
+        return c;
+    }
+    void merge_nodes(Node* local, const Node* remote) {  // :1338-1545
+        merge_tenants(local, remote, local->text.size());
+        for (auto& re : remote->children) {
+            const char32_t rc = re.first;
+            const Node* rchild = re.second;
+            auto lit = local->children.find(rc);
+            if (lit == local->children.end()) {   // no local child at this char: copy the whole remote subtree (:1538-1543)
+                Node* cl = clone_subtree(rchild, local);
+                accumulate_tenant_counts(cl);
+                local->children[rc] = cl;
+                continue;
+            }
+            Node* lchild = lit->second;
+            const size_t ln = lchild->text.size(), rn = rchild->text.size();
+            size_t shared = 0;
+            while (shared < ln && shared < rn && lchild->text[shared] == rchild->text[shared]) ++shared;
+            if (shared == ln && shared == rn) {   // case 1: exact match
+                merge_nodes(lchild, rchild);
+            } else if (shared == ln) {            // case 2: local edge is a prefix of the remote edge (:1385-1448)
+                merge_tenants(lchild, rchild, ln);
+                Node* trimmed = clone_trimmed(rchild, shared, nullptr);
+                const char32_t rem_first = trimmed->text[0];
+                auto dit = lchild->children.find(rem_first);
+                if (dit != lchild->children.end()) {
+                    merge_nodes(dit->second, trimmed);   // as in the reference: the deeper local edge is NOT compared with the remainder
+                    free_subtree(trimmed);
+                } else {
+                    trimmed->parent = lchild;
+                    accumulate_tenant_counts(trimmed);
+                    lchild->children[rem_first] = trimmed;
+                }
+            } else {                              // case 3: split the local child at the shared prefix (:1449-1537)
+                Node* split = new Node();
+                split->text = lchild->text.substr(0, shared);
+                split->tenants = lchild->tenants;
+                split->parent = local;
+                split->has_last = lchild->has_last; split->last_tenant = lchild->last_tenant;
+                merge_tenants(split, rchild, shared);
+                lchild->text = lchild->text.substr(shared);
+                lchild->parent = split;
+                split->children[lchild->text[0]] = lchild;
+                if (shared < rn) {   // remote remainder as a sibling; when the remote edge IS the shared prefix its children are dropped (:1517)
+                    Node* rem = clone_trimmed(rchild, shared, split);
+                    accumulate_tenant_counts(rem);
+                    split->children[rem->text[0]] = rem;
+                }
+                lit->second = split;
+            }
+        }
+    }
+
+public:
 
 private:
     static uint64_t next_epoch() { return tree_globals().string_epoch++; }
