@@ -225,6 +225,16 @@ smgx_status smgx_stree_entries(smgx_policy* p, const char* model_key, char** out
 smgx_status smgx_stree_walk_many_device(smgx_policy* p, const char* model_key, uint32_t n_batches, const uint8_t* const* d_text,
                                         const uint32_t* const* d_offsets, const uint32_t* n, int32_t* const* d_out_worker_idx,
                                         smgx_decision_info* const* d_out_info, uint32_t* const* d_out_node, char** err);
+/* Mesh wire format: kv_index::snapshot::TreeSnapshot (crates/kv_index/src/snapshot.rs:18-52) in bincode 1.3 default
+ * encoding — u64-LE node count, then per node in pre-order { u64 len + UTF-8 edge, u64 n + n × { u64 len + tenant, u64 epoch }, u32
+ * child_count }, children in char order (tenants in name order, where DashMap order is arbitrary).
+ *   smgx_stree_snapshot        Tree::snapshot().to_bytes()       (string_tree.rs:1066-1102; *out_bytes is freed with smgx_free_string)
+ *   smgx_stree_load_snapshot   Tree::from_snapshot(from_bytes())  (:1228-1309): REPLACES the model's string tree
+ *   smgx_stree_merge_snapshot  Tree::merge_snapshot               (:1318-1545): remote wins on a newer epoch; three edge cases
+ * Malformed bytes → SMGX_INVALID_ARGUMENT, the tree is left untouched.  No epoch is drawn by any of the three. */
+smgx_status smgx_stree_snapshot(smgx_policy* p, const char* model_key, char** out_bytes, uint64_t* out_len, char** err);
+smgx_status smgx_stree_load_snapshot(smgx_policy* p, const char* model_key, const uint8_t* bytes, uint64_t n_bytes, char** err);
+smgx_status smgx_stree_merge_snapshot(smgx_policy* p, const char* model_key, const uint8_t* bytes, uint64_t n_bytes, char** err);
 smgx_status smgx_stree_clear(smgx_policy* p, const char* model_key, char** err);
 smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_t* out, char** err);
 

@@ -120,6 +120,9 @@ def load():
     sig("smgx_stree_prefix_match_tenant", st, vp, cp, vp, u32, cp, P(u32), pp)
     sig("smgx_stree_sizes", st, vp, cp, C.c_int, P(C.c_void_p), pp)
     sig("smgx_stree_entries", st, vp, cp, P(C.c_void_p), P(u64), pp)
+    sig("smgx_stree_snapshot", st, vp, cp, P(C.c_void_p), P(u64), pp)
+    sig("smgx_stree_load_snapshot", st, vp, cp, vp, u64, pp)
+    sig("smgx_stree_merge_snapshot", st, vp, cp, vp, u64, pp)
     sig("smgx_stree_walk_many_device", st, vp, cp, u32, vp, vp, vp, vp, vp, vp, pp)
     sig("smgx_stree_clear", st, vp, cp, pp)
     sig("smgx_stree_node_count", st, vp, cp, P(u64), pp)

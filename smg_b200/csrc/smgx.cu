@@ -1553,6 +1553,37 @@ smgx_status smgx_stree_entries(smgx_policy* p, const char* model_key, char** out
         return SMGX_SUCCESS;
     });
 }
+smgx_status smgx_stree_snapshot(smgx_policy* p, const char* model_key, char** out_bytes, uint64_t* out_len, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_bytes); NONNULL(out_len);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        std::string b;
+        p->impl.stree_of(m).snapshot_bytes(b);
+        *out_bytes = dup_cstr(b);
+        *out_len = b.size();
+        return SMGX_SUCCESS;
+    });
+}
+static smgx_status stree_apply_snapshot(smgx_policy* p, const char* model_key, const uint8_t* bytes, uint64_t n, bool merge, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || bytes, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        ModelState& m = p->impl.model(model_key, true);
+        StringTreeIndex& t = p->impl.stree_of(m);
+        const bool ok = merge ? t.merge_snapshot(bytes, n) : t.load_snapshot(bytes, n);
+        if (!ok) throw Error(SMGX_INVALID_ARGUMENT, "malformed TreeSnapshot (bincode)");
+        m.fleet_dirty_tenant = true;   // new tenants may have been interned
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_stree_load_snapshot(smgx_policy* p, const char* model_key, const uint8_t* bytes, uint64_t n_bytes, char** err) {
+    return stree_apply_snapshot(p, model_key, bytes, n_bytes, false, err);
+}
+smgx_status smgx_stree_merge_snapshot(smgx_policy* p, const char* model_key, const uint8_t* bytes, uint64_t n_bytes, char** err) {
+    return stree_apply_snapshot(p, model_key, bytes, n_bytes, true, err);
+}
 smgx_status smgx_stree_clear(smgx_policy* p, const char* model_key, char** err) {
     return guard(err, [&]() {
         NONNULL(p);

@@ -1,6 +1,8 @@
 // K2c — char-level string tree: host tree + device mirror + the match/decide kernel.  See string_tree.h.
 #include "string_tree.h"
 
+#include <memory>
+
 #include <algorithm>
 #include <cstring>
 #include <queue>
@@ -370,6 +372,237 @@ void StringTreeIndex::entries(std::vector<std::pair<std::string, std::vector<std
         }
         for (size_t k = nd.kids.size(); k-- > 0;) stack.push_back({nd.kids[k].second, path.size()});
     }
+}
+
+// =================================================================================================================
+// mesh wire format: TreeSnapshot (crates/kv_index/src/snapshot.rs:18-52) and its producers / consumers
+// (string_tree.rs:1066-1102 snapshot, :1228-1309 from_snapshot, :1318-1545 merge_snapshot).  bincode 1.3 default options:
+// u64-LE lengths for Vec / String, fixed-width little-endian integers.
+// =================================================================================================================
+struct StringTreeIndex::SnapNode {
+    std::string edge;                                        // UTF-8
+    std::vector<std::pair<uint32_t, uint64_t>> tenants;      // (interned tenant, epoch), wire order
+    std::vector<uint32_t> dup_tenants;                       // occurrences of a tenant beyond its first in the wire list (restore_node counts each)
+    uint32_t child_count = 0;
+    std::vector<std::pair<uint32_t, std::unique_ptr<SnapNode>>> kids;   // reconstructed remote tree: (first char, child), ascending
+};
+
+namespace {
+void put64(std::string& b, uint64_t v) { for (int i = 0; i < 8; ++i) b.push_back((char)((v >> (8 * i)) & 0xFF)); }
+bool get64(const uint8_t* b, size_t n, size_t& at, uint64_t& v) {
+    if (n - at < 8) return false;
+    v = 0;
+    for (int i = 0; i < 8; ++i) v |= (uint64_t)b[at + i] << (8 * i);
+    at += 8;
+    return true;
+}
+}  // namespace
+
+void StringTreeIndex::snapshot_bytes(std::string& out) const {
+    out.clear();
+    put64(out, 0);   // node count, patched below
+    uint64_t count = 0;
+    std::vector<uint32_t> stack{0};
+    while (!stack.empty()) {   // pre-order, children ascending by char (children.sort_by_key, :1091)
+        const uint32_t id = stack.back(); stack.pop_back();
+        const Node& nd = nodes_[id];
+        ++count;
+        put64(out, nd.label_bytes);
+        out.append((const char*)label(nd), nd.label_bytes);
+        std::vector<std::pair<uint32_t, uint64_t>> ts(nd.tenants.begin(), nd.tenants.end());   // DashMap order is arbitrary: by name, like the oracle
+        std::sort(ts.begin(), ts.end(), [&](auto& a, auto& b) { return tenants_->rank[a.first] < tenants_->rank[b.first]; });
+        put64(out, ts.size());
+        for (auto& t : ts) { const std::string& name = tenants_->names[t.first]; put64(out, name.size()); out += name; put64(out, t.second); }
+        const uint32_t cc = (uint32_t)nd.kids.size();
+        for (int i = 0; i < 4; ++i) out.push_back((char)((cc >> (8 * i)) & 0xFF));
+        for (size_t k = nd.kids.size(); k-- > 0;) stack.push_back(nd.kids[k].second);
+    }
+    for (int i = 0; i < 8; ++i) out[i] = (char)((count >> (8 * i)) & 0xFF);
+}
+
+// remote wins on a newer epoch; a tenant new to the node adds `chars` to its size (:1343-1369, :1392-1414, :1479-1500)
+void StringTreeIndex::merge_tenant_list(uint32_t node, const std::vector<std::pair<uint32_t, uint64_t>>& remote, uint32_t chars) {
+    bool changed = false;
+    for (auto& kv : remote) {
+        Node& nd = nodes_[node];
+        const int64_t i = find_tenant(nd, kv.first);
+        if (i < 0) { nd.tenants.emplace_back(kv.first, kv.second); tenant_chars_[kv.first] += chars; changed = true; }
+        else if (kv.second > nd.tenants[(size_t)i].second) { nd.tenants[(size_t)i].second = kv.second; changed = true; }
+    }
+    if (changed) mark_node(node);
+}
+
+// clone_subtree / the trimmed remote node (:1422-1435, :1506-1520, :1563-1578) + accumulate_tenant_counts (:1548-1561): the remote
+// node, its edge starting skip_bytes in, and everything below it become local nodes under `parent`
+uint32_t StringTreeIndex::graft(uint32_t parent, const SnapNode& rn, size_t skip_bytes, bool count_dups) {
+    const uint8_t* e = (const uint8_t*)rn.edge.data() + skip_bytes;
+    const size_t nb = rn.edge.size() - skip_bytes;
+    uint32_t cl;
+    const uint32_t cp = utf8_first(e, &cl);
+    const uint32_t chars = count_chars(e, nb);
+    const uint64_t boff = bytes_.size();
+    bytes_.insert(bytes_.end(), e, e + nb);
+    const uint32_t id = new_node(boff, (uint32_t)nb, chars, parent, cp);
+    for (auto& t : rn.tenants) { set_tenant(nodes_[id], t.first, t.second); tenant_chars_[t.first] += chars; }
+    if (count_dups) for (uint32_t t : rn.dup_tenants) tenant_chars_[t] += chars;
+    nodes_[id].last_tenant = -1;   // nodes restored from a snapshot carry no cached tenant (:1298-1304)
+    const int64_t old = find_child(parent, cp);
+    if (old >= 0) drop_subtree(table_[(size_t)old].child);   // DashMap::insert replaces
+    table_insert(parent, cp, id);
+    kids_insert(nodes_[parent], cp, id);
+    for (auto& k : rn.kids) graft(id, *k.second, 0, count_dups);
+    return id;
+}
+
+void StringTreeIndex::drop_subtree(uint32_t id) {
+    const std::vector<std::pair<uint32_t, uint32_t>> kids = nodes_[id].kids;
+    for (auto& k : kids) drop_subtree(k.second);
+    table_erase(nodes_[id].parent, nodes_[id].first_cp);
+    kids_erase(nodes_[nodes_[id].parent], nodes_[id].first_cp);
+    free_node(id);
+}
+
+// merge_nodes(local, remote) (:1338-1545): only the remote node's tenants and children are read, never its edge
+void StringTreeIndex::merge_nodes(uint32_t local, const SnapNode& remote) {
+    merge_tenant_list(local, remote.tenants, nodes_[local].label_chars);
+    for (auto& re : remote.kids) {
+        const uint32_t rc = re.first;
+        const SnapNode& rchild = *re.second;
+        const int64_t slot = find_child(local, rc);
+        if (slot < 0) { graft(local, rchild, 0); continue; }   // no local child at this char: the whole remote subtree (:1538-1543)
+        const uint32_t m = table_[(size_t)slot].child;
+        const size_t lb = nodes_[m].label_bytes, rb = rchild.edge.size();
+        const size_t shared = shared_prefix_bytes((const uint8_t*)rchild.edge.data(), rb, label(nodes_[m]), lb);
+        if (shared == lb && shared == rb) {            // case 1
+            merge_nodes(m, rchild);
+        } else if (shared == lb) {                     // case 2: the local edge is a prefix of the remote edge (:1385-1448)
+            merge_tenant_list(m, rchild.tenants, nodes_[m].label_chars);
+            uint32_t cl;
+            const uint32_t rem_first = utf8_first((const uint8_t*)rchild.edge.data() + shared, &cl);
+            const int64_t deeper = find_child(m, rem_first);
+            if (deeper >= 0) merge_nodes(table_[(size_t)deeper].child, rchild);   // as in the reference: no edge comparison at this level
+            else graft(m, rchild, shared);
+        } else {                                       // case 3: split the local child at the shared prefix (:1449-1537)
+            const uint32_t shared_chars = count_chars(label(nodes_[m]), shared);
+            const uint64_t moff = nodes_[m].label_off;
+            const uint32_t nn = new_node(moff, (uint32_t)shared, shared_chars, local, rc);
+            nodes_[nn].tenants = nodes_[m].tenants;
+            nodes_[nn].last_tenant = nodes_[m].last_tenant;
+            nodes_[nn].split_epoch = nodes_[m].split_epoch = chunk_epoch_;
+            Node& mm = nodes_[m];
+            mm.label_off = moff + shared; mm.label_bytes -= (uint32_t)shared; mm.label_chars -= shared_chars; mm.parent = nn;
+            uint32_t l2;
+            mm.first_cp = utf8_first(label(mm), &l2);
+            mark_node(m);
+            kids_insert(nodes_[nn], mm.first_cp, m);
+            table_set(local, rc, nn);
+            kids_insert(nodes_[local], rc, nn);
+            table_insert(nn, mm.first_cp, m);
+            merge_tenant_list(nn, rchild.tenants, shared_chars);
+            if (shared < rb) graft(nn, rchild, shared);   // a remote edge that IS the shared prefix loses its children (:1517)
+        }
+    }
+}
+
+
+// TreeSnapshot::from_bytes (snapshot.rs:49-51): false = bincode error (short input, trailing bytes, invalid UTF-8)
+bool StringTreeIndex::decode_snapshot(const uint8_t* b, size_t n, std::vector<std::unique_ptr<SnapNode>>& flat) {
+    size_t at = 0;
+    uint64_t count;
+    if (!get64(b, n, at, count)) return false;
+    for (uint64_t i = 0; i < count; ++i) {
+        auto nd = std::make_unique<SnapNode>();
+        uint64_t len, nt;
+        if (!get64(b, n, at, len) || n - at < len) return false;
+        if (!valid_utf8(b + at, len)) return false;   // String deserialisation validates UTF-8
+        nd->edge.assign((const char*)b + at, len); at += len;
+        if (!get64(b, n, at, nt)) return false;
+        for (uint64_t k = 0; k < nt; ++k) {
+            uint64_t tl, ep;
+            if (!get64(b, n, at, tl) || n - at < tl) return false;
+            if (!valid_utf8(b + at, tl)) return false;
+            const uint32_t t = tenants_->intern(std::string((const char*)b + at, tl)); at += tl;
+            if (!get64(b, n, at, ep)) return false;
+            bool seen = false;
+            for (auto& kv : nd->tenants) if (kv.first == t) { kv.second = ep; seen = true; }   // DashMap::insert: the later entry wins
+            if (seen) nd->dup_tenants.push_back(t); else nd->tenants.emplace_back(t, ep);
+        }
+        if (n - at < 4) return false;
+        for (int k = 0; k < 4; ++k) nd->child_count |= (uint32_t)b[at + k] << (8 * k);
+        at += 4;
+        flat.push_back(std::move(nd));
+    }
+    return at == n;
+}
+
+// restore_node's shape (:1245-1309): pre-order list → tree; children with an empty edge are skipped with their subtrees, a later child
+// with the same first char replaces an earlier one.  `lost` collects (tenant, chars) of everything restore_node would have counted in
+// subtrees that end up replaced (from_snapshot keeps those counts).
+std::unique_ptr<StringTreeIndex::SnapNode> StringTreeIndex::build_remote(std::vector<std::unique_ptr<SnapNode>>& flat, size_t& idx,
+                                                                          std::vector<std::pair<uint32_t, uint32_t>>* lost) {
+    std::unique_ptr<SnapNode> nd = std::move(flat[idx++]);
+    for (uint32_t c = 0; c < nd->child_count; ++c) {
+        if (idx >= flat.size()) break;
+        if (flat[idx]->edge.empty()) {
+            std::vector<size_t> todo{1};   // skip the node and all its descendants (:1284-1296)
+            while (!todo.empty() && idx < flat.size()) {
+                if (todo.back() == 0) { todo.pop_back(); continue; }
+                --todo.back();
+                todo.push_back(flat[idx++]->child_count);
+            }
+            continue;
+        }
+        std::unique_ptr<SnapNode> child = build_remote(flat, idx, lost);
+        uint32_t cl;
+        const uint32_t cp = utf8_first((const uint8_t*)child->edge.data(), &cl);
+        auto it = std::lower_bound(nd->kids.begin(), nd->kids.end(), cp, [](auto& a, uint32_t v) { return a.first < v; });
+        if (it != nd->kids.end() && it->first == cp) {
+            if (lost) {
+                std::vector<const SnapNode*> st{it->second.get()};
+                while (!st.empty()) {
+                    const SnapNode* x = st.back(); st.pop_back();
+                    const uint32_t chars = count_chars((const uint8_t*)x->edge.data(), x->edge.size());
+                    for (auto& t : x->tenants) lost->push_back({t.first, chars});
+                    for (uint32_t t : x->dup_tenants) lost->push_back({t, chars});
+                    for (auto& k : x->kids) st.push_back(k.second.get());
+                }
+            }
+            it->second = std::move(child);
+        } else nd->kids.insert(it, std::make_pair(cp, std::move(child)));
+    }
+    return nd;
+}
+
+bool StringTreeIndex::load_snapshot(const uint8_t* bytes, size_t n) {
+    std::vector<std::unique_ptr<SnapNode>> flat;
+    if (!decode_snapshot(bytes, n, flat)) return false;
+    clear();
+    if (flat.empty()) return true;
+    size_t idx = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> lost;
+    std::unique_ptr<SnapNode> root = build_remote(flat, idx, &lost);
+    // the root: edge text (normally empty), tenants and their counts (:1258-1274)
+    const uint32_t rchars = count_chars((const uint8_t*)root->edge.data(), root->edge.size());
+    nodes_[0].label_off = bytes_.size();
+    nodes_[0].label_bytes = (uint32_t)root->edge.size();
+    nodes_[0].label_chars = rchars;
+    bytes_.insert(bytes_.end(), root->edge.begin(), root->edge.end());
+    for (auto& t : root->tenants) { set_tenant(nodes_[0], t.first, t.second); tenant_chars_[t.first] += rchars; }
+    for (uint32_t t : root->dup_tenants) tenant_chars_[t] += rchars;
+    for (auto& k : root->kids) graft(0, *k.second, 0, true);
+    for (auto& l : lost) tenant_chars_[l.first] += l.second;
+    mark_node(0);
+    return true;
+}
+
+bool StringTreeIndex::merge_snapshot(const uint8_t* bytes, size_t n) {
+    std::vector<std::unique_ptr<SnapNode>> flat;
+    if (!decode_snapshot(bytes, n, flat)) return false;
+    if (flat.empty()) return true;   // :1319-1321
+    size_t idx = 0;
+    std::unique_ptr<SnapNode> root = build_remote(flat, idx, nullptr);
+    merge_nodes(0, *root);
+    return true;
 }
 
 // =================================================================================================================

@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -70,6 +71,10 @@ public:
     size_t node_count() const { return live_nodes_; }
     void clear();
     void entries(std::vector<std::pair<std::string, std::vector<std::pair<uint32_t, uint64_t>>>>& out) const;   // :1116-1221
+    // mesh wire format (crates/kv_index/src/snapshot.rs; string_tree.rs:1052-1578), host side like every other writer
+    void snapshot_bytes(std::string& out) const;                     // Tree::snapshot().to_bytes(): bincode 1.3, pre-order, children in char order
+    bool load_snapshot(const uint8_t* bytes, size_t n);              // TreeSnapshot::from_bytes + Tree::from_snapshot into this (emptied) tree; false = malformed
+    bool merge_snapshot(const uint8_t* bytes, size_t n);             // Tree::merge_snapshot (:1318-1545)
     bool root_has_child(uint32_t cp) const { return find_child(0, cp) >= 0; }
     // optimistic batching (smgx.cu text_select)
     void begin_chunk() { ++chunk_epoch_; }
@@ -122,6 +127,13 @@ private:
         if (slot_stamp_[i] != flush_gen_) { slot_stamp_[i] = flush_gen_; dirty_slots_.push_back(i); }
     }
     const uint8_t* label(const Node& nd) const { return bytes_.data() + nd.label_off; }
+    struct SnapNode;   // decoded SnapshotNode / reconstructed remote tree node (string_tree.cu)
+    bool decode_snapshot(const uint8_t* b, size_t n, std::vector<std::unique_ptr<SnapNode>>& flat);
+    static std::unique_ptr<SnapNode> build_remote(std::vector<std::unique_ptr<SnapNode>>& flat, size_t& idx, std::vector<std::pair<uint32_t, uint32_t>>* lost);
+    uint32_t graft(uint32_t parent, const SnapNode& rn, size_t skip_bytes, bool count_dups = false);
+    void drop_subtree(uint32_t id);
+    void merge_tenant_list(uint32_t node, const std::vector<std::pair<uint32_t, uint64_t>>& remote, uint32_t chars);
+    void merge_nodes(uint32_t local, const SnapNode& remote);
     StrSlot device_slot(uint32_t i) const;
 
     TenantTable* tenants_;

@@ -376,6 +376,23 @@ class Tree:
     def clear(self):
         self.h.call("smgx_stree_clear", self.model)
 
+    # -- mesh wire format: kv_index::snapshot::TreeSnapshot, bincode (snapshot.rs; string_tree.rs:1052-1578) --
+    def snapshot_bytes(self) -> bytes:  # Tree::snapshot().to_bytes()
+        out, ln = C.c_void_p(), C.c_uint64()
+        self.h.call("smgx_stree_snapshot", self.model, C.byref(out), C.byref(ln))
+        raw = C.string_at(out, ln.value)
+        self.h.L.smgx_free_string(out)
+        return raw
+
+    @classmethod
+    def from_snapshot_bytes(cls, data: bytes, device_id: int = 0):  # TreeSnapshot::from_bytes + Tree::from_snapshot (:1228)
+        t = cls.standalone(device_id)
+        t.h.call("smgx_stree_load_snapshot", t.model, data, len(data))
+        return t
+
+    def merge_snapshot_bytes(self, data: bytes):  # Tree::merge_snapshot (:1318)
+        self.h.call("smgx_stree_merge_snapshot", self.model, data, len(data))
+
     def entries(self):
         out, ln = C.c_void_p(), C.c_uint64()
         self.h.call("smgx_stree_entries", self.model, C.byref(out), C.byref(ln))
