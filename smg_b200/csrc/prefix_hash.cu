@@ -15,9 +15,10 @@
 namespace smgx {
 namespace {
 
-constexpr int kReqPerCta = 32;
-constexpr int kThreads = 128;
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreads = 128;       // pick kernel: one thread per request
+constexpr int kHashThreads = 64;    // hash kernel: 2 warps × 4 requests, one round — short CTAs keep the last wave of a launch small
+constexpr int kWarps = kHashThreads / 32;
+constexpr int kReqPerCta = kWarps * 4;
 
 // inputs of ≤ 240 bytes take XXH3's short forms: a handful of dependent multiplies, done by every lane on the same words
 __device__ __noinline__ uint64_t xxh3_small(const uint32_t* __restrict__ w, uint32_t n) { return xxh3_words_upto60(w, n, 0); }
@@ -120,7 +121,7 @@ __device__ __forceinline__ bool load_ok(uint64_t load, const PrefixDerived& d) {
 }
 
 // K-prefix-1: compute_prefix_hash of every request → bt.hash[r].  8 lanes per request, 4 requests per warp, 2 rounds per warp.
-__global__ void __launch_bounds__(kThreads) prefix_hash_kernel(const __grid_constant__ PrefixArgs a) {
+__global__ void __launch_bounds__(kHashThreads) prefix_hash_kernel(const __grid_constant__ PrefixArgs a) {
     const PrefixBatch& bt = a.b[blockIdx.y];
     const uint32_t first = blockIdx.x * kReqPerCta;
     if (first >= bt.n) return;
@@ -295,7 +296,7 @@ uint32_t launch_prefix_select(const RingView& ring, const PrefixFleetView& fleet
     uint32_t max_n = 0;
     for (uint32_t k = 0; k < a.count; ++k) max_n = max_n > a.b[k].n ? max_n : a.b[k].n;
     if (max_n == 0 || a.count == 0) return 0;
-    prefix_hash_kernel<<<dim3((max_n + kReqPerCta - 1) / kReqPerCta, a.count), kThreads, 0, stream>>>(a);
+    prefix_hash_kernel<<<dim3((max_n + kReqPerCta - 1) / kReqPerCta, a.count), kHashThreads, 0, stream>>>(a);
     bool pick = false;
     for (uint32_t k = 0; k < a.count; ++k) pick = pick || a.b[k].out_idx != nullptr;
     if (pick) {
