@@ -1,0 +1,108 @@
+// Per-request front end (include/smgx_batcher.hpp) on a B200: T caller threads route R requests each through smgx::Batcher against the
+// event-driven index; every pick must equal the oracle's pick for that request (event-mode picks do not depend on arrival order), and
+// the run reports throughput and per-request latency.  Test infrastructure: the oracle is the checker.
+//   test_batcher [threads] [requests_per_thread] [window] [max_wait_us]
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "../../include/smgx.hpp"
+#include "../../include/smgx_batcher.hpp"
+#include "../../oracle/cache_aware.h"
+
+int main(int argc, char** argv) {
+    const int T = argc > 1 ? std::atoi(argv[1]) : 16, R = argc > 2 ? std::atoi(argv[2]) : 2000, WIN = argc > 3 ? std::atoi(argv[3]) : 32;
+    const int wait_us = argc > 4 ? std::atoi(argv[4]) : 100;
+    const uint32_t W = 64, BS = 16, TOK = 512, SEQS = 20000;
+    std::mt19937_64 rng(7);
+    smgx::CacheAwareConfig cfg; cfg.eviction_interval_secs = 0; cfg.cache_threshold = 0.3f; cfg.balance_abs_threshold = 64; cfg.balance_rel_threshold = 1.5f; cfg.block_size = BS;
+    smgx::CacheAwarePolicy policy(cfg, 0, 4096, TOK);
+    orc::CacheAwareConfig oc; oc.cache_threshold = 0.3f; oc.balance_abs_threshold = 64; oc.balance_rel_threshold = 1.5f; oc.eviction_interval_secs = 0; oc.block_size = BS;
+    orc::CacheAwarePolicy opol(oc);
+    smgx::Workers ws;
+    std::vector<orc::Worker> ows(W);
+    for (uint32_t i = 0; i < W; ++i) {
+        auto w = std::make_shared<smgx::BasicWorker>("http://w" + std::to_string(i) + ":8000", "m");
+        w->set_load(rng() % 16);
+        ows[i].url = w->url(); ows[i].model_id = "m"; ows[i].load = w->load();
+        ws.push_back(w);
+    }
+    policy.init_workers(ws);
+    opol.init_workers(ows);
+    auto monitor = policy.kv_event_monitor();
+    auto ix = monitor->create_indexer("m", 64);
+    monitor->set_block_size("m", BS);
+    orc::PositionalIndexer oix(64);
+    std::vector<orc::WorkerBlockMap> owb(W);
+    opol.set_monitor(true); opol.attach_indexer("m", &oix); opol.set_block_size("m", BS);
+    std::vector<std::vector<uint32_t>> seqs(SEQS, std::vector<uint32_t>(TOK));
+    uint64_t next_seq = 1;
+    for (uint32_t s = 0; s < SEQS; ++s) {
+        for (auto& t : seqs[s]) t = (uint32_t)(rng() % 50000);
+        const uint32_t w = s % W;
+        const uint32_t wid = ix->intern_worker(ws[w]->url());
+        oix.intern_worker(ws[w]->url());
+        std::vector<uint64_t> seq(TOK / BS), con(TOK / BS);
+        for (uint32_t b = 0; b < TOK / BS; ++b) { seq[b] = next_seq++; con[b] = orc::compute_content_hash(seqs[s].data() + b * BS, BS); }
+        std::vector<smgx::StoredBlock> blocks(TOK / BS);
+        for (uint32_t b = 0; b < TOK / BS; ++b) blocks[b] = {seq[b], con[b]};
+        ix->apply_stored(wid, blocks);
+        oix.apply_stored(wid, seq.data(), con.data(), seq.size(), false, 0, owb[wid]);
+    }
+    policy.set_kv_event_monitor(monitor);
+    // the fleet snapshot the batches read (the Worker scalars are pushed once; the gateway refreshes them as loads change)
+    policy.select_worker_batch(ws, {seqs[0]});
+
+    // requests: 80 % a cached sequence, 10 % a cached prefix + novel tail, 10 % novel
+    const size_t N = (size_t)T * R;
+    std::vector<std::vector<uint32_t>> reqs(N);
+    for (auto& q : reqs) {
+        const uint64_t u = rng() % 10;
+        q = seqs[rng() % SEQS];
+        if (u == 8) { const uint32_t keep = BS * (1 + rng() % 31); for (uint32_t i = keep; i < TOK; ++i) q[i] = (uint32_t)(rng() % 50000); }
+        else if (u == 9) for (auto& t : q) t = (uint32_t)(rng() % 50000);
+    }
+    std::vector<int32_t> got(N, -2);
+    std::vector<float> lat_us(N, 0.f);
+    smgx::Batcher::Options bo;
+    bo.max_batch = 4096; bo.tokens_per_batch = 4096 * TOK; bo.max_wait = std::chrono::microseconds(wait_us);
+    double secs;
+    smgx::Batcher::Stats st;
+    {
+        smgx::Batcher batcher(policy.handle()->p, "m", bo);
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t] {
+                std::vector<smgx::Batcher::Ticket> tk(WIN);
+                std::vector<std::chrono::steady_clock::time_point> at(WIN);
+                for (int r0 = 0; r0 < R; r0 += WIN) {   // a router task pool: WIN requests outstanding per thread
+                    const int cnt = std::min(WIN, R - r0);
+                    for (int k = 0; k < cnt; ++k) { const size_t id = (size_t)t * R + r0 + k; at[k] = std::chrono::steady_clock::now(); tk[k] = batcher.enqueue(reqs[id].data(), (uint32_t)reqs[id].size()); }
+                    for (int k = 0; k < cnt; ++k) {
+                        const size_t id = (size_t)t * R + r0 + k;
+                        got[id] = batcher.get(tk[k]);
+                        lat_us[id] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - at[k]).count();
+                    }
+                }
+            });
+        for (auto& x : th) x.join();
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        st = batcher.stats();
+    }
+    size_t bad = 0;
+    for (size_t i = 0; i < N; ++i) {
+        const orc::Decision d = opol.select_worker(ows, nullptr, reqs[i].data(), reqs[i].size(), true);
+        if (got[i] != (int32_t)d.idx) { if (++bad <= 5) std::fprintf(stderr, "MISMATCH request %zu: got %d, oracle %lld\n", i, got[i], (long long)d.idx); }
+    }
+    std::sort(lat_us.begin(), lat_us.end());
+    std::printf("{\"mode\": \"per-request front end (smgx::Batcher over smgx_submit_tokens/smgx_wait), event-driven cache_aware, 64 workers, 512-token requests\", "
+                "\"threads\": %d, \"outstanding_per_thread\": %d, \"requests\": %zu, \"max_wait_us\": %d, \"decisions_per_s\": %.1f, \"batches\": %llu, "
+                "\"mean_batch\": %.1f, \"p50_latency_us\": %.1f, \"p99_latency_us\": %.1f, \"mismatches_vs_oracle\": %zu}\n",
+                T, WIN, N, wait_us, N / secs, (unsigned long long)st.batches, st.batches ? (double)st.requests / st.batches : 0.0, lat_us[N / 2], lat_us[(size_t)(N * 0.99)], bad);
+    return bad ? 1 : 0;
+}
