@@ -209,6 +209,7 @@ public:
 };
 
 struct Decision { int32_t idx; smgx_decision_info info; };
+class StringTree;
 
 class CacheAwarePolicy : public LoadBalancingPolicy {   // policies/cache_aware.rs:74-352, 648-710
 public:
@@ -278,6 +279,7 @@ public:
         return zip(idx, info);
     }
     std::shared_ptr<detail::Handle> handle() const { return h_; }
+    std::shared_ptr<StringTree> string_tree(const std::string& model = UNKNOWN_MODEL_ID);   // string_trees[model] (cache_aware.rs:78)
 
 private:
     static std::vector<Decision> zip(const std::vector<int32_t>& idx, const std::vector<smgx_decision_info>& info) {
@@ -312,6 +314,33 @@ private:
     std::shared_ptr<KvEventMonitor> monitor_;
     std::map<std::string, std::vector<std::string>> slices_;
 };
+
+// kv_index::Tree (char-level string tree, HTTP text routing) of one model: writers on the host-authoritative tree inside the library,
+// including the mesh wire format (crates/kv_index/src/snapshot.rs; string_tree.rs:1052-1578)
+class StringTree {
+public:
+    StringTree(std::shared_ptr<detail::Handle> h, std::string model = UNKNOWN_MODEL_ID) : h_(std::move(h)), model_(std::move(model)) {}
+    void insert_text(const std::string& text, const std::string& tenant) {                  // :393-557
+        call(smgx_stree_insert_text, (const uint8_t*)text.data(), (uint32_t)text.size(), tenant.c_str());
+    }
+    size_t node_count() { uint64_t n = 0; call(smgx_stree_node_count, &n); return (size_t)n; }
+    void clear() { call(smgx_stree_clear); }
+    std::string snapshot_bytes() {                                                            // Tree::snapshot().to_bytes()
+        char* out = nullptr; uint64_t len = 0;
+        call(smgx_stree_snapshot, &out, &len);
+        std::string b(out, (size_t)len);
+        smgx_free_string(out);
+        return b;
+    }
+    void load_snapshot(const std::string& bytes) { call(smgx_stree_load_snapshot, (const uint8_t*)bytes.data(), (uint64_t)bytes.size()); }    // Tree::from_snapshot
+    void merge_snapshot(const std::string& bytes) { call(smgx_stree_merge_snapshot, (const uint8_t*)bytes.data(), (uint64_t)bytes.size()); }  // Tree::merge_snapshot
+private:
+    template <class F, class... A> void call(F f, A... a) { char* err = nullptr; detail::check(f(h_->p, model_.c_str(), a..., &err), err); }
+    std::shared_ptr<detail::Handle> h_;
+    std::string model_;
+};
+
+inline std::shared_ptr<StringTree> CacheAwarePolicy::string_tree(const std::string& model) { return std::make_shared<StringTree>(h_, normalize_model_key(model)); }
 
 // ---- adjacent policy on the same plumbing: prefix_hash (policies/prefix_hash.rs) over worker::HashRing (worker/hash_ring.rs) ----
 struct PrefixHashConfig {   // prefix_hash.rs:38-58

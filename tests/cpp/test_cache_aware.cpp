@@ -12,6 +12,7 @@
 #include "../../include/smgx.hpp"
 #include "../../oracle/cache_aware.h"
 #include "../../oracle/prefix_hash.h"
+#include "../../oracle/string_tree.h"
 
 static int g_fail = 0, g_checks = 0;
 #define CHECK(cond)                                                                                \
@@ -475,6 +476,36 @@ static void test_indexer_writers_and_apply_errors() {   // event_tree.rs tests: 
     CHECK_EQ(code, SMGX_DEVICE_ERROR);
 }
 
+static void test_string_tree_snapshot_wire_format() {   // snapshot.rs:66-109, string_tree.rs:2804-2935 — host-authoritative tree, no GPU needed
+    orc::tree_globals() = orc::TreeGlobals();
+    CacheAwarePolicy pa(test_config(), -1), pb(test_config(), -1);
+    auto ta = pa.string_tree(), tb = pb.string_tree();
+    orc::StringTree oa, ob;
+    const char* texts[] = {"Hello world", "Hello there", "Goodbye", "héllo wörld", "Hell", "日本語のテキスト", "日本"};
+    int k = 0;
+    for (const char* t : texts) { const std::string w = "worker-" + std::to_string(k++ % 3); ta->insert_text(t, w); oa.insert_text(t, w); }
+    const std::string snap = ta->snapshot_bytes();
+    CHECK(snap == orc::StringTree::snapshot_to_bytes(oa.snapshot()));
+    orc::tree_globals() = orc::TreeGlobals();
+    for (const char* t : {"Hello wonder", "Good", "zulu", "日本酒"}) { tb->insert_text(t, "worker-9"); ob.insert_text(t, "worker-9"); }
+    const std::string remote = tb->snapshot_bytes();
+    CHECK(remote == orc::StringTree::snapshot_to_bytes(ob.snapshot()));
+    ta->merge_snapshot(remote);                                  // Tree::merge_snapshot
+    orc::StringTree::TreeSnapshot rs;
+    CHECK(orc::StringTree::snapshot_from_bytes(remote, rs));
+    oa.merge_snapshot(rs);
+    CHECK(ta->snapshot_bytes() == orc::StringTree::snapshot_to_bytes(oa.snapshot()));
+    CHECK_EQ(ta->node_count(), oa.node_count());
+    CacheAwarePolicy pc(test_config(), -1);
+    auto tc = pc.string_tree();
+    tc->load_snapshot(ta->snapshot_bytes());                     // Tree::from_snapshot
+    CHECK(tc->snapshot_bytes() == ta->snapshot_bytes());
+    int code = 0;
+    try { tc->load_snapshot(remote.substr(0, remote.size() - 3)); } catch (const smgx::Error& e) { code = e.code; }
+    CHECK_EQ(code, SMGX_INVALID_ARGUMENT);
+    CHECK(tc->snapshot_bytes() == ta->snapshot_bytes());         // a malformed snapshot leaves the tree untouched
+}
+
 static void test_select_without_device_fails_loudly() {   // there is no CPU fallback behind the interface
     CacheAwarePolicy policy(test_config(), -1);
     Workers ws = two_workers();
@@ -494,6 +525,7 @@ int main(int argc, char** argv) {
         {"policy_surface", test_policy_surface, false},
         {"indexer_writers_and_apply_errors", test_indexer_writers_and_apply_errors, false},
         {"select_without_device_fails_loudly", test_select_without_device_fails_loudly, false},
+        {"string_tree_snapshot_wire_format", test_string_tree_snapshot_wire_format, false},
         {"cache_aware_with_balanced_load", test_cache_aware_with_balanced_load, true},
         {"cache_aware_with_imbalanced_load", test_cache_aware_with_imbalanced_load, true},
         {"cache_aware_worker_removal", test_cache_aware_worker_removal, true},

@@ -26,13 +26,13 @@ def _run(args, name="test_cache_aware", timeout=300):
 
 def test_cpp_mirror_host_subset():
     out = _run(["--host"])
-    assert "0 failures" in out and "3 tests" in out
+    assert "0 failures" in out and "4 tests" in out
 
 
 @pytest.mark.gpu
 def test_cpp_mirror_full():
     out = _run([])
-    assert "0 failures" in out and "20 tests" in out, out
+    assert "0 failures" in out and "21 tests" in out, out
 
 
 def test_cpp_batcher_builds():
