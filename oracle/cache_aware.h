@@ -155,6 +155,47 @@ public:
     const std::map<uint64_t, std::vector<uint32_t>>& hash_index_tokens(const std::string& model) { return hash_index_tokens_[model]; }
     const std::map<uint64_t, std::string>& hash_index_text(const std::string& model) { return hash_index_text_[model]; }
 
+    // ---- TreeHandle (cache_aware.rs:443-645): what the mesh adapter calls to apply remote tenant inserts and repair pages ----
+    enum TreeKind { TREE_STRING = 0, TREE_TOKEN = 1 };   // :445-448
+    // :496-553: true iff node_hash is in hash_index[model] of that kind AND the tree exists; then the stored prefix is inserted for worker_url
+    bool apply_known_remote_insert(const std::string& model_in, TreeKind kind, uint64_t node_hash, const std::string& worker_url) {
+        const std::string model = normalize_model_key(model_in);
+        if (kind == TREE_STRING) {
+            auto mi = hash_index_text_.find(model);
+            if (mi == hash_index_text_.end() && hash_index_tokens_.find(model) == hash_index_tokens_.end()) return false;   // hash_index.get(model_id)?
+            if (mi == hash_index_text_.end()) return false;
+            auto it = mi->second.find(node_hash);
+            if (it == mi->second.end()) return false;
+            StringTree* t = string_tree(model);
+            if (!t) return false;   // populate-site invariant violated (:512-526)
+            t->insert_text(it->second, worker_url);
+            return true;
+        }
+        auto mi = hash_index_tokens_.find(model);
+        if (mi == hash_index_tokens_.end()) return false;
+        auto it = mi->second.find(node_hash);
+        if (it == mi->second.end()) return false;
+        TokenTree* t = token_tree(model);
+        if (!t) return false;
+        t->insert_tokens(it->second.data(), it->second.size(), worker_url);
+        return true;
+    }
+    // :575-645, one entry of a page whose variant matches the page kind: every listed tenant is inserted (epochs are ignored) and the
+    // path is recorded under its blake3 path hash; the tree is created on first use
+    void apply_repair_entry_text(const std::string& model_in, const std::string& path, const std::vector<std::string>& tenants) {
+        const std::string model = normalize_model_key(model_in);
+        StringTree* t = string_tree(model, true);
+        for (auto& tenant : tenants) t->insert_text(path, tenant);
+        hash_index_text_[model][hash_node_path(path)] = path;
+    }
+    void apply_repair_entry_tokens(const std::string& model_in, const uint32_t* tokens, size_t n, const std::vector<std::string>& tenants) {
+        const std::string model = normalize_model_key(model_in);
+        TokenTree* t = token_tree(model, true);
+        for (auto& tenant : tenants) t->insert_tokens(tokens, n, tenant);
+        hash_index_tokens_[model][hash_token_path(tokens, n)] = std::vector<uint32_t>(tokens, tokens + n);
+    }
+    // open_repair_stream (:555-573) is iter_entries of the model's tree: string_tree(model)->entries() / token_tree(model)->entries()
+
     bool has_event_indexer(const std::string& model) const {  // :723-729
         if (!monitor_) return false;
         auto it = indexers_.find(model);

@@ -348,6 +348,19 @@ double orc_policy_select_steps_mt(void* h, const uint32_t* const* tokens, const 
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// TreeHandle (cache_aware.rs:443-645)
+int orc_policy_apply_known_remote_insert(void* h, const char* model, int kind, uint64_t node_hash, const char* worker_url) {
+    return ((PolicyBox*)h)->pol.apply_known_remote_insert(model, kind ? CacheAwarePolicy::TREE_TOKEN : CacheAwarePolicy::TREE_STRING, node_hash, worker_url) ? 1 : 0;
+}
+// one repair entry; tenants = '\n'-separated URLs
+void orc_policy_apply_repair_entry(void* h, const char* model, int kind, const void* data, size_t n, const char* tenants) {
+    std::vector<std::string> ts;
+    std::string cur;
+    for (const char* c = tenants; ; ++c) { if (*c == '\n' || *c == 0) { if (!cur.empty()) ts.push_back(cur); cur.clear(); if (*c == 0) break; } else cur.push_back(*c); }
+    if (kind) ((PolicyBox*)h)->pol.apply_repair_entry_tokens(model, (const uint32_t*)data, n, ts);
+    else ((PolicyBox*)h)->pol.apply_repair_entry_text(model, std::string((const char*)data, n), ts);
+}
+
 // ---- prefix_hash policy + hash ring (prefix_hash.h) ----
 void* orc_ring_new(const char* const* urls, size_t n) {
     std::vector<std::string> u;

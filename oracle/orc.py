@@ -92,6 +92,8 @@ def lib():
         sig("orc_hash_token_path", C.c_uint64, vp, sz)
         sig("orc_policy_hash_index", sz, vp, cp, C.c_int, vp, sz)
         sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int, C.c_int)
+        sig("orc_policy_apply_known_remote_insert", C.c_int, vp, cp, C.c_int, u64, cp)
+        sig("orc_policy_apply_repair_entry", None, vp, cp, C.c_int, vp, sz, cp)
         sig("orc_ring_new", vp, P(cp), sz)
         sig("orc_ring_free", None, vp)
         sig("orc_ring_len", sz, vp)
@@ -549,6 +551,28 @@ class CacheAwarePolicy:
         idx = np.zeros(n, np.int32)
         secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads, 1 if step_barrier else 0)
         return idx, secs
+
+    # ---- TreeHandle (cache_aware.rs:443-645) ----
+    def apply_known_remote_insert(self, model_id, tree_kind, node_hash, worker_url) -> bool:
+        """tree_kind: "string" | "token".  True iff the hash resolves locally; the stored prefix then gains worker_url as a tenant."""
+        return bool(lib().orc_policy_apply_known_remote_insert(self.h, model_id.encode(), 1 if tree_kind == "token" else 0, int(node_hash), worker_url.encode()))
+
+    def apply_repair_page(self, model_id, tree_kind, entries) -> int:
+        """entries: [("string", path, [(tenant, epoch)]) | ("token", tokens, [(tenant, epoch)])].  Entries whose variant differs from the
+        page kind are skipped (:606-613, :633-640).  Returns the number applied."""
+        applied = 0
+        for kind, path, tenants in entries:
+            if kind != tree_kind:
+                continue
+            names = "\n".join(t for t, _ in tenants).encode()
+            if kind == "token":
+                t = _u32(path)
+                lib().orc_policy_apply_repair_entry(self.h, model_id.encode(), 1, _ptr(t), t.size, names)
+            else:
+                b = path.encode("utf-8")
+                lib().orc_policy_apply_repair_entry(self.h, model_id.encode(), 0, b, len(b), names)
+            applied += 1
+        return applied
 
     def hash_index(self, kind="tokens", model="unknown"):
         """hash_index[model].token_tree / .string_tree (cache_aware.rs:95-101): {path hash: matched prefix}."""
