@@ -409,7 +409,7 @@ void StringTreeIndex::snapshot_bytes(std::string& out) const {
         ++count;
         put64(out, nd.label_bytes);
         out.append((const char*)label(nd), nd.label_bytes);
-        std::vector<std::pair<uint32_t, uint64_t>> ts(nd.tenants.begin(), nd.tenants.end());   // DashMap order is arbitrary: by name, like the oracle
+        std::vector<std::pair<uint32_t, uint64_t>> ts(nd.tenants.begin(), nd.tenants.end());   // DashMap order is arbitrary: by name
         std::sort(ts.begin(), ts.end(), [&](auto& a, auto& b) { return tenants_->rank[a.first] < tenants_->rank[b.first]; });
         put64(out, ts.size());
         for (auto& t : ts) { const std::string& name = tenants_->names[t.first]; put64(out, name.size()); out += name; put64(out, t.second); }
