@@ -110,7 +110,7 @@ __device__ __forceinline__ bool load_ok(uint64_t load, const PrefixDerived& d) {
     return d.all_ok || (double)load <= d.threshold;
 }
 
-// K-prefix-1: compute_prefix_hash of every request → bt.hash[r].  8 lanes per request, 4 requests per warp, 2 rounds per warp.
+// K-prefix-1: compute_prefix_hash of every request → bt.hash[r].  8 lanes per request, 4 requests per warp, kRounds (= 1) rounds per warp.
 __global__ void __launch_bounds__(kHashThreads) prefix_hash_kernel(const __grid_constant__ PrefixArgs a) {
     const PrefixBatch& bt = a.b[blockIdx.y];
     const uint32_t first = blockIdx.x * kReqPerCta;
