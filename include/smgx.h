@@ -116,6 +116,9 @@ void smgx_policy_free(smgx_policy* p);
 const char* smgx_policy_name(void);                                     /* "cache_aware" (cache_aware.rs:704-706) */
 uint32_t smgx_abi_version(void);
 void smgx_free_string(char* s);                                         /* sgl_free_string (memory.rs:10-15) */
+/* Opt-in: bind the calling thread to the CPUs of the NUMA node `device_id` is attached to and prefer that node for the memory it
+ * allocates next (call it before smgx_alloc_pinned / smgx_policy_create on multi-socket boxes).  *out_node = the node, -1 if unknown. */
+smgx_status smgx_bind_numa(int device_id, int* out_node, char** err);
 void* smgx_alloc_pinned(size_t bytes);                                  /* page-locked host memory for hot-path buffers */
 void smgx_free_pinned(void* ptr);
 
@@ -388,6 +391,10 @@ smgx_status smgx_timer_stop_ms(smgx_policy* p, uint32_t lane, float* out_ms, cha
  * into lane 0 before recording the end event — so the interval covers work issued round-robin over the lanes. */
 smgx_status smgx_timer_start_all(smgx_policy* p, char** err);
 smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
+/* Process-wide switch between the two implementations of the event-driven pick (A/B measurements, tests): fused != 0 (default) = the
+ * one-kernel persistent path, 0 = the round-1 hash kernel + search kernel pair.  min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant
+ * of the fused kernel.  Also settable through the environment: SMGX_EVENT_PATH=split|fused, SMGX_FUSED_MINB=3|4. */
+void smgx_set_event_path(int fused, int min_blocks_per_sm);
 /* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
 uint64_t smgx_kernel_launches(const smgx_policy* p);
 /* Writes a buffer larger than L2 (bench hygiene between timed iterations). */

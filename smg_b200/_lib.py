@@ -70,6 +70,7 @@ def load():
     sig("smgx_policy_name", cp)
     sig("smgx_abi_version", u32)
     sig("smgx_free_string", None, vp)
+    sig("smgx_bind_numa", st, C.c_int, P(C.c_int), pp)
     sig("smgx_alloc_pinned", vp, C.c_size_t)
     sig("smgx_free_pinned", None, vp)
     sig("smgx_set_workers", st, vp, cp, P(cp), u32, pp)
@@ -153,6 +154,7 @@ def load():
     sig("smgx_timer_stop_ms", st, vp, u32, P(C.c_float), pp)
     sig("smgx_timer_start_all", st, vp, pp)
     sig("smgx_timer_stop_all_ms", st, vp, P(C.c_float), pp)
+    sig("smgx_set_event_path", None, C.c_int, C.c_int)
     sig("smgx_kernel_launches", u64, vp)
     sig("smgx_flush_l2", st, vp, pp)
     _lib = L

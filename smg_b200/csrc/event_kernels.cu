@@ -16,6 +16,11 @@
 // one u64 word per lane (≤ 2048 workers) reduced with warp collectives.  No tensor-core work exists on this path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <string>
+
 #include "kernels.h"
 #include "xxh3.cuh"
 
@@ -507,6 +512,124 @@ __global__ void __launch_bounds__(256) event_search_warp_kernel(EventIndexView v
     }
 }
 
+// ---- the whole event-driven pick in ONE kernel: hash → search → pick, one warp per request, software-pipelined --------------
+// The split design above needs two launches and a 256 B/request hash scratch, and its search kernel is a partial wave of dependent
+// loads that only disappears when other launches overlap it.  Here a persistent warp walks requests g, g+S, g+2S, …; while it hashes
+// and probes for request g, the 2 KB token load of request g+S (one 64 B block per lane, 4×LDG.128) and the offsets of request g+2S
+// are already in flight — the token stream never pauses for the probe latency, every token is read exactly once, the hashes never
+// leave the SM (per-warp shared-memory row), and a launch of K batches is one grid.
+//   ← compute_request_content_hashes + PositionalIndexer::find_matches + score_overlap   event_tree.rs:141-151, :461-753; cache_aware.rs:736-831
+struct FusedReq { const BatchDesc* b; uint32_t r, off, ntok; };
+
+__device__ __forceinline__ FusedReq fused_fetch(const MultiArgs& a, uint32_t g) {
+    uint32_t j, r;
+    if (a.uniform_n) { j = g / a.uniform_n; r = g - j * a.uniform_n; }
+    else { j = 0; while (j + 1 < a.count && a.b[j + 1].hash_base <= g) ++j; r = g - a.b[j].hash_base; }
+    FusedReq q;
+    q.b = &a.b[j]; q.r = r;
+    q.off = __ldg(q.b->offsets + r);
+    q.ntok = __ldg(q.b->offsets + r + 1) - q.off;
+    return q;
+}
+// block `lane` of the request (the only block of a lane when the request has ≤ 32 blocks): loads issued, not consumed
+__device__ __forceinline__ void fused_load_first(const FusedReq& q, int lane, uint32_t (&w)[16]) {
+    if ((uint32_t)lane < q.ntok / 16) {
+        const uint32_t* p = q.b->tokens + q.off + (size_t)lane * 16;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const uint4* q4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { uint4 t = __ldg(q4 + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = __ldg(p + i);
+        }
+    }
+}
+
+template <bool W1, int BS, int MINB>
+__global__ void __launch_bounds__(256, MINB) event_fused_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    extern __shared__ uint64_t smem_ch[];
+    __shared__ int32_t s_slice[64];
+    __shared__ uint64_t s_load[64], s_ts[64];
+    if (W1 && threadIdx.x < 64) {
+        bool ok = threadIdx.x < v.n_workers;
+        s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
+    const FleetDerived fd = *f.derived;
+    const uint64_t elig = W1 ? f.elig[0] : ((uint32_t)lane < v.words ? f.elig[lane] : 0ULL);
+    const uint32_t total = a.total, S = gridDim.x * wpc;
+    uint32_t g = blockIdx.x * wpc + wic;
+    if (g >= total) return;
+    const uint32_t bs = BS ? (uint32_t)BS : a.block_size;
+
+    FusedReq q0 = fused_fetch(a, g), q1 = q0;
+    if (g + S < total) q1 = fused_fetch(a, g + S);
+    uint32_t w0[16];
+    if (BS == 16) fused_load_first(q0, lane, w0);
+    for (; g < total; g += S) {
+        uint32_t w1[16];
+        if (BS == 16 && g + S < total) fused_load_first(q1, lane, w1);
+        FusedReq q2 = q1;
+        if (g + 2 * S < total) q2 = fused_fetch(a, g + 2 * S);
+
+        // ---- request g ----
+        const BatchDesc& b = *q0.b;
+        const bool cand_mode = b.cand != nullptr;
+        int32_t out = -1;
+        uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+        Cand best{false, 0, 0, -1};
+        if (!cand_mode && fd.n_healthy == 0) {
+        } else if (!cand_mode && fd.imbalanced) {
+            out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
+        } else {
+            const uint32_t nb = bs ? q0.ntok / bs : 0;
+            if (nb > a.max_blocks) { if (lane == 0) atomicExch(a.err_flag, 1u); branch = 255; }
+            else {
+                uint64_t winset = 0;
+                uint32_t score = 0;
+                if (nb > 0 && v.n_workers > 0) {
+                    if (BS == 16) {
+                        if ((uint32_t)lane < nb) ch[lane] = xxh3_16words(w0, kSeed);
+                        for (uint32_t blk = lane + 32; blk < nb; blk += 32) ch[blk] = hash_block<16>(b.tokens + q0.off + (size_t)blk * 16, 16);
+                    } else {
+                        for (uint32_t blk = lane; blk < nb; blk += 32) ch[blk] = hash_block<0>(b.tokens + q0.off + (size_t)blk * bs, bs);
+                    }
+                    __syncwarp();
+                    SelectSink<W1> sink{elig, 0, 0};
+                    uint64_t surv = jump_search<W1>(v, ch, (int)nb, lane, sink, false) & elig;
+                    if (set_any<W1>(surv)) { winset = surv; score = nb; }
+                    else { winset = sink.last; score = sink.last_score; }
+                    __syncwarp();
+                }
+                if (set_any<W1>(winset)) {
+                    if (W1) {
+                        uint64_t w = winset;
+                        while (w) { int id = __ffsll((long long)w) - 1; w &= w - 1; best.consider(s_slice[id], s_load[id], s_ts[id]); }
+                    } else best = warp_arg_best(v, f, winset, lane);
+                    out = best.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
+                } else { out = fd.min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD; }
+            }
+        }
+        if (lane == 0) {
+            if (cand_mode) {
+                smgx_shard_candidate sc;
+                sc.score = best.have ? matched : 0; sc.local_idx = best.have ? (uint32_t)best.sl : 0xFFFFFFFFu; sc.load = best.ld; sc.tree_size = best.ts;
+                b.cand[q0.r] = sc;
+            } else write_pick(b, q0.r, out, branch, matched, q0.ntok);
+        }
+        q0 = q1; q1 = q2;
+        if (BS == 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w0[i] = w1[i];
+        }
+    }
+}
+
 template <bool W1>
 __global__ void find_matches_kernel(EventIndexView v, const uint64_t* __restrict__ hashes, uint32_t n, int early_exit, uint32_t* scores) {
     extern __shared__ uint64_t smem_ch[];
@@ -562,10 +685,22 @@ __global__ void __launch_bounds__(256) fleet_prepare_kernel(FleetRaw raw, FleetD
             int32_t id = raw.id_of_slice[i];
             if (id >= 0 && (uint32_t)id < raw.n_ids) {
                 atomicOr(&elig[id >> 6], 1ULL << (id & 63));
-                slice_of_id[id] = (int32_t)i;
-                load_of_id[id] = load;
+                if (!raw.has_dups) { slice_of_id[id] = (int32_t)i; load_of_id[id] = load; }
             }
         }
+    }
+    if (raw.has_dups) {
+        // Two slice entries with the same URL map to the same indexer id: score_overlap (cache_aware.rs:795-818) scores BOTH indices
+        // with the same (score, tree_size), so among them max_by_key keeps the lowest load and, on equal loads, the LAST index.
+        // Pre-reduce per id in slice order (one thread: fleets are a few thousand entries and this runs once per fleet snapshot).
+        __syncthreads();
+        if (tid == 0)
+            for (uint32_t i = 0; i < raw.n_slice; ++i) {
+                if ((raw.flags[i] & 3) != 3) continue;
+                const int32_t id = raw.id_of_slice[i];
+                if (id < 0 || (uint32_t)id >= raw.n_ids) continue;
+                if (slice_of_id[id] < 0 || raw.loads[i] <= load_of_id[id]) { slice_of_id[id] = (int32_t)i; load_of_id[id] = raw.loads[i]; }
+            }
     }
     s_mn[tid] = mn; s_mx[tid] = mx; s_hl[tid] = hl; s_hidx[tid] = hidx; s_fh[tid] = fh; s_nh[tid] = nh;
     __syncthreads();
@@ -604,11 +739,66 @@ void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t*
     SMGX_CUDA(cudaGetLastError());
 }
 
+// 1 = fused (default), 0 = split; initialised from SMGX_EVENT_PATH, switchable at run time for A/B runs and tests
+static std::atomic<int> g_event_path{-1};
+bool event_select_fused() {
+    int v = g_event_path.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SMGX_EVENT_PATH");
+        v = (e && std::string(e) == "split") ? 0 : 1;
+        g_event_path.store(v, std::memory_order_relaxed);
+    }
+    return v == 1;
+}
+void set_event_select_fused(bool fused) { g_event_path.store(fused ? 1 : 0, std::memory_order_relaxed); }
+static std::atomic<int> g_fused_minb{-1};
+void set_fused_minb(int minb) { g_fused_minb.store(minb == 3 ? 3 : 4, std::memory_order_relaxed); }
+
+// resident CTAs per SM the fused kernel is compiled for: 4 = 64 registers / 32 warps, 3 = 80 registers / 24 warps (SMGX_FUSED_MINB, A/B runs)
+static int fused_minb() {
+    int v = g_fused_minb.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SMGX_FUSED_MINB");
+        v = (e && e[0] == '3') ? 3 : 4;
+        g_fused_minb.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+template <bool W1, int BS>
+static void launch_fused(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
+    auto k = fused_minb() == 3 ? event_fused_kernel<W1, BS, 3> : event_fused_kernel<W1, BS, 4>;
+    const size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
+    int wpc = 8;
+    while (wpc > 1 && per_warp * wpc > 64 * 1024) wpc >>= 1;
+    const size_t smem = per_warp * wpc;
+    if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "request too long for the per-warp scratch (max_tokens_per_request)");
+    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static thread_local int occ_cache[2][2][2][4] = {};   // [minb][W1][BS16][log2 wpc] for the common small-smem case
+    int occ = 0;
+    int& slot = occ_cache[fused_minb() == 3 ? 1 : 0][W1 ? 1 : 0][BS == 16 ? 1 : 0][wpc == 8 ? 3 : wpc == 4 ? 2 : wpc == 2 ? 1 : 0];
+    if (smem <= 4096 && slot) occ = slot;
+    else {
+        SMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
+        if (smem <= 4096) slot = occ;
+    }
+    const unsigned persistent = (unsigned)sm_count * (unsigned)std::max(occ, 1);
+    const unsigned need = (a.total + wpc - 1) / wpc;
+    k<<<std::max(1u, std::min(persistent, need)), wpc * 32, smem, stream>>>(ix, fleet, a);
+}
+
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
     if (a.count == 0) return;
     uint32_t max_n = 0;
     for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
     if (max_n == 0) return;
+    if (event_select_fused()) {
+        const bool w1 = ix.words == 1;
+        if (a.block_size == 16) { if (w1) launch_fused<true, 16>(ix, fleet, a, sm_count, stream); else launch_fused<false, 16>(ix, fleet, a, sm_count, stream); }
+        else { if (w1) launch_fused<true, 0>(ix, fleet, a, sm_count, stream); else launch_fused<false, 0>(ix, fleet, a, sm_count, stream); }
+        SMGX_CUDA(cudaGetLastError());
+        ++*launches;
+        return;
+    }
     // K2b hashes: one thread per block slot, capped at a few waves (grid-stride beyond that)
     if (a.block_size) {
         uint64_t threads = (uint64_t)max_n * a.max_blocks;

@@ -33,6 +33,7 @@ struct FleetRaw {
     uint32_t n_slice;
     uint32_t n_ids;               // interned workers
     uint32_t words;               // bitset words (id space)
+    uint32_t has_dups;            // two slice entries share a URL (same indexer id): resolve in slice order, see fleet_prepare_kernel
     uint64_t abs_threshold;
     float rel_threshold;
 };
@@ -42,11 +43,12 @@ void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t*
 
 // The event-driven pick for up to kMaxMultiBatches batches per launch (blockIdx.y = batch; descriptors travel in the
 // kernel parameter block).  Two kernels in stream order:
+// Default: event_fused_kernel — ONE persistent kernel, one warp per request, hash → jump search → argmax, the next request's
+// tokens prefetched while the current one is probed.  SMGX_EVENT_PATH=split keeps the round-1 two-kernel form for A/B runs:
 //   hash_blocks_kernel           K2b part 1: XXH3 content hash of every full block, one thread per block, streaming
 //   event_search_{thread,warp}   K2b part 2 + K3: jump search over the positional index + argmax worker
 //                                (one thread per request for fleets ≤ 64 interned workers, one warp per request above)
-// `hashes` is a scratch of sum(n) × max_blocks u64 laid out [request][max_blocks]; it is written and read back within
-// microseconds, i.e. out of L2.
+//   `hashes` is then a scratch of sum(n) × max_blocks u64 laid out [request][max_blocks], written and read back out of L2.
 constexpr int kMaxMultiBatches = 32;
 struct BatchDesc {
     const uint32_t* tokens;        // device, ragged
@@ -62,9 +64,15 @@ struct MultiArgs {
     uint32_t count;
     uint32_t block_size;
     uint32_t max_blocks;           // row length of the hash scratch = max blocks per request
-    uint64_t* hashes;
+    uint64_t* hashes;              // split path only (nullptr on the fused path)
     uint32_t* err_flag;            // device: set to 1 when a request exceeds max_blocks
+    uint32_t total;                // sum of b[k].n  (b[k].hash_base = requests before batch k)
+    uint32_t uniform_n;            // every batch has this many requests (0: look the batch up through hash_base)
 };
+// true: launch_event_select runs the one-kernel fused path (no hash scratch needed).  SMGX_EVENT_PATH=split selects the two-kernel path.
+bool event_select_fused();
+void set_event_select_fused(bool fused);
+void set_fused_minb(int minb);
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
 
 // PositionalIndexer::find_matches on precomputed content hashes; one warp, one query.

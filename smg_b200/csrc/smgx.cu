@@ -25,6 +25,10 @@
 #include "blake3.h"
 #include "prefix_hash.h"
 #include <cstdio>
+#include <cctype>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -49,6 +53,7 @@ struct ModelState {
     std::unordered_map<uint64_t, std::pair<uint64_t, uint32_t>> hash_index_tokens, hash_index_text;   // hash → (arena offset, length)
     std::vector<uint32_t> hash_arena_tokens;
     std::string hash_arena_text;
+    uint64_t hash_dead_tokens = 0, hash_dead_text = 0;   // arena elements / bytes no entry points at any more
     DevBuf d_slice_of_tenant;
     std::vector<uint32_t> tenant_of_slice;        // tenant id of urls[i]
     uint64_t seen_tenants_version = ~0ULL;
@@ -212,6 +217,16 @@ public:
             FleetRaw raw;
             raw.loads = m.d_loads.as<uint64_t>(); raw.flags = m.d_flags.as<uint8_t>(); raw.id_of_slice = m.d_id_of_slice.as<int32_t>();
             raw.n_slice = ns; raw.n_ids = n_ids; raw.words = words;
+            raw.has_dups = 0;
+            {   // duplicate URLs in the slice → several slice entries share one indexer id
+                std::vector<uint8_t> seen(std::max<uint32_t>(n_ids, 1), 0);
+                for (uint32_t i = 0; i < ns; ++i) {
+                    const int32_t id = id_of_slice[i];
+                    if (id < 0 || (uint32_t)id >= n_ids) continue;
+                    if (seen[(size_t)id]) { raw.has_dups = 1; break; }
+                    seen[(size_t)id] = 1;
+                }
+            }
             raw.abs_threshold = cfg.balance_abs_threshold; raw.rel_threshold = cfg.balance_rel_threshold;
             launch_fleet_prepare(raw, m.d_derived.as<FleetDerived>(), m.d_slice_of_id.as<int32_t>(), m.d_load_of_id.as<uint64_t>(),
                                  m.d_elig.as<uint64_t>(), ctrl);
@@ -249,10 +264,16 @@ public:
         a.block_size = bs;
         a.max_blocks = bs ? std::max<uint32_t>(max_req_tokens / bs, 1) : 1;
         uint64_t rows = 0;
-        for (uint32_t k = 0; k < count; ++k) { a.b[k] = descs[k]; a.b[k].hash_base = (uint32_t)rows; rows += descs[k].n; }
+        bool uniform = true;
+        for (uint32_t k = 0; k < count; ++k) { a.b[k] = descs[k]; a.b[k].hash_base = (uint32_t)rows; rows += descs[k].n; uniform = uniform && descs[k].n == descs[0].n; }
         SMGX_REQUIRE(rows < (1ull << 32), "too many requests in one launch");
-        lane.d_hash.reserve(std::max<uint64_t>(rows, 1) * a.max_blocks * 8);
-        a.hashes = lane.d_hash.as<uint64_t>();
+        a.total = (uint32_t)rows;
+        a.uniform_n = uniform && count ? descs[0].n : 0;
+        a.hashes = nullptr;
+        if (!event_select_fused()) {
+            lane.d_hash.reserve(std::max<uint64_t>(rows, 1) * a.max_blocks * 8);
+            a.hashes = lane.d_hash.as<uint64_t>();
+        }
         a.err_flag = d_err.as<uint32_t>();
         launch_event_select(ixv, fv, a, sm_count, lane.stream, &launches);
         SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
@@ -262,6 +283,61 @@ public:
                         int32_t* d_out, smgx_decision_info* d_info) {
         BatchDesc d{d_tokens, d_offsets, d_out, d_info, n, 0, nullptr};
         enqueue_batches(m, lane, &d, 1, max_req_tokens);
+    }
+
+
+    // hash_index.insert(hash, matched_prefix) (cache_aware.rs:881-886, :950-956) REPLACES the previous value.  Values live in one arena
+    // per model: an existing key is overwritten in place when the new prefix fits, otherwise the old bytes are counted dead and the
+    // arena is compacted once more than half of it is dead — repeated identical requests no longer grow it.
+    static void hash_index_put_tokens(ModelState& m, uint64_t key, const uint32_t* tk, uint32_t len) {
+        auto it = m.hash_index_tokens.find(key);
+        if (it != m.hash_index_tokens.end()) {
+            if (len <= it->second.second) {
+                std::copy(tk, tk + len, m.hash_arena_tokens.begin() + (ptrdiff_t)it->second.first);
+                m.hash_dead_tokens += it->second.second - len;
+                it->second.second = len;
+                return;
+            }
+            m.hash_dead_tokens += it->second.second;
+        }
+        m.hash_index_tokens[key] = {m.hash_arena_tokens.size(), len};
+        m.hash_arena_tokens.insert(m.hash_arena_tokens.end(), tk, tk + len);
+        if (m.hash_dead_tokens > 4096 && m.hash_dead_tokens * 2 > m.hash_arena_tokens.size()) {
+            std::vector<uint32_t> live;
+            live.reserve(m.hash_arena_tokens.size() - m.hash_dead_tokens);
+            for (auto& kv : m.hash_index_tokens) {
+                const uint64_t at = live.size();
+                live.insert(live.end(), m.hash_arena_tokens.begin() + (ptrdiff_t)kv.second.first, m.hash_arena_tokens.begin() + (ptrdiff_t)(kv.second.first + kv.second.second));
+                kv.second.first = at;
+            }
+            m.hash_arena_tokens.swap(live);
+            m.hash_dead_tokens = 0;
+        }
+    }
+    static void hash_index_put_text(ModelState& m, uint64_t key, const uint8_t* tx, uint32_t len) {
+        auto it = m.hash_index_text.find(key);
+        if (it != m.hash_index_text.end()) {
+            if (len <= it->second.second) {
+                memcpy(&m.hash_arena_text[(size_t)it->second.first], tx, len);
+                m.hash_dead_text += it->second.second - len;
+                it->second.second = len;
+                return;
+            }
+            m.hash_dead_text += it->second.second;
+        }
+        m.hash_index_text[key] = {m.hash_arena_text.size(), len};
+        m.hash_arena_text.append((const char*)tx, len);
+        if (m.hash_dead_text > 16384 && m.hash_dead_text * 2 > m.hash_arena_text.size()) {
+            std::string live;
+            live.reserve(m.hash_arena_text.size() - m.hash_dead_text);
+            for (auto& kv : m.hash_index_text) {
+                const uint64_t at = live.size();
+                live.append(m.hash_arena_text, (size_t)kv.second.first, kv.second.second);
+                kv.second.first = at;
+            }
+            m.hash_arena_text.swap(live);
+            m.hash_dead_text = 0;
+        }
     }
 
     TokenTreeIndex& tree_of(ModelState& m, bool create) {
@@ -391,8 +467,7 @@ public:
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
                     const size_t idx = (size_t)out_idx[r];
                     tree.insert_tokens(tk, len, m.tenant_of_slice[idx]);   // :868 / :396
-                    m.hash_index_tokens[path_hash[r]] = {m.hash_arena_tokens.size(), info[r].matched};
-                    m.hash_arena_tokens.insert(m.hash_arena_tokens.end(), tk, tk + info[r].matched);
+                    hash_index_put_tokens(m, path_hash[r], tk, info[r].matched);
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -625,8 +700,7 @@ public:
                     tree.insert_text(tx, nb, m.tenant_of_slice[idx]);   // :938 / :421
                     uint32_t pb = 0, chars = 0;   // text.chars().take(matched_char_count): byte length of the matched prefix
                     while (pb < nb && chars < info[r].matched) { ++pb; while (pb < nb && (tx[pb] & 0xC0) == 0x80) ++pb; ++chars; }
-                    m.hash_index_text[path_hash[r]] = {m.hash_arena_text.size(), pb};
-                    m.hash_arena_text.append((const char*)tx, pb);
+                    hash_index_put_text(m, path_hash[r], tx, pb);
                     if (idx < m.processed.size()) ++m.processed[idx];
                 }
             }
@@ -641,8 +715,8 @@ public:
         for (auto& kv : models) if (kv.second->string_tree) kv.second->string_tree->evict_tenant_by_size((size_t)max_size);   // :317-321
         for (auto& kv : models) if (kv.second->token_tree) kv.second->token_tree->evict_tenant_by_size((size_t)max_size);     // :322-326
         for (auto& kv : models) {   // per model, per tree kind (:335-351)
-            if (kv.second->hash_index_text.size() > max_size) { kv.second->hash_index_text.clear(); kv.second->hash_arena_text.clear(); }
-            if (kv.second->hash_index_tokens.size() > max_size) { kv.second->hash_index_tokens.clear(); kv.second->hash_arena_tokens.clear(); }
+            if (kv.second->hash_index_text.size() > max_size) { kv.second->hash_index_text.clear(); kv.second->hash_arena_text.clear(); kv.second->hash_dead_text = 0; }
+            if (kv.second->hash_index_tokens.size() > max_size) { kv.second->hash_index_tokens.clear(); kv.second->hash_arena_tokens.clear(); kv.second->hash_dead_tokens = 0; }
         }
     }
     // The reference's background eviction thread (cache_aware.rs:126-199): every eviction_interval_secs, bound every tree to
@@ -675,8 +749,8 @@ public:
         if (!has_event_indexer(m) || (host_imbalanced(m) && m.token_tree)) {
             // approximate token tree (or the imbalanced path's tree update): completes synchronously
             for (uint32_t i = 0; i < n; ++i) SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
+            Lane& l = free_lane();   // SMGX_BUSY must be raised BEFORE the tree is touched: callers retry the whole batch on BUSY
             tree_select(m, tokens, offsets, n, out_idx, out_info, true, nullptr);
-            Lane& l = free_lane();
             l.busy = true; l.ticket = ++ticket_seq; l.model = &m; l.host_out = out_idx; l.n = 0;   // n = 0: processed already counted
             return l.ticket;
         }
@@ -830,6 +904,59 @@ void* smgx_alloc_pinned(size_t bytes) {
 }
 void smgx_free_pinned(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
+// Bind the CALLING thread (and, by first touch / preferred policy, the pinned buffers it allocates afterwards) to the NUMA node the
+// device hangs off: a rank whose staging memory sits on the other socket pays for every H2D copy twice (UPI hop).  Opt-in, process-local.
+smgx_status smgx_bind_numa(int device_id, int* out_node, char** err) {
+    return guard(err, [&]() {
+        if (out_node) *out_node = -1;
+        char bus[32] = {0};
+        SMGX_CUDA(cudaDeviceGetPCIBusId(bus, sizeof(bus), device_id));
+        for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+        int node = -1;
+        {
+            std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+            FILE* f = fopen(path.c_str(), "r");
+            if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+        }
+        if (node < 0) return SMGX_SUCCESS;   // single-node box or no topology information: nothing to do
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        int n_cpu = 0;
+        {
+            std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+            FILE* f = fopen(path.c_str(), "r");
+            if (f) {
+                int a, b;
+                for (;;) {
+                    if (fscanf(f, "%d", &a) != 1) break;
+                    b = a;
+                    int ch = fgetc(f);
+                    if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+                    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++n_cpu; }
+                    if (ch != ',') break;
+                }
+                fclose(f);
+            }
+        }
+        if (n_cpu > 0) {
+            cpu_set_t cur;   // intersect with what the process is allowed to use (containers)
+            CPU_ZERO(&cur);
+            if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+                cpu_set_t both;
+                CPU_AND(&both, &cur, &set);
+                if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof(both), &both);
+            }
+        }
+        if (node < 64) {
+            unsigned long mask = 1ul << node;
+            syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8);
+        }
+        if (out_node) *out_node = node;
+        return SMGX_SUCCESS;
+    });
+}
+
+
 // ---- fleet ----
 smgx_status smgx_set_workers(smgx_policy* p, const char* model_key, const char* const* urls, uint32_t n, char** err) {
     return guard(err, [&]() {
@@ -861,7 +988,7 @@ smgx_status smgx_set_fleet_state(smgx_policy* p, const char* model_key, const ui
         for (uint32_t i = 0; i < n; ++i) {
             if (loads) m.loads[i] = loads[i];
             uint8_t h = healthy ? (healthy[i] ? 1 : 0) : (m.flags[i] & 1);
-            uint8_t c = circuit_ok ? (circuit_ok[i] ? 2 : 0) : 2;
+            uint8_t c = circuit_ok ? (circuit_ok[i] ? 2 : 0) : (m.flags[i] & 2);   // null = keep the previous circuit-breaker bit
             m.flags[i] = h | c;
         }
         m.fleet_dirty = true;
@@ -2288,6 +2415,10 @@ smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err) {
         SMGX_CUDA(cudaEventElapsedTime(out_ms, P.lanes[0].t0, P.lanes[0].t1));
         return SMGX_SUCCESS;
     });
+}
+void smgx_set_event_path(int fused, int min_blocks_per_sm) {
+    set_event_select_fused(fused != 0);
+    if (min_blocks_per_sm) set_fused_minb(min_blocks_per_sm);
 }
 uint64_t smgx_kernel_launches(const smgx_policy* p) { return p ? p->impl.launches : 0; }
 smgx_status smgx_flush_l2(smgx_policy* p, char** err) {

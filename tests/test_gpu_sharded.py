@@ -82,7 +82,8 @@ def _worker(rank, world, port, n_workers, seed, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_workers,seed", [(2, 128, 1), (2, 200, 2), (4, 300, 3)])
+@pytest.mark.parametrize("world,n_workers,seed", [(2, 128, 1), (2, 200, 2), (4, 300, 3),
+                                                   (8, 4096, 4)])   # BASELINE config 4 shape: 8 ranks × 512 workers (ranks share the device)
 def test_sharded_pick_matches_oracle_on_whole_fleet(world, n_workers, seed):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -92,6 +93,6 @@ def test_sharded_pick_matches_oracle_on_whole_fleet(world, n_workers, seed):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(300)
+        p.join(600)
     assert all(p.exitcode == 0 for p in procs)
     assert all(ret.get(r) is True for r in range(world))
