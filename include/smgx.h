@@ -340,6 +340,16 @@ smgx_status smgx_submit_tokens(smgx_policy* p, const char* model_key, const uint
                                int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err);
 smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err);
 
+/* Latency path (small batches, per-request callers): zero-copy.  `tokens`, `offsets`, `out_worker_idx`, `out_info` and `done_flag` must
+ * live in memory from smgx_alloc_pinned (device-visible at the same address).  The kernel reads the requests in place over PCIe, stores
+ * the picks straight into out_worker_idx and finally stores `done_value` to *done_flag (release, system scope): the caller spins on the
+ * flag — no staging copy, no stream synchronisation, no ticket, no lane is held.  Requests longer than max_request_tokens (0 = the
+ * policy's max_tokens_per_request) get pick -1 / branch 255.  Event-driven mode only: SMGX_NOT_FOUND when the model is currently routed
+ * through a tree (those modes mutate host state; use smgx_submit_tokens).  increment_processed() accounting is left to the caller. */
+smgx_status smgx_submit_tokens_mapped(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                                      uint32_t max_request_tokens, int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* done_flag,
+                                      uint64_t done_value, char** err);
+
 /* Same for rendered text (smgx_select_batch_text without the token read-back): H2D, GPU tokenize, pick and D2H ride one lane. */
 smgx_status smgx_submit_text(smgx_policy* p, const char* model_key, const uint8_t* text, const uint32_t* offsets, uint32_t n,
                              int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* out_ticket, char** err);
@@ -395,6 +405,8 @@ smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
  * one-kernel persistent path, 0 = the round-1 hash kernel + search kernel pair.  min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant
  * of the fused kernel.  Also settable through the environment: SMGX_EVENT_PATH=split|fused, SMGX_FUSED_MINB=3|4. */
 void smgx_set_event_path(int fused, int min_blocks_per_sm);
+/* L2 prefetch flavour of the fused kernel: 0 none, 1 one bulk prefetch per request (default), 2 one prefetch per lane (SMGX_FUSED_PF). */
+void smgx_set_fused_prefetch(int flavour);
 /* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
 uint64_t smgx_kernel_launches(const smgx_policy* p);
 /* Writes a buffer larger than L2 (bench hygiene between timed iterations). */

@@ -4,6 +4,17 @@
 // first one), keeps up to smgx_pipeline_depth() batches in flight through smgx_submit_tokens / smgx_wait, and hands every caller its
 // own pick.  Every request of a batch sees one fleet snapshot — the state the reference's select_worker would read at that instant.
 //
+// Two transports, chosen by Options::mapped:
+//   mapped = true (default; event-driven mode) — the LATENCY path.  The dispatcher is a busy-polling group-commit loop: the moment the
+//     open batch holds a request and fewer than max_inflight batches are on the GPU it closes the batch and hands it to
+//     smgx_submit_tokens_mapped — the kernel reads the batch's pinned staging in place (zero copy), writes the picks back into pinned
+//     memory and raises a completion word the callers themselves spin on.  No staging copy, no cudaStreamSynchronize, no completer
+//     thread, no mutex or condition variable on the request path.  While max_inflight batches are out, arrivals pile into the open
+//     batch — batches grow with load instead of with a fixed window.  A model that is currently routed through a tree (SMGX_NOT_FOUND
+//     from the mapped call) falls back to the staged transport for that batch.
+//   mapped = false — the staged transport of round 1: smgx_submit_tokens / smgx_wait (H2D copy, ≤ pipeline_depth tickets in flight, a
+//     completer thread publishing per-batch results through a condition variable), batches close max_wait after their first request.
+//
 // Header-only C++17 over the C ABI (include/smgx.h); the same structure is what INTEGRATION.md's Rust `batcher.route()` does with
 // tokio::sync::oneshot instead of condition variables.
 #pragma once
@@ -31,6 +42,10 @@ public:
         std::chrono::microseconds max_wait{100};         // a batch leaves at most this long after its first request arrived
         uint32_t ring = 6;                               // batches allocated up front: open + in flight + being read by their callers
         uint32_t max_ring = 64;                          // the ring grows on demand up to this many batches (a caller may hold tickets of many)
+        bool mapped = true;                              // zero-copy latency transport (see above); false = staged copies + tickets
+        uint32_t max_inflight = 3;                       // mapped: batches on the GPU at once; arrivals beyond that join the open batch
+        std::chrono::microseconds linger{0};             // mapped: keep a non-full batch open this long after its first request (0 = ship at once)
+        uint32_t max_request_tokens = 0;                 // mapped: bound on the longest request (0 = the policy's max_tokens_per_request)
     };
     struct Stats { uint64_t requests = 0, batches = 0, full_batches = 0; };
 
@@ -42,15 +57,20 @@ public:
         for (uint32_t i = 0; i < opt_.max_ring; ++i) slots_[i].store(nullptr, std::memory_order_relaxed);
         for (uint32_t i = 0; i < opt_.ring; ++i) add_batch();
         make_open(0);
-        dispatcher_ = std::thread([this] { dispatch_loop(); });
-        completer_ = std::thread([this] { complete_loop(); });
+        if (opt_.mapped) dispatcher_ = std::thread([this] { dispatch_loop_mapped(); });
+        else {
+            dispatcher_ = std::thread([this] { dispatch_loop(); });
+            completer_ = std::thread([this] { complete_loop(); });
+        }
     }
     ~Batcher() {
-        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
-        cv_work_.notify_all(); cv_inflight_.notify_all(); cv_space_.notify_all();
-        if (dispatcher_.joinable()) dispatcher_.join();
-        if (completer_.joinable()) completer_.join();
-        for (auto& b : ring_) { smgx_free_pinned(b->tokens); smgx_free_pinned(b->offsets); smgx_free_pinned(b->out); smgx_free_pinned(b->info); }
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; stop_flag_.store(true, std::memory_order_release); }
+        cv_work_.notify_all(); cv_space_.notify_all();
+        if (dispatcher_.joinable()) dispatcher_.join();   // first: nothing is submitted after this …
+        { std::lock_guard<std::mutex> g(mu_); dispatcher_done_ = true; }
+        cv_inflight_.notify_all();
+        if (completer_.joinable()) completer_.join();      // … then the completer drains what is still in flight before the buffers go
+        for (auto& b : ring_) { smgx_free_pinned(b->tokens); smgx_free_pinned(b->offsets); smgx_free_pinned(b->out); smgx_free_pinned(b->info); smgx_free_pinned((void*)b->done_flag); }
     }
     Batcher(const Batcher&) = delete;
     Batcher& operator=(const Batcher&) = delete;
@@ -70,7 +90,18 @@ public:
         int status;
         std::string error;
         int32_t idx;
-        {
+        if (opt_.mapped) {   // the GPU (or the fallback path) stores the batch's generation into the pinned completion word
+            uint32_t spins = 0;
+            while (__atomic_load_n(b->done_flag, __ATOMIC_ACQUIRE) != t.gen) {
+                if (++spins < 4096) cpu_relax();
+                else std::this_thread::yield();   // oversubscribed box: give the core away instead of burning the time slice
+            }
+            std::lock_guard<std::mutex> lk(b->mu);   // uncontended; orders the reads below after a fallback's status write
+            status = b->status;
+            if (status != SMGX_SUCCESS) error = b->error;
+            idx = b->out[t.slot];
+            if (info) *info = b->info[t.slot];
+        } else {
             std::unique_lock<std::mutex> lk(b->mu);
             b->cv_done.wait(lk, [&] { return b->done_gen == t.gen; });
             status = b->status;
@@ -100,6 +131,7 @@ private:
     enum State { FREE, OPEN, SUBMITTED };
     struct Batch {
         uint32_t* tokens = nullptr; uint32_t* offsets = nullptr; int32_t* out = nullptr; smgx_decision_info* info = nullptr;
+        uint64_t* done_flag = nullptr;           // pinned: generation of the last completed use (written by the GPU in mapped mode)
         std::atomic<uint64_t> rsv{kClosed};      // closed until the batch is opened
         std::atomic<uint32_t> filled{0}, readers{0};
         std::atomic<uint64_t> gen{1};
@@ -122,8 +154,10 @@ private:
         b->offsets = (uint32_t*)smgx_alloc_pinned(((size_t)opt_.max_batch + 1) * 4);
         b->out = (int32_t*)smgx_alloc_pinned((size_t)opt_.max_batch * 4);
         b->info = (smgx_decision_info*)smgx_alloc_pinned((size_t)opt_.max_batch * sizeof(smgx_decision_info));
-        if (!b->tokens || !b->offsets || !b->out || !b->info) throw std::runtime_error("smgx::Batcher: pinned allocation failed");
+        b->done_flag = (uint64_t*)smgx_alloc_pinned(64);
+        if (!b->tokens || !b->offsets || !b->out || !b->info || !b->done_flag) throw std::runtime_error("smgx::Batcher: pinned allocation failed");
         b->offsets[0] = 0;
+        *b->done_flag = 0;
         return b;
     }
     void add_batch() {   // mu_ held (or construction)
@@ -182,6 +216,7 @@ private:
         b->offsets[t.slot + 1] = (uint32_t)(at + n);
         if (n) std::memcpy(b->tokens + at, tokens, (size_t)n * 4);
         b->filled.fetch_add(1, std::memory_order_release);   // the dispatcher submits once every reserved slot is filled
+        if (opt_.mapped) return t;   // the dispatcher polls the reservation word: no lock, no wake-up on the request path
         if (t.slot == 0) { std::lock_guard<std::mutex> g(mu_); b->first = std::chrono::steady_clock::now(); b->first_set = b->gen.load(std::memory_order_relaxed); cv_work_.notify_one(); }
         else if (t.slot + 1 == opt_.max_batch) { std::lock_guard<std::mutex> g(mu_); cv_work_.notify_one(); }
         return t;
@@ -219,11 +254,94 @@ private:
             else { lk.lock(); inflight_.push_back(mine); cv_inflight_.notify_one(); }
         }
     }
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    // mapped transport: busy-polling group commit (see the header comment).  Only this thread closes batches.
+    void dispatch_loop_mapped() {
+        std::deque<std::pair<Batch*, uint64_t>> flying;   // (batch, generation) handed to the GPU, oldest first
+        auto retire = [&] { while (!flying.empty() && __atomic_load_n(flying.front().first->done_flag, __ATOMIC_ACQUIRE) == flying.front().second) flying.pop_front(); };
+        std::chrono::steady_clock::time_point first_seen{};
+        uint64_t seen_gen = 0;
+        uint32_t seen_batch = ~0u;
+        uint32_t idle = 0;
+        while (!stop_flag_.load(std::memory_order_acquire)) {
+            retire();
+            const uint32_t oi = open_idx_.load(std::memory_order_acquire);
+            Batch* ob = batch_at(oi);
+            const uint64_t r = ob->rsv.load(std::memory_order_acquire);
+            const uint32_t have = (r & kClosed) ? 0 : slots_of(r);
+            bool ship = false;
+            if (have) {
+                const bool full = have >= opt_.max_batch || tokens_of(r) + (opt_.max_request_tokens ? opt_.max_request_tokens : 1) > opt_.tokens_per_batch;
+                if (opt_.linger.count() > 0 && !full) {
+                    const uint64_t g = ob->gen.load(std::memory_order_relaxed);
+                    if (seen_batch != oi || seen_gen != g) { seen_batch = oi; seen_gen = g; first_seen = std::chrono::steady_clock::now(); }
+                    ship = std::chrono::steady_clock::now() - first_seen >= opt_.linger;
+                } else ship = true;
+                if (ship && flying.size() >= opt_.max_inflight && !full) ship = false;   // GPU busy: let the batch grow (group commit)
+                if (ship && flying.size() >= 2 * (size_t)opt_.max_inflight) ship = false; // even full batches queue only so deep
+            }
+            bool close_req;
+            if (!ship) {
+                // a caller may be asking for a rotation (its request did not fit) or for space; serve that under the lock, rarely
+                ++idle;
+                if ((idle & 63) != 0) { cpu_relax(); continue; }
+                if (idle > (1u << 18) && !have && flying.empty()) std::this_thread::sleep_for(std::chrono::microseconds(20));   // long idle: stop burning the core
+                std::lock_guard<std::mutex> g(mu_);
+                close_req = ring_[open_]->state == OPEN && ring_[open_]->close_now && slots_of(ring_[open_]->rsv.load(std::memory_order_relaxed)) > 0;
+                if (!close_req) continue;
+            }
+            idle = 0;
+            std::unique_lock<std::mutex> lk(mu_);
+            if (stop_) break;
+            Batch& b = *ring_[open_];
+            if (b.state != OPEN) continue;
+            const uint64_t rr = b.rsv.fetch_or(kClosed, std::memory_order_acq_rel);
+            const uint32_t n = slots_of(rr);
+            if (n == 0) { b.rsv.store(rr & ~kClosed, std::memory_order_release); continue; }   // raced with a recycle: nothing to ship
+            b.n = n;
+            b.state = SUBMITTED;
+            b.readers.store(n, std::memory_order_release);
+            ++stats_.batches; stats_.requests += n;
+            if (n == opt_.max_batch) ++stats_.full_batches;
+            const uint64_t gen = b.gen.load(std::memory_order_relaxed);
+            open_next();
+            lk.unlock();
+            while (b.filled.load(std::memory_order_acquire) != n) cpu_relax();   // callers still copying their tokens in
+            { std::lock_guard<std::mutex> g(b.mu); b.status = SMGX_SUCCESS; b.error.clear(); }
+            char* err = nullptr;
+            smgx_status st = smgx_submit_tokens_mapped(p_, model_.c_str(), b.tokens, b.offsets, n, opt_.max_request_tokens, b.out, b.info, b.done_flag, gen, &err);
+            if (st == SMGX_NOT_FOUND) {   // the model is routed through a tree right now: staged transport for this batch, synchronously
+                if (err) { smgx_free_string(err); err = nullptr; }
+                uint64_t ticket = 0;
+                for (;;) {
+                    st = smgx_submit_tokens(p_, model_.c_str(), b.tokens, b.offsets, n, b.out, b.info, &ticket, &err);
+                    if (st != SMGX_BUSY) break;
+                    if (err) { smgx_free_string(err); err = nullptr; }
+                    std::this_thread::yield();
+                }
+                if (st == SMGX_SUCCESS) st = smgx_wait(p_, ticket, &err);
+                { std::lock_guard<std::mutex> g(b.mu); b.status = st; b.error = err ? err : ""; }
+                __atomic_store_n(b.done_flag, gen, __ATOMIC_RELEASE);
+            } else if (st != SMGX_SUCCESS) {
+                { std::lock_guard<std::mutex> g(b.mu); b.status = st; b.error = err ? err : "mapped submit failed"; }
+                __atomic_store_n(b.done_flag, gen, __ATOMIC_RELEASE);
+            } else flying.emplace_back(&b, gen);
+            if (err) smgx_free_string(err);
+        }
+        // drain: the callers of batches still on the GPU are spinning on their flags; the GPU raises them
+        for (uint32_t spins = 0; !flying.empty() && spins < 200000000u; ++spins) { retire(); cpu_relax(); }
+    }
     void complete_loop() {
         std::unique_lock<std::mutex> lk(mu_);
         for (;;) {
-            cv_inflight_.wait(lk, [&] { return stop_ || !inflight_.empty(); });
-            if (inflight_.empty()) { if (stop_) return; continue; }
+            cv_inflight_.wait(lk, [&] { return dispatcher_done_ || !inflight_.empty(); });
+            if (inflight_.empty()) { if (dispatcher_done_) return; continue; }   // the dispatcher has been joined: nothing more can arrive
             Batch& b = *ring_[inflight_.front()];
             inflight_.pop_front();
             lk.unlock();
@@ -249,7 +367,8 @@ private:
     std::atomic<uint32_t> open_idx_{0};
     std::deque<uint32_t> inflight_;
     uint32_t open_ = 0;
-    bool stop_ = false;
+    bool stop_ = false, dispatcher_done_ = false;
+    std::atomic<bool> stop_flag_{false};
     Stats stats_;
     std::thread dispatcher_, completer_;
 };

@@ -11,6 +11,7 @@
 #include <thread>
 
 #include "cache_aware.h"
+#include "tuned_event.h"
 #include "prefix_hash.h"
 
 using namespace orc;
@@ -346,6 +347,17 @@ double orc_policy_select_steps_mt(void* h, const uint32_t* const* tokens, const 
     }
     for (auto& th : ts) th.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// "port-tuned" (oracle/tuned_event.h): same decisions from a flat bitset index, threads created before the clock starts.
+// cfg thresholds are passed again because the policy keeps them private.  Returns elapsed seconds of the routed steps only.
+double orc_tuned_select_steps_mt(void* h, void* indexer, float rel_thr, uint64_t abs_thr, size_t block_size, const uint32_t* const* tokens,
+                                 const uint64_t* const* offsets, size_t n_batches, size_t n, size_t steps, int32_t* out_idx, int threads) {
+    auto* b = (PolicyBox*)h;
+    CacheAwareConfig c;
+    c.balance_rel_threshold = rel_thr; c.balance_abs_threshold = abs_thr; c.block_size = block_size;
+    TunedEventRouter r(((IndexerBox*)indexer)->ix, b->workers, c, block_size);
+    return r.run(tokens, offsets, n_batches, n, steps, out_idx, threads);
 }
 
 // TreeHandle (cache_aware.rs:443-645)

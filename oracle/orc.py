@@ -92,6 +92,7 @@ def lib():
         sig("orc_hash_token_path", C.c_uint64, vp, sz)
         sig("orc_policy_hash_index", sz, vp, cp, C.c_int, vp, sz)
         sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int, C.c_int)
+        sig("orc_tuned_select_steps_mt", C.c_double, vp, vp, C.c_float, C.c_uint64, sz, vp, vp, sz, sz, sz, vp, C.c_int)
         sig("orc_policy_apply_known_remote_insert", C.c_int, vp, cp, C.c_int, u64, cp)
         sig("orc_policy_apply_repair_entry", None, vp, cp, C.c_int, vp, sz, cp)
         sig("orc_ring_new", vp, P(cp), sz)
@@ -550,6 +551,18 @@ class CacheAwarePolicy:
         OP = (C.c_void_p * len(batches))(*[o.ctypes.data for o in offs])
         idx = np.zeros(n, np.int32)
         secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads, 1 if step_barrier else 0)
+        return idx, secs
+
+    def tuned_select_steps_mt(self, indexer, batches, steps, threads, rel_thr, abs_thr, block_size):
+        """The "port-tuned" variant (oracle/tuned_event.h): same event-mode decisions from a flat bitset index built from `indexer`,
+        worker threads created before the clock starts.  → (picks of the last step, seconds)."""
+        toks = [_u32(b[0]) for b in batches]
+        offs = [_u64(b[1]) for b in batches]
+        n = offs[0].size - 1
+        TP = (C.c_void_p * len(batches))(*[t.ctypes.data for t in toks])
+        OP = (C.c_void_p * len(batches))(*[o.ctypes.data for o in offs])
+        idx = np.zeros(n, np.int32)
+        secs = lib().orc_tuned_select_steps_mt(self.h, indexer.h, float(rel_thr), int(abs_thr), int(block_size), TP, OP, len(batches), n, steps, _ptr(idx), threads)
         return idx, secs
 
     # ---- TreeHandle (cache_aware.rs:443-645) ----

@@ -192,6 +192,8 @@ public:
     size_t tree_size(uint32_t wid) const { return tree_sizes_[wid]; }
     size_t jump_size() const { return jump_size_; }
     uint32_t worker_count() const { return next_worker_id_; }
+    // read-only visit of every (position, content hash) → SeqEntry (used to build the tuned bench variant, oracle/tuned_event.h)
+    template <class F> void for_each_entry(F&& f) const { for (auto& kv : index_) f(kv.first.first, kv.first.second, kv.second); }
 
     // :659-753 (find_matches :461)
     OverlapScores find_matches(const std::vector<uint64_t>& seq, bool early_exit) const {

@@ -137,6 +137,7 @@ def load():
     sig("smgx_pipeline_depth", u32, vp)
     sig("smgx_submit_tokens", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)
     sig("smgx_wait", st, vp, u64, pp)
+    sig("smgx_submit_tokens_mapped", st, vp, cp, vp, vp, u32, u32, vp, vp, vp, u64, pp)
     sig("smgx_submit_text", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)
     sig("smgx_select_batch_tokens_device", st, vp, cp, u32, vp, vp, u32, u32, vp, vp, pp)
     sig("smgx_select_many_tokens_device", st, vp, cp, u32, vp, vp, vp, u32, vp, pp)
@@ -155,6 +156,7 @@ def load():
     sig("smgx_timer_start_all", st, vp, pp)
     sig("smgx_timer_stop_all_ms", st, vp, P(C.c_float), pp)
     sig("smgx_set_event_path", None, C.c_int, C.c_int)
+    sig("smgx_set_fused_prefetch", None, C.c_int)
     sig("smgx_kernel_launches", u64, vp)
     sig("smgx_flush_l2", st, vp, pp)
     _lib = L

@@ -517,40 +517,58 @@ __global__ void __launch_bounds__(256) event_search_warp_kernel(EventIndexView v
 // loads that only disappears when other launches overlap it.  Here a persistent warp walks requests g, g+S, g+2S, …; while it hashes
 // and probes for request g, the 2 KB token load of request g+S (one 64 B block per lane, 4×LDG.128) and the offsets of request g+2S
 // are already in flight — the token stream never pauses for the probe latency, every token is read exactly once, the hashes never
-// leave the SM (per-warp shared-memory row), and a launch of K batches is one grid.
+// leave the SM, and a launch of K batches is one grid.
 //   ← compute_request_content_hashes + PositionalIndexer::find_matches + score_overlap   event_tree.rs:141-151, :461-753; cache_aware.rs:736-831
-struct FusedReq { const BatchDesc* b; uint32_t r, off, ntok; };
+//
+// The kernel is co-limited by instruction issue (ncu, first version: 578 warp instructions per request, issue-active 55 %), so the
+// common shapes take a FAST PATH that never leaves registers: a request of ≤ 32 blocks whose jump search is one jump (jump_size ≥
+// blocks − 1: BASELINE config 2) probes positions 0 and last from the two lanes that hold those hashes, and decides from two shuffled
+// slots: miss at 0 → no overlap; Single at 0 and a Single at `last` of equal cardinality (the reference's count-only jump test, :720)
+// → the position-0 set survives with score = blocks.  Everything else (a failed count test → linear drain, Multi entries, longer
+// requests, more than one jump, fleets above 64 workers) goes through the generic warp-cooperative jump_search on a per-warp
+// shared-memory row of hashes — a __noinline__ call, so its registers do not tax the fast path.
+struct FusedPos { uint32_t j, r; };   // batch index, request index inside the batch
 
-__device__ __forceinline__ FusedReq fused_fetch(const MultiArgs& a, uint32_t g) {
-    uint32_t j, r;
-    if (a.uniform_n) { j = g / a.uniform_n; r = g - j * a.uniform_n; }
-    else { j = 0; while (j + 1 < a.count && a.b[j + 1].hash_base <= g) ++j; r = g - a.b[j].hash_base; }
-    FusedReq q;
-    q.b = &a.b[j]; q.r = r;
-    q.off = __ldg(q.b->offsets + r);
-    q.ntok = __ldg(q.b->offsets + r + 1) - q.off;
-    return q;
+__device__ __forceinline__ void fused_advance(const MultiArgs& a, FusedPos& p, uint32_t by) {
+    p.r += by;
+    while (p.j < a.count && p.r >= a.b[p.j].n) { p.r -= a.b[p.j].n; ++p.j; }
 }
-// block `lane` of the request (the only block of a lane when the request has ≤ 32 blocks): loads issued, not consumed
-__device__ __forceinline__ void fused_load_first(const FusedReq& q, int lane, uint32_t (&w)[16]) {
-    if ((uint32_t)lane < q.ntok / 16) {
-        const uint32_t* p = q.b->tokens + q.off + (size_t)lane * 16;
-        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-            const uint4* q4 = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { uint4 t = __ldg(q4 + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = __ldg(p + i);
+struct SlowResult { uint64_t winset; uint32_t score; };
+// generic search on the shared-memory hash row; returns the eligible set the argmax runs over (survivors, else the latest eligible drained set)
+template <bool W1>
+__device__ __noinline__ SlowResult fused_slow_search(const EventIndexView* vp, const uint64_t* ch, int nb, int lane, uint64_t elig) {
+    const EventIndexView v = *vp;
+    SelectSink<W1> sink{elig, 0, 0};
+    const uint64_t surv = jump_search<W1>(v, ch, nb, lane, sink, false) & elig;
+    SlowResult r;
+    if (set_any<W1>(surv)) { r.winset = surv; r.score = (uint32_t)nb; }
+    else { r.winset = sink.last; r.score = sink.last_score; }
+    return r;
+}
+
+// L2 prefetch of a request's token range, two pipeline stages ahead of its use: PF = 1 one bulk prefetch per request issued by lane 0
+// (cp.async.bulk.prefetch.L2 → UBLKPF.L2: the TMA unit walks the range, no register, no scoreboard), PF = 2 one CCTL.PF2 per lane
+// (its own 64 B block), PF = 0 none.  The tokens are then read from L2 one iteration later, so a warp never holds a second request's
+// tokens in registers while it works (the first version did, and the 16 extra live registers spilled around the slow-path call).
+template <int PF>
+__device__ __forceinline__ void fused_prefetch(const uint32_t* __restrict__ tokens, uint32_t off, uint32_t ntok, int lane) {
+    if (PF == 1) {
+        if (lane == 0 && ntok >= 16) {
+            const uintptr_t lo = reinterpret_cast<uintptr_t>(tokens + off) & ~(uintptr_t)15;
+            const uintptr_t hi = (reinterpret_cast<uintptr_t>(tokens + off + (ntok & ~15u)) + 15) & ~(uintptr_t)15;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
         }
+    } else if (PF == 2) {
+        for (uint32_t blk = lane; blk < (ntok >> 4); blk += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(tokens + off + (size_t)blk * 16));
     }
 }
 
-template <bool W1, int BS, int MINB>
-__global__ void __launch_bounds__(256, MINB) event_fused_kernel(EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+template <bool W1, int BS, int MINB, int PF>
+__global__ void __launch_bounds__(256, MINB) event_fused_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
     extern __shared__ uint64_t smem_ch[];
     __shared__ int32_t s_slice[64];
     __shared__ uint64_t s_load[64], s_ts[64];
+    __shared__ uint32_t s_park[8][16];
     if (W1 && threadIdx.x < 64) {
         bool ok = threadIdx.x < v.n_workers;
         s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
@@ -560,72 +578,130 @@ __global__ void __launch_bounds__(256, MINB) event_fused_kernel(EventIndexView v
     __syncthreads();
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
-    const FleetDerived fd = *f.derived;
+    const uint32_t n_healthy = f.derived->n_healthy, imbalanced = f.derived->imbalanced;
+    const int32_t min_load_idx = f.derived->min_load_idx;
     const uint64_t elig = W1 ? f.elig[0] : ((uint32_t)lane < v.words ? f.elig[lane] : 0ULL);
-    const uint32_t total = a.total, S = gridDim.x * wpc;
-    uint32_t g = blockIdx.x * wpc + wic;
-    if (g >= total) return;
+    const uint32_t S = gridDim.x * wpc;
     const uint32_t bs = BS ? (uint32_t)BS : a.block_size;
 
-    FusedReq q0 = fused_fetch(a, g), q1 = q0;
-    if (g + S < total) q1 = fused_fetch(a, g + S);
-    uint32_t w0[16];
-    if (BS == 16) fused_load_first(q0, lane, w0);
-    for (; g < total; g += S) {
-        uint32_t w1[16];
-        if (BS == 16 && g + S < total) fused_load_first(q1, lane, w1);
-        FusedReq q2 = q1;
-        if (g + 2 * S < total) q2 = fused_fetch(a, g + 2 * S);
+    // pipeline stages: A = request being processed, B = its successor (tokens already prefetched into L2), C = prefetched now, D = offsets loaded now
+    FusedPos pA{0, 0};
+    fused_advance(a, pA, blockIdx.x * wpc + wic);
+    FusedPos pB = pA; fused_advance(a, pB, S);
+    FusedPos pC = pB; fused_advance(a, pC, S);
+    FusedPos pD = pC; fused_advance(a, pD, S);
+    uint32_t offA = 0, endA = 0, offB = 0, endB = 0, offC = 0, endC = 0, offD = 0, endD = 0;
+    if (pA.j < a.count) { offA = __ldg(a.b[pA.j].offsets + pA.r); endA = __ldg(a.b[pA.j].offsets + pA.r + 1); }
+    if (pB.j < a.count) { offB = __ldg(a.b[pB.j].offsets + pB.r); endB = __ldg(a.b[pB.j].offsets + pB.r + 1); }
+    if (pC.j < a.count) { offC = __ldg(a.b[pC.j].offsets + pC.r); endC = __ldg(a.b[pC.j].offsets + pC.r + 1); }
+    if (PF && BS == 16 && pB.j < a.count) fused_prefetch<PF>(a.b[pB.j].tokens, offB, endB - offB, lane);
 
-        // ---- request g ----
-        const BatchDesc& b = *q0.b;
+#pragma unroll 1
+    while (pA.j < a.count) {
+        if (PF && BS == 16 && pC.j < a.count) fused_prefetch<PF>(a.b[pC.j].tokens, offC, endC - offC, lane);
+        if (pD.j < a.count) { offD = __ldg(a.b[pD.j].offsets + pD.r); endD = __ldg(a.b[pD.j].offsets + pD.r + 1); }
+
+        // ---- request A ----
+        const BatchDesc& b = a.b[pA.j];
+        uint32_t ntok = endA - offA;
         const bool cand_mode = b.cand != nullptr;
         int32_t out = -1;
         uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
         Cand best{false, 0, 0, -1};
-        if (!cand_mode && fd.n_healthy == 0) {
-        } else if (!cand_mode && fd.imbalanced) {
-            out = fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
+        if (!cand_mode && n_healthy == 0) {
+        } else if (!cand_mode && imbalanced) {
+            out = min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
         } else {
-            const uint32_t nb = bs ? q0.ntok / bs : 0;
+            const uint32_t nb = bs ? ntok / bs : 0;
             if (nb > a.max_blocks) { if (lane == 0) atomicExch(a.err_flag, 1u); branch = 255; }
             else {
                 uint64_t winset = 0;
                 uint32_t score = 0;
                 if (nb > 0 && v.n_workers > 0) {
-                    if (BS == 16) {
-                        if ((uint32_t)lane < nb) ch[lane] = xxh3_16words(w0, kSeed);
-                        for (uint32_t blk = lane + 32; blk < nb; blk += 32) ch[blk] = hash_block<16>(b.tokens + q0.off + (size_t)blk * 16, 16);
-                    } else {
-                        for (uint32_t blk = lane; blk < nb; blk += 32) ch[blk] = hash_block<0>(b.tokens + q0.off + (size_t)blk * bs, bs);
+                    uint64_t h = 0;
+                    if (BS == 16) { if ((uint32_t)lane < nb) h = hash_block<16>(b.tokens + offA + (size_t)lane * 16, 16); }
+                    bool slow = true;
+                    if (W1 && BS == 16 && nb <= 32 && nb - 1 <= v.jump) {
+                        // fast path: destinations are exactly {0, last}; lane p holds the hash of block p
+                        const int last = (int)nb - 1;
+                        Slot sl{0, 0, SLOT_EMPTY, 0, 0};
+                        bool found = false;
+                        if (lane == 0 || lane == last) found = probe(v, (uint32_t)lane, h, sl);
+                        const bool f0 = __shfl_sync(FULL, (int)found, 0) != 0;
+                        const uint32_t st0 = __shfl_sync(FULL, sl.state, 0);
+                        if (!f0) slow = false;                                   // nothing cached at position 0: no scores (:676-683)
+                        else if (st0 == SLOT_SINGLE) {
+                            const uint64_t act = shfl64(sl.payload, 0);
+                            if (act == 0) slow = false;
+                            else if (last == 0) { slow = false; winset = act & elig; score = nb; }
+                            else {
+                                const bool fl = __shfl_sync(FULL, (int)found, last) != 0;
+                                const uint32_t stl = __shfl_sync(FULL, sl.state, last);
+                                const uint64_t pl = shfl64(sl.payload, last);
+                                if (fl && stl == SLOT_SINGLE && __popcll(pl) == __popcll(act)) { slow = false; winset = act & elig; score = nb; }   // count-only jump test (:720)
+                            }
+                        }
                     }
-                    __syncwarp();
-                    SelectSink<W1> sink{elig, 0, 0};
-                    uint64_t surv = jump_search<W1>(v, ch, (int)nb, lane, sink, false) & elig;
-                    if (set_any<W1>(surv)) { winset = surv; score = nb; }
-                    else { winset = sink.last; score = sink.last_score; }
-                    __syncwarp();
+                    if (slow) {
+                        if (BS == 16) {
+                            if ((uint32_t)lane < nb) ch[lane] = h;
+                            for (uint32_t blk = lane + 32; blk < nb; blk += 32) ch[blk] = hash_block<16>(b.tokens + offA + (size_t)blk * 16, 16);
+                        } else {
+                            for (uint32_t blk = lane; blk < nb; blk += 32) ch[blk] = hash_block<0>(b.tokens + offA + (size_t)blk * bs, bs);
+                        }
+                        // The generic search is a real call: whatever is live across it would have to sit in the few callee-saved registers, and
+                        // ptxas answers by keeping the whole pipeline state in local memory for EVERY iteration.  The state is warp-uniform, so it
+                        // is parked in 64 B of shared memory around the call instead — the common path keeps it in registers.
+                        if (lane == 0) {
+                            volatile uint32_t* pk = s_park[wic];
+                            pk[0] = pA.j; pk[1] = pA.r; pk[2] = pB.j; pk[3] = pB.r; pk[4] = pC.j; pk[5] = pC.r; pk[6] = pD.j; pk[7] = pD.r;
+                            pk[8] = offB; pk[9] = endB; pk[10] = offC; pk[11] = endC; pk[12] = offD; pk[13] = endD; pk[14] = ntok;
+                        }
+                        __syncwarp();
+                        const SlowResult sr = fused_slow_search<W1>(&v, ch, (int)nb, lane, elig);
+                        winset = sr.winset; score = sr.score;
+                        __syncwarp();
+                        {
+                            const volatile uint32_t* pk = s_park[wic];
+                            pA.j = pk[0]; pA.r = pk[1]; pB.j = pk[2]; pB.r = pk[3]; pC.j = pk[4]; pC.r = pk[5]; pD.j = pk[6]; pD.r = pk[7];
+                            offB = pk[8]; endB = pk[9]; offC = pk[10]; endC = pk[11]; offD = pk[12]; endD = pk[13]; ntok = pk[14];
+                        }
+                    }
                 }
                 if (set_any<W1>(winset)) {
                     if (W1) {
                         uint64_t w = winset;
+                        const int id0 = __ffsll((long long)w) - 1;
+                        w &= w - 1;
+                        best.have = true; best.sl = s_slice[id0]; best.ld = s_load[id0]; best.ts = s_ts[id0];
                         while (w) { int id = __ffsll((long long)w) - 1; w &= w - 1; best.consider(s_slice[id], s_load[id], s_ts[id]); }
                     } else best = warp_arg_best(v, f, winset, lane);
                     out = best.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
-                } else { out = fd.min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD; }
+                } else { out = min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD; }
             }
         }
         if (lane == 0) {
             if (cand_mode) {
                 smgx_shard_candidate sc;
                 sc.score = best.have ? matched : 0; sc.local_idx = best.have ? (uint32_t)best.sl : 0xFFFFFFFFu; sc.load = best.ld; sc.tree_size = best.ts;
-                b.cand[q0.r] = sc;
-            } else write_pick(b, q0.r, out, branch, matched, q0.ntok);
+                b.cand[pA.r] = sc;
+            } else write_pick(b, pA.r, out, branch, matched, ntok);
         }
-        q0 = q1; q1 = q2;
-        if (BS == 16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w0[i] = w1[i];
+        // rotate the pipeline
+        pA = pB; offA = offB; endA = endB;
+        pB = pC; offB = offC; endB = endC;
+        pC = pD; offC = offD; endC = endD;
+        fused_advance(a, pD, S);
+    }
+    if (a.done_flag) {   // mapped submission: picks were stored straight into pinned host memory — publish completion to the spinning caller
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) {
+                *a.done_counter = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.done_flag), "l"(a.done_value) : "memory");
+            }
         }
     }
 }
@@ -764,18 +840,32 @@ static int fused_minb() {
     }
     return v;
 }
+static std::atomic<int> g_fused_pf{-1};
+void set_fused_prefetch(int pf) { g_fused_pf.store(pf < 0 || pf > 2 ? 1 : pf, std::memory_order_relaxed); }
+static int fused_pf() {   // SMGX_FUSED_PF=0|1|2 (A/B runs): L2 prefetch flavour, default 1 = bulk
+    int v = g_fused_pf.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SMGX_FUSED_PF");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+        g_fused_pf.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 template <bool W1, int BS>
 static void launch_fused(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
-    auto k = fused_minb() == 3 ? event_fused_kernel<W1, BS, 3> : event_fused_kernel<W1, BS, 4>;
+    using K = void (*)(EventIndexView, FleetView, MultiArgs);
+    const int minb = fused_minb(), pf = fused_pf();
+    K k = minb == 3 ? (pf == 0 ? (K)event_fused_kernel<W1, BS, 3, 0> : pf == 2 ? (K)event_fused_kernel<W1, BS, 3, 2> : (K)event_fused_kernel<W1, BS, 3, 1>)
+                    : (pf == 0 ? (K)event_fused_kernel<W1, BS, 4, 0> : pf == 2 ? (K)event_fused_kernel<W1, BS, 4, 2> : (K)event_fused_kernel<W1, BS, 4, 1>);
     const size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
     int wpc = 8;
     while (wpc > 1 && per_warp * wpc > 64 * 1024) wpc >>= 1;
     const size_t smem = per_warp * wpc;
     if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "request too long for the per-warp scratch (max_tokens_per_request)");
     if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static thread_local int occ_cache[2][2][2][4] = {};   // [minb][W1][BS16][log2 wpc] for the common small-smem case
+    static thread_local int occ_cache[3][2][2][2][4] = {};   // [pf][minb][W1][BS16][log2 wpc] for the common small-smem case
     int occ = 0;
-    int& slot = occ_cache[fused_minb() == 3 ? 1 : 0][W1 ? 1 : 0][BS == 16 ? 1 : 0][wpc == 8 ? 3 : wpc == 4 ? 2 : wpc == 2 ? 1 : 0];
+    int& slot = occ_cache[pf][minb == 3 ? 1 : 0][W1 ? 1 : 0][BS == 16 ? 1 : 0][wpc == 8 ? 3 : wpc == 4 ? 2 : wpc == 2 ? 1 : 0];
     if (smem <= 4096 && slot) occ = slot;
     else {
         SMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));

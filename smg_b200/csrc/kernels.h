@@ -66,6 +66,11 @@ struct MultiArgs {
     uint32_t max_blocks;           // row length of the hash scratch = max blocks per request
     uint64_t* hashes;              // split path only (nullptr on the fused path)
     uint32_t* err_flag;            // device: set to 1 when a request exceeds max_blocks
+    // mapped (zero-copy) submissions: when done_flag != nullptr the last CTA to finish stores done_value there with system-scope release
+    // semantics (the flag lives in pinned host memory the caller spins on); done_counter = device word counting finished CTAs (self-resetting)
+    uint64_t* done_flag;
+    uint64_t done_value;
+    uint32_t* done_counter;
     uint32_t total;                // sum of b[k].n  (b[k].hash_base = requests before batch k)
     uint32_t uniform_n;            // every batch has this many requests (0: look the batch up through hash_base)
 };
@@ -73,6 +78,7 @@ struct MultiArgs {
 bool event_select_fused();
 void set_event_select_fused(bool fused);
 void set_fused_minb(int minb);
+void set_fused_prefetch(int pf);
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
 
 // PositionalIndexer::find_matches on precomputed content hashes; one warp, one query.

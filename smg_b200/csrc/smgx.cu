@@ -118,6 +118,8 @@ public:
             }
             d_err.reserve(64);
             SMGX_CUDA(cudaMemset(d_err.ptr, 0, 64));
+            d_done_counters.reserve(kDoneCounters * 4);
+            SMGX_CUDA(cudaMemset(d_done_counters.ptr, 0, kDoneCounters * 4));
         }
     }
     ~Policy() {
@@ -156,7 +158,7 @@ public:
             pf_stage.release(); pf_out.release();
             for (uint32_t q = 0; q < xch.peer.size(); ++q) if (q < xch.opened.size() && xch.opened[q] && xch.peer[q]) cudaIpcCloseMemHandle(xch.peer[q]);
             xch.local.release(); xch.d_bases.release(); xch.d_cand.release(); xch.d_fleet.release(); xch.d_arrive.release(); xch.d_gbase.release();
-            d_err.release(); d_flush.release(); scratch.release(); scratch2.release(); d_gbase.release();
+            d_err.release(); d_done_counters.release(); d_flush.release(); scratch.release(); scratch2.release(); d_gbase.release();
             if (state_ready) cudaEventDestroy(state_ready);
             if (ctrl) cudaStreamDestroy(ctrl);
         }
@@ -248,7 +250,8 @@ public:
     }
 
     // Enqueue the kernels of up to kMaxMultiBatches token batches on `lane` (device pointers).
-    void enqueue_batches(ModelState& m, Lane& lane, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens) {
+    void enqueue_batches(ModelState& m, Lane& lane, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens, uint64_t* done_flag = nullptr,
+                         uint64_t done_value = 0) {
         const bool cand_mode = count && descs[0].cand != nullptr;   // a worker-id shard may legitimately hold no blocks yet
         if (cand_mode && !m.indexer) throw Error(SMGX_NOT_FOUND, "no event indexer for this model");
         if (!cand_mode && !has_event_indexer(m))
@@ -270,6 +273,11 @@ public:
         a.total = (uint32_t)rows;
         a.uniform_n = uniform && count ? descs[0].n : 0;
         a.hashes = nullptr;
+        a.done_flag = done_flag; a.done_value = done_value; a.done_counter = nullptr;
+        if (done_flag) {
+            if (!event_select_fused()) throw Error(SMGX_INVALID_ARGUMENT, "mapped submissions need the fused event path");
+            a.done_counter = d_done_counters.as<uint32_t>() + (done_seq++ % kDoneCounters);
+        }
         if (!event_select_fused()) {
             lane.d_hash.reserve(std::max<uint64_t>(rows, 1) * a.max_blocks * 8);
             a.hashes = lane.d_hash.as<uint64_t>();
@@ -833,7 +841,9 @@ public:
     std::vector<Lane> lanes;
     cudaStream_t ctrl = nullptr;
     cudaEvent_t state_ready = nullptr;
-    DevBuf d_err, d_flush, scratch, scratch2, d_gbase;
+    DevBuf d_err, d_flush, scratch, scratch2, d_gbase, d_done_counters;
+    static constexpr uint32_t kDoneCounters = 256;   // completion counters of mapped submissions in flight (one per launch, reused round-robin)
+    uint64_t done_seq = 0, mapped_seq = 0;
     uint64_t launches = 0;
     uint64_t ticket_seq = 0;
 };
@@ -2145,6 +2155,30 @@ smgx_status smgx_select_batch_tokens(smgx_policy* p, const char* model_key, cons
     return smgx_wait(p, t, err);
 }
 
+// Zero-copy submission for small, latency-bound batches: the kernel reads the caller's PINNED host buffers in place over PCIe, stores the
+// picks straight back into pinned host memory and raises *done_flag = done_value when the whole batch is out — no staging copy, no
+// cudaStreamSynchronize, no ticket.  Event-driven mode only (tree modes mutate host state: use smgx_submit_tokens).
+smgx_status smgx_submit_tokens_mapped(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
+                                      uint32_t max_request_tokens, int32_t* out_worker_idx, smgx_decision_info* out_info, uint64_t* done_flag,
+                                      uint64_t done_value, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(done_flag);
+        SMGX_REQUIRE(n == 0 || (tokens && offsets && out_worker_idx), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        if (!P.has_event_indexer(m) || (P.host_imbalanced(m) && m.token_tree))
+            throw Error(SMGX_NOT_FOUND, "mapped submissions serve the event-driven mode only; this model is routed through a tree right now (use smgx_submit_tokens)");
+        if (n == 0) { *done_flag = done_value; return SMGX_SUCCESS; }
+        const uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
+        Lane& L = P.lanes[(P.mapped_seq++) % P.lanes.size()];   // any stream: nothing is staged, so a lane busy with a host-buffer submission is fine
+        BatchDesc d{tokens, offsets, out_worker_idx, out_info, n, 0, nullptr};
+        P.enqueue_batches(m, L, &d, 1, cap, done_flag, done_value);
+        return SMGX_SUCCESS;
+    });
+}
+
 smgx_status smgx_select_batch_tokens_device(smgx_policy* p, const char* model_key, uint32_t lane, const uint32_t* d_tokens,
                                             const uint32_t* d_offsets, uint32_t n, uint32_t max_request_tokens, int32_t* d_out_worker_idx,
                                             smgx_decision_info* d_out_info, char** err) {
@@ -2420,6 +2454,7 @@ void smgx_set_event_path(int fused, int min_blocks_per_sm) {
     set_event_select_fused(fused != 0);
     if (min_blocks_per_sm) set_fused_minb(min_blocks_per_sm);
 }
+void smgx_set_fused_prefetch(int flavour) { set_fused_prefetch(flavour); }
 uint64_t smgx_kernel_launches(const smgx_policy* p) { return p ? p->impl.launches : 0; }
 smgx_status smgx_flush_l2(smgx_policy* p, char** err) {
     return guard(err, [&]() {

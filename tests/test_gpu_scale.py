@@ -5,6 +5,7 @@
   * both implementations of the event-driven pick (fused one-kernel path, round-1 hash + search pair) on the randomized small cases;
   * duplicate URLs in the worker slice in event-driven mode (two slice entries share one indexer id; score_overlap scores both)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -21,8 +22,13 @@ CFG = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=
 def event_path():
     from smg_b200 import _lib
     L = _lib.load()
-    yield lambda fused, minb=0: L.smgx_set_event_path(1 if fused else 0, minb)
+    def setter(fused, minb=0, pf=-1):
+        L.smgx_set_event_path(1 if fused else 0, minb)
+        if pf >= 0:
+            L.smgx_set_fused_prefetch(pf)
+    yield setter
     L.smgx_set_event_path(1, 4)
+    L.smgx_set_fused_prefetch(1)
 
 
 def _config2(n_seq, W, T, bs, B):
@@ -47,11 +53,11 @@ def _config2(n_seq, W, T, bs, B):
     return pol, ws, ix, op, seqs
 
 
-@pytest.mark.parametrize("variant", ["fused4", "fused3", "split"])
+@pytest.mark.parametrize("variant", ["fused4", "fused3", "fused4-pf2", "fused4-pf0", "split"])
 def test_config2_full_scale_multi_launch(variant, event_path):
     import bench
     from smg_b200 import _lib
-    event_path(variant != "split", 3 if variant == "fused3" else 4)
+    event_path(variant != "split", 3 if variant == "fused3" else 4, 2 if variant.endswith("pf2") else 0 if variant.endswith("pf0") else 1)
     n_seq, W, T, bs, B, NB = 31250, 64, 512, 16, 4096, 37
     pol, ws, ix, op, seqs = _config2(n_seq, W, T, bs, B)
     assert ix.entry_count() == n_seq * (T // bs)
@@ -99,7 +105,11 @@ def test_config2_full_scale_multi_launch(variant, event_path):
 @pytest.mark.parametrize("variant", ["fused3", "split"])
 def test_random_parity_other_variants(case, variant, event_path):
     """The randomized ragged parity cases of test_gpu_event_select.py (which run the default fused path) on the other two variants."""
-    from test_gpu_event_select import test_random_select_parity
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_gpu_event_select", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_event_select.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    test_random_select_parity = mod.test_random_select_parity
     event_path(variant != "split", 3 if variant == "fused3" else 4)
     test_random_select_parity(*case)
 
