@@ -333,6 +333,16 @@ smgx_status smgx_select_batch_text(smgx_policy* p, const char* model_key, const 
  * copies the result back before returning. */
 smgx_status smgx_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets,
                                      uint32_t n, int32_t* out_worker_idx, smgx_decision_info* out_info, char** err);
+/* Batch semantics of the event-driven mode with respect to load():
+ *   off (default): every request of a batch is decided against ONE fleet snapshot (the state at submission).
+ *   on: "request i sees the snapshot plus the picks of requests < i" — after each pick the chosen worker's load is bumped before the next
+ *       request of the call is decided, which is what the reference's request stream does (one select_worker per request, then
+ *       WorkerLoadGuard::new → increment_load, routers/http/router.rs:319-321, worker/worker.rs:1067-1070): min-load picks spread over the
+ *       fleet instead of all landing on one worker, (score, load) tie-breaks read the running loads and the f32 imbalance gate is
+ *       re-evaluated per request.  Batches handed over in one smgx_select_many_tokens_device call form one stream.  The bumps are not
+ *       kept: the next call starts from the snapshot of its own smgx_set_fleet_state.  Not available with duplicate URLs in the slice,
+ *       for mapped submissions or for sharded candidates. */
+smgx_status smgx_set_load_feedback(smgx_policy* p, int enabled, char** err);
 /* Pipelined form for the host batcher: up to smgx_pipeline_depth() submissions may be in flight; each owns a stream
  * and device staging.  Buffers must stay valid (and should be pinned) until smgx_wait(ticket) returns. */
 uint32_t smgx_pipeline_depth(const smgx_policy* p);
@@ -407,6 +417,9 @@ smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
 void smgx_set_event_path(int fused, int min_blocks_per_sm);
 /* L2 prefetch flavour of the fused kernel: 0 none, 1 one bulk prefetch per request (default), 2 one prefetch per lane (SMGX_FUSED_PF). */
 void smgx_set_fused_prefetch(int flavour);
+/* Requests per warp of the tiled event kernel (8, 16 or 32; 0 = never use it) and the launch size from which it is used (requests; < 0 =
+ * the default, tile × 4 × SM count).  Environment: SMGX_FUSED_TILE. */
+void smgx_set_fused_tile(int tile, int64_t min_total);
 /* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
 uint64_t smgx_kernel_launches(const smgx_policy* p);
 /* Writes a buffer larger than L2 (bench hygiene between timed iterations). */

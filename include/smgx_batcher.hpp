@@ -44,7 +44,8 @@ public:
         uint32_t max_ring = 64;                          // the ring grows on demand up to this many batches (a caller may hold tickets of many)
         bool mapped = true;                              // zero-copy latency transport (see above); false = staged copies + tickets
         uint32_t max_inflight = 3;                       // mapped: batches on the GPU at once; arrivals beyond that join the open batch
-        std::chrono::microseconds linger{0};             // mapped: keep a non-full batch open this long after its first request (0 = ship at once)
+        std::chrono::microseconds linger{0};             // mapped: keep a non-full batch open at least this long after its first request
+        std::chrono::nanoseconds quiet{1500};            // mapped: … and until no request has joined it for this long (arrival pause)
         uint32_t max_request_tokens = 0;                 // mapped: bound on the longest request (0 = the policy's max_tokens_per_request)
     };
     struct Stats { uint64_t requests = 0, batches = 0, full_batches = 0; };
@@ -265,7 +266,8 @@ private:
     void dispatch_loop_mapped() {
         std::deque<std::pair<Batch*, uint64_t>> flying;   // (batch, generation) handed to the GPU, oldest first
         auto retire = [&] { while (!flying.empty() && __atomic_load_n(flying.front().first->done_flag, __ATOMIC_ACQUIRE) == flying.front().second) flying.pop_front(); };
-        std::chrono::steady_clock::time_point first_seen{};
+        std::chrono::steady_clock::time_point first_seen{}, last_change{};
+        uint32_t last_have = 0;
         uint64_t seen_gen = 0;
         uint32_t seen_batch = ~0u;
         uint32_t idle = 0;
@@ -278,10 +280,14 @@ private:
             bool ship = false;
             if (have) {
                 const bool full = have >= opt_.max_batch || tokens_of(r) + (opt_.max_request_tokens ? opt_.max_request_tokens : 1) > opt_.tokens_per_batch;
-                if (opt_.linger.count() > 0 && !full) {
+                if (!full) {
+                    // ship once arrivals PAUSE: callers that enqueue back to back (a task pool with many requests outstanding) keep the batch open
+                    // and it grows towards max_batch; a burst of blocking callers is complete within a microsecond or two and leaves at once
                     const uint64_t g = ob->gen.load(std::memory_order_relaxed);
-                    if (seen_batch != oi || seen_gen != g) { seen_batch = oi; seen_gen = g; first_seen = std::chrono::steady_clock::now(); }
-                    ship = std::chrono::steady_clock::now() - first_seen >= opt_.linger;
+                    const auto now = std::chrono::steady_clock::now();
+                    if (seen_batch != oi || seen_gen != g) { seen_batch = oi; seen_gen = g; first_seen = now; last_have = 0; }
+                    if (have != last_have) { last_have = have; last_change = now; }
+                    ship = now - last_change >= opt_.quiet && now - first_seen >= opt_.linger;
                 } else ship = true;
                 if (ship && flying.size() >= opt_.max_inflight && !full) ship = false;   // GPU busy: let the batch grow (group commit)
                 if (ship && flying.size() >= 2 * (size_t)opt_.max_inflight) ship = false; // even full batches queue only so deep

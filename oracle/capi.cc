@@ -269,6 +269,26 @@ double orc_policy_select_batch_tokens_snapshot(void* h, const uint32_t* tokens, 
     b->pol.end_snapshot_batch();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+// The request STREAM as the reference router sees it: after every pick the router takes a WorkerLoadGuard on the chosen worker
+// (routers/http/router.rs:319-321, gated on policy.name() == "cache_aware"; worker/worker.rs:1067-1070 increment_load), so request i+1
+// reads load()+1 there.  Requests are routed one after another, each pick bumping its worker's load; no request completes inside the
+// batch.  The box's own fleet vector is left untouched (the bumps live in a copy); out_loads (nullable) receives the loads after the batch.
+double orc_policy_select_batch_tokens_feedback(void* h, const uint32_t* tokens, const uint64_t* offsets, size_t n, int32_t* out_idx,
+                                               uint8_t* out_branch, uint32_t* out_matched, uint64_t* out_loads) {
+    auto* b = (PolicyBox*)h;
+    std::vector<Worker> ws = b->workers;
+    auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < n; ++i) {
+        Decision d = b->pol.select_worker(ws, nullptr, tokens + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), true);
+        out_idx[i] = (int32_t)d.idx;
+        if (out_branch) out_branch[i] = (uint8_t)d.branch;
+        if (out_matched) out_matched[i] = (uint32_t)d.matched;
+        if (d.idx >= 0) ++ws[(size_t)d.idx].load;
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (out_loads) for (size_t i = 0; i < ws.size(); ++i) out_loads[i] = ws[i].load;
+    return secs;
+}
 // Batch of text requests (HTTP routing, cache_aware.rs:907-974): ragged UTF-8, offsets[n+1]; snapshot != 0 → snapshot batch.
 double orc_policy_select_batch_text(void* h, const char* text, const uint64_t* offsets, size_t n, int snapshot, int32_t* out_idx,
                                     uint8_t* out_branch, uint32_t* out_matched, uint32_t* out_input) {

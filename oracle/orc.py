@@ -92,6 +92,7 @@ def lib():
         sig("orc_hash_token_path", C.c_uint64, vp, sz)
         sig("orc_policy_hash_index", sz, vp, cp, C.c_int, vp, sz)
         sig("orc_policy_select_steps_mt", C.c_double, vp, vp, vp, sz, sz, sz, vp, C.c_int, C.c_int)
+        sig("orc_policy_select_batch_tokens_feedback", C.c_double, vp, vp, vp, sz, vp, vp, vp, vp)
         sig("orc_tuned_select_steps_mt", C.c_double, vp, vp, C.c_float, C.c_uint64, sz, vp, vp, sz, sz, sz, vp, C.c_int)
         sig("orc_policy_apply_known_remote_insert", C.c_int, vp, cp, C.c_int, u64, cp)
         sig("orc_policy_apply_repair_entry", None, vp, cp, C.c_int, vp, sz, cp)
@@ -552,6 +553,16 @@ class CacheAwarePolicy:
         idx = np.zeros(n, np.int32)
         secs = lib().orc_policy_select_steps_mt(self.h, TP, OP, len(batches), n, steps, _ptr(idx), threads, 1 if step_barrier else 0)
         return idx, secs
+
+    def select_batch_tokens_feedback(self, tokens, offsets):
+        """The request stream with the router's WorkerLoadGuard (router.rs:319-321): each pick bumps its worker's load before the next
+        request is routed.  → (idx, branch, matched, loads after the batch)."""
+        tk, off = _u32(tokens), _u64(offsets)
+        n = off.size - 1
+        idx, br, ma = np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        loads = np.zeros(max(self.n, 1), np.uint64)
+        lib().orc_policy_select_batch_tokens_feedback(self.h, _ptr(tk), _ptr(off), n, _ptr(idx), _ptr(br), _ptr(ma), _ptr(loads))
+        return idx, br, ma, loads[: self.n]
 
     def tuned_select_steps_mt(self, indexer, batches, steps, threads, rel_thr, abs_thr, block_size):
         """The "port-tuned" variant (oracle/tuned_event.h): same event-mode decisions from a flat bitset index built from `indexer`,

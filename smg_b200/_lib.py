@@ -134,6 +134,7 @@ def load():
     sig("smgx_tokenize_batch", st, vp, cp, vp, vp, u32, vp, vp, u32, pp)
     sig("smgx_select_batch_text", st, vp, cp, vp, vp, u32, vp, vp, vp, vp, u32, pp)
     sig("smgx_select_batch_tokens", st, vp, cp, vp, vp, u32, vp, vp, pp)
+    sig("smgx_set_load_feedback", st, vp, C.c_int, pp)
     sig("smgx_pipeline_depth", u32, vp)
     sig("smgx_submit_tokens", st, vp, cp, vp, vp, u32, vp, vp, P(u64), pp)
     sig("smgx_wait", st, vp, u64, pp)
@@ -157,6 +158,7 @@ def load():
     sig("smgx_timer_stop_all_ms", st, vp, P(C.c_float), pp)
     sig("smgx_set_event_path", None, C.c_int, C.c_int)
     sig("smgx_set_fused_prefetch", None, C.c_int)
+    sig("smgx_set_fused_tile", None, C.c_int, C.c_int64)
     sig("smgx_kernel_launches", u64, vp)
     sig("smgx_flush_l2", st, vp, pp)
     _lib = L

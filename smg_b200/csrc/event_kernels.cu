@@ -546,6 +546,145 @@ __device__ __noinline__ SlowResult fused_slow_search(const EventIndexView* vp, c
     return r;
 }
 
+// ---- the same pick, TILED: one warp routes TILE consecutive requests of a batch -------------------------------------------------
+// ncu on the warp-per-request kernel above: 440 warp instructions per request of which only ≈ 110 are the XXH3 arithmetic — pipeline
+// bookkeeping, descriptor fetches, probe/shuffle/pick logic and the store are paid once per REQUEST by a whole warp, and the kernel is
+// issue-bound (issue-active 52 %, DRAM 40 %).  Here those costs are paid once per TILE:
+//   phase 1  lane L fetches the offsets of request r0+L (one coalesced load for the tile); then, request by request, the warp streams the
+//            2 KB of tokens (lane = block, the next request's 4×LDG.128 issued before the current one is hashed) and leaves the 32 content
+//            hashes in a shared-memory row — ≈ 130 warp instructions per request, 106 of them hashing;
+//   phase 2  lane L owns request r0+L: both jump destinations (positions 0 and last) probed by every lane at once — 2·TILE independent
+//            32 B probes in flight per warp — count-only jump test, argmax, one coalesced store of the picks: ≈ 100 instructions per TILE;
+//   phase 3  requests whose count test failed (stored prefix shorter than the request, Multi entries) are resolved one after another by
+//            the generic warp-cooperative jump_search on their shared-memory row.
+// Requirements (checked by the launcher, otherwise the warp-per-request kernel runs): ≤ 64 interned workers, block size 16, requests of
+// ≤ 32 blocks with jump_size ≥ 31 (one jump), batches of equal size, plain picks (no shard candidates / load feedback).
+// 16 B-aligned 64 B block of lane `lane` (loads issued, not consumed)
+__device__ __forceinline__ void tile_load(const uint32_t* __restrict__ tokens, uint32_t off, uint32_t nb, int lane, uint32_t (&w)[16]) {
+    if ((uint32_t)lane < nb) {
+        const uint4* q4 = reinterpret_cast<const uint4*>(tokens + off + (size_t)lane * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { uint4 t = __ldg(q4 + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
+    }
+}
+
+template <int TILE, int MINB>
+__global__ void __launch_bounds__(128, MINB) event_tile_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    extern __shared__ uint64_t smem_ch[];   // [warps][TILE][32]
+    __shared__ int32_t s_slice[64];
+    __shared__ uint64_t s_load[64], s_ts[64];
+    if (threadIdx.x < 64) {
+        bool ok = threadIdx.x < v.n_workers;
+        s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint64_t* ch = smem_ch + (size_t)wic * TILE * 32;
+    const uint32_t n_healthy = f.derived->n_healthy, imbalanced = f.derived->imbalanced;
+    const int32_t min_load_idx = f.derived->min_load_idx;
+    const uint64_t elig = f.elig[0];
+    const uint32_t n = a.uniform_n;
+    const uint32_t tpb = (n + TILE - 1) / TILE, n_tiles = tpb * a.count;
+    const uint32_t stride = gridDim.x * wpc;
+
+#pragma unroll 1
+    for (uint32_t t = blockIdx.x * wpc + wic; t < n_tiles; t += stride) {
+        const uint32_t j = t / tpb, r0 = (t - j * tpb) * TILE;
+        const BatchDesc& b = a.b[j];
+        const uint32_t cnt = min((uint32_t)TILE, n - r0);
+        uint32_t off = 0, ntok = 0;
+        if ((uint32_t)lane < cnt) { off = __ldg(b.offsets + r0 + lane); ntok = __ldg(b.offsets + r0 + lane + 1) - off; }
+        uint32_t nb = ntok >> 4;
+        const bool too_long = nb > a.max_blocks;
+        if (too_long) { nb = 0; atomicExch(a.err_flag, 1u); }
+        const bool trivial = n_healthy == 0 || imbalanced;   // no index involvement: None / first min load (cache_aware.rs:653-655, :670)
+
+        // ---- phase 1: hash the tile, request by request (lane = block), next request's loads in flight while this one is hashed ----
+        if (!trivial) {
+            // 16 B alignment of every request of the tile (warp-uniform): the pipelined loop issues LDG.128 only
+            const bool aligned = (reinterpret_cast<uintptr_t>(b.tokens) & 15) == 0 && !__any_sync(FULL, (uint32_t)lane < cnt && (off & 3) != 0);
+            if (aligned) {
+                uint32_t w0[16], w1[16];
+                uint32_t off_i = __shfl_sync(FULL, off, 0), nb_i = __shfl_sync(FULL, nb, 0);
+                tile_load(b.tokens, off_i, nb_i, lane, w0);
+#pragma unroll 1
+                for (uint32_t i = 0; i < cnt; i += 2) {
+                    // request i (tokens in w0); issue request i+1 into w1 first
+                    const uint32_t off_1 = __shfl_sync(FULL, off, (int)(i + 1) & 31), nb_1 = (i + 1 < cnt) ? __shfl_sync(FULL, nb, (int)(i + 1) & 31) : 0;
+                    tile_load(b.tokens, off_1, nb_1, lane, w1);
+                    if ((uint32_t)lane < nb_i) ch[i * 32 + lane] = xxh3_16words(w0, kSeed);
+                    // request i+1 (tokens in w1); issue request i+2 into w0 first
+                    const uint32_t off_2 = __shfl_sync(FULL, off, (int)(i + 2) & 31), nb_2 = (i + 2 < cnt) ? __shfl_sync(FULL, nb, (int)(i + 2) & 31) : 0;
+                    tile_load(b.tokens, off_2, nb_2, lane, w0);
+                    if ((uint32_t)lane < nb_1) ch[(i + 1) * 32 + lane] = xxh3_16words(w1, kSeed);
+                    nb_i = nb_2;
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    const uint32_t off_i = __shfl_sync(FULL, off, (int)i), nb_i = __shfl_sync(FULL, nb, (int)i);
+                    if ((uint32_t)lane < nb_i) ch[i * 32 + lane] = hash_block<16>(b.tokens + off_i + (size_t)lane * 16, 16);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- phase 2: lane L decides request r0 + L ----
+        int32_t out = -1;
+        uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+        bool slow = false;
+        const bool mine = (uint32_t)lane < cnt;
+        if (mine) {
+            if (n_healthy == 0) {
+            } else if (imbalanced) { out = min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD; }
+            else if (too_long) { branch = 255; }
+            else {
+                out = min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD;   // until an overlap is found
+                if (nb > 0 && v.n_workers > 0) {
+                    const int last = (int)nb - 1;
+                    const uint64_t c0 = ch[lane * 32], c1 = ch[lane * 32 + last];
+                    const uint32_t h0 = slot_hash(0, c0) & v.mask, h1 = slot_hash((uint32_t)last, c1) & v.mask;
+                    Slot s0 = load_slot(v.slots + h0), s1 = load_slot(v.slots + h1);          // both probes in flight together
+                    uint64_t win = 0;
+                    if (finish_probe(v, 0, c0, h0, s0)) {
+                        if (s0.state != SLOT_SINGLE) slow = true;
+                        else if (s0.payload != 0) {
+                            if (last == 0) win = s0.payload & elig;
+                            else if (finish_probe(v, (uint32_t)last, c1, h1, s1) && s1.state == SLOT_SINGLE && __popcll(s1.payload) == __popcll(s0.payload)) win = s0.payload & elig;
+                            else slow = true;   // count test failed (or a Multi entry): the generic search decides
+                        }
+                    }
+                    if (win) {
+                        Cand c{false, 0, 0, -1};
+                        while (win) { int id = __ffsll((long long)win) - 1; win &= win - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
+                        out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = nb;
+                    }
+                }
+            }
+        }
+        // ---- phase 3: the tile's slow requests, one after another, warp-cooperatively ----
+        unsigned sm = __ballot_sync(FULL, slow);
+        while (sm) {
+            const int L = __ffs((int)sm) - 1;
+            sm &= sm - 1;
+            const int nb_L = (int)__shfl_sync(FULL, nb, L);
+            const SlowResult sr = fused_slow_search<true>(&v, ch + L * 32, nb_L, lane, elig);
+            if (lane == L) {
+                uint64_t win = sr.winset;
+                if (win) {
+                    Cand c{false, 0, 0, -1};
+                    while (win) { int id = __ffsll((long long)win) - 1; win &= win - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
+                    out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = sr.score;
+                }
+            }
+        }
+        if (mine) write_pick(b, r0 + lane, out, branch, matched, ntok);
+        __syncwarp();   // the shared-memory rows are reused by the next tile
+    }
+}
+
 // L2 prefetch of a request's token range, two pipeline stages ahead of its use: PF = 1 one bulk prefetch per request issued by lane 0
 // (cp.async.bulk.prefetch.L2 → UBLKPF.L2: the TMA unit walks the range, no register, no scoreboard), PF = 2 one CCTL.PF2 per lane
 // (its own 64 B block), PF = 0 none.  The tokens are then read from L2 one iteration later, so a warp never holds a second request's
@@ -608,12 +747,21 @@ __global__ void __launch_bounds__(256, MINB) event_fused_kernel(const __grid_con
         int32_t out = -1;
         uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
         Cand best{false, 0, 0, -1};
+        const bool fb = a.fb_winsets != nullptr && !cand_mode;   // load feedback: emit (tied set, score), the in-order pass picks
         if (!cand_mode && n_healthy == 0) {
-        } else if (!cand_mode && imbalanced) {
+        } else if (!fb && !cand_mode && imbalanced) {
             out = min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD;
         } else {
             const uint32_t nb = bs ? ntok / bs : 0;
-            if (nb > a.max_blocks) { if (lane == 0) atomicExch(a.err_flag, 1u); branch = 255; }
+            if (nb > a.max_blocks) {
+                if (lane == 0) atomicExch(a.err_flag, 1u);
+                branch = 255;
+                if (fb) {
+                    const size_t gi = (size_t)b.hash_base + pA.r;
+                    if ((uint32_t)lane < v.words) a.fb_winsets[gi * v.words + lane] = 0;
+                    if (lane == 0) a.fb_scores[gi] = 0xFFFFFFFFu;
+                }
+            }
             else {
                 uint64_t winset = 0;
                 uint32_t score = 0;
@@ -668,7 +816,12 @@ __global__ void __launch_bounds__(256, MINB) event_fused_kernel(const __grid_con
                         }
                     }
                 }
-                if (set_any<W1>(winset)) {
+                if (fb) {
+                    const size_t gi = (size_t)b.hash_base + pA.r;
+                    if (W1) { if (lane == 0) a.fb_winsets[gi] = winset; }
+                    else if ((uint32_t)lane < v.words) a.fb_winsets[gi * v.words + lane] = winset;
+                    if (lane == 0) a.fb_scores[gi] = score;
+                } else if (set_any<W1>(winset)) {
                     if (W1) {
                         uint64_t w = winset;
                         const int id0 = __ffsll((long long)w) - 1;
@@ -685,7 +838,7 @@ __global__ void __launch_bounds__(256, MINB) event_fused_kernel(const __grid_con
                 smgx_shard_candidate sc;
                 sc.score = best.have ? matched : 0; sc.local_idx = best.have ? (uint32_t)best.sl : 0xFFFFFFFFu; sc.load = best.ld; sc.tree_size = best.ts;
                 b.cand[pA.r] = sc;
-            } else write_pick(b, pA.r, out, branch, matched, ntok);
+            } else if (!fb || n_healthy == 0) write_pick(b, pA.r, out, branch, matched, ntok);
         }
         // rotate the pipeline
         pA = pB; offA = offB; endA = endB;
@@ -851,6 +1004,38 @@ static int fused_pf() {   // SMGX_FUSED_PF=0|1|2 (A/B runs): L2 prefetch flavour
     }
     return v;
 }
+static std::atomic<int> g_tile{-1};
+static std::atomic<long long> g_tile_min_total{-1};   // < 0: tile × 4 × SMs (enough tiles to fill the GPU a few times over)
+void set_fused_tile(int tile, long long min_total) {
+    g_tile.store((tile == 0 || tile == 8 || tile == 16 || tile == 32) ? tile : 16, std::memory_order_relaxed);
+    g_tile_min_total.store(min_total, std::memory_order_relaxed);
+}
+static int fused_tile() {   // SMGX_FUSED_TILE=0|8|16|32: requests per warp of the tiled kernel (0 = always the warp-per-request kernel)
+    int v = g_tile.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SMGX_FUSED_TILE");
+        v = e ? atoi(e) : 16;
+        if (v != 0 && v != 8 && v != 16 && v != 32) v = 16;
+        g_tile.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+template <int TILE>
+static void launch_tile(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
+    using K = void (*)(EventIndexView, FleetView, MultiArgs);
+    const int minb = fused_minb();
+    K k = minb == 3 ? (K)event_tile_kernel<TILE, 4> : (K)event_tile_kernel<TILE, 5>;
+    const int wpc = 4;
+    const size_t smem = (size_t)wpc * TILE * 32 * 8;
+    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static thread_local int occ_cache[2] = {0, 0};
+    int& occ = occ_cache[minb == 3 ? 1 : 0];
+    if (!occ) SMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
+    const unsigned n_tiles = ((a.uniform_n + TILE - 1) / TILE) * a.count;
+    const unsigned persistent = (unsigned)sm_count * (unsigned)std::max(occ, 1);
+    k<<<std::max(1u, std::min(persistent, (n_tiles + wpc - 1) / wpc)), wpc * 32, smem, stream>>>(ix, fleet, a);
+}
+
 template <bool W1, int BS>
 static void launch_fused(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
     using K = void (*)(EventIndexView, FleetView, MultiArgs);
@@ -883,6 +1068,21 @@ void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const
     if (max_n == 0) return;
     if (event_select_fused()) {
         const bool w1 = ix.words == 1;
+        const int tile = fused_tile();
+        // the tiled kernel: one warp per TILE requests (see event_tile_kernel); needs uniform single-jump requests and enough tiles to fill the GPU
+        if (tile && w1 && a.block_size == 16 && a.max_blocks <= 32 && ix.jump + 1 >= a.max_blocks && a.uniform_n && !a.b[0].cand && !a.fb_winsets && !a.done_flag &&
+            (long long)a.total >= (g_tile_min_total.load(std::memory_order_relaxed) >= 0 ? g_tile_min_total.load(std::memory_order_relaxed) : (long long)tile * 4 * sm_count)) {
+            bool plain = true;
+            for (uint32_t j = 0; j < a.count; ++j) plain = plain && a.b[j].cand == nullptr;
+            if (plain) {
+                if (tile == 8) launch_tile<8>(ix, fleet, a, sm_count, stream);
+                else if (tile == 32) launch_tile<32>(ix, fleet, a, sm_count, stream);
+                else launch_tile<16>(ix, fleet, a, sm_count, stream);
+                SMGX_CUDA(cudaGetLastError());
+                ++*launches;
+                return;
+            }
+        }
         if (a.block_size == 16) { if (w1) launch_fused<true, 16>(ix, fleet, a, sm_count, stream); else launch_fused<false, 16>(ix, fleet, a, sm_count, stream); }
         else { if (w1) launch_fused<true, 0>(ix, fleet, a, sm_count, stream); else launch_fused<false, 0>(ix, fleet, a, sm_count, stream); }
         SMGX_CUDA(cudaGetLastError());
@@ -912,6 +1112,96 @@ void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const
     }
     SMGX_CUDA(cudaGetLastError());
     ++*launches;
+}
+
+namespace {
+// ---- load-feedback mode, phase 2: the request STREAM with the router's WorkerLoadGuard --------------------------------------------
+// In the reference every request is routed by its own select_worker call and the router bumps the chosen worker's load() right after
+// (routers/http/router.rs:319-321 → worker.rs:1067-1070), so request i+1 sees request i's increment: min-load picks spread over the
+// fleet (water-filling), overlap ties re-read the running loads and the f32 imbalance gate is re-evaluated per request.  One warp walks
+// the a.total requests in order.  Everything that does not depend on loads was done by the fused kernel (per request: the eligible
+// workers tied on the best overlap score).  Running state: loads per slice entry in shared memory, global min / max over ALL workers
+// (cache_aware.rs:662-666) with the number of workers at the minimum — a +1 bump changes them in O(1) except when the last worker leaves
+// the minimum — and the first healthy argmin, rescanned by the warp only after it was itself picked.
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { uint64_t o = shfl64_xor(v, d); v = o < v ? o : v; }
+    return v;
+}
+__global__ void __launch_bounds__(32) feedback_resolve_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a,
+                                                              const uint64_t* __restrict__ loads0, const uint8_t* __restrict__ flags, uint32_t n_slice,
+                                                              uint64_t abs_thr, float rel_thr, uint64_t* loads_out) {
+    extern __shared__ uint64_t s_L[];   // [n_slice]
+    const int lane = threadIdx.x;
+    const uint32_t n_healthy = f.derived->n_healthy;
+    for (uint32_t i = lane; i < n_slice; i += 32) s_L[i] = loads0[i];
+    __syncwarp();
+    uint64_t gmin = f.derived->min_load, gmax = f.derived->max_load, hmin = f.derived->min_healthy_load;
+    int32_t hidx = f.derived->min_load_idx;
+    auto count_at = [&](uint64_t val) { uint32_t c = 0; for (uint32_t i = lane; i < n_slice; i += 32) c += s_L[i] == val; return __reduce_add_sync(FULL, c); };
+    uint32_t cnt_gmin = n_slice ? count_at(gmin) : 0;
+    auto rescan_healthy = [&]() {   // first argmin load over healthy (min_by_key → FIRST minimum)
+        uint64_t m = ~0ULL;
+        for (uint32_t i = lane; i < n_slice; i += 32) if ((flags[i] & 3) == 3 && s_L[i] < m) m = s_L[i];
+        m = warp_min_u64(m);
+        uint32_t first = 0xFFFFFFFFu;
+        for (uint32_t i = lane; i < n_slice; i += 32) if ((flags[i] & 3) == 3 && s_L[i] == m) { first = i; break; }
+        first = __reduce_min_sync(FULL, first);
+        hmin = m; hidx = (int32_t)first;
+    };
+    uint32_t g = 0;
+    for (uint32_t j = 0; j < a.count; ++j) {
+        const BatchDesc& b = a.b[j];
+        for (uint32_t r = 0; r < b.n; ++r, ++g) {
+            int32_t out = -1;
+            uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+            const uint32_t score = a.fb_scores[g];
+            if (n_healthy == 0) continue;               // the fused kernel already wrote None for these
+            if (score == 0xFFFFFFFFu) { branch = 255; }
+            else {
+                const bool imbalanced = (gmax - gmin) > abs_thr && __ull2float_rn(gmax) > __fmul_rn(__ull2float_rn(gmin), rel_thr);
+                if (imbalanced) { out = hidx; branch = SMGX_BR_IMBALANCED_MIN_LOAD; }
+                else {
+                    Cand c{false, 0, 0, -1};
+                    for (uint32_t w = 0; w < v.words; ++w) {
+                        uint64_t bits = a.fb_winsets[(size_t)g * v.words + w];
+                        while (bits) {
+                            const uint32_t id = w * 64 + (uint32_t)(__ffsll((long long)bits) - 1);
+                            bits &= bits - 1;
+                            const int32_t sl = f.slice_of_id[id];
+                            if (sl >= 0) c.consider(sl, s_L[sl], v.tree_sizes[id]);
+                        }
+                    }
+                    if (c.have) { out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score; }
+                    else { out = hidx; branch = SMGX_BR_EVENT_MIN_LOAD; }
+                }
+            }
+            if (lane == 0) {
+                const uint32_t off = b.offsets[r];
+                write_pick(b, r, out, branch, matched, b.offsets[r + 1] - off);
+            }
+            if (out >= 0) {   // WorkerLoadGuard::new → increment_load()
+                const uint64_t old = s_L[out];
+                __syncwarp();
+                if (lane == 0) s_L[out] = old + 1;
+                __syncwarp();
+                if (old + 1 > gmax) gmax = old + 1;
+                if (old == gmin && --cnt_gmin == 0) { gmin = old + 1; cnt_gmin = count_at(gmin); }
+                if (out == hidx) rescan_healthy();
+            }
+        }
+    }
+    if (loads_out) for (uint32_t i = lane; i < n_slice; i += 32) loads_out[i] = s_L[i];
+}
+}  // namespace
+
+void launch_feedback_resolve(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, const uint64_t* d_loads, const uint8_t* d_flags,
+                             uint32_t n_slice, uint64_t abs_threshold, float rel_threshold, uint64_t* d_loads_out, cudaStream_t stream) {
+    const size_t smem = (size_t)std::max<uint32_t>(n_slice, 1) * 8;
+    if (smem > 200 * 1024) throw Error(SMGX_INVALID_ARGUMENT, "fleet too large for the load-feedback pass");
+    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(feedback_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    feedback_resolve_kernel<<<1, 32, smem, stream>>>(ix, fleet, a, d_loads, d_flags, n_slice, abs_threshold, rel_threshold, d_loads_out);
+    SMGX_CUDA(cudaGetLastError());
 }
 
 void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uint32_t n, bool early_exit, uint32_t* d_scores,

@@ -71,6 +71,11 @@ struct MultiArgs {
     uint64_t* done_flag;
     uint64_t done_value;
     uint32_t* done_counter;
+    // load-feedback mode (smgx_set_load_feedback): the fused kernel stores, per request, the eligible set of workers tied on the best
+    // overlap score ([total][words] u64, id space) and that score instead of a pick; feedback_resolve_kernel then walks the requests in
+    // order, each pick bumping its worker's load before the next request is decided (the router's WorkerLoadGuard, router.rs:319-321).
+    uint64_t* fb_winsets;
+    uint32_t* fb_scores;           // 0xFFFFFFFF = request longer than max_blocks
     uint32_t total;                // sum of b[k].n  (b[k].hash_base = requests before batch k)
     uint32_t uniform_n;            // every batch has this many requests (0: look the batch up through hash_base)
 };
@@ -79,7 +84,11 @@ bool event_select_fused();
 void set_event_select_fused(bool fused);
 void set_fused_minb(int minb);
 void set_fused_prefetch(int pf);
+void set_fused_tile(int tile, long long min_total);
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
+// second phase of the load-feedback mode: one warp resolves a.total requests in order against running loads (starting from `loads`)
+void launch_feedback_resolve(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, const uint64_t* d_loads, const uint8_t* d_flags,
+                             uint32_t n_slice, uint64_t abs_threshold, float rel_threshold, uint64_t* d_loads_out, cudaStream_t stream);
 
 // PositionalIndexer::find_matches on precomputed content hashes; one warp, one query.
 void launch_find_matches(const EventIndexView& ix, const uint64_t* d_hashes, uint32_t n, bool early_exit, uint32_t* d_scores,

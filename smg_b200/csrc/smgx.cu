@@ -62,6 +62,7 @@ struct ModelState {
     // device copy of the fleet
     DevBuf d_loads, d_flags, d_id_of_slice, d_derived, d_slice_of_id, d_load_of_id, d_elig;
     bool fleet_dirty = true;
+    bool fleet_has_dups = false;   // two slice entries share a URL
     bool fleet_dirty_tenant = true;
     uint64_t seen_workers_version = ~0ULL;
     // prefix_hash policy (policies/prefix_hash.rs): info.hash_ring of this model (worker/hash_ring.rs) and its device copies
@@ -78,6 +79,7 @@ struct ModelState {
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
+    DevBuf d_fb;   // load-feedback scratch: per-request tied sets + scores
     DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill, d_chunk_start, d_cv, d_hashes;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
@@ -128,7 +130,7 @@ public:
             cudaSetDevice(cfg.device_id);
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
-                l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
+                l.d_fb.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
                 l.d_path_tenant.release(); l.d_fill.release(); l.d_chunk_start.release(); l.d_cv.release(); l.d_hashes.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
@@ -220,12 +222,13 @@ public:
             raw.loads = m.d_loads.as<uint64_t>(); raw.flags = m.d_flags.as<uint8_t>(); raw.id_of_slice = m.d_id_of_slice.as<int32_t>();
             raw.n_slice = ns; raw.n_ids = n_ids; raw.words = words;
             raw.has_dups = 0;
+            m.fleet_has_dups = false;
             {   // duplicate URLs in the slice → several slice entries share one indexer id
                 std::vector<uint8_t> seen(std::max<uint32_t>(n_ids, 1), 0);
                 for (uint32_t i = 0; i < ns; ++i) {
                     const int32_t id = id_of_slice[i];
                     if (id < 0 || (uint32_t)id >= n_ids) continue;
-                    if (seen[(size_t)id]) { raw.has_dups = 1; break; }
+                    if (seen[(size_t)id]) { raw.has_dups = 1; m.fleet_has_dups = true; break; }
                     seen[(size_t)id] = 1;
                 }
             }
@@ -273,7 +276,17 @@ public:
         a.total = (uint32_t)rows;
         a.uniform_n = uniform && count ? descs[0].n : 0;
         a.hashes = nullptr;
-        a.done_flag = done_flag; a.done_value = done_value; a.done_counter = nullptr;
+        a.fb_winsets = nullptr; a.fb_scores = nullptr;
+        const bool feedback = load_feedback && !cand_mode && rows > 0;
+        if (feedback) {
+            if (!event_select_fused()) throw Error(SMGX_INVALID_ARGUMENT, "load feedback needs the fused event path");
+            if (m.fleet_has_dups) throw Error(SMGX_INVALID_ARGUMENT, "load feedback is not available for worker slices with duplicate URLs");
+            lane.d_fb.reserve(rows * ixv.words * 8 + rows * 4 + 64);
+            a.fb_winsets = lane.d_fb.as<uint64_t>();
+            a.fb_scores = reinterpret_cast<uint32_t*>(lane.d_fb.as<uint64_t>() + rows * ixv.words);
+        }
+        a.done_flag = feedback ? nullptr : done_flag; a.done_value = done_value; a.done_counter = nullptr;
+        if (feedback && done_flag) throw Error(SMGX_INVALID_ARGUMENT, "mapped submissions do not combine with load feedback (the in-order pass publishes the picks)");
         if (done_flag) {
             if (!event_select_fused()) throw Error(SMGX_INVALID_ARGUMENT, "mapped submissions need the fused event path");
             a.done_counter = d_done_counters.as<uint32_t>() + (done_seq++ % kDoneCounters);
@@ -284,6 +297,11 @@ public:
         }
         a.err_flag = d_err.as<uint32_t>();
         launch_event_select(ixv, fv, a, sm_count, lane.stream, &launches);
+        if (feedback) {
+            launch_feedback_resolve(ixv, fv, a, m.d_loads.as<uint64_t>(), m.d_flags.as<uint8_t>(), (uint32_t)m.urls.size(), cfg.balance_abs_threshold,
+                                    cfg.balance_rel_threshold, nullptr, lane.stream);
+            ++launches;
+        }
         SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
         lane.has_done = true;
     }
@@ -827,6 +845,7 @@ public:
     uint64_t token_ts = 0;       // GLOBAL_TIMESTAMP (token_tree.rs:179), shared by every token tree of the policy
     uint64_t string_epoch = 0;   // EPOCH_COUNTER (string_tree.rs:239), shared by every string tree of the policy
     uint32_t tree_batch_mode = SMGX_TREE_BATCH_SEQUENTIAL;
+    bool load_feedback = false;   // smgx_set_load_feedback
     uint32_t walk_chunk_seq = 0;
     smgx_cache_aware_config cfg;
     int sm_count = 148;
@@ -2141,6 +2160,14 @@ smgx_status smgx_wait(smgx_policy* p, uint64_t ticket, char** err) {
         return SMGX_SUCCESS;
     });
 }
+smgx_status smgx_set_load_feedback(smgx_policy* p, int enabled, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        p->impl.load_feedback = enabled != 0;
+        return SMGX_SUCCESS;
+    });
+}
 smgx_status smgx_select_batch_tokens(smgx_policy* p, const char* model_key, const uint32_t* tokens, const uint32_t* offsets, uint32_t n,
                                      int32_t* out_worker_idx, smgx_decision_info* out_info, char** err) {
     uint64_t t = 0;
@@ -2455,6 +2482,7 @@ void smgx_set_event_path(int fused, int min_blocks_per_sm) {
     if (min_blocks_per_sm) set_fused_minb(min_blocks_per_sm);
 }
 void smgx_set_fused_prefetch(int flavour) { set_fused_prefetch(flavour); }
+void smgx_set_fused_tile(int tile, int64_t min_total) { set_fused_tile(tile, (long long)min_total); }
 uint64_t smgx_kernel_launches(const smgx_policy* p) { return p ? p->impl.launches : 0; }
 smgx_status smgx_flush_l2(smgx_policy* p, char** err) {
     return guard(err, [&]() {

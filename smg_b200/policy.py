@@ -651,6 +651,11 @@ class CacheAwarePolicy:
         raw = buf[:nb.value].tobytes()
         return raw.decode("utf-8") if tk else np.frombuffer(raw, dtype=np.uint32).tolist()
 
+    def set_load_feedback(self, enabled: bool):
+        """Event-driven batches as a request STREAM: every pick bumps its worker's load before the next request is decided
+        (WorkerLoadGuard, routers/http/router.rs:319-321); off = one frozen fleet snapshot per batch."""
+        self._h.call("smgx_set_load_feedback", 1 if enabled else 0)
+
     def set_tree_batch_mode(self, mode: str):
         self._h.call("smgx_set_tree_batch_mode", TREE_BATCH_MODES[mode])
 

@@ -1,7 +1,7 @@
 // Per-request front end (include/smgx_batcher.hpp) on a B200: T caller threads route R requests each through smgx::Batcher against the
 // event-driven index; every pick must equal the oracle's pick for that request (event-mode picks do not depend on arrival order), and
 // the run reports throughput and per-request latency.  Test infrastructure: the oracle is the checker.
-//   test_batcher [threads] [requests_per_thread] [window] [max_wait_us] [mapped 1|0] [max_inflight] [linger_us]
+//   test_batcher [threads] [requests_per_thread] [window] [max_wait_us] [mapped 1|0] [max_inflight] [linger_us] [quiet_ns]
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -18,7 +18,7 @@ int main(int argc, char** argv) {
     const int T = argc > 1 ? std::atoi(argv[1]) : 16, R = argc > 2 ? std::atoi(argv[2]) : 2000, WIN = argc > 3 ? std::atoi(argv[3]) : 32;
     const int wait_us = argc > 4 ? std::atoi(argv[4]) : 100;
     const bool mapped = argc > 5 ? std::atoi(argv[5]) != 0 : true;
-    const int max_inflight = argc > 6 ? std::atoi(argv[6]) : 3, linger_us = argc > 7 ? std::atoi(argv[7]) : 0;
+    const int max_inflight = argc > 6 ? std::atoi(argv[6]) : 3, linger_us = argc > 7 ? std::atoi(argv[7]) : 0, quiet_ns = argc > 8 ? std::atoi(argv[8]) : 1500;
     const uint32_t W = 64, BS = 16, TOK = 512, SEQS = 20000;
     std::mt19937_64 rng(7);
     smgx::CacheAwareConfig cfg; cfg.eviction_interval_secs = 0; cfg.cache_threshold = 0.3f; cfg.balance_abs_threshold = 64; cfg.balance_rel_threshold = 1.5f; cfg.block_size = BS;
@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
     smgx::Batcher::Options bo;
     bo.max_batch = 4096; bo.tokens_per_batch = 4096 * TOK; bo.max_wait = std::chrono::microseconds(wait_us);
     bo.ring = 24;   // sized for the run: no pinned allocation on the request path
-    bo.mapped = mapped; bo.max_inflight = (uint32_t)max_inflight; bo.linger = std::chrono::microseconds(linger_us); bo.max_request_tokens = TOK;
+    bo.mapped = mapped; bo.max_inflight = (uint32_t)max_inflight; bo.linger = std::chrono::microseconds(linger_us); bo.max_request_tokens = TOK; bo.quiet = std::chrono::nanoseconds(quiet_ns);
     double secs;
     smgx::Batcher::Stats st;
     {
@@ -110,10 +110,10 @@ int main(int argc, char** argv) {
     }
     std::sort(lat_us.begin(), lat_us.end());
     std::printf("{\"mode\": \"per-request front end (smgx::Batcher), event-driven cache_aware, 64 workers, 512-token requests\", \"transport\": \"%s\", "
-                "\"threads\": %d, \"outstanding_per_thread\": %d, \"requests\": %zu, \"max_wait_us\": %d, \"max_inflight\": %d, \"linger_us\": %d, \"decisions_per_s\": %.1f, \"batches\": %llu, "
+                "\"threads\": %d, \"outstanding_per_thread\": %d, \"requests\": %zu, \"max_wait_us\": %d, \"max_inflight\": %d, \"linger_us\": %d, \"quiet_ns\": %d, \"decisions_per_s\": %.1f, \"batches\": %llu, "
                 "\"mean_batch\": %.1f, \"p50_latency_us\": %.1f, \"p99_latency_us\": %.1f, \"p999_latency_us\": %.1f, \"mismatches_vs_oracle\": %zu}\n",
                 mapped ? "mapped zero-copy (smgx_submit_tokens_mapped, callers spin on the completion word)" : "staged (smgx_submit_tokens / smgx_wait)",
-                T, WIN, N, wait_us, max_inflight, linger_us, N / secs, (unsigned long long)st.batches, st.batches ? (double)st.requests / st.batches : 0.0, lat_us[N / 2],
+                T, WIN, N, wait_us, max_inflight, linger_us, quiet_ns, N / secs, (unsigned long long)st.batches, st.batches ? (double)st.requests / st.batches : 0.0, lat_us[N / 2],
                 lat_us[(size_t)(N * 0.99)], lat_us[(size_t)(N * 0.999)], bad);
     return bad ? 1 : 0;
 }
