@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text-in", action="store_true", help="skip the text-in leg (GPU tokenize → pick) of the N=1 line")
+    ap.add_argument("--no-per-request", action="store_true", help="skip the per-request front-end leg (smgx::Batcher, 32 blocking callers) of the N=1 line")
     ap.add_argument("--no-sharded", action="store_true", help="skip the worker-id-sharded config-4 sub-record of the N>1 line")
     ap.add_argument("--text-in", action="store_true", help="(kept for compatibility: the text-in leg is on by default at N=1)")
     ap.add_argument("--text-docs", type=int, default=8192)
@@ -393,20 +394,25 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    region_ms, gpu_launches = [], 0
-    for order, TOK, OFF, OUT, NS in regions:
+    region_ms, region_ms_ungated, gpu_launches = [], [], 0
+    hold_us = int(100 + 2 * K)   # long enough for the host to enqueue the whole region behind the hold kernel
+    for gated in (True, False):
+      for order, TOK, OFF, OUT, NS in (regions if gated else regions[:1]):
         barrier()
         launches0 = pol.kernel_launches()
         ms = C.c_float()
-        h.call("smgx_timer_start_all")
+        if gated:
+            h.call("smgx_timer_start_all_gated", hold_us)
+        else:
+            h.call("smgx_timer_start_all")
         if n_lanes == 1:
             for j in range(K):
                 h.call("smgx_select_batch_tokens_device", model, 0, TOK[j], d_off, B, T, OUT[j], None)
         else:
             h.call("smgx_select_many_tokens_device", model, K, TOK, OFF, NS, T, OUT)
         h.call("smgx_timer_stop_all_ms", C.byref(ms))
-        region_ms.append(float(ms.value))
-        gpu_launches = pol.kernel_launches() - launches0
+        (region_ms if gated else region_ms_ungated).append(float(ms.value))
+        gpu_launches = pol.kernel_launches() - launches0   # the hold kernel is not counted: it is not part of the path
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_med = float(np.median(region_ms))
@@ -521,11 +527,12 @@ def main():
                    "l2_hygiene": f"ring of {R} distinct device-resident batches = {R * B * T * 4 / 2**20:.0f} MiB of tokens > L2, each timed region starts "
                                  f"at a different ring position; index ({ix.entry_count() * 32 / 2**20:.0f} MiB live slots) is the L2-resident working set",
                    "index_build_s": round(t_pop, 2), "numa_node": numa_node,
-                   "timing": f"{len(region_ms)} back-to-back regions of exactly {K} steps, CUDA events across the launching lanes; the median region is "
-                             f"reported (all regions in region_ms), max over ranks",
+                   "timing": f"{len(region_ms)} back-to-back regions of exactly {K} steps each, CUDA events across the launching lanes, every region enqueued behind a "
+                             f"{hold_us} us hold kernel so that the events bracket GPU execution only (region_ms); the same region with the start event recorded "
+                             f"on an idle stream, i.e. including the host's launch latency, is region_ms_ungated; the median gated region is reported, max over ranks",
                    "issue": (f"K steps handed to smgx_select_many_tokens_device in one call: up to 32 batches per launch, launches alternate over "
                              f"{n_lanes} CUDA stream lanes") if n_lanes > 1 else "K launches, one batch each, on one stream"},
-        "region_ms": region_ms,
+        "region_ms": region_ms, "region_ms_ungated": region_ms_ungated,
         "e2e": {"value": e2e_value, "unit": "decisions/s", "h2d_bytes_per_step": int(B * T * 4 + (B + 1) * 4), "d2h_bytes_per_step": int(B * 4),
                 "pipeline_depth": int(depth), "regions_s": e2e_s,
                 "timing": "host wall clock around K pipelined submit/wait calls (median of the regions), device synchronised on both sides"},
@@ -555,6 +562,8 @@ def main():
             line["text_in"] = text_in_leg(args, local_rank)
         except Exception as e:  # noqa: BLE001
             line["text_in"] = {"error": str(e)[:300]}
+    if rank == 0 and world == 1 and not args.no_per_request:
+        line["per_request"] = per_request_leg(local_rank)
     if world > 1 and not args.no_sharded:
         try:
             sh = sharded_leg(args, rank, world, local_rank, dist)
@@ -567,6 +576,29 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def per_request_leg(local_rank):
+    """The reference's real call shape: LoadBalancingPolicy::select_worker is called once per request from many router tasks
+    (policies/mod.rs:43-86, routers/grpc/common/stages/worker_selection.rs:157).  tests/cpp/test_batcher drives include/smgx_batcher.hpp —
+    callers enqueue single requests, a group-commit dispatcher hands small batches to the zero-copy smgx_submit_tokens_mapped call, callers
+    spin on the completion word — against a 640 k-entry index, and checks every pick against the oracle (checker only).  Two caller shapes:
+    32 blocking callers (one request outstanding each: the latency-bound shape) and a 16-thread task pool with 512 requests outstanding."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_batcher")
+    if not os.path.exists(exe):
+        return {"unavailable": "tests/cpp/test_batcher not built"}
+    out = {}
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+    for name, argv in (("blocking_32_callers", ["32", "4000", "1", "50", "1", "3", "0", "1500"]), ("task_pool_16x512", ["16", "16384", "512", "100", "1", "3", "0", "1500"])):
+        try:
+            r = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=240, env=env)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[name] = {k: d[k] for k in ("transport", "threads", "outstanding_per_thread", "requests", "decisions_per_s", "mean_batch", "p50_latency_us",
+                                           "p99_latency_us", "p999_latency_us", "mismatches_vs_oracle")}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": str(e)[:200]}
+    out["what"] = "per-request decisions through smgx::Batcher (include/smgx_batcher.hpp), every pick compared with the oracle; latency = enqueue → pick in the caller's hands"
+    return out
 
 
 def sharded_leg(args, rank, world, local_rank, dist):

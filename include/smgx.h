@@ -249,6 +249,25 @@ smgx_status smgx_stree_node_count(smgx_policy* p, const char* model_key, uint64_
 smgx_status smgx_hash_token_paths(smgx_policy* p, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err);
 smgx_status smgx_hash_node_paths(smgx_policy* p, const uint8_t* text, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err);
 /* text_kind 0: token_tree map (values are u32 ids), 1: string_tree map (values are UTF-8 bytes). */
+/* ---- TreeHandle (cache_aware.rs:454-645): what the mesh adapter calls on the policy -------------------------------------------------
+ *   apply_known_remote_insert (:499-551)  smgx_tree_apply_known_remote_insert: *out_known = 1 and the stored matched prefix gains
+ *                                         `worker_url` as a tenant when hash_index[model] resolves `node_hash`; 0 otherwise (ask a peer for repair)
+ *   open_repair_stream (:553-573)         smgx_stree_entries / smgx_tree_entries (iter_entries in the trees' deterministic pre-order)
+ *   apply_repair_page (:575-645)          smgx_tree_apply_repair_page: entries whose kind differs from tree_kind are skipped; the tree is
+ *                                         created if missing; every applied entry seeds hash_index with its blake3 path hash (GPU)
+ * tree_kind / smgx_repair_entry.kind: 0 = TreeKind::String (UTF-8 bytes), 1 = TreeKind::Token (u32 ids). */
+typedef struct smgx_repair_entry {
+    uint32_t kind;                 /* 0 = RepairEntry::String, 1 = RepairEntry::Token */
+    uint32_t len;                  /* bytes (String) or tokens (Token) */
+    const void* data;
+    const char* const* tenants;    /* the entry's tenant URLs (epochs are not used by apply_repair_page) */
+    uint32_t n_tenants;
+    uint32_t reserved;
+} smgx_repair_entry;
+smgx_status smgx_tree_apply_known_remote_insert(smgx_policy* p, const char* model_key, int tree_kind, uint64_t node_hash, const char* worker_url,
+                                                int* out_known, char** err);
+smgx_status smgx_tree_apply_repair_page(smgx_policy* p, const char* model_key, int tree_kind, const smgx_repair_entry* entries, uint32_t n,
+                                        uint32_t* out_applied, char** err);
 smgx_status smgx_hash_index_size(smgx_policy* p, const char* model_key, int text_kind, uint64_t* out, char** err);
 smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_kind, uint64_t path_hash, void* out, uint32_t cap_bytes,
                                 uint32_t* out_bytes, int* out_found, char** err);
@@ -410,6 +429,9 @@ smgx_status smgx_timer_stop_ms(smgx_policy* p, uint32_t lane, float* out_ms, cha
 /* Same across ALL lanes: start is recorded on lane 0 and every other lane is made to wait for it; stop joins every lane
  * into lane 0 before recording the end event — so the interval covers work issued round-robin over the lanes. */
 smgx_status smgx_timer_start_all(smgx_policy* p, char** err);
+/* start_all behind a hold kernel of ~hold_us µs: work enqueued during the hold runs back to back afterwards, so the measured interval is GPU
+ * execution only (no host launch latency between the start event and the first kernel). */
+smgx_status smgx_timer_start_all_gated(smgx_policy* p, uint32_t hold_us, char** err);
 smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
 /* Process-wide switch between the two implementations of the event-driven pick (A/B measurements, tests): fused != 0 (default) = the
  * one-kernel persistent path, 0 = the round-1 hash kernel + search kernel pair.  min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant

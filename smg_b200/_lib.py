@@ -26,6 +26,10 @@ class KvEvent(C.Structure):
                 ("parent_block_hash", C.c_int64), ("has_parent", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class RepairEntry(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("len", C.c_uint32), ("data", C.c_void_p), ("tenants", C.POINTER(C.c_char_p)), ("n_tenants", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class DecisionInfo(C.Structure):
     _fields_ = [("matched", C.c_uint32), ("input", C.c_uint32), ("branch", C.c_uint8), ("nodes", C.c_uint8), ("reserved", C.c_uint8 * 2)]
 
@@ -113,6 +117,8 @@ def load():
     sig("smgx_prefix_hashes", st, vp, vp, vp, u32, vp, pp)
     sig("smgx_prefix_hash_select_batch_tokens", st, vp, cp, vp, vp, u32, vp, vp, vp, pp)
     sig("smgx_prefix_hash_select_many_tokens_device", st, vp, cp, u32, vp, vp, vp, vp, pp)
+    sig("smgx_tree_apply_known_remote_insert", st, vp, cp, C.c_int, u64, cp, P(C.c_int), pp)
+    sig("smgx_tree_apply_repair_page", st, vp, cp, C.c_int, vp, u32, P(u32), pp)
     sig("smgx_hash_index_size", st, vp, cp, C.c_int, P(u64), pp)
     sig("smgx_hash_index_get", st, vp, cp, C.c_int, u64, vp, u32, P(u32), P(C.c_int), pp)
     sig("smgx_set_tree_batch_mode", st, vp, u32, pp)
@@ -155,6 +161,7 @@ def load():
     sig("smgx_timer_start", st, vp, u32, pp)
     sig("smgx_timer_stop_ms", st, vp, u32, P(C.c_float), pp)
     sig("smgx_timer_start_all", st, vp, pp)
+    sig("smgx_timer_start_all_gated", st, vp, u32, pp)
     sig("smgx_timer_stop_all_ms", st, vp, P(C.c_float), pp)
     sig("smgx_set_event_path", None, C.c_int, C.c_int)
     sig("smgx_set_fused_prefetch", None, C.c_int)

@@ -99,6 +99,7 @@ void launch_content_hashes(const uint32_t* d_tokens, uint32_t n_tokens, uint32_t
 
 void launch_content_hashes_ragged(const uint32_t* d_tokens, const uint32_t* d_offs, uint32_t n_blocks, uint64_t* d_out, cudaStream_t stream);
 void launch_fill(uint32_t* d, uint32_t value, size_t n_words, cudaStream_t stream);
+void launch_hold(uint32_t us, cudaStream_t stream);
 // peer-memory exchange of the sharded pick (smgx.cu: Exchange)
 void launch_shard_push(const smgx_shard_candidate* d_cand, uint32_t n, const smgx_shard_fleet* d_fleet, uint8_t* const* d_peer_parity_base, uint32_t world,
                        uint32_t rank, size_t cand_off, size_t cand_slot_bytes, size_t fleet_off, uint32_t fleet_stride, size_t flag_off, uint64_t seq,

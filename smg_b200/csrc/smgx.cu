@@ -89,6 +89,11 @@ struct Lane {
     ModelState* model = nullptr;
     const int32_t* host_out = nullptr;
     uint32_t n = 0;
+    // load-feedback bookkeeping of a host-buffer submission (see Policy::wait)
+    const uint32_t* fb_tokens = nullptr;
+    const uint32_t* fb_offsets = nullptr;
+    const smgx_decision_info* fb_info_host = nullptr;
+    std::vector<smgx_decision_info> fb_info;
 };
 
 class Policy {
@@ -406,10 +411,14 @@ public:
     // included).  SMGX_TREE_BATCH_SNAPSHOT: the whole batch is one segment — every request walks and decides against the
     // pre-batch tree, then the side effects are applied in request order: one admissible interleaving of concurrent
     // select_worker calls (include/smgx.h), identical to SEQUENTIAL when no two requests of the batch share a first page.
+    // `forced` (load-feedback mode): the picks were made by the in-order pass; this call only performs select_worker_min_load's tree side
+    // effects (match touches, insert under the picked worker, hash_index; cache_aware.rs:380-402) for them.  `use_lane`: whose staging and
+    // stream to use (default lane 0).
     void tree_select(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info,
-                     bool decide, int32_t* out_tenant) {
+                     bool decide, int32_t* out_tenant, const int32_t* forced = nullptr, Lane* use_lane = nullptr) {
         TokenTreeIndex& tree = tree_of(m, true);
-        Lane& lane = lanes[0];
+        Lane& lane = use_lane ? *use_lane : lanes[0];
+        if (forced) decide = false;
         const uint64_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
         const uint32_t n1 = std::max<uint32_t>(n, 1);
         lane.d_tokens.reserve(std::max<uint64_t>(total, 1) * 4 + 16);
@@ -427,7 +436,7 @@ public:
         std::vector<uint32_t> path((size_t)n * kPathCap), path_len(n);
         std::vector<int32_t> path_ten((size_t)n * kPathCap), ten(n);
         std::vector<uint64_t> path_hash;   // hash_token_path of every request, for the hash_index side effect (:881-886, :397-401)
-        if (decide) enqueue_path_hashes(lane, reinterpret_cast<const uint8_t*>(lane.d_tokens.as<uint32_t>() - base), lane.d_offsets.as<uint32_t>(), offsets, n, 4, path_hash);
+        if (decide || forced) enqueue_path_hashes(lane, reinterpret_cast<const uint8_t*>(lane.d_tokens.as<uint32_t>() - base), lane.d_offsets.as<uint32_t>(), offsets, n, 4, path_hash);
         const bool snapshot = tree_batch_mode == SMGX_TREE_BATCH_SNAPSHOT;
         // SEQUENTIAL is run optimistically: the rest of the batch is walked against one snapshot, then the host replays the
         // requests in order and stops at the first one whose snapshot walk is no longer what a walk at that moment would
@@ -488,6 +497,13 @@ public:
                     else { const TreeMatch& hm = deep.at(r); tree.apply_match_touches(hm.path.data(), hm.path_tenants.data(), (uint32_t)hm.path.size()); }
                 } else if (path_len[r] <= kPathCap) tree.apply_match_touches(pth, path_len[r]);        // tenants as they are now
                 else { TreeMatch hm = tree.match_prefix_host(tk, len, false); tree.apply_match_touches(hm.path.data(), (uint32_t)hm.path.size()); }
+                if (forced) {
+                    if (forced[r] >= 0 && (size_t)forced[r] < m.tenant_of_slice.size()) {
+                        tree.insert_tokens(tk, len, m.tenant_of_slice[(size_t)forced[r]]);   // :396
+                        hash_index_put_tokens(m, path_hash[r], tk, info[r].matched);
+                    }
+                    continue;
+                }
                 if (!decide) continue;
                 const uint8_t br = info[r].branch;
                 if ((br == SMGX_BR_TREE_MATCH || br == SMGX_BR_TREE_MIN_LOAD || br == SMGX_BR_IMBALANCED_MIN_LOAD) && out_idx[r] >= 0) {
@@ -772,11 +788,14 @@ public:
 
     uint64_t submit_host(ModelState& m, const uint32_t* tokens, const uint32_t* offsets, uint32_t n, int32_t* out_idx, smgx_decision_info* out_info) {
         SMGX_REQUIRE(n <= cfg.max_batch, "batch larger than max_batch");
-        if (!has_event_indexer(m) || (host_imbalanced(m) && m.token_tree)) {
+        // load feedback: the imbalance gate is re-evaluated per request by the in-order pass, so an event-mode model always takes the event path;
+        // the tree update of the picks that did take the imbalanced branch is applied when the ticket is waited for
+        const bool fb_event = load_feedback && has_event_indexer(m);
+        if (!fb_event && (!has_event_indexer(m) || (host_imbalanced(m) && m.token_tree))) {
             // approximate token tree (or the imbalanced path's tree update): completes synchronously
             for (uint32_t i = 0; i < n; ++i) SMGX_REQUIRE(offsets[i + 1] >= offsets[i], "offsets must be non-decreasing");
             Lane& l = free_lane();   // SMGX_BUSY must be raised BEFORE the tree is touched: callers retry the whole batch on BUSY
-            tree_select(m, tokens, offsets, n, out_idx, out_info, true, nullptr);
+            tree_select(m, tokens, offsets, n, out_idx, out_info, true, nullptr, nullptr, &l);   // on the lane just reserved: its staging is idle
             l.busy = true; l.ticket = ++ticket_seq; l.model = &m; l.host_out = out_idx; l.n = 0;   // n = 0: processed already counted
             return l.ticket;
         }
@@ -793,22 +812,27 @@ public:
         lane.d_tokens.reserve(std::max<uint64_t>(total - base, 1) * 4 + 16);
         lane.d_offsets.reserve(((size_t)n + 1) * 4);
         lane.d_out.reserve(std::max<uint32_t>(n, 1) * 4);
-        if (out_info) lane.d_info.reserve(std::max<uint32_t>(n, 1) * sizeof(smgx_decision_info));
+        smgx_decision_info* info_host = out_info;
+        if (fb_event && !out_info && m.token_tree) { lane.fb_info.resize(std::max<uint32_t>(n, 1)); info_host = lane.fb_info.data(); }   // branches are needed at wait()
+        if (info_host) lane.d_info.reserve(std::max<uint32_t>(n, 1) * sizeof(smgx_decision_info));
         if (n) {
             // tokens are copied from offsets[0]; the kernel indexes with the caller's absolute offsets
             SMGX_CUDA(cudaMemcpyAsync(lane.d_tokens.ptr, tokens + base, (total - base) * 4, cudaMemcpyHostToDevice, lane.stream));
             SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, lane.stream));
             enqueue_tokens(m, lane, lane.d_tokens.as<uint32_t>() - base, lane.d_offsets.as<uint32_t>(), n, std::max<uint32_t>(max_len, 1),
-                           lane.d_out.as<int32_t>(), out_info ? lane.d_info.as<smgx_decision_info>() : nullptr);
+                           lane.d_out.as<int32_t>(), info_host ? lane.d_info.as<smgx_decision_info>() : nullptr);
             SMGX_CUDA(cudaMemcpyAsync(out_idx, lane.d_out.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
-            if (out_info)
-                SMGX_CUDA(cudaMemcpyAsync(out_info, lane.d_info.ptr, (size_t)n * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
+            if (info_host)
+                SMGX_CUDA(cudaMemcpyAsync(info_host, lane.d_info.ptr, (size_t)n * sizeof(smgx_decision_info), cudaMemcpyDeviceToHost, lane.stream));
         }
         lane.busy = true;
         lane.ticket = ++ticket_seq;
         lane.model = &m;
         lane.host_out = out_idx;
         lane.n = n;
+        lane.fb_tokens = (fb_event && m.token_tree) ? tokens : nullptr;
+        lane.fb_offsets = offsets;
+        lane.fb_info_host = info_host;
         return lane.ticket;
     }
 
@@ -822,6 +846,25 @@ public:
             for (uint32_t i = 0; i < l.n; ++i) {
                 int32_t idx = l.host_out[i];
                 if (idx >= 0 && (size_t)idx < m.processed.size()) ++m.processed[(size_t)idx];
+            }
+            if (l.fb_tokens && l.fb_info_host && m.token_tree) {
+                // load-feedback batches: the picks that took the imbalanced branch still owe select_worker_min_load's tree update (cache_aware.rs:380-402)
+                std::vector<uint32_t> toks, offs{0};
+                std::vector<int32_t> forced;
+                for (uint32_t i = 0; i < l.n; ++i) {
+                    if (l.fb_info_host[i].branch != SMGX_BR_IMBALANCED_MIN_LOAD || l.host_out[i] < 0) continue;
+                    toks.insert(toks.end(), l.fb_tokens + l.fb_offsets[i], l.fb_tokens + l.fb_offsets[i + 1]);
+                    offs.push_back((uint32_t)toks.size());
+                    forced.push_back(l.host_out[i]);
+                }
+                const ModelState* mp = &m;
+                l.fb_tokens = nullptr;
+                if (!forced.empty()) {
+                    std::vector<int32_t> scratch(forced.size());
+                    uint32_t dummy = 0;
+                    tree_select(const_cast<ModelState&>(*mp), toks.empty() ? &dummy : toks.data(), offs.data(), (uint32_t)forced.size(), scratch.data(), nullptr, false, nullptr,
+                                forced.data(), &l);
+                }
             }
             return;
         }
@@ -1789,6 +1832,90 @@ smgx_status smgx_hash_token_paths(smgx_policy* p, const uint32_t* tokens, const 
 smgx_status smgx_hash_node_paths(smgx_policy* p, const uint8_t* text, const uint32_t* offsets, uint32_t n, uint64_t* out_hashes, char** err) {
     return hash_paths(p, text, offsets, n, 1, out_hashes, err);
 }
+// ---- TreeHandle (cache_aware.rs:454-645): the mesh adapter's view of the policy ----
+// apply_known_remote_insert (:499-551): resolve `node_hash` through hash_index[model] to the stored matched prefix and insert it for
+// `worker_url`; false when the model, the hash or the tree is unknown (the caller then asks a peer for repair).
+smgx_status smgx_tree_apply_known_remote_insert(smgx_policy* p, const char* model_key, int tree_kind, uint64_t node_hash, const char* worker_url,
+                                                int* out_known, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(worker_url); NONNULL(out_known);
+        SMGX_REQUIRE(tree_kind == 0 || tree_kind == 1, "tree_kind: 0 = String, 1 = Token");
+        *out_known = 0;
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        auto it = P.models.find(norm_model(model_key));
+        if (it == P.models.end()) return SMGX_SUCCESS;
+        ModelState& m = *it->second;
+        if (tree_kind == 0) {
+            auto e = m.hash_index_text.find(node_hash);
+            if (e == m.hash_index_text.end() || !m.string_tree) return SMGX_SUCCESS;
+            const std::string path(m.hash_arena_text.data() + e->second.first, e->second.second);   // copy: the insert may not alias the arena
+            m.string_tree->insert_text(reinterpret_cast<const uint8_t*>(path.data()), (uint32_t)path.size(), P.tenants.intern(worker_url));
+        } else {
+            auto e = m.hash_index_tokens.find(node_hash);
+            if (e == m.hash_index_tokens.end() || !m.token_tree) return SMGX_SUCCESS;
+            const std::vector<uint32_t> toks(m.hash_arena_tokens.begin() + (ptrdiff_t)e->second.first,
+                                             m.hash_arena_tokens.begin() + (ptrdiff_t)(e->second.first + e->second.second));
+            if (toks.size() >= kPage) m.token_tree->insert_tokens(toks.data(), toks.size(), P.tenants.intern(worker_url));   // shorter inputs return before interning (:403-410)
+        }
+        *out_known = 1;
+        return SMGX_SUCCESS;
+    });
+}
+// apply_repair_page (:575-645): every entry of the page's kind is inserted for each of its tenants (the tree is created on first use —
+// repair is the cold-start path of a fresh peer) and its path hash (blake3 of the whole path, hashed on the GPU in one launch) is seeded
+// into hash_index; entries of the other kind are skipped.  *out_applied = entries applied.
+smgx_status smgx_tree_apply_repair_page(smgx_policy* p, const char* model_key, int tree_kind, const smgx_repair_entry* entries, uint32_t n,
+                                        uint32_t* out_applied, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p); NONNULL(out_applied);
+        SMGX_REQUIRE(tree_kind == 0 || tree_kind == 1, "tree_kind: 0 = String, 1 = Token");
+        SMGX_REQUIRE(n == 0 || entries, "Invalid arguments: null pointer");
+        *out_applied = 0;
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        ModelState& m = P.model(model_key, true);
+        if (tree_kind == 0) P.stree_of(m); else P.tree_of(m, true);
+        // gather the page's entries of the right kind into one ragged buffer and hash their paths in one launch
+        const uint32_t eb = tree_kind == 0 ? 1 : 4;
+        std::vector<uint32_t> which;
+        std::vector<uint32_t> offs{0};
+        std::string blob;
+        for (uint32_t i = 0; i < n; ++i) {
+            if ((int)entries[i].kind != tree_kind) continue;   // variant mismatch: logged and skipped in the reference (:606-613, :633-640)
+            SMGX_REQUIRE(entries[i].len == 0 || entries[i].data, "Invalid arguments: null pointer");
+            SMGX_REQUIRE(entries[i].n_tenants == 0 || entries[i].tenants, "Invalid arguments: null pointer");
+            which.push_back(i);
+            blob.append(reinterpret_cast<const char*>(entries[i].data), (size_t)entries[i].len * eb);
+            SMGX_REQUIRE(blob.size() / eb < (1ull << 32), "repair page too large");
+            offs.push_back((uint32_t)(blob.size() / eb));
+        }
+        if (which.empty()) return SMGX_SUCCESS;
+        P.use_device();
+        std::vector<uint64_t> hashes;
+        {
+            Lane& lane = P.lanes[0];
+            lane.d_text.reserve(std::max<size_t>(blob.size(), 1) + 16);
+            lane.d_offsets.reserve(offs.size() * 4);
+            if (!blob.empty()) SMGX_CUDA(cudaMemcpyAsync(lane.d_text.ptr, blob.data(), blob.size(), cudaMemcpyHostToDevice, lane.stream));
+            SMGX_CUDA(cudaMemcpyAsync(lane.d_offsets.ptr, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, lane.stream));
+            P.enqueue_path_hashes(lane, lane.d_text.as<uint8_t>(), lane.d_offsets.as<uint32_t>(), offs.data(), (uint32_t)which.size(), eb, hashes);
+            SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+        }
+        for (size_t k = 0; k < which.size(); ++k) {
+            const smgx_repair_entry& e = entries[which[k]];
+            for (uint32_t t = 0; t < e.n_tenants; ++t) {
+                NONNULL(e.tenants[t]);
+                if (tree_kind == 0) m.string_tree->insert_text(reinterpret_cast<const uint8_t*>(e.data), e.len, P.tenants.intern(e.tenants[t]));
+                else if (e.len >= kPage) m.token_tree->insert_tokens(reinterpret_cast<const uint32_t*>(e.data), e.len, P.tenants.intern(e.tenants[t]));
+            }
+            if (tree_kind == 0) Policy::hash_index_put_text(m, hashes[k], reinterpret_cast<const uint8_t*>(e.data), e.len);
+            else Policy::hash_index_put_tokens(m, hashes[k], reinterpret_cast<const uint32_t*>(e.data), e.len);
+            ++*out_applied;
+        }
+        return SMGX_SUCCESS;
+    });
+}
 smgx_status smgx_hash_index_size(smgx_policy* p, const char* model_key, int text_kind, uint64_t* out, char** err) {
     return guard(err, [&]() {
         NONNULL(p); NONNULL(out);
@@ -2457,6 +2584,20 @@ smgx_status smgx_timer_start_all(smgx_policy* p, char** err) {
         NONNULL(p);
         Policy& P = p->impl;
         P.use_device();
+        SMGX_CUDA(cudaEventRecord(P.lanes[0].t0, P.lanes[0].stream));
+        for (size_t i = 1; i < P.lanes.size(); ++i) SMGX_CUDA(cudaStreamWaitEvent(P.lanes[i].stream, P.lanes[0].t0, 0));
+        return SMGX_SUCCESS;
+    });
+}
+// Same as smgx_timer_start_all, but a hold kernel first keeps lane 0 (and with it every lane, which waits for the start event) busy for
+// ~hold_us microseconds: everything the caller enqueues in that window runs back to back once the hold ends, so the interval
+// smgx_timer_stop_all_ms reports is GPU execution of the region, free of host launch latency.
+smgx_status smgx_timer_start_all_gated(smgx_policy* p, uint32_t hold_us, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        Policy& P = p->impl;
+        P.use_device();
+        launch_hold(hold_us, P.lanes[0].stream);
         SMGX_CUDA(cudaEventRecord(P.lanes[0].t0, P.lanes[0].stream));
         for (size_t i = 1; i < P.lanes.size(); ++i) SMGX_CUDA(cudaStreamWaitEvent(P.lanes[i].stream, P.lanes[0].t0, 0));
         return SMGX_SUCCESS;

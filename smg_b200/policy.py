@@ -651,6 +651,29 @@ class CacheAwarePolicy:
         raw = buf[:nb.value].tobytes()
         return raw.decode("utf-8") if tk else np.frombuffer(raw, dtype=np.uint32).tolist()
 
+    # -- TreeHandle (cache_aware.rs:454-645) ----------------------------------------------------------------------------
+    def apply_known_remote_insert(self, model_id: str, tree_kind: str, node_hash: int, worker_url: str) -> bool:
+        known = C.c_int()
+        self._h.call("smgx_tree_apply_known_remote_insert", (model_id or "").encode(), 1 if tree_kind == "token" else 0, int(node_hash), worker_url.encode(), C.byref(known))
+        return bool(known.value)
+
+    def apply_repair_page(self, model_id: str, tree_kind: str, entries) -> int:
+        """entries: [("string", path: str, [(tenant, epoch)]) | ("token", tokens, [(tenant, epoch)])] → entries applied."""
+        arr = (_lib.RepairEntry * max(len(entries), 1))()
+        keep = []
+        for i, (kind, path, tenants) in enumerate(entries):
+            data = np.frombuffer(path.encode(), dtype=np.uint8).copy() if kind == "string" else _u32(path)
+            names = (C.c_char_p * max(len(tenants), 1))(*[t.encode() for t, _ in tenants])
+            keep.append((data, names))
+            arr[i].kind = 1 if kind == "token" else 0
+            arr[i].len = data.size
+            arr[i].data = data.ctypes.data if data.size else None
+            arr[i].tenants = names
+            arr[i].n_tenants = len(tenants)
+        applied = C.c_uint32()
+        self._h.call("smgx_tree_apply_repair_page", (model_id or "").encode(), 1 if tree_kind == "token" else 0, C.cast(arr, C.c_void_p), len(entries), C.byref(applied))
+        return applied.value
+
     def set_load_feedback(self, enabled: bool):
         """Event-driven batches as a request STREAM: every pick bumps its worker's load before the next request is decided
         (WorkerLoadGuard, routers/http/router.rs:319-321); off = one frozen fleet snapshot per batch."""

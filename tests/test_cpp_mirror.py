@@ -47,12 +47,16 @@ def test_cpp_batcher_logic_against_mock_device():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("threads,per_thread,window,wait_us", [(8, 1500, 64, 100), (32, 400, 1, 50), (3, 2000, 700, 200)])
-def test_cpp_batcher_picks_equal_oracle(threads, per_thread, window, wait_us):
-    """Many caller threads through smgx::Batcher (include/smgx_batcher.hpp): every per-request pick equals the oracle's; blocking
-    route() (window 1), a task pool with 64 outstanding requests, and windows wide enough to fill 4096-request batches."""
+@pytest.mark.parametrize("threads,per_thread,window,wait_us,mapped", [(8, 1500, 64, 100, 1), (32, 400, 1, 50, 1), (8, 1500, 64, 100, 0), (32, 400, 1, 50, 0),
+                                                                      (3, 2000, 700, 200, 0)])
+def test_cpp_batcher_picks_equal_oracle(threads, per_thread, window, wait_us, mapped):
+    """Many caller threads through smgx::Batcher (include/smgx_batcher.hpp), both transports — mapped = the zero-copy latency path
+    (smgx_submit_tokens_mapped, group commit, callers spin on the completion word), staged = smgx_submit_tokens / smgx_wait: every
+    per-request pick equals the oracle's; blocking route() (window 1), a task pool with 64 outstanding requests and, on the staged
+    transport, windows wide enough to fill 4096-request batches."""
     import json
-    out = _run([str(threads), str(per_thread), str(window), str(wait_us)], name="test_batcher", timeout=120)
+    out = _run([str(threads), str(per_thread), str(window), str(wait_us), str(mapped)], name="test_batcher", timeout=120)
     res = json.loads(out.strip().splitlines()[-1])
     assert res["mismatches_vs_oracle"] == 0 and res["requests"] == threads * per_thread
     assert res["batches"] >= 1 and res["decisions_per_s"] > 0
+    assert ("mapped" in res["transport"]) == bool(mapped)
