@@ -442,6 +442,9 @@ void smgx_set_fused_prefetch(int flavour);
 /* Requests per warp of the tiled event kernel (8, 16 or 32; 0 = never use it) and the launch size from which it is used (requests; < 0 =
  * the default, tile × 4 × SM count).  Environment: SMGX_FUSED_TILE. */
 void smgx_set_fused_tile(int tile, int64_t min_total);
+/* The simple event kernel (one warp per request, registers only; default): 0 = off, 4 / 5 / 6 = resident 256-thread CTAs per SM it is compiled
+ * for (64 / 48 / 40 registers).  Environment: SMGX_EVENT_SIMPLE. */
+void smgx_set_event_simple(int min_blocks_per_sm);
 /* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
 uint64_t smgx_kernel_launches(const smgx_policy* p);
 /* Writes a buffer larger than L2 (bench hygiene between timed iterations). */

@@ -568,12 +568,6 @@ __device__ __forceinline__ void tile_load(const uint32_t* __restrict__ tokens, u
     }
 }
 
-__device__ __forceinline__ void tile_prefetch(const uint32_t* __restrict__ tokens, uint32_t lo_tok, uint32_t hi_tok) {
-    const uintptr_t lo = reinterpret_cast<uintptr_t>(tokens + lo_tok) & ~(uintptr_t)15;
-    const uintptr_t hi = (reinterpret_cast<uintptr_t>(tokens + hi_tok) + 15) & ~(uintptr_t)15;
-    if (hi > lo && hi - lo <= (1u << 20)) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
-}
-
 template <int TILE, int MINB>
 __global__ void __launch_bounds__(128, MINB) event_tile_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
     extern __shared__ uint64_t smem_ch[];   // [warps][TILE][32]
@@ -602,18 +596,6 @@ __global__ void __launch_bounds__(128, MINB) event_tile_kernel(const __grid_cons
         const uint32_t cnt = min((uint32_t)TILE, n - r0);
         uint32_t off = 0, ntok = 0;
         if ((uint32_t)lane < cnt) { off = __ldg(b.offsets + r0 + lane); ntok = __ldg(b.offsets + r0 + lane + 1) - off; }
-        // the tile's tokens are one contiguous range for back-to-back requests: one bulk L2 prefetch for this tile (the loads below then hit L2)
-        // and one for the tile this warp takes next, so that DRAM latency is paid by the prefetch engine, not by this warp's scoreboard
-        {
-            const uint32_t lo = __shfl_sync(FULL, off, 0), hi = __shfl_sync(FULL, off + ntok, (int)cnt - 1);
-            if (lane == 0 && hi > lo) tile_prefetch(b.tokens, lo, hi);
-            const uint32_t t2 = t + stride;
-            if (t2 < n_tiles) {
-                const uint32_t j2 = t2 / tpb, r2 = (t2 - j2 * tpb) * TILE;
-                const uint32_t cnt2 = min((uint32_t)TILE, n - r2);
-                if (lane == 0) tile_prefetch(a.b[j2].tokens, __ldg(a.b[j2].offsets + r2), __ldg(a.b[j2].offsets + r2 + cnt2));
-            }
-        }
         uint32_t nb = ntok >> 4;
         const bool too_long = nb > a.max_blocks;
         if (too_long) { nb = 0; atomicExch(a.err_flag, 1u); }
@@ -701,6 +683,168 @@ __global__ void __launch_bounds__(128, MINB) event_tile_kernel(const __grid_cons
         if (mine) write_pick(b, r0 + lane, out, branch, matched, ntok);
         __syncwarp();   // the shared-memory rows are reused by the next tile
     }
+}
+
+// ---- the same pick, SIMPLE: one warp per request, no persistence, no software pipeline ------------------------------------------
+// What the measurements of the two kernels above say: a warp that walks several requests pays each request's DRAM latency in sequence
+// (tile kernel: 183 instructions per request but 14 warps per SM doing anything, 2.9 TB/s), and software pipelining costs registers and
+// bookkeeping instructions (440 per request, issue-bound).  The cheapest way to keep ≥ 64 KB per SM in flight is the hardware's own
+// warp scheduler: ONE request per warp, as many warps per SM as the register budget allows, a grid of ⌈requests / 8⌉ CTAs that the block
+// scheduler streams through the SMs.  Everything lives in registers: lane p holds the hash of block p, the two jump destinations are
+// probed by lanes 0 and last, a failed count test drains positions 1..last with one parallel probe per lane and an ordered ballot loop
+// (linear_scan_drain with the retain guard, event_tree.rs:582-657).  Only what needs the rolling prefix hashes or more than one jump
+// (Multi entries, > 32 blocks, jump_size < blocks − 1) is pushed onto a device queue and finished by event_slow_kernel right behind.
+struct SimpleLoc { uint32_t j, r; };
+__device__ __forceinline__ SimpleLoc simple_locate(const MultiArgs& a, uint32_t g) {
+    SimpleLoc l;
+    if (a.uniform_n) { l.j = g / a.uniform_n; l.r = g - l.j * a.uniform_n; }
+    else { l.j = 0; while (l.j + 1 < a.count && a.b[l.j + 1].hash_base <= g) ++l.j; l.r = g - a.b[l.j].hash_base; }
+    return l;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) event_simple_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a,
+                                                                  uint32_t* __restrict__ slow_queue) {
+    __shared__ int32_t s_slice[64];
+    __shared__ uint64_t s_load[64], s_ts[64];
+    if (threadIdx.x < 64) {
+        bool ok = threadIdx.x < v.n_workers;
+        s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= a.total) return;
+    const SimpleLoc loc = simple_locate(a, g);
+    const BatchDesc& b = a.b[loc.j];
+    const uint32_t off = __ldg(b.offsets + loc.r), ntok = __ldg(b.offsets + loc.r + 1) - off;
+    const FleetDerived* fd = f.derived;
+    int32_t out = -1;
+    uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
+    if (fd->n_healthy == 0) {
+    } else if (fd->imbalanced) { out = fd->min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD; }
+    else {
+        const uint32_t nb = ntok >> 4;
+        if (nb > a.max_blocks) { if (lane == 0) atomicExch(a.err_flag, 1u); branch = 255; }
+        else {
+            out = fd->min_load_idx; branch = SMGX_BR_EVENT_MIN_LOAD;   // until an overlap is found
+            if (nb > 0 && v.n_workers > 0) {
+                if (nb > 32 || nb - 1 > v.jump) {   // more than one jump / more blocks than lanes: the generic search
+                    if (lane == 0) slow_queue[1 + atomicAdd(slow_queue, 1u)] = g;
+                    return;
+                }
+                const int last = (int)nb - 1;
+                uint64_t h = 0;
+                if ((uint32_t)lane < nb) h = hash_block<16>(b.tokens + off + (size_t)lane * 16, 16);
+                Slot sl{0, 0, SLOT_EMPTY, 0, 0};
+                bool found = false;
+                if (lane == 0 || lane == last) found = probe(v, (uint32_t)lane, h, sl);
+                const uint64_t elig = f.elig[0];
+                uint64_t win = 0;
+                uint32_t score = 0;
+                bool bail = false;
+                if (__shfl_sync(FULL, (int)found, 0)) {
+                    if (__shfl_sync(FULL, sl.state, 0) != SLOT_SINGLE) bail = true;   // Multi at position 0: needs the prefix hash
+                    else {
+                        uint64_t active = shfl64(sl.payload, 0);
+                        if (last > 0 && active) {
+                            const bool fl = __shfl_sync(FULL, (int)found, last) != 0;
+                            const uint32_t stl = __shfl_sync(FULL, sl.state, last);
+                            uint32_t count = 0;   // count_workers_at(last) (:555-574)
+                            if (fl) { if (stl == SLOT_SINGLE) count = (uint32_t)__popcll(shfl64(sl.payload, last)); else bail = true; }
+                            if (!bail && count != (uint32_t)__popcll(active)) {
+                                // linear_scan_drain over positions 1..=last (:582-657): every position probed at once, one lane each
+                                const bool in_range = lane >= 1 && lane <= last;
+                                if (lane >= 1 && lane < last) found = probe(v, (uint32_t)lane, h, sl);
+                                const uint32_t cnt = (found && sl.state == SLOT_SINGLE) ? (uint32_t)__popcll(sl.payload) : 0;
+                                uint64_t last_set = 0;
+                                uint32_t last_score = 0;
+                                unsigned remaining = __ballot_sync(FULL, in_range);
+                                while (remaining && active) {
+                                    const uint32_t nact = (uint32_t)__popcll(active);
+                                    const bool noop = found && sl.state == SLOT_SINGLE && cnt >= nact;   // retain guard (:611, :641)
+                                    const unsigned bm = __ballot_sync(FULL, in_range && !noop) & remaining;
+                                    if (!bm) break;
+                                    const int k = __ffs((int)bm) - 1;
+                                    if (!__shfl_sync(FULL, (int)found, k)) {   // missing entry drains everything (:598-604)
+                                        const uint64_t e = active & elig;
+                                        if (e) { last_set = e; last_score = (uint32_t)k; }
+                                        active = 0;
+                                        break;
+                                    }
+                                    if (__shfl_sync(FULL, sl.state, k) != SLOT_SINGLE) { bail = true; break; }
+                                    const uint64_t ws = shfl64(sl.payload, k);
+                                    if ((uint32_t)__popcll(ws) < nact) {
+                                        const uint64_t e = active & ~ws & elig;
+                                        if (e) { last_set = e; last_score = (uint32_t)k; }
+                                        active &= ws;
+                                    }
+                                    remaining &= ~((2u << k) - 1u);
+                                }
+                                win = active & elig; score = nb;
+                                if (!win) { win = last_set; score = last_score; }
+                            } else { win = active & elig; score = nb; }
+                        } else { win = active & elig; score = nb; }
+                    }
+                }
+                if (bail) {
+                    if (lane == 0) slow_queue[1 + atomicAdd(slow_queue, 1u)] = g;
+                    return;
+                }
+                if (win) {
+                    Cand c{false, 0, 0, -1};
+                    while (win) { int id = __ffsll((long long)win) - 1; win &= win - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
+                    out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
+                }
+            }
+        }
+    }
+    if (lane == 0) write_pick(b, loc.r, out, branch, matched, ntok);
+}
+
+// the queue of event_simple_kernel: generic warp-cooperative search, one warp per queued request (hashes staged in a shared-memory row)
+__global__ void __launch_bounds__(256) event_slow_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a,
+                                                         uint32_t* __restrict__ slow_queue) {
+    extern __shared__ uint64_t smem_ch[];
+    __shared__ int32_t s_slice[64];
+    __shared__ uint64_t s_load[64], s_ts[64];
+    if (threadIdx.x < 64) {
+        bool ok = threadIdx.x < v.n_workers;
+        s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    uint64_t* ch = smem_ch + (size_t)wic * a.max_blocks;
+    const uint32_t n_slow = slow_queue[0];
+    const uint64_t elig = f.elig[0];
+    const int32_t min_load_idx = f.derived->min_load_idx;
+    for (uint32_t q = blockIdx.x * wpc + wic; q < n_slow; q += gridDim.x * wpc) {
+        const uint32_t g = slow_queue[1 + q];
+        const SimpleLoc loc = simple_locate(a, g);
+        const BatchDesc& b = a.b[loc.j];
+        const uint32_t off = __ldg(b.offsets + loc.r), ntok = __ldg(b.offsets + loc.r + 1) - off;
+        const uint32_t nb = ntok >> 4;
+        for (uint32_t blk = lane; blk < nb; blk += 32) ch[blk] = hash_block<16>(b.tokens + off + (size_t)blk * 16, 16);
+        __syncwarp();
+        const SlowResult sr = fused_slow_search<true>(&v, ch, (int)nb, lane, elig);
+        int32_t out = min_load_idx;
+        uint32_t branch = SMGX_BR_EVENT_MIN_LOAD, matched = 0;
+        if (sr.winset) {
+            uint64_t win = sr.winset;
+            Cand c{false, 0, 0, -1};
+            while (win) { int id = __ffsll((long long)win) - 1; win &= win - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
+            out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = sr.score;
+        }
+        if (lane == 0) write_pick(b, loc.r, out, branch, matched, ntok);
+        __syncwarp();
+    }
+    // the last CTA out resets the queue for the next launch on this lane
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(slow_queue + a.total + 1, 1u) == gridDim.x - 1) { slow_queue[0] = 0; slow_queue[a.total + 1] = 0; }
 }
 
 // L2 prefetch of a request's token range, two pipeline stages ahead of its use: PF = 1 one bulk prefetch per request issued by lane 0
@@ -1038,6 +1182,30 @@ static int fused_tile() {   // SMGX_FUSED_TILE=0|8|16|32: requests per warp of t
     }
     return v;
 }
+static std::atomic<int> g_simple{-1};
+void set_event_simple(int minb) { g_simple.store(minb, std::memory_order_relaxed); }
+static int event_simple_minb() {   // SMGX_EVENT_SIMPLE=0|4|5|6: resident CTAs per SM the simple kernel is compiled for (0 = do not use it)
+    int v = g_simple.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SMGX_EVENT_SIMPLE");
+        v = e ? atoi(e) : 5;
+        if (v != 0 && v != 4 && v != 5 && v != 6) v = 5;
+        g_simple.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+static void launch_simple(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint32_t* d_queue, int minb) {
+    const unsigned grid = (a.total + 7) / 8;
+    if (minb == 4) event_simple_kernel<4><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue);
+    else if (minb == 6) event_simple_kernel<6><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue);
+    else event_simple_kernel<5><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue);
+    SMGX_CUDA(cudaGetLastError());
+    const size_t smem = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
+    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    event_slow_kernel<<<std::min<unsigned>((unsigned)sm_count * 2, std::max(1u, grid)), 256, smem, stream>>>(ix, fleet, a, d_queue);
+    SMGX_CUDA(cudaGetLastError());
+}
+
 template <int TILE>
 static void launch_tile(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
     using K = void (*)(EventIndexView, FleetView, MultiArgs);
@@ -1086,6 +1254,17 @@ void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const
     if (max_n == 0) return;
     if (event_select_fused()) {
         const bool w1 = ix.words == 1;
+        const int simple = event_simple_minb();
+        // the simple kernel: one warp per request, everything in registers, rare shapes queued for event_slow_kernel (see event_simple_kernel)
+        if (simple && w1 && a.block_size == 16 && a.slow_queue && !a.fb_winsets && !a.done_flag && a.max_blocks * 8 * 8 <= 200 * 1024) {
+            bool plain = true;
+            for (uint32_t j = 0; j < a.count; ++j) plain = plain && a.b[j].cand == nullptr;
+            if (plain) {
+                launch_simple(ix, fleet, a, sm_count, stream, a.slow_queue, simple);
+                *launches += 2;
+                return;
+            }
+        }
         const int tile = fused_tile();
         // the tiled kernel: one warp per TILE requests (see event_tile_kernel); needs uniform single-jump requests and enough tiles to fill the GPU
         if (tile && w1 && a.block_size == 16 && a.max_blocks <= 32 && ix.jump + 1 >= a.max_blocks && a.uniform_n && !a.b[0].cand && !a.fb_winsets && !a.done_flag &&

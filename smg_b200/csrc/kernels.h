@@ -74,6 +74,7 @@ struct MultiArgs {
     // load-feedback mode (smgx_set_load_feedback): the fused kernel stores, per request, the eligible set of workers tied on the best
     // overlap score ([total][words] u64, id space) and that score instead of a pick; feedback_resolve_kernel then walks the requests in
     // order, each pick bumping its worker's load before the next request is decided (the router's WorkerLoadGuard, router.rs:319-321).
+    uint32_t* slow_queue;          // event_simple_kernel → event_slow_kernel: [0] = count, [1 .. total] = request indices, [total + 1] = CTA exit counter (all zero between launches)
     uint64_t* fb_winsets;
     uint32_t* fb_scores;           // 0xFFFFFFFF = request longer than max_blocks
     uint32_t total;                // sum of b[k].n  (b[k].hash_base = requests before batch k)
@@ -85,6 +86,7 @@ void set_event_select_fused(bool fused);
 void set_fused_minb(int minb);
 void set_fused_prefetch(int pf);
 void set_fused_tile(int tile, long long min_total);
+void set_event_simple(int minb);
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
 // second phase of the load-feedback mode: one warp resolves a.total requests in order against running loads (starting from `loads`)
 void launch_feedback_resolve(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, const uint64_t* d_loads, const uint8_t* d_flags,

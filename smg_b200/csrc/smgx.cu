@@ -80,6 +80,7 @@ struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
     DevBuf d_fb;   // load-feedback scratch: per-request tied sets + scores
+    DevBuf d_slowq;   // queue between event_simple_kernel and event_slow_kernel
     DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill, d_chunk_start, d_cv, d_hashes;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
@@ -92,7 +93,7 @@ struct Lane {
     // load-feedback bookkeeping of a host-buffer submission (see Policy::wait)
     const uint32_t* fb_tokens = nullptr;
     const uint32_t* fb_offsets = nullptr;
-    const smgx_decision_info* fb_info_host = nullptr;
+    smgx_decision_info* fb_info_host = nullptr;
     std::vector<smgx_decision_info> fb_info;
 };
 
@@ -135,7 +136,7 @@ public:
             cudaSetDevice(cfg.device_id);
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
-                l.d_fb.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
+                l.d_fb.release(); l.d_slowq.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
                 l.d_path_tenant.release(); l.d_fill.release(); l.d_chunk_start.release(); l.d_cv.release(); l.d_hashes.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
@@ -281,6 +282,15 @@ public:
         a.total = (uint32_t)rows;
         a.uniform_n = uniform && count ? descs[0].n : 0;
         a.hashes = nullptr;
+        a.slow_queue = nullptr;
+        if (event_select_fused() && !cand_mode && !done_flag && rows > 0) {   // queue of the simple kernel (zeroed once; the slow kernel leaves it zeroed)
+            const size_t need = ((size_t)rows + 2) * 4;
+            if (need > lane.d_slowq.cap) {
+                lane.d_slowq.reserve(need * 2);
+                SMGX_CUDA(cudaMemsetAsync(lane.d_slowq.ptr, 0, lane.d_slowq.cap, lane.stream));
+            }
+            a.slow_queue = lane.d_slowq.as<uint32_t>();
+        }
         a.fb_winsets = nullptr; a.fb_scores = nullptr;
         const bool feedback = load_feedback && !cand_mode && rows > 0;
         if (feedback) {
@@ -851,19 +861,24 @@ public:
                 // load-feedback batches: the picks that took the imbalanced branch still owe select_worker_min_load's tree update (cache_aware.rs:380-402)
                 std::vector<uint32_t> toks, offs{0};
                 std::vector<int32_t> forced;
+                std::vector<uint32_t> who;
                 for (uint32_t i = 0; i < l.n; ++i) {
                     if (l.fb_info_host[i].branch != SMGX_BR_IMBALANCED_MIN_LOAD || l.host_out[i] < 0) continue;
                     toks.insert(toks.end(), l.fb_tokens + l.fb_offsets[i], l.fb_tokens + l.fb_offsets[i + 1]);
                     offs.push_back((uint32_t)toks.size());
                     forced.push_back(l.host_out[i]);
+                    who.push_back(i);
                 }
                 const ModelState* mp = &m;
                 l.fb_tokens = nullptr;
                 if (!forced.empty()) {
                     std::vector<int32_t> scratch(forced.size());
+                    std::vector<smgx_decision_info> sub(forced.size());
+                    smgx_decision_info* dst = l.fb_info_host;
                     uint32_t dummy = 0;
-                    tree_select(const_cast<ModelState&>(*mp), toks.empty() ? &dummy : toks.data(), offs.data(), (uint32_t)forced.size(), scratch.data(), nullptr, false, nullptr,
+                    tree_select(const_cast<ModelState&>(*mp), toks.empty() ? &dummy : toks.data(), offs.data(), (uint32_t)forced.size(), scratch.data(), sub.data(), false, nullptr,
                                 forced.data(), &l);
+                    for (size_t k = 0; k < who.size(); ++k) { dst[who[k]].matched = sub[k].matched; dst[who[k]].nodes = sub[k].nodes; }   // select_worker_min_load reports the tree match (:380-395)
                 }
             }
             return;
@@ -2624,6 +2639,7 @@ void smgx_set_event_path(int fused, int min_blocks_per_sm) {
 }
 void smgx_set_fused_prefetch(int flavour) { set_fused_prefetch(flavour); }
 void smgx_set_fused_tile(int tile, int64_t min_total) { set_fused_tile(tile, (long long)min_total); }
+void smgx_set_event_simple(int min_blocks_per_sm) { set_event_simple(min_blocks_per_sm); }
 uint64_t smgx_kernel_launches(const smgx_policy* p) { return p ? p->impl.launches : 0; }
 smgx_status smgx_flush_l2(smgx_policy* p, char** err) {
     return guard(err, [&]() {

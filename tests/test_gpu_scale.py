@@ -22,8 +22,9 @@ CFG = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=
 def event_path():
     from smg_b200 import _lib
     L = _lib.load()
-    def setter(fused, minb=0, pf=-1, tile=None, min_total=-1):
+    def setter(fused, minb=0, pf=-1, tile=None, min_total=-1, simple=0):
         L.smgx_set_event_path(1 if fused else 0, minb)
+        L.smgx_set_event_simple(simple)
         if pf >= 0:
             L.smgx_set_fused_prefetch(pf)
         if tile is not None:
@@ -32,6 +33,7 @@ def event_path():
     L.smgx_set_event_path(1, 4)
     L.smgx_set_fused_prefetch(1)
     L.smgx_set_fused_tile(16, -1)
+    L.smgx_set_event_simple(5)
 
 
 def _config2(n_seq, W, T, bs, B):
@@ -56,12 +58,13 @@ def _config2(n_seq, W, T, bs, B):
     return pol, ws, ix, op, seqs
 
 
-@pytest.mark.parametrize("variant", ["tile16", "tile8", "tile32", "tile16-m3", "fused4", "fused3", "fused4-pf2", "fused4-pf0", "split"])
+@pytest.mark.parametrize("variant", ["simple", "tile16", "tile8", "tile32", "tile16-m3", "fused4", "fused3", "fused4-pf2", "fused4-pf0", "split"])
 def test_config2_full_scale_multi_launch(variant, event_path):
     import bench
     from smg_b200 import _lib
     tile = int(variant[4:6].rstrip("-")) if variant.startswith("tile") else 0
-    event_path(variant != "split", 3 if variant.endswith("3") else 4, 2 if variant.endswith("pf2") else 0 if variant.endswith("pf0") else 1, tile=tile)
+    event_path(variant != "split", 3 if variant.endswith("3") else 4, 2 if variant.endswith("pf2") else 0 if variant.endswith("pf0") else 1, tile=tile,
+               simple=5 if variant == "simple" else 0)
     n_seq, W, T, bs, B, NB = 31250, 64, 512, 16, 4096, 37
     pol, ws, ix, op, seqs = _config2(n_seq, W, T, bs, B)
     assert ix.entry_count() == n_seq * (T // bs)
@@ -106,9 +109,10 @@ def test_config2_full_scale_multi_launch(variant, event_path):
 
 @pytest.mark.parametrize("case", [(1, 64, 512, 16, 64, 512), (3, 256, 1024, 16, 64, 256), (5, 64, 512, 64, 64, 256), (7, 100, 2048, 32, 32, 128),
                                   (8, 64, 8192, 16, 64, 48)])
-@pytest.mark.parametrize("variant", ["fused3", "split", "tile8", "tile16", "tile32"])
+@pytest.mark.parametrize("variant", ["fused4", "fused3", "split", "tile8", "tile16", "tile32"])
 def test_random_parity_other_variants(case, variant, event_path):
-    """The randomized ragged parity cases of test_gpu_event_select.py (which run the default fused path) on the other two variants."""
+    """The randomized ragged parity cases of test_gpu_event_select.py (which run the default path: the simple kernel + its slow queue) on every
+    other implementation of the event-driven pick."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("_gpu_event_select", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_event_select.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -117,7 +121,7 @@ def test_random_parity_other_variants(case, variant, event_path):
     if variant.startswith("tile"):   # force the tiled kernel wherever the launch is eligible (≤ 32 blocks, one jump, ≤ 64 workers), however small
         event_path(True, 4, tile=int(variant[4:]), min_total=1)
     else:
-        event_path(variant != "split", 3 if variant == "fused3" else 4, tile=0)
+        event_path(variant != "split", 3 if variant == "fused3" else 4, tile=0)   # simple = 0: the warp-per-request pipelined kernel / the split pair
     test_random_select_parity(*case)
 
 
@@ -158,8 +162,8 @@ def test_duplicate_urls_event_mode(seed, event_path):
             ix.apply_stored(int(w), blocks); oix.apply_stored(int(w), blocks)
     q = synth.gen_queries(seqs, B, seed, block=bs)
     tokens, offsets = synth.ragged(q)
-    for variant in (True, False):
-        event_path(variant)
+    for variant in ("simple", True, False):
+        event_path(variant is not False, simple=5 if variant == "simple" else 0)
         for rnd in range(4):
             loads = rng.integers(0, 6, size=n)            # small range → many equal loads among duplicates
             healthy = (rng.random(n) > 0.2).astype(np.uint8)
