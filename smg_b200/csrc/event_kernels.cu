@@ -546,6 +546,147 @@ __device__ __noinline__ SlowResult fused_slow_search(const EventIndexView* vp, c
     return r;
 }
 
+// ---- search + pick, fleets of ≤ 64 interned workers, second version: balanced drains -------------------------------------------
+// event_search_thread_kernel above is one partial wave whose duration is set by its UNLUCKIEST warp: every request whose count test
+// fails (a stored prefix shorter than the request: ≈ 10 % of BASELINE config 2) is drained in its home warp, one after another, two to
+// three dependent memory round trips each — the warp that happens to hold nine of them finishes ≈ 30 µs after the one that holds none
+// (ncu r01: 39–43 µs per launch whatever its size, warps active 30 %, issue active 14 %).  Here a CTA of 256 requests runs three phases:
+//   A  one THREAD per request: offsets, the two jump-destination hashes from the scratch, both probes in flight together, the count-only
+//      jump test (event_tree.rs:720).  Done for full hits and novel requests; otherwise the request is pushed onto a shared-memory queue;
+//   B  the queue is spread over the CTA's 8 warps (≈ 3 drains per warp instead of up to ≈ 10): lane p loads hash p (one coalesced 256 B
+//      read), every position 1..last is probed at once, the reference's ordered scan with its retain guard is replayed from registers by
+//      a ballot loop — ONE round trip per drain;
+//   C  whatever needs rolling prefix hashes or more than one jump (Multi entries, > 32 blocks, jump_size < blocks − 1) runs the generic
+//      warp-cooperative jump_search on a shared-memory row, again spread over the warps.
+struct Search2Item { uint32_t r; uint32_t nb; };
+
+__global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    extern __shared__ uint64_t smem_ch[];                 // [8 warps][max_blocks] for phase C
+    __shared__ int32_t s_slice[64];
+    __shared__ uint64_t s_load[64], s_ts[64];
+    __shared__ Search2Item s_qb[256], s_qc[256];
+    __shared__ uint32_t s_nb, s_nc;
+    if (threadIdx.x < 64) {
+        bool ok = threadIdx.x < v.n_workers;
+        s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
+    }
+    if (threadIdx.x == 0) { s_nb = 0; s_nc = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const BatchDesc& b = a.b[blockIdx.y];
+    const bool cand_mode = b.cand != nullptr;
+    const FleetDerived fd = *f.derived;
+    const uint64_t elig = f.elig[0];
+    auto finish = [&](uint32_t r, uint64_t win, uint32_t score, uint32_t ntok) {   // argmax + store for one request (any single thread)
+        int32_t out = fd.min_load_idx;
+        uint32_t branch = SMGX_BR_EVENT_MIN_LOAD, matched = 0;
+        Cand c{false, 0, 0, -1};
+        if (win) {
+            while (win) { int id = __ffsll((long long)win) - 1; win &= win - 1; c.consider(s_slice[id], s_load[id], s_ts[id]); }
+            out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
+        }
+        if (cand_mode) {
+            smgx_shard_candidate sc;
+            sc.score = c.have ? matched : 0; sc.local_idx = c.have ? (uint32_t)c.sl : 0xFFFFFFFFu; sc.load = c.ld; sc.tree_size = c.ts;
+            b.cand[r] = sc;
+        } else write_pick(b, r, out, branch, matched, ntok);
+    };
+
+    // ---- phase A ----
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < b.n) {
+        const uint32_t off = __ldg(b.offsets + r), ntok = __ldg(b.offsets + r + 1) - off;
+        if (!cand_mode && fd.n_healthy == 0) write_pick(b, r, -1, SMGX_BR_NO_HEALTHY, 0, ntok);
+        else if (!cand_mode && fd.imbalanced) write_pick(b, r, fd.min_load_idx, SMGX_BR_IMBALANCED_MIN_LOAD, 0, ntok);
+        else {
+            const uint32_t nb = a.block_size ? ntok / a.block_size : 0;
+            if (nb > a.max_blocks) { atomicExch(a.err_flag, 1u); if (!cand_mode) write_pick(b, r, -1, 255, 0, ntok); else finish(r, 0, 0, ntok); }
+            else if (nb == 0 || v.n_workers == 0) finish(r, 0, 0, ntok);
+            else if (nb > 32 || nb - 1 > v.jump) { const uint32_t q = atomicAdd(&s_nc, 1u); s_qc[q] = Search2Item{r, nb}; }
+            else {
+                const uint64_t* ch = a.hashes + ((uint64_t)b.hash_base + r) * a.max_blocks;
+                const int last = (int)nb - 1;
+                const uint64_t c0 = ch[0], c1 = ch[last];
+                const uint32_t h0 = slot_hash(0, c0) & v.mask, h1 = slot_hash((uint32_t)last, c1) & v.mask;
+                Slot s0 = load_slot(v.slots + h0), s1 = load_slot(v.slots + h1);          // both probes in flight together
+                if (!finish_probe(v, 0, c0, h0, s0)) finish(r, 0, 0, ntok);               // nothing cached at position 0 (:676-683)
+                else if (s0.state != SLOT_SINGLE) { const uint32_t q = atomicAdd(&s_nc, 1u); s_qc[q] = Search2Item{r, nb}; }
+                else if (s0.payload == 0 || last == 0) finish(r, s0.payload & elig, nb, ntok);
+                else {
+                    const bool f1 = finish_probe(v, (uint32_t)last, c1, h1, s1);
+                    if (f1 && s1.state != SLOT_SINGLE) { const uint32_t q = atomicAdd(&s_nc, 1u); s_qc[q] = Search2Item{r, nb}; }
+                    else if (f1 && __popcll(s1.payload) == __popcll(s0.payload)) finish(r, s0.payload & elig, nb, ntok);   // count-only jump test (:720)
+                    else { const uint32_t q = atomicAdd(&s_nb, 1u); s_qb[q] = Search2Item{r, nb}; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: register drains, one warp per queued request, the queue striped over the warps ----
+    const uint32_t n_b = s_nb;
+    for (uint32_t q = wic; q < n_b; q += 8) {
+        const Search2Item it = s_qb[q];
+        const int last = (int)it.nb - 1;
+        const uint64_t* ch = a.hashes + ((uint64_t)b.hash_base + it.r) * a.max_blocks;
+        const uint64_t h = (uint32_t)lane < it.nb ? ch[lane] : 0;
+        Slot sl{0, 0, SLOT_EMPTY, 0, 0};
+        bool found = false;
+        if ((uint32_t)lane < it.nb) found = probe(v, (uint32_t)lane, h, sl);           // position 0 again (L2-hot) and 1..last, all at once
+        uint64_t active = shfl64(sl.payload, 0);                                        // phase A saw a Single entry at position 0
+        const bool in_range = lane >= 1 && lane <= last;
+        const uint32_t cnt = (found && sl.state == SLOT_SINGLE) ? (uint32_t)__popcll(sl.payload) : 0;
+        uint64_t last_set = 0;
+        uint32_t last_score = 0;
+        bool bail = !__shfl_sync(FULL, (int)found, 0) || __shfl_sync(FULL, sl.state, 0) != SLOT_SINGLE;   // (index changed under us: cannot happen within a launch)
+        unsigned remaining = __ballot_sync(FULL, in_range);
+        while (!bail && remaining && active) {
+            const uint32_t nact = (uint32_t)__popcll(active);
+            const bool noop = found && sl.state == SLOT_SINGLE && cnt >= nact;           // retain guard (:611, :641)
+            const unsigned bm = __ballot_sync(FULL, in_range && !noop) & remaining;
+            if (!bm) break;
+            const int k = __ffs((int)bm) - 1;
+            if (!__shfl_sync(FULL, (int)found, k)) {                                     // missing entry drains everything (:598-604)
+                const uint64_t e = active & elig;
+                if (e) { last_set = e; last_score = (uint32_t)k; }
+                active = 0;
+                break;
+            }
+            if (__shfl_sync(FULL, sl.state, k) != SLOT_SINGLE) { bail = true; break; }
+            const uint64_t ws = shfl64(sl.payload, k);
+            if ((uint32_t)__popcll(ws) < nact) {
+                const uint64_t e = active & ~ws & elig;
+                if (e) { last_set = e; last_score = (uint32_t)k; }
+                active &= ws;
+            }
+            remaining &= ~((2u << k) - 1u);
+        }
+        if (bail) { if (lane == 0) { const uint32_t qq = atomicAdd(&s_nc, 1u); s_qc[qq] = it; } }
+        else if (lane == 0) {
+            uint64_t win = active & elig;
+            uint32_t score = it.nb;
+            if (!win) { win = last_set; score = last_score; }
+            finish(it.r, win, score, __ldg(b.offsets + it.r + 1) - __ldg(b.offsets + it.r));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: generic search ----
+    const uint32_t n_c = s_nc;
+    uint64_t* row = smem_ch + (size_t)wic * a.max_blocks;
+    for (uint32_t q = wic; q < n_c; q += 8) {
+        const Search2Item it = s_qc[q];
+        const uint64_t* ch = a.hashes + ((uint64_t)b.hash_base + it.r) * a.max_blocks;
+        for (uint32_t i = lane; i < it.nb; i += 32) row[i] = ch[i];
+        __syncwarp();
+        const SlowResult sr = fused_slow_search<true>(&v, row, (int)it.nb, lane, elig);
+        if (lane == 0) finish(it.r, sr.winset, sr.score, __ldg(b.offsets + it.r + 1) - __ldg(b.offsets + it.r));
+        __syncwarp();
+    }
+}
+
 // ---- the same pick, TILED: one warp routes TILE consecutive requests of a batch -------------------------------------------------
 // ncu on the warp-per-request kernel above: 440 warp instructions per request of which only ≈ 110 are the XXH3 arithmetic — pipeline
 // bookkeeping, descriptor fetches, probe/shuffle/pick logic and the store are paid once per REQUEST by a whole warp, and the kernel is
@@ -1296,7 +1437,13 @@ void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const
         ++*launches;
     }
     if (ix.words == 1) {
-        event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
+        static const bool old_search = [] { const char* e = getenv("SMGX_SEARCH_V1"); return e && e[0] == '1'; }();
+        const size_t smem2 = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
+        if (old_search || smem2 > 160 * 1024) event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
+        else {
+            if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            event_search2_kernel<<<dim3((max_n + 255) / 256, a.count), 256, smem2, stream>>>(ix, fleet, a);
+        }
     } else {
         size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;
         int wpc = 8;

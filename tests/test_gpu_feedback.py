@@ -67,7 +67,8 @@ def test_feedback_stream_matches_one_by_one_reference(n_workers, seed):
         oidx, obr, oma, oloads = op.select_batch_tokens_feedback(tokens, offsets.astype(np.uint64))
         assert np.array_equal(idx, oidx), f"round {rnd}: {(idx != oidx).sum()} picks differ"
         assert [i.branch for i in info] == list(obr)
-        assert [i.matched * bs for i in info] == list(oma)
+        # overlap scores are reported in blocks, the imbalanced branch's tree match (select_worker_min_load) in tokens
+        assert [i.matched * bs if i.branch == 2 else i.matched for i in info] == list(oma)
         minload = np.asarray(obr) == 3
         assert minload.sum() > B // 10
         assert len(set(int(x) for x in oidx[minload])) > 8          # water-filling: the min-load picks spread over the fleet …
