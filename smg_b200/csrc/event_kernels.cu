@@ -263,7 +263,14 @@ __global__ void __launch_bounds__(256) hash_blocks_kernel(const __grid_constant_
         const uint32_t off = __ldg(b.offsets + r), ntok = __ldg(b.offsets + r + 1) - off;
         const uint32_t bs = BS ? (uint32_t)BS : a.block_size;
         const uint32_t nb = ntok / bs;
-        if (blk < nb) a.hashes[((uint64_t)b.hash_base + r) * a.max_blocks + blk] = hash_block<BS>(b.tokens + off + (size_t)blk * bs, bs);
+        if (blk < nb) {
+            const uint64_t h = hash_block<BS>(b.tokens + off + (size_t)blk * bs, bs);
+            a.hashes[((uint64_t)b.hash_base + r) * a.max_blocks + blk] = h;
+            // the search kernel probes positions 0 and min(jump, last) first: pull those 32 B slots into L2 now (fire and forget), so that
+            // its dependent chain offsets → hashes → slots runs at L2 latency instead of paying a DRAM miss per probe
+            if (a.pf_slots && (blk == 0 || blk == min(a.pf_jump, nb - 1)))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(blk, h) & a.pf_mask)));
+        }
     }
 }
 
@@ -625,22 +632,17 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
     }
     __syncthreads();
 
-    // ---- phase B: register drains, one warp per queued request, the queue striped over the warps ----
+    // ---- phase B: register drains, one warp per queued request, the queue striped over the warps; two requests per round so that the
+    //      hash loads and the probes of the second overlap those of the first ----
     const uint32_t n_b = s_nb;
-    for (uint32_t q = wic; q < n_b; q += 8) {
-        const Search2Item it = s_qb[q];
+    auto resolve = [&](const Search2Item it, bool found, const Slot& sl) {
         const int last = (int)it.nb - 1;
-        const uint64_t* ch = a.hashes + ((uint64_t)b.hash_base + it.r) * a.max_blocks;
-        const uint64_t h = (uint32_t)lane < it.nb ? ch[lane] : 0;
-        Slot sl{0, 0, SLOT_EMPTY, 0, 0};
-        bool found = false;
-        if ((uint32_t)lane < it.nb) found = probe(v, (uint32_t)lane, h, sl);           // position 0 again (L2-hot) and 1..last, all at once
         uint64_t active = shfl64(sl.payload, 0);                                        // phase A saw a Single entry at position 0
         const bool in_range = lane >= 1 && lane <= last;
         const uint32_t cnt = (found && sl.state == SLOT_SINGLE) ? (uint32_t)__popcll(sl.payload) : 0;
         uint64_t last_set = 0;
         uint32_t last_score = 0;
-        bool bail = !__shfl_sync(FULL, (int)found, 0) || __shfl_sync(FULL, sl.state, 0) != SLOT_SINGLE;   // (index changed under us: cannot happen within a launch)
+        bool bail = !__shfl_sync(FULL, (int)found, 0) || __shfl_sync(FULL, sl.state, 0) != SLOT_SINGLE;
         unsigned remaining = __ballot_sync(FULL, in_range);
         while (!bail && remaining && active) {
             const uint32_t nact = (uint32_t)__popcll(active);
@@ -670,6 +672,25 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
             if (!win) { win = last_set; score = last_score; }
             finish(it.r, win, score, __ldg(b.offsets + it.r + 1) - __ldg(b.offsets + it.r));
         }
+    };
+    for (uint32_t q = wic; q < n_b; q += 16) {
+        const Search2Item it0 = s_qb[q];
+        const bool two = q + 8 < n_b;
+        const Search2Item it1 = two ? s_qb[q + 8] : Search2Item{0, 0};
+        const uint64_t* ch0 = a.hashes + ((uint64_t)b.hash_base + it0.r) * a.max_blocks;
+        const uint64_t* ch1 = a.hashes + ((uint64_t)b.hash_base + it1.r) * a.max_blocks;
+        const uint64_t h0 = (uint32_t)lane < it0.nb ? ch0[lane] : 0;
+        const uint64_t h1 = (uint32_t)lane < it1.nb ? ch1[lane] : 0;
+        // every position of both requests probed at once (position 0 again: L2-hot)
+        const uint32_t i0 = slot_hash((uint32_t)lane, h0) & v.mask, i1 = slot_hash((uint32_t)lane, h1) & v.mask;
+        Slot sl0{0, 0, SLOT_EMPTY, 0, 0}, sl1{0, 0, SLOT_EMPTY, 0, 0};
+        if ((uint32_t)lane < it0.nb) sl0 = load_slot(v.slots + i0);
+        if ((uint32_t)lane < it1.nb) sl1 = load_slot(v.slots + i1);
+        bool f0 = false, f1 = false;
+        if ((uint32_t)lane < it0.nb) f0 = finish_probe(v, (uint32_t)lane, h0, i0, sl0);
+        if ((uint32_t)lane < it1.nb) f1 = finish_probe(v, (uint32_t)lane, h1, i1, sl1);
+        resolve(it0, f0, sl0);
+        if (two) resolve(it1, f1, sl1);
     }
     __syncthreads();
 
@@ -1271,13 +1292,13 @@ void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t*
     SMGX_CUDA(cudaGetLastError());
 }
 
-// 1 = fused (default), 0 = split; initialised from SMGX_EVENT_PATH, switchable at run time for A/B runs and tests
+// 0 = split (default), 1 = fused; initialised from SMGX_EVENT_PATH, switchable at run time for A/B runs and tests
 static std::atomic<int> g_event_path{-1};
 bool event_select_fused() {
     int v = g_event_path.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("SMGX_EVENT_PATH");
-        v = (e && std::string(e) == "split") ? 0 : 1;
+        v = (e && std::string(e) == "fused") ? 1 : 0;   // default: the split pair
         g_event_path.store(v, std::memory_order_relaxed);
     }
     return v == 1;
@@ -1388,54 +1409,32 @@ static void launch_fused(const EventIndexView& ix, const FleetView& fleet, const
     k<<<std::max(1u, std::min(persistent, need)), wpc * 32, smem, stream>>>(ix, fleet, a);
 }
 
-void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
-    if (a.count == 0) return;
+// Which implementation serves a launch.  SMGX_EVENT_PATH / smgx_set_event_path:
+//   split (default for plain picks)  hash stream kernel + balanced search kernel — the hash kernel is a pure bandwidth kernel (2048 resident
+//                                    threads per SM, 5.5 TB/s), the search works on 24 B + probes per request; multi-batch calls pipeline the
+//                                    two over two stream lanes (smgx.cu: enqueue_split_pipelined)
+//   fused                            one kernel per launch (simple / tiled / warp-per-request pipelined: see the kernels above).  Mapped
+//                                    (zero-copy) submissions and load-feedback batches always run the warp-per-request fused kernel: they
+//                                    need its completion word / tied-set outputs.
+static bool needs_fused_kernel(const MultiArgs& a) { return a.done_flag != nullptr || a.fb_winsets != nullptr; }
+bool event_launch_is_split(const MultiArgs& a) { return !event_select_fused() && !needs_fused_kernel(a); }
+
+void launch_event_hash(const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
     uint32_t max_n = 0;
     for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
-    if (max_n == 0) return;
-    if (event_select_fused()) {
-        const bool w1 = ix.words == 1;
-        const int simple = event_simple_minb();
-        // the simple kernel: one warp per request, everything in registers, rare shapes queued for event_slow_kernel (see event_simple_kernel)
-        if (simple && w1 && a.block_size == 16 && a.slow_queue && !a.fb_winsets && !a.done_flag && a.max_blocks * 8 * 8 <= 200 * 1024) {
-            bool plain = true;
-            for (uint32_t j = 0; j < a.count; ++j) plain = plain && a.b[j].cand == nullptr;
-            if (plain) {
-                launch_simple(ix, fleet, a, sm_count, stream, a.slow_queue, simple);
-                *launches += 2;
-                return;
-            }
-        }
-        const int tile = fused_tile();
-        // the tiled kernel: one warp per TILE requests (see event_tile_kernel); needs uniform single-jump requests and enough tiles to fill the GPU
-        if (tile && w1 && a.block_size == 16 && a.max_blocks <= 32 && ix.jump + 1 >= a.max_blocks && a.uniform_n && !a.b[0].cand && !a.fb_winsets && !a.done_flag &&
-            (long long)a.total >= (g_tile_min_total.load(std::memory_order_relaxed) >= 0 ? g_tile_min_total.load(std::memory_order_relaxed) : (long long)tile * 4 * sm_count)) {
-            bool plain = true;
-            for (uint32_t j = 0; j < a.count; ++j) plain = plain && a.b[j].cand == nullptr;
-            if (plain) {
-                if (tile == 8) launch_tile<8>(ix, fleet, a, sm_count, stream);
-                else if (tile == 32) launch_tile<32>(ix, fleet, a, sm_count, stream);
-                else launch_tile<16>(ix, fleet, a, sm_count, stream);
-                SMGX_CUDA(cudaGetLastError());
-                ++*launches;
-                return;
-            }
-        }
-        if (a.block_size == 16) { if (w1) launch_fused<true, 16>(ix, fleet, a, sm_count, stream); else launch_fused<false, 16>(ix, fleet, a, sm_count, stream); }
-        else { if (w1) launch_fused<true, 0>(ix, fleet, a, sm_count, stream); else launch_fused<false, 0>(ix, fleet, a, sm_count, stream); }
-        SMGX_CUDA(cudaGetLastError());
-        ++*launches;
-        return;
-    }
+    if (!max_n || !a.block_size) return;
     // K2b hashes: one thread per block slot, capped at a few waves (grid-stride beyond that)
-    if (a.block_size) {
-        uint64_t threads = (uint64_t)max_n * a.max_blocks;
-        unsigned gx = (unsigned)std::min<uint64_t>((threads + 255) / 256, (uint64_t)sm_count * 64);
-        if (a.block_size == 16) hash_blocks_kernel<16><<<dim3(std::max(1u, gx), a.count), 256, 0, stream>>>(a);
-        else hash_blocks_kernel<0><<<dim3(std::max(1u, gx), a.count), 256, 0, stream>>>(a);
-        SMGX_CUDA(cudaGetLastError());
-        ++*launches;
-    }
+    uint64_t threads = (uint64_t)max_n * a.max_blocks;
+    unsigned gx = (unsigned)std::min<uint64_t>((threads + 255) / 256, (uint64_t)sm_count * 64);
+    if (a.block_size == 16) hash_blocks_kernel<16><<<dim3(std::max(1u, gx), a.count), 256, 0, stream>>>(a);
+    else hash_blocks_kernel<0><<<dim3(std::max(1u, gx), a.count), 256, 0, stream>>>(a);
+    SMGX_CUDA(cudaGetLastError());
+    ++*launches;
+}
+void launch_event_search(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
+    uint32_t max_n = 0;
+    for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
+    if (!max_n) return;
     if (ix.words == 1) {
         static const bool old_search = [] { const char* e = getenv("SMGX_SEARCH_V1"); return e && e[0] == '1'; }();
         const size_t smem2 = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
@@ -1456,6 +1455,51 @@ void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const
     }
     SMGX_CUDA(cudaGetLastError());
     ++*launches;
+}
+
+void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
+    if (a.count == 0) return;
+    uint32_t max_n = 0;
+    for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
+    if (max_n == 0) return;
+    if (event_launch_is_split(a)) {
+        launch_event_hash(a, sm_count, stream, launches);
+        launch_event_search(ix, fleet, a, sm_count, stream, launches);
+        return;
+    }
+    {
+        const bool w1 = ix.words == 1;
+        const int simple = needs_fused_kernel(a) ? 0 : event_simple_minb();
+        // the simple kernel: one warp per request, everything in registers, rare shapes queued for event_slow_kernel (see event_simple_kernel)
+        if (simple && w1 && a.block_size == 16 && a.slow_queue && a.max_blocks * 8 * 8 <= 200 * 1024) {
+            bool plain = true;
+            for (uint32_t j = 0; j < a.count; ++j) plain = plain && a.b[j].cand == nullptr;
+            if (plain) {
+                launch_simple(ix, fleet, a, sm_count, stream, a.slow_queue, simple);
+                *launches += 2;
+                return;
+            }
+        }
+        const int tile = needs_fused_kernel(a) ? 0 : fused_tile();
+        // the tiled kernel: one warp per TILE requests (see event_tile_kernel); needs uniform single-jump requests and enough tiles to fill the GPU
+        if (tile && w1 && a.block_size == 16 && a.max_blocks <= 32 && ix.jump + 1 >= a.max_blocks && a.uniform_n && !a.b[0].cand &&
+            (long long)a.total >= (g_tile_min_total.load(std::memory_order_relaxed) >= 0 ? g_tile_min_total.load(std::memory_order_relaxed) : (long long)tile * 4 * sm_count)) {
+            bool plain = true;
+            for (uint32_t j = 0; j < a.count; ++j) plain = plain && a.b[j].cand == nullptr;
+            if (plain) {
+                if (tile == 8) launch_tile<8>(ix, fleet, a, sm_count, stream);
+                else if (tile == 32) launch_tile<32>(ix, fleet, a, sm_count, stream);
+                else launch_tile<16>(ix, fleet, a, sm_count, stream);
+                SMGX_CUDA(cudaGetLastError());
+                ++*launches;
+                return;
+            }
+        }
+        if (a.block_size == 16) { if (w1) launch_fused<true, 16>(ix, fleet, a, sm_count, stream); else launch_fused<false, 16>(ix, fleet, a, sm_count, stream); }
+        else { if (w1) launch_fused<true, 0>(ix, fleet, a, sm_count, stream); else launch_fused<false, 0>(ix, fleet, a, sm_count, stream); }
+        SMGX_CUDA(cudaGetLastError());
+        ++*launches;
+    }
 }
 
 namespace {

@@ -74,6 +74,9 @@ struct MultiArgs {
     // load-feedback mode (smgx_set_load_feedback): the fused kernel stores, per request, the eligible set of workers tied on the best
     // overlap score ([total][words] u64, id space) and that score instead of a pick; feedback_resolve_kernel then walks the requests in
     // order, each pick bumping its worker's load before the next request is decided (the router's WorkerLoadGuard, router.rs:319-321).
+    // split path: the hash kernel warms L2 with the index slots the search kernel will probe first (positions 0 and min(jump, last))
+    const void* pf_slots;          // EventIndexView.slots (nullable)
+    uint32_t pf_mask, pf_jump;
     uint32_t* slow_queue;          // event_simple_kernel → event_slow_kernel: [0] = count, [1 .. total] = request indices, [total + 1] = CTA exit counter (all zero between launches)
     uint64_t* fb_winsets;
     uint32_t* fb_scores;           // 0xFFFFFFFF = request longer than max_blocks
@@ -88,6 +91,10 @@ void set_fused_prefetch(int pf);
 void set_fused_tile(int tile, long long min_total);
 void set_event_simple(int minb);
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
+// the two halves of the split path, for callers that pipeline them over two streams; event_launch_is_split: would launch_event_select run them?
+bool event_launch_is_split(const MultiArgs& a);
+void launch_event_hash(const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
+void launch_event_search(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
 // second phase of the load-feedback mode: one warp resolves a.total requests in order against running loads (starting from `loads`)
 void launch_feedback_resolve(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, const uint64_t* d_loads, const uint8_t* d_flags,
                              uint32_t n_slice, uint64_t abs_threshold, float rel_threshold, uint64_t* d_loads_out, cudaStream_t stream);

@@ -158,6 +158,7 @@ public:
                 m.d_ring_pos.release(); m.d_ring_slice.release(); m.d_ring_url.release(); m.d_ring_bucket.release(); m.d_dup_prev.release();
                 m.d_pf_loads.release(); m.d_pf_flags.release(); m.d_pf_derived.release();
             }
+            for (uint32_t i = 0; i < kPipeSlots; ++i) { if (pipe_hashed[i]) cudaEventDestroy(pipe_hashed[i]); if (pipe_searched[i]) cudaEventDestroy(pipe_searched[i]); }
             for (int b = 0; b < 2; ++b) {
                 pf_hash_buf[b].release();
                 if (pf_hash_ev[b]) cudaEventDestroy(pf_hash_ev[b]);
@@ -294,7 +295,6 @@ public:
         a.fb_winsets = nullptr; a.fb_scores = nullptr;
         const bool feedback = load_feedback && !cand_mode && rows > 0;
         if (feedback) {
-            if (!event_select_fused()) throw Error(SMGX_INVALID_ARGUMENT, "load feedback needs the fused event path");
             if (m.fleet_has_dups) throw Error(SMGX_INVALID_ARGUMENT, "load feedback is not available for worker slices with duplicate URLs");
             lane.d_fb.reserve(rows * ixv.words * 8 + rows * 4 + 64);
             a.fb_winsets = lane.d_fb.as<uint64_t>();
@@ -303,12 +303,15 @@ public:
         a.done_flag = feedback ? nullptr : done_flag; a.done_value = done_value; a.done_counter = nullptr;
         if (feedback && done_flag) throw Error(SMGX_INVALID_ARGUMENT, "mapped submissions do not combine with load feedback (the in-order pass publishes the picks)");
         if (done_flag) {
-            if (!event_select_fused()) throw Error(SMGX_INVALID_ARGUMENT, "mapped submissions need the fused event path");
             a.done_counter = d_done_counters.as<uint32_t>() + (done_seq++ % kDoneCounters);
         }
-        if (!event_select_fused()) {
+        a.pf_slots = nullptr; a.pf_mask = 0; a.pf_jump = 0;
+        if (event_launch_is_split(a)) {
+            if (&lane == &lanes[0])   // lane 0's scratch doubles as the ring of enqueue_split_pipelined: its readers run on lane 1
+                for (uint32_t i = 0; i < kPipeSlots; ++i) if (pipe_used[i]) SMGX_CUDA(cudaStreamWaitEvent(lane.stream, pipe_searched[i], 0));
             lane.d_hash.reserve(std::max<uint64_t>(rows, 1) * a.max_blocks * 8);
             a.hashes = lane.d_hash.as<uint64_t>();
+            a.pf_slots = ixv.slots; a.pf_mask = ixv.mask; a.pf_jump = ixv.jump;
         }
         a.err_flag = d_err.as<uint32_t>();
         launch_event_select(ixv, fv, a, sm_count, lane.stream, &launches);
@@ -319,6 +322,61 @@ public:
         }
         SMGX_CUDA(cudaEventRecord(lane.done, lane.stream));
         lane.has_done = true;
+    }
+    // Several device-resident batches on the split path: the hash stream of chunk c+1 runs on lane 0 while the search of chunk c runs on
+    // lane 1, so a call's duration is the hash stream (HBM-bound) plus the last chunk's search instead of the sum of both for every chunk.
+    // The hash scratch is a ring of kPipeSlots chunk-sized regions guarded by events in both directions.
+    static constexpr uint32_t kPipeSlots = 4;
+    cudaEvent_t pipe_hashed[kPipeSlots] = {}, pipe_searched[kPipeSlots] = {};
+    bool pipe_used[kPipeSlots] = {};
+    uint64_t pipe_seq = 0;
+    bool enqueue_split_pipelined(ModelState& m, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens) {
+        if (count < 2 || lanes.size() < 2 || load_feedback || event_select_fused()) return false;
+        if (!has_event_indexer(m)) return false;   // let enqueue_batches raise the error
+        EventIndexView ixv;
+        FleetView fv;
+        sync_state(m, &ixv, &fv);
+        const uint32_t bs = block_size_for(m);
+        const uint32_t max_blocks = bs ? std::max<uint32_t>(max_req_tokens / bs, 1) : 1;
+        // chunk size: at most kMaxMultiBatches, at least 2 chunks per call, about 4 for short calls so that only ~1/4 of the search is exposed
+        const uint32_t per = std::min<uint32_t>(kMaxMultiBatches, std::max<uint32_t>(1, (count + 3) / 4));
+        uint32_t max_n = 0;
+        for (uint32_t k = 0; k < count; ++k) max_n = std::max(max_n, descs[k].n);
+        const uint64_t slot_rows = (uint64_t)per * max_n;
+        SMGX_REQUIRE(slot_rows < (1ull << 32), "too many requests in one launch");
+        Lane& lh = lanes[0];
+        Lane& ls = lanes[1];
+        lh.d_hash.reserve(std::max<uint64_t>(slot_rows, 1) * max_blocks * 8 * kPipeSlots);
+        for (uint32_t i = 0; i < kPipeSlots; ++i) if (!pipe_hashed[i]) {
+            SMGX_CUDA(cudaEventCreateWithFlags(&pipe_hashed[i], cudaEventDisableTiming));
+            SMGX_CUDA(cudaEventCreateWithFlags(&pipe_searched[i], cudaEventDisableTiming));
+        }
+        for (uint32_t j0 = 0; j0 < count; j0 += per) {
+            const uint32_t cnt = std::min(per, count - j0);
+            const uint32_t slot = (uint32_t)(pipe_seq++ % kPipeSlots);
+            MultiArgs a;
+            a.count = cnt; a.block_size = bs; a.max_blocks = max_blocks;
+            uint64_t rows = 0;
+            bool uniform = true;
+            for (uint32_t k = 0; k < cnt; ++k) { a.b[k] = descs[j0 + k]; a.b[k].hash_base = (uint32_t)rows; rows += descs[j0 + k].n; uniform = uniform && descs[j0 + k].n == descs[j0].n; }
+            a.total = (uint32_t)rows; a.uniform_n = uniform ? descs[j0].n : 0;
+            a.hashes = lh.d_hash.as<uint64_t>() + (uint64_t)slot * slot_rows * max_blocks;
+            a.slow_queue = nullptr; a.fb_winsets = nullptr; a.fb_scores = nullptr;
+            a.done_flag = nullptr; a.done_value = 0; a.done_counter = nullptr;
+            a.pf_slots = ixv.slots; a.pf_mask = ixv.mask; a.pf_jump = ixv.jump;
+            a.err_flag = d_err.as<uint32_t>();
+            if (pipe_used[slot]) SMGX_CUDA(cudaStreamWaitEvent(lh.stream, pipe_searched[slot], 0));   // the region's previous reader is done
+            launch_event_hash(a, sm_count, lh.stream, &launches);
+            SMGX_CUDA(cudaEventRecord(pipe_hashed[slot], lh.stream));
+            SMGX_CUDA(cudaStreamWaitEvent(ls.stream, pipe_hashed[slot], 0));
+            launch_event_search(ixv, fv, a, sm_count, ls.stream, &launches);
+            SMGX_CUDA(cudaEventRecord(pipe_searched[slot], ls.stream));
+            pipe_used[slot] = true;
+        }
+        SMGX_CUDA(cudaEventRecord(lh.done, lh.stream));
+        SMGX_CUDA(cudaEventRecord(ls.done, ls.stream));
+        lh.has_done = ls.has_done = true;
+        return true;
     }
     void enqueue_tokens(ModelState& m, Lane& lane, const uint32_t* d_tokens, const uint32_t* d_offsets, uint32_t n, uint32_t max_req_tokens,
                         int32_t* d_out, smgx_decision_info* d_info) {
@@ -2376,6 +2434,11 @@ smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key
         P.use_device();
         ModelState& m = P.model(model_key, false);
         uint32_t cap = max_request_tokens ? std::min(max_request_tokens, P.cfg.max_tokens_per_request) : P.cfg.max_tokens_per_request;
+        if (n_batches >= 2 && n_batches <= 4096) {   // split path: hash stream and searches pipelined over two lanes
+            std::vector<BatchDesc> all(n_batches);
+            for (uint32_t k = 0; k < n_batches; ++k) all[k] = BatchDesc{d_tokens[k], d_offsets[k], d_out_worker_idx[k], nullptr, n[k], 0, nullptr};
+            if (P.enqueue_split_pipelined(m, all.data(), n_batches, cap)) return SMGX_SUCCESS;
+        }
         // up to kMaxMultiBatches batches per launch (blockIdx.y = batch); chunks alternate over the stream lanes
         uint32_t chunk_no = 0;
         for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxMultiBatches, ++chunk_no) {

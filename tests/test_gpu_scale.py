@@ -30,7 +30,7 @@ def event_path():
         if tile is not None:
             L.smgx_set_fused_tile(tile, min_total)
     yield setter
-    L.smgx_set_event_path(1, 4)
+    L.smgx_set_event_path(0, 4)   # the default: split pair (hash stream + balanced search)
     L.smgx_set_fused_prefetch(1)
     L.smgx_set_fused_tile(16, -1)
     L.smgx_set_event_simple(5)
@@ -58,7 +58,7 @@ def _config2(n_seq, W, T, bs, B):
     return pol, ws, ix, op, seqs
 
 
-@pytest.mark.parametrize("variant", ["simple", "tile16", "tile8", "tile32", "tile16-m3", "fused4", "fused3", "fused4-pf2", "fused4-pf0", "split"])
+@pytest.mark.parametrize("variant", ["split", "simple", "tile16", "tile8", "tile32", "tile16-m3", "fused4", "fused3", "fused4-pf2", "fused4-pf0"])
 def test_config2_full_scale_multi_launch(variant, event_path):
     import bench
     from smg_b200 import _lib
@@ -94,6 +94,14 @@ def test_config2_full_scale_multi_launch(variant, event_path):
         assert np.array_equal(got, want), f"batch {r}: {(got != want).sum()} of {B} picks differ from the oracle"
         n_overlap += int((np.asarray(br) == 2).sum())
     assert n_overlap > 0.8 * NB * B        # ≈ 90 % of the mix has a stored prefix
+    if variant == "split":   # 150 batches in one call: five 32-batch chunks, the hash-scratch ring of the two-lane pipeline wraps around
+        rep = [i % NB for i in range(150)]
+        h.call("smgx_select_many_tokens_device", model, 150, (C.c_void_p * 150)(*[d_tok[i] for i in rep]), (C.c_void_p * 150)(*[d_off] * 150),
+               (C.c_uint32 * 150)(*[B] * 150), T, (C.c_void_p * 150)(*[d_out[i] for i in rep]))
+        h.call("smgx_synchronize")
+        for r in (0, 17, 36):
+            h.call("smgx_memcpy_d2h", got.ctypes.data_as(C.c_void_p), d_out[r], B * 4)
+            assert np.array_equal(got, op.select_batch_tokens(host[r], off64)[0])
     # a ragged batch with non-uniform sizes per launch (different n per batch → the per-batch lookup path of the fused kernel)
     ns = [4096, 1000, 1, 2500]
     NSr = (C.c_uint32 * 4)(*ns)
@@ -109,9 +117,9 @@ def test_config2_full_scale_multi_launch(variant, event_path):
 
 @pytest.mark.parametrize("case", [(1, 64, 512, 16, 64, 512), (3, 256, 1024, 16, 64, 256), (5, 64, 512, 64, 64, 256), (7, 100, 2048, 32, 32, 128),
                                   (8, 64, 8192, 16, 64, 48)])
-@pytest.mark.parametrize("variant", ["fused4", "fused3", "split", "tile8", "tile16", "tile32"])
+@pytest.mark.parametrize("variant", ["simple", "fused4", "fused3", "tile8", "tile16", "tile32"])
 def test_random_parity_other_variants(case, variant, event_path):
-    """The randomized ragged parity cases of test_gpu_event_select.py (which run the default path: the simple kernel + its slow queue) on every
+    """The randomized ragged parity cases of test_gpu_event_select.py (which run the default path: hash stream + balanced search kernel) on every
     other implementation of the event-driven pick."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("_gpu_event_select", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_event_select.py"))
@@ -121,7 +129,7 @@ def test_random_parity_other_variants(case, variant, event_path):
     if variant.startswith("tile"):   # force the tiled kernel wherever the launch is eligible (≤ 32 blocks, one jump, ≤ 64 workers), however small
         event_path(True, 4, tile=int(variant[4:]), min_total=1)
     else:
-        event_path(variant != "split", 3 if variant == "fused3" else 4, tile=0)   # simple = 0: the warp-per-request pipelined kernel / the split pair
+        event_path(True, 3 if variant == "fused3" else 4, tile=0, simple=5 if variant == "simple" else 0)
     test_random_select_parity(*case)
 
 
@@ -162,8 +170,8 @@ def test_duplicate_urls_event_mode(seed, event_path):
             ix.apply_stored(int(w), blocks); oix.apply_stored(int(w), blocks)
     q = synth.gen_queries(seqs, B, seed, block=bs)
     tokens, offsets = synth.ragged(q)
-    for variant in ("simple", True, False):
-        event_path(variant is not False, simple=5 if variant == "simple" else 0)
+    for variant in ("split", "simple", "fused"):
+        event_path(variant != "split", simple=5 if variant == "simple" else 0, tile=0)
         for rnd in range(4):
             loads = rng.integers(0, 6, size=n)            # small range → many equal loads among duplicates
             healthy = (rng.random(n) > 0.2).astype(np.uint8)

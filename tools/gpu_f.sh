@@ -11,7 +11,7 @@ SMGX_EVENT_PATH=split timeout 300 python bench.py --steps 2000 --warmup 5 --lane
 SMGX_EVENT_PATH=split timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_f.csv python bench.py --steps 20 --warmup 5 --no-text-in --no-per-request --no-cpu-baseline > gpurun_out/b_under_ncu.log 2>&1
 SMGX_EVENT_PATH=split timeout 900 ncu --set full --clock-control none --import-source on -k regex:event_search2 -s 12 -c 2 -o gpurun_out/search2_r02f -f python bench.py --steps 20 --warmup 5 --no-text-in --no-per-request --no-cpu-baseline > gpurun_out/b_under_ncu_full.log 2>&1
 grep -E "^FAILED|passed|failed" gpurun_out/pytest_gpu.log | tail -8
-for f in gpurun_out/bench_f_*.json; do python - "$f" <<'PY'
+for f in gpurun_out/bench_g_*.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1]))
