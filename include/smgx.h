@@ -432,6 +432,8 @@ smgx_status smgx_timer_start_all(smgx_policy* p, char** err);
 /* start_all behind a hold kernel of ~hold_us µs: work enqueued during the hold runs back to back afterwards, so the measured interval is GPU
  * execution only (no host launch latency between the start event and the first kernel). */
 smgx_status smgx_timer_start_all_gated(smgx_policy* p, uint32_t hold_us, char** err);
+smgx_status smgx_timer_start_gated(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err);
+smgx_status smgx_stream_hold(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err);       /* only the hold kernel */   /* one lane; stop with smgx_timer_stop_ms(lane) */
 smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
 /* Process-wide switch between the two implementations of the event-driven pick (A/B measurements, tests): fused != 0 (default) = the
  * one-kernel persistent path, 0 = the round-1 hash kernel + search kernel pair.  min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant

@@ -292,7 +292,7 @@ private:
                 if (ship && flying.size() >= opt_.max_inflight && !full) ship = false;   // GPU busy: let the batch grow (group commit)
                 if (ship && flying.size() >= 2 * (size_t)opt_.max_inflight) ship = false; // even full batches queue only so deep
             }
-            bool close_req;
+            bool close_req = false;
             if (!ship) {
                 // a caller may be asking for a rotation (its request did not fit) or for space; serve that under the lock, rarely
                 ++idle;
@@ -307,6 +307,14 @@ private:
             if (stop_) break;
             Batch& b = *ring_[open_];
             if (b.state != OPEN) continue;
+            if (!close_req && ring_.size() >= opt_.max_ring) {
+                // ring pressure: callers hold tickets of almost every batch (deep windows produce many small batches).  Let this one fill up
+                // for a while instead of burning the last free batches on a handful of requests each.
+                uint32_t free_batches = 0;
+                for (auto& x : ring_) free_batches += x->state == FREE;
+                if (free_batches <= 2 && slots_of(b.rsv.load(std::memory_order_relaxed)) < opt_.max_batch / 4 &&
+                    std::chrono::steady_clock::now() - first_seen < std::chrono::microseconds(200)) continue;
+            }
             const uint64_t rr = b.rsv.fetch_or(kClosed, std::memory_order_acq_rel);
             const uint32_t n = slots_of(rr);
             if (n == 0) { b.rsv.store(rr & ~kClosed, std::memory_order_release); continue; }   // raced with a recycle: nothing to ship

@@ -162,6 +162,8 @@ def load():
     sig("smgx_timer_stop_ms", st, vp, u32, P(C.c_float), pp)
     sig("smgx_timer_start_all", st, vp, pp)
     sig("smgx_timer_start_all_gated", st, vp, u32, pp)
+    sig("smgx_timer_start_gated", st, vp, u32, u32, pp)
+    sig("smgx_stream_hold", st, vp, u32, u32, pp)
     sig("smgx_timer_stop_all_ms", st, vp, P(C.c_float), pp)
     sig("smgx_set_event_path", None, C.c_int, C.c_int)
     sig("smgx_set_fused_prefetch", None, C.c_int)

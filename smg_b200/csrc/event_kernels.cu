@@ -263,9 +263,14 @@ __global__ void __launch_bounds__(256) hash_blocks_kernel(const __grid_constant_
         const uint32_t off = __ldg(b.offsets + r), ntok = __ldg(b.offsets + r + 1) - off;
         const uint32_t bs = BS ? (uint32_t)BS : a.block_size;
         const uint32_t nb = ntok / bs;
+        if (blk == 0 && a.recs) a.recs[(uint64_t)b.hash_base + r].ntok = ntok;
         if (blk < nb) {
             const uint64_t h = hash_block<BS>(b.tokens + off + (size_t)blk * bs, bs);
             a.hashes[((uint64_t)b.hash_base + r) * a.max_blocks + blk] = h;
+            if (a.recs) {   // the search kernel's phase A reads these instead of walking offsets → hash row
+                if (blk == 0) a.recs[(uint64_t)b.hash_base + r].h0 = h;
+                if (blk == min(a.pf_jump, nb - 1)) a.recs[(uint64_t)b.hash_base + r].h1 = h;
+            }
             // the search kernel probes positions 0 and min(jump, last) first: pull those 32 B slots into L2 now (fire and forget), so that
             // its dependent chain offsets → hashes → slots runs at L2 latency instead of paying a DRAM miss per probe
             if (a.pf_slots && (blk == 0 || blk == min(a.pf_jump, nb - 1)))
@@ -567,6 +572,7 @@ __device__ __noinline__ SlowResult fused_slow_search(const EventIndexView* vp, c
 //      warp-cooperative jump_search on a shared-memory row, again spread over the warps.
 struct Search2Item { uint32_t r; uint32_t nb; };
 
+template <int RPC>   // requests per CTA handled by phase A (256 threads either way: the queues of phases B / C are spread over all 8 warps)
 __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
     extern __shared__ uint64_t smem_ch[];                 // [8 warps][max_blocks] for phase C
     __shared__ int32_t s_slice[64];
@@ -602,9 +608,10 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
     };
 
     // ---- phase A ----
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < b.n) {
-        const uint32_t off = __ldg(b.offsets + r), ntok = __ldg(b.offsets + r + 1) - off;
+    const uint32_t r = blockIdx.x * RPC + threadIdx.x;
+    if (threadIdx.x < RPC && r < b.n) {
+        const SearchRec rec = a.recs[(uint64_t)b.hash_base + r];   // one 32 B record written by the hash kernel
+        const uint32_t ntok = rec.ntok;
         if (!cand_mode && fd.n_healthy == 0) write_pick(b, r, -1, SMGX_BR_NO_HEALTHY, 0, ntok);
         else if (!cand_mode && fd.imbalanced) write_pick(b, r, fd.min_load_idx, SMGX_BR_IMBALANCED_MIN_LOAD, 0, ntok);
         else {
@@ -613,11 +620,10 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
             else if (nb == 0 || v.n_workers == 0) finish(r, 0, 0, ntok);
             else if (nb > 32 || nb - 1 > v.jump) { const uint32_t q = atomicAdd(&s_nc, 1u); s_qc[q] = Search2Item{r, nb}; }
             else {
-                const uint64_t* ch = a.hashes + ((uint64_t)b.hash_base + r) * a.max_blocks;
                 const int last = (int)nb - 1;
-                const uint64_t c0 = ch[0], c1 = ch[last];
+                const uint64_t c0 = rec.h0, c1 = rec.h1;
                 const uint32_t h0 = slot_hash(0, c0) & v.mask, h1 = slot_hash((uint32_t)last, c1) & v.mask;
-                Slot s0 = load_slot(v.slots + h0), s1 = load_slot(v.slots + h1);          // both probes in flight together
+                Slot s0 = load_slot(v.slots + h0), s1 = load_slot(v.slots + h1);          // both probes in flight together (L2-warm: prefetched by the hash kernel)
                 if (!finish_probe(v, 0, c0, h0, s0)) finish(r, 0, 0, ntok);               // nothing cached at position 0 (:676-683)
                 else if (s0.state != SLOT_SINGLE) { const uint32_t q = atomicAdd(&s_nc, 1u); s_qc[q] = Search2Item{r, nb}; }
                 else if (s0.payload == 0 || last == 0) finish(r, s0.payload & elig, nb, ntok);
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
             uint64_t win = active & elig;
             uint32_t score = it.nb;
             if (!win) { win = last_set; score = last_score; }
-            finish(it.r, win, score, __ldg(b.offsets + it.r + 1) - __ldg(b.offsets + it.r));
+            finish(it.r, win, score, a.recs[(uint64_t)b.hash_base + it.r].ntok);
         }
     };
     for (uint32_t q = wic; q < n_b; q += 16) {
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
         for (uint32_t i = lane; i < it.nb; i += 32) row[i] = ch[i];
         __syncwarp();
         const SlowResult sr = fused_slow_search<true>(&v, row, (int)it.nb, lane, elig);
-        if (lane == 0) finish(it.r, sr.winset, sr.score, __ldg(b.offsets + it.r + 1) - __ldg(b.offsets + it.r));
+        if (lane == 0) finish(it.r, sr.winset, sr.score, a.recs[(uint64_t)b.hash_base + it.r].ntok);
         __syncwarp();
     }
 }
@@ -866,7 +872,7 @@ __device__ __forceinline__ SimpleLoc simple_locate(const MultiArgs& a, uint32_t 
 
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) event_simple_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a,
-                                                                  uint32_t* __restrict__ slow_queue) {
+                                                                  uint32_t* __restrict__ slow_queue, uint32_t pf_ahead) {
     __shared__ int32_t s_slice[64];
     __shared__ uint64_t s_load[64], s_ts[64];
     if (threadIdx.x < 64) {
@@ -882,6 +888,16 @@ __global__ void __launch_bounds__(256, MINB) event_simple_kernel(const __grid_co
     const SimpleLoc loc = simple_locate(a, g);
     const BatchDesc& b = a.b[loc.j];
     const uint32_t off = __ldg(b.offsets + loc.r), ntok = __ldg(b.offsets + loc.r + 1) - off;
+    if (pf_ahead && g + pf_ahead < a.total && lane == 0) {
+        // pull the tokens of a request a couple of waves ahead into L2 (one bulk prefetch, fire and forget): the warp that will own it then
+        // starts its dependent chain with an L2 hit instead of a DRAM miss
+        const SimpleLoc lp = simple_locate(a, g + pf_ahead);
+        const BatchDesc& bp = a.b[lp.j];
+        const uint32_t po = __ldg(bp.offsets + lp.r), pe = __ldg(bp.offsets + lp.r + 1);
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(bp.tokens + po) & ~(uintptr_t)15;
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(bp.tokens + pe) + 15) & ~(uintptr_t)15;
+        if (hi > lo && hi - lo <= (1u << 16)) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo)) : "memory");
+    }
     const FleetDerived* fd = f.derived;
     int32_t out = -1;
     uint32_t branch = SMGX_BR_NO_HEALTHY, matched = 0;
@@ -1358,9 +1374,11 @@ static int event_simple_minb() {   // SMGX_EVENT_SIMPLE=0|4|5|6: resident CTAs p
 }
 static void launch_simple(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint32_t* d_queue, int minb) {
     const unsigned grid = (a.total + 7) / 8;
-    if (minb == 4) event_simple_kernel<4><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue);
-    else if (minb == 6) event_simple_kernel<6><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue);
-    else event_simple_kernel<5><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue);
+    static const int pf_waves = [] { const char* e = getenv("SMGX_SIMPLE_PF"); return e ? atoi(e) : 0; }();   // waves of resident warps to prefetch ahead (0 = off)
+    const uint32_t pf_ahead = (uint32_t)std::max(pf_waves, 0) * 48u * (uint32_t)sm_count;
+    if (minb == 4) event_simple_kernel<4><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue, pf_ahead);
+    else if (minb == 6) event_simple_kernel<6><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue, pf_ahead);
+    else event_simple_kernel<5><<<grid, 256, 0, stream>>>(ix, fleet, a, d_queue, pf_ahead);
     SMGX_CUDA(cudaGetLastError());
     const size_t smem = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
     if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1438,10 +1456,17 @@ void launch_event_search(const EventIndexView& ix, const FleetView& fleet, const
     if (ix.words == 1) {
         static const bool old_search = [] { const char* e = getenv("SMGX_SEARCH_V1"); return e && e[0] == '1'; }();
         const size_t smem2 = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
-        if (old_search || smem2 > 160 * 1024) event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
+        if (old_search || smem2 > 160 * 1024 || !a.recs) event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
         else {
-            if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            event_search2_kernel<<<dim3((max_n + 255) / 256, a.count), 256, smem2, stream>>>(ix, fleet, a);
+            // 128 requests per CTA while that still fits one wave of resident CTAs (fewer queued drains per warp), else 256
+            const bool small = (uint64_t)((max_n + 127) / 128) * a.count <= (uint64_t)sm_count * 4;
+            if (small) {
+                if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                event_search2_kernel<128><<<dim3((max_n + 127) / 128, a.count), 256, smem2, stream>>>(ix, fleet, a);
+            } else {
+                if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                event_search2_kernel<256><<<dim3((max_n + 255) / 256, a.count), 256, smem2, stream>>>(ix, fleet, a);
+            }
         }
     } else {
         size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;

@@ -50,6 +50,9 @@ void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t*
 //                                (one thread per request for fleets ≤ 64 interned workers, one warp per request above)
 //   `hashes` is then a scratch of sum(n) × max_blocks u64 laid out [request][max_blocks], written and read back out of L2.
 constexpr int kMaxMultiBatches = 32;
+// what the hash kernel leaves per request for the search kernel's first phase: the two hashes the jump search probes first and the
+// request's length — one 32 B record instead of the chain offsets → hash row → slots
+struct alignas(32) SearchRec { uint64_t h0, h1; uint32_t ntok, pad0; uint64_t pad1; };
 struct BatchDesc {
     const uint32_t* tokens;        // device, ragged
     const uint32_t* offsets;       // device, n + 1
@@ -75,6 +78,7 @@ struct MultiArgs {
     // overlap score ([total][words] u64, id space) and that score instead of a pick; feedback_resolve_kernel then walks the requests in
     // order, each pick bumping its worker's load before the next request is decided (the router's WorkerLoadGuard, router.rs:319-321).
     // split path: the hash kernel warms L2 with the index slots the search kernel will probe first (positions 0 and min(jump, last))
+    SearchRec* recs;               // [total] (split path)
     const void* pf_slots;          // EventIndexView.slots (nullable)
     uint32_t pf_mask, pf_jump;
     uint32_t* slow_queue;          // event_simple_kernel → event_slow_kernel: [0] = count, [1 .. total] = request indices, [total + 1] = CTA exit counter (all zero between launches)

@@ -81,6 +81,7 @@ struct Lane {
     cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
     DevBuf d_fb;   // load-feedback scratch: per-request tied sets + scores
     DevBuf d_slowq;   // queue between event_simple_kernel and event_slow_kernel
+    DevBuf d_recs;    // SearchRec per request: hash kernel → search kernel
     DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill, d_chunk_start, d_cv, d_hashes;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
@@ -136,7 +137,7 @@ public:
             cudaSetDevice(cfg.device_id);
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
-                l.d_fb.release(); l.d_slowq.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
+                l.d_fb.release(); l.d_slowq.release(); l.d_recs.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
                 l.d_path_tenant.release(); l.d_fill.release(); l.d_chunk_start.release(); l.d_cv.release(); l.d_hashes.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
@@ -305,12 +306,14 @@ public:
         if (done_flag) {
             a.done_counter = d_done_counters.as<uint32_t>() + (done_seq++ % kDoneCounters);
         }
-        a.pf_slots = nullptr; a.pf_mask = 0; a.pf_jump = 0;
+        a.pf_slots = nullptr; a.pf_mask = 0; a.pf_jump = 0; a.recs = nullptr;
         if (event_launch_is_split(a)) {
             if (&lane == &lanes[0])   // lane 0's scratch doubles as the ring of enqueue_split_pipelined: its readers run on lane 1
                 for (uint32_t i = 0; i < kPipeSlots; ++i) if (pipe_used[i]) SMGX_CUDA(cudaStreamWaitEvent(lane.stream, pipe_searched[i], 0));
             lane.d_hash.reserve(std::max<uint64_t>(rows, 1) * a.max_blocks * 8);
             a.hashes = lane.d_hash.as<uint64_t>();
+            lane.d_recs.reserve(std::max<uint64_t>(rows, 1) * sizeof(SearchRec));
+            a.recs = lane.d_recs.as<SearchRec>();
             a.pf_slots = ixv.slots; a.pf_mask = ixv.mask; a.pf_jump = ixv.jump;
         }
         a.err_flag = d_err.as<uint32_t>();
@@ -331,7 +334,10 @@ public:
     bool pipe_used[kPipeSlots] = {};
     uint64_t pipe_seq = 0;
     bool enqueue_split_pipelined(ModelState& m, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens) {
-        if (count < 2 || lanes.size() < 2 || load_feedback || event_select_fused()) return false;
+        // measured (profiles/r02_event.md): the search kernel is a latency chain of ≈ 20 µs whatever its size, so chunking a short call only
+        // multiplies that chain — the two-lane pipeline stays opt-in (SMGX_SPLIT_PIPE=1) for experiments
+        static const int pipe = [] { const char* e = getenv("SMGX_SPLIT_PIPE"); return e ? atoi(e) : 0; }();   // number of chunks a short call is cut into (0 = off)
+        if (pipe < 2 || count < 2 || count > kMaxMultiBatches || lanes.size() < 4 || load_feedback || event_select_fused()) return false;
         if (!has_event_indexer(m)) return false;   // let enqueue_batches raise the error
         EventIndexView ixv;
         FleetView fv;
@@ -339,21 +345,22 @@ public:
         const uint32_t bs = block_size_for(m);
         const uint32_t max_blocks = bs ? std::max<uint32_t>(max_req_tokens / bs, 1) : 1;
         // chunk size: at most kMaxMultiBatches, at least 2 chunks per call, about 4 for short calls so that only ~1/4 of the search is exposed
-        const uint32_t per = std::min<uint32_t>(kMaxMultiBatches, std::max<uint32_t>(1, (count + 3) / 4));
+        const uint32_t per = std::min<uint32_t>(kMaxMultiBatches, std::max<uint32_t>(1, (count + (uint32_t)pipe - 1) / (uint32_t)pipe));
         uint32_t max_n = 0;
         for (uint32_t k = 0; k < count; ++k) max_n = std::max(max_n, descs[k].n);
         const uint64_t slot_rows = (uint64_t)per * max_n;
         SMGX_REQUIRE(slot_rows < (1ull << 32), "too many requests in one launch");
         Lane& lh = lanes[0];
-        Lane& ls = lanes[1];
         lh.d_hash.reserve(std::max<uint64_t>(slot_rows, 1) * max_blocks * 8 * kPipeSlots);
         for (uint32_t i = 0; i < kPipeSlots; ++i) if (!pipe_hashed[i]) {
             SMGX_CUDA(cudaEventCreateWithFlags(&pipe_hashed[i], cudaEventDisableTiming));
             SMGX_CUDA(cudaEventCreateWithFlags(&pipe_searched[i], cudaEventDisableTiming));
         }
-        for (uint32_t j0 = 0; j0 < count; j0 += per) {
+        uint32_t chunk_idx = 0;
+        for (uint32_t j0 = 0; j0 < count; j0 += per, ++chunk_idx) {
             const uint32_t cnt = std::min(per, count - j0);
             const uint32_t slot = (uint32_t)(pipe_seq++ % kPipeSlots);
+            Lane& ls = lanes[1 + chunk_idx % 3];   // every chunk's search on its own lane: the searches are latency chains and must overlap each other too
             MultiArgs a;
             a.count = cnt; a.block_size = bs; a.max_blocks = max_blocks;
             uint64_t rows = 0;
@@ -364,6 +371,8 @@ public:
             a.slow_queue = nullptr; a.fb_winsets = nullptr; a.fb_scores = nullptr;
             a.done_flag = nullptr; a.done_value = 0; a.done_counter = nullptr;
             a.pf_slots = ixv.slots; a.pf_mask = ixv.mask; a.pf_jump = ixv.jump;
+            lh.d_recs.reserve(std::max<uint64_t>(slot_rows, 1) * sizeof(SearchRec) * kPipeSlots);
+            a.recs = lh.d_recs.as<SearchRec>() + (uint64_t)slot * slot_rows;
             a.err_flag = d_err.as<uint32_t>();
             if (pipe_used[slot]) SMGX_CUDA(cudaStreamWaitEvent(lh.stream, pipe_searched[slot], 0));   // the region's previous reader is done
             launch_event_hash(a, sm_count, lh.stream, &launches);
@@ -373,9 +382,7 @@ public:
             SMGX_CUDA(cudaEventRecord(pipe_searched[slot], ls.stream));
             pipe_used[slot] = true;
         }
-        SMGX_CUDA(cudaEventRecord(lh.done, lh.stream));
-        SMGX_CUDA(cudaEventRecord(ls.done, ls.stream));
-        lh.has_done = ls.has_done = true;
+        for (auto& l : lanes) { SMGX_CUDA(cudaEventRecord(l.done, l.stream)); l.has_done = true; }
         return true;
     }
     void enqueue_tokens(ModelState& m, Lane& lane, const uint32_t* d_tokens, const uint32_t* d_offsets, uint32_t n, uint32_t max_req_tokens,
@@ -2440,10 +2447,15 @@ smgx_status smgx_select_many_tokens_device(smgx_policy* p, const char* model_key
             if (P.enqueue_split_pipelined(m, all.data(), n_batches, cap)) return SMGX_SUCCESS;
         }
         // up to kMaxMultiBatches batches per launch (blockIdx.y = batch); chunks alternate over the stream lanes
+        // SMGX_SPREAD=1 (experiment): a short call is cut into one chunk per lane.  Measured worse than one launch pair (profiles/r02_event.md):
+        // small kernels run below the bandwidth a single large hash stream reaches.
+        static const int spread = [] { const char* e = getenv("SMGX_SPREAD"); return e ? atoi(e) : 0; }();
+        const uint32_t n_lanes = (uint32_t)P.lanes.size();
+        const uint32_t per = spread ? std::min<uint32_t>(kMaxMultiBatches, std::max<uint32_t>(1, (n_batches + n_lanes - 1) / n_lanes)) : kMaxMultiBatches;
         uint32_t chunk_no = 0;
-        for (uint32_t j0 = 0; j0 < n_batches; j0 += kMaxMultiBatches, ++chunk_no) {
+        for (uint32_t j0 = 0; j0 < n_batches; j0 += per, ++chunk_no) {
             BatchDesc d[kMaxMultiBatches];
-            uint32_t cnt = std::min<uint32_t>(kMaxMultiBatches, n_batches - j0);
+            uint32_t cnt = std::min<uint32_t>(per, n_batches - j0);
             for (uint32_t k = 0; k < cnt; ++k) d[k] = BatchDesc{d_tokens[j0 + k], d_offsets[j0 + k], d_out_worker_idx[j0 + k], nullptr, n[j0 + k], 0, nullptr};
             P.enqueue_batches(m, P.lanes[chunk_no % P.lanes.size()], d, cnt, cap);
         }
@@ -2678,6 +2690,29 @@ smgx_status smgx_timer_start_all_gated(smgx_policy* p, uint32_t hold_us, char** 
         launch_hold(hold_us, P.lanes[0].stream);
         SMGX_CUDA(cudaEventRecord(P.lanes[0].t0, P.lanes[0].stream));
         for (size_t i = 1; i < P.lanes.size(); ++i) SMGX_CUDA(cudaStreamWaitEvent(P.lanes[i].stream, P.lanes[0].t0, 0));
+        return SMGX_SUCCESS;
+    });
+}
+// just the hold kernel on `lane` (bench.py: hold → untimed warm-up region → smgx_timer_start → timed region, all enqueued back to back)
+smgx_status smgx_stream_hold(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(lane < P.lanes.size(), "lane out of range");
+        launch_hold(hold_us, P.lanes[lane].stream);
+        return SMGX_SUCCESS;
+    });
+}
+// single-lane form: hold kernel + start event on `lane`; pair with smgx_timer_stop_ms(lane)
+smgx_status smgx_timer_start_gated(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        Policy& P = p->impl;
+        P.use_device();
+        SMGX_REQUIRE(lane < P.lanes.size(), "lane out of range");
+        launch_hold(hold_us, P.lanes[lane].stream);
+        SMGX_CUDA(cudaEventRecord(P.lanes[lane].t0, P.lanes[lane].stream));
         return SMGX_SUCCESS;
     });
 }

@@ -59,7 +59,7 @@ def test_feedback_stream_matches_one_by_one_reference(n_workers, seed):
         healthy = (rng.random(n_workers) > 0.1).astype(np.uint8)
         if rnd == 2:
             loads[:] = 3
-            loads[5] = 200          # starts imbalanced: the gate sends everything to the least loaded worker until (max-min) and the ratio close
+            loads[5] = 80           # starts imbalanced: the gate sends everything to the least loaded worker until max - min <= 64 (≈ 800 picks)
         for i, w in enumerate(ws):
             w.set_load(int(loads[i])); w.set_healthy(bool(healthy[i]))
         op.set_state(loads, healthy, [1] * n_workers)
@@ -69,11 +69,11 @@ def test_feedback_stream_matches_one_by_one_reference(n_workers, seed):
         assert [i.branch for i in info] == list(obr)
         # overlap scores are reported in blocks, the imbalanced branch's tree match (select_worker_min_load) in tokens
         assert [i.matched * bs if i.branch == 2 else i.matched for i in info] == list(oma)
-        minload = np.asarray(obr) == 3
+        minload = np.isin(np.asarray(obr), (1, 3))                   # load-dependent picks: imbalanced-gate and no-overlap min-load
         assert minload.sum() > B // 10
         assert len(set(int(x) for x in oidx[minload])) > 8          # water-filling: the min-load picks spread over the fleet …
         if rnd == 2:
-            assert (np.asarray(obr) == 1).sum() > 0 and (np.asarray(obr) == 2).sum() > 0   # the gate was on, then closed inside the batch
+            assert (np.asarray(obr) == 1).sum() > 100 and (np.asarray(obr) == 2).sum() > 0   # the gate was on, then closed inside the batch
     # … whereas the frozen snapshot sends every min-load request of a batch to ONE worker
     pol.set_load_feedback(False)
     idx2, info2 = pol.select_worker_batch(ws, tokens=tokens, offsets=offsets)
