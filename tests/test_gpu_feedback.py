@@ -59,6 +59,7 @@ def test_feedback_stream_matches_one_by_one_reference(n_workers, seed):
         healthy = (rng.random(n_workers) > 0.1).astype(np.uint8)
         if rnd == 2:
             loads[:] = 3
+            healthy[:] = 1          # (min / max run over ALL workers: an unhealthy one would pin the minimum and keep the gate open)
             loads[5] = 80           # starts imbalanced: the gate sends everything to the least loaded worker until max - min <= 64 (≈ 800 picks)
         for i, w in enumerate(ws):
             w.set_load(int(loads[i])); w.set_healthy(bool(healthy[i]))
