@@ -447,6 +447,9 @@ void smgx_set_fused_tile(int tile, int64_t min_total);
 /* The simple event kernel (one warp per request, registers only; default): 0 = off, 4 / 5 / 6 = resident 256-thread CTAs per SM it is compiled
  * for (64 / 48 / 40 registers).  Environment: SMGX_EVENT_SIMPLE. */
 void smgx_set_event_simple(int min_blocks_per_sm);
+/* Token stream of the tiled kernel: 0 = register double buffer, 4 / 8 = cp.async shared-memory ring of that many requests per warp
+ * (SMGX_TILE_DEPTH). */
+void smgx_set_tile_depth(int depth);
 /* Number of smgx kernel launches issued by this policy so far (bench.py's gpu_launches). */
 uint64_t smgx_kernel_launches(const smgx_policy* p);
 /* Writes a buffer larger than L2 (bench hygiene between timed iterations). */

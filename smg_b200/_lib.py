@@ -169,6 +169,7 @@ def load():
     sig("smgx_set_fused_prefetch", None, C.c_int)
     sig("smgx_set_fused_tile", None, C.c_int, C.c_int64)
     sig("smgx_set_event_simple", None, C.c_int)
+    sig("smgx_set_tile_depth", None, C.c_int)
     sig("smgx_kernel_launches", u64, vp)
     sig("smgx_flush_l2", st, vp, pp)
     _lib = L

@@ -736,9 +736,13 @@ __device__ __forceinline__ void tile_load(const uint32_t* __restrict__ tokens, u
     }
 }
 
-template <int TILE, int MINB>
+// DEPTH > 0: phase 1 streams the tokens through a per-warp shared-memory ring of DEPTH requests filled by cp.async (LDGSTS: 16 B per lane per
+// instruction, [piece][lane] layout so that a lane reads its own 64 B back with four conflict-free LDS.128) — DEPTH × 2 KB per warp are in flight
+// without holding a single register, which is what the register double buffer (DEPTH = 0) could not do: that variant keeps ≤ 2 requests in flight
+// per warp and is latency-bound (14 of 64 warp slots busy, 2.9 TB/s, profiles/r02_event.md).
+template <int TILE, int MINB, int DEPTH>
 __global__ void __launch_bounds__(128, MINB) event_tile_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
-    extern __shared__ uint64_t smem_ch[];   // [warps][TILE][32]
+    extern __shared__ uint64_t smem_ch[];   // [warps][TILE][32] hashes, then (DEPTH > 0) [warps][DEPTH][4][32] uint4 token stages
     __shared__ int32_t s_slice[64];
     __shared__ uint64_t s_load[64], s_ts[64];
     if (threadIdx.x < 64) {
@@ -773,7 +777,38 @@ __global__ void __launch_bounds__(128, MINB) event_tile_kernel(const __grid_cons
         if (!trivial) {
             // 16 B alignment of every request of the tile (warp-uniform): the pipelined loop issues LDG.128 only
             const bool aligned = (reinterpret_cast<uintptr_t>(b.tokens) & 15) == 0 && !__any_sync(FULL, (uint32_t)lane < cnt && (off & 3) != 0);
-            if (aligned) {
+            if (aligned && DEPTH > 0) {
+                uint4* ring = reinterpret_cast<uint4*>(smem_ch + (size_t)wpc * TILE * 32) + (size_t)wic * (DEPTH > 0 ? DEPTH : 1) * 128;
+                auto issue = [&](uint32_t i) {   // request i of the tile → stage i % DEPTH; one commit group per call, empty when there is nothing to copy
+                    if (i < cnt) {
+                        const uint32_t off_i = __shfl_sync(FULL, off, (int)i), nb_i = __shfl_sync(FULL, nb, (int)i);
+                        if ((uint32_t)lane < nb_i) {
+                            const uint32_t* src = b.tokens + off_i + (size_t)lane * 16;
+                            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(i % (DEPTH > 0 ? DEPTH : 1)) * 128 + lane);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 512), "l"(src + k * 4) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+#pragma unroll
+                for (int s0 = 0; s0 < DEPTH; ++s0) issue((uint32_t)s0);
+#pragma unroll 1
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH > 0 ? DEPTH - 1 : 0) : "memory");   // groups complete in order: request i has landed
+                    const uint32_t nb_i = __shfl_sync(FULL, nb, (int)i);
+                    if ((uint32_t)lane < nb_i) {
+                        const uint4* st = ring + (size_t)(i % (DEPTH > 0 ? DEPTH : 1)) * 128 + lane;
+                        uint32_t w[16];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { const uint4 t4 = st[k * 32]; w[4 * k] = t4.x; w[4 * k + 1] = t4.y; w[4 * k + 2] = t4.z; w[4 * k + 3] = t4.w; }
+                        ch[i * 32 + lane] = xxh3_16words(w, kSeed);
+                    }
+                    issue(i + DEPTH);   // refill the stage this lane has just read (every lane touches only its own 64 B of a stage)
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else if (aligned) {
                 uint32_t w0[16], w1[16];
                 uint32_t off_i = __shfl_sync(FULL, off, 0), nb_i = __shfl_sync(FULL, nb, 0);
                 tile_load(b.tokens, off_i, nb_i, lane, w0);
@@ -1386,16 +1421,29 @@ static void launch_simple(const EventIndexView& ix, const FleetView& fleet, cons
     SMGX_CUDA(cudaGetLastError());
 }
 
+static std::atomic<int> g_tile_depth{-1};
+void set_tile_depth(int d) { g_tile_depth.store(d, std::memory_order_relaxed); }
+static int tile_depth() {   // SMGX_TILE_DEPTH=0|4|8: cp.async ring depth of the tiled kernel's token stream (0 = register double buffer)
+    int v = g_tile_depth.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("SMGX_TILE_DEPTH");
+        v = e ? atoi(e) : 0;   // measured: the ring is slower than the register double buffer (profiles/r02_event.md)
+        if (v != 0 && v != 4 && v != 8) v = 0;
+        g_tile_depth.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 template <int TILE>
 static void launch_tile(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
     using K = void (*)(EventIndexView, FleetView, MultiArgs);
-    const int minb = fused_minb();
-    K k = minb == 3 ? (K)event_tile_kernel<TILE, 4> : (K)event_tile_kernel<TILE, 5>;
+    const int minb = fused_minb(), depth = tile_depth();
+    K k = depth == 8 ? (K)event_tile_kernel<TILE, 4, 8> : depth == 4 ? (K)event_tile_kernel<TILE, 4, 4>
+        : minb == 3 ? (K)event_tile_kernel<TILE, 4, 0> : (K)event_tile_kernel<TILE, 5, 0>;
     const int wpc = 4;
-    const size_t smem = (size_t)wpc * TILE * 32 * 8;
-    if (smem > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static thread_local int occ_cache[2] = {0, 0};
-    int& occ = occ_cache[minb == 3 ? 1 : 0];
+    const size_t smem = (size_t)wpc * TILE * 32 * 8 + (size_t)wpc * depth * 2048;
+    if (smem + 2048 > 48 * 1024) SMGX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // + the kernel's static arrays
+    static thread_local int occ_cache[3][2] = {};
+    int& occ = occ_cache[depth == 8 ? 2 : depth == 4 ? 1 : 0][minb == 3 ? 1 : 0];
     if (!occ) SMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
     const unsigned n_tiles = ((a.uniform_n + TILE - 1) / TILE) * a.count;
     const unsigned persistent = (unsigned)sm_count * (unsigned)std::max(occ, 1);

@@ -94,6 +94,7 @@ void set_fused_minb(int minb);
 void set_fused_prefetch(int pf);
 void set_fused_tile(int tile, long long min_total);
 void set_event_simple(int minb);
+void set_tile_depth(int depth);
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches);
 // the two halves of the split path, for callers that pipeline them over two streams; event_launch_is_split: would launch_event_select run them?
 bool event_launch_is_split(const MultiArgs& a);

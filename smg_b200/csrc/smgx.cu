@@ -2738,6 +2738,7 @@ void smgx_set_event_path(int fused, int min_blocks_per_sm) {
 void smgx_set_fused_prefetch(int flavour) { set_fused_prefetch(flavour); }
 void smgx_set_fused_tile(int tile, int64_t min_total) { set_fused_tile(tile, (long long)min_total); }
 void smgx_set_event_simple(int min_blocks_per_sm) { set_event_simple(min_blocks_per_sm); }
+void smgx_set_tile_depth(int depth) { set_tile_depth(depth); }
 uint64_t smgx_kernel_launches(const smgx_policy* p) { return p ? p->impl.launches : 0; }
 smgx_status smgx_flush_l2(smgx_policy* p, char** err) {
     return guard(err, [&]() {

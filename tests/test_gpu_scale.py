@@ -22,9 +22,10 @@ CFG = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=
 def event_path():
     from smg_b200 import _lib
     L = _lib.load()
-    def setter(fused, minb=0, pf=-1, tile=None, min_total=-1, simple=0):
+    def setter(fused, minb=0, pf=-1, tile=None, min_total=-1, simple=0, depth=0):
         L.smgx_set_event_path(1 if fused else 0, minb)
         L.smgx_set_event_simple(simple)
+        L.smgx_set_tile_depth(depth)
         if pf >= 0:
             L.smgx_set_fused_prefetch(pf)
         if tile is not None:
@@ -34,6 +35,7 @@ def event_path():
     L.smgx_set_fused_prefetch(1)
     L.smgx_set_fused_tile(16, -1)
     L.smgx_set_event_simple(5)
+    L.smgx_set_tile_depth(0)
 
 
 def _config2(n_seq, W, T, bs, B):
@@ -58,13 +60,13 @@ def _config2(n_seq, W, T, bs, B):
     return pol, ws, ix, op, seqs
 
 
-@pytest.mark.parametrize("variant", ["split", "simple", "tile16", "tile8", "tile32", "tile16-m3", "fused4", "fused3", "fused4-pf2", "fused4-pf0"])
+@pytest.mark.parametrize("variant", ["split", "simple", "tile16", "tile8", "tile32", "tile16-m3", "tile16-d4", "tile8-d8", "fused4", "fused3", "fused4-pf2", "fused4-pf0"])
 def test_config2_full_scale_multi_launch(variant, event_path):
     import bench
     from smg_b200 import _lib
     tile = int(variant[4:6].rstrip("-")) if variant.startswith("tile") else 0
     event_path(variant != "split", 3 if variant.endswith("3") else 4, 2 if variant.endswith("pf2") else 0 if variant.endswith("pf0") else 1, tile=tile,
-               simple=5 if variant == "simple" else 0)
+               simple=5 if variant == "simple" else 0, depth=4 if "-d4" in variant else 8 if "-d8" in variant else 0)
     n_seq, W, T, bs, B, NB = 31250, 64, 512, 16, 4096, 37
     pol, ws, ix, op, seqs = _config2(n_seq, W, T, bs, B)
     assert ix.entry_count() == n_seq * (T // bs)
@@ -117,7 +119,7 @@ def test_config2_full_scale_multi_launch(variant, event_path):
 
 @pytest.mark.parametrize("case", [(1, 64, 512, 16, 64, 512), (3, 256, 1024, 16, 64, 256), (5, 64, 512, 64, 64, 256), (7, 100, 2048, 32, 32, 128),
                                   (8, 64, 8192, 16, 64, 48)])
-@pytest.mark.parametrize("variant", ["simple", "fused4", "fused3", "tile8", "tile16", "tile32"])
+@pytest.mark.parametrize("variant", ["simple", "fused4", "fused3", "tile8", "tile16", "tile32", "tile16-d4"])
 def test_random_parity_other_variants(case, variant, event_path):
     """The randomized ragged parity cases of test_gpu_event_select.py (which run the default path: hash stream + balanced search kernel) on every
     other implementation of the event-driven pick."""
@@ -127,7 +129,7 @@ def test_random_parity_other_variants(case, variant, event_path):
     spec.loader.exec_module(mod)
     test_random_select_parity = mod.test_random_select_parity
     if variant.startswith("tile"):   # force the tiled kernel wherever the launch is eligible (≤ 32 blocks, one jump, ≤ 64 workers), however small
-        event_path(True, 4, tile=int(variant[4:]), min_total=1)
+        event_path(True, 4, tile=int(variant[4:6].rstrip("-")), min_total=1, depth=4 if "-d4" in variant else 0)
     else:
         event_path(True, 3 if variant == "fused3" else 4, tile=0, simple=5 if variant == "simple" else 0)
     test_random_select_parity(*case)
