@@ -277,6 +277,11 @@ __global__ void __launch_bounds__(256) hash_blocks_kernel(const __grid_constant_
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(blk, h) & a.pf_mask)));
         }
     }
+    if (a.ready) {   // concurrent split launch: this CTA's share of batch blockIdx.y is in memory
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(a.ready + blockIdx.y, 1u);
+    }
 }
 
 // ---- K3: max_by_key((score, Reverse(load), Reverse(tree_size))) with LAST max = highest slice index ---------
@@ -585,7 +590,19 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
         s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
         s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
     }
-    if (threadIdx.x == 0) { s_nb = 0; s_nc = 0; }
+    if (threadIdx.x == 0) {
+        s_nb = 0; s_nc = 0;
+        if (a.ready) {   // launched alongside the hash kernel: wait until every hash CTA of this batch has counted itself in
+            const long long t0 = clock64();
+            for (;;) {
+                uint32_t cur;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(a.ready + blockIdx.y) : "memory");
+                if ((int32_t)(cur - a.ready_target[blockIdx.y]) >= 0) break;
+                if (clock64() - t0 > 4000000000LL) { atomicExch(a.err_flag, 3u); break; }   // ≈ 2 s: the hash kernel never ran — report, do not hang
+                __nanosleep(100);
+            }
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const BatchDesc& b = a.b[blockIdx.y];
@@ -1507,7 +1524,8 @@ void launch_event_search(const EventIndexView& ix, const FleetView& fleet, const
         if (old_search || smem2 > 160 * 1024 || !a.recs) event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
         else {
             // 128 requests per CTA while that still fits one wave of resident CTAs (fewer queued drains per warp), else 256
-            const bool small = (uint64_t)((max_n + 127) / 128) * a.count <= (uint64_t)sm_count * 4;
+            static const int rpc_env = [] { const char* e = getenv("SMGX_SEARCH_RPC"); return e ? atoi(e) : 0; }();   // 128 / 256 force, else by size
+            const bool small = rpc_env == 128 || (rpc_env != 256 && (uint64_t)((max_n + 127) / 128) * a.count <= (uint64_t)sm_count * 4);
             if (small) {
                 if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 event_search2_kernel<128><<<dim3((max_n + 127) / 128, a.count), 256, smem2, stream>>>(ix, fleet, a);

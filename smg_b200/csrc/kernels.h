@@ -79,6 +79,10 @@ struct MultiArgs {
     // order, each pick bumping its worker's load before the next request is decided (the router's WorkerLoadGuard, router.rs:319-321).
     // split path: the hash kernel warms L2 with the index slots the search kernel will probe first (positions 0 and min(jump, last))
     SearchRec* recs;               // [total] (split path)
+    // concurrent split launch: the search kernel runs on a side stream AT THE SAME TIME as the hash kernel; its CTAs of batch y wait until the
+    // hash CTAs of batch y have all counted themselves into ready[y] (cumulative counters, never reset: target = value to reach)
+    uint32_t* ready;               // device [kMaxMultiBatches] (nullable: plain stream order)
+    uint32_t ready_target[kMaxMultiBatches];
     const void* pf_slots;          // EventIndexView.slots (nullable)
     uint32_t pf_mask, pf_jump;
     uint32_t* slow_queue;          // event_simple_kernel → event_slow_kernel: [0] = count, [1 .. total] = request indices, [total + 1] = CTA exit counter (all zero between launches)

@@ -82,6 +82,11 @@ struct Lane {
     DevBuf d_fb;   // load-feedback scratch: per-request tied sets + scores
     DevBuf d_slowq;   // queue between event_simple_kernel and event_slow_kernel
     DevBuf d_recs;    // SearchRec per request: hash kernel → search kernel
+    // concurrent split launch (hash on `stream`, search on `side`): device counters the hash CTAs count into + their host-side running totals
+    cudaStream_t side = nullptr;
+    cudaEvent_t pre = nullptr, side_done = nullptr;
+    DevBuf d_ready;
+    uint32_t ready_cum[kMaxMultiBatches] = {};
     DevBuf d_tokens, d_offsets, d_out, d_info, d_hash, d_text, d_toff, d_path, d_path_len, d_tenant, d_path_tenant, d_fill, d_chunk_start, d_cv, d_hashes;
     Tokenizer::Scratch tok_scratch;
     bool busy = false;
@@ -124,6 +129,11 @@ public:
                 SMGX_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
                 SMGX_CUDA(cudaEventCreate(&l.t0));
                 SMGX_CUDA(cudaEventCreate(&l.t1));
+                SMGX_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+                SMGX_CUDA(cudaEventCreateWithFlags(&l.pre, cudaEventDisableTiming));
+                SMGX_CUDA(cudaEventCreateWithFlags(&l.side_done, cudaEventDisableTiming));
+                l.d_ready.reserve(kMaxMultiBatches * 4);
+                SMGX_CUDA(cudaMemset(l.d_ready.ptr, 0, kMaxMultiBatches * 4));
             }
             d_err.reserve(64);
             SMGX_CUDA(cudaMemset(d_err.ptr, 0, 64));
@@ -145,6 +155,10 @@ public:
                 if (l.done) cudaEventDestroy(l.done);
                 if (l.t0) cudaEventDestroy(l.t0);
                 if (l.t1) cudaEventDestroy(l.t1);
+                if (l.pre) cudaEventDestroy(l.pre);
+                if (l.side_done) cudaEventDestroy(l.side_done);
+                if (l.side) cudaStreamDestroy(l.side);
+                l.d_ready.release();
                 if (l.stream) cudaStreamDestroy(l.stream);
             }
             for (auto& kv : models) {
@@ -260,6 +274,7 @@ public:
         }
     }
 
+    static uint32_t max_n_of(const BatchDesc* d, uint32_t count) { uint32_t m = 0; for (uint32_t k = 0; k < count; ++k) m = std::max(m, d[k].n); return m; }
     // Enqueue the kernels of up to kMaxMultiBatches token batches on `lane` (device pointers).
     void enqueue_batches(ModelState& m, Lane& lane, const BatchDesc* descs, uint32_t count, uint32_t max_req_tokens, uint64_t* done_flag = nullptr,
                          uint64_t done_value = 0) {
@@ -317,6 +332,23 @@ public:
             a.pf_slots = ixv.slots; a.pf_mask = ixv.mask; a.pf_jump = ixv.jump;
         }
         a.err_flag = d_err.as<uint32_t>();
+        a.ready = nullptr;
+        // concurrent split launch (SMGX_SPLIT_CONCURRENT=1, experiment): the search kernel starts together with the hash kernel on a side stream and
+        // follows it batch by batch through device-side counters.  Measured worse than plain stream order (K = 20: 73 µs vs 65 µs; the waiting search
+        // CTAs take registers from the hash stream and the stream join costs more than the overlap gains; profiles/r02_event.md) — off by default.
+        static const int concurrent = [] { const char* e = getenv("SMGX_SPLIT_CONCURRENT"); return e ? atoi(e) : 0; }();
+        if (concurrent && event_launch_is_split(a) && ixv.words == 1 && count >= 2 && bs == 16 && (uint64_t)count * ((max_n_of(descs, count) + 255) / 256) <= (uint64_t)sm_count * 3) {
+            const uint64_t threads = (uint64_t)max_n_of(descs, count) * a.max_blocks;
+            const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((threads + 255) / 256, (uint64_t)sm_count * 64));   // = launch_event_hash's grid.x
+            a.ready = lane.d_ready.as<uint32_t>();
+            for (uint32_t k = 0; k < count; ++k) { lane.ready_cum[k] += gx; a.ready_target[k] = lane.ready_cum[k]; }
+            SMGX_CUDA(cudaEventRecord(lane.pre, lane.stream));             // everything the kernels depend on (copies, state updates) is ordered before this
+            SMGX_CUDA(cudaStreamWaitEvent(lane.side, lane.pre, 0));
+            launch_event_hash(a, sm_count, lane.stream, &launches);
+            launch_event_search(ixv, fv, a, sm_count, lane.side, &launches);
+            SMGX_CUDA(cudaEventRecord(lane.side_done, lane.side));
+            SMGX_CUDA(cudaStreamWaitEvent(lane.stream, lane.side_done, 0));  // the lane's later work (D2H of the picks, the next call's hash stream) follows the search
+        } else
         launch_event_select(ixv, fv, a, sm_count, lane.stream, &launches);
         if (feedback) {
             launch_feedback_resolve(ixv, fv, a, m.d_loads.as<uint64_t>(), m.d_flags.as<uint8_t>(), (uint32_t)m.urls.size(), cfg.balance_abs_threshold,
@@ -2643,6 +2675,7 @@ smgx_status smgx_synchronize(smgx_policy* p, char** err) {
         if (flag) {
             SMGX_CUDA(cudaMemset(p->impl.d_err.ptr, 0, 4));
             if (flag == 2) throw Error(SMGX_DEVICE_ERROR, "peer-memory exchange: a rank did not publish its candidates in time");
+            if (flag == 3) throw Error(SMGX_DEVICE_ERROR, "concurrent split launch: the search kernel gave up waiting for the hash kernel");
             throw Error(SMGX_INVALID_ARGUMENT, "a request exceeded max_tokens_per_request on the device-resident path");
         }
         return SMGX_SUCCESS;
