@@ -48,10 +48,12 @@ def measured_peak():
 
 
 def ncu_traffic():
+    """DRAM bytes per DECISION of the dominant kernel pair, from the committed ncu --set full capture (profiles/roofline_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch_pair")
+            d = json.load(open(p))
+            return d["dram_bytes_per_launch_pair"] / d["decisions_per_launch_pair"]
         except Exception:  # noqa: BLE001
             return None
     return None
@@ -548,8 +550,11 @@ def main():
                     "copies_p50_us": p50_us - k50_us,
                     "what": "one 4096-request batch, submit → wait; device_resident = kernel + launch + sync, copies = H2D of 8.4 MB tokens + D2H of 16 KB picks"},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                     "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of one 20-batch launch of this kernel, cold L2) — static, not measured in this run",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (ncu_traffic() * B * args.steps / n_launch_groups) if ncu_traffic() else None,
+                     "traffic_source": "per launch (pair) = DRAM bytes per decision of profiles/roofline_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write of the "
+                                       "hash + search pair on one 20-batch call, cold L2: 2926 B/decision vs 2192 B algorithmic) x the decisions of one launch of this run; a "
+                                       "committed capture, not measured in this run",
                      "kernel": ("event_fused_kernel<W1,16> (hash → jump search → argmax in one persistent kernel)" if fused else
                                 "hash_blocks_kernel<16> + event_search_thread_kernel (whole step: both kernels' time, the path's algorithmic bytes)"),
                      "batches_per_launch": args.steps / n_launch_groups,

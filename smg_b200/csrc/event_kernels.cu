@@ -255,7 +255,7 @@ __device__ __forceinline__ uint64_t hash_block(const uint32_t* __restrict__ p, u
 }
 
 template <int BS>   // BS = 16: the common block size, fully unrolled; BS = 0: any run-time block size
-__global__ void __launch_bounds__(256) hash_blocks_kernel(const __grid_constant__ MultiArgs a) {
+__global__ void __launch_bounds__(256, 8) hash_blocks_kernel(const __grid_constant__ MultiArgs a) {   // 8 CTAs = 2048 threads per SM: the 64 B per thread in flight are the bandwidth
     const BatchDesc& b = a.b[blockIdx.y];
     const uint64_t total = (uint64_t)b.n * a.max_blocks;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {

@@ -44,7 +44,7 @@ def main():
                 [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                  "--master-port", "29533", "bench.py"]
             cell = ["--gpus", str(args.gpus), "--steps", str(steps), "--warmup", "3", "--batch", str(B), "--tokens", str(T), "--sequences", str(n_seq),
-                    "--ring", str(ring), "--no-cpu-baseline"]
+                    "--ring", str(ring), "--no-cpu-baseline", "--no-text-in", "--no-per-request", "--no-sharded"]
             d = run(base + cell)
             rec = {"T": T, "B": B, "n_gpus": args.gpus, "sequences": n_seq, "ring": ring, "steps": steps, "smgx": d}
             if (T, B) in REF_CELLS and args.gpus == 1:
