@@ -523,7 +523,7 @@ def main():
     k99_us, k50_us = float(np.percentile(lat_k, 99) * 1e6), float(np.percentile(lat_k, 50) * 1e6)
 
     peak, peak_src = measured_peak()
-    fused = os.environ.get("SMGX_EVENT_PATH", "fused") != "split"
+    fused = os.environ.get("SMGX_EVENT_PATH", "split") == "fused"   # the library's default is the pair (hash stream + balanced search)
     kernels_per_launch = 1 if fused else 2
     n_launch_groups = max(gpu_launches // kernels_per_launch, 1)
     achieved = alg_bytes * B * args.steps / (ms_med / 1e3) / 1e9
@@ -556,7 +556,7 @@ def main():
                                        "hash + search pair on one 20-batch call, cold L2: 2926 B/decision vs 2192 B algorithmic) x the decisions of one launch of this run; a "
                                        "committed capture, not measured in this run",
                      "kernel": ("event_fused_kernel<W1,16> (hash → jump search → argmax in one persistent kernel)" if fused else
-                                "hash_blocks_kernel<16> + event_search_thread_kernel (whole step: both kernels' time, the path's algorithmic bytes)"),
+                                "hash_blocks_kernel<16> + event_search2_kernel<256> (whole step: both kernels' time, the path's algorithmic bytes)"),
                      "batches_per_launch": args.steps / n_launch_groups,
                      "algorithmic_bytes_per_decision": alg_bytes, "mean_reference_probes": mean_pr,
                      "avg_launch_us": ms_med * 1e3 / n_launch_groups, "peak_source": peak_src},

@@ -431,7 +431,7 @@ class Tree:
             raise ValueError("bincode: malformed TreeSnapshot")
 
 
-def decode_snapshot(data: bytes):
+def decode_snapshot(data: bytes, allow_trailing: bool = False):
     """bincode 1.3 (default options) TreeSnapshot → [(edge, [(tenant, epoch)], child_count)], in plain Python (an independent reader
     of the wire format for the tests)."""
     import struct
@@ -449,7 +449,7 @@ def decode_snapshot(data: bytes):
             tens.append((name, ep))
         (cc,) = struct.unpack_from("<I", data, at); at += 4
         out.append((edge, tens, cc))
-    assert at == len(data)
+    assert allow_trailing or at == len(data)
     return out
 
 

@@ -337,7 +337,7 @@ public:
         }
         return b;
     }
-    static bool snapshot_from_bytes(const std::string& b, TreeSnapshot& out) {  // bincode::deserialize (:49-51); false = Err
+    static bool snapshot_from_bytes(const std::string& b, TreeSnapshot& out) {  // bincode::deserialize (:49-51; bincode 1.3: fixint, trailing bytes allowed); false = Err
         size_t at = 0;
         uint64_t n;
         out.clear();
@@ -361,7 +361,7 @@ public:
             at += 4;
             out.push_back(std::move(nd));
         }
-        return at == b.size();
+        return true;
     }
     // Tree::from_snapshot (:1228-1243) into THIS (emptied) tree
     void load_snapshot(const TreeSnapshot& snap) {

@@ -505,7 +505,8 @@ void StringTreeIndex::merge_nodes(uint32_t local, const SnapNode& remote) {
 }
 
 
-// TreeSnapshot::from_bytes (snapshot.rs:49-51): false = bincode error (short input, trailing bytes, invalid UTF-8)
+// TreeSnapshot::from_bytes (snapshot.rs:49-51) = bincode::deserialize, i.e. bincode 1.3's DefaultOptions + fixint + allow_trailing_bytes:
+// false = bincode error (short input, invalid UTF-8); bytes after the last node are accepted and ignored, as there
 bool StringTreeIndex::decode_snapshot(const uint8_t* b, size_t n, std::vector<std::unique_ptr<SnapNode>>& flat) {
     size_t at = 0;
     uint64_t count;
@@ -532,7 +533,7 @@ bool StringTreeIndex::decode_snapshot(const uint8_t* b, size_t n, std::vector<st
         at += 4;
         flat.push_back(std::move(nd));
     }
-    return at == n;
+    return true;
 }
 
 // restore_node's shape (:1245-1309): pre-order list → tree; children with an empty edge are skipped with their subtrees, a later child

@@ -148,9 +148,30 @@ def test_malformed_bytes_are_rejected(mk, from_bytes):
     t = mk()
     t.insert_text("Hello", "w")
     data = t.snapshot_bytes()
-    for bad in (data[:-1], data + b"\x00", b"\x01", (3).to_bytes(8, "little") + data[8:]):
+    for bad in (data[:-1], b"\x01", (3).to_bytes(8, "little") + data[8:], data[:8] + b"\x02\x00\x00\x00\x00\x00\x00\x00\xff\xfe" + data[8:]):
         with pytest.raises(Exception):
             from_bytes(bad)
+
+
+def test_trailing_bytes_are_accepted(mk, from_bytes):
+    """TreeSnapshot::from_bytes is bincode::deserialize (snapshot.rs:49-51; bincode 1.3 = DefaultOptions + fixint + allow_trailing_bytes):
+    a padded / extended payload deserialises to the same snapshot, for from_snapshot and for merge_snapshot."""
+    t = mk()
+    t.insert_text("Hello world", "w1")
+    t.insert_text("Hello there", "w2")
+    data = t.snapshot_bytes()
+    for pad in (b"\x00", b"\xff" * 7, b"trailing garbage that is not a node"):
+        assert decode_snapshot(data + pad, allow_trailing=True) == decode_snapshot(data)
+        r = from_bytes(data + pad)
+        assert r.snapshot_bytes() == data
+        m = mk()
+        m.insert_text("Help", "w3")
+        m2 = mk()
+        m2.insert_text("Help", "w3")
+        m.merge_snapshot_bytes(data + pad)
+        m2.merge_snapshot_bytes(data)
+        shape = lambda tr: [(e, sorted(n for n, _ in tens)) for e, tens in tr.entries()]   # epochs come from a process-wide clock
+        assert shape(m) == shape(m2) and m.get_tenant_char_count() == m2.get_tenant_char_count()
 
 
 ALL = {k: v for k, v in globals().items() if k.startswith("test_")}

@@ -8,7 +8,7 @@ from tests import scenarios_snapshot as SC
 
 NO_MATCH = ["test_snapshot_empty_tree", "test_snapshot_size_vs_flat_ops", "test_snapshot_wire_layout", "test_from_snapshot_accounting_and_structure",
             "test_from_snapshot_skips_empty_child_edges_and_truncation", "test_merge_remote_prefix_of_local_drops_remote_children",
-            "test_malformed_bytes_are_rejected"]
+            "test_malformed_bytes_are_rejected", "test_trailing_bytes_are_accepted"]
 
 
 def _mk():
