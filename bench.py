@@ -441,10 +441,14 @@ def main():
         checked, bad = 0, 0
         got = np.zeros(B, np.int32)
         off64 = offsets.astype(np.uint64)
+        def check(dptr, j, what):
+            h.call("smgx_memcpy_d2h", got.ctypes.data_as(C.c_void_p), dptr, B * 4)
+            want = np.asarray(op.select_batch_tokens(host_batches[j], off64)[0])
+            for r_ in np.nonzero(got != want)[0][:8]:
+                print(f"PARITY: {what} ring batch {j} request {r_}: got {got[r_]} want {want[r_]}", file=sys.stderr)
+            return int((got != want).sum())
         for j in sorted(set(order))[: (R if rank == 0 else 4)]:
-            h.call("smgx_memcpy_d2h", got.ctypes.data_as(C.c_void_p), d_out[j], B * 4)
-            want = op.select_batch_tokens(host_batches[j], off64)[0]
-            bad += int((got != want).sum()); checked += B
+            bad += check(d_out[j], j, f"{args.steps}-step timed region"); checked += B
         # branches + overlap scores of one batch through the info-carrying call
         info = (_lib.DecisionInfo * B)()
         d_info = L.smgx_device_alloc(h.p, C.sizeof(info), C.byref(err))
@@ -523,8 +527,9 @@ def main():
     k99_us, k50_us = float(np.percentile(lat_k, 99) * 1e6), float(np.percentile(lat_k, 50) * 1e6)
 
     peak, peak_src = measured_peak()
-    fused = os.environ.get("SMGX_EVENT_PATH", "split") == "fused"   # the library's default is the pair (hash stream + balanced search)
-    kernels_per_launch = 1 if fused else 2
+    path = os.environ.get("SMGX_EVENT_PATH", "split")   # the library's default: the pair (hash stream + balanced search)
+    fused = path == "fused"
+    kernels_per_launch = 2 if path == "split" else 1
     n_launch_groups = max(gpu_launches // kernels_per_launch, 1)
     achieved = alg_bytes * B * args.steps / (ms_med / 1e3) / 1e9
     line = {
@@ -556,6 +561,8 @@ def main():
                                        "hash + search pair on one 20-batch call, cold L2: 2926 B/decision vs 2192 B algorithmic) x the decisions of one launch of this run; a "
                                        "committed capture, not measured in this run",
                      "kernel": ("event_fused_kernel<W1,16> (hash → jump search → argmax in one persistent kernel)" if fused else
+                                "event_hs_kernel<16,2> (one launch: hash stream; the last CTA of every 256-request group runs search + argmax)" if path == "hs" else
+                                "event_stream_kernel (one launch of persistent CTAs: bulk-copy token ring → XXH3 → jump search → argmax)" if path != "split" else
                                 "hash_blocks_kernel<16> + event_search2_kernel<256> (whole step: both kernels' time, the path's algorithmic bytes)"),
                      "batches_per_launch": args.steps / n_launch_groups,
                      "algorithmic_bytes_per_decision": alg_bytes, "mean_reference_probes": mean_pr,

@@ -435,10 +435,14 @@ smgx_status smgx_timer_start_all_gated(smgx_policy* p, uint32_t hold_us, char** 
 smgx_status smgx_timer_start_gated(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err);
 smgx_status smgx_stream_hold(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err);       /* only the hold kernel */   /* one lane; stop with smgx_timer_stop_ms(lane) */
 smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
-/* Process-wide switch between the two implementations of the event-driven pick (A/B measurements, tests): fused != 0 (default) = the
- * one-kernel persistent path, 0 = the round-1 hash kernel + search kernel pair.  min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant
- * of the fused kernel.  Also settable through the environment: SMGX_EVENT_PATH=split|fused, SMGX_FUSED_MINB=3|4. */
-void smgx_set_event_path(int fused, int min_blocks_per_sm);
+/* Process-wide switch between the implementations of the event-driven pick (A/B measurements, tests): path 3 (default) = ONE launch of
+ * persistent CTAs, each streaming its run of requests through a shared-memory ring (bulk async copies), hashing it and searching what it
+ * hashed (event_stream_kernel; block size 16, ≤ 32 blocks per request, ≤ 64 interned workers — anything else runs the pair); 0 = hash kernel +
+ * search kernel pair; 1 = the warp-per-request family (simple / tiled / persistent fused kernels); 2 = hash stream whose last CTA per
+ * 256-request group runs the search (event_hs_kernel).  Mapped submissions and load-feedback batches always run the persistent fused kernel.
+ * min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant of the fused kernel.  Environment: SMGX_EVENT_PATH=stream|hs|split|fused,
+ * SMGX_FUSED_MINB=3|4. */
+void smgx_set_event_path(int path, int min_blocks_per_sm);
 /* L2 prefetch flavour of the fused kernel: 0 none, 1 one bulk prefetch per request (default), 2 one prefetch per lane (SMGX_FUSED_PF). */
 void smgx_set_fused_prefetch(int flavour);
 /* Requests per warp of the tiled event kernel (8, 16 or 32; 0 = never use it) and the launch size from which it is used (requests; < 0 =

@@ -553,6 +553,15 @@ __device__ __forceinline__ void fused_advance(const MultiArgs& a, FusedPos& p, u
 struct SlowResult { uint64_t winset; uint32_t score; };
 // generic search on the shared-memory hash row; returns the eligible set the argmax runs over (survivors, else the latest eligible drained set)
 template <bool W1>
+__device__ __forceinline__ SlowResult slow_search_inline(const EventIndexView& v, const uint64_t* ch, int nb, int lane, uint64_t elig) {
+    SelectSink<W1> sink{elig, 0, 0};
+    const uint64_t surv = jump_search<W1>(v, ch, nb, lane, sink, false) & elig;
+    SlowResult r;
+    if (set_any<W1>(surv)) { r.winset = surv; r.score = (uint32_t)nb; }
+    else { r.winset = sink.last; r.score = sink.last_score; }
+    return r;
+}
+template <bool W1>
 __device__ __noinline__ SlowResult fused_slow_search(const EventIndexView* vp, const uint64_t* ch, int nb, int lane, uint64_t elig) {
     const EventIndexView v = *vp;
     SelectSink<W1> sink{elig, 0, 0};
@@ -577,13 +586,43 @@ __device__ __noinline__ SlowResult fused_slow_search(const EventIndexView* vp, c
 //      warp-cooperative jump_search on a shared-memory row, again spread over the warps.
 struct Search2Item { uint32_t r; uint32_t nb; };
 
-template <int RPC>   // requests per CTA handled by phase A (256 threads either way: the queues of phases B / C are spread over all 8 warps)
-__global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
-    extern __shared__ uint64_t smem_ch[];                 // [8 warps][max_blocks] for phase C
-    __shared__ int32_t s_slice[64];
-    __shared__ uint64_t s_load[64], s_ts[64];
-    __shared__ Search2Item s_qb[256], s_qc[256];
-    __shared__ uint32_t s_nb, s_nc;
+struct Search2Smem {
+    int32_t slice[64];
+    uint64_t load[64], ts[64];
+    Search2Item qb[256], qc[256];
+    uint32_t nb, nc, last;
+};
+// The three phases for r_count ≤ 256 requests of batch `by` starting at r_begin, run by a whole CTA of 256 threads.  WAIT: the stand-alone search
+// kernel launched beside the hash kernel (a.ready).  CG: records and hash rows were written by OTHER CTAs of the running kernel
+// (event_hs_kernel) — read them from L2 (ld.global.cg), never through this SM's L1.
+template <int NT> __device__ __forceinline__ void search2_sync() {   // the NT threads running search2_body (NT < 256: named barrier 1)
+    if (NT == 256) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+template <bool WAIT, bool CG, int NT = 256>
+__device__ __forceinline__ void search2_body(const EventIndexView& v, const FleetView& f, const MultiArgs& a, const uint32_t by, const uint32_t r_begin,
+                                             const uint32_t r_count, Search2Smem& sm, uint64_t* smem_ch, const uint32_t tile_req = 256,
+                                             const uint32_t tile_stride = 0) {
+    int32_t (&s_slice)[64] = sm.slice;
+    uint64_t (&s_load)[64] = sm.load;
+    uint64_t (&s_ts)[64] = sm.ts;
+    Search2Item (&s_qb)[256] = sm.qb;
+    Search2Item (&s_qc)[256] = sm.qc;
+    uint32_t& s_nb = sm.nb;
+    uint32_t& s_nc = sm.nc;
+    auto ld_rec = [&](uint64_t i) -> SearchRec {
+        if (!CG) return a.recs[i];
+        const uint4* q = reinterpret_cast<const uint4*>(a.recs + i);
+        const uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+        SearchRec rr;
+        rr.h0 = (uint64_t)lo.x | ((uint64_t)lo.y << 32); rr.h1 = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+        rr.ntok = hi.x;
+        return rr;
+    };
+    auto ld_hash = [&](const uint64_t* p) -> uint64_t { return CG ? (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)) : *p; };
+    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
+    const bool trace = NT != 256 && (a.dbg & 64) && threadIdx.x == 0 && blockIdx.x % 59 == 0;
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
     if (threadIdx.x < 64) {
         bool ok = threadIdx.x < v.n_workers;
         s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
@@ -592,20 +631,20 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
     }
     if (threadIdx.x == 0) {
         s_nb = 0; s_nc = 0;
-        if (a.ready) {   // launched alongside the hash kernel: wait until every hash CTA of this batch has counted itself in
+        if (WAIT && a.ready) {   // launched alongside the hash kernel: wait until every hash CTA of this batch has counted itself in
             const long long t0 = clock64();
             for (;;) {
                 uint32_t cur;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(a.ready + blockIdx.y) : "memory");
-                if ((int32_t)(cur - a.ready_target[blockIdx.y]) >= 0) break;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(a.ready + by) : "memory");
+                if ((int32_t)(cur - a.ready_target[by]) >= 0) break;
                 if (clock64() - t0 > 4000000000LL) { atomicExch(a.err_flag, 3u); break; }   // ≈ 2 s: the hash kernel never ran — report, do not hang
                 __nanosleep(100);
             }
         }
     }
-    __syncthreads();
+    search2_sync<NT>();
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-    const BatchDesc& b = a.b[blockIdx.y];
+    const BatchDesc& b = a.b[by];
     const bool cand_mode = b.cand != nullptr;
     const FleetDerived fd = *f.derived;
     const uint64_t elig = f.elig[0];
@@ -624,10 +663,12 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
         } else write_pick(b, r, out, branch, matched, ntok);
     };
 
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr1));
     // ---- phase A ----
-    const uint32_t r = blockIdx.x * RPC + threadIdx.x;
-    if (threadIdx.x < RPC && r < b.n) {
-        const SearchRec rec = a.recs[(uint64_t)b.hash_base + r];   // one 32 B record written by the hash kernel
+    // thread t ↔ request t of the range; a range may be a run of equally spaced tiles (event_stream_kernel): tile t / tile_req, slot t % tile_req
+    const uint32_t r = r_begin + (threadIdx.x / tile_req) * tile_stride + threadIdx.x % tile_req;
+    if (threadIdx.x < r_count) {
+        const SearchRec rec = ld_rec((uint64_t)b.hash_base + r);   // one 32 B record written by the hash kernel
         const uint32_t ntok = rec.ntok;
         if (!cand_mode && fd.n_healthy == 0) write_pick(b, r, -1, SMGX_BR_NO_HEALTHY, 0, ntok);
         else if (!cand_mode && fd.imbalanced) write_pick(b, r, fd.min_load_idx, SMGX_BR_IMBALANCED_MIN_LOAD, 0, ntok);
@@ -653,7 +694,9 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
             }
         }
     }
-    __syncthreads();
+    search2_sync<NT>();
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr2));
+    if (NT != 256 && (a.dbg & 16)) return;                        // A/B timing: phase A only
 
     // ---- phase B: register drains, one warp per queued request, the queue striped over the warps; two requests per round so that the
     //      hash loads and the probes of the second overlap those of the first ----
@@ -693,17 +736,18 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
             uint64_t win = active & elig;
             uint32_t score = it.nb;
             if (!win) { win = last_set; score = last_score; }
-            finish(it.r, win, score, a.recs[(uint64_t)b.hash_base + it.r].ntok);
+            finish(it.r, win, score, ld_rec((uint64_t)b.hash_base + it.r).ntok);
         }
     };
-    for (uint32_t q = wic; q < n_b; q += 16) {
+    constexpr uint32_t NW = NT / 32;
+    for (uint32_t q = wic; q < n_b; q += 2 * NW) {
         const Search2Item it0 = s_qb[q];
-        const bool two = q + 8 < n_b;
-        const Search2Item it1 = two ? s_qb[q + 8] : Search2Item{0, 0};
+        const bool two = q + NW < n_b;
+        const Search2Item it1 = two ? s_qb[q + NW] : Search2Item{0, 0};
         const uint64_t* ch0 = a.hashes + ((uint64_t)b.hash_base + it0.r) * a.max_blocks;
         const uint64_t* ch1 = a.hashes + ((uint64_t)b.hash_base + it1.r) * a.max_blocks;
-        const uint64_t h0 = (uint32_t)lane < it0.nb ? ch0[lane] : 0;
-        const uint64_t h1 = (uint32_t)lane < it1.nb ? ch1[lane] : 0;
+        const uint64_t h0 = (uint32_t)lane < it0.nb ? ld_hash(ch0 + lane) : 0;
+        const uint64_t h1 = (uint32_t)lane < it1.nb ? ld_hash(ch1 + lane) : 0;
         // every position of both requests probed at once (position 0 again: L2-hot)
         const uint32_t i0 = slot_hash((uint32_t)lane, h0) & v.mask, i1 = slot_hash((uint32_t)lane, h1) & v.mask;
         Slot sl0{0, 0, SLOT_EMPTY, 0, 0}, sl1{0, 0, SLOT_EMPTY, 0, 0};
@@ -715,19 +759,357 @@ __global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constan
         resolve(it0, f0, sl0);
         if (two) resolve(it1, f1, sl1);
     }
-    __syncthreads();
+    search2_sync<NT>();
+    if (trace) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr3));
+        printf("cta %u n %u: tables %llu ns, phase A %llu ns, phase B %llu ns (nb %u nc %u) t0 %llu\n", blockIdx.x, r_count, tr1 - tr0, tr2 - tr1, tr3 - tr2, s_nb, s_nc, tr0);
+    }
+    if (NT != 256 && (a.dbg & 32)) return;                        // A/B timing: phases A + B
 
     // ---- phase C: generic search ----
     const uint32_t n_c = s_nc;
     uint64_t* row = smem_ch + (size_t)wic * a.max_blocks;
-    for (uint32_t q = wic; q < n_c; q += 8) {
+    for (uint32_t q = wic; q < n_c; q += NW) {
         const Search2Item it = s_qc[q];
         const uint64_t* ch = a.hashes + ((uint64_t)b.hash_base + it.r) * a.max_blocks;
-        for (uint32_t i = lane; i < it.nb; i += 32) row[i] = ch[i];
+        for (uint32_t i = lane; i < it.nb; i += 32) row[i] = ld_hash(ch + i);
         __syncwarp();
-        const SlowResult sr = fused_slow_search<true>(&v, row, (int)it.nb, lane, elig);
-        if (lane == 0) finish(it.r, sr.winset, sr.score, a.recs[(uint64_t)b.hash_base + it.r].ntok);
+        const SlowResult sr = NT == 256 ? fused_slow_search<true>(&v, row, (int)it.nb, lane, elig) : slow_search_inline<true>(v, row, (int)it.nb, lane, elig);
+        if (lane == 0) finish(it.r, sr.winset, sr.score, ld_rec((uint64_t)b.hash_base + it.r).ntok);
         __syncwarp();
+    }
+}
+
+template <int RPC>   // requests per CTA handled by phase A (256 threads either way: the queues of phases B / C are spread over all 8 warps)
+__global__ void __launch_bounds__(256) event_search2_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    extern __shared__ uint64_t smem_ch[];                 // [8 warps][max_blocks] for phase C
+    __shared__ Search2Smem sm;
+    const uint32_t r_begin = blockIdx.x * RPC, n = a.b[blockIdx.y].n;
+    search2_body<true, false>(v, f, a, blockIdx.y, r_begin, r_begin < n ? min((uint32_t)RPC, n - r_begin) : 0u, sm, smem_ch);
+}
+
+// ---- ONE launch: the hash stream, and the search of every 256-request group run by the LAST hash CTA of that group ------------------
+// The pair above costs a lone call ≈ 26 µs beyond its streaming time: the search kernel cannot start before the last hash CTA has
+// retired, and is itself a chain of dependent round trips (profiles/r02_event.md §3).  Here the dependency is resolved per GROUP of 256
+// requests instead of per launch.  The grid is the hash kernel's (one thread per UNR slots of the [n][max_blocks] block grid — UNR = 2:
+// 128 B in flight per thread, 1024 resident threads per SM hold the same bytes in flight as the stand-alone kernel's 2048 × 64 B, which
+// leaves every thread 64 registers, what the search phases need).  A CTA that has stored its hashes and records fences, then counts
+// itself into the counter of every group its slots belong to; whoever brings a counter to the group's CTA count is the last writer of
+// that group: it resets the counter for the next launch and runs search2_body on the group — one thread per request, all inputs in L2,
+// read with ld.global.cg.  Nobody spins, nobody waits: the searches of the early groups run under the hash stream of the later ones,
+// and only the last groups' searches (one chain of round trips) remain after the stream ends.
+template <int BS, int UNR>
+__global__ void __launch_bounds__(256, 4) event_hs_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a) {
+    extern __shared__ uint64_t smem_ch[];
+    __shared__ Search2Smem sm;
+    const BatchDesc& b = a.b[blockIdx.y];
+    const uint32_t mb = a.max_blocks;
+    const uint64_t total = (uint64_t)b.n * mb;
+    const uint64_t t0 = (uint64_t)blockIdx.x * (256u * UNR);
+    if (t0 >= total) return;                                  // CTAs beyond this batch's block grid (the grid is sized for the largest batch)
+    const uint32_t bs = BS ? (uint32_t)BS : a.block_size;
+    {
+        uint32_t rr[UNR], blk[UNR], off[UNR], ntok[UNR];
+        bool live[UNR];
+        uint32_t w[UNR][16];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const uint64_t t = t0 + (uint64_t)u * 256 + threadIdx.x;
+            live[u] = t < total;
+            rr[u] = live[u] ? (uint32_t)(t / mb) : 0; blk[u] = live[u] ? (uint32_t)(t % mb) : 0;
+            off[u] = 0; ntok[u] = 0;
+            if (live[u]) { off[u] = __ldg(b.offsets + rr[u]); ntok[u] = __ldg(b.offsets + rr[u] + 1) - off[u]; }
+        }
+        if (BS == 16) {   // all token loads of the thread's UNR blocks in flight before the first hash
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const uint32_t nb = ntok[u] / 16;
+                const uint32_t* p = b.tokens + off[u] + (size_t)blk[u] * 16;
+                if (live[u] && blk[u] < nb) {
+                    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                        const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { uint4 x = __ldg(q + i); w[u][4 * i] = x.x; w[u][4 * i + 1] = x.y; w[u][4 * i + 2] = x.z; w[u][4 * i + 3] = x.w; }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) w[u][i] = __ldg(p + i);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (!live[u]) continue;
+            const uint32_t nb = ntok[u] / bs;
+            SearchRec* rec = a.recs + (uint64_t)b.hash_base + rr[u];
+            if (blk[u] == 0) rec->ntok = ntok[u];
+            if (blk[u] < nb) {
+                const uint64_t h = BS == 16 ? xxh3_16words(w[u], kSeed) : xxh3_words(b.tokens + off[u] + (size_t)blk[u] * bs, bs, kSeed);
+                a.hashes[((uint64_t)b.hash_base + rr[u]) * mb + blk[u]] = h;
+                if (blk[u] == 0) rec->h0 = h;
+                if (blk[u] == min(a.pf_jump, nb - 1)) rec->h1 = h;
+                if (a.pf_slots && (blk[u] == 0 || blk[u] == min(a.pf_jump, nb - 1)))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(blk[u], h) & a.pf_mask)));
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    // groups of 256 requests = 256·mb consecutive slots; this CTA's slots [t0, t1] touch groups g_first..g_last (one, unless mb is odd or tiny)
+    const uint64_t gsz = 256ull * mb;
+    const uint64_t t1 = (t0 + 256ull * UNR < total ? t0 + 256ull * UNR : total) - 1;
+    const uint32_t g_first = (uint32_t)(t0 / gsz), g_last = (uint32_t)(t1 / gsz);
+    for (uint32_t g = g_first; g <= g_last; ++g) {
+        if (threadIdx.x == 0) {
+            const uint64_t lo = (uint64_t)g * gsz, hi = lo + gsz < total ? lo + gsz : total;    // the group's slots [lo, hi)
+            const uint32_t n_cta = (uint32_t)((hi - 1) / (256u * UNR) - lo / (256u * UNR)) + 1;
+            uint32_t* cnt = a.group_count + (uint64_t)blockIdx.y * a.group_stride + g;
+            const uint32_t old = atomicAdd(cnt, 1u);
+            sm.last = old + 1 == n_cta;
+            if (sm.last) *cnt = 0;                                                              // nobody else touches it until the next launch
+        }
+        __syncthreads();
+        if (sm.last) {
+            __threadfence();
+            search2_body<false, true>(v, f, a, blockIdx.y, g * 256u, min(256u, b.n - g * 256u), sm, smem_ch);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- ONE launch, persistent CTAs: tokens streamed through a shared-memory ring by the copy engine, each CTA searches what it hashed ----
+// What the measurements above ask for (profiles/r02_event.md): the hash stream's bytes in flight must not depend on resident threads
+// or on registers, and the search's chain of dependent round trips must be paid once per CTA, not once per request, tile or launch.
+//   * The flattened list of tiles (a tile = the R = ⌊224 / max_blocks⌋ consecutive requests of one batch whose block slots fill one
+//     14 KB stage) is dealt round-robin to the CTAs (tile g → CTA g mod grid); grid = resident CTAs (4 per SM).
+//   * Warp 7 is the PRODUCER: per tile, lane j reads request j's offsets (one tile ahead of the ring), waits on the stage's `empty`
+//     mbarrier, and issues ONE bulk copy (cp.async.bulk → UBLKCP, completion counted on the stage's `full` mbarrier) of the request's
+//     whole blocks, global → stage slot j.  Three stages per CTA, all of them in flight whenever the consumers are ahead: up to 168 KB
+//     per SM with no register and no thread waiting on them.  A request whose tokens are not 16 B aligned is copied by the producer
+//     warp with plain loads instead.
+//   * Warps 0-6 are CONSUMERS.  They read a stage TRANSPOSED: lane l of warp w takes the 16 B chunk l & 3 of blocks 32w + (l >> 2) +
+//     8k, k = 0..3 — conflict-free LDS.128, after which the warp releases the stage — and does that chunk's XXH3 lane mix (each of
+//     the four 16 B mixes of a 64 B input has its own secret words and is independent of the others); a 4-lane shuffle sum gives the
+//     accumulator, lane l finishes block (l >> 2) + 8·(l & 3).  Hash rows, records and the L2 prefetch of the first two slots are as
+//     in hash_blocks_kernel.  No CTA-wide barrier per tile: the warps drift.
+//   * After ≤ 224 requests (or at the end of its tiles, or of a batch) the consumers meet on a named barrier and run search2_body on
+//     them (a run of equally spaced tiles): the rows they read were written by the CTA's own threads (bar.sync + ld.global.cg).  Meanwhile the producer keeps the
+//     ring full.
+constexpr int kStStages = 3;
+constexpr int kStConsumers = 224;                                   // 7 hashing warps; warp 7 feeds the ring
+constexpr uint32_t kStStageBytes = kStConsumers * 64;               // 14 KB
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* err_flag) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;   // try_wait suspends the thread up to the hint (ns) while the phase is pending: few issue slots are spent spinning
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+        if (ok) return;
+        if (++spins > (1u << 22)) { atomicExch(err_flag, 3u); return; }   // seconds: the other side never arrived — report, do not hang
+    }
+}
+// the flattened tile list: tile = R consecutive requests of one batch
+struct StPos { uint32_t y, r0; };
+__device__ __forceinline__ StPos st_locate(const MultiArgs& a, uint32_t g, uint32_t R) {
+    StPos t;
+    if (a.uniform_n) { const uint32_t tpb = (a.uniform_n + R - 1) / R; t.y = g / tpb; t.r0 = (g - t.y * tpb) * R; }
+    else {
+        uint32_t y = 0, left = g;
+        for (;; ++y) { const uint32_t tpb = (a.b[y].n + R - 1) / R; if (left < tpb || y + 1 >= a.count) break; left -= tpb; }
+        t.y = y; t.r0 = left * R;
+    }
+    return t;
+}
+// `step` tiles further in the flattened list (the caller knows that tile exists)
+__device__ __forceinline__ void st_next(const MultiArgs& a, StPos& t, uint32_t R, uint32_t step) {
+    t.r0 += step * R;
+    for (;;) {
+        const uint32_t span = (a.b[t.y].n + R - 1) / R * R;       // the batch's tiles × R
+        if (t.r0 < span) break;
+        t.r0 -= span; ++t.y;
+    }
+}
+
+__device__ __forceinline__ void stream_search(const EventIndexView* v, const FleetView* f, const MultiArgs* a, uint32_t y, uint32_t r0, uint32_t cnt,
+                                              Search2Smem* sm, uint64_t* smem_ch, uint32_t R, uint32_t stride) {
+    if (a->dbg & 4) return;                                         // A/B: streaming only (no picks are written)
+    if (a->dbg & 2) __threadfence();
+    search2_sync<kStConsumers>();                                   // the consumers' rows and records are in L2
+    search2_body<false, true, kStConsumers>(*v, *f, *a, y, r0, cnt, *sm, smem_ch, R, stride);
+    search2_sync<kStConsumers>();
+}
+
+__global__ void __launch_bounds__(256, 4) event_stream_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a,
+                                                              const uint32_t n_tiles) {
+    extern __shared__ __align__(128) uint8_t st_dyn[];            // [3 stages × 14 KB][phase C rows: 7 × max_blocks u64][full[3], empty[3] mbarriers]
+    __shared__ Search2Smem sm;
+    const uint32_t mb = a.max_blocks;
+    const uint32_t R = (uint32_t)kStConsumers / mb;               // requests per tile (launcher: 1 ≤ max_blocks ≤ 32)
+    uint64_t* smem_ch = reinterpret_cast<uint64_t*>(st_dyn + kStStages * kStStageBytes);
+    uint64_t* bars = smem_ch + 7 * mb;
+    const uint32_t stage0 = smem_addr(st_dyn), full0 = smem_addr(bars), empty0 = full0 + 8 * kStStages;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(kStConsumers / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // this CTA's tiles: blockIdx.x, + grid, + 2·grid … — at any moment the resident CTAs sweep ONE contiguous window of the token buffers
+    // (as the stand-alone hash kernel's grid does), which is what keeps the DRAM pages open; a private contiguous run per CTA measured
+    // 3.4 TB/s with 25 MB of copies outstanding
+    const bool contiguous = (a.dbg & 8) != 0;                       // A/B: one contiguous run of tiles per CTA
+    const uint32_t G = contiguous ? 1u : gridDim.x;
+    const uint32_t q_ = n_tiles / gridDim.x, rem_ = n_tiles % gridDim.x;
+    const uint32_t g_n = contiguous ? q_ + (blockIdx.x < rem_ ? 1u : 0u) : (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    StPos pos = st_locate(a, contiguous ? blockIdx.x * q_ + min(blockIdx.x, rem_) : blockIdx.x, R);
+
+    if (wic == kStConsumers / 32) {
+        // ---- producer warp: lane j (+32, +64 …) owns request slot j of every tile; the offsets are fetched one tile ahead of the copies ----
+        const int n_u = (int)((R + 31) / 32);
+        uint32_t o_lo[7], o_hi[7];                                  // offsets[r], offsets[r + 1] of this lane's requests of the NEXT tile to issue
+        auto fetch = [&](const StPos& t) {
+            const BatchDesc& b = a.b[t.y];
+            const uint32_t cnt = min(R, b.n - t.r0);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                if (u >= n_u) break;
+                const uint32_t j = (uint32_t)lane + 32u * u;
+                o_lo[u] = 0; o_hi[u] = 0;
+                if (j < cnt) { o_lo[u] = __ldg(b.offsets + t.r0 + j); o_hi[u] = __ldg(b.offsets + t.r0 + j + 1); }
+            }
+        };
+        if (g_n) fetch(pos);
+        for (uint32_t k = 0; k < g_n; ++k) {
+            const BatchDesc& b = a.b[pos.y];
+            const uint32_t cnt = min(R, b.n - pos.r0);
+            const uint32_t s = k % kStStages, full = full0 + 8 * s;
+            bool any_slow = false;
+            uint32_t tx = 0;                                        // bytes the copy engine will deliver
+            uint32_t bytes[7];
+            const uint32_t* src[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                if (u >= n_u) break;
+                const uint32_t j = (uint32_t)lane + 32u * u;
+                const uint32_t nb = (o_hi[u] - o_lo[u]) / 16;
+                bytes[u] = (j < cnt && nb <= mb) ? nb * 64 : 0;    // longer than max_blocks: search2_body flags the request, nothing is hashed
+                src[u] = b.tokens + o_lo[u];
+                const bool slow = bytes[u] && (reinterpret_cast<uintptr_t>(src[u]) & 15) != 0;
+                any_slow = any_slow || slow;
+                if (!slow) tx += bytes[u]; else bytes[u] |= 0x80000000u;
+            }
+            const StPos cur = pos;
+            if (k + 1 < g_n) { st_next(a, pos, R, G); fetch(pos); }                            // in flight while this tile waits for its stage
+            any_slow = __any_sync(FULL, any_slow);
+            tx = __reduce_add_sync(FULL, tx);
+            mbar_wait(empty0 + 8 * s, ((k / kStStages) & 1) ^ 1, a.err_flag);   // the consumers have read the stage's previous tile
+            if (any_slow) {                                         // requests whose tokens are not 16 B aligned: plain loads by the whole warp
+#pragma unroll 1
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const uint32_t off = __ldg(b.offsets + cur.r0 + j), ntok = __ldg(b.offsets + cur.r0 + j + 1) - off;
+                    const uint32_t nb = ntok / 16;
+                    const uint32_t* sp = b.tokens + off;
+                    if (nb == 0 || nb > mb || (reinterpret_cast<uintptr_t>(sp) & 15) == 0) continue;
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(st_dyn + s * kStStageBytes + j * mb * 64);
+                    for (uint32_t i = lane; i < nb * 16; i += 32) dst[i] = __ldg(sp + i);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage's next fill is an async-proxy write
+                __syncwarp();
+            }
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(tx) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                if (u >= n_u) break;
+                const uint32_t j = (uint32_t)lane + 32u * u;
+                if (bytes[u] && !(bytes[u] & 0x80000000u))
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(stage0 + s * kStStageBytes + j * mb * 64), "l"(src[u]), "r"(bytes[u]), "r"(full) : "memory");
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps ----
+    // this lane's chunk of a 64 B block: XXH3 17..128-byte path, len 64 — chunk 0 ↔ secret 0, 1 ↔ 32, 2 ↔ 48, 3 ↔ 16
+    const int c = lane & 3;
+    const uint64_t sec_lo = c == 0 ? sec64c<0>() : c == 1 ? sec64c<32>() : c == 2 ? sec64c<48>() : sec64c<16>();
+    const uint64_t sec_hi = c == 0 ? sec64c<8>() : c == 1 ? sec64c<40>() : c == 2 ? sec64c<56>() : sec64c<24>();
+    const uint64_t k_lo = sec_lo + kSeed, k_hi = sec_hi - kSeed;
+    const uint32_t sb = 32u * (uint32_t)wic + (uint32_t)(lane >> 2) + 8u * (uint32_t)c;   // the slot this lane finishes: request sb / mb, block sb % mb
+    const uint32_t my_j = sb / mb, my_blk = sb - my_j * mb;
+    const uint32_t lds_off = (32u * wic + (lane >> 2)) * 64u + c * 16u;
+
+    uint32_t seg_y = 0, seg_r0 = 0, seg_cnt = 0;                                           // hashed, not yet searched
+    // the offsets of this lane's request are fetched one tile ahead
+    uint32_t off = 0, ntok = 0;
+    if (g_n && my_j < min(R, a.b[pos.y].n - pos.r0)) { off = __ldg(a.b[pos.y].offsets + pos.r0 + my_j); ntok = __ldg(a.b[pos.y].offsets + pos.r0 + my_j + 1) - off; }
+    uint32_t k = 0;
+    while (k < g_n) {
+    // the hot loop: tiles of one segment; the search call sits outside it, so that nothing of the loop's state lives on the stack
+    bool flush = false;
+    do {
+        const BatchDesc& b = a.b[pos.y];
+        const uint32_t cnt = min(R, b.n - pos.r0), r0 = pos.r0, y = pos.y;
+        const uint32_t s = k % kStStages;
+        const uint32_t cur_ntok = ntok;
+        StPos nx = pos;
+        const bool more = k + 1 < g_n;
+        uint32_t nx_cnt = 0;
+        if (more) {
+            st_next(a, nx, R, G);
+            nx_cnt = min(R, a.b[nx.y].n - nx.r0);
+            if (my_j < nx_cnt) { off = __ldg(a.b[nx.y].offsets + nx.r0 + my_j); ntok = __ldg(a.b[nx.y].offsets + nx.r0 + my_j + 1) - off; }
+        }
+        mbar_wait(full0 + 8 * s, (k / kStStages) & 1, a.err_flag);
+        uint64_t acc = 0;
+        {
+            const uint8_t* base = st_dyn + s * kStStageBytes + lds_off;
+            uint4 x[4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) x[rr] = *reinterpret_cast<const uint4*>(base + rr * 8 * 64);
+            // release the stage only once the four loads have RETURNED (the address depends on their data: a scoreboard wait, three instructions)
+            uint32_t dep;
+            asm volatile("and.b32 %0, %1, 0;" : "=r"(dep) : "r"(x[0].x | x[1].x | x[2].x | x[3].x));
+            __syncwarp();
+            if (lane == 0 && !(a.dbg & 1)) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s + dep) : "memory");   // this warp has read the stage
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                uint64_t m = mul128_fold64(mk64(x[rr].x, x[rr].y) ^ k_lo, mk64(x[rr].z, x[rr].w) ^ k_hi);
+                m += shfl64_xor(m, 1);
+                m += shfl64_xor(m, 2);
+                if (c == rr) acc = m;
+            }
+        }
+        if (my_j < cnt) {
+            const uint32_t nb = cur_ntok / 16;
+            const uint32_t r = r0 + my_j;
+            SearchRec* rec = a.recs + (uint64_t)b.hash_base + r;
+            if (my_blk == 0) rec->ntok = cur_ntok;
+            if (nb <= mb && my_blk < nb) {
+                const uint64_t h = avalanche(acc + 64ULL * P64_1);
+                a.hashes[((uint64_t)b.hash_base + r) * mb + my_blk] = h;
+                const uint32_t jb = min(a.pf_jump, nb - 1);
+                if (my_blk == 0) rec->h0 = h;
+                if (my_blk == jb) rec->h1 = h;
+                if (a.pf_slots && (my_blk == 0 || my_blk == jb))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(my_blk, h) & a.pf_mask)));
+            }
+        }
+        if (a.dbg & 1) { __syncwarp(); if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory"); }
+        if (seg_cnt == 0) { seg_y = y; seg_r0 = r0; }
+        seg_cnt += cnt;
+        flush = !more || nx.y != seg_y || seg_cnt + nx_cnt > (uint32_t)kStConsumers;
+        pos = nx;
+        ++k;
+    } while (!flush);
+    stream_search(&v, &f, &a, seg_y, seg_r0, seg_cnt, &sm, smem_ch, R, G * R);
+    seg_cnt = 0;
     }
 }
 
@@ -1360,18 +1742,22 @@ void launch_fleet_prepare(const FleetRaw& raw, FleetDerived* d_derived, int32_t*
     SMGX_CUDA(cudaGetLastError());
 }
 
-// 0 = split (default), 1 = fused; initialised from SMGX_EVENT_PATH, switchable at run time for A/B runs and tests
+// 0 = pair, 1 = warp-per-request family, 2 = one launch (hash stream + last-arriver search), 3 = persistent streaming kernel;
+// initialised from SMGX_EVENT_PATH (split | fused | hs | stream), switchable at run time for A/B runs and tests
 static std::atomic<int> g_event_path{-1};
-bool event_select_fused() {
+int event_path() {
     int v = g_event_path.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("SMGX_EVENT_PATH");
-        v = (e && std::string(e) == "fused") ? 1 : 0;   // default: the split pair
+        const std::string s = e ? e : "";
+        v = s == "fused" ? 1 : s == "stream" ? 3 : s == "hs" ? 2 : 0;
         g_event_path.store(v, std::memory_order_relaxed);
     }
-    return v == 1;
+    return v;
 }
+bool event_select_fused() { return event_path() == 1; }
 void set_event_select_fused(bool fused) { g_event_path.store(fused ? 1 : 0, std::memory_order_relaxed); }
+void set_event_path(int path) { g_event_path.store(path < 0 || path > 3 ? 3 : path, std::memory_order_relaxed); }
 static std::atomic<int> g_fused_minb{-1};
 void set_fused_minb(int minb) { g_fused_minb.store(minb == 3 ? 3 : 4, std::memory_order_relaxed); }
 
@@ -1548,12 +1934,50 @@ void launch_event_search(const EventIndexView& ix, const FleetView& fleet, const
     ++*launches;
 }
 
+// the one-launch path: ≤ 64 interned workers, counters and records present, phase C's shared-memory rows small enough to leave 4 CTAs per SM
+static bool launch_event_hs(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, uint32_t max_n, cudaStream_t stream) {
+    if (event_path() != 2 || ix.words != 1 || !a.group_count || !a.recs || !a.hashes || !a.block_size || a.ready) return false;
+    const size_t smem = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
+    if (smem > 40 * 1024 || (max_n + 255) / 256 > a.group_stride) return false;
+    constexpr int UNR = 2;
+    const uint64_t slots = (uint64_t)max_n * a.max_blocks;
+    const uint64_t gx = (slots + 256 * UNR - 1) / (256 * UNR);
+    if (gx == 0 || gx > 0x7FFFFFFFull) return false;
+    if (a.block_size == 16) event_hs_kernel<16, UNR><<<dim3((unsigned)gx, a.count), 256, smem, stream>>>(ix, fleet, a);
+    else event_hs_kernel<0, UNR><<<dim3((unsigned)gx, a.count), 256, smem, stream>>>(ix, fleet, a);
+    SMGX_CUDA(cudaGetLastError());
+    return true;
+}
+
+// the persistent streaming path: ≤ 64 interned workers, block size 16, ≤ 32 blocks per request (one request slot ≤ 2 KB of a 16 KB stage)
+static bool launch_event_stream(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream) {
+    if (event_path() != 3 || ix.words != 1 || !a.recs || !a.hashes || a.block_size != 16 || a.ready || a.max_blocks < 1 || a.max_blocks > 32) return false;
+    const uint32_t R = (uint32_t)kStConsumers / a.max_blocks;
+    uint64_t n_tiles = 0;
+    for (uint32_t j = 0; j < a.count; ++j) n_tiles += (a.b[j].n + R - 1) / R;
+    if (n_tiles == 0 || n_tiles > 0xFFFFFFFFull) return false;
+    const size_t smem = (size_t)kStStages * kStStageBytes + (size_t)a.max_blocks * 7 * 8 + 2 * kStStages * 8;
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        SMGX_CUDA(cudaFuncSetAttribute(event_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStStages * kStStageBytes + 32 * 7 * 8 + 2 * kStStages * 8)));
+        int occ = 0;
+        SMGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, event_stream_kernel, 256, kStStages * kStStageBytes + 32 * 7 * 8 + 2 * kStStages * 8));
+        per_sm = std::max(occ, 1);
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)per_sm * sm_count);
+    event_stream_kernel<<<grid, 256, smem, stream>>>(ix, fleet, a, (uint32_t)n_tiles);
+    SMGX_CUDA(cudaGetLastError());
+    return true;
+}
+
 void launch_event_select(const EventIndexView& ix, const FleetView& fleet, const MultiArgs& a, int sm_count, cudaStream_t stream, uint64_t* launches) {
     if (a.count == 0) return;
     uint32_t max_n = 0;
     for (uint32_t j = 0; j < a.count; ++j) max_n = std::max(max_n, a.b[j].n);
     if (max_n == 0) return;
     if (event_launch_is_split(a)) {
+        if (launch_event_stream(ix, fleet, a, sm_count, stream)) { ++*launches; return; }
+        if (launch_event_hs(ix, fleet, a, max_n, stream)) { ++*launches; return; }
         launch_event_hash(a, sm_count, stream, launches);
         launch_event_search(ix, fleet, a, sm_count, stream, launches);
         return;

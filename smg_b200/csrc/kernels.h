@@ -88,12 +88,20 @@ struct MultiArgs {
     uint32_t* slow_queue;          // event_simple_kernel → event_slow_kernel: [0] = count, [1 .. total] = request indices, [total + 1] = CTA exit counter (all zero between launches)
     uint64_t* fb_winsets;
     uint32_t* fb_scores;           // 0xFFFFFFFF = request longer than max_blocks
+    // one-launch path (event_hs_kernel): per (batch, group of 256 requests) arrival counters, zero between launches
+    uint32_t* group_count;         // device [kMaxMultiBatches][group_stride] (nullable: the pair runs)
+    uint32_t dbg;                  // SMGX_STREAM_DBG (diagnostics of event_stream_kernel): 1 = release a stage only after hashing it, 2 = __threadfence before the search
+    uint32_t group_stride;
     uint32_t total;                // sum of b[k].n  (b[k].hash_base = requests before batch k)
     uint32_t uniform_n;            // every batch has this many requests (0: look the batch up through hash_base)
 };
 // true: launch_event_select runs the one-kernel fused path (no hash scratch needed).  SMGX_EVENT_PATH=split selects the two-kernel path.
 bool event_select_fused();
 void set_event_select_fused(bool fused);
+// 0 = pair (hash stream + search kernel), 1 = the warp-per-request family (simple / tiled / fused), 2 = one launch: hash stream whose last CTA per
+// 256-request group runs the search (event_hs_kernel)
+int event_path();
+void set_event_path(int path);
 void set_fused_minb(int minb);
 void set_fused_prefetch(int pf);
 void set_fused_tile(int tile, long long min_total);

@@ -82,6 +82,8 @@ struct Lane {
     DevBuf d_fb;   // load-feedback scratch: per-request tied sets + scores
     DevBuf d_slowq;   // queue between event_simple_kernel and event_slow_kernel
     DevBuf d_recs;    // SearchRec per request: hash kernel → search kernel
+    DevBuf d_groups;  // event_hs_kernel's arrival counters, [kMaxMultiBatches][group_stride] (zeroed once; self-resetting)
+    uint32_t group_stride = 0;
     // concurrent split launch (hash on `stream`, search on `side`): device counters the hash CTAs count into + their host-side running totals
     cudaStream_t side = nullptr;
     cudaEvent_t pre = nullptr, side_done = nullptr;
@@ -147,7 +149,7 @@ public:
             cudaSetDevice(cfg.device_id);
             cudaDeviceSynchronize();
             for (auto& l : lanes) {
-                l.d_fb.release(); l.d_slowq.release(); l.d_recs.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
+                l.d_fb.release(); l.d_slowq.release(); l.d_recs.release(); l.d_groups.release(); l.d_tokens.release(); l.d_offsets.release(); l.d_out.release(); l.d_info.release(); l.d_hash.release();
                 l.d_text.release(); l.d_toff.release(); l.d_path.release(); l.d_path_len.release(); l.d_tenant.release();
                 l.d_path_tenant.release(); l.d_fill.release(); l.d_chunk_start.release(); l.d_cv.release(); l.d_hashes.release();
                 l.tok_scratch.flags.release(); l.tok_scratch.tmp_ids.release(); l.tok_scratch.tmp_rk.release(); l.tok_scratch.totals.release();
@@ -321,7 +323,8 @@ public:
         if (done_flag) {
             a.done_counter = d_done_counters.as<uint32_t>() + (done_seq++ % kDoneCounters);
         }
-        a.pf_slots = nullptr; a.pf_mask = 0; a.pf_jump = 0; a.recs = nullptr;
+        a.pf_slots = nullptr; a.pf_mask = 0; a.pf_jump = 0; a.recs = nullptr; a.group_count = nullptr; a.group_stride = 0;
+        { static const uint32_t dbg = [] { const char* e = getenv("SMGX_STREAM_DBG"); return e ? (uint32_t)atoi(e) : 0u; }(); a.dbg = dbg; }
         if (event_launch_is_split(a)) {
             if (&lane == &lanes[0])   // lane 0's scratch doubles as the ring of enqueue_split_pipelined: its readers run on lane 1
                 for (uint32_t i = 0; i < kPipeSlots; ++i) if (pipe_used[i]) SMGX_CUDA(cudaStreamWaitEvent(lane.stream, pipe_searched[i], 0));
@@ -330,6 +333,15 @@ public:
             lane.d_recs.reserve(std::max<uint64_t>(rows, 1) * sizeof(SearchRec));
             a.recs = lane.d_recs.as<SearchRec>();
             a.pf_slots = ixv.slots; a.pf_mask = ixv.mask; a.pf_jump = ixv.jump;
+            if (event_path() == 2 && ixv.words == 1) {   // arrival counters of event_hs_kernel
+                const uint32_t need = (max_n_of(descs, count) + 255) / 256;
+                if (need > lane.group_stride) {
+                    lane.group_stride = std::max<uint32_t>(need * 2, 64);
+                    lane.d_groups.reserve((size_t)kMaxMultiBatches * lane.group_stride * 4);
+                    SMGX_CUDA(cudaMemsetAsync(lane.d_groups.ptr, 0, (size_t)kMaxMultiBatches * lane.group_stride * 4, lane.stream));
+                }
+                a.group_count = lane.d_groups.as<uint32_t>(); a.group_stride = lane.group_stride;
+            }
         }
         a.err_flag = d_err.as<uint32_t>();
         a.ready = nullptr;
@@ -2765,7 +2777,7 @@ smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err) {
     });
 }
 void smgx_set_event_path(int fused, int min_blocks_per_sm) {
-    set_event_select_fused(fused != 0);
+    set_event_path(fused);
     if (min_blocks_per_sm) set_fused_minb(min_blocks_per_sm);
 }
 void smgx_set_fused_prefetch(int flavour) { set_fused_prefetch(flavour); }

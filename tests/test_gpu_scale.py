@@ -15,6 +15,8 @@ from smg_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
+PATHS = {"split": 0, "hs": 2, "stream": 3}     # smgx_set_event_path; everything else is a variant of path 1
+
 CFG = dict(cache_threshold=0.3, balance_abs_threshold=64, balance_rel_threshold=1.5, block_size=16)
 
 
@@ -23,7 +25,7 @@ def event_path():
     from smg_b200 import _lib
     L = _lib.load()
     def setter(fused, minb=0, pf=-1, tile=None, min_total=-1, simple=0, depth=0):
-        L.smgx_set_event_path(1 if fused else 0, minb)
+        L.smgx_set_event_path(int(fused), minb)      # 0 = pair, 1 (True) = warp-per-request family, 2 = hash stream + last-arriver search, 3 = persistent streaming kernel
         L.smgx_set_event_simple(simple)
         L.smgx_set_tile_depth(depth)
         if pf >= 0:
@@ -31,7 +33,7 @@ def event_path():
         if tile is not None:
             L.smgx_set_fused_tile(tile, min_total)
     yield setter
-    L.smgx_set_event_path(0, 4)   # the default: split pair (hash stream + balanced search)
+    L.smgx_set_event_path(0, 4)   # the default: the pair (hash stream + balanced search)
     L.smgx_set_fused_prefetch(1)
     L.smgx_set_fused_tile(16, -1)
     L.smgx_set_event_simple(5)
@@ -60,12 +62,12 @@ def _config2(n_seq, W, T, bs, B):
     return pol, ws, ix, op, seqs
 
 
-@pytest.mark.parametrize("variant", ["split", "simple", "tile16", "tile8", "tile32", "tile16-m3", "tile16-d4", "tile8-d8", "fused4", "fused3", "fused4-pf2", "fused4-pf0"])
+@pytest.mark.parametrize("variant", ["stream", "hs", "split", "simple", "tile16", "tile8", "tile32", "tile16-m3", "tile16-d4", "tile8-d8", "fused4", "fused3", "fused4-pf2", "fused4-pf0"])
 def test_config2_full_scale_multi_launch(variant, event_path):
     import bench
     from smg_b200 import _lib
     tile = int(variant[4:6].rstrip("-")) if variant.startswith("tile") else 0
-    event_path(variant != "split", 3 if variant.endswith("3") else 4, 2 if variant.endswith("pf2") else 0 if variant.endswith("pf0") else 1, tile=tile,
+    event_path(PATHS.get(variant, 1), 3 if variant.endswith("3") else 4, 2 if variant.endswith("pf2") else 0 if variant.endswith("pf0") else 1, tile=tile,
                simple=5 if variant == "simple" else 0, depth=4 if "-d4" in variant else 8 if "-d8" in variant else 0)
     n_seq, W, T, bs, B, NB = 31250, 64, 512, 16, 4096, 37
     pol, ws, ix, op, seqs = _config2(n_seq, W, T, bs, B)
@@ -96,7 +98,7 @@ def test_config2_full_scale_multi_launch(variant, event_path):
         assert np.array_equal(got, want), f"batch {r}: {(got != want).sum()} of {B} picks differ from the oracle"
         n_overlap += int((np.asarray(br) == 2).sum())
     assert n_overlap > 0.8 * NB * B        # ≈ 90 % of the mix has a stored prefix
-    if variant == "split":   # 150 batches in one call: five 32-batch chunks, the hash-scratch ring of the two-lane pipeline wraps around
+    if variant in PATHS:   # 150 batches in one call: five 32-batch chunks, the hash-scratch ring of the two-lane pipeline wraps around
         rep = [i % NB for i in range(150)]
         h.call("smgx_select_many_tokens_device", model, 150, (C.c_void_p * 150)(*[d_tok[i] for i in rep]), (C.c_void_p * 150)(*[d_off] * 150),
                (C.c_uint32 * 150)(*[B] * 150), T, (C.c_void_p * 150)(*[d_out[i] for i in rep]))
@@ -119,7 +121,7 @@ def test_config2_full_scale_multi_launch(variant, event_path):
 
 @pytest.mark.parametrize("case", [(1, 64, 512, 16, 64, 512), (3, 256, 1024, 16, 64, 256), (5, 64, 512, 64, 64, 256), (7, 100, 2048, 32, 32, 128),
                                   (8, 64, 8192, 16, 64, 48)])
-@pytest.mark.parametrize("variant", ["simple", "fused4", "fused3", "tile8", "tile16", "tile32", "tile16-d4"])
+@pytest.mark.parametrize("variant", ["split", "hs", "simple", "fused4", "fused3", "tile8", "tile16", "tile32", "tile16-d4"])
 def test_random_parity_other_variants(case, variant, event_path):
     """The randomized ragged parity cases of test_gpu_event_select.py (which run the default path: hash stream + balanced search kernel) on every
     other implementation of the event-driven pick."""
@@ -128,7 +130,9 @@ def test_random_parity_other_variants(case, variant, event_path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     test_random_select_parity = mod.test_random_select_parity
-    if variant.startswith("tile"):   # force the tiled kernel wherever the launch is eligible (≤ 32 blocks, one jump, ≤ 64 workers), however small
+    if variant in PATHS:
+        event_path(PATHS[variant])
+    elif variant.startswith("tile"):   # force the tiled kernel wherever the launch is eligible (≤ 32 blocks, one jump, ≤ 64 workers), however small
         event_path(True, 4, tile=int(variant[4:6].rstrip("-")), min_total=1, depth=4 if "-d4" in variant else 0)
     else:
         event_path(True, 3 if variant == "fused3" else 4, tile=0, simple=5 if variant == "simple" else 0)
@@ -172,8 +176,8 @@ def test_duplicate_urls_event_mode(seed, event_path):
             ix.apply_stored(int(w), blocks); oix.apply_stored(int(w), blocks)
     q = synth.gen_queries(seqs, B, seed, block=bs)
     tokens, offsets = synth.ragged(q)
-    for variant in ("split", "simple", "fused"):
-        event_path(variant != "split", simple=5 if variant == "simple" else 0, tile=0)
+    for variant in ("stream", "hs", "split", "simple", "fused"):
+        event_path(PATHS.get(variant, 1), simple=5 if variant == "simple" else 0, tile=0)
         for rnd in range(4):
             loads = rng.integers(0, 6, size=n)            # small range → many equal loads among duplicates
             healthy = (rng.random(n) > 0.2).astype(np.uint8)
