@@ -237,6 +237,17 @@ __device__ __forceinline__ uint64_t jump_search(const EventIndexView& v, const u
 // One THREAD per block of tokens (64 B at block_size 16: 4×LDG.128, consecutive threads → consecutive blocks, a warp
 // streams 2 KB).  Hashes land in a scratch laid out [request][max_blocks] that the search kernel reads back from L2.
 // HBM-bound by construction: 4·T bytes in, 8·P bytes out per request, ~110 integer instructions per 64 B.
+// tokens are read once: evict-first in L2 (L1 as usual — a thread's four 16 B loads share sectors), so that the stream does not push the
+// index slots the same kernel prefetches (evict-last) for the search out of L2 before the search gets to them.  ld.global.cs (evict-first
+// in L1 too) was measured: 0.44 for a lone 20-batch call but 0.59 instead of 0.70 in steady state — the second half of every sector came
+// from L2 again.
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
 template <int BS>
 __device__ __forceinline__ uint64_t hash_block(const uint32_t* __restrict__ p, uint32_t bs) {
     if (BS == 16) {
@@ -244,7 +255,7 @@ __device__ __forceinline__ uint64_t hash_block(const uint32_t* __restrict__ p, u
         if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
             const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { uint4 t = __ldg(q + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
+            for (int i = 0; i < 4; ++i) { uint4 t = ld_stream(q + i); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) w[i] = __ldg(p + i);
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(256, 8) hash_blocks_kernel(const __grid_consta
             // the search kernel probes positions 0 and min(jump, last) first: pull those 32 B slots into L2 now (fire and forget), so that
             // its dependent chain offsets → hashes → slots runs at L2 latency instead of paying a DRAM miss per probe
             if (a.pf_slots && (blk == 0 || blk == min(a.pf_jump, nb - 1)))
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(blk, h) & a.pf_mask)));
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(blk, h) & a.pf_mask)));
         }
     }
     if (a.ready) {   // concurrent split launch: this CTA's share of batch blockIdx.y is in memory
@@ -932,19 +943,192 @@ __device__ __forceinline__ void st_next(const MultiArgs& a, StPos& t, uint32_t R
     }
 }
 
-__device__ __forceinline__ void stream_search(const EventIndexView* v, const FleetView* f, const MultiArgs* a, uint32_t y, uint32_t r0, uint32_t cnt,
-                                              Search2Smem* sm, uint64_t* smem_ch, uint32_t R, uint32_t stride) {
-    if (a->dbg & 4) return;                                         // A/B: streaming only (no picks are written)
-    if (a->dbg & 2) __threadfence();
-    search2_sync<kStConsumers>();                                   // the consumers' rows and records are in L2
-    search2_body<false, true, kStConsumers>(*v, *f, *a, y, r0, cnt, *sm, smem_ch, R, stride);
-    search2_sync<kStConsumers>();
+// ---- the streaming kernel's own search: the same decisions as search2_body, organised around round trips -------------------------
+// Timed inside the kernel (SMGX_STREAM_DBG=64) search2_body cost a CTA of 140 requests 4-8 µs in phase A and 7-16 µs in phase B: not
+// arithmetic, but chains of dependent round trips — fleet tables → record → slots in A; and in B one round (row → 31 probes → scan →
+// record again) per PAIR of drains and warp, so 17 drains on 7 warps are two rounds.  Here
+//   * the fleet tables and the derived fleet state are in shared memory from the start of the kernel;
+//   * the consumers leave h0 / h1 / ntok of every hashed request in shared memory (no record in global memory at all);
+//   * phase A is one thread per request: two probes in flight, classification, ONE argmax for whatever was decided;
+//   * phase B issues every probe of up to 16 drains at once — (drain, position) pairs dealt over all 224 threads, results into a
+//     shared-memory matrix — and only then replays the reference's ordered scan, one warp per drain, from that matrix: one round trip
+//     for the whole CTA instead of one per pair;
+//   * phase C (Multi entries, more than one jump) is the generic warp-cooperative search, as before.
+constexpr int kStDrains = 16;
+struct StreamSmem {
+    int32_t slice[64];
+    uint64_t load[64], ts[64];
+    FleetDerived fd;
+    uint64_t elig;
+    uint64_t h0[kStConsumers], h1[kStConsumers];                  // of the requests hashed since the last search
+    uint32_t ntok[kStConsumers];
+    uint8_t qb[kStConsumers], qc[kStConsumers];
+    uint32_t nb, nc;
+    uint64_t dset[kStDrains][32];
+    uint8_t dkind[kStDrains][32];                                  // 0 = no entry, 1 = Single, 2 = Multi
+};
+
+__device__ __forceinline__ void stream_search(const EventIndexView& v, const MultiArgs& a, const uint32_t y, const uint32_t r0, const uint32_t cnt,
+                                              StreamSmem& sm, uint64_t* smem_ch) {
+    if (a.dbg & 4) return;                                         // A/B: streaming only (no picks are written)
+    constexpr int NT = kStConsumers;
+    constexpr uint32_t NW = NT / 32;
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const BatchDesc& b = a.b[y];
+    const bool cand_mode = b.cand != nullptr;
+    const uint32_t mb = a.max_blocks;
+    if (threadIdx.x == 0) { sm.nb = 0; sm.nc = 0; }
+    search2_sync<NT>();                                            // the consumers' h0 / h1 / ntok are in shared memory, their hash rows in L2
+    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+    const bool trace = (a.dbg & 64) && threadIdx.x == 0 && blockIdx.x % 59 == 0;
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
+    const uint64_t elig = sm.elig;
+    auto finish = [&](uint32_t t, uint64_t win, uint32_t score) {  // argmax + store for request t of the segment (any single thread)
+        int32_t out = sm.fd.min_load_idx;
+        uint32_t branch = SMGX_BR_EVENT_MIN_LOAD, matched = 0;
+        Cand c{false, 0, 0, -1};
+        if (win) {
+            while (win) { int id = __ffsll((long long)win) - 1; win &= win - 1; c.consider(sm.slice[id], sm.load[id], sm.ts[id]); }
+            out = c.sl; branch = SMGX_BR_EVENT_OVERLAP; matched = score;
+        }
+        if (cand_mode) {
+            smgx_shard_candidate sc;
+            sc.score = c.have ? matched : 0; sc.local_idx = c.have ? (uint32_t)c.sl : 0xFFFFFFFFu; sc.load = c.ld; sc.tree_size = c.ts;
+            b.cand[r0 + t] = sc;
+        } else write_pick(b, r0 + t, out, branch, matched, sm.ntok[t]);
+    };
+    auto row_of = [&](uint32_t t) { return a.hashes + ((uint64_t)b.hash_base + r0 + t) * mb; };
+    auto ld_hash = [&](const uint64_t* p) -> uint64_t { return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)); };
+
+    // ---- phase A ----
+    {
+        const uint32_t t = threadIdx.x;
+        enum { K_NONE, K_FIN, K_PICK };
+        int kind = K_NONE;
+        uint64_t win = 0;
+        uint32_t score = 0, branch = 0;
+        int32_t out = -1;
+        if (t < cnt) {
+            const uint32_t ntok = sm.ntok[t];
+            const uint32_t nb = ntok / 16;
+            if (!cand_mode && sm.fd.n_healthy == 0) { kind = K_PICK; out = -1; branch = SMGX_BR_NO_HEALTHY; }
+            else if (!cand_mode && sm.fd.imbalanced) { kind = K_PICK; out = sm.fd.min_load_idx; branch = SMGX_BR_IMBALANCED_MIN_LOAD; }
+            else if (nb > mb) { atomicExch(a.err_flag, 1u); if (cand_mode) kind = K_FIN; else { kind = K_PICK; out = -1; branch = 255; } }
+            else if (nb == 0 || v.n_workers == 0) kind = K_FIN;
+            else if (nb - 1 > v.jump) sm.qc[atomicAdd(&sm.nc, 1u)] = (uint8_t)t;
+            else {
+                const uint32_t last = nb - 1;
+                const uint64_t c0 = sm.h0[t], c1 = sm.h1[t];
+                const uint32_t i0 = slot_hash(0, c0) & v.mask, i1 = slot_hash(last, c1) & v.mask;
+                Slot s0 = load_slot(v.slots + i0), s1 = load_slot(v.slots + i1);          // both probes in flight together (L2-warm: prefetched at hash time)
+                if (!finish_probe(v, 0, c0, i0, s0)) kind = K_FIN;                         // nothing cached at position 0 (:676-683)
+                else if (s0.state != SLOT_SINGLE) sm.qc[atomicAdd(&sm.nc, 1u)] = (uint8_t)t;
+                else if (s0.payload == 0 || last == 0) { kind = K_FIN; win = s0.payload & elig; score = nb; }
+                else {
+                    const bool f1 = finish_probe(v, last, c1, i1, s1);
+                    if (f1 && s1.state != SLOT_SINGLE) sm.qc[atomicAdd(&sm.nc, 1u)] = (uint8_t)t;
+                    else if (f1 && __popcll(s1.payload) == __popcll(s0.payload)) { kind = K_FIN; win = s0.payload & elig; score = nb; }   // count-only jump test (:720)
+                    else sm.qb[atomicAdd(&sm.nb, 1u)] = (uint8_t)t;
+                }
+            }
+        }
+        if (kind == K_FIN) finish(t, win, score);
+        else if (kind == K_PICK) write_pick(b, r0 + t, out, branch, 0, sm.ntok[t]);
+    }
+    search2_sync<NT>();
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr1));
+
+    // ---- phase B ----
+    const uint32_t n_b = sm.nb;
+    for (uint32_t base = 0; base < n_b; base += kStDrains) {
+        const uint32_t chunk = min((uint32_t)kStDrains, n_b - base);
+        for (uint32_t idx = threadIdx.x; idx < chunk * 32; idx += NT) {          // every probe of the chunk's drains at once
+            const uint32_t d = idx >> 5, p = idx & 31;
+            const uint32_t t = sm.qb[base + d];
+            const uint32_t nb = sm.ntok[t] / 16;
+            uint8_t kind = 0;
+            uint64_t set = 0;
+            if (p < nb) {
+                const uint64_t h = ld_hash(row_of(t) + p);
+                const uint32_t i = slot_hash(p, h) & v.mask;
+                Slot sl = load_slot(v.slots + i);
+                if (finish_probe(v, p, h, i, sl)) { kind = sl.state == SLOT_SINGLE ? 1 : 2; set = sl.payload; }
+            }
+            sm.dset[d][p] = set; sm.dkind[d][p] = kind;
+        }
+        search2_sync<NT>();
+        for (uint32_t d = wic; d < chunk; d += NW) {                                // the ordered scan with its retain guard, from the matrix
+            const uint32_t t = sm.qb[base + d];
+            const uint32_t nb = sm.ntok[t] / 16;
+            const int last = (int)nb - 1;
+            const uint8_t kd = sm.dkind[d][lane];
+            const uint64_t pl = sm.dset[d][lane];
+            const bool found = kd != 0, single = kd == 1;
+            uint64_t active = shfl64(pl, 0);                                         // phase A saw a Single entry at position 0
+            const bool in_range = lane >= 1 && lane <= last;
+            const uint32_t pc = single ? (uint32_t)__popcll(pl) : 0;
+            uint64_t last_set = 0;
+            uint32_t last_score = 0;
+            bool bail = __shfl_sync(FULL, (int)kd, 0) != 1;
+            unsigned remaining = __ballot_sync(FULL, in_range);
+            while (!bail && remaining && active) {
+                const uint32_t nact = (uint32_t)__popcll(active);
+                const bool noop = single && pc >= nact;                              // retain guard (:611, :641)
+                const unsigned bm = __ballot_sync(FULL, in_range && !noop) & remaining;
+                if (!bm) break;
+                const int k = __ffs((int)bm) - 1;
+                if (!__shfl_sync(FULL, (int)found, k)) {                             // missing entry drains everything (:598-604)
+                    const uint64_t e = active & elig;
+                    if (e) { last_set = e; last_score = (uint32_t)k; }
+                    active = 0;
+                    break;
+                }
+                if (!__shfl_sync(FULL, (int)single, k)) { bail = true; break; }
+                const uint64_t ws = shfl64(pl, k);
+                if ((uint32_t)__popcll(ws) < nact) {
+                    const uint64_t e = active & ~ws & elig;
+                    if (e) { last_set = e; last_score = (uint32_t)k; }
+                    active &= ws;
+                }
+                remaining &= ~((2u << k) - 1u);
+            }
+            if (lane == 0) {
+                if (bail) sm.qc[atomicAdd(&sm.nc, 1u)] = (uint8_t)t;
+                else {
+                    uint64_t win = active & elig;
+                    uint32_t score = nb;
+                    if (!win) { win = last_set; score = last_score; }
+                    finish(t, win, score);
+                }
+            }
+        }
+        search2_sync<NT>();
+    }
+    if (trace) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr2));
+        printf("cta %u n %u: phase A %llu ns, phase B %llu ns (nb %u nc %u)\n", blockIdx.x, cnt, tr1 - tr0, tr2 - tr1, sm.nb, sm.nc);
+    }
+
+    // ---- phase C: generic search ----
+    const uint32_t n_c = sm.nc;
+    uint64_t* row = smem_ch + (size_t)wic * mb;
+    for (uint32_t q = wic; q < n_c; q += NW) {
+        const uint32_t t = sm.qc[q];
+        const uint32_t nb = sm.ntok[t] / 16;
+        const uint64_t* ch = row_of(t);
+        for (uint32_t i = lane; i < nb; i += 32) row[i] = ld_hash(ch + i);
+        __syncwarp();
+        const SlowResult sr = slow_search_inline<true>(v, row, (int)nb, lane, elig);
+        if (lane == 0) finish(t, sr.winset, sr.score);
+        __syncwarp();
+    }
+    search2_sync<NT>();
 }
 
 __global__ void __launch_bounds__(256, 4) event_stream_kernel(const __grid_constant__ EventIndexView v, FleetView f, const __grid_constant__ MultiArgs a,
                                                               const uint32_t n_tiles) {
     extern __shared__ __align__(128) uint8_t st_dyn[];            // [3 stages × 14 KB][phase C rows: 7 × max_blocks u64][full[3], empty[3] mbarriers]
-    __shared__ Search2Smem sm;
+    __shared__ StreamSmem sm;
     const uint32_t mb = a.max_blocks;
     const uint32_t R = (uint32_t)kStConsumers / mb;               // requests per tile (launcher: 1 ≤ max_blocks ≤ 32)
     uint64_t* smem_ch = reinterpret_cast<uint64_t*>(st_dyn + kStStages * kStStageBytes);
@@ -957,20 +1141,28 @@ __global__ void __launch_bounds__(256, 4) event_stream_kernel(const __grid_const
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(kStConsumers / 32));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.fd = *f.derived; sm.elig = f.elig[0];
+    }
+    if (threadIdx.x < 64) {
+        const bool ok = threadIdx.x < v.n_workers;
+        sm.slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
+        sm.load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
+        sm.ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
     }
     __syncthreads();
-    // this CTA's tiles: blockIdx.x, + grid, + 2·grid … — at any moment the resident CTAs sweep ONE contiguous window of the token buffers
-    // (as the stand-alone hash kernel's grid does), which is what keeps the DRAM pages open; a private contiguous run per CTA measured
-    // 3.4 TB/s with 25 MB of copies outstanding
-    const bool contiguous = (a.dbg & 8) != 0;                       // A/B: one contiguous run of tiles per CTA
-    const uint32_t G = contiguous ? 1u : gridDim.x;
+    // this CTA's tiles: one contiguous run of the flattened list (its requests are then contiguous inside every batch, which is what the
+    // search's request = first + thread mapping needs).  Dealing the tiles round-robin instead — every CTA sweeping the same moving window
+    // of the token buffers, like the stand-alone hash kernel's grid — was measured and streams no faster (46.8 vs 42.7 µs for 20 batches).
+    const uint32_t G = 1;
     const uint32_t q_ = n_tiles / gridDim.x, rem_ = n_tiles % gridDim.x;
-    const uint32_t g_n = contiguous ? q_ + (blockIdx.x < rem_ ? 1u : 0u) : (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    StPos pos = st_locate(a, contiguous ? blockIdx.x * q_ + min(blockIdx.x, rem_) : blockIdx.x, R);
+    const uint32_t g_n = q_ + (blockIdx.x < rem_ ? 1u : 0u);
+    StPos pos = st_locate(a, blockIdx.x * q_ + min(blockIdx.x, rem_), R);
 
     if (wic == kStConsumers / 32) {
         // ---- producer warp: lane j (+32, +64 …) owns request slot j of every tile; the offsets are fetched one tile ahead of the copies ----
         const int n_u = (int)((R + 31) / 32);
+        uint64_t pol_stream;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         uint32_t o_lo[7], o_hi[7];                                  // offsets[r], offsets[r + 1] of this lane's requests of the NEXT tile to issue
         auto fetch = [&](const StPos& t) {
             const BatchDesc& b = a.b[t.y];
@@ -1027,9 +1219,14 @@ __global__ void __launch_bounds__(256, 4) event_stream_kernel(const __grid_const
             for (int u = 0; u < 7; ++u) {
                 if (u >= n_u) break;
                 const uint32_t j = (uint32_t)lane + 32u * u;
-                if (bytes[u] && !(bytes[u] & 0x80000000u))
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(stage0 + s * kStStageBytes + j * mb * 64), "l"(src[u]), "r"(bytes[u]), "r"(full) : "memory");
+                if (bytes[u] && !(bytes[u] & 0x80000000u)) {
+                    if (a.dbg & 128)   // A/B: tokens without the evict-first hint
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(stage0 + s * kStStageBytes + j * mb * 64), "l"(src[u]), "r"(bytes[u]), "r"(full) : "memory");
+                    else               // tokens are read once: evict-first, so that the stream does not push the prefetched index slots out of L2
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                                     ::"r"(stage0 + s * kStStageBytes + j * mb * 64), "l"(src[u]), "r"(bytes[u]), "r"(full), "l"(pol_stream) : "memory");
+                }
             }
         }
         return;
@@ -1089,16 +1286,16 @@ __global__ void __launch_bounds__(256, 4) event_stream_kernel(const __grid_const
         if (my_j < cnt) {
             const uint32_t nb = cur_ntok / 16;
             const uint32_t r = r0 + my_j;
-            SearchRec* rec = a.recs + (uint64_t)b.hash_base + r;
-            if (my_blk == 0) rec->ntok = cur_ntok;
+            const uint32_t st = seg_cnt + my_j;                     // the request's place in the segment being collected
+            if (my_blk == 0) sm.ntok[st] = cur_ntok;
             if (nb <= mb && my_blk < nb) {
                 const uint64_t h = avalanche(acc + 64ULL * P64_1);
                 a.hashes[((uint64_t)b.hash_base + r) * mb + my_blk] = h;
                 const uint32_t jb = min(a.pf_jump, nb - 1);
-                if (my_blk == 0) rec->h0 = h;
-                if (my_blk == jb) rec->h1 = h;
+                if (my_blk == 0) sm.h0[st] = h;
+                if (my_blk == jb) sm.h1[st] = h;
                 if (a.pf_slots && (my_blk == 0 || my_blk == jb))
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(my_blk, h) & a.pf_mask)));
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(reinterpret_cast<const Slot*>(a.pf_slots) + (slot_hash(my_blk, h) & a.pf_mask)));
             }
         }
         if (a.dbg & 1) { __syncwarp(); if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * s) : "memory"); }
@@ -1108,7 +1305,7 @@ __global__ void __launch_bounds__(256, 4) event_stream_kernel(const __grid_const
         pos = nx;
         ++k;
     } while (!flush);
-    stream_search(&v, &f, &a, seg_y, seg_r0, seg_cnt, &sm, smem_ch, R, G * R);
+    stream_search(v, a, seg_y, seg_r0, seg_cnt, sm, smem_ch);
     seg_cnt = 0;
     }
 }
