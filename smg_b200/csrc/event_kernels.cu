@@ -267,6 +267,9 @@ __device__ __forceinline__ uint64_t hash_block(const uint32_t* __restrict__ p, u
 
 template <int BS>   // BS = 16: the common block size, fully unrolled; BS = 0: any run-time block size
 __global__ void __launch_bounds__(256, 8) hash_blocks_kernel(const __grid_constant__ MultiArgs a) {   // 8 CTAs = 2048 threads per SM: the 64 B per thread in flight are the bandwidth
+    // programmatic dependent launch: once every CTA of this grid has started, the search kernel's CTAs may take the slots the last wave frees
+    // (they load their fleet tables and then wait for this grid's completion in griddepcontrol.wait); a no-op without a dependent launch
+    asm volatile("griddepcontrol.launch_dependents;");
     const BatchDesc& b = a.b[blockIdx.y];
     const uint64_t total = (uint64_t)b.n * a.max_blocks;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
@@ -632,7 +635,7 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
     };
     auto ld_hash = [&](const uint64_t* p) -> uint64_t { return CG ? (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)) : *p; };
     unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
-    const bool trace = NT != 256 && (a.dbg & 64) && threadIdx.x == 0 && blockIdx.x % 59 == 0;
+    const bool trace = (a.dbg & 64) && threadIdx.x == 0 && (NT != 256 ? blockIdx.x % 59 == 0 : (blockIdx.x % 5 == 0 && blockIdx.y % 6 == 0));
     if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
     if (threadIdx.x < 64) {
         bool ok = threadIdx.x < v.n_workers;
@@ -640,6 +643,7 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
         s_load[threadIdx.x] = ok ? f.load_of_id[threadIdx.x] : 0;
         s_ts[threadIdx.x] = ok ? v.tree_sizes[threadIdx.x] : 0;
     }
+    if (WAIT) asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent of the hash kernel: its rows and records are complete and visible from here on
     if (threadIdx.x == 0) {
         s_nb = 0; s_nc = 0;
         if (WAIT && a.ready) {   // launched alongside the hash kernel: wait until every hash CTA of this batch has counted itself in
@@ -747,7 +751,7 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
             uint64_t win = active & elig;
             uint32_t score = it.nb;
             if (!win) { win = last_set; score = last_score; }
-            finish(it.r, win, score, ld_rec((uint64_t)b.hash_base + it.r).ntok);
+            finish(it.r, win, score, b.out_info ? ld_rec((uint64_t)b.hash_base + it.r).ntok : 0u);   // ntok only feeds out_info: no round trip without it
         }
     };
     constexpr uint32_t NW = NT / 32;
@@ -786,7 +790,7 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
         for (uint32_t i = lane; i < it.nb; i += 32) row[i] = ld_hash(ch + i);
         __syncwarp();
         const SlowResult sr = NT == 256 ? fused_slow_search<true>(&v, row, (int)it.nb, lane, elig) : slow_search_inline<true>(v, row, (int)it.nb, lane, elig);
-        if (lane == 0) finish(it.r, sr.winset, sr.score, ld_rec((uint64_t)b.hash_base + it.r).ntok);
+        if (lane == 0) finish(it.r, sr.winset, sr.score, b.out_info ? ld_rec((uint64_t)b.hash_base + it.r).ntok : 0u);
         __syncwarp();
     }
 }
@@ -2106,16 +2110,28 @@ void launch_event_search(const EventIndexView& ix, const FleetView& fleet, const
         const size_t smem2 = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8 * 8;
         if (old_search || smem2 > 160 * 1024 || !a.recs) event_search_thread_kernel<<<dim3((max_n + 127) / 128, a.count), 128, 0, stream>>>(ix, fleet, a);
         else {
-            // 128 requests per CTA while that still fits one wave of resident CTAs (fewer queued drains per warp), else 256
-            static const int rpc_env = [] { const char* e = getenv("SMGX_SEARCH_RPC"); return e ? atoi(e) : 0; }();   // 128 / 256 force, else by size
-            const bool small = rpc_env == 128 || (rpc_env != 256 && (uint64_t)((max_n + 127) / 128) * a.count <= (uint64_t)sm_count * 4);
-            if (small) {
-                if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                event_search2_kernel<128><<<dim3((max_n + 127) / 128, a.count), 256, smem2, stream>>>(ix, fleet, a);
-            } else {
-                if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(event_search2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                event_search2_kernel<256><<<dim3((max_n + 255) / 256, a.count), 256, smem2, stream>>>(ix, fleet, a);
-            }
+            // requests per CTA: the fewest of 128 / 160 / 192 / 256 whose grid is still ONE wave of resident CTAs (4 per SM) — fewer requests per
+            // CTA are fewer queued drains per warp, i.e. fewer rounds of dependent round trips in phase B; a second wave would cost more than that
+            static const int rpc_env = [] { const char* e = getenv("SMGX_SEARCH_RPC"); return e ? atoi(e) : 0; }();   // force one of them
+            int rpc = 256;
+            for (int c : {128, 160, 192, 256})
+                if ((uint64_t)((max_n + c - 1) / c) * a.count <= (uint64_t)sm_count * 4) { rpc = c; break; }
+            if (rpc_env == 128 || rpc_env == 160 || rpc_env == 192 || rpc_env == 256) rpc = rpc_env;
+            static const bool pdl = [] { const char* e = getenv("SMGX_PDL"); return !(e && e[0] == '0'); }();
+            auto go = [&](auto kernel, int c) {
+                if (smem2 > 32 * 1024) SMGX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((max_n + c - 1) / c, a.count); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem2; cfg.stream = stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;   // may start while the preceding kernel of the stream (the hash kernel) drains
+                cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+                SMGX_CUDA(cudaLaunchKernelEx(&cfg, kernel, ix, fleet, a));
+            };
+            if (rpc == 128) go(event_search2_kernel<128>, 128);
+            else if (rpc == 160) go(event_search2_kernel<160>, 160);
+            else if (rpc == 192) go(event_search2_kernel<192>, 192);
+            else go(event_search2_kernel<256>, 256);
         }
     } else {
         size_t per_warp = (size_t)std::max<uint32_t>(a.max_blocks, 1) * 8;

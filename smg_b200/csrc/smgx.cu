@@ -290,7 +290,7 @@ public:
         FleetView fv;
         sync_state(m, &ixv, &fv);
         uint32_t bs = block_size_for(m);
-        MultiArgs a;
+        MultiArgs a{};
         a.count = count;
         a.block_size = bs;
         a.max_blocks = bs ? std::max<uint32_t>(max_req_tokens / bs, 1) : 1;
@@ -405,7 +405,7 @@ public:
             const uint32_t cnt = std::min(per, count - j0);
             const uint32_t slot = (uint32_t)(pipe_seq++ % kPipeSlots);
             Lane& ls = lanes[1 + chunk_idx % 3];   // every chunk's search on its own lane: the searches are latency chains and must overlap each other too
-            MultiArgs a;
+            MultiArgs a{};
             a.count = cnt; a.block_size = bs; a.max_blocks = max_blocks;
             uint64_t rows = 0;
             bool uniform = true;
