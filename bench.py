@@ -558,12 +558,12 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (ncu_traffic() * B * args.steps / n_launch_groups) if ncu_traffic() else None,
                      "traffic_source": "per launch (pair) = DRAM bytes per decision of profiles/roofline_traffic.json (ncu --set full, dram__bytes_read + dram__bytes_write of the "
-                                       "hash + search pair on one 20-batch call, cold L2: 2926 B/decision vs 2192 B algorithmic) x the decisions of one launch of this run; a "
+                                       "hash + search pair on one 20-batch call, cold L2: 2750 B/decision vs 2192 B algorithmic) x the decisions of one launch of this run; a "
                                        "committed capture, not measured in this run",
                      "kernel": ("event_fused_kernel<W1,16> (hash → jump search → argmax in one persistent kernel)" if fused else
                                 "event_hs_kernel<16,2> (one launch: hash stream; the last CTA of every 256-request group runs search + argmax)" if path == "hs" else
                                 "event_stream_kernel (one launch of persistent CTAs: bulk-copy token ring → XXH3 → jump search → argmax)" if path != "split" else
-                                "hash_blocks_kernel<16> + event_search2_kernel<256> (whole step: both kernels' time, the path's algorithmic bytes)"),
+                                "hash_blocks_kernel<16> + event_search2_kernel (programmatic dependent launch; whole step: both kernels' time, the path's algorithmic bytes)"),
                      "batches_per_launch": args.steps / n_launch_groups,
                      "algorithmic_bytes_per_decision": alg_bytes, "mean_reference_probes": mean_pr,
                      "avg_launch_us": ms_med * 1e3 / n_launch_groups, "peak_source": peak_src},

@@ -634,9 +634,6 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
         return rr;
     };
     auto ld_hash = [&](const uint64_t* p) -> uint64_t { return CG ? (uint64_t)__ldcg(reinterpret_cast<const unsigned long long*>(p)) : *p; };
-    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
-    const bool trace = (a.dbg & 64) && threadIdx.x == 0 && (NT != 256 ? blockIdx.x % 59 == 0 : (blockIdx.x % 5 == 0 && blockIdx.y % 6 == 0));
-    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr0));
     if (threadIdx.x < 64) {
         bool ok = threadIdx.x < v.n_workers;
         s_slice[threadIdx.x] = ok ? f.slice_of_id[threadIdx.x] : -1;
@@ -678,7 +675,6 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
         } else write_pick(b, r, out, branch, matched, ntok);
     };
 
-    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr1));
     // ---- phase A ----
     // thread t ↔ request t of the range; a range may be a run of equally spaced tiles (event_stream_kernel): tile t / tile_req, slot t % tile_req
     const uint32_t r = r_begin + (threadIdx.x / tile_req) * tile_stride + threadIdx.x % tile_req;
@@ -710,8 +706,6 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
         }
     }
     search2_sync<NT>();
-    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr2));
-    if (NT != 256 && (a.dbg & 16)) return;                        // A/B timing: phase A only
 
     // ---- phase B: register drains, one warp per queued request, the queue striped over the warps; two requests per round so that the
     //      hash loads and the probes of the second overlap those of the first ----
@@ -775,11 +769,6 @@ __device__ __forceinline__ void search2_body(const EventIndexView& v, const Flee
         if (two) resolve(it1, f1, sl1);
     }
     search2_sync<NT>();
-    if (trace) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr3));
-        printf("cta %u n %u: tables %llu ns, phase A %llu ns, phase B %llu ns (nb %u nc %u) t0 %llu\n", blockIdx.x, r_count, tr1 - tr0, tr2 - tr1, tr3 - tr2, s_nb, s_nc, tr0);
-    }
-    if (NT != 256 && (a.dbg & 32)) return;                        // A/B timing: phases A + B
 
     // ---- phase C: generic search ----
     const uint32_t n_c = s_nc;
