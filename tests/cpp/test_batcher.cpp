@@ -96,6 +96,13 @@ int main(int argc, char** argv) {
                 std::vector<std::chrono::steady_clock::time_point> at(WIN);
                 for (int r0 = 0; r0 < R; r0 += WIN) {   // a router task pool: WIN requests outstanding per thread
                     const int cnt = std::min(WIN, R - r0);
+                    if (WIN == 1) {   // the blocking per-request call: route() may wait for a batch to come free, enqueue() (a caller that may hold tickets) must not
+                        const size_t id = (size_t)t * R + r0;
+                        at[0] = std::chrono::steady_clock::now();
+                        got[id] = batcher.route(reqs[id].data(), (uint32_t)reqs[id].size());
+                        lat_us[id] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - at[0]).count();
+                        continue;
+                    }
                     for (int k = 0; k < cnt; ++k) { const size_t id = (size_t)t * R + r0 + k; at[k] = std::chrono::steady_clock::now(); tk[k] = batcher.enqueue(reqs[id].data(), (uint32_t)reqs[id].size()); }
                     for (int k = 0; k < cnt; ++k) {
                         const size_t id = (size_t)t * R + r0 + k;
