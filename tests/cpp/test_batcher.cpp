@@ -78,10 +78,10 @@ int main(int argc, char** argv) {
     smgx::Batcher::Stats st;
     {
         smgx::Batcher batcher(policy.handle()->p, "m", bo);
-        {   // warm-up, untimed: four full batches in flight at once size the device staging of all four lanes
-            // (staged: four full batches in flight at once; mapped: the group commit ships small batches, so the warm-up redeems in windows —
-            //  a caller must not hold more tickets than the ring has batches)
-            const size_t win = mapped ? 512 : 4 * 4096;
+        {   // warm-up, untimed: sizes the device staging of the lanes.  Redeemed in windows: a caller must not hold more tickets than the ring
+            // has batches, and how many batches a window becomes depends on how fast the dispatcher turns them around (a 16 384-ticket window
+            // became more than max_ring = 64 batches once the kernels got faster)
+            const size_t win = mapped ? 512 : 2048;
             for (size_t k0 = 0; k0 < 4 * 4096; k0 += win) {
                 std::vector<smgx::Batcher::Ticket> warm;
                 for (size_t k = k0; k < k0 + win; ++k) warm.push_back(batcher.enqueue(reqs[k % N].data(), (uint32_t)reqs[k % N].size()));

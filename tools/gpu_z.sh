@@ -1,10 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hash_blocks|event_search2" -s 14 -c 2 -o gpurun_out/split_r02z -f python bench.py --steps 20 --warmup 5 --no-text-in --no-per-request --no-cpu-baseline > gpurun_out/z_under_ncu_full.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_z.csv python bench.py --steps 20 --warmup 5 --no-text-in --no-per-request --no-cpu-baseline > gpurun_out/z_under_ncu.log 2>&1
-grep -c "hash_blocks\|event_search2" gpurun_out/launches_z.csv
-# sanitizer over the kernels touched this round (pair with PDL, stream, hs)
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_event_select.py tests/test_gpu_feedback.py -q -m gpu -x -k "random or feedback" > gpurun_out/sanitizer_z_pair.log 2>&1; echo "memcheck pair rc=$?"; tail -3 gpurun_out/sanitizer_z_pair.log
-SMGX_EVENT_PATH=stream timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_event_select.py -q -m gpu -x -k "random" > gpurun_out/sanitizer_z_stream.log 2>&1; echo "memcheck stream rc=$?"; tail -3 gpurun_out/sanitizer_z_stream.log
-SMGX_EVENT_PATH=hs timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_event_select.py -q -m gpu -x -k "random" > gpurun_out/sanitizer_z_hs.log 2>&1; echo "memcheck hs rc=$?"; tail -3 gpurun_out/sanitizer_z_hs.log
-SMGX_EVENT_PATH=stream timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_event_select.py -q -m gpu -x -k "random" > gpurun_out/sanitizer_z_stream_race.log 2>&1; echo "racecheck stream rc=$?"; tail -3 gpurun_out/sanitizer_z_stream_race.log
+for i in 1 2 3 4 5 6 7 8; do timeout 100 tests/cpp/test_batcher 32 400 1 50 0 > gpurun_out/tb_$i.out 2> gpurun_out/tb_$i.err; echo "run $i rc=$?"; tail -c 300 gpurun_out/tb_$i.err; done
+timeout 100 tests/cpp/test_batcher 3 2000 700 200 0 > gpurun_out/tb_w.out 2> gpurun_out/tb_w.err; echo "wide rc=$?"; tail -c 300 gpurun_out/tb_w.err
+timeout 100 tests/cpp/test_batcher 8 1500 64 100 0 > gpurun_out/tb_p.out 2> gpurun_out/tb_p.err; echo "pool rc=$?"; tail -c 300 gpurun_out/tb_p.err
+timeout 300 python -m pytest tests/test_cpp_mirror.py -q -m gpu 2>&1 | tail -2
