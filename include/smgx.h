@@ -272,6 +272,20 @@ smgx_status smgx_hash_index_size(smgx_policy* p, const char* model_key, int text
 smgx_status smgx_hash_index_get(smgx_policy* p, const char* model_key, int text_kind, uint64_t path_hash, void* out, uint32_t cap_bytes,
                                 uint32_t* out_bytes, int* out_found, char** err);
 
+/* ---- adjacent policy on the same plumbing: power_of_two (model_gateway/src/policies/power_of_two.rs) ----
+ * PowerOfTwoPolicy::update_loads (:129-135): extends the cached url → load-response map; only effective_token_usage() (protocols worker.rs:1039-1044,
+ * the mean token_usage over the DP ranks, 0.0 for an empty list) is read by select_worker, so that is what crosses the boundary. */
+smgx_status smgx_power_of_two_update_loads(smgx_policy* p, const char* const* urls, const double* token_usage, uint32_t n, char** err);
+/* PowerOfTwoPolicy::select_worker (:36-120) for n requests against the worker slice and fleet snapshot of `model_key` (smgx_set_workers +
+ * smgx_set_fleet_state): None (-1) without a healthy worker, the only healthy worker if there is one, else two distinct candidates drawn
+ * as idx1 = uniform(0..h), idx2 = (idx1 + 1 + uniform(0..h-1)) % h over the healthy indices, compared by token usage when BOTH have a cached
+ * load response and by request count (Worker::load()) otherwise, first candidate on ties.  The reference draws from an unseedable
+ * thread-local generator; here request i of the call uses draws 2i and 2i + 1 of the counter-based stream `seed` selects (csrc/power_of_two.cu),
+ * so a caller advances `seed` per call.  out_pairs (2n, nullable): the two candidates, -1 -1 when none were drawn; out_metric (n, nullable):
+ * 0 = request_count, 1 = token_usage, 2 = no comparison.  The router's own follow-ups stay on the host: increment_processed() (:110) on the pick. */
+smgx_status smgx_power_of_two_select_batch(smgx_policy* p, const char* model_key, uint32_t n, uint64_t seed, int32_t* out_worker_idx, int32_t* out_pairs,
+                                           uint8_t* out_metric, char** err);
+
 /* ---- adjacent policy on the same plumbing: prefix_hash (model_gateway/src/policies/prefix_hash.rs) ---- */
 /* Which branch of PrefixHashPolicy::select_worker_impl produced the result (prefix_hash.rs:61-83), reported in
  * smgx_decision_info.branch by the smgx_prefix_hash_* calls (matched = 0, input = request length in tokens). */

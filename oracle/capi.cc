@@ -4,6 +4,7 @@
  * Flat C surface over the oracle classes so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * `--impl reference` legs can drive it through ctypes.  See the class headers for reference file:line.
  */
+#include "power_of_two.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -440,5 +441,28 @@ double orc_prefix_select_batch(size_t prefix_token_count, double load_factor, co
     }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+
+// power_of_two: one batch against one fleet snapshot (loads are NOT bumped between requests: a snapshot, like the product's batch call); request i
+// uses draws 2i and 2i + 1 of the stream `seed`.  cached_urls / cached_usage = the policy's cached_loads (update_loads), effective_token_usage per URL.
+void orc_p2c_select_batch(const char* const* urls, const uint64_t* loads, const uint8_t* healthy, const uint8_t* circuit, size_t n_workers,
+                          const char* const* cached_urls, const double* cached_usage, size_t n_cached, uint64_t seed, size_t n, int32_t* out_idx,
+                          int32_t* out_pairs, uint8_t* out_metric, uint64_t* out_processed) {
+    PowerOfTwoPolicy pol;
+    std::vector<std::pair<std::string, double>> cl;
+    for (size_t i = 0; i < n_cached; ++i) cl.emplace_back(cached_urls[i], cached_usage[i]);
+    pol.update_loads(cl);
+    std::vector<Worker> ws(n_workers);
+    for (size_t i = 0; i < n_workers; ++i) { ws[i].url = urls[i]; ws[i].load = loads[i]; ws[i].healthy = healthy[i] != 0; ws[i].circuit_ok = circuit ? circuit[i] != 0 : true; }
+    for (size_t i = 0; i < n; ++i) {
+        P2cStream rng(seed);
+        rng.k = 2 * (uint64_t)i;
+        const P2cDecision d = pol.select_worker(ws, rng);
+        out_idx[i] = (int32_t)d.idx;
+        if (out_pairs) { out_pairs[2 * i] = (int32_t)d.cand1; out_pairs[2 * i + 1] = (int32_t)d.cand2; }
+        if (out_metric) out_metric[i] = (uint8_t)d.metric;
+    }
+    if (out_processed) for (size_t i = 0; i < n_workers; ++i) out_processed[i] = ws[i].processed;
+}
+double orc_p2c_effective_token_usage(const double* token_usage, size_t n) { return PowerOfTwoPolicy::effective_token_usage(std::vector<double>(token_usage, token_usage + n)); }
 
 }  // extern "C"

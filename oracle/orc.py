@@ -106,6 +106,8 @@ def lib():
         sig("orc_prefix_hash", u64, vp, sz, sz)
         sig("orc_prefix_load_ok", C.c_int, C.c_double, u64, u64, sz)
         sig("orc_prefix_select_batch", C.c_double, sz, C.c_double, P(cp), vp, vp, sz, vp, vp, vp, sz, C.c_int, vp, vp)
+        sig("orc_p2c_select_batch", None, P(cp), vp, vp, vp, sz, P(cp), vp, sz, C.c_uint64, sz, vp, vp, vp, vp)
+        sig("orc_p2c_effective_token_usage", C.c_double, vp, sz)
         _lib = L
     return _lib
 
@@ -716,3 +718,42 @@ class PrefixHashPolicy:                      # model_gateway/src/policies/prefix
         t = _u32(tokens if tokens is not None else [])
         idx, br, _ = self.select_batch(urls, loads, healthy, ring, t, np.array([0, t.size], np.uint64), has_tokens=tokens is not None)
         return (None if idx[0] < 0 else int(idx[0])), PREFIX_BRANCHES[int(br[0])]
+
+
+class PowerOfTwoPolicy:                     # model_gateway/src/policies/power_of_two.rs
+    """select over an explicit draw stream (oracle/power_of_two.h): request i of a batch uses draws 2i and 2i + 1 of `seed`."""
+
+    def __init__(self):
+        self.cached = {}                     # url → effective_token_usage (update_loads, :129-135)
+
+    def name(self):
+        return "power_of_two"
+
+    @staticmethod
+    def effective_token_usage(token_usage_per_dp_rank) -> float:   # protocols worker.rs:1039-1044
+        a = np.ascontiguousarray(np.asarray(token_usage_per_dp_rank, np.float64))
+        return float(lib().orc_p2c_effective_token_usage(_ptr(a) if a.size else None, a.size))
+
+    def update_loads(self, loads: dict):
+        self.cached.update({k: float(v) for k, v in loads.items()})
+
+    def select_batch(self, urls, loads, healthy, circuit, n, seed):
+        """→ (idx int32[n], pairs int32[n, 2], metric uint8[n], processed uint64[W]) against ONE fleet snapshot."""
+        enc = [u.encode() for u in urls]
+        arr = (C.c_char_p * max(len(enc), 1))(*enc)
+        cu = [k.encode() for k in self.cached]
+        carr = (C.c_char_p * max(len(cu), 1))(*cu)
+        cv = np.ascontiguousarray(np.asarray(list(self.cached.values()) or [0.0], np.float64))
+        ld, hl = _u64(loads), np.ascontiguousarray(np.asarray(healthy, np.uint8))
+        ck = np.ascontiguousarray(np.asarray(circuit if circuit is not None else [1] * len(enc), np.uint8))
+        idx = np.full(max(n, 1), -1, np.int32)
+        pairs = np.full((max(n, 1), 2), -1, np.int32)
+        metric = np.zeros(max(n, 1), np.uint8)
+        proc = np.zeros(max(len(enc), 1), np.uint64)
+        lib().orc_p2c_select_batch(arr, _ptr(ld), _ptr(hl), _ptr(ck), len(enc), carr, _ptr(cv), len(cu), int(seed) & (2**64 - 1), n, _ptr(idx), _ptr(pairs),
+                                   _ptr(metric), _ptr(proc))
+        return idx[:n], pairs[:n], metric[:n], proc[:len(enc)]
+
+    def select_worker(self, urls, loads, healthy, circuit=None, seed=0):
+        idx, pairs, metric, _ = self.select_batch(urls, loads, healthy, circuit, 1, seed)
+        return None if idx[0] < 0 else int(idx[0])

@@ -24,6 +24,7 @@
 #include "string_tree.h"
 #include "blake3.h"
 #include "prefix_hash.h"
+#include "power_of_two.h"
 #include <cstdio>
 #include <cctype>
 #include <sched.h>
@@ -767,6 +768,8 @@ public:
     uint64_t prefix_token_count = 256;   // PrefixHashConfig::default() (prefix_hash.rs:52-58)
     double prefix_load_factor = 1.25;
     PinBuf pf_stage, pf_out;             // pinned staging of the host-buffer prefix_hash call
+    // power_of_two policy (policies/power_of_two.rs:22): cached_loads, reduced to what select_worker reads — effective_token_usage() per URL
+    std::unordered_map<std::string, double> p2c_usage;
     DevBuf pf_hash_buf[2];               // prefix hashes between the hash and pick kernels of the device-resident path
     cudaEvent_t pf_hash_ev[2] = {nullptr, nullptr}, pf_pick_ev[2] = {nullptr, nullptr};
     bool pf_pick_pending[2] = {false, false};
@@ -2776,6 +2779,60 @@ smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err) {
         return SMGX_SUCCESS;
     });
 }
+// ---- adjacent policy: power_of_two (model_gateway/src/policies/power_of_two.rs) ----
+smgx_status smgx_power_of_two_update_loads(smgx_policy* p, const char* const* urls, const double* token_usage, uint32_t n, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || (urls && token_usage), "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        for (uint32_t i = 0; i < n; ++i) { SMGX_REQUIRE(urls[i], "Invalid arguments: null pointer"); p->impl.p2c_usage[urls[i]] = token_usage[i]; }   // HashMap::extend (:130-134)
+        return SMGX_SUCCESS;
+    });
+}
+smgx_status smgx_power_of_two_select_batch(smgx_policy* p, const char* model_key, uint32_t n, uint64_t seed, int32_t* out_worker_idx, int32_t* out_pairs,
+                                           uint8_t* out_metric, char** err) {
+    return guard(err, [&]() {
+        NONNULL(p);
+        SMGX_REQUIRE(n == 0 || out_worker_idx, "Invalid arguments: null pointer");
+        std::lock_guard<std::mutex> g(p->impl.mu);
+        Policy& P = p->impl;
+        P.use_device();
+        ModelState& m = P.model(model_key, false);
+        if (n == 0) return SMGX_SUCCESS;
+        const uint32_t ns = (uint32_t)m.urls.size();
+        SMGX_REQUIRE(m.loads.size() == ns && m.flags.size() == ns, "fleet state not set for this model (smgx_set_fleet_state)");
+        std::vector<int32_t> healthy;
+        std::vector<double> usage(std::max<uint32_t>(ns, 1), std::numeric_limits<double>::quiet_NaN());
+        for (uint32_t i = 0; i < ns; ++i) {
+            if ((m.flags[i] & 3) == 3) healthy.push_back((int32_t)i);   // is_healthy() && circuit_breaker_can_execute() (policies/mod.rs:137-144)
+            auto it = P.p2c_usage.find(m.urls[i]);
+            if (it != P.p2c_usage.end()) usage[i] = it->second;
+        }
+        Lane& lane = P.lanes[0];
+        const size_t usage_bytes = usage.size() * 8, healthy_bytes = (std::max<size_t>(healthy.size(), 1) * 4 + 7) & ~(size_t)7, loads_bytes = (size_t)std::max<uint32_t>(ns, 1) * 8;
+        P.scratch.reserve(usage_bytes + loads_bytes + healthy_bytes);
+        P.scratch2.reserve((size_t)n * (4 + 8 + 1) + 16);
+        double* d_usage = P.scratch.as<double>();
+        uint64_t* d_loads = reinterpret_cast<uint64_t*>(d_usage + usage.size());
+        int32_t* d_healthy = reinterpret_cast<int32_t*>(d_loads + std::max<uint32_t>(ns, 1));
+        SMGX_CUDA(cudaMemcpyAsync(d_usage, usage.data(), usage_bytes, cudaMemcpyHostToDevice, lane.stream));
+        if (ns) SMGX_CUDA(cudaMemcpyAsync(d_loads, m.loads.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, lane.stream));
+        if (!healthy.empty()) SMGX_CUDA(cudaMemcpyAsync(d_healthy, healthy.data(), healthy.size() * 4, cudaMemcpyHostToDevice, lane.stream));
+        P2cArgs a;
+        a.healthy = d_healthy; a.n_healthy = (uint32_t)healthy.size(); a.loads = d_loads; a.usage = d_usage; a.seed = seed; a.n = n;
+        a.out_pair = reinterpret_cast<int32_t*>(P.scratch2.ptr);
+        a.out_idx = a.out_pair + 2 * (size_t)n;
+        a.out_metric = reinterpret_cast<uint8_t*>(a.out_idx + n);
+        launch_power_of_two(a, lane.stream);
+        ++P.launches;
+        SMGX_CUDA(cudaMemcpyAsync(out_worker_idx, a.out_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, lane.stream));
+        if (out_pairs) SMGX_CUDA(cudaMemcpyAsync(out_pairs, a.out_pair, (size_t)n * 8, cudaMemcpyDeviceToHost, lane.stream));
+        if (out_metric) SMGX_CUDA(cudaMemcpyAsync(out_metric, a.out_metric, n, cudaMemcpyDeviceToHost, lane.stream));
+        SMGX_CUDA(cudaStreamSynchronize(lane.stream));
+        return SMGX_SUCCESS;
+    });
+}
+
 void smgx_set_event_path(int fused, int min_blocks_per_sm) {
     set_event_path(fused);
     if (min_blocks_per_sm) set_fused_minb(min_blocks_per_sm);

@@ -53,6 +53,8 @@ class BasicWorker:
     def load(self): return self._load
     def is_healthy(self): return self._healthy
     def circuit_breaker_can_execute(self): return self._circuit_ok
+    def increment_processed(self): self._processed = getattr(self, "_processed", 0) + 1
+    def processed(self): return getattr(self, "_processed", 0)
     def processed(self): return self._processed
     def increment_load(self): self._load += 1
     def decrement_load(self): self._load = max(0, self._load - 1)
@@ -878,6 +880,78 @@ def _tok_ptr(tokens):
     return _p(tokens) if tokens.size else C.cast(C.create_string_buffer(4), C.c_void_p)
 
 
+class PowerOfTwoPolicy:
+    """policies::PowerOfTwoPolicy (power_of_two.rs:18-135) on the GPU: two random healthy candidates per request, the less loaded one wins
+    (token usage when both have a cached load response, request counts otherwise).  The reference draws from a thread-local generator;
+    here every call consumes one value of a per-policy seed sequence and request i of the call uses draws 2i, 2i + 1 of that stream."""
+
+    def __init__(self, device_id: int = 0, max_batch: int = 0, seed: int = 0x5EED):
+        self._h = _Handle(CacheAwareConfig(eviction_interval_secs=0), device_id, max_batch)
+        self._slices = {}
+        self._seed = int(seed) & (2**64 - 1)
+        self._calls = 0
+
+    def name(self) -> str:  # :122-124
+        return "power_of_two"
+
+    def needs_request_text(self) -> bool:  # trait default (policies/mod.rs:77-79)
+        return False
+
+    def update_loads(self, loads: dict):
+        """update_loads (:129-135): url → WorkerLoadResponse; a value may be the response's per-DP-rank token_usage list (→ its mean,
+        effective_token_usage, protocols worker.rs:1039-1044, 0.0 when empty) or that number itself."""
+        if not loads:
+            return
+        urls = [u.encode() for u in loads]
+        vals = []
+        for v in loads.values():
+            if isinstance(v, (list, tuple, np.ndarray)):
+                vals.append(float(np.sum(np.asarray(v, np.float64)) / len(v)) if len(v) else 0.0)
+            else:
+                vals.append(float(v))
+        arr = (C.c_char_p * len(urls))(*urls)
+        usage = np.ascontiguousarray(np.asarray(vals, np.float64))
+        self._h.call("smgx_power_of_two_update_loads", arr, _p(usage), len(urls))
+
+    def _push_fleet(self, workers) -> bytes:
+        model = normalize_model_key(workers[0].model_id() if workers else "").encode()
+        urls = tuple(w.url() for w in workers)
+        if self._slices.get(model) != urls:
+            enc = [u.encode() for u in urls]
+            arr = (C.c_char_p * max(len(enc), 1))(*enc)
+            self._h.call("smgx_set_workers", model, arr, len(enc))
+            self._slices[model] = urls
+        loads = _u64([w.load() for w in workers])
+        healthy = np.ascontiguousarray(np.asarray([1 if w.is_healthy() else 0 for w in workers] or [0], dtype=np.uint8))
+        circuit = np.ascontiguousarray(np.asarray([1 if w.circuit_breaker_can_execute() else 0 for w in workers] or [0], dtype=np.uint8))
+        self._h.call("smgx_set_fleet_state", model, _p(loads) if len(workers) else None, _p(healthy), _p(circuit), len(workers))
+        return model
+
+    def next_seed(self) -> int:
+        self._calls += 1
+        return (self._seed + 0xD1B54A32D192ED03 * self._calls) & (2**64 - 1)
+
+    def select_worker_batch(self, workers, n: int, seed: Optional[int] = None, with_details: bool = False):
+        """n requests against one fleet snapshot → idx int32[n] (-1 = None) [, pairs int32[n, 2], metric uint8[n]]."""
+        model = self._push_fleet(workers)
+        seed = self.next_seed() if seed is None else int(seed) & (2**64 - 1)
+        out = np.full(max(n, 1), -1, np.int32)
+        pairs = np.full((max(n, 1), 2), -1, np.int32)
+        metric = np.zeros(max(n, 1), np.uint8)
+        self._h.call("smgx_power_of_two_select_batch", model, n, seed, _p(out), _p(pairs) if with_details else None, _p(metric) if with_details else None)
+        for i in out[:n]:
+            if i >= 0 and len(workers) > 1 and hasattr(workers[int(i)], "increment_processed"):
+                workers[int(i)].increment_processed()        # :110 (not on the single-healthy-worker early return, :44-46)
+        return (out[:n], pairs[:n], metric[:n]) if with_details else out[:n]
+
+    def select_worker(self, workers, info=None) -> Optional[int]:
+        """LoadBalancingPolicy::select_worker (:36-120)."""
+        if not workers:
+            return None
+        idx = self.select_worker_batch(workers, 1)
+        return None if idx[0] < 0 else int(idx[0])
+
+
 class PolicyFactory:
     """policies::PolicyFactory for the one policy this library replaces (factory.rs:17-93)."""
 
@@ -887,6 +961,8 @@ class PolicyFactory:
             return CacheAwarePolicy(CacheAwareConfig(), **kw)
         if name.lower() in ("prefix_hash", "prefixhash"):  # factory.rs:90
             return PrefixHashPolicy.with_defaults(**kw)
+        if name.lower() in ("power_of_two", "poweroftwo"):  # factory.rs:83
+            return PowerOfTwoPolicy(**kw)
         return None
 
     @staticmethod
