@@ -435,4 +435,57 @@ private:
     std::map<std::string, std::vector<std::string>> slices_;
 };
 
+class PowerOfTwoPolicy : public LoadBalancingPolicy {   // power_of_two.rs:18-135
+public:
+    explicit PowerOfTwoPolicy(int device_id = 0, uint32_t max_batch = 0, uint64_t seed = 0x5EED) : seed_(seed) {
+        smgx_cache_aware_config c;
+        smgx_default_config(&c);
+        c.eviction_interval_secs = 0; c.device_id = device_id; c.max_batch = max_batch;
+        h_ = std::make_shared<detail::Handle>(c);
+    }
+    const char* name() const override { return "power_of_two"; }             // :122-124
+    // update_loads (:129-135): url → WorkerLoadResponse::effective_token_usage() (the mean token_usage over the DP ranks; 0.0 for none)
+    void update_loads(const std::map<std::string, double>& token_usage) {
+        if (token_usage.empty()) return;
+        std::vector<const char*> urls;
+        std::vector<double> v;
+        for (auto& kv : token_usage) { urls.push_back(kv.first.c_str()); v.push_back(kv.second); }
+        char* err = nullptr;
+        detail::check(smgx_power_of_two_update_loads(h_->p, urls.data(), v.data(), (uint32_t)urls.size(), &err), err);
+    }
+    // n requests against one snapshot of the slice; every call consumes one value of the policy's seed sequence
+    std::vector<int32_t> select_worker_batch(const Workers& workers, uint32_t n) {
+        const std::string model = normalize_model_key(workers.empty() ? "" : workers[0]->model_id());
+        char* err = nullptr;
+        std::vector<std::string> urls;
+        for (auto& w : workers) urls.push_back(w->url());
+        auto it = slices_.find(model);
+        if (it == slices_.end() || it->second != urls) {
+            std::vector<const char*> c;
+            for (auto& u : urls) c.push_back(u.c_str());
+            detail::check(smgx_set_workers(h_->p, model.c_str(), c.data(), (uint32_t)c.size(), &err), err);
+            slices_[model] = urls;
+        }
+        std::vector<uint64_t> loads;
+        std::vector<uint8_t> healthy, circuit;
+        for (auto& w : workers) { loads.push_back(w->load()); healthy.push_back(w->is_healthy()); circuit.push_back(w->circuit_breaker_can_execute()); }
+        detail::check(smgx_set_fleet_state(h_->p, model.c_str(), loads.data(), healthy.data(), circuit.data(), (uint32_t)workers.size(), &err), err);
+        std::vector<int32_t> idx(n, -1);
+        std::vector<int32_t> pairs(2 * (size_t)n, -1);
+        ++calls_;
+        detail::check(smgx_power_of_two_select_batch(h_->p, model.c_str(), n, seed_ + 0xD1B54A32D192ED03ULL * calls_, idx.data(), pairs.data(), nullptr, &err), err);
+        for (uint32_t i = 0; i < n; ++i) if (idx[i] >= 0 && pairs[2 * (size_t)i] >= 0) workers[(size_t)idx[i]]->increment_processed();   // :110 (not on the single-worker return)
+        return idx;
+    }
+    std::optional<size_t> select_worker(const Workers& workers, const SelectWorkerInfo&) override {   // :36-120
+        if (workers.empty()) return std::nullopt;
+        const int32_t i = select_worker_batch(workers, 1)[0];
+        return i < 0 ? std::nullopt : std::optional<size_t>((size_t)i);
+    }
+private:
+    std::shared_ptr<detail::Handle> h_;
+    std::map<std::string, std::vector<std::string>> slices_;
+    uint64_t seed_, calls_ = 0;
+};
+
 }  // namespace smgx

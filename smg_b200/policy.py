@@ -938,9 +938,9 @@ class PowerOfTwoPolicy:
         out = np.full(max(n, 1), -1, np.int32)
         pairs = np.full((max(n, 1), 2), -1, np.int32)
         metric = np.zeros(max(n, 1), np.uint8)
-        self._h.call("smgx_power_of_two_select_batch", model, n, seed, _p(out), _p(pairs) if with_details else None, _p(metric) if with_details else None)
-        for i in out[:n]:
-            if i >= 0 and len(workers) > 1 and hasattr(workers[int(i)], "increment_processed"):
+        self._h.call("smgx_power_of_two_select_batch", model, n, seed, _p(out), _p(pairs), _p(metric) if with_details else None)
+        for i, pr in zip(out[:n], pairs[:n]):
+            if i >= 0 and pr[0] >= 0 and hasattr(workers[int(i)], "increment_processed"):
                 workers[int(i)].increment_processed()        # :110 (not on the single-healthy-worker early return, :44-46)
         return (out[:n], pairs[:n], metric[:n]) if with_details else out[:n]
 
