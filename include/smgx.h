@@ -449,13 +449,13 @@ smgx_status smgx_timer_start_all_gated(smgx_policy* p, uint32_t hold_us, char** 
 smgx_status smgx_timer_start_gated(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err);
 smgx_status smgx_stream_hold(smgx_policy* p, uint32_t lane, uint32_t hold_us, char** err);       /* only the hold kernel */   /* one lane; stop with smgx_timer_stop_ms(lane) */
 smgx_status smgx_timer_stop_all_ms(smgx_policy* p, float* out_ms, char** err);
-/* Process-wide switch between the implementations of the event-driven pick (A/B measurements, tests): path 3 (default) = ONE launch of
- * persistent CTAs, each streaming its run of requests through a shared-memory ring (bulk async copies), hashing it and searching what it
- * hashed (event_stream_kernel; block size 16, ≤ 32 blocks per request, ≤ 64 interned workers — anything else runs the pair); 0 = hash kernel +
- * search kernel pair; 1 = the warp-per-request family (simple / tiled / persistent fused kernels); 2 = hash stream whose last CTA per
- * 256-request group runs the search (event_hs_kernel).  Mapped submissions and load-feedback batches always run the persistent fused kernel.
- * min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant of the fused kernel.  Environment: SMGX_EVENT_PATH=stream|hs|split|fused,
- * SMGX_FUSED_MINB=3|4. */
+/* Process-wide switch between the implementations of the event-driven pick (A/B measurements, tests): path 0 (default) = hash kernel + search
+ * kernel pair, the search launched as a programmatic dependent of the hash kernel; 1 = the warp-per-request family (simple / tiled / persistent
+ * fused kernels); 2 = hash stream whose last CTA per 256-request group runs the search (event_hs_kernel); 3 = ONE launch of persistent CTAs, each
+ * streaming its run of requests through a shared-memory ring (bulk async copies), hashing it and searching what it hashed (event_stream_kernel;
+ * block size 16, ≤ 32 blocks per request, ≤ 64 interned workers — anything else runs the pair).  Mapped submissions and load-feedback batches always
+ * run the persistent fused kernel.  min_blocks_per_sm: 0 = keep, 3 or 4 = occupancy variant of the fused kernel.
+ * Environment: SMGX_EVENT_PATH=split|fused|hs|stream, SMGX_FUSED_MINB=3|4, SMGX_PDL=0 (no dependent launch), SMGX_SEARCH_RPC=128|160|192|256. */
 void smgx_set_event_path(int path, int min_blocks_per_sm);
 /* L2 prefetch flavour of the fused kernel: 0 none, 1 one bulk prefetch per request (default), 2 one prefetch per lane (SMGX_FUSED_PF). */
 void smgx_set_fused_prefetch(int flavour);

@@ -1947,7 +1947,7 @@ int event_path() {
 }
 bool event_select_fused() { return event_path() == 1; }
 void set_event_select_fused(bool fused) { g_event_path.store(fused ? 1 : 0, std::memory_order_relaxed); }
-void set_event_path(int path) { g_event_path.store(path < 0 || path > 3 ? 3 : path, std::memory_order_relaxed); }
+void set_event_path(int path) { g_event_path.store(path < 0 || path > 3 ? 0 : path, std::memory_order_relaxed); }
 static std::atomic<int> g_fused_minb{-1};
 void set_fused_minb(int minb) { g_fused_minb.store(minb == 3 ? 3 : 4, std::memory_order_relaxed); }
 
