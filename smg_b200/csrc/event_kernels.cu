@@ -10,10 +10,26 @@
 //        fleet_prepare: healthy filter, min/max load, f32 imbalance gate, first-min-load
 //          ← select_worker prologue   cache_aware.rs:651-670, policies/mod.rs:137-144
 //
-// Mapping: one warp per request.  Lanes hash blocks lane, lane+32, … (64 B each, 4×LDG.128) into a per-warp
-// shared-memory array; index probes are 32-byte slot loads (one sector); worker sets are bitsets so set
-// algebra is popc/and/andnot — replicated in every lane when the fleet has ≤ 64 interned workers (W1), otherwise
-// one u64 word per lane (≤ 2048 workers) reduced with warp collectives.  No tensor-core work exists on this path.
+// What runs by default (launch_event_select, bottom of the file): the PAIR — hash_blocks_kernel (one thread per 64 B block, a pure HBM
+// stream; writes hash rows + one record per request, prefetches the first two index slots evict-last while the tokens are loaded
+// evict-first) followed by event_search2_kernel as a programmatic dependent launch (≤ 64 interned workers; one thread per request, then
+// balanced drains) or event_search_warp_kernel (wider fleets: one warp per request, one u64 set word per lane).  Mapped submissions and
+// load-feedback batches run event_fused_kernel (+ feedback_resolve_kernel).
+//
+// Contents, in file order:
+//   shared device code     slot probes, worker-set algebra, scan_drain / jump_search (generic search), hash_block
+//   hash_blocks_kernel     the hash stream
+//   event_search_thread_kernel, event_search_warp_kernel, search2_body / event_search2_kernel
+//   measured alternatives  (SMGX_EVENT_PATH, profiles/r02_event.md — every one parity-green, none faster than the pair)
+//       event_hs_kernel        hash stream whose last CTA per 256-request group searches
+//       event_stream_kernel    persistent, warp-specialised, fed by bulk async copies (+ stream_search)
+//       event_tile_kernel      one warp per 8 / 16 / 32 requests
+//       event_simple_kernel    one warp per request in registers, event_slow_kernel for rare shapes
+//       event_fused_kernel     persistent warp per request (also the mapped / feedback path)
+//   small kernels          find_matches, content_hashes, fill, fleet_prepare
+//   launchers              path selection (event_path), launch_event_hash / _search / _select
+//   feedback_resolve_kernel, shard_push / shard_reduce kernels (sharded fleets), hold_kernel (gated timing)
+// No tensor-core work exists on this path: it is integer hashing and 32 B probes, HBM-bound.
 #include <cuda_runtime.h>
 
 #include <algorithm>
